@@ -1,0 +1,248 @@
+/*
+ * kai_engine.h — C ABI of libkaigpu.so, the B200-native scheduling-cycle engine.
+ *
+ * This is the drop-in boundary for ONE hot path of NVIDIA/KAI-Scheduler: the
+ * per-Session scheduling cycle in pkg/scheduler.  A Go `framework.Action`
+ * (reference: pkg/scheduler/framework/interface.go:41-47, registered through
+ * framework.RegisterAction, pkg/scheduler/framework/plugins.go:47-62) packs
+ * `ssn.ClusterInfo` into the structure-of-arrays snapshot below, calls
+ * kai_engine_run(), and replays the returned bindings through
+ * Statement.Allocate/Pipeline/Evict + Commit (INTEGRATION.md shows the cgo stub).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns 0 (KAI_OK)
+ *     or a negative kai_status; kai_last_error() gives a message.
+ *   - the caller owns every input buffer; buffers only have to stay valid for
+ *     the duration of kai_engine_load_snapshot() (the engine copies to pinned
+ *     host memory and then to HBM).
+ *   - result arrays are engine-owned and valid until the next
+ *     kai_engine_load_snapshot()/kai_engine_run()/kai_engine_destroy().
+ *   - one caller thread at a time per engine (Scheduler.runOnce is
+ *     single-threaded: pkg/scheduler/scheduler.go:107-138).
+ *   - there is NO CPU fallback inside the library: if no CUDA device is
+ *     usable, kai_engine_create() fails with KAI_ERR_NO_DEVICE and the shim
+ *     falls back to the stock Go action for that cycle.
+ *
+ * Resource vector layout (reference: api/resource_info/resource_vector.go:23-36):
+ *   index 0 cpu (milli-cores), 1 memory (bytes), 2 gpu (whole devices),
+ *   3 pods, 4.. extra scalar resources in first-seen order.
+ * Queue-level resource order (reference: plugins/proportion/resource_share/
+ *   resource_quantities.go `AllResources`): 0 CPU, 1 Memory, 2 GPU.
+ */
+#ifndef KAI_ENGINE_H_
+#define KAI_ENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAI_ABI_VERSION 1
+#define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
+#define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
+#define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
+
+enum { KAI_RES_CPU = 0, KAI_RES_MEM = 1, KAI_RES_GPU = 2, KAI_RES_PODS = 3 };
+enum { KAI_Q_CPU = 0, KAI_Q_MEM = 1, KAI_Q_GPU = 2 };
+
+/* reference: pkg/common/constants/constants.go:8-13 */
+#define KAI_UNLIMITED (-1.0)
+
+typedef enum kai_status {
+  KAI_OK = 0,
+  KAI_ERR_INVALID = -1,     /* bad argument / malformed snapshot */
+  KAI_ERR_NO_DEVICE = -2,   /* no usable CUDA device (no CPU fallback exists) */
+  KAI_ERR_CUDA = -3,        /* CUDA runtime error, see kai_last_error */
+  KAI_ERR_UNSUPPORTED = -4, /* snapshot uses a feature outside the engine's scope */
+  KAI_ERR_STATE = -5        /* call order violated (e.g. run before load) */
+} kai_status;
+
+/* Pod status bitmask values. reference: api/pod_status/pod_status.go:25-71 */
+enum {
+  KAI_POD_PENDING = 1,
+  KAI_POD_GATED = 2,
+  KAI_POD_ALLOCATED = 4,
+  KAI_POD_PIPELINED = 8,
+  KAI_POD_BINDING = 16,
+  KAI_POD_BOUND = 32,
+  KAI_POD_RUNNING = 64,
+  KAI_POD_RELEASING = 128,
+  KAI_POD_SUCCEEDED = 256,
+  KAI_POD_FAILED = 512,
+  KAI_POD_UNKNOWN = 1024,
+  KAI_POD_DELETED = 2048
+};
+
+/* node_flags bits */
+enum {
+  KAI_NODE_READY = 1u,       /* counts toward fair-share totals (proportion.go:258-263) */
+  KAI_NODE_NOT_CPU_ONLY = 2u /* MIG-enabled or DRA GPUs: never a "CPU-only node" (node_info.go:697-702) */
+};
+
+/* job_flags bits */
+enum {
+  KAI_JOB_PREEMPTIBLE = 1u /* pkg/common/podgroup/preemptible.go:10-26 */
+};
+
+/* Actions. reference: pkg/scheduler/framework/interface.go:30-39 */
+typedef enum kai_action {
+  KAI_ACTION_ALLOCATE = 1,
+  KAI_ACTION_CONSOLIDATION = 2,
+  KAI_ACTION_RECLAIM = 3
+} kai_action;
+
+/* node placement strategy. reference: plugins/nodeplacement/nodeplacement.go:53-73 */
+enum { KAI_PLACEMENT_BINPACK = 0, KAI_PLACEMENT_SPREAD = 1 };
+
+typedef struct kai_config {
+  int32_t abi_version;          /* = KAI_ABI_VERSION */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t gpu_placement;        /* nodeplacement `gpu:` argument */
+  int32_t cpu_placement;        /* nodeplacement `cpu:` argument */
+  double k_value;               /* proportion `kValue` (proportion.go:78-85) */
+  double saturation_multiplier; /* proportion `relcaimerSaturationMultiplier` (proportion.go:68-76) */
+  int32_t max_consolidation_preemptees; /* -1 = unlimited (options.go:38) */
+  int32_t allow_consolidating_reclaim;  /* options.go:121 */
+  /* node sharding across engines of one box.  shard_count = 1
+     for a single GPU.  Shard s owns node rows [s*N/S, (s+1)*N/S) of the
+     snapshot; the exchange buffer is wired with kai_engine_wire_peers(). */
+  int32_t shard_rank;
+  int32_t shard_count;
+} kai_config;
+
+/*
+ * Structure-of-arrays snapshot of api.ClusterInfo
+ * (reference: pkg/scheduler/api/cluster_info.go:43-64).
+ *
+ * Node tables are resource-major: x[r * n_nodes + n].
+ * Queue tables are resource-major as well: x[r * n_queues + q], r in KAI_Q_*.
+ * Task request table is task-major: task_req[t * n_res + r].
+ */
+typedef struct kai_snapshot {
+  int32_t abi_version;
+  int32_t n_res; /* 4..KAI_MAX_RES */
+  int32_t n_nodes;
+  int32_t n_queues;
+  int32_t n_jobs;
+  int32_t n_podsets;
+  int32_t n_tasks;
+  int32_t n_pred_classes;
+
+  /* ---- nodes: NodeInfo (api/node_info/node_info.go:68-105) ---- */
+  const double *node_allocatable; /* [n_res][N] Allocatable */
+  const double *node_idle;        /* [n_res][N] Idle */
+  const double *node_releasing;   /* [n_res][N] Releasing */
+  const int32_t *node_name_rank;  /* [N] rank of Name in byte-wise ascending order (session.go:480-485) */
+  const uint32_t *node_flags;     /* [N] KAI_NODE_* */
+  const double *node_gpu_count;   /* [N] GetNumberOfGPUsInNode (node_info.go:644-651); NULL = Allocatable gpu */
+  const double *node_foreign;     /* [3][N] resources of active pods of other schedulers (proportion.go:276-286); NULL = 0 */
+
+  /* ---- queues: QueueInfo (api/queue_info/queue_info.go:32-43) ---- */
+  const int32_t *queue_parent;   /* [Q] index of ParentQueue, -1 = top level */
+  const int32_t *queue_priority; /* [Q] */
+  const int64_t *queue_creation; /* [Q] CreationTimestamp, any monotone integer clock */
+  const int32_t *queue_uid_rank; /* [Q] rank of UID string */
+  const double *queue_deserved;  /* [3][Q] quota; memory already in bytes; -1 unlimited */
+  const double *queue_limit;     /* [3][Q] limit; -1 unlimited */
+  const double *queue_oqw;       /* [3][Q] overQuotaWeight */
+  const double *queue_usage;     /* [3][Q] historical usage (normalised); NULL = 0 */
+
+  /* ---- jobs: PodGroupInfo (api/podgroup_info/job_info.go:65-103) ---- */
+  const int32_t *job_queue;        /* [J] leaf queue index, -1 = queue missing */
+  const int32_t *job_priority;     /* [J] */
+  const int32_t *job_order_rank;   /* [J] rank under (CreationTimestamp, UID) (session_plugins.go:235-241) */
+  const uint32_t *job_flags;       /* [J] KAI_JOB_* */
+  const int32_t *job_podset_begin; /* [J+1] podsets of job j = [begin[j], begin[j+1]), in PodSet name order */
+
+  /* ---- podsets: subgroup_info.PodSet ---- */
+  const int32_t *podset_min_available; /* [S] */
+  const int32_t *podset_task_begin;    /* [S+1] tasks of podset s = [begin[s], begin[s+1]) */
+
+  /* ---- tasks: PodInfo (api/pod_info/pod_info.go:70-112) ---- */
+  const int32_t *task_status;     /* [T] KAI_POD_* */
+  const int32_t *task_node;       /* [T] node index for active-used tasks, else -1 */
+  const double *task_req;         /* [T][n_res] ResReq vector; pods column = 1 (pod_info.go:390) */
+  const int32_t *task_order_rank; /* [T] rank under TaskOrderFn within the job (session_plugins.go:244-259) */
+  const int32_t *task_nominated;  /* [T] Status.NominatedNodeName as node index, -1 none; NULL = none */
+  const int32_t *task_pred_class; /* [T] row of pred_mask, -1 = passes everywhere; NULL = all -1 */
+
+  /* ---- host-evaluated predicates (k8s Filters, node conditions, MIG rules):
+         bit n of row c set = node n passes for predicate class c ---- */
+  const uint32_t *pred_mask; /* [n_pred_classes][(N+31)/32] */
+} kai_snapshot;
+
+/* One entry per job popped by an action, in visiting order. */
+typedef struct kai_job_visit {
+  int32_t job;
+  int32_t outcome; /* 1 = statement committed, 0 = discarded */
+} kai_job_visit;
+
+typedef struct kai_result {
+  int32_t n_tasks;
+  const int32_t *task_node;   /* [T] node index after the action, -1 = none */
+  const int32_t *task_status; /* [T] KAI_POD_* after the action (Binding for committed allocations) */
+  int32_t n_visits;
+  const kai_job_visit *visits; /* [n_visits] */
+  int32_t n_queues;
+  const double *queue_fair_share;              /* [3][Q] */
+  const double *queue_allocated;               /* [3][Q] */
+  const double *queue_allocated_non_preemptible; /* [3][Q] */
+  const double *queue_request;                 /* [3][Q] */
+  const double *total_resource;                /* [3] */
+  int32_t n_nodes;
+  const double *node_idle;      /* [n_res][N] after the action */
+  const double *node_releasing; /* [n_res][N] after the action */
+  int64_t pods_placed;          /* tasks that moved Pending -> Binding/Pipelined in this run */
+  int64_t pods_evicted;         /* tasks that moved to Releasing in this run */
+} kai_result;
+
+typedef struct kai_stats {
+  double upload_ms;      /* host -> HBM snapshot copy of the last load */
+  double open_session_ms;/* totals + queue usage + fair-share kernels */
+  double action_ms;      /* device time of the last kai_engine_run action kernel (CUDA events) */
+  double download_ms;    /* HBM -> host result copy */
+  int64_t decisions;     /* node-table sweeps executed (one per allocateTask call) */
+  int64_t nodes_scanned; /* sum over sweeps of node-set size */
+  int64_t kernel_launches; /* kernels launched by the last load+run */
+  int64_t algorithmic_bytes; /* nodes_scanned * bytes/node */
+} kai_stats;
+
+typedef struct kai_engine kai_engine;
+
+/* replaces: the per-cycle construction in framework.OpenSession
+   (pkg/scheduler/framework/framework.go:32-62) for the plugins on the path. */
+int kai_engine_create(const kai_config *cfg, kai_engine **out);
+
+/* replaces: cache.Snapshot() -> ClusterInfo hand-off (framework/session.go:341-366)
+   followed by proportion.OnSessionOpen (plugins/proportion/proportion.go:99-124):
+   copies the SoA to HBM and computes totals, queue usage and fair shares. */
+int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *snap);
+
+/* replaces: Action.Execute(ssn) for allocate / consolidation / reclaim
+   (actions/allocate/allocate.go:46-77, actions/consolidation/consolidation.go:32-78,
+   actions/reclaim/reclaim.go:47-100).  Session state persists between calls so
+   that `allocate, consolidation, reclaim` can be run in sequence. */
+int kai_engine_run(kai_engine *e, kai_action action, kai_result *out);
+
+/* replaces: fairshare-simulator's SetResourcesShare call
+   (cmd/fairshare-simulator/main.go:95-103) — results of the last load. */
+int kai_engine_fair_share(kai_engine *e, kai_result *out);
+
+int kai_engine_stats(kai_engine *e, kai_stats *out);
+
+/* Multi-GPU wiring (one engine per process per GPU).  Each engine exports a
+   64-byte opaque handle of its exchange buffer; after an out-of-band
+   all-gather the full table is handed to every engine. */
+#define KAI_PEER_HANDLE_BYTES 64
+int kai_engine_export_peer_handle(kai_engine *e, uint8_t handle[KAI_PEER_HANDLE_BYTES]);
+int kai_engine_wire_peers(kai_engine *e, const uint8_t *handles /* [shard_count][64] */);
+
+void kai_engine_destroy(kai_engine *e);
+const char *kai_last_error(const kai_engine *e);
+int kai_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAI_ENGINE_H_ */

@@ -1,0 +1,1483 @@
+// kai_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY (see kai_oracle.h).
+//
+// A plain, sequential restatement of the reference's per-Session scheduling
+// cycle (NVIDIA/KAI-Scheduler @72de64fc, pkg/scheduler).  Every function cites
+// the reference file:line it follows (paths relative to pkg/scheduler/).  The
+// reference is Go and cannot be compiled in this image (no Go toolchain, un-
+// vendored k8s modules), so parity is pinned by the reference's own
+// known-answer tests transcribed under tests/golden/ (tests/golden/README.md).
+//
+// Numeric contract: IEEE-754 binary64, no fused multiply-add (build with
+// -ffp-contract=off), operation order exactly as in the Go sources.
+//
+// Where the reference iterates a Go map (unspecified order) the oracle uses
+// ascending index order; SURVEY.md Appendix A.6 lists those places.
+#include "kai_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr int QR = KAI_QRES;
+constexpr int kActiveUsed = KAI_POD_ALLOCATED | KAI_POD_PIPELINED | KAI_POD_BINDING | KAI_POD_BOUND |
+                            KAI_POD_RUNNING | KAI_POD_RELEASING;  // pod_status.go:55
+constexpr int kActiveAllocated = KAI_POD_ALLOCATED | KAI_POD_PIPELINED | KAI_POD_BINDING | KAI_POD_BOUND |
+                                 KAI_POD_RUNNING;  // pod_status.go:56
+constexpr int kAlive = kActiveAllocated | KAI_POD_PENDING | KAI_POD_GATED;                       // :57
+constexpr int kAllocatedStatuses = KAI_POD_ALLOCATED | KAI_POD_BOUND | KAI_POD_BINDING | KAI_POD_RUNNING;  // :59
+
+// ---------------------------------------------------------------------------
+// container/heap (Go standard library, go1.24 src/container/heap/heap.go) —
+// the algorithm behind scheduler_util.PriorityQueue (scheduler_util/priority_queue.go:50-118).
+// Restated exactly because comparator inconsistencies make the pop order depend on it.
+// ---------------------------------------------------------------------------
+template <class T>
+struct GoHeap {
+  std::vector<T> items;
+  std::function<bool(const T &, const T &)> less;
+  int len() const { return (int)items.size(); }
+  bool empty() const { return items.empty(); }
+  void up(int j) {
+    for (;;) {
+      int i = (j - 1) / 2;  // parent
+      if (i == j || !less(items[j], items[i])) break;
+      std::swap(items[i], items[j]);
+      j = i;
+    }
+  }
+  bool down(int i0, int n) {
+    int i = i0;
+    for (;;) {
+      int j1 = 2 * i + 1;
+      if (j1 >= n || j1 < 0) break;
+      int j = j1;
+      int j2 = j1 + 1;
+      if (j2 < n && less(items[j2], items[j1])) j = j2;
+      if (!less(items[j], items[i])) break;
+      std::swap(items[i], items[j]);
+      i = j;
+    }
+    return i > i0;
+  }
+  void push(const T &x) {
+    items.push_back(x);
+    up(len() - 1);
+  }
+  T pop() {
+    int n = len() - 1;
+    std::swap(items[0], items[n]);
+    down(0, n);
+    T x = items.back();
+    items.pop_back();
+    return x;
+  }
+  void fix(int i) {
+    if (!down(i, len())) up(i);
+  }
+  const T &peek() const { return items[0]; }
+};
+
+// ---------------------------------------------------------------------------
+// data model (api/**)
+// ---------------------------------------------------------------------------
+struct Share {  // plugins/proportion/resource_share/resource_share.go:12-21
+  double deserved = 0, fair = 0, max_allowed = 0, oqw = 0, allocated = 0, alloc_np = 0, request = 0, usage = 0;
+};
+
+// resource_share.go:40-45
+double requestable_share(const Share &s) {
+  if (s.max_allowed == KAI_UNLIMITED) return s.request;
+  return std::fmin(s.max_allowed, s.request);
+}
+// resource_share.go:51-61
+double allocatable_share(const Share &s) {
+  if (s.deserved == KAI_UNLIMITED) return s.max_allowed;
+  double a = std::fmax(s.deserved, s.fair);
+  if (s.max_allowed != KAI_UNLIMITED) a = std::fmin(s.max_allowed, a);
+  return a;
+}
+// resource_quantities.go:81-97 compareQuantities
+int compare_quantities(double q, double o) {
+  if (q == KAI_UNLIMITED) return o == KAI_UNLIMITED ? 0 : 1;
+  if (o == KAI_UNLIMITED) return -1;
+  if (q > o) return 1;
+  if (q < o) return -1;
+  return 0;
+}
+// resource_quantities.go:57-64 LessEqual
+bool q_less_equal(const double *a, const double *b) {
+  for (int r = 0; r < QR; r++)
+    if (compare_quantities(a[r], b[r]) > 0) return false;
+  return true;
+}
+
+struct QueueAttr {  // resource_share/queue_resource_share.go:22-31
+  int parent = -1, priority = 0, uid_rank = 0;
+  int64_t creation = 0;
+  Share s[QR];
+  std::vector<int> children;
+};
+
+// queue_resource_share.go:142-166 GetDominantResourceShare
+double dominant_share(const QueueAttr &q, const double *total) {
+  double dom = 0.0;
+  for (int r = 0; r < QR; r++) {
+    double value;
+    double allocatable = allocatable_share(q.s[r]);
+    if (allocatable == KAI_UNLIMITED) allocatable = total[r];
+    double allocated = q.s[r].allocated;
+    if (allocatable == 0)
+      value = allocated * 1000;  // noFairShareDrfMultiplier
+    else
+      value = allocated / allocatable;
+    dom = std::fmax(dom, value);
+  }
+  return dom;
+}
+
+// ---------------------------------------------------------------------------
+// plugins/proportion/resource_division/resource_division.go
+// ---------------------------------------------------------------------------
+// :283-290
+bool is_queue_satisfied(const Share &s) {
+  if (s.request <= s.fair) return true;
+  if (s.max_allowed != KAI_UNLIMITED && s.max_allowed <= s.fair) return true;
+  return false;
+}
+// :317-325
+double remaining_requested(const Share &s) {
+  double requested = requestable_share(s);
+  if (requested < s.fair) return 0;
+  return requested - s.fair;
+}
+
+struct RemReq {
+  int q;
+  double amount;
+};
+
+// :164-222 divideUpToFairShare — `group` in ascending index order (map order in Go)
+double divide_up_to_fair_share(double total, double k, std::vector<QueueAttr> &Q, const std::vector<int> &group, int r,
+                               std::map<int, double> &rr) {
+  for (;;) {
+    bool another = false;
+    double round_amount = total;
+    // :224-251 calcShareWeights, :307-315 getTotalWeightsForUnsatisfied
+    double total_weights = 0;
+    for (int q : group)
+      if (remaining_requested(Q[q].s[r]) > 0) total_weights += Q[q].s[r].oqw;
+    std::map<int, double> w;
+    double wsum = 0.0;
+    if (total_weights != 0) {
+      for (int q : group) {
+        const Share &s = Q[q].s[r];
+        if (is_queue_satisfied(s)) continue;
+        double n_weight = s.oqw / total_weights;
+        double n_usage = s.usage;
+        double t = n_weight - n_usage;
+        double t2 = k * t;
+        double sw = std::fmax(0.0, n_weight + t2);
+        w[q] = sw;
+        wsum += sw;
+      }
+    }
+    if (wsum == 0) break;
+    for (int q : group) {
+      if (total == 0) break;
+      Share &s = Q[q].s[r];
+      if (is_queue_satisfied(s)) continue;
+      double requested = remaining_requested(s);
+      if (s.oqw == 0) continue;
+      double qw = w.count(q) ? w[q] : 0.0;
+      double nqw = qw / wsum;
+      double fair = round_amount * nqw;
+      // :264-281 getResourceToGiveInCurrentRound
+      double give = 0;
+      if (requested <= fair) {
+        give = requested;
+        rr.erase(q);
+      } else {
+        double rf = std::floor(fair);
+        if (rf > 0) give = rf;
+        if (fair - give > 0) rr[q] = fair - give;
+      }
+      if (give == 0) continue;
+      s.fair += give;
+      total -= give;
+      another = another || requested < fair;
+    }
+    if (!another || total == 0) break;
+  }
+  return total;
+}
+
+// :33-43 setResourceShare for one sibling group and one resource
+double set_resource_share(double total, double k, std::vector<QueueAttr> &Q, const std::vector<int> &group, int r) {
+  // :92-109 setDeservedResource
+  double remaining = total;
+  for (int q : group) {
+    Share &s = Q[q].s[r];
+    double deserved = s.deserved;
+    if (deserved == KAI_UNLIMITED) deserved = total;
+    double amount = std::fmin(deserved, requestable_share(s));
+    s.fair += amount;
+    remaining -= amount;
+  }
+  if (!(remaining > 0)) return 0;
+  // :111-144 divideOverQuotaResource; :146-162 getQueuesByPriority (priorities descending)
+  std::map<int, std::vector<int>, std::greater<int>> by_prio;
+  for (int q : group) by_prio[Q[q].priority].push_back(q);
+  std::map<int, std::map<int, double>, std::greater<int>> rem;
+  for (auto &kv : by_prio) {
+    std::map<int, double> rr;
+    remaining = divide_up_to_fair_share(remaining, k, Q, kv.second, r, rr);
+    rem[kv.first] = rr;
+  }
+  for (auto &kv : by_prio) {
+    if (remaining <= 0) break;
+    auto &rr = rem[kv.first];
+    if (rr.empty()) continue;
+    // :253-262 divideRemainingResource; order :335-357 (remaining desc, creation asc, uid asc)
+    std::vector<RemReq> v;
+    for (auto &e : rr) v.push_back({e.first, e.second});
+    std::sort(v.begin(), v.end(), [&](const RemReq &a, const RemReq &b) {
+      if (a.amount > b.amount) return true;
+      if (a.amount < b.amount) return false;
+      if (Q[a.q].creation != Q[b.q].creation) return Q[a.q].creation < Q[b.q].creation;
+      return Q[a.q].uid_rank < Q[b.q].uid_rank;
+    });
+    size_t i = 0;
+    while (!(remaining == 0) && i < v.size()) {
+      double give = std::fmin(1.0, remaining);
+      Q[v[i].q].s[r].fair += give;
+      remaining -= give;
+      i++;
+    }
+  }
+  return remaining;
+}
+
+// ---------------------------------------------------------------------------
+// plugins/proportion/queue_order/queue_order.go:19-73
+// job_req: QuantifyResource(GetTasksToAllocateInitResource(job,..,false)) of the best pending job
+// victims_alloc: Σ QuantifyResource(victim.Allocated) (reclaim victim queues), may be null
+// ---------------------------------------------------------------------------
+int queue_order_result(const QueueAttr &l, const QueueAttr &r, const double *l_req, const double *r_req,
+                       const double *l_victims, const double *r_victims, const double *total) {
+  // :87-100 prioritizeUnderUtilized — FairShare.Less(Allocated): strictly less on all resources
+  auto over_utilized = [](const QueueAttr &q) {
+    for (int i = 0; i < QR; i++)
+      if (q.s[i].fair >= q.s[i].allocated) return false;
+    return true;
+  };
+  bool lo = over_utilized(l), ro = over_utilized(r);
+  if (!lo && ro) return -1;
+  if (lo && !ro) return 1;
+  // :102-128 prioritizeUnderQuotaWithJob
+  double lw[QR], rw[QR], ld[QR], rd[QR];
+  for (int i = 0; i < QR; i++) {
+    lw[i] = l.s[i].allocated + l_req[i];
+    rw[i] = r.s[i].allocated + r_req[i];
+    ld[i] = l.s[i].deserved;
+    rd[i] = r.s[i].deserved;
+  }
+  bool ls = q_less_equal(lw, ld), rs_ = q_less_equal(rw, rd);
+  if (ls && !rs_) return -1;
+  if (rs_ && !ls) return 1;
+  // :75-85 prioritizePrioritized
+  if (l.priority > r.priority) return -1;
+  if (l.priority < r.priority) return 1;
+  // :130-180 penalizeZeroShareWithJob
+  auto violation = [](const QueueAttr &q, const double *with_job) {
+    bool v = false;
+    for (int i = 0; i < QR; i++) {
+      if (allocatable_share(q.s[i]) != 0) continue;
+      if (with_job[i] > 0) v = true;
+    }
+    return v;
+  };
+  bool lv = violation(l, lw), rv = violation(r, rw);
+  if (lv && !rv) return 1;
+  if (!lv && rv) return -1;
+  // :182-201 prioritizeSmallerResourceShare; :242-273 calculateDominantResourceShareWithJob
+  auto drf_with_job = [&](const QueueAttr &q, const double *req, const double *vict) {
+    QueueAttr tmp = q;
+    for (int i = 0; i < QR; i++) tmp.s[i].allocated += req[i];
+    if (vict)
+      for (int i = 0; i < QR; i++) tmp.s[i].allocated -= vict[i];
+    return dominant_share(tmp, total);
+  };
+  double lsh = drf_with_job(l, l_req, l_victims), rsh = drf_with_job(r, r_req, r_victims);
+  if (lsh < rsh) return -1;
+  if (lsh > rsh) return 1;
+  // :203-219
+  lsh = dominant_share(l, total);
+  rsh = dominant_share(r, total);
+  if (lsh < rsh) return -1;
+  if (lsh > rsh) return 1;
+  // :221-233 prioritizeBasedOnAllocatableShare
+  double la[QR], ra[QR];
+  for (int i = 0; i < QR; i++) {
+    la[i] = allocatable_share(l.s[i]);
+    ra[i] = allocatable_share(r.s[i]);
+  }
+  if (!q_less_equal(ra, la) && q_less_equal(la, ra)) return -1;
+  if (!q_less_equal(la, ra) && q_less_equal(ra, la)) return 1;
+  // :235-240 prioritizeBasedOnCreationTime
+  if (l.creation < r.creation) return -1;
+  return 1;
+}
+
+// plugins/nodeplacement/pack.go:45-64
+double binpack_score(double mn, double mx, double cur, double overall) {
+  if (overall == 0) return 0.0;
+  if (mx == 0) return 0.0;
+  if (mn == mx) return 9.0;
+  double t1 = cur - mn;
+  double t2 = mx - mn;
+  double t3 = t1 / t2;
+  double t4 = 1 - t3;
+  return 9 * t4;
+}
+// plugins/nodeplacement/spread.go:16-36
+double spread_score(double non_allocated, double count) {
+  if (count == 0) return 0;
+  return non_allocated / count;
+}
+
+struct Task {
+  int job = -1, podset = -1, status = 0, node = -1, order_rank = 0, nominated = -1, pred_class = -1;
+  double req[KAI_MAX_RES] = {0};
+  bool is_virtual = false;  // PodInfo.IsVirtualStatus
+  int node_status = 0;      // status of the clone stored in NodeInfo.PodInfos (node_info.go:400-402)
+  bool on_node = false;
+};
+struct PodSet {
+  int job = -1, min_available = 0;
+  std::vector<int> tasks;
+};
+struct Job {
+  int queue = -1, priority = 0, order_rank = 0;
+  bool preemptible = false;
+  std::vector<int> podsets;
+  // inner caches (job_info.go:98-101; invalidated on any status change :281-284)
+  bool tta_valid = false;
+  std::vector<int> tta;
+  bool tta_res_valid = false;
+  double tta_res[QR] = {0, 0, 0};
+};
+
+struct Op {  // framework/statement.go operations
+  enum Kind { ALLOCATE, PIPELINE, EVICT, UNDO } kind;
+  int task = -1;
+  int prev_status = 0, prev_node = -1, next_node = -1;
+  bool prev_virtual = false;
+  int undo_index = -1;
+};
+
+struct QNode {  // actions/utils/job_order_by_queue.go:18-25 queueNode
+  int queue = -1;
+  bool is_leaf = false, needs_reorder = false;
+  int parent = -1;  // index into nodes, -1 root level
+  GoHeap<int> children;  // job ids (leaf) or QNode ids (non-leaf)
+};
+
+}  // namespace
+
+struct kai_oracle {
+  kai_config cfg;
+  std::string err;
+  int R = 4, N = 0, NQ = 0, NJ = 0, NS = 0, NT = 0, NPC = 0, mask_words = 0;
+  std::vector<double> alloc, idle, rel;  // [R][N]
+  std::vector<int> name_rank;
+  std::vector<uint32_t> nflags;
+  std::vector<double> gpu_count;
+  std::vector<double> foreign;
+  std::vector<QueueAttr> Q;
+  std::vector<Job> J;
+  std::vector<PodSet> PS;
+  std::vector<Task> T;
+  std::vector<uint32_t> pred_mask;
+  double total[QR] = {0, 0, 0};
+  bool loaded = false;
+  int n_threads = 1;
+
+  // results
+  std::vector<int32_t> r_task_node, r_task_status;
+  std::vector<kai_job_visit> r_visits;
+  std::vector<double> r_fair, r_alloc, r_alloc_np, r_request, r_idle, r_rel;
+  double r_total[QR];
+  int64_t pods_placed = 0, pods_evicted = 0;
+  kai_stats stats;
+
+  // statement
+  std::vector<Op> ops;
+
+  double &A(int r, int n) { return alloc[(size_t)r * N + n]; }
+  double &I(int r, int n) { return idle[(size_t)r * N + n]; }
+  double &L(int r, int n) { return rel[(size_t)r * N + n]; }
+
+  // ---------------- PodInfo helpers (api/pod_info/pod_info.go) ----------------
+  // :343-347 IsRequireAnyKindOfGPU (whole-GPU scope: GPUs() > 0)
+  bool task_requires_gpu(const Task &t) const { return t.req[KAI_RES_GPU] > 0; }
+  // resource_requirment.go:97-102 + base_resources.go:119-130 + gpu_resource_requirment.go:89-104
+  bool task_req_is_empty(const Task &t) const {
+    if (t.req[KAI_RES_GPU] > 0.01) return false;
+    if (t.req[KAI_RES_CPU] >= 10 || t.req[KAI_RES_MEM] >= 10.0 * 1024 * 1024) return false;
+    for (int r = 3; r < R; r++)
+      if (t.req[r] >= 10) return false;
+    return true;
+  }
+  // :518-521 ShouldAllocate
+  bool should_allocate(const Task &t, bool real) const {
+    return t.status == KAI_POD_PENDING || (!real && t.status == KAI_POD_RELEASING && t.is_virtual);
+  }
+
+  // ---------------- NodeInfo (api/node_info/node_info.go) ----------------
+  // :361-382 isTaskAllocatableOnNonAllocatedResources -> :771-778 -> resource_requirment.go:126-140
+  //  -> base_resources.go:90-105
+  bool fits(const Task &t, int n, bool with_releasing) {
+    for (int r = 0; r < R; r++) {
+      double avail = I(r, n);
+      if (with_releasing) avail = avail + L(r, n);
+      if (r >= 3) {  // scalar resources: only requested ones are checked
+        if (t.req[r] != 0 && t.req[r] > avail) return false;
+      } else if (t.req[r] > avail)
+        return false;
+    }
+    return true;
+  }
+  // :168-188 IsTaskAllocatable
+  bool is_task_allocatable(const Task &t, int n) {
+    if (task_req_is_empty(t)) return true;
+    return fits(t, n, false);
+  }
+  // :190-206 IsTaskAllocatableOnReleasingOrIdle
+  bool is_task_allocatable_releasing_or_idle(const Task &t, int n) { return fits(t, n, true); }
+  // :697-702 IsCPUOnlyNode
+  bool is_cpu_only_node(int n) { return !(nflags[n] & KAI_NODE_NOT_CPU_ONLY) && A(KAI_RES_GPU, n) <= 0; }
+
+  // :457-493 addTaskResources (Used is not tracked: it never feeds a decision)
+  void node_add_task(int ti) {
+    Task &t = T[ti];
+    int n = t.node;
+    t.node_status = t.status;
+    t.on_node = true;
+    for (int r = 0; r < R; r++) {
+      switch (t.status) {
+        case KAI_POD_RELEASING:
+          L(r, n) += t.req[r];
+          I(r, n) -= t.req[r];
+          break;
+        case KAI_POD_PIPELINED:
+          L(r, n) -= t.req[r];
+          break;
+        default:
+          I(r, n) -= t.req[r];
+      }
+    }
+  }
+  // :515-551 removeTaskResources — uses the status of the clone stored on the node
+  void node_remove_task(int ti, int n) {
+    Task &t = T[ti];
+    for (int r = 0; r < R; r++) {
+      switch (t.node_status) {
+        case KAI_POD_RELEASING:
+          L(r, n) -= t.req[r];
+          I(r, n) += t.req[r];
+          break;
+        case KAI_POD_PIPELINED:
+          L(r, n) += t.req[r];
+          break;
+        default:
+          I(r, n) += t.req[r];
+      }
+    }
+    t.on_node = false;
+  }
+
+  // ---------------- PodGroupInfo ----------------
+  void set_status(int ti, int status) {  // job_info.go:253-264 UpdateTaskStatus
+    Task &t = T[ti];
+    t.status = status;
+    J[t.job].tta_valid = false;
+    J[t.job].tta_res_valid = false;
+  }
+  int podset_count(const PodSet &ps, int mask) const {
+    int c = 0;
+    for (int ti : ps.tasks)
+      if (T[ti].status & mask) c++;
+    return c;
+  }
+  // subgroup_info/podset.go:114-120
+  bool job_ready(const Job &j) const {
+    for (int s : j.podsets) {
+      const PodSet &ps = PS[s];
+      int ready = podset_count(ps, kAlive) - podset_count(ps, KAI_POD_GATED);
+      if (ready < ps.min_available) return false;
+    }
+    return true;
+  }
+  int job_count(const Job &j, int mask) const {
+    int c = 0;
+    for (int s : j.podsets) c += podset_count(PS[s], mask);
+    return c;
+  }
+
+  // plugins/subgrouporder/subgroup_order.go:31-62 + framework/session_plugins.go:261-270 (name order = index order)
+  bool podset_less(int a, int b) const {
+    const PodSet &l = PS[a], &r = PS[b];
+    int ln = podset_count(l, kActiveAllocated), rn = podset_count(r, kActiveAllocated);
+    bool lsat = ln >= l.min_available, rsat = rn >= r.min_available;
+    if (!lsat && !rsat) return a < b;
+    if (!lsat) return true;
+    if (!rsat) return false;
+    double lr = (double)ln / (double)l.min_available;
+    double rr = (double)rn / (double)r.min_available;
+    if (lr < rr) return true;
+    if (rr < lr) return false;
+    return a < b;
+  }
+
+  // api/podgroup_info/allocation_info.go:27-54 GetTasksToAllocate
+  const std::vector<int> &tasks_to_allocate(int ji, bool real) {
+    Job &j = J[ji];
+    if (j.tta_valid) return j.tta;
+    std::vector<int> out;
+    std::vector<int> sets = j.podsets;
+    std::sort(sets.begin(), sets.end(), [&](int a, int b) { return podset_less(a, b); });
+    // :165-177 getMaxNumSubGroupsToAllocate
+    int unsat = 0;
+    for (int s : j.podsets)
+      if (podset_count(PS[s], kActiveAllocated) < PS[s].min_available) unsat++;
+    int max_sets = unsat > 0 ? unsat : 1;
+    int n_sets = 0;
+    for (size_t k = 0; k < sets.size() && n_sets < max_sets; k++) {
+      const PodSet &ps = PS[sets[k]];
+      std::vector<int> cand;
+      for (int ti : ps.tasks)
+        if (should_allocate(T[ti], real)) cand.push_back(ti);
+      if (cand.empty()) continue;
+      std::sort(cand.begin(), cand.end(), [&](int a, int b) { return T[a].order_rank < T[b].order_rank; });
+      // :144-153 getNumTasksToAllocate
+      int n_alloc = podset_count(ps, kActiveAllocated);
+      int max_tasks;
+      if (n_alloc >= ps.min_available)
+        max_tasks = std::min((int)cand.size(), 1);
+      else
+        max_tasks = ps.min_available - n_alloc;
+      for (int k2 = 0; k2 < (int)cand.size() && k2 < max_tasks; k2++) out.push_back(cand[k2]);
+      n_sets++;
+    }
+    j.tta = out;
+    j.tta_valid = true;
+    return j.tta;
+  }
+  // allocation_info.go:87-113 GetTasksToAllocateInitResource, quantified (proportion/utils/utils.go:11-13)
+  const double *tasks_to_allocate_init_resource(int ji, bool real) {
+    Job &j = J[ji];
+    if (j.tta_res_valid) return j.tta_res;
+    double acc[QR] = {0, 0, 0};
+    for (int ti : tasks_to_allocate(ji, real))
+      if (should_allocate(T[ti], real))
+        for (int r = 0; r < QR; r++) acc[r] += T[ti].req[r];
+    for (int r = 0; r < QR; r++) j.tta_res[r] = acc[r];
+    j.tta_res_valid = true;
+    return j.tta_res;
+  }
+  bool has_tasks_to_allocate(int ji, bool real) const {  // allocation_info.go:18-25
+    for (int s : J[ji].podsets)
+      for (int ti : PS[s].tasks)
+        if (should_allocate(T[ti], real)) return true;
+    return false;
+  }
+
+  // ---------------- proportion: session open (proportion.go:242-423) ----------------
+  void open_session() {
+    // :252-288 setTotalResources
+    for (int r = 0; r < QR; r++) total[r] = 0;
+    for (int n = 0; n < N; n++) {
+      if (!(nflags[n] & KAI_NODE_READY)) continue;
+      for (int r = 0; r < QR; r++) {
+        double v = A(r, n);
+        if (!foreign.empty()) v -= foreign[(size_t)r * N + n];
+        total[r] += v;
+      }
+    }
+    // :347-401 updateQueuesCurrentResourceUsage
+    for (auto &q : Q)
+      for (int r = 0; r < QR; r++) q.s[r].allocated = q.s[r].alloc_np = q.s[r].request = q.s[r].fair = 0;
+    for (int ji = 0; ji < NJ; ji++) {
+      const Job &j = J[ji];
+      for (int s : j.podsets)
+        for (int ti : PS[s].tasks) {
+          const Task &t = T[ti];
+          if (t.status & kAllocatedStatuses) {
+            for (int q = j.queue; q >= 0; q = Q[q].parent)
+              for (int r = 0; r < QR; r++) {
+                Q[q].s[r].allocated += t.req[r];
+                Q[q].s[r].request += t.req[r];
+                if (!j.preemptible) Q[q].s[r].alloc_np += t.req[r];
+              }
+          } else if (t.status == KAI_POD_PENDING) {
+            for (int q = j.queue; q >= 0; q = Q[q].parent)
+              for (int r = 0; r < QR; r++) Q[q].s[r].request += t.req[r];
+          }
+        }
+    }
+    // :403-423 setFairShare
+    std::vector<int> top;
+    for (int q = 0; q < NQ; q++)
+      if (Q[q].parent < 0) top.push_back(q);
+    set_fair_share_for_queues(total, top);
+  }
+  void set_fair_share_for_queues(const double *tot, const std::vector<int> &group) {
+    if (group.empty()) return;
+    for (int r = 0; r < QR; r++) set_resource_share(tot[r], cfg.k_value, Q, group, r);
+    for (int q : group) {
+      double fs[QR];
+      for (int r = 0; r < QR; r++) fs[r] = Q[q].s[r].fair;
+      set_fair_share_for_queues(fs, Q[q].children);
+    }
+  }
+
+  // ---------------- capacity policy (plugins/proportion/capacity_policy) ----------------
+  // max_allowed_check.go:16-66 + quota_check.go:25-77 through capacity_policy.go:63-74
+  bool over_capacity(int ji, const double *req) {
+    const Job &j = J[ji];
+    for (int q = j.queue; q >= 0; q = Q[q].parent)
+      for (int r = 0; r < QR; r++) {
+        const Share &s = Q[q].s[r];
+        if (s.max_allowed == KAI_UNLIMITED) continue;
+        if (req[r] == 0) continue;
+        if (s.max_allowed < s.allocated + req[r]) return true;
+      }
+    if (j.preemptible) return false;
+    return non_preemptible_over_quota(ji, req);
+  }
+  bool non_preemptible_over_quota(int ji, const double *req) {
+    const Job &j = J[ji];
+    if (j.preemptible) return false;
+    for (int q = j.queue; q >= 0; q = Q[q].parent)
+      for (int r = 0; r < QR; r++) {
+        const Share &s = Q[q].s[r];
+        if (s.deserved == KAI_UNLIMITED) continue;
+        if (req[r] == 0) continue;
+        if (s.deserved < s.alloc_np + req[r]) return true;
+      }
+    return false;
+  }
+
+  // ---------------- event handlers (proportion.go:443-489) ----------------
+  void queue_allocate(int ti, double sign) {
+    const Task &t = T[ti];
+    const Job &j = J[t.job];
+    for (int q = j.queue; q >= 0; q = Q[q].parent)
+      for (int r = 0; r < QR; r++) {
+        if (sign > 0) {
+          Q[q].s[r].allocated += t.req[r];
+          if (!j.preemptible) Q[q].s[r].alloc_np += t.req[r];
+        } else {
+          Q[q].s[r].allocated -= t.req[r];
+          if (!j.preemptible) Q[q].s[r].alloc_np -= t.req[r];
+        }
+      }
+  }
+
+  // ---------------- Statement (framework/statement.go) ----------------
+  // :297-358 Allocate
+  void stmt_allocate(int ti, int n) {
+    Task &t = T[ti];
+    Op op;
+    op.kind = Op::ALLOCATE;
+    op.task = ti;
+    op.prev_status = t.status;
+    op.prev_node = t.node;
+    op.next_node = n;
+    op.prev_virtual = t.is_virtual;
+    set_status(ti, KAI_POD_ALLOCATED);
+    t.node = n;
+    node_add_task(ti);
+    queue_allocate(ti, +1);
+    ops.push_back(op);
+    t.is_virtual = true;
+  }
+  // :392-427 unallocate
+  void unallocate(int ti, bool prev_virtual) {
+    Task &t = T[ti];
+    set_status(ti, KAI_POD_PENDING);
+    node_remove_task(ti, t.node);
+    t.node = -1;
+    t.is_virtual = prev_virtual;
+    queue_allocate(ti, -1);
+  }
+  // :197-295 Pipeline
+  void stmt_pipeline(int ti, int n, bool update_if_exists) {
+    Task &t = T[ti];
+    bool found_on_node = t.on_node && t.node == n;
+    if (found_on_node && !update_if_exists) {
+      stmt_unevict(ti);
+      return;
+    }
+    Op op;
+    op.kind = Op::PIPELINE;
+    op.task = ti;
+    op.prev_status = t.status;
+    op.prev_node = t.node;
+    op.next_node = n;
+    op.prev_virtual = t.is_virtual;
+    set_status(ti, KAI_POD_PIPELINED);
+    if (found_on_node) {
+      node_remove_task(ti, n);  // node_info.go:570-576 UpdateTask
+      t.node = n;
+      node_add_task(ti);
+    } else {
+      t.node = n;
+      node_add_task(ti);
+    }
+    queue_allocate(ti, +1);
+    ops.push_back(op);
+    t.is_virtual = true;
+  }
+  // :432-476 unpipeline
+  void unpipeline(const Op &op) {
+    Task &t = T[op.task];
+    set_status(op.task, op.prev_status);
+    int host = t.node;
+    t.node = op.prev_node;
+    t.is_virtual = op.prev_virtual;
+    node_remove_task(op.task, host);
+    queue_allocate(op.task, -1);
+  }
+  // :63-128 Evict
+  void stmt_evict(int ti) {
+    Task &t = T[ti];
+    Op op;
+    op.kind = Op::EVICT;
+    op.task = ti;
+    op.prev_status = t.status;
+    op.prev_node = t.node;
+    op.next_node = t.node;
+    op.prev_virtual = t.is_virtual;
+    set_status(ti, KAI_POD_RELEASING);
+    node_remove_task(ti, t.node);  // UpdateTask
+    node_add_task(ti);
+    queue_allocate(ti, -1);
+    ops.push_back(op);
+    t.is_virtual = true;
+  }
+  // :156-195 unevict
+  void unevict(const Op &op) {
+    Task &t = T[op.task];
+    set_status(op.task, op.prev_status);
+    t.is_virtual = op.prev_virtual;
+    node_remove_task(op.task, t.node);  // UpdateTask on previous node
+    node_add_task(op.task);
+    queue_allocate(op.task, +1);
+  }
+  // :652-663 operationValid
+  bool op_valid(int i) {
+    for (int u = 0; u < (int)ops.size(); u++) {
+      if (ops[u].kind != Op::UNDO) continue;
+      if (ops[u].undo_index == i) return !op_valid(u);
+    }
+    return true;
+  }
+  // :597-643 undoOperation
+  void undo_operation(int index) {
+    if (!op_valid(index)) return;
+    Op op = ops[index];
+    switch (op.kind) {
+      case Op::EVICT:
+        unevict(op);
+        break;
+      case Op::PIPELINE:
+        unpipeline(op);
+        break;
+      case Op::ALLOCATE:
+        unallocate(op.task, op.prev_virtual);
+        break;
+      case Op::UNDO:
+        redo_operation(op.undo_index);
+        break;
+    }
+    Op u;
+    u.kind = Op::UNDO;
+    u.undo_index = index;
+    ops.push_back(u);
+  }
+  // the redoOperation closures of :607-628
+  void redo_operation(int index) {
+    Op op = ops[index];
+    switch (op.kind) {
+      case Op::EVICT:
+        stmt_evict(op.task);
+        break;
+      case Op::PIPELINE:
+        stmt_pipeline(op.task, op.next_node, true);
+        break;
+      case Op::ALLOCATE:
+        stmt_allocate(op.task, op.next_node);
+        break;
+      case Op::UNDO:
+        undo_operation(op.undo_index);
+        break;
+    }
+  }
+  // :478-481 Unevict -> :573-595 undoEarliestValidOperation
+  void stmt_unevict(int ti) {
+    for (int i = 0; i < (int)ops.size(); i++) {
+      if (!op_valid(i)) continue;
+      if (ops[i].kind != Op::EVICT || ops[i].task != ti) continue;
+      undo_operation(i);
+      return;
+    }
+  }
+  int stmt_checkpoint() { return (int)ops.size(); }  // :44-46
+  void stmt_rollback(int cp) {                       // :48-61
+    for (int i = (int)ops.size() - 1; i >= cp; i--) undo_operation(i);
+    ops.resize(cp);
+  }
+  void stmt_discard() {  // :522-534
+    for (int i = (int)ops.size() - 1; i >= 0; i--) undo_operation(i);
+    ops.clear();
+  }
+  // :483-520 ConvertAllAllocatedToPipelined
+  void stmt_convert_all_allocated_to_pipelined(int ji) {
+    size_t n0 = ops.size();
+    for (size_t i = 0; i < n0; i++) {
+      Op op = ops[i];
+      if (op.kind != Op::ALLOCATE || T[op.task].job != ji) continue;
+      int node = T[op.task].node;
+      unallocate(op.task, true);
+      stmt_pipeline(op.task, node, true);
+    }
+    std::vector<Op> keep;
+    for (auto &op : ops)
+      if (!(op.kind == Op::ALLOCATE && T[op.task].job == ji)) keep.push_back(op);
+    ops = keep;
+  }
+  // :536-571 Commit: allocate -> BindPod -> Binding (session.go:111-125); pipeline/evict keep their session status
+  void stmt_commit() {
+    for (int i = 0; i < (int)ops.size(); i++) {
+      if (!op_valid(i)) continue;
+      const Op &op = ops[i];
+      if (op.kind == Op::ALLOCATE) {
+        T[op.task].status = KAI_POD_BINDING;  // updatePodOnSession: node clone keeps accounting (default branch)
+        T[op.task].node_status = KAI_POD_BINDING;
+        J[T[op.task].job].tta_valid = J[T[op.task].job].tta_res_valid = false;
+        pods_placed++;
+      } else if (op.kind == Op::PIPELINE) {
+        pods_placed++;
+      } else if (op.kind == Op::EVICT) {
+        pods_evicted++;
+      }
+    }
+    ops.clear();
+  }
+
+  // ---------------- node ordering + fitting (framework/session.go:201-264,466-485) ----------------
+  struct Best {
+    double score;
+    int rank;
+    int node;
+  };
+  // returns best fitting node or -1.  node_set == nullptr means all nodes.
+  int pick_node(int ti, const std::vector<int> *node_set) {
+    const Task &t = T[ti];
+    const int n_set = node_set ? (int)node_set->size() : N;
+    stats.decisions++;
+    stats.nodes_scanned += n_set;
+    const bool gpu_task = task_requires_gpu(t);
+    const int res = gpu_task ? KAI_RES_GPU : KAI_RES_CPU;  // nodeplacement.go:75-87
+    const int strategy = gpu_task ? cfg.gpu_placement : cfg.cpu_placement;
+    // pack.go:66-86 getMinMaxPerNode over the node set passed to allocateTask
+    double mn = DBL_MAX, mx = 0;
+    if (strategy == KAI_PLACEMENT_BINPACK) {
+      for (int k = 0; k < n_set; k++) {
+        int n = node_set ? (*node_set)[k] : k;
+        if (A(res, n) == 0) continue;
+        double cur = I(res, n) + L(res, n);
+        if (cur < mn) mn = cur;
+        if (cur > mx) mx = cur;
+      }
+    }
+    const uint32_t *mask = t.pred_class >= 0 ? &pred_mask[(size_t)t.pred_class * mask_words] : nullptr;
+    auto sweep = [&](int k0, int k1) {
+      Best b{-1.0, 0, -1};
+      for (int k = k0; k < k1; k++) {
+        int n = node_set ? (*node_set)[k] : k;
+        // FittingNode (session.go:201-232): capacity part hoisted by the caller
+        if (!is_task_allocatable_releasing_or_idle(t, n)) continue;
+        if (mask && !((mask[n >> 5] >> (n & 31)) & 1u)) continue;
+        // NodeOrderFn sum in plugin registration order (session_plugins.go:427-437)
+        double score = 0.0;
+        score += is_task_allocatable(t, n) ? 100.0 : 0.0;        // nodeavailability.go:29-40
+        score += 0.0;                                            // gpusharingorder (whole GPUs only)
+        score += (!gpu_task && is_cpu_only_node(n)) ? 10.0 : 0.0;  // resourcetype.go:29-41
+        score += (t.nominated == n) ? 1000000.0 : 0.0;           // nominatednode.go:29-41
+        double cur = I(res, n) + L(res, n);
+        if (strategy == KAI_PLACEMENT_BINPACK)
+          score += binpack_score(mn, mx, cur, A(res, n));
+        else
+          score += spread_score(cur, res == KAI_RES_GPU ? (double)(int64_t)gpu_count[n] : A(res, n));
+        if (b.node < 0 || score > b.score || (score == b.score && name_rank[n] < b.rank)) {
+          b.score = score;
+          b.rank = name_rank[n];
+          b.node = n;
+        }
+      }
+      return b;
+    };
+    if (n_threads <= 1 || n_set < 4096) return sweep(0, n_set).node;
+    std::vector<Best> part(n_threads);
+    std::vector<std::thread> th;
+    for (int w = 0; w < n_threads; w++)
+      th.emplace_back([&, w] {
+        int k0 = (int)((int64_t)n_set * w / n_threads), k1 = (int)((int64_t)n_set * (w + 1) / n_threads);
+        part[w] = sweep(k0, k1);
+      });
+    for (auto &x : th) x.join();
+    Best b{-1.0, 0, -1};
+    for (auto &p : part) {
+      if (p.node < 0) continue;
+      if (b.node < 0 || p.score > b.score || (p.score == b.score && p.rank < b.rank)) b = p;
+    }
+    return b.node;
+  }
+
+  // ---------------- actions/common/allocate.go ----------------
+  // :121-174 allocateTask + allocateTaskToNode
+  bool allocate_task(int ti, const std::vector<int> *node_set, bool pipeline_only) {
+    const Task &t = T[ti];
+    // predicates.go:196-200 -> capacity_policy.go:51-61 with node_info.go:734-744:
+    // whole-GPU pods are checked with GPU = 1, CPU-only pods with GPU = 0; node independent.
+    double req[QR] = {t.req[KAI_RES_CPU], t.req[KAI_RES_MEM], task_requires_gpu(t) ? 1.0 : 0.0};
+    if (over_capacity(t.job, req)) return false;
+    int n = pick_node(ti, node_set);
+    if (n < 0) return false;
+    if (!pipeline_only && is_task_allocatable(t, n))
+      stmt_allocate(ti, n);
+    else
+      stmt_pipeline(ti, n, !pipeline_only);
+    return true;
+  }
+  // :20-119 AllocateJob (flat root SubGroupSet; topology subsetting = single node set)
+  bool allocate_job(int ji, const std::vector<int> *node_set, bool pipeline_only) {
+    std::vector<int> tta = tasks_to_allocate(ji, !pipeline_only);
+    // capacity_policy.go:26-36 IsJobOverQueueCapacity
+    double req[QR] = {0, 0, 0};
+    for (int ti : tta)
+      for (int r = 0; r < QR; r++) req[r] += T[ti].req[r];
+    if (over_capacity(ji, req)) return false;
+    int cp = stmt_checkpoint();
+    std::vector<int> sets = J[ji].podsets;
+    std::sort(sets.begin(), sets.end(), [&](int a, int b) { return podset_less(a, b); });
+    for (int s : sets) {
+      int cp2 = stmt_checkpoint();
+      bool ok = true;
+      for (int ti : tta) {
+        if (T[ti].podset != s) continue;
+        if (!allocate_task(ti, node_set, pipeline_only)) {
+          ok = false;
+          break;
+        }
+      }
+      if (!ok) {
+        stmt_rollback(cp2);
+        stmt_rollback(cp);
+        return false;
+      }
+    }
+    return true;
+  }
+  // job_info.go:443-464 ShouldPipelineJob
+  bool should_pipeline_job(int ji) const {
+    for (int s : J[ji].podsets) {
+      const PodSet &ps = PS[s];
+      bool has_pipelined = false;
+      int active = 0;
+      for (int ti : ps.tasks) {
+        if (T[ti].status == KAI_POD_PIPELINED)
+          has_pipelined = true;
+        else if (T[ti].status & kActiveAllocated)
+          active++;
+      }
+      if (has_pipelined && active < ps.min_available) return true;
+    }
+    return false;
+  }
+
+  // ---------------- job ordering (actions/utils/job_order_by_queue.go) ----------------
+  struct JobsOrder {
+    kai_oracle *o;
+    bool victim_queue = false;
+    std::vector<QNode> nodes;
+    std::vector<int> queue_node;  // queue -> QNode index or -1
+    GoHeap<int> root;
+    std::vector<std::vector<int>> popped_by_queue;
+
+    // plugins/elastic/elastic.go:50-63 minAvailableState
+    void min_available_state(int ji, bool &below, bool &above, bool &exactly) const {
+      exactly = true;
+      for (int s : o->J[ji].podsets) {
+        int n = o->podset_count(o->PS[s], kActiveAllocated);
+        if (n < o->PS[s].min_available) {
+          below = true;
+          above = false;
+          exactly = false;
+          return;
+        }
+        if (n > o->PS[s].min_available) exactly = false;
+      }
+      below = false;
+      above = !exactly;
+    }
+    // framework/session_plugins.go:227-242 JobOrderFn = priority, elastic, creation, UID
+    bool job_less(int l, int r) const {
+      const Job &lj = o->J[l], &rj = o->J[r];
+      if (lj.priority > rj.priority) return true;  // plugins/priority/priority.go:41-54
+      if (lj.priority < rj.priority) return false;
+      bool lb, la, le, rb, ra, re;
+      min_available_state(l, lb, la, le);
+      min_available_state(r, rb, ra, re);
+      if (lb && !rb) return true;  // plugins/elastic/elastic.go:25-48
+      if (le && ra) return true;
+      if (!lb && rb) return false;
+      if (la && re) return false;
+      return lj.order_rank < rj.order_rank;
+    }
+    // :280-346 best job of a subtree and the queue comparator
+    int best_job(int ni) const {
+      const QNode &n = nodes[ni];
+      if (n.is_leaf) return n.children.peek();
+      return best_job(n.children.peek());
+    }
+    int leaf_of_best(int ni) const {
+      const QNode &n = nodes[ni];
+      if (n.is_leaf) return ni;
+      return leaf_of_best(n.children.peek());
+    }
+    bool node_less(int l, int r) {
+      if (nodes[l].children.empty()) return !victim_queue;
+      if (nodes[r].children.empty()) return victim_queue;
+      double lreq[QR] = {0, 0, 0}, rreq[QR] = {0, 0, 0}, lv[QR] = {0, 0, 0}, rv[QR] = {0, 0, 0};
+      if (!victim_queue) {
+        const double *a = o->tasks_to_allocate_init_resource(best_job(l), false);
+        for (int i = 0; i < QR; i++) lreq[i] = a[i];
+        const double *b = o->tasks_to_allocate_init_resource(best_job(r), false);
+        for (int i = 0; i < QR; i++) rreq[i] = b[i];
+      } else {
+        victims_allocated(l, lv);
+        victims_allocated(r, rv);
+      }
+      int res = queue_order_result(o->Q[nodes[l].queue], o->Q[nodes[r].queue], lreq, rreq,
+                                   victim_queue ? lv : nullptr, victim_queue ? rv : nullptr, o->total);
+      bool result = res < 0;
+      return victim_queue ? !result : result;
+    }
+    // :338-346 getVictimsForQueue: popped jobs of the leaf + its next job; Σ job.Allocated (cpu, mem, gpu)
+    void victims_allocated(int ni, double *out) {
+      int leaf = leaf_of_best(ni);
+      int q = nodes[leaf].queue;
+      std::vector<int> v = popped_by_queue[q];
+      if (!nodes[leaf].children.empty()) v.push_back(nodes[leaf].children.peek());
+      for (int ji : v)
+        for (int s : o->J[ji].podsets)
+          for (int ti : o->PS[s].tasks)
+            if (o->T[ti].status & kAllocatedStatuses)  // job_info.go:245-250 PodGroupInfo.Allocated
+              for (int r = 0; r < QR; r++) out[r] += o->T[ti].req[r];
+    }
+    void init(kai_oracle *oracle, bool victims) {
+      o = oracle;
+      victim_queue = victims;
+      nodes.clear();
+      nodes.reserve(o->NQ);
+      queue_node.assign(o->NQ, -1);
+      popped_by_queue.assign(o->NQ, {});
+      root = GoHeap<int>();
+      root.less = [this](const int &a, const int &b) { return node_less(a, b); };
+    }
+    int make_node(int q, bool leaf) {
+      nodes.emplace_back();
+      int id = (int)nodes.size() - 1;
+      QNode &n = nodes[id];
+      n.queue = q;
+      n.is_leaf = leaf;
+      if (leaf)
+        n.children.less = [this](const int &a, const int &b) { return victim_queue ? !job_less(a, b) : job_less(a, b); };
+      else
+        n.children.less = [this](const int &a, const int &b) { return node_less(a, b); };
+      return id;
+    }
+    void mark_ancestors(int ni) {  // :246-250
+      for (int c = ni; c >= 0; c = nodes[c].parent) nodes[c].needs_reorder = true;
+    }
+    // :135-175 ensureAncestorChainForPush.  `linked` tracks whether the node already sits in a parent heap
+    std::vector<char> linked;
+    void ensure_chain(int child) {
+      int cq = nodes[child].queue;
+      if ((int)linked.size() < (int)nodes.size()) linked.resize(nodes.size(), 0);
+      if (o->Q[cq].parent < 0) {
+        if (!linked[child]) {
+          root.push(child);
+          linked[child] = 1;
+        }
+        return;
+      }
+      int pq = o->Q[cq].parent;
+      int pn = queue_node[pq];
+      bool is_new = pn < 0;
+      if (is_new) {
+        pn = make_node(pq, false);
+        queue_node[pq] = pn;
+        if ((int)linked.size() < (int)nodes.size()) linked.resize(nodes.size(), 0);
+      }
+      if (!linked[child]) {
+        nodes[child].parent = pn;
+        nodes[pn].children.push(child);
+        linked[child] = 1;
+      }
+      if (is_new) ensure_chain(pn);
+    }
+    void push_job(int ji) {  // :90-119
+      int q = o->J[ji].queue;
+      if (!o->Q[q].children.empty()) return;
+      int leaf = queue_node[q];
+      bool needs_linking = leaf < 0;
+      if (needs_linking) {
+        leaf = make_node(q, true);
+        queue_node[q] = leaf;
+      }
+      nodes[leaf].children.push(ji);
+      if (needs_linking) ensure_chain(leaf);
+      mark_ancestors(leaf);
+    }
+    bool is_empty() const { return root.empty(); }
+    int get_next_node(GoHeap<int> &pq) {  // :193-215
+      for (;;) {
+        if (pq.empty()) return -1;
+        int ni = pq.peek();
+        if (nodes[ni].needs_reorder) {
+          pq.fix(0);
+          nodes[ni].needs_reorder = false;
+          continue;
+        }
+        if (nodes[ni].children.empty()) return -1;
+        return ni;
+      }
+    }
+    int traverse_to_leaf() {  // :178-190
+      GoHeap<int> *pq = &root;
+      for (;;) {
+        int ni = get_next_node(*pq);
+        if (ni < 0) return -1;
+        if (nodes[ni].is_leaf) return ni;
+        pq = &nodes[ni].children;
+      }
+    }
+    void handle_pop(int ni) {  // :219-243
+      if (nodes[ni].children.len() == 0) {
+        if (nodes[ni].parent >= 0)
+          nodes[nodes[ni].parent].children.pop();
+        else
+          root.pop();
+        queue_node[nodes[ni].queue] = -1;
+        linked[ni] = 0;
+        if (nodes[ni].parent >= 0) handle_pop(nodes[ni].parent);
+        return;
+      }
+      mark_ancestors(ni);
+    }
+    int pop_next_job() {  // :61-88
+      if (is_empty()) return -1;
+      int leaf = traverse_to_leaf();
+      if (leaf < 0) return -1;
+      int job = nodes[leaf].children.pop();
+      if (victim_queue) popped_by_queue[nodes[leaf].queue].push_back(job);
+      handle_pop(leaf);
+      return job;
+    }
+  };
+
+  // actions/utils/input_jobs.go:21-68 InitializeWithJobs (jobs in ascending index order)
+  void init_jobs_order(JobsOrder &jo, bool filter_non_pending, bool filter_unready) {
+    for (int ji = 0; ji < NJ; ji++) {
+      const Job &j = J[ji];
+      if (filter_unready && !job_ready(j)) continue;
+      if (filter_non_pending && job_count(j, KAI_POD_PENDING) == 0) continue;
+      if (j.queue < 0) continue;
+      if (!Q[j.queue].children.empty()) continue;
+      jo.push_job(ji);
+    }
+  }
+
+  // ---------------- actions/allocate/allocate.go:46-111 ----------------
+  void run_allocate() {
+    JobsOrder jo;
+    jo.init(this, false);
+    init_jobs_order(jo, true, true);
+    while (!jo.is_empty()) {
+      int ji = jo.pop_next_job();
+      if (ji < 0) break;
+      ops.clear();
+      bool ok = allocate_job(ji, nullptr, false);
+      if (ok) {
+        if (should_pipeline_job(ji)) stmt_convert_all_allocated_to_pipelined(ji);
+        stmt_commit();
+        r_visits.push_back({ji, 1});
+        if (has_tasks_to_allocate(ji, true)) {
+          jo.push_job(ji);
+          continue;
+        }
+      } else {
+        stmt_discard();
+        r_visits.push_back({ji, 0});
+      }
+    }
+  }
+
+  void fill_result(kai_result *out) {
+    r_task_node.resize(NT);
+    r_task_status.resize(NT);
+    for (int t = 0; t < NT; t++) {
+      r_task_node[t] = T[t].node;
+      r_task_status[t] = T[t].status;
+    }
+    r_fair.assign((size_t)QR * NQ, 0);
+    r_alloc.assign((size_t)QR * NQ, 0);
+    r_alloc_np.assign((size_t)QR * NQ, 0);
+    r_request.assign((size_t)QR * NQ, 0);
+    for (int q = 0; q < NQ; q++)
+      for (int r = 0; r < QR; r++) {
+        r_fair[(size_t)r * NQ + q] = Q[q].s[r].fair;
+        r_alloc[(size_t)r * NQ + q] = Q[q].s[r].allocated;
+        r_alloc_np[(size_t)r * NQ + q] = Q[q].s[r].alloc_np;
+        r_request[(size_t)r * NQ + q] = Q[q].s[r].request;
+      }
+    for (int r = 0; r < QR; r++) r_total[r] = total[r];
+    r_idle = idle;
+    r_rel = rel;
+    memset(out, 0, sizeof(*out));
+    out->n_tasks = NT;
+    out->task_node = r_task_node.data();
+    out->task_status = r_task_status.data();
+    out->n_visits = (int)r_visits.size();
+    out->visits = r_visits.data();
+    out->n_queues = NQ;
+    out->queue_fair_share = r_fair.data();
+    out->queue_allocated = r_alloc.data();
+    out->queue_allocated_non_preemptible = r_alloc_np.data();
+    out->queue_request = r_request.data();
+    out->total_resource = r_total;
+    out->n_nodes = N;
+    out->node_idle = r_idle.data();
+    out->node_releasing = r_rel.data();
+    out->pods_placed = pods_placed;
+    out->pods_evicted = pods_evicted;
+  }
+};
+
+extern "C" {
+
+int kai_oracle_create(const kai_config *cfg, kai_oracle **out) {
+  if (!cfg || !out || cfg->abi_version != KAI_ABI_VERSION) return KAI_ERR_INVALID;
+  kai_oracle *o = new kai_oracle();
+  o->cfg = *cfg;
+  memset(&o->stats, 0, sizeof(o->stats));
+  *out = o;
+  return KAI_OK;
+}
+
+int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
+  if (!o || !s || s->abi_version != KAI_ABI_VERSION) return KAI_ERR_INVALID;
+  if (s->n_res < 4 || s->n_res > KAI_MAX_RES) {
+    o->err = "n_res out of range";
+    return KAI_ERR_INVALID;
+  }
+  o->R = s->n_res;
+  o->N = s->n_nodes;
+  o->NQ = s->n_queues;
+  o->NJ = s->n_jobs;
+  o->NS = s->n_podsets;
+  o->NT = s->n_tasks;
+  o->NPC = s->n_pred_classes;
+  o->mask_words = (o->N + 31) / 32;
+  size_t rn = (size_t)o->R * o->N;
+  o->alloc.assign(s->node_allocatable, s->node_allocatable + rn);
+  o->idle.assign(s->node_idle, s->node_idle + rn);
+  o->rel.assign(s->node_releasing, s->node_releasing + rn);
+  o->name_rank.assign(s->node_name_rank, s->node_name_rank + o->N);
+  o->nflags.assign(s->node_flags, s->node_flags + o->N);
+  o->gpu_count.resize(o->N);
+  for (int n = 0; n < o->N; n++)
+    o->gpu_count[n] = s->node_gpu_count ? s->node_gpu_count[n] : o->alloc[(size_t)KAI_RES_GPU * o->N + n];
+  o->foreign.clear();
+  if (s->node_foreign) o->foreign.assign(s->node_foreign, s->node_foreign + (size_t)3 * o->N);
+  o->Q.assign(o->NQ, QueueAttr());
+  for (int q = 0; q < o->NQ; q++) {
+    QueueAttr &a = o->Q[q];
+    a.parent = s->queue_parent[q];
+    a.priority = s->queue_priority[q];
+    a.creation = s->queue_creation[q];
+    a.uid_rank = s->queue_uid_rank[q];
+    for (int r = 0; r < QR; r++) {
+      a.s[r].deserved = s->queue_deserved[(size_t)r * o->NQ + q];
+      a.s[r].max_allowed = s->queue_limit[(size_t)r * o->NQ + q];
+      a.s[r].oqw = s->queue_oqw[(size_t)r * o->NQ + q];
+      a.s[r].usage = s->queue_usage ? s->queue_usage[(size_t)r * o->NQ + q] : 0.0;
+    }
+  }
+  for (int q = 0; q < o->NQ; q++) {
+    int p = o->Q[q].parent;
+    if (p >= o->NQ || p == q) {
+      o->err = "bad queue parent";
+      return KAI_ERR_INVALID;
+    }
+    if (p >= 0) o->Q[p].children.push_back(q);
+  }
+  o->J.assign(o->NJ, Job());
+  o->PS.assign(o->NS, PodSet());
+  o->T.assign(o->NT, Task());
+  for (int j = 0; j < o->NJ; j++) {
+    Job &jb = o->J[j];
+    jb.queue = s->job_queue[j];
+    jb.priority = s->job_priority[j];
+    jb.order_rank = s->job_order_rank[j];
+    jb.preemptible = (s->job_flags[j] & KAI_JOB_PREEMPTIBLE) != 0;
+    for (int ps = s->job_podset_begin[j]; ps < s->job_podset_begin[j + 1]; ps++) {
+      jb.podsets.push_back(ps);
+      o->PS[ps].job = j;
+      o->PS[ps].min_available = s->podset_min_available[ps];
+      for (int t = s->podset_task_begin[ps]; t < s->podset_task_begin[ps + 1]; t++) {
+        o->PS[ps].tasks.push_back(t);
+        Task &tk = o->T[t];
+        tk.job = j;
+        tk.podset = ps;
+        tk.status = s->task_status[t];
+        tk.node = s->task_node[t];
+        for (int r = 0; r < o->R; r++) tk.req[r] = s->task_req[(size_t)t * o->R + r];
+        tk.order_rank = s->task_order_rank[t];
+        tk.nominated = s->task_nominated ? s->task_nominated[t] : -1;
+        tk.pred_class = s->task_pred_class ? s->task_pred_class[t] : -1;
+        tk.on_node = (tk.status & kActiveUsed) && tk.node >= 0;
+        tk.node_status = tk.status;
+        if (!tk.on_node && !(tk.status & kActiveUsed)) tk.node = -1;
+      }
+    }
+  }
+  o->pred_mask.clear();
+  if (s->pred_mask && o->NPC > 0)
+    o->pred_mask.assign(s->pred_mask, s->pred_mask + (size_t)o->NPC * o->mask_words);
+  o->open_session();
+  o->loaded = true;
+  o->pods_placed = o->pods_evicted = 0;
+  memset(&o->stats, 0, sizeof(o->stats));
+  return KAI_OK;
+}
+
+int kai_oracle_run(kai_oracle *o, kai_action action, kai_result *out) {
+  if (!o || !out) return KAI_ERR_INVALID;
+  if (!o->loaded) return KAI_ERR_STATE;
+  o->r_visits.clear();
+  o->pods_placed = o->pods_evicted = 0;
+  switch (action) {
+    case KAI_ACTION_ALLOCATE:
+      o->run_allocate();
+      break;
+    default:
+      o->err = "action not implemented by the oracle";
+      return KAI_ERR_UNSUPPORTED;
+  }
+  o->fill_result(out);
+  return KAI_OK;
+}
+
+int kai_oracle_fair_share(kai_oracle *o, kai_result *out) {
+  if (!o || !out) return KAI_ERR_INVALID;
+  if (!o->loaded) return KAI_ERR_STATE;
+  o->fill_result(out);
+  return KAI_OK;
+}
+
+int kai_oracle_stats(kai_oracle *o, kai_stats *out) {
+  if (!o || !out) return KAI_ERR_INVALID;
+  *out = o->stats;
+  out->algorithmic_bytes = o->stats.nodes_scanned * ((2 * o->R + 1) * 8 + 4);
+  return KAI_OK;
+}
+
+int kai_oracle_set_threads(kai_oracle *o, int n) {
+  if (!o || n < 1) return KAI_ERR_INVALID;
+  o->n_threads = n;
+  return KAI_OK;
+}
+
+void kai_oracle_destroy(kai_oracle *o) { delete o; }
+const char *kai_oracle_last_error(const kai_oracle *o) { return o ? o->err.c_str() : "null oracle"; }
+
+double kai_oracle_binpack_score(double mn, double mx, double cur, double overall) {
+  return binpack_score(mn, mx, cur, overall);
+}
+double kai_oracle_spread_score(double non_allocated, double count) { return spread_score(non_allocated, count); }
+
+double kai_oracle_set_resource_share(int n, double total, double k_value, const double *deserved,
+                                     const double *limit, const double *oqw, const double *request,
+                                     const double *usage, const int32_t *priority, const int64_t *creation,
+                                     const int32_t *uid_rank, double *fair_share) {
+  std::vector<QueueAttr> Q(n);
+  std::vector<int> group;
+  for (int i = 0; i < n; i++) {
+    Q[i].priority = priority[i];
+    Q[i].creation = creation[i];
+    Q[i].uid_rank = uid_rank[i];
+    Share &s = Q[i].s[0];
+    s.deserved = deserved[i];
+    s.max_allowed = limit[i];
+    s.oqw = oqw[i];
+    s.request = request[i];
+    s.usage = usage ? usage[i] : 0;
+    s.fair = fair_share[i];
+    group.push_back(i);
+  }
+  double rem = set_resource_share(total, k_value, Q, group, 0);
+  for (int i = 0; i < n; i++) fair_share[i] = Q[i].s[0].fair;
+  return rem;
+}
+
+int kai_oracle_queue_order(const double *l_share, const double *r_share, int l_priority, int r_priority,
+                           int64_t l_creation, int64_t r_creation, const double *l_job_req,
+                           const double *r_job_req, const double *total) {
+  QueueAttr l, r;
+  auto fill = [](QueueAttr &q, const double *s) {
+    for (int i = 0; i < QR; i++) {
+      q.s[i].deserved = s[i * 8 + 0];
+      q.s[i].fair = s[i * 8 + 1];
+      q.s[i].max_allowed = s[i * 8 + 2];
+      q.s[i].oqw = s[i * 8 + 3];
+      q.s[i].allocated = s[i * 8 + 4];
+      q.s[i].alloc_np = s[i * 8 + 5];
+      q.s[i].request = s[i * 8 + 6];
+      q.s[i].usage = s[i * 8 + 7];
+    }
+  };
+  fill(l, l_share);
+  fill(r, r_share);
+  l.priority = l_priority;
+  r.priority = r_priority;
+  l.creation = l_creation;
+  r.creation = r_creation;
+  return queue_order_result(l, r, l_job_req, r_job_req, nullptr, nullptr, total);
+}
+
+}  // extern "C"

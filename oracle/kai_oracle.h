@@ -1,0 +1,61 @@
+/*
+ * kai_oracle.h — C entry points of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+ *
+ * The oracle is a CPU restatement of the reference's per-Session scheduling
+ * cycle (NVIDIA/KAI-Scheduler, pkg/scheduler).  It consumes the same
+ * kai_snapshot / kai_config as libkaigpu.so (include/kai_engine.h) and returns
+ * a kai_result with identical meaning, so that tests can compare the CUDA
+ * engine with it field by field.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
+ * legs may load this library.  The product (kai_scheduler_b200/) never does.
+ */
+#ifndef KAI_ORACLE_H_
+#define KAI_ORACLE_H_
+#include "../include/kai_engine.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kai_oracle kai_oracle;
+
+int kai_oracle_create(const kai_config *cfg, kai_oracle **out);
+int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *snap);
+int kai_oracle_run(kai_oracle *o, kai_action action, kai_result *out);
+int kai_oracle_fair_share(kai_oracle *o, kai_result *out);
+int kai_oracle_stats(kai_oracle *o, kai_stats *out);
+/* threads used for the per-task node sweep (mirrors the reference's
+   goroutine-per-node fan-out, framework/session.go:243-262); 1 = scalar */
+int kai_oracle_set_threads(kai_oracle *o, int n_threads);
+void kai_oracle_destroy(kai_oracle *o);
+const char *kai_oracle_last_error(const kai_oracle *o);
+
+/* Known-answer hooks used by tests/ to pin the oracle against the
+   reference's own unit tests. */
+/* plugins/nodeplacement/pack.go:45-64 getScoreOfCurrentNode */
+double kai_oracle_binpack_score(double min_alloc, double max_alloc, double cur, double node_overall);
+/* plugins/nodeplacement/spread.go:16-36 */
+double kai_oracle_spread_score(double non_allocated, double resource_count);
+/* plugins/proportion/resource_division/resource_division.go:33-43 setResourceShare
+   on ONE sibling group and ONE resource; arrays of length n; fair_share is in/out.
+   returns the remaining amount. */
+double kai_oracle_set_resource_share(int n, double total, double k_value,
+                                     const double *deserved, const double *limit,
+                                     const double *oqw, const double *request,
+                                     const double *usage, const int32_t *priority,
+                                     const int64_t *creation, const int32_t *uid_rank,
+                                     double *fair_share);
+/* plugins/proportion/queue_order/queue_order.go:19-73 for two queues described by
+   8-field ResourceShare rows [3][8] = {Deserved,FairShare,MaxAllowed,OverQuotaWeight,
+   Allocated,AllocatedNotPreemptible,Request,Usage}; job requirement vectors [3].
+   returns -1 (l first) or 1 (r first). */
+int kai_oracle_queue_order(const double *l_share, const double *r_share,
+                           int l_priority, int r_priority,
+                           int64_t l_creation, int64_t r_creation,
+                           const double *l_job_req, const double *r_job_req,
+                           const double *total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,263 @@
+"""The reference's declarative test DSL -> SoA snapshot (test infrastructure).
+
+Mirrors pkg/scheduler/test_utils (reference @72de64fc): a `TestTopologyBasic`
+table (transcribed to JSON by tests/golden/gen_fixtures.py) is turned into the
+kai_snapshot the engine and the oracle consume, following the same rules as
+`test_utils.BuildSession` (test_utils_builder.go:260-289):
+
+  jobs    jobs_fake/jobs.go:53-98     stable sort by Priority desc; job i created now-(n-i) min;
+                                      UID = Name; preemptible iff priority < 100 unless explicit
+  tasks   jobs_fake/jobs.go:188-291   pod "<job>-<k>", UID = name; cpu default "1" (1000m),
+                                      memory default "1G"; pods = 1; best effort = empty request
+  nodes   nodes_fake/nodes.go:31-36,171-224   cpu "20000" cores-quantity = 2e7 m, memory "20G",
+                                      pods 110 (or MaxTaskNum), running tasks pre-added
+  queues  test_utils_builder.go:96-225        queue k created now+k min, CPU/memory quota/limit -1,
+                                      default department when none given
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from kai_scheduler_b200 import abi  # noqa: E402
+
+ACTIVE_USED = {"Allocated", "Pipelined", "Binding", "Bound", "Running", "Releasing"}
+DEFAULT_SUBGROUP = "default-sub-group"
+
+
+def _parse_quantity_cpu(cores: float) -> float:
+    return float(cores) * 1000.0
+
+
+def build_snapshot(topo: dict):
+    """Return (Snapshot, meta) for a transcribed TestTopologyBasic.
+
+    meta: node_names, job_names (snapshot order), task_names, task_job, queue_names.
+    """
+    topo = dict(topo)
+    queues = [dict(q) for q in (topo.get("Queues") or [])]
+    departments = [dict(d) for d in (topo.get("Departments") or [])]
+    # test_utils_builder.go:160-177 addDefaultDepartmentIfNeeded
+    if not departments and not topo.get("DisableDefaultDepartment"):
+        for q in queues:
+            q["ParentQueue"] = "default"
+        departments = [{"Name": "default", "DeservedGPUs": -1.0, "MaxAllowedGPUs": -1.0}]
+
+    # ---- queues (leaf queues first, then departments; creation = index minutes) ----
+    qnames, qparent, qprio, qcreate = [], [], [], []
+    qd, ql, qw = [], [], []
+    for k, q in enumerate(queues):
+        qnames.append(q["Name"])
+        qparent.append(q.get("ParentQueue") or "")
+        qprio.append(q["Priority"] if q.get("Priority") is not None else 100)
+        qcreate.append(k * 60)
+        max_gpu = q.get("MaxAllowedGPUs", 0) or 0
+        gpu_limit = max_gpu if max_gpu != 0 else -1.0
+        cpu_q = q["DeservedCPUs"] if q.get("DeservedCPUs") is not None else -1.0
+        mem_q = q["DeservedMemory"] if q.get("DeservedMemory") is not None else -1.0
+        cpu_l = q["MaxAllowedCPUs"] if q.get("MaxAllowedCPUs") is not None else -1.0
+        mem_l = q["MaxAllowedMemory"] if q.get("MaxAllowedMemory") is not None else -1.0
+        # proportion.go:48-50,327-328: memory quota/limit are in MB in the Queue CR
+        qd.append([cpu_q, max(-1.0, mem_q * 1e6), q.get("DeservedGPUs", 0) or 0])
+        ql.append([cpu_l, max(-1.0, mem_l * 1e6), gpu_limit])
+        qw.append([1.0, 1.0, q.get("GPUOverQuotaWeight", 0) or 0])
+    for d_i, d in enumerate(departments):
+        qnames.append(d["Name"])
+        qparent.append(d.get("ParentQueue") or "")
+        qprio.append(100)
+        qcreate.append(d_i * 60)
+        max_gpu = d.get("MaxAllowedGPUs", 0) or 0
+        gpu_limit = max_gpu if max_gpu != 0 else -1.0
+        cpu_l = d["MaxAllowedCPUs"] if d.get("MaxAllowedCPUs") is not None else -1.0
+        mem_l = d["MaxAllowedMemory"] if d.get("MaxAllowedMemory") is not None else -1.0
+        dg = d.get("DeservedGPUs", 0) or 0
+        qd.append([-1.0, -1.0, dg])
+        ql.append([cpu_l, max(-1.0, mem_l * 1e6), gpu_limit])
+        qw.append([1.0, 1.0, dg])  # department OverQuotaWeight = DeservedGPUs (:194-198)
+    qindex = {n: i for i, n in enumerate(qnames)}
+    Q = len(qnames)
+    # cache/cluster_info/queue.go:90-129 UpdateQueueHierarchy: orphans (missing parent) are deleted
+    parent_idx = []
+    for i in range(Q):
+        p = qparent[i]
+        parent_idx.append(qindex[p] if p in qindex else (-1 if p == "" else -2))
+    if any(p == -2 for p in parent_idx):
+        raise ValueError("queue with missing parent: unsupported in DSL")
+    uid_rank = np.argsort(np.argsort(np.array(qnames, dtype=object), kind="stable"), kind="stable")
+
+    # ---- nodes ----
+    node_names = sorted((topo.get("Nodes") or {}).keys())
+    nindex = {n: i for i, n in enumerate(node_names)}
+    N = len(node_names)
+    R = 4
+    alloc = np.zeros((R, N))
+    for n, name in enumerate(node_names):
+        nd = topo["Nodes"][name]
+        alloc[0, n] = float(nd["CPUMillis"]) * 1000.0 if (nd.get("CPUMillis") or 0) > 0 else 2e7
+        alloc[1, n] = float(nd["CPUMemory"]) if (nd.get("CPUMemory") or 0) > 0 else 2e10
+        alloc[2, n] = float(nd.get("GPUs", 0) or 0)
+        alloc[3, n] = float(nd["MaxTaskNum"]) if nd.get("MaxTaskNum") is not None else 110.0
+    idle = alloc.copy()
+    rel = np.zeros((R, N))
+    name_rank = np.arange(N, dtype=np.int32)  # node_names is already sorted byte-wise
+    flags = np.full(N, abi.NODE_READY, dtype=np.uint32)
+
+    # ---- jobs ----
+    jobs = [dict(j) for j in (topo.get("Jobs") or [])]
+    jobs.sort(key=lambda j: -(j.get("Priority", 0) or 0))  # stable, like sort.SliceStable
+    nj = len(jobs)
+    job_names, job_queue, job_prio, job_flags, job_creation = [], [], [], [], []
+    job_podset_begin = [0]
+    podset_min, podset_task_begin = [], [0]
+    t_status, t_node, t_req, t_rank, t_names, t_job = [], [], [], [], [], []
+    for ji, job in enumerate(jobs):
+        job_names.append(job["Name"])
+        job_queue.append(qindex.get(job.get("QueueName", ""), -1))
+        prio = int(job.get("Priority", 0) or 0)
+        job_prio.append(prio)
+        age = job.get("JobAgeInMinutes", 0) or 0
+        job_creation.append(-(age if age != 0 else (nj - ji)) * 60)
+        pre = job.get("Preemptibility") or ""
+        preemptible = pre == "preemptible" or (pre != "non-preemptible" and prio < 100)
+        job_flags.append(abi.JOB_PREEMPTIBLE if preemptible else 0)
+        tasks = job.get("Tasks") or []
+        # requests
+        if job.get("IsBestEffortJob"):
+            base = [0.0, 0.0, 0.0, 1.0]
+        else:
+            cpu = _parse_quantity_cpu(job["RequiredCPUsPerTask"]) if job.get("RequiredCPUsPerTask") else 1000.0
+            mem = float(job["RequiredMemoryPerTask"]) if job.get("RequiredMemoryPerTask") else 1e9
+            base = [cpu, mem, float(job.get("RequiredGPUsPerTask", 0) or 0), 1.0]
+        # podsets: jobs_fake.go:117-134
+        root = job.get("RootSubGroupSet")
+        if root:
+            podsets = [(p["name"], int(p["min_available"])) for p in root["podsets"]]
+        else:
+            podsets = []
+        names_in_sets = {p[0] for p in podsets}
+        if any(not t.get("SubGroupName") for t in tasks) and DEFAULT_SUBGROUP not in names_in_sets:
+            podsets.append((DEFAULT_SUBGROUP, len(tasks)))
+        podsets.sort(key=lambda p: p[0])  # PodSet name order (session_plugins.go:261-270 fallback)
+        if job.get("JobNotReadyForSsn"):
+            # integration tables: job exists but is not ready -> model as gated-like by min_available > tasks
+            podsets = [(n_, m_ + len(tasks) + 1) for n_, m_ in podsets]
+        # task order: TaskOrderFn = taskorder label priority desc, then creation (equal), then UID (pod name)
+        order_keys = []
+        for k, t in enumerate(tasks):
+            uid = f"{job['Name']}-{k}"
+            pr = t.get("Priority")
+            order_keys.append((0 if pr is not None else 1, -(pr or 0), uid, k))
+        order_rank = {k: r for r, (_, _, _, k) in enumerate(sorted(order_keys))}
+        for ps_name, ps_min in podsets:
+            podset_min.append(ps_min)
+            for k, t in enumerate(tasks):
+                sg = t.get("SubGroupName") or DEFAULT_SUBGROUP
+                if sg != ps_name:
+                    continue
+                st = t.get("State", "Pending")
+                t_status.append(abi.POD_STATUS_NAMES[st])
+                node = t.get("NodeName") or ""
+                t_node.append(nindex[node] if (st in ACTIVE_USED and node in nindex) else -1)
+                req = list(base)
+                if t.get("RequiredGPUs") is not None and not job.get("IsBestEffortJob"):
+                    req[2] = float(t["RequiredGPUs"])
+                t_req.append(req)
+                t_rank.append(order_rank[k])
+                t_names.append(f"{job['Name']}-{k}")
+                t_job.append(ji)
+            podset_task_begin.append(len(t_status))
+        job_podset_begin.append(len(podset_min))
+    # job order rank under (CreationTimestamp, UID)
+    order = sorted(range(nj), key=lambda i: (job_creation[i], job_names[i]))
+    job_order_rank = np.zeros(nj, dtype=np.int32)
+    for r, i in enumerate(order):
+        job_order_rank[i] = r
+
+    # ---- pre-place active-used tasks on nodes (node_info.go:457-493), sorted pod-key order is irrelevant for sums
+    T = len(t_status)
+    t_req_a = np.array(t_req, dtype=np.float64).reshape(T, R)
+    for t in range(T):
+        n = t_node[t]
+        if n < 0:
+            continue
+        st = t_status[t]
+        if st == abi.POD_RELEASING:
+            rel[:, n] += t_req_a[t]
+            idle[:, n] -= t_req_a[t]
+        elif st == abi.POD_PIPELINED:
+            rel[:, n] -= t_req_a[t]
+        else:
+            idle[:, n] -= t_req_a[t]
+    # nodes_fake.go:103-112: with MaxTaskNum the idle pods are clamped at 0
+    for n, name in enumerate(node_names):
+        if topo["Nodes"][name].get("MaxTaskNum") is not None and idle[3, n] < 0:
+            idle[3, n] = 0
+
+    snap = abi.Snapshot(
+        n_res=R,
+        node_allocatable=alloc, node_idle=idle, node_releasing=rel,
+        node_name_rank=name_rank, node_flags=flags,
+        queue_parent=np.array(parent_idx, dtype=np.int32), queue_priority=np.array(qprio, dtype=np.int32),
+        queue_creation=np.array(qcreate, dtype=np.int64), queue_uid_rank=uid_rank.astype(np.int32),
+        queue_deserved=np.array(qd, dtype=np.float64).reshape(Q, 3).T.copy(),
+        queue_limit=np.array(ql, dtype=np.float64).reshape(Q, 3).T.copy(),
+        queue_oqw=np.array(qw, dtype=np.float64).reshape(Q, 3).T.copy(),
+        job_queue=np.array(job_queue, dtype=np.int32), job_priority=np.array(job_prio, dtype=np.int32),
+        job_order_rank=job_order_rank, job_flags=np.array(job_flags, dtype=np.uint32),
+        job_podset_begin=np.array(job_podset_begin, dtype=np.int32),
+        podset_min_available=np.array(podset_min, dtype=np.int32),
+        podset_task_begin=np.array(podset_task_begin, dtype=np.int32),
+        task_status=np.array(t_status, dtype=np.int32), task_node=np.array(t_node, dtype=np.int32),
+        task_req=t_req_a, task_order_rank=np.array(t_rank, dtype=np.int32),
+    )
+    meta = {
+        "node_names": node_names, "job_names": job_names, "task_names": t_names,
+        "task_job": np.array(t_job, dtype=np.int32), "queue_names": qnames,
+    }
+    return snap, meta
+
+
+def check_expectations(topo: dict, meta: dict, res: "abi.Result", snap: "abi.Snapshot"):
+    """MatchExpectedAndRealTasks (test_utils.go:121-314) restated: returns a list of mismatch strings."""
+    errs = []
+    status_name = {v: k for k, v in abi.POD_STATUS_NAMES.items()}
+    tj = meta["task_job"]
+    for jname, exp in (topo.get("JobExpectedResults") or {}).items():
+        if jname not in meta["job_names"]:
+            errs.append(f"job {jname} missing")
+            continue
+        ji = meta["job_names"].index(jname)
+        gpus = 0.0
+        for t in np.nonzero(tj == ji)[0]:
+            st = status_name[int(res.task_status[t])]
+            if st != exp.get("Status"):
+                errs.append(f"job {jname} task {meta['task_names'][t]}: status {st}, expected {exp.get('Status')}")
+            want = exp.get("NodeName") or ""
+            got = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else ""
+            if want and got != want:
+                errs.append(f"job {jname} task {meta['task_names'][t]}: node {got!r}, expected {want!r}")
+            gpus += snap.task_req[t, 2]
+        if gpus != float(exp.get("GPUsRequired", 0) or 0):
+            errs.append(f"job {jname}: GPUsRequired {gpus} expected {exp.get('GPUsRequired')}")
+    for tname, exp in (topo.get("TaskExpectedResults") or {}).items():
+        if tname not in meta["task_names"]:
+            errs.append(f"task {tname} missing")
+            continue
+        t = meta["task_names"].index(tname)
+        st = status_name[int(res.task_status[t])]
+        if st != exp.get("Status"):
+            errs.append(f"task {tname}: status {st}, expected {exp.get('Status')}")
+        want = exp.get("NodeName") or ""
+        got = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else ""
+        if want and got != want:
+            errs.append(f"task {tname}: node {got!r}, expected {want!r}")
+    for nname, exp in (topo.get("ExpectedNodesResources") or {}).items():
+        n = meta["node_names"].index(nname)
+        if res.node_idle[2, n] != float(exp.get("IdleGPUs", 0) or 0):
+            errs.append(f"node {nname}: idle GPUs {res.node_idle[2, n]} expected {exp.get('IdleGPUs')}")
+        if res.node_releasing[2, n] != float(exp.get("ReleasingGPUs", 0) or 0):
+            errs.append(f"node {nname}: releasing GPUs {res.node_releasing[2, n]} expected {exp.get('ReleasingGPUs')}")
+    return errs
