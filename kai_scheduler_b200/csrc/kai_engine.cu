@@ -1,0 +1,688 @@
+// kai_engine.cu — host side of libkaigpu.so: the C ABI declared in include/kai_engine.h.
+//
+// Validates the caller's SoA snapshot, derives the index structures the kernels need (queue
+// children CSR, jobs grouped by leaf queue in JobOrderFn order, tasks per podset in TaskOrderFn
+// order, name-rank inverse), stages everything through one pinned buffer into HBM, runs the
+// open-session kernels and the persistent action kernel, and copies results back.
+//
+// There is NO CPU fallback: without a usable CUDA device kai_engine_create fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "kai_device.cuh"
+#include "kai_kernels.cuh"  // single translation unit: kernels + host API
+
+using namespace kai;
+
+namespace {
+
+// Simple device bump arena: one cudaMalloc per snapshot generation.
+struct DeviceArena {
+  unsigned char *base = nullptr;
+  size_t cap = 0, off = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) {
+      off = 0;
+      return cudaSuccess;
+    }
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&base, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    off = 0;
+    return e;
+  }
+  template <class T>
+  T *take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T *p = (T *)(base + off);
+    off += bytes;
+    return p;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = 0;
+  }
+};
+
+struct Staging {  // pinned host staging buffer mirrored 1:1 onto a device arena region
+  unsigned char *host = nullptr;
+  size_t cap = 0, off = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) {
+      off = 0;
+      return cudaSuccess;
+    }
+    if (host) cudaFreeHost(host);
+    host = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&host, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    off = 0;
+    return e;
+  }
+  void release() {
+    if (host) cudaFreeHost(host);
+    host = nullptr;
+    cap = off = 0;
+  }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+}  // namespace
+
+struct kai_engine {
+  kai_config cfg;
+  std::string err;
+  int device = 0;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool loaded = false;
+
+  DeviceArena dsnap;     // snapshot + session state
+  Staging stage;         // pinned mirror of the uploaded part of dsnap
+  DeviceArena dreplica;  // replica arenas
+  DeviceArena dmisc;     // exchange buffers, counters, visits, fair-share scratch
+  DevSnap ds;
+  int R = 4, N = 0, Q = 0, J = 0, S = 0, T = 0;
+  int grid = 0, npc = 0;
+  size_t smem_bytes = 0, replica_bytes = 0;
+  int ops_cap = 0, visits_cap = 0;
+  unsigned long long *xbuf = nullptr, *mmbuf = nullptr;
+  long long *counters = nullptr;
+  kai_job_visit *d_visits = nullptr;
+  double *fs_w = nullptr, *fs_rr = nullptr;
+  unsigned int seq = 2;
+
+  // host result buffers (pinned)
+  Staging rstage;
+  std::vector<int32_t> r_task_node, r_task_status;
+  std::vector<kai_job_visit> r_visits;
+  std::vector<double> r_fair, r_alloc, r_alloc_np, r_request, r_idle, r_rel;
+  double r_total[3] = {0, 0, 0};
+  kai_stats stats;
+
+  int fail(int code, const std::string &m) {
+    err = m;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char *what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return KAI_ERR_CUDA;
+  }
+};
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t _e = (call);                       \
+    if (_e != cudaSuccess) return e->cuda_fail(_e, #call); \
+  } while (0)
+
+extern "C" {
+
+int kai_abi_version(void) { return KAI_ABI_VERSION; }
+
+int kai_engine_create(const kai_config *cfg, kai_engine **out) {
+  if (!cfg || !out) return KAI_ERR_INVALID;
+  if (cfg->abi_version != KAI_ABI_VERSION) return KAI_ERR_INVALID;
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev <= 0 || cfg->device < 0 || cfg->device >= n_dev) return KAI_ERR_NO_DEVICE;
+  kai_engine *e = new kai_engine();
+  e->cfg = *cfg;
+  if (e->cfg.shard_count < 1) e->cfg.shard_count = 1;
+  e->device = cfg->device;
+  memset(&e->stats, 0, sizeof(e->stats));
+  if (cudaSetDevice(e->device) != cudaSuccess) {
+    delete e;
+    return KAI_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, e->device) != cudaSuccess) {
+    delete e;
+    return KAI_ERR_NO_DEVICE;
+  }
+  if (prop.major < 10) {  // sm_100a cubin only
+    delete e;
+    return KAI_ERR_NO_DEVICE;
+  }
+  e->num_sms = prop.multiProcessorCount;
+  e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return KAI_ERR_CUDA;
+  }
+  for (auto &ev : e->ev) cudaEventCreate(&ev);
+  *out = e;
+  return KAI_OK;
+}
+
+void kai_engine_destroy(kai_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  e->dsnap.release();
+  e->dreplica.release();
+  e->dmisc.release();
+  e->stage.release();
+  e->rstage.release();
+  for (auto &ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char *kai_last_error(const kai_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
+  if (!e || !s) return KAI_ERR_INVALID;
+  if (s->abi_version != KAI_ABI_VERSION) return e->fail(KAI_ERR_INVALID, "snapshot abi_version mismatch");
+  if (s->n_res < 4 || s->n_res > KAI_MAX_RES) return e->fail(KAI_ERR_INVALID, "n_res out of range");
+  if (s->n_nodes < 0 || s->n_queues < 0 || s->n_jobs < 0 || s->n_podsets < 0 || s->n_tasks < 0)
+    return e->fail(KAI_ERR_INVALID, "negative count");
+  if (!s->node_allocatable || !s->node_idle || !s->node_releasing || !s->node_name_rank || !s->node_flags)
+    if (s->n_nodes > 0) return e->fail(KAI_ERR_INVALID, "null node table");
+  CK(cudaSetDevice(e->device));
+  e->loaded = false;
+  const int R = s->n_res, N = s->n_nodes, Q = s->n_queues, J = s->n_jobs, S = s->n_podsets, T = s->n_tasks;
+  e->R = R;
+  e->N = N;
+  e->Q = Q;
+  e->J = J;
+  e->S = S;
+  e->T = T;
+  const int NPC = s->n_pred_classes;
+  const int mask_words = (N + 31) / 32;
+
+  // ---------------- host-side derived index structures ----------------
+  std::vector<int> rank_to_node(N, -1);
+  for (int n = 0; n < N; n++) {
+    int rk = s->node_name_rank[n];
+    if (rk < 0 || rk >= N || rank_to_node[rk] != -1) return e->fail(KAI_ERR_INVALID, "node_name_rank is not a permutation");
+    rank_to_node[rk] = n;
+  }
+  std::vector<int> q_nchildren(Q, 0), q_child_begin(Q + 1, 0), q_children(std::max(Q, 1), 0), top;
+  for (int q = 0; q < Q; q++) {
+    int p = s->queue_parent[q];
+    if (p >= Q || p == q || p < -1) return e->fail(KAI_ERR_INVALID, "bad queue_parent");
+    if (p >= 0)
+      q_nchildren[p]++;
+    else
+      top.push_back(q);
+  }
+  for (int q = 0; q < Q; q++) q_child_begin[q + 1] = q_child_begin[q] + q_nchildren[q];
+  {
+    std::vector<int> fill(q_child_begin.begin(), q_child_begin.end() - 1);
+    for (int q = 0; q < Q; q++) {
+      int p = s->queue_parent[q];
+      if (p >= 0) q_children[fill[p]++] = q;
+    }
+  }
+  // levels for the fair-share recursion (proportion.go:410-423): level 0 = {top group}
+  std::vector<int> level_group_begin{0}, level_groups;
+  {
+    std::vector<int> cur{-1};
+    int depth = 0;
+    while (!cur.empty()) {
+      if (++depth > KAI_MAX_QUEUE_DEPTH + 1) return e->fail(KAI_ERR_INVALID, "queue hierarchy too deep or cyclic");
+      std::vector<int> next;
+      for (int g : cur) {
+        level_groups.push_back(g);
+        if (g < 0) {
+          for (int q : top)
+            if (q_nchildren[q] > 0) next.push_back(q);
+        } else {
+          for (int k = q_child_begin[g]; k < q_child_begin[g + 1]; k++)
+            if (q_nchildren[q_children[k]] > 0) next.push_back(q_children[k]);
+        }
+      }
+      level_group_begin.push_back((int)level_groups.size());
+      cur.swap(next);
+    }
+  }
+  const int n_levels = (int)level_group_begin.size() - 1;
+  // jobs grouped by leaf queue, in (priority desc, order_rank) order
+  std::vector<int> q_job_begin(Q + 1, 0), q_jobs_sorted(std::max(J, 1), 0);
+  {
+    std::vector<int> cnt(Q, 0);
+    for (int j = 0; j < J; j++) {
+      int q = s->job_queue[j];
+      if (q >= Q) return e->fail(KAI_ERR_INVALID, "bad job_queue");
+      if (q < 0 || q_nchildren[q] != 0) continue;  // input_jobs.go:47-63
+      int p = s->queue_parent[q];
+      (void)p;
+      cnt[q]++;
+    }
+    for (int q = 0; q < Q; q++) q_job_begin[q + 1] = q_job_begin[q] + cnt[q];
+    std::vector<int> fill(q_job_begin.begin(), q_job_begin.end() - 1);
+    for (int j = 0; j < J; j++) {
+      int q = s->job_queue[j];
+      if (q < 0 || q_nchildren[q] != 0) continue;
+      q_jobs_sorted[fill[q]++] = j;
+    }
+    for (int q = 0; q < Q; q++)
+      std::sort(q_jobs_sorted.begin() + q_job_begin[q], q_jobs_sorted.begin() + q_job_begin[q + 1], [&](int a, int b) {
+        if (s->job_priority[a] != s->job_priority[b]) return s->job_priority[a] > s->job_priority[b];
+        return s->job_order_rank[a] < s->job_order_rank[b];
+      });
+  }
+  // podsets / tasks
+  std::vector<int> ps_job(std::max(S, 1), 0), t_job(std::max(T, 1), 0), t_podset(std::max(T, 1), 0),
+      ps_sorted_tasks(std::max(T, 1), 0);
+  int max_job_tasks = 1, max_job_podsets = 1;
+  for (int j = 0; j < J; j++) {
+    int b = s->job_podset_begin[j], en = s->job_podset_begin[j + 1];
+    if (b < 0 || en < b || en > S) return e->fail(KAI_ERR_INVALID, "bad job_podset_begin");
+    max_job_podsets = std::max(max_job_podsets, en - b);
+    int nt = 0;
+    for (int ps = b; ps < en; ps++) {
+      ps_job[ps] = j;
+      int tb = s->podset_task_begin[ps], te = s->podset_task_begin[ps + 1];
+      if (tb < 0 || te < tb || te > T) return e->fail(KAI_ERR_INVALID, "bad podset_task_begin");
+      nt += te - tb;
+      for (int t = tb; t < te; t++) {
+        t_job[t] = j;
+        t_podset[t] = ps;
+        ps_sorted_tasks[t] = t;
+      }
+      std::sort(ps_sorted_tasks.begin() + tb, ps_sorted_tasks.begin() + te,
+                [&](int a, int b2) { return s->task_order_rank[a] < s->task_order_rank[b2]; });
+    }
+    max_job_tasks = std::max(max_job_tasks, nt);
+  }
+  if (J > 0 && (s->job_podset_begin[0] != 0 || s->job_podset_begin[J] != S))
+    return e->fail(KAI_ERR_INVALID, "job_podset_begin must cover all podsets");
+  if (S > 0 && (s->podset_task_begin[0] != 0 || s->podset_task_begin[S] != T))
+    return e->fail(KAI_ERR_INVALID, "podset_task_begin must cover all tasks");
+  for (int t = 0; t < T; t++) {
+    int n = s->task_node[t];
+    if (n >= N) return e->fail(KAI_ERR_INVALID, "bad task_node");
+    if ((s->task_status[t] & kActiveUsed) && n < 0) return e->fail(KAI_ERR_INVALID, "active task without node");
+  }
+
+  // ---------------- layout of the device arena (upload region first, then device-only) ----------------
+  cudaEventRecord(e->ev[0], e->stream);
+  size_t up = 0;
+  auto reserve_up = [&](size_t bytes) {
+    size_t o = up;
+    up += align_up(bytes, 256);
+    return o;
+  };
+  const size_t RN = (size_t)R * N, QN = (size_t)QR * Q;
+  size_t o_alloc = reserve_up(RN * 8), o_idle = reserve_up(RN * 8), o_rel = reserve_up(RN * 8);
+  size_t o_rank = reserve_up((size_t)N * 4), o_r2n = reserve_up((size_t)N * 4), o_nflags = reserve_up((size_t)N * 4);
+  size_t o_gpuc = reserve_up((size_t)N * 8);
+  size_t o_foreign = s->node_foreign ? reserve_up((size_t)3 * N * 8) : 0;
+  size_t o_qparent = reserve_up((size_t)Q * 4), o_qprio = reserve_up((size_t)Q * 4), o_quid = reserve_up((size_t)Q * 4);
+  size_t o_qnch = reserve_up((size_t)Q * 4), o_qcreate = reserve_up((size_t)Q * 8);
+  size_t o_qdes = reserve_up(QN * 8), o_qlim = reserve_up(QN * 8), o_qoqw = reserve_up(QN * 8);
+  size_t o_quse = s->queue_usage ? reserve_up(QN * 8) : 0;
+  size_t o_qcb = reserve_up((size_t)(Q + 1) * 4), o_qch = reserve_up((size_t)std::max(Q, 1) * 4);
+  size_t o_top = reserve_up((size_t)std::max((int)top.size(), 1) * 4);
+  size_t o_lgb = reserve_up(level_group_begin.size() * 4), o_lg = reserve_up(std::max<size_t>(level_groups.size(), 1) * 4);
+  size_t o_qjb = reserve_up((size_t)(Q + 1) * 4), o_qjs = reserve_up((size_t)std::max(J, 1) * 4);
+  size_t o_jq = reserve_up((size_t)std::max(J, 1) * 4), o_jp = reserve_up((size_t)std::max(J, 1) * 4);
+  size_t o_jor = reserve_up((size_t)std::max(J, 1) * 4), o_jfl = reserve_up((size_t)std::max(J, 1) * 4);
+  size_t o_jpb = reserve_up((size_t)(J + 1) * 4);
+  size_t o_psmin = reserve_up((size_t)std::max(S, 1) * 4), o_pstb = reserve_up((size_t)(S + 1) * 4);
+  size_t o_psjob = reserve_up((size_t)std::max(S, 1) * 4), o_psst = reserve_up((size_t)std::max(T, 1) * 4);
+  size_t o_treq = reserve_up((size_t)std::max(T, 1) * R * 8);
+  size_t o_tjob = reserve_up((size_t)std::max(T, 1) * 4), o_tps = reserve_up((size_t)std::max(T, 1) * 4);
+  size_t o_tnom = s->task_nominated ? reserve_up((size_t)std::max(T, 1) * 4) : 0;
+  size_t o_tpc = s->task_pred_class ? reserve_up((size_t)std::max(T, 1) * 4) : 0;
+  size_t o_tst = reserve_up((size_t)std::max(T, 1) * 4), o_tnode = reserve_up((size_t)std::max(T, 1) * 4);
+  size_t o_tnst = reserve_up((size_t)std::max(T, 1) * 4);
+  size_t o_mask = (s->pred_mask && NPC > 0) ? reserve_up((size_t)NPC * mask_words * 4) : 0;
+  const size_t upload_bytes = up;
+  // device-only region
+  size_t o_tvirt = reserve_up((size_t)std::max(T, 1));
+  size_t o_qfair = reserve_up(QN * 8), o_qreq = reserve_up(QN * 8), o_qal = reserve_up(QN * 8), o_qalnp = reserve_up(QN * 8);
+  size_t o_total = reserve_up(3 * 8);
+  const size_t zero_begin = o_tvirt, zero_bytes = up - o_tvirt;
+
+  CK(e->dsnap.reserve(up + 256));
+  CK(e->stage.reserve(upload_bytes + 256));
+  unsigned char *h = e->stage.host;
+  unsigned char *d = e->dsnap.base;
+  auto put = [&](size_t off, const void *src, size_t bytes) {
+    if (bytes) memcpy(h + off, src, bytes);
+  };
+  put(o_alloc, s->node_allocatable, RN * 8);
+  put(o_idle, s->node_idle, RN * 8);
+  put(o_rel, s->node_releasing, RN * 8);
+  put(o_rank, s->node_name_rank, (size_t)N * 4);
+  put(o_r2n, rank_to_node.data(), (size_t)N * 4);
+  put(o_nflags, s->node_flags, (size_t)N * 4);
+  if (s->node_gpu_count)
+    put(o_gpuc, s->node_gpu_count, (size_t)N * 8);
+  else
+    put(o_gpuc, s->node_allocatable + (size_t)KAI_RES_GPU * N, (size_t)N * 8);
+  if (s->node_foreign) put(o_foreign, s->node_foreign, (size_t)3 * N * 8);
+  put(o_qparent, s->queue_parent, (size_t)Q * 4);
+  put(o_qprio, s->queue_priority, (size_t)Q * 4);
+  put(o_quid, s->queue_uid_rank, (size_t)Q * 4);
+  put(o_qnch, q_nchildren.data(), (size_t)Q * 4);
+  put(o_qcreate, s->queue_creation, (size_t)Q * 8);
+  put(o_qdes, s->queue_deserved, QN * 8);
+  put(o_qlim, s->queue_limit, QN * 8);
+  put(o_qoqw, s->queue_oqw, QN * 8);
+  if (s->queue_usage) put(o_quse, s->queue_usage, QN * 8);
+  put(o_qcb, q_child_begin.data(), (size_t)(Q + 1) * 4);
+  put(o_qch, q_children.data(), (size_t)Q * 4);
+  put(o_top, top.data(), top.size() * 4);
+  put(o_lgb, level_group_begin.data(), level_group_begin.size() * 4);
+  put(o_lg, level_groups.data(), level_groups.size() * 4);
+  put(o_qjb, q_job_begin.data(), (size_t)(Q + 1) * 4);
+  put(o_qjs, q_jobs_sorted.data(), (size_t)J * 4);
+  put(o_jq, s->job_queue, (size_t)J * 4);
+  put(o_jp, s->job_priority, (size_t)J * 4);
+  put(o_jor, s->job_order_rank, (size_t)J * 4);
+  put(o_jfl, s->job_flags, (size_t)J * 4);
+  put(o_jpb, s->job_podset_begin, (size_t)(J + 1) * 4);
+  put(o_psmin, s->podset_min_available, (size_t)S * 4);
+  put(o_pstb, s->podset_task_begin, (size_t)(S + 1) * 4);
+  put(o_psjob, ps_job.data(), (size_t)S * 4);
+  put(o_psst, ps_sorted_tasks.data(), (size_t)T * 4);
+  put(o_treq, s->task_req, (size_t)T * R * 8);
+  put(o_tjob, t_job.data(), (size_t)T * 4);
+  put(o_tps, t_podset.data(), (size_t)T * 4);
+  if (s->task_nominated) put(o_tnom, s->task_nominated, (size_t)T * 4);
+  if (s->task_pred_class) put(o_tpc, s->task_pred_class, (size_t)T * 4);
+  put(o_tst, s->task_status, (size_t)T * 4);
+  {
+    int *tn = (int *)(h + o_tnode);
+    for (int t = 0; t < T; t++) tn[t] = (s->task_status[t] & kActiveUsed) ? s->task_node[t] : -1;
+  }
+  put(o_tnst, s->task_status, (size_t)T * 4);
+  if (o_mask || (s->pred_mask && NPC > 0)) put(o_mask, s->pred_mask, (size_t)NPC * mask_words * 4);
+
+  CK(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemsetAsync(d + zero_begin, 0, zero_bytes, e->stream));
+  cudaEventRecord(e->ev[1], e->stream);
+
+  DevSnap &ds = e->ds;
+  memset(&ds, 0, sizeof(ds));
+  ds.R = R;
+  ds.N = N;
+  ds.Q = Q;
+  ds.J = J;
+  ds.S = S;
+  ds.T = T;
+  ds.NPC = NPC;
+  ds.mask_words = mask_words;
+  ds.n_top = (int)top.size();
+  ds.max_job_tasks = max_job_tasks;
+  ds.max_job_podsets = max_job_podsets;
+  ds.n_levels = n_levels;
+  ds.alloc = (const double *)(d + o_alloc);
+  ds.idle = (double *)(d + o_idle);
+  ds.rel = (double *)(d + o_rel);
+  ds.name_rank = (const int *)(d + o_rank);
+  ds.rank_to_node = (const int *)(d + o_r2n);
+  ds.nflags = (const uint32_t *)(d + o_nflags);
+  ds.gpu_count = (const double *)(d + o_gpuc);
+  ds.foreign = s->node_foreign ? (const double *)(d + o_foreign) : nullptr;
+  ds.q_parent = (const int *)(d + o_qparent);
+  ds.q_priority = (const int *)(d + o_qprio);
+  ds.q_uid_rank = (const int *)(d + o_quid);
+  ds.q_nchildren = (const int *)(d + o_qnch);
+  ds.q_creation = (const long long *)(d + o_qcreate);
+  ds.q_deserved = (const double *)(d + o_qdes);
+  ds.q_limit = (const double *)(d + o_qlim);
+  ds.q_oqw = (const double *)(d + o_qoqw);
+  ds.q_usage = s->queue_usage ? (const double *)(d + o_quse) : nullptr;
+  ds.q_fair = (double *)(d + o_qfair);
+  ds.q_request = (double *)(d + o_qreq);
+  ds.q_alloc = (double *)(d + o_qal);
+  ds.q_alloc_np = (double *)(d + o_qalnp);
+  ds.q_child_begin = (const int *)(d + o_qcb);
+  ds.q_children = (const int *)(d + o_qch);
+  ds.top_queues = (const int *)(d + o_top);
+  ds.level_group_begin = (const int *)(d + o_lgb);
+  ds.level_groups = (const int *)(d + o_lg);
+  ds.q_job_begin = (const int *)(d + o_qjb);
+  ds.q_jobs_sorted = (const int *)(d + o_qjs);
+  ds.j_queue = (const int *)(d + o_jq);
+  ds.j_priority = (const int *)(d + o_jp);
+  ds.j_order_rank = (const int *)(d + o_jor);
+  ds.j_flags = (const uint32_t *)(d + o_jfl);
+  ds.j_ps_begin = (const int *)(d + o_jpb);
+  ds.ps_min = (const int *)(d + o_psmin);
+  ds.ps_task_begin = (const int *)(d + o_pstb);
+  ds.ps_job = (const int *)(d + o_psjob);
+  ds.ps_sorted_tasks = (const int *)(d + o_psst);
+  ds.t_req = (const double *)(d + o_treq);
+  ds.t_job = (const int *)(d + o_tjob);
+  ds.t_podset = (const int *)(d + o_tps);
+  ds.t_nominated = s->task_nominated ? (const int *)(d + o_tnom) : nullptr;
+  ds.t_pred_class = s->task_pred_class ? (const int *)(d + o_tpc) : nullptr;
+  ds.t_status = (int *)(d + o_tst);
+  ds.t_node = (int *)(d + o_tnode);
+  ds.t_node_status = (int *)(d + o_tnst);
+  ds.t_virtual = (unsigned char *)(d + o_tvirt);
+  ds.pred_mask = (s->pred_mask && NPC > 0) ? (const uint32_t *)(d + o_mask) : nullptr;
+  ds.total = (double *)(d + o_total);
+
+  // ---------------- launch geometry of the action kernel ----------------
+  int grid = std::min(e->num_sms, kMaxGrid);
+  if (const char *g = getenv("KAI_GRID")) {
+    int v = atoi(g);
+    if (v >= 1) grid = std::min(v, grid);
+  }
+  if (N > 0) grid = std::min(grid, N);  // at least one node per CTA when possible
+  grid = std::max(grid, 1);
+  if (const char *g = getenv("KAI_GRID_EXACT")) {  // tests: force CTAs without nodes as well
+    int v = atoi(g);
+    if (v >= 1) grid = std::min(std::min(v, e->num_sms), kMaxGrid);
+  }
+  int npc = std::max(1, (N + grid - 1) / grid);
+  npc = (npc + 1) & ~1;  // keep the int arrays 8-byte aligned
+  size_t smem = (size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4);
+  if (smem > (size_t)e->max_smem_optin - 4096)
+    return e->fail(KAI_ERR_UNSUPPORTED, "node tile does not fit in shared memory (N too large for one GPU tile)");
+  e->grid = grid;
+  e->npc = npc;
+  e->smem_bytes = smem;
+  e->ops_cap = 4 * max_job_tasks + 64;
+  e->visits_cap = std::max(16, 2 * J + T + 16);
+  {  // replica layout — must match the carving in k_action
+    size_t b = 0;
+    auto take = [&](size_t bytes) { b += (bytes + 15) & ~(size_t)15; };
+    take(sizeof(double) * QR * Q);
+    take(sizeof(double) * QR * Q);
+    take(sizeof(int) * (size_t)T);
+    take(sizeof(int) * (size_t)T);
+    take(sizeof(int) * (size_t)T);
+    take((size_t)T);
+    take(sizeof(int) * (size_t)S);
+    take(sizeof(double) * QR * (size_t)J);
+    take((size_t)J);
+    take(sizeof(int) * (size_t)J);
+    take(sizeof(int) * (size_t)Q);
+    take(sizeof(int) * (size_t)Q);
+    take(sizeof(int) * (size_t)Q);
+    take(sizeof(int) * (size_t)(ds.n_top + 1));
+    take((size_t)Q);
+    take(sizeof(Op) * (size_t)e->ops_cap);
+    take(sizeof(int) * (size_t)(max_job_tasks + 1));
+    take(sizeof(int) * (size_t)(max_job_podsets + 1));
+    e->replica_bytes = align_up(b, 256);
+  }
+  CK(e->dreplica.reserve(e->replica_bytes * grid + 256));
+  {
+    size_t xb = (size_t)2 * kMaxGrid * 8 * 8;
+    size_t misc = 2 * xb + 256 + sizeof(long long) * 16 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096;
+    CK(e->dmisc.reserve(misc));
+    e->xbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
+    e->mmbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
+    e->counters = e->dmisc.take<long long>(16);
+    e->d_visits = e->dmisc.take<kai_job_visit>(e->visits_cap);
+    e->fs_w = e->dmisc.take<double>(QN + 1);
+    e->fs_rr = e->dmisc.take<double>(QN + 1);
+    CK(cudaMemsetAsync(e->xbuf, 0, xb, e->stream));
+    CK(cudaMemsetAsync(e->mmbuf, 0, xb, e->stream));
+    e->seq = 2;
+  }
+
+  // ---------------- open session: totals, queue usage, fair share ----------------
+  if (N > 0) {
+    int blocks = std::min(e->num_sms * 4, (N + 255) / 256);
+    k_node_totals<<<blocks, 256, 0, e->stream>>>(ds);
+  }
+  if (T > 0) {
+    int blocks = std::min(e->num_sms * 8, (T + 255) / 256);
+    k_queue_usage<<<blocks, 256, 0, e->stream>>>(ds);
+  }
+  if (Q > 0) k_fair_share<<<1, 1024, 0, e->stream>>>(ds, e->cfg.k_value, e->fs_w, e->fs_rr);
+  cudaEventRecord(e->ev[2], e->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+  e->stats.upload_ms = ms;
+  cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]);
+  e->stats.open_session_ms = ms;
+  e->stats.kernel_launches = (N > 0) + (T > 0) + (Q > 0);
+  e->stats.action_ms = 0;
+  e->stats.download_ms = 0;
+  e->stats.decisions = e->stats.nodes_scanned = e->stats.algorithmic_bytes = 0;
+
+  // result buffers
+  e->r_task_node.assign(T, -1);
+  e->r_task_status.assign(T, 0);
+  e->r_fair.assign(QN, 0);
+  e->r_alloc.assign(QN, 0);
+  e->r_alloc_np.assign(QN, 0);
+  e->r_request.assign(QN, 0);
+  e->r_idle.assign(RN, 0);
+  e->r_rel.assign(RN, 0);
+  e->r_visits.clear();
+  e->loaded = true;
+  return KAI_OK;
+}
+
+static int download(kai_engine *e, kai_result *out, long long n_visits, long long placed, long long evicted) {
+  const DevSnap &ds = e->ds;
+  const size_t QN = (size_t)QR * e->Q, RN = (size_t)e->R * e->N;
+  cudaEventRecord(e->ev[4], e->stream);
+  CK(cudaMemcpyAsync(e->r_task_node.data(), ds.t_node, (size_t)e->T * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_task_status.data(), ds.t_status, (size_t)e->T * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_fair.data(), ds.q_fair, QN * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_alloc.data(), ds.q_alloc, QN * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_alloc_np.data(), ds.q_alloc_np, QN * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_request.data(), ds.q_request, QN * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_idle.data(), ds.idle, RN * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_rel.data(), ds.rel, RN * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_total, ds.total, 3 * 8, cudaMemcpyDeviceToHost, e->stream));
+  long long nv = std::min<long long>(n_visits, e->visits_cap);
+  e->r_visits.resize((size_t)nv);
+  if (nv > 0)
+    CK(cudaMemcpyAsync(e->r_visits.data(), e->d_visits, (size_t)nv * sizeof(kai_job_visit), cudaMemcpyDeviceToHost,
+                       e->stream));
+  cudaEventRecord(e->ev[5], e->stream);
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
+  e->stats.download_ms = ms;
+  memset(out, 0, sizeof(*out));
+  out->n_tasks = e->T;
+  out->task_node = e->r_task_node.data();
+  out->task_status = e->r_task_status.data();
+  out->n_visits = (int)nv;
+  out->visits = e->r_visits.data();
+  out->n_queues = e->Q;
+  out->queue_fair_share = e->r_fair.data();
+  out->queue_allocated = e->r_alloc.data();
+  out->queue_allocated_non_preemptible = e->r_alloc_np.data();
+  out->queue_request = e->r_request.data();
+  out->total_resource = e->r_total;
+  out->n_nodes = e->N;
+  out->node_idle = e->r_idle.data();
+  out->node_releasing = e->r_rel.data();
+  out->pods_placed = placed;
+  out->pods_evicted = evicted;
+  return KAI_OK;
+}
+
+int kai_engine_fair_share(kai_engine *e, kai_result *out) {
+  if (!e || !out) return KAI_ERR_INVALID;
+  if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
+  CK(cudaSetDevice(e->device));
+  return download(e, out, 0, 0, 0);
+}
+
+int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
+  if (!e || !out) return KAI_ERR_INVALID;
+  if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
+  if (action != KAI_ACTION_ALLOCATE) return e->fail(KAI_ERR_UNSUPPORTED, "action not implemented on device yet");
+  if (e->cfg.shard_count != 1) return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU sharding not wired");
+  CK(cudaSetDevice(e->device));
+  ActionParams p;
+  memset(&p, 0, sizeof(p));
+  p.s = e->ds;
+  p.cfg = e->cfg;
+  p.action = (int)action;
+  p.grid = e->grid;
+  p.nodes_per_cta = e->npc;
+  p.node_base = 0;
+  p.node_count = e->N;
+  p.replica_arena = e->dreplica.base;
+  p.replica_bytes = e->replica_bytes;
+  p.ops_cap = e->ops_cap;
+  p.xbuf = e->xbuf;
+  p.mmbuf = e->mmbuf;
+  p.visits = e->d_visits;
+  p.visits_cap = e->visits_cap;
+  p.counters = e->counters;
+  p.seq0 = e->seq;
+  CK(cudaFuncSetAttribute(k_action, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+  int max_blocks = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_action, kThreads, e->smem_bytes));
+  if (max_blocks < 1 || max_blocks * e->num_sms < e->grid)
+    return e->fail(KAI_ERR_CUDA, "action kernel cannot be made co-resident");
+  void *args[] = {(void *)&p};
+  CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 16, e->stream));
+  cudaEventRecord(e->ev[2], e->stream);
+  CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
+  cudaEventRecord(e->ev[3], e->stream);
+  long long c[16];
+  CK(cudaMemcpyAsync(c, e->counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]);
+  e->stats.action_ms = ms;
+  e->stats.decisions = c[1];
+  e->stats.nodes_scanned = c[2];
+  e->stats.algorithmic_bytes = c[2] * ((2 * e->R + 1) * 8 + 4);
+  e->stats.kernel_launches += 1;
+  e->seq = (unsigned int)c[7];
+  if (c[6] != 0) return e->fail(KAI_ERR_CUDA, "device sequencer overflow (statement log)");
+  return download(e, out, c[0], c[3], c[4]);
+}
+
+int kai_engine_stats(kai_engine *e, kai_stats *out) {
+  if (!e || !out) return KAI_ERR_INVALID;
+  *out = e->stats;
+  return KAI_OK;
+}
+
+int kai_engine_export_peer_handle(kai_engine *e, uint8_t handle[KAI_PEER_HANDLE_BYTES]) {
+  if (!e || !handle) return KAI_ERR_INVALID;
+  return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU sharding not wired");
+}
+int kai_engine_wire_peers(kai_engine *e, const uint8_t *handles) {
+  if (!e || !handles) return KAI_ERR_INVALID;
+  return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU sharding not wired");
+}
+
+}  // extern "C"

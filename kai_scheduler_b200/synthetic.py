@@ -1,0 +1,127 @@
+"""Synthetic cluster snapshots of the shapes BASELINE.json names.
+
+Vectorised restatement of the reference's benchmark topology builders
+(pkg/scheduler/actions/benchmark_test.go:199-244 createBenchmarkTopology,
+:360-421 createBenchmarkTopologyWithManyQueues, :424-473 ...WithGangJobs) as
+they come out of test_utils.BuildSession:
+
+  nodes   "node-%d", 8 GPUs, 2e7 mCPU, 2e10 B, 110 pods          (nodes_fake/nodes.go:31-36,171-180)
+  jobs    "job-%d", priority 50 (train, preemptible), queue i % numQueues, each task 1 GPU +
+          1000 mCPU + 1e9 B + 1 pod; job i created now-(n-i) min  (jobs_fake/jobs.go:83,261-291)
+  queues  "queue-%d" under "dept-%d" (i % numDepts, numDepts = ceil(numQueues/4)), deserved GPUs
+          = total/numQueues, over-quota weight 1, CPU/memory unlimited; department over-quota
+          weight = its deserved GPUs                               (test_utils_builder.go:96-225)
+
+Snapshot queue order: leaf queues first (creation now+k min), then departments (now+d min).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import abi
+
+
+def _name_rank(prefix: str, n: int) -> np.ndarray:
+    """Rank of f"{prefix}{i}" in byte-wise ascending order (node-10 < node-2)."""
+    names = np.array([f"{prefix}{i}" for i in range(n)], dtype=object)
+    order = np.argsort(names, kind="stable")
+    rank = np.empty(n, dtype=np.int32)
+    rank[order] = np.arange(n, dtype=np.int32)
+    return rank
+
+
+def benchmark_snapshot(n_nodes: int, n_jobs: int, tasks_per_job: int = 1, n_queues: int = 4,
+                       gpus_per_node: int = 8, mixed: bool = False, seed: int = 0x0C41,
+                       named_depts: bool | None = None) -> abi.Snapshot:
+    """createBenchmarkTopology{,WithManyQueues,WithGangJobs} scaled to any size.
+
+    mixed=True draws per-job GPUs in {1,2,4,8}, CPU in {1000,2000,4000} m and memory in
+    {1,2,4}e9 B from a seeded PRNG (SURVEY.md §8d config 3 request-mix variant; integer valued).
+    """
+    R = 4
+    N = n_nodes
+    alloc = np.empty((R, N), dtype=np.float64)
+    alloc[0], alloc[1], alloc[2], alloc[3] = 2e7, 2e10, float(gpus_per_node), 110.0
+    idle = alloc.copy()
+    rel = np.zeros((R, N), dtype=np.float64)
+    name_rank = _name_rank("node-", N)
+    flags = np.full(N, abi.NODE_READY, dtype=np.uint32)
+
+    total_gpus = float(N * gpus_per_node)
+    if named_depts is None:
+        named_depts = n_queues == 4
+    if named_depts:  # createBenchmarkTopology / ...WithGangJobs: dept-a {q0,q1}, dept-b {q2,q3}
+        n_depts = 2
+        q_dept = np.array([0, 0, 1, 1], dtype=np.int32)
+        dept_names = ["dept-a", "dept-b"]
+    else:  # ...WithManyQueues
+        n_depts = max(1, (n_queues + 3) // 4)
+        q_dept = (np.arange(n_queues) % n_depts).astype(np.int32)
+        dept_names = [f"dept-{i}" for i in range(n_depts)]
+    Q = n_queues + n_depts
+    parent = np.concatenate([q_dept + n_queues, np.full(n_depts, -1)]).astype(np.int32)
+    prio = np.full(Q, 100, dtype=np.int32)
+    creation = np.concatenate([np.arange(n_queues) * 60, np.arange(n_depts) * 60]).astype(np.int64)
+    qnames = np.array([f"queue-{i}" for i in range(n_queues)] + dept_names, dtype=object)
+    uid_rank = np.empty(Q, dtype=np.int32)
+    uid_rank[np.argsort(qnames, kind="stable")] = np.arange(Q, dtype=np.int32)
+    deserved = np.full((3, Q), -1.0)
+    limit = np.full((3, Q), -1.0)
+    oqw = np.ones((3, Q))
+    per_queue = total_gpus / n_queues
+    per_dept = total_gpus / n_depts
+    deserved[2, :n_queues] = per_queue
+    deserved[2, n_queues:] = per_dept
+    oqw[2, :n_queues] = 1.0
+    oqw[2, n_queues:] = per_dept
+
+    J = n_jobs
+    T = J * tasks_per_job
+    job_queue = (np.arange(J) % n_queues).astype(np.int32)
+    job_prio = np.full(J, 50, dtype=np.int32)
+    # creation now-(n-i) min, UID = name: all distinct creation times -> rank = index
+    job_order_rank = np.arange(J, dtype=np.int32)
+    job_flags = np.full(J, abi.JOB_PREEMPTIBLE, dtype=np.uint32)
+    job_podset_begin = np.arange(J + 1, dtype=np.int32)
+    podset_min = np.full(J, tasks_per_job, dtype=np.int32)  # default podset, minAvailable = len(Tasks)
+    podset_task_begin = (np.arange(J + 1) * tasks_per_job).astype(np.int32)
+    task_status = np.full(T, abi.POD_PENDING, dtype=np.int32)
+    task_node = np.full(T, -1, dtype=np.int32)
+    req = np.empty((T, R), dtype=np.float64)
+    if mixed:
+        rng = np.random.default_rng(seed)
+        g = rng.choice(np.array([1.0, 2.0, 4.0, 8.0]), size=J)
+        c = rng.choice(np.array([1000.0, 2000.0, 4000.0]), size=J)
+        m = rng.choice(np.array([1e9, 2e9, 4e9]), size=J)
+        req[:, 0] = np.repeat(c, tasks_per_job)
+        req[:, 1] = np.repeat(m, tasks_per_job)
+        req[:, 2] = np.repeat(g, tasks_per_job)
+    else:
+        req[:, 0], req[:, 1], req[:, 2] = 1000.0, 1e9, 1.0
+    req[:, 3] = 1.0
+    # TaskOrderFn falls back to the pod UID "<job>-<k>" (byte-wise): rank of str(k) among 0..tasks_per_job-1
+    k_rank = _name_rank("", tasks_per_job)
+    task_order_rank = np.tile(k_rank, J).astype(np.int32)
+
+    return abi.Snapshot(
+        n_res=R, node_allocatable=alloc, node_idle=idle, node_releasing=rel, node_name_rank=name_rank,
+        node_flags=flags, queue_parent=parent, queue_priority=prio, queue_creation=creation,
+        queue_uid_rank=uid_rank, queue_deserved=deserved, queue_limit=limit, queue_oqw=oqw,
+        job_queue=job_queue, job_priority=job_prio, job_order_rank=job_order_rank, job_flags=job_flags,
+        job_podset_begin=job_podset_begin, podset_min_available=podset_min,
+        podset_task_begin=podset_task_begin, task_status=task_status, task_node=task_node, task_req=req,
+        task_order_rank=task_order_rank)
+
+
+# The BASELINE.json configs
+CONFIGS = {
+    # name: kwargs
+    "config1": dict(n_nodes=100, n_jobs=500, tasks_per_job=1, n_queues=10),
+    "config2": dict(n_nodes=10_000, n_jobs=40_000, tasks_per_job=1, n_queues=4),
+    "config3": dict(n_nodes=50_000, n_jobs=50_000, tasks_per_job=4, n_queues=1000),
+    "config3-mixed": dict(n_nodes=50_000, n_jobs=50_000, tasks_per_job=4, n_queues=1000, mixed=True),
+}
+
+
+def config_snapshot(name: str) -> abi.Snapshot:
+    return benchmark_snapshot(**CONFIGS[name])

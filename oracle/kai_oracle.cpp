@@ -1210,15 +1210,22 @@ struct kai_oracle {
     }
   };
 
-  // actions/utils/input_jobs.go:21-68 InitializeWithJobs (jobs in ascending index order)
+  // actions/utils/input_jobs.go:21-68 InitializeWithJobs.  The reference ranges over a Go map
+  // (unspecified order); the canonical order used here and by the engine is: leaf queues in
+  // ascending index, the jobs of a queue in JobOrderFn order.
   void init_jobs_order(JobsOrder &jo, bool filter_non_pending, bool filter_unready) {
+    std::vector<std::vector<int>> by_queue(NQ);
     for (int ji = 0; ji < NJ; ji++) {
       const Job &j = J[ji];
       if (filter_unready && !job_ready(j)) continue;
       if (filter_non_pending && job_count(j, KAI_POD_PENDING) == 0) continue;
       if (j.queue < 0) continue;
       if (!Q[j.queue].children.empty()) continue;
-      jo.push_job(ji);
+      by_queue[j.queue].push_back(ji);
+    }
+    for (int q = 0; q < NQ; q++) {
+      std::sort(by_queue[q].begin(), by_queue[q].end(), [&](int a, int b) { return jo.job_less(a, b); });
+      for (int ji : by_queue[q]) jo.push_job(ji);
     }
   }
 

@@ -1,0 +1,141 @@
+"""Parity of the CUDA engine with the CPU oracle through the C ABI (GPU box only).
+
+Bit-exact: bindings (task -> node), task statuses, job visiting order and outcomes, node Idle/Releasing
+tables, queue Allocated / fair-share tables (DRF inputs; tolerance 0 here since inputs are integer valued).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import dsl
+from fixtures import action_cases
+from kai_scheduler_b200 import abi, synthetic
+from kai_scheduler_b200.engine import Engine
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+ALLOCATE = action_cases(["allocate__"], single_action="allocate")
+
+
+def assert_same(res_e: abi.Result, res_o: abi.Result):
+    np.testing.assert_array_equal(res_e.task_node, res_o.task_node)
+    np.testing.assert_array_equal(res_e.task_status, res_o.task_status)
+    np.testing.assert_array_equal(res_e.visits, res_o.visits)
+    np.testing.assert_array_equal(res_e.node_idle, res_o.node_idle)
+    np.testing.assert_array_equal(res_e.node_releasing, res_o.node_releasing)
+    np.testing.assert_array_equal(res_e.queue_allocated, res_o.queue_allocated)
+    np.testing.assert_array_equal(res_e.queue_allocated_non_preemptible, res_o.queue_allocated_non_preemptible)
+    np.testing.assert_array_equal(res_e.queue_request, res_o.queue_request)
+    np.testing.assert_array_equal(res_e.total_resource, res_o.total_resource)
+    # DRF / fair shares: BASELINE.json tolerance 1e-6; integer-valued inputs give exact equality
+    np.testing.assert_allclose(res_e.queue_fair_share, res_o.queue_fair_share, rtol=0, atol=1e-6)
+    assert res_e.pods_placed == res_o.pods_placed
+
+
+def run_both(snap, action="allocate", cfg=None):
+    e = Engine(cfg)
+    e.load(snap)
+    re_ = e.run(action)
+    e.close()
+    o = Oracle(cfg)
+    o.load(snap)
+    ro = o.run(action)
+    return re_, ro
+
+
+@pytest.mark.parametrize("cid,case", ALLOCATE, ids=[c[0] for c in ALLOCATE])
+def test_allocate_tables_gpu(cid, case):
+    snap, meta = dsl.build_snapshot(case["topology"])
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+    errs = dsl.check_expectations(case["topology"], meta, re_, snap)
+    assert not errs, f"{case['source']} #{case['index']}: {errs}"
+
+
+@pytest.mark.parametrize("grid", ["1", "3", "148"])
+def test_allocate_tables_forced_grid(grid, monkeypatch):
+    """Same tables with forced CTA counts (including CTAs that own no node) to exercise the slot exchange."""
+    monkeypatch.setenv("KAI_GRID_EXACT", grid)
+    for cid, case in ALLOCATE:
+        snap, meta = dsl.build_snapshot(case["topology"])
+        re_, ro = run_both(snap)
+        assert_same(re_, ro)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_nodes=100, n_jobs=500, tasks_per_job=1, n_queues=10),            # BASELINE config 1
+    dict(n_nodes=64, n_jobs=700, tasks_per_job=1, n_queues=4),              # over-subscribed: failures + leftovers
+    dict(n_nodes=300, n_jobs=400, tasks_per_job=4, n_queues=12),            # gangs, many queues
+    dict(n_nodes=257, n_jobs=600, tasks_per_job=3, n_queues=7, mixed=True),  # request mix, ragged sizes
+    dict(n_nodes=1000, n_jobs=3000, tasks_per_job=2, n_queues=40, mixed=True),
+])
+def test_synthetic_parity(kw):
+    snap = synthetic.benchmark_snapshot(**kw)
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+
+
+def test_spread_strategy():
+    snap = synthetic.benchmark_snapshot(n_nodes=50, n_jobs=200, tasks_per_job=2, n_queues=4, mixed=True)
+    cfg = abi.make_config(gpu_placement=abi.PLACEMENT_SPREAD, cpu_placement=abi.PLACEMENT_SPREAD)
+    re_, ro = run_both(snap, cfg=cfg)
+    assert_same(re_, ro)
+
+
+def test_cpu_only_pods_and_cpu_nodes():
+    snap = synthetic.benchmark_snapshot(n_nodes=40, n_jobs=300, tasks_per_job=1, n_queues=4)
+    # half of the nodes lose their GPUs, a third of the jobs become CPU-only
+    snap.node_allocatable[2, ::2] = 0
+    snap.node_idle[2, ::2] = 0
+    snap.task_req[::3, 2] = 0
+    snap.task_req[::3, 0] = 3000
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+
+
+def test_predicate_mask_and_nominated_node():
+    snap = synthetic.benchmark_snapshot(n_nodes=96, n_jobs=200, tasks_per_job=1, n_queues=4)
+    rng = np.random.default_rng(7)
+    words = (96 + 31) // 32
+    mask = rng.integers(0, 2**32, size=(3, words), dtype=np.uint64).astype(np.uint32)
+    snap.pred_mask = mask
+    snap.task_pred_class = rng.integers(-1, 3, size=snap.n_tasks).astype(np.int32)
+    snap.task_nominated = np.where(rng.random(snap.n_tasks) < 0.2, rng.integers(0, 96, size=snap.n_tasks), -1).astype(np.int32)
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+
+
+def test_empty_and_degenerate_snapshots():
+    # no jobs at all
+    snap = synthetic.benchmark_snapshot(n_nodes=5, n_jobs=0, tasks_per_job=1, n_queues=4)
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+    # a single node, more demand than supply
+    snap = synthetic.benchmark_snapshot(n_nodes=1, n_jobs=20, tasks_per_job=1, n_queues=4)
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+    assert re_.pods_placed == 8
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size: size-independent properties (the oracle needs ~5 s here, so also compare)."""
+    snap = synthetic.config_snapshot("config2")
+    e = Engine()
+    e.load(snap)
+    res = e.run("allocate")
+    st = e.stats()
+    e.close()
+    assert res.pods_placed == 40_000
+    assert (res.task_node >= 0).all() and (res.task_status == abi.POD_BINDING).all()
+    used = np.bincount(res.task_node, minlength=snap.n_nodes)
+    assert used.max() <= 8 and (res.node_idle[2] == 8 - used).all()
+    # binpack: exactly 5000 nodes completely full, and they are the 5000 lexicographically smallest names
+    full = np.nonzero(used == 8)[0]
+    assert len(full) == 5000 and set(snap.node_name_rank[full]) == set(range(5000))
+    assert st.decisions == 40_000
+    o = Oracle(threads=os.cpu_count() or 1)
+    o.load(snap)
+    ro = o.run("allocate")
+    assert_same(res, ro)

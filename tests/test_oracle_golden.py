@@ -1,0 +1,28 @@
+"""Pin the CPU oracle against the reference's own action tables (CPU only).
+
+Each case is a `test_utils.TestTopologyBasic` literal transcribed from
+pkg/scheduler/actions/*/*_test.go by tests/golden/gen_fixtures.py; the assertions are
+`MatchExpectedAndRealTasks` (pkg/scheduler/test_utils/test_utils.go:121-314) restated in tests/dsl.py.
+"""
+import pytest
+
+import dsl
+from fixtures import action_cases
+from oracle_lib import Oracle
+
+ALLOCATE = action_cases(["allocate__"], single_action="allocate")
+
+
+@pytest.mark.parametrize("cid,case", ALLOCATE, ids=[c[0] for c in ALLOCATE])
+def test_allocate_tables(cid, case):
+    snap, meta = dsl.build_snapshot(case["topology"])
+    o = Oracle()
+    o.load(snap)
+    res = o.run("allocate")
+    errs = dsl.check_expectations(case["topology"], meta, res, snap)
+    assert not errs, f"{case['source']} #{case['index']} {case['name']}: {errs}"
+
+
+def test_case_counts():
+    # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
+    assert len(ALLOCATE) == 41
