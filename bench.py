@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line per run (driver contract).
+
+A "step" is one scheduling cycle (proportion OnSessionOpen + allocate Action) over one synthetic
+cluster snapshot.  Default workload at N=1: BASELINE.json configs[1] — 10 000 nodes ("node-%d",
+8 GPUs) / 40 000 pending single-pod 1-GPU jobs / 4 leaf queues under 2 departments, binpack.
+
+  value        pods placed per second, device time (CUDA events on the engine's stream) of the open-session
+               kernels + the action kernel, snapshot already resident in HBM
+  e2e          the same metric through the C-ABI call a Go shim makes: kai_engine_load_snapshot(HOST
+               buffers) + kai_engine_run(), host->device and device->host copies inside the timed region
+  roofline     dominant kernel k_action: algorithmic bytes = node rows swept x 76 B
+  cpu_baseline the CPU oracle (port of the reference's Go path) on this box's host cores
+
+  --impl reference   times the CPU oracle instead (the reference is Go; no Go toolchain exists here or on the
+                     GPU box, so the "reference arm" is the restatement in oracle/, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+from kai_scheduler_b200 import abi, synthetic  # noqa: E402
+
+METRIC = "pods_placed_per_sec"
+UNIT = "pods/s"
+BYTES_PER_NODE = (2 * 4 + 1) * 8 + 4  # Idle[R]+Releasing[R]+Allocatable[1] f64 + 4 B flags, R=4
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args, snap, workload):
+    """--impl reference: CPU oracle with all host threads on the same config/metric."""
+    from oracle_lib import Oracle
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    o = Oracle(threads=cores)
+    times, placed = [], 0
+    for i in range(args.warmup + args.steps):
+        o.load(snap)
+        t0 = time.perf_counter()
+        res = o.run("allocate")
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            placed += res.pods_placed
+    total = sum(times)
+    value = placed / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "full workload per step (oracle/kai_oracle.cpp, node sweep over all host threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--config", default="config2", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "off"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local = dist_env()
+
+    kw = synthetic.CONFIGS[args.config]
+    snap = synthetic.benchmark_snapshot(**kw)
+    workload = {
+        "workload": f"{args.config}: {kw['n_nodes']} nodes x {kw['n_jobs']} jobs x {kw.get('tasks_per_job', 1)} pods, "
+                    f"{kw.get('n_queues', 4)} leaf queues, binpack, allocate action",
+        "nodes": kw["n_nodes"], "pods": kw["n_jobs"] * kw.get("tasks_per_job", 1), "queues": kw.get("n_queues", 4),
+        "parallelism": "replicas" if args.gpus > 1 else "1 GPU",
+        "l2_policy": "node tables are re-uploaded (H2D) before every timed step, which replaces the L2-resident copy; "
+                     "the action kernel then keeps its node tiles in shared memory",
+    }
+    if args.impl == "reference":
+        run_reference(args, snap, workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kai_scheduler_b200.engine import Engine
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    eng = Engine(abi.make_config(device=local))
+    c_snap = snap.to_c()
+    h2d = snap.host_bytes()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        """returns (device_ms, e2e_s, pods, stats)"""
+        t0 = time.perf_counter()
+        eng.load_c(c_snap, snap.n_res)       # H2D of the whole snapshot + open-session kernels
+        r = eng.run("allocate", copy=False)  # action kernel + D2H of the results
+        e2e = time.perf_counter() - t0
+        st = eng.stats()
+        return st.open_session_ms + st.action_ms, e2e, int(r.pods_placed), st, r
+
+    for _ in range(max(args.warmup, 3) if args.steps > 0 else 0):
+        one_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms, e2e_s, pods, launches, alg_bytes, act_ms, d2h = 0.0, 0.0, 0, 0, 0, 0.0, 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        d, e, p, st, r = one_step()
+        dev_ms += d
+        e2e_s += e
+        pods += p
+        launches += int(st.kernel_launches)
+        alg_bytes += int(st.algorithmic_bytes)
+        act_ms += st.action_ms
+        d2h = (r.n_tasks * 8 + r.n_visits * 8 + r.n_queues * 3 * 8 * 4 + r.n_nodes * snap.n_res * 8 * 2 + 24)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    # max over ranks of the timed quantities
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, wall = [float(x) for x in t.tolist()]
+        tp = torch.tensor([pods], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        pods_all = int(tp.item())
+    else:
+        pods_all = pods
+    if rank == 0:
+        peak, which = measured_peak_gbs()
+        achieved = (alg_bytes / args.steps) / (act_ms / args.steps * 1e-3) / 1e9 if act_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": pods_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload,
+            "e2e": {"value": pods_all / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_action", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "algorithmic_bytes_per_launch": alg_bytes // max(args.steps, 1),
+                         "kernel_ms_per_launch": act_ms / args.steps, "traffic": None},
+            "clocks": clocks,
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+        }
+        if args.cpu_baseline != "off" and args.gpus == 1:
+            from oracle_lib import Oracle
+            o = Oracle(threads=1)
+            o.load(snap)
+            t0 = time.perf_counter()
+            ro = o.run("allocate")
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ro.pods_placed / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"one full {args.config} allocate cycle, scalar oracle, {dt:.2f} s",
+                                    "host_cores_available": os.cpu_count()}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

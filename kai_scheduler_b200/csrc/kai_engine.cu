@@ -666,6 +666,12 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   e->stats.algorithmic_bytes = c[2] * ((2 * e->R + 1) * 8 + 4);
   e->stats.kernel_launches += 1;
   e->seq = (unsigned int)c[7];
+  if (getenv("KAI_PROFILE")) {
+    const char *nm[] = {"init", "pop", "prepare", "scan", "exchange", "apply", "finish"};
+    fprintf(stderr, "[kai] action %.3f ms, %lld sweeps, %lld minmax exchanges; CTA0 thread0 cycles:", ms, c[1], c[5]);
+    for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%lld", nm[i], c[8 + i]);
+    fprintf(stderr, "\n");
+  }
   if (c[6] != 0) return e->fail(KAI_ERR_CUDA, "device sequencer overflow (statement log)");
   return download(e, out, c[0], c[3], c[4]);
 }

@@ -332,6 +332,7 @@ struct Seq {  // replicated sequencer state (thread 0 of every CTA)
   kai_job_visit *visits;
   int visits_cap;
   int error;
+  long long t_pop, t_prep, t_scan, t_xchg, t_apply, t_finish, t_init;  // clock64 phase totals (thread 0)
 };
 
 __device__ __forceinline__ double &q_alloc(Seq &q, int r, int qi) { return q.rp.q_alloc[(size_t)r * q.s->Q + qi]; }
@@ -1369,11 +1370,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
     seq.visits = p.visits;
     seq.visits_cap = p.visits_cap;
     seq.error = 0;
+    seq.t_pop = seq.t_prep = seq.t_scan = seq.t_xchg = seq.t_apply = seq.t_finish = seq.t_init = 0;
     ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
     ctl.seq = p.seq0;
     ctl.stop = 0;
   }
   __syncthreads();
+  long long tk0 = clock64();
 
   // ---- load the tile (coalesced per resource row) and the replica state ----
   for (int ln = tid; ln < tile.count; ln += blockDim.x) {
@@ -1449,10 +1452,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
   __syncthreads();
   if (tid == 0) seq_init_job_order(seq);
   __syncthreads();
+  if (tid == 0) seq.t_init = clock64() - tk0;
 
   // ---- allocate action main loop (actions/allocate/allocate.go:46-111) ----
   for (;;) {
     if (tid == 0) {
+      long long tk = clock64();
       int job = pop_next_job(seq);
       ctl.job = job;
       ctl.n_items = 0;
@@ -1472,6 +1477,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
         }
       }
       if (seq.error) ctl.stop = 1;
+      seq.t_pop += clock64() - tk;
     }
     __syncthreads();
     if (ctl.job < 0 || ctl.stop) break;
@@ -1480,10 +1486,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
       const int n_items = ctl.n_items;
       for (int k = 0; k < n_items; k++) {
         if (tid == 0) {
+          long long tk = clock64();
           int t = seq.rp.tta[k];
           ctl.need_minmax = 0;
           ctl.item_ok = seq_prepare_task(seq, t) ? 1 : 0;
           if (ctl.need_minmax) seq.minmax_exchanges++;
+          seq.t_prep += clock64() - tk;
         }
         __syncthreads();
         if (!ctl.item_ok) {
@@ -1503,16 +1511,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
           ctl.dec.mx = ctl.trk[tk].mx;
         }
         __syncthreads();
+        long long tk1 = clock64();
         Cand local = scan_tile(tile, ctl.dec, s, sh_warp);
         if (tid < 32) {
+          long long tk2 = clock64();
           local.score = __shfl_sync(0xffffffffu, local.score, 0);
           local.rank = __shfl_sync(0xffffffffu, local.rank, 0);
           local.ln = __shfl_sync(0xffffffffu, local.ln, 0);
           unsigned int sq = ctl.seq;
           exchange_candidates(p, ctl, tile, ctl.dec, local, sq);
           if (tid == 0) {
+            long long tk3 = clock64();
             ctl.seq = sq + 1;
             seq_apply_winner(seq, ctl.dec.task);
+            long long tk4 = clock64();
+            seq.t_scan += tk2 - tk1;
+            seq.t_xchg += tk3 - tk2;
+            seq.t_apply += tk4 - tk3;
           }
         }
         __syncthreads();
@@ -1523,6 +1538,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
       }
     }
     if (tid == 0) {
+      long long tk = clock64();
       int job = ctl.job;
       if (job_success) {
         if (should_pipeline_job(seq, job)) stmt_convert_all_allocated_to_pipelined(seq, job);
@@ -1534,6 +1550,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
         record_visit(seq, job, 0);
       }
       if (seq.error) ctl.stop = 1;
+      seq.t_finish += clock64() - tk;
     }
     __syncthreads();
     if (ctl.stop) break;
@@ -1569,6 +1586,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
       p.counters[5] = seq.minmax_exchanges;
       p.counters[6] = seq.error;
       p.counters[7] = ctl.seq;
+      p.counters[8] = seq.t_init;
+      p.counters[9] = seq.t_pop;
+      p.counters[10] = seq.t_prep;
+      p.counters[11] = seq.t_scan;
+      p.counters[12] = seq.t_xchg;
+      p.counters[13] = seq.t_apply;
+      p.counters[14] = seq.t_finish;
     }
   }
 }
