@@ -71,25 +71,44 @@ struct DevSnap {
   unsigned char *t_virtual;                // session state
   const uint32_t *pred_mask;
   double *total;  // [3] device
+  // ---- written by the fair-share / prepare kernels (device only) ----
+  double *q_allocatable;  // [3][Q] GetAllocatableShare per queue (static within a cycle)
+  unsigned long long *j_key0;  // [J] JobOrderFn sort key at action start
+  int *leaf_sorted;            // [J] eligible jobs per leaf queue (arena offsets q_job_begin) in JobOrderFn order
+  int *leaf_count;             // [Q]
+  int *ps_cnt0;                // [3][S] tasks per podset: active-allocated, pending, pipelined
 };
 
-// Per-CTA replica of the mutable session state (arrays live in one big arena per replica).
+// Cached comparator inputs of one queue node (plugins/proportion/queue_order/queue_order.go:19-73)
+struct QKey {
+  double drf_job, drf;
+  int priority;
+  unsigned char over, starved, viol, valid;
+};
+
+// Per-CTA replica of the mutable session state.  The "hot" arrays live in shared memory when they
+// fit (ActionParams.hot_in_smem), everything else in the per-CTA global arena.
 struct Replica {
+  // hot: per queue
   double *q_alloc, *q_alloc_np;  // [3][Q]
+  QKey *qkey;                    // [Q]
+  int *leaf_head, *leaf_end;     // [Q] sorted part of the leaf job list = leaf_heap[head, end)
+  int *ovl_len;                  // [Q] overflow heap (re-pushed jobs) = leaf_heap[q_job_begin, +ovl_len)
+  int *child_len;                // [Q]
+  int *child_heap;               // [Q] arena by q_child_begin
+  int *root_heap;                // [n_top + 1]
+  unsigned char *qn_flags;       // [Q]
+  // cold
   int *t_status, *t_node, *t_node_status;
   unsigned char *t_virtual;
-  int *ps_active_alloc;  // [S] tasks in an active-allocated status
-  double *j_req;         // [J][3] cached GetTasksToAllocateInitResource
+  int *ps_active_alloc, *ps_pending, *ps_pipelined;  // [S]
+  double *j_req;                                     // [J][3] cached GetTasksToAllocateInitResource
   unsigned char *j_req_valid;
-  int *leaf_heap;  // [J]
-  int *leaf_len;   // [Q]
-  int *child_heap; // [Q]
-  int *child_len;  // [Q]
-  int *root_heap;  // [n_top]
-  unsigned char *qn_flags;  // [Q]
-  Op *ops;                  // [ops_cap]
-  int *tta;                 // [max_job_tasks]
-  int *ps_order;            // [max_job_podsets]
+  unsigned long long *j_key;  // [J]
+  int *leaf_heap;             // [J]
+  Op *ops;                    // [ops_cap]
+  int *tta;                   // [max_job_tasks]
+  int *ps_order;              // [max_job_podsets]
 };
 
 struct ActionParams {
@@ -103,12 +122,15 @@ struct ActionParams {
   unsigned char *replica_arena;  // grid * replica_bytes
   size_t replica_bytes;
   int ops_cap;
-  unsigned long long *xbuf;  // exchange slots: [2][kMaxGrid][4] u64 (A word pair + B word pair)
+  unsigned long long *xbuf;  // exchange slots: [2][kMaxGrid][8] u64 (tagged 128-bit words A, B, C, D)
   unsigned long long *mmbuf; // min/max exchange: [2][kMaxGrid][8] u64
   kai_job_visit *visits;     // [visits_cap]
   int visits_cap;
-  long long *counters;  // [8]: n_visits, decisions, nodes_scanned, pods_placed, pods_evicted, minmax_exchanges, error
+  long long *counters;  // [16]: n_visits, sweeps, nodes_scanned, pods_placed, pods_evicted, minmax_exchanges, error, seq, phase timers
   unsigned int seq0;    // first exchange sequence number of this launch
+  int hot_in_smem;      // hot replica arrays carved from dynamic shared memory after the node tile
+  size_t tile_bytes, hot_bytes;
+  int batching;         // same-node batching of consecutive identical pods (1 = on)
 };
 
 }  // namespace kai

@@ -16,6 +16,7 @@
 
 #include "kai_device.cuh"
 #include "kai_kernels.cuh"  // single translation unit: kernels + host API
+#include "kai_action.cuh"
 
 using namespace kai;
 
@@ -96,7 +97,8 @@ struct kai_engine {
   DevSnap ds;
   int R = 4, N = 0, Q = 0, J = 0, S = 0, T = 0;
   int grid = 0, npc = 0;
-  size_t smem_bytes = 0, replica_bytes = 0;
+  size_t smem_bytes = 0, replica_bytes = 0, tile_bytes = 0, hot_bytes = 0;
+  bool hot_in_smem = false;
   int ops_cap = 0, visits_cap = 0;
   unsigned long long *xbuf = nullptr, *mmbuf = nullptr;
   long long *counters = nullptr;
@@ -348,6 +350,9 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   size_t o_tvirt = reserve_up((size_t)std::max(T, 1));
   size_t o_qfair = reserve_up(QN * 8), o_qreq = reserve_up(QN * 8), o_qal = reserve_up(QN * 8), o_qalnp = reserve_up(QN * 8);
   size_t o_total = reserve_up(3 * 8);
+  size_t o_qla = reserve_up(QN * 8);
+  size_t o_jkey = reserve_up((size_t)std::max(J, 1) * 8), o_leafs = reserve_up((size_t)std::max(J, 1) * 4);
+  size_t o_leafc = reserve_up((size_t)std::max(Q, 1) * 4), o_pscnt = reserve_up((size_t)3 * std::max(S, 1) * 4);
   const size_t zero_begin = o_tvirt, zero_bytes = up - o_tvirt;
 
   CK(e->dsnap.reserve(up + 256));
@@ -472,6 +477,11 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   ds.t_virtual = (unsigned char *)(d + o_tvirt);
   ds.pred_mask = (s->pred_mask && NPC > 0) ? (const uint32_t *)(d + o_mask) : nullptr;
   ds.total = (double *)(d + o_total);
+  ds.q_allocatable = (double *)(d + o_qla);
+  ds.j_key0 = (unsigned long long *)(d + o_jkey);
+  ds.leaf_sorted = (int *)(d + o_leafs);
+  ds.leaf_count = (int *)(d + o_leafc);
+  ds.ps_cnt0 = (int *)(d + o_pscnt);
 
   // ---------------- launch geometry of the action kernel ----------------
   int grid = std::min(e->num_sms, kMaxGrid);
@@ -487,32 +497,37 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   }
   int npc = std::max(1, (N + grid - 1) / grid);
   npc = (npc + 1) & ~1;  // keep the int arrays 8-byte aligned
-  size_t smem = (size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4);
-  if (smem > (size_t)e->max_smem_optin - 4096)
+  size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4), 16);
+  if (tile_bytes > (size_t)e->max_smem_optin - 4096)
     return e->fail(KAI_ERR_UNSUPPORTED, "node tile does not fit in shared memory (N too large for one GPU tile)");
+  auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  // hot replica arrays — must match the carving in k_action
+  size_t hot = 2 * a16(sizeof(double) * QR * Q) + a16(sizeof(QKey) * (size_t)Q) + 5 * a16(sizeof(int) * (size_t)Q) +
+               a16(sizeof(int) * (size_t)(ds.n_top + 1)) + a16((size_t)Q);
+  bool hot_in_smem = tile_bytes + hot <= (size_t)e->max_smem_optin - 4096;
+  if (getenv("KAI_NO_SMEM_HOT")) hot_in_smem = false;
   e->grid = grid;
   e->npc = npc;
-  e->smem_bytes = smem;
+  e->tile_bytes = tile_bytes;
+  e->hot_bytes = hot;
+  e->hot_in_smem = hot_in_smem;
+  e->smem_bytes = tile_bytes + (hot_in_smem ? hot : 0);
   e->ops_cap = 4 * max_job_tasks + 64;
   e->visits_cap = std::max(16, 2 * J + T + 16);
-  {  // replica layout — must match the carving in k_action
-    size_t b = 0;
-    auto take = [&](size_t bytes) { b += (bytes + 15) & ~(size_t)15; };
-    take(sizeof(double) * QR * Q);
-    take(sizeof(double) * QR * Q);
+  {  // cold replica layout — must match the carving in k_action
+    size_t b = hot_in_smem ? 0 : hot;
+    auto take = [&](size_t bytes) { b += a16(bytes); };
     take(sizeof(int) * (size_t)T);
     take(sizeof(int) * (size_t)T);
     take(sizeof(int) * (size_t)T);
     take((size_t)T);
     take(sizeof(int) * (size_t)S);
+    take(sizeof(int) * (size_t)S);
+    take(sizeof(int) * (size_t)S);
     take(sizeof(double) * QR * (size_t)J);
     take((size_t)J);
+    take(sizeof(unsigned long long) * (size_t)J);
     take(sizeof(int) * (size_t)J);
-    take(sizeof(int) * (size_t)Q);
-    take(sizeof(int) * (size_t)Q);
-    take(sizeof(int) * (size_t)Q);
-    take(sizeof(int) * (size_t)(ds.n_top + 1));
-    take((size_t)Q);
     take(sizeof(Op) * (size_t)e->ops_cap);
     take(sizeof(int) * (size_t)(max_job_tasks + 1));
     take(sizeof(int) * (size_t)(max_job_podsets + 1));
@@ -645,6 +660,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   p.visits_cap = e->visits_cap;
   p.counters = e->counters;
   p.seq0 = e->seq;
+  p.hot_in_smem = e->hot_in_smem ? 1 : 0;
+  p.tile_bytes = e->tile_bytes;
+  p.hot_bytes = e->hot_bytes;
+  p.batching = getenv("KAI_NO_BATCHING") ? 0 : 1;
   CK(cudaFuncSetAttribute(k_action, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
   int max_blocks = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_action, kThreads, e->smem_bytes));
@@ -653,6 +672,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   void *args[] = {(void *)&p};
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 16, e->stream));
   cudaEventRecord(e->ev[2], e->stream);
+  if (e->J > 0) k_prep_jobs<<<std::min(e->num_sms * 8, (e->J + 255) / 256), 256, 0, e->stream>>>(e->ds, 1, 1);
+  if (e->Q > 0) k_prep_queues<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->ds);
   CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
   cudaEventRecord(e->ev[3], e->stream);
   long long c[16];
@@ -664,11 +685,11 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   e->stats.decisions = c[1];
   e->stats.nodes_scanned = c[2];
   e->stats.algorithmic_bytes = c[2] * ((2 * e->R + 1) * 8 + 4);
-  e->stats.kernel_launches += 1;
+  e->stats.kernel_launches += 1 + (e->J > 0) + (e->Q > 0);
   e->seq = (unsigned int)c[7];
   if (getenv("KAI_PROFILE")) {
     const char *nm[] = {"init", "pop", "prepare", "scan", "exchange", "apply", "finish"};
-    fprintf(stderr, "[kai] action %.3f ms, %lld sweeps, %lld minmax exchanges; CTA0 thread0 cycles:", ms, c[1], c[5]);
+    fprintf(stderr, "[kai] action %.3f ms, %lld sweeps, %lld batched placements, %lld minmax exchanges, hot_in_smem=%d; CTA0 thread0 cycles:", ms, c[1], c[15], c[5], (int)e->hot_in_smem);
     for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%lld", nm[i], c[8 + i]);
     fprintf(stderr, "\n");
   }

@@ -77,6 +77,28 @@ def test_synthetic_parity(kw):
     assert_same(re_, ro)
 
 
+@pytest.mark.parametrize("env", ["KAI_NO_BATCHING", "KAI_NO_SMEM_HOT"])
+def test_synthetic_parity_fallback_paths(env, monkeypatch):
+    """Same answers with same-node batching off / with the hot replica arrays in global memory."""
+    monkeypatch.setenv(env, "1")
+    for kw in (dict(n_nodes=300, n_jobs=400, tasks_per_job=4, n_queues=12),
+               dict(n_nodes=257, n_jobs=600, tasks_per_job=3, n_queues=7, mixed=True)):
+        snap = synthetic.benchmark_snapshot(**kw)
+        re_, ro = run_both(snap)
+        assert_same(re_, ro)
+
+
+def test_batching_reduces_sweeps():
+    snap = synthetic.benchmark_snapshot(n_nodes=200, n_jobs=1000, tasks_per_job=1, n_queues=4)
+    e = Engine()
+    e.load(snap)
+    res = e.run("allocate")
+    st = e.stats()
+    e.close()
+    assert res.pods_placed == 1000
+    assert st.decisions < 400  # 8 identical 1-GPU pods per node fill: about one sweep per node
+
+
 def test_spread_strategy():
     snap = synthetic.benchmark_snapshot(n_nodes=50, n_jobs=200, tasks_per_job=2, n_queues=4, mixed=True)
     cfg = abi.make_config(gpu_placement=abi.PLACEMENT_SPREAD, cpu_placement=abi.PLACEMENT_SPREAD)
@@ -134,7 +156,7 @@ def test_config2_full_size_properties():
     # binpack: exactly 5000 nodes completely full, and they are the 5000 lexicographically smallest names
     full = np.nonzero(used == 8)[0]
     assert len(full) == 5000 and set(snap.node_name_rank[full]) == set(range(5000))
-    assert st.decisions == 40_000
+    assert 0 < st.decisions <= 40_000  # sweeps; same-node batching places the rest without a sweep
     o = Oracle(threads=os.cpu_count() or 1)
     o.load(snap)
     ro = o.run("allocate")
