@@ -1,12 +1,16 @@
 // kai_action.cuh — the persistent action kernel (allocate) and its two prepare kernels.
 //
-//   k_prep_jobs    per job: podset status counters, readiness, JobOrderFn sort key      (grid-parallel)
+//   k_prep_jobs    per job: podset status counters, readiness, JobOrderFn sort key, cached
+//                  GetTasksToAllocateInitResource                                        (grid-parallel)
 //   k_prep_queues  per leaf queue: eligible jobs in JobOrderFn order                     (thread per queue)
-//   k_action       whole Action on device.  One CTA per SM; the CTA's slice of the node tables lives in
-//                  shared memory for the whole action; thread 0 of EVERY CTA runs the same sequencer
-//                  (job order tree, capacity checks, statement) on its own replica of the small mutable
-//                  state, so that the only cross-CTA traffic per allocateTask sweep is one 16-byte slot per
-//                  CTA (all-to-all through L2, tagged 128-bit relaxed stores/loads, parity double-buffered).
+//   k_action       whole Action on device, one CTA per SM, cooperative launch:
+//                    CTA 0      the sequencer (warp 0): job-order tree, capacity checks, statement; its
+//                               per-queue state lives in shared memory, per-task/job state is the session
+//                               state in HBM/L2 (single copy)
+//                    CTA 1..G-1 scanners: each keeps its slice of the node tables in shared memory for the
+//                               whole action and answers every decision record with one 16-byte candidate
+//                  sequencer -> scanners: a 16-word decision record (tagged 128-bit relaxed stores) plus a
+//                  list of node deltas since the previous record; scanners -> sequencer: one slot per CTA.
 //
 // Exactness notes
 //   * FittingNode + NodeOrderFn + sortNodesByScore (framework/session.go:201-264,466-485) are evaluated as
@@ -67,6 +71,25 @@ __global__ void k_prep_jobs(DevSnap s, int filter_non_pending, int filter_unread
     bool eligible = (!filter_unready || ready) && (!filter_non_pending || pending > 0) && q >= 0 &&
                     s.q_nchildren[q] == 0;  // input_jobs.go:24-63
     s.j_key0[j] = eligible ? make_job_key(s.j_priority[j], cls, s.j_order_rank[j]) : kKeyNone;
+    // GetTasksToAllocateInitResource(job, isRealAllocation=false) (allocation_info.go:87-113) for the common
+    // single-podset job; other jobs are evaluated lazily by the sequencer
+    s.j_req_valid[j] = 0;
+    if (s.j_ps_begin[j + 1] - s.j_ps_begin[j] == 1) {
+      int ps = s.j_ps_begin[j];
+      int act = s.ps_cnt0[ps], m = s.ps_min[ps];
+      int max_tasks = act >= m ? 1 : m - act;
+      double sum[QR] = {0, 0, 0};
+      int taken = 0;
+      for (int i = s.ps_task_begin[ps]; i < s.ps_task_begin[ps + 1] && taken < max_tasks; i++) {
+        int t = s.ps_sorted_tasks[i];
+        int st = s.t_status[t];
+        if (!(st == KAI_POD_PENDING || (st == KAI_POD_RELEASING && s.t_virtual[t]))) continue;
+        for (int r = 0; r < QR; r++) sum[r] = __dadd_rn(sum[r], s.t_req[(size_t)t * s.R + r]);
+        taken++;
+      }
+      for (int r = 0; r < QR; r++) s.j_req[(size_t)j * QR + r] = sum[r];
+      s.j_req_valid[j] = 1;
+    }
   }
 }
 
@@ -116,18 +139,23 @@ struct Winner {
   int node;
 };
 
-struct Batch {  // same-node batching state (replicated)
+struct Batch {  // same-node batching state
   int valid, node, to_idle, left, idx;
   unsigned long long fl;  // 6 tracker-event bits per repeat
 };
 
-struct Ctl {  // broadcast block, written by thread 0 / lane 0
+enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4 };
+enum { DB_GPU_TASK = 1, DB_BEST_EFFORT = 2, DB_PIPELINE_ONLY = 4, DB_BATCHING = 8, DB_DIRTY0 = 16, DB_DIRTY1 = 32 };
+
+struct Ctl {  // sequencer control block (shared memory of CTA 0), written by lane 0
   int job, n_items, job_ok, item_ok, need_minmax, use_batch, stop;
-  unsigned int seq;
+  unsigned int seq;  // sequence number of the next decision record
+  int n_delta;       // node deltas queued for the next record
   Decision dec;
   Winner win;
   Track trk[2];  // 0 gpu, 1 cpu
   Batch batch;
+  unsigned long long dw[kDecWords];
 };
 
 struct Tile {  // shared-memory node tile of this CTA
@@ -139,9 +167,10 @@ struct Tile {  // shared-memory node tile of this CTA
   int npc, base, count, R;
 };
 
-struct Seq {  // replicated sequencer state (thread 0 of every CTA)
+struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   const DevSnap *s;
   const kai_config *cfg;
+  const ActionParams *p;
   Replica rp;
   Tile *tile;
   Ctl *ctl;
@@ -170,45 +199,34 @@ __device__ __forceinline__ bool should_allocate(const Seq &q, int t, bool real) 
   return st == KAI_POD_PENDING || (!real && st == KAI_POD_RELEASING && q.rp.t_virtual[t]);
 }
 
-// ---- node tile mutation by the owning CTA (node_info.go:457-551) ----
+// ---- node mutations (node_info.go:457-551) are queued as deltas for the scanner that owns the node ----
+enum { ND_ADD = 0, ND_ADD_PIPELINED = 1, ND_ADD_RELEASING = 2, ND_REM = 3, ND_REM_PIPELINED = 4, ND_REM_RELEASING = 5 };
+__device__ void seq_flush_deltas(Seq &q);  // single-threaded FLUSH exchange when the delta list is full
+__device__ void emit_delta(Seq &q, int node, int code, int t) {
+  Ctl &c = *q.ctl;
+  if (c.n_delta >= kMaxDelta) seq_flush_deltas(q);
+  q.p->delta[(size_t)(c.seq & 1) * kMaxDelta + c.n_delta] = make_int2(node | (code << 28), t);
+  c.n_delta++;
+}
 __device__ void node_add_task(Seq &q, int t) {
-  const DevSnap &s = *q.s;
   int n = q.rp.t_node[t];
   int st = q.rp.t_status[t];
   q.rp.t_node_status[t] = st;
-  Tile &tl = *q.tile;
-  int ln = n - tl.base;
-  if (ln < 0 || ln >= tl.count) return;
-  for (int r = 0; r < s.R; r++) {
-    double v = __ldg(&s.t_req[(size_t)t * s.R + r]);
-    double &I = tl.I[r * tl.npc + ln], &L = tl.L[r * tl.npc + ln];
-    if (st == KAI_POD_RELEASING) {
-      L = __dadd_rn(L, v);
-      I = __dsub_rn(I, v);
-    } else if (st == KAI_POD_PIPELINED) {
-      L = __dsub_rn(L, v);
-    } else {
-      I = __dsub_rn(I, v);
-    }
-  }
+  emit_delta(q, n, st == KAI_POD_RELEASING ? ND_ADD_RELEASING : (st == KAI_POD_PIPELINED ? ND_ADD_PIPELINED : ND_ADD), t);
 }
 __device__ void node_remove_task(Seq &q, int t, int n) {
-  const DevSnap &s = *q.s;
   int st = q.rp.t_node_status[t];
-  Tile &tl = *q.tile;
-  int ln = n - tl.base;
-  if (ln < 0 || ln >= tl.count) return;
-  for (int r = 0; r < s.R; r++) {
-    double v = __ldg(&s.t_req[(size_t)t * s.R + r]);
-    double &I = tl.I[r * tl.npc + ln], &L = tl.L[r * tl.npc + ln];
-    if (st == KAI_POD_RELEASING) {
-      L = __dsub_rn(L, v);
-      I = __dadd_rn(I, v);
-    } else if (st == KAI_POD_PIPELINED) {
-      L = __dadd_rn(L, v);
-    } else {
-      I = __dadd_rn(I, v);
-    }
+  emit_delta(q, n, st == KAI_POD_RELEASING ? ND_REM_RELEASING : (st == KAI_POD_PIPELINED ? ND_REM_PIPELINED : ND_REM), t);
+}
+// applied by the owning scanner to its tile row (lane r handles resource r)
+__device__ __forceinline__ void apply_delta_row(double &I, double &L, int code, double v) {
+  switch (code) {
+    case ND_ADD: I = __dsub_rn(I, v); break;
+    case ND_ADD_PIPELINED: L = __dsub_rn(L, v); break;
+    case ND_ADD_RELEASING: L = __dadd_rn(L, v); I = __dsub_rn(I, v); break;
+    case ND_REM: I = __dadd_rn(I, v); break;
+    case ND_REM_PIPELINED: L = __dadd_rn(L, v); break;
+    case ND_REM_RELEASING: L = __dsub_rn(L, v); I = __dadd_rn(I, v); break;
   }
 }
 
@@ -893,7 +911,7 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
 constexpr int kSlotWords = 8;
 
 // candidate of this CTA -> slot words, including the same-node repeat analysis (lane 0 of warp 0)
-__device__ void publish_candidate(const ActionParams &p, Ctl &ctl, const Tile &tl, const Decision &d, Cand local,
+__device__ void publish_candidate(const Track *trk, const Tile &tl, const Decision &d, Cand local,
                                   unsigned long long *slot, unsigned int tag, int batching) {
   uint32_t flags = 0, repeat = 0;
   double a_gpu = 0, a_cpu = 0;
@@ -914,7 +932,7 @@ __device__ void publish_candidate(const ActionParams &p, Ctl &ctl, const Tile &t
     }
     const bool to_idle = !d.pipeline_only && (d.best_effort || fit_i);  // common/allocate.go:165-174
     if (to_idle) flags |= SLOT_TO_IDLE;
-    Track sim[2] = {ctl.trk[0], ctl.trk[1]};
+    Track sim[2] = {trk[0], trk[1]};
     bool stop = false;
     // placement 0 is the swept one; placements 1..kMaxRepeat are candidate repeats on the same node
     for (int rep = 0; rep <= kMaxRepeat; rep++) {
@@ -978,18 +996,53 @@ __device__ void publish_candidate(const ActionParams &p, Ctl &ctl, const Tile &t
   st_relaxed_b128(slot, (unsigned long long)__double_as_longlong(local.score), hi);
 }
 
-// all-to-all exchange of the per-CTA candidates; executed by warp 0; result broadcast through ctl
-__device__ void exchange_candidates(const ActionParams &p, Ctl &ctl, const Tile &tl, const Decision &d, Cand local,
-                                    unsigned int seq, int batching) {
+
+// =============================================================================================
+// sequencer <-> scanner protocol
+// =============================================================================================
+// decision record words (each stored as {data, tag}):
+//   0  kind | res<<8 | strategy<<16 | bits<<24 | n_delta<<32      1  nominated | pred_class<<32
+//   2..9 req[0..7]      10,11 gpu tracker mn,mx      12,13 cpu tracker mn,mx
+//   14 gpu cnt_mn | cnt_mx<<32      15 cpu cnt_mn | cnt_mx<<32
+__device__ void build_decision_words(Ctl &c, int kind, int batching) {
+  const Decision &d = c.dec;
+  unsigned long long bits = (d.gpu_task ? DB_GPU_TASK : 0) | (d.best_effort ? DB_BEST_EFFORT : 0) |
+                            (d.pipeline_only ? DB_PIPELINE_ONLY : 0) | (batching ? DB_BATCHING : 0) |
+                            (c.trk[0].dirty ? DB_DIRTY0 : 0) | (c.trk[1].dirty ? DB_DIRTY1 : 0);
+  c.dw[0] = (unsigned long long)kind | ((unsigned long long)d.res << 8) | ((unsigned long long)d.strategy << 16) |
+            (bits << 24) | ((unsigned long long)c.n_delta << 32);
+  c.dw[1] = (unsigned long long)(unsigned int)d.nominated | ((unsigned long long)(unsigned int)d.pred_class << 32);
+  for (int r = 0; r < KAI_MAX_RES; r++) c.dw[2 + r] = (unsigned long long)__double_as_longlong(d.req[r]);
+  for (int k = 0; k < 2; k++) {
+    c.dw[10 + 2 * k] = (unsigned long long)__double_as_longlong(c.trk[k].mn);
+    c.dw[11 + 2 * k] = (unsigned long long)__double_as_longlong(c.trk[k].mx);
+    c.dw[14 + k] = (unsigned long long)(unsigned int)c.trk[k].cnt_mn | ((unsigned long long)(unsigned int)c.trk[k].cnt_mx << 32);
+  }
+}
+
+// Publish the next decision record (warp 0 of CTA 0; lane 0 has prepared ctl.dec / trackers / deltas).
+__device__ void seq_publish(const ActionParams &p, Ctl &ctl, int kind) {
   const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    build_decision_words(ctl, kind, p.batching);
+    __threadfence();  // node deltas (plain stores) become visible before the record's tags
+  }
+  __syncwarp();
+  unsigned long long *rec = p.dbuf + (size_t)(ctl.seq & 1) * kDecWords * 2;
+  if (lane < kDecWords) st_relaxed_b128(rec + 2 * lane, ctl.dw[lane], (unsigned long long)ctl.seq);
+  __syncwarp();
+}
+
+// Gather the candidate slots of all scanners (warp 0 of CTA 0) and let lane 0 digest the winner.
+__device__ void seq_gather_candidates(const ActionParams &p, Ctl &ctl) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int seq = ctl.seq;
   unsigned long long *buf = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
   const unsigned int tag = seq & 0xffffffu;
-  if (lane == 0) publish_candidate(p, ctl, tl, d, local, buf + (size_t)blockIdx.x * kSlotWords, tag, batching);
-  // gather: lane l polls slots l, l+32, ...
   double bs = -1.0;
   uint32_t brank = kRankNone, bmeta = 0;
   int bslot = -1;
-  for (int c = lane; c < p.grid; c += 32) {
+  for (int c = lane; c < p.grid - 1; c += 32) {
     const unsigned long long *slot = buf + (size_t)c * kSlotWords;
     unsigned long long lo, hi;
     do {
@@ -1050,77 +1103,22 @@ __device__ void exchange_candidates(const ActionParams &p, Ctl &ctl, const Tile 
         ctl.batch.fl = lo;
       }
     }
+    ctl.seq = seq + 1;
+    ctl.n_delta = 0;
   }
+  __syncwarp();
 }
 
-// min/max exchange (rare): every CTA publishes local (mn, mx, cnt_mn, cnt_mx) for gpu and cpu
-__device__ void exchange_minmax(const ActionParams &p, Ctl &ctl, const Tile &tl, unsigned int seq, double *sh_d,
-                                int *sh_i) {
-  double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
-  for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
-    for (int k = 0; k < 2; k++) {
-      int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
-      double overall = k == 0 ? tl.Agpu[ln] : tl.Acpu[ln];
-      if (overall == 0) continue;
-      double cur = __dadd_rn(tl.I[res * tl.npc + ln], tl.L[res * tl.npc + ln]);
-      if (cur < mn[k]) mn[k] = cur;
-      if (cur > mx[k]) mx[k] = cur;
-    }
-  }
-  for (int k = 0; k < 2; k++)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-      mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-    }
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  if (lane == 0) {
-    sh_d[warp * 4 + 0] = mn[0];
-    sh_d[warp * 4 + 1] = mx[0];
-    sh_d[warp * 4 + 2] = mn[1];
-    sh_d[warp * 4 + 3] = mx[1];
-  }
-  __syncthreads();
-  for (int w = 0; w < nw; w++) {
-    mn[0] = fmin(mn[0], sh_d[w * 4 + 0]);
-    mx[0] = fmax(mx[0], sh_d[w * 4 + 1]);
-    mn[1] = fmin(mn[1], sh_d[w * 4 + 2]);
-    mx[1] = fmax(mx[1], sh_d[w * 4 + 3]);
-  }
-  int c[4] = {0, 0, 0, 0};
-  for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
-    for (int k = 0; k < 2; k++) {
-      int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
-      double overall = k == 0 ? tl.Agpu[ln] : tl.Acpu[ln];
-      if (overall == 0) continue;
-      double cur = __dadd_rn(tl.I[res * tl.npc + ln], tl.L[res * tl.npc + ln]);
-      if (cur == mn[k]) c[2 * k]++;
-      if (cur == mx[k]) c[2 * k + 1]++;
-    }
-  }
-  for (int i = 0; i < 4; i++)
-    for (int o = 16; o > 0; o >>= 1) c[i] += __shfl_xor_sync(0xffffffffu, c[i], o);
-  __syncthreads();
-  if (lane == 0)
-    for (int i = 0; i < 4; i++) sh_i[warp * 4 + i] = c[i];
-  __syncthreads();
-  if (warp != 0) return;
-  unsigned long long *buf = p.mmbuf + (size_t)(seq & 1) * kMaxGrid * 8;
+// min/max answer slots: four tagged words {value, [tag:32][count:32]} = gpu mn, gpu mx, cpu mn, cpu mx
+__device__ void seq_gather_minmax(const ActionParams &p, Ctl &ctl) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int seq = ctl.seq;
+  unsigned long long *buf = p.mmbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
   const unsigned long long tag = seq;
-  if (lane == 0) {
-    int tot[4] = {0, 0, 0, 0};
-    for (int w = 0; w < nw; w++)
-      for (int i = 0; i < 4; i++) tot[i] += sh_i[w * 4 + i];
-    unsigned long long *slot = buf + (size_t)blockIdx.x * 8;
-    st_relaxed_b128(slot + 0, (unsigned long long)__double_as_longlong(mn[0]), (tag << 32) | (unsigned int)tot[0]);
-    st_relaxed_b128(slot + 2, (unsigned long long)__double_as_longlong(mx[0]), (tag << 32) | (unsigned int)tot[1]);
-    st_relaxed_b128(slot + 4, (unsigned long long)__double_as_longlong(mn[1]), (tag << 32) | (unsigned int)tot[2]);
-    st_relaxed_b128(slot + 6, (unsigned long long)__double_as_longlong(mx[1]), (tag << 32) | (unsigned int)tot[3]);
-  }
-  // lanes split the slots; partial results are combined in a fixed order by lane 0
   double gmn[2] = {DBL_MAX, DBL_MAX}, gmx[2] = {0, 0};
   long long cmn[2] = {0, 0}, cmx[2] = {0, 0};
-  for (int cta = lane; cta < p.grid; cta += 32) {
-    const unsigned long long *slot = buf + (size_t)cta * 8;
+  for (int cta = lane; cta < p.grid - 1; cta += 32) {
+    const unsigned long long *slot = buf + (size_t)cta * kSlotWords;
     for (int k = 0; k < 2; k++) {
       unsigned long long lo, hi;
       do {
@@ -1129,7 +1127,7 @@ __device__ void exchange_minmax(const ActionParams &p, Ctl &ctl, const Tile &tl,
       double v = __longlong_as_double((long long)lo);
       int cnt = (int)(hi & 0xffffffffu);
       if (cnt > 0) {
-        if (v < gmn[k]) {
+        if (cmn[k] == 0 || v < gmn[k]) {
           gmn[k] = v;
           cmn[k] = cnt;
         } else if (v == gmn[k])
@@ -1141,7 +1139,7 @@ __device__ void exchange_minmax(const ActionParams &p, Ctl &ctl, const Tile &tl,
       v = __longlong_as_double((long long)lo);
       cnt = (int)(hi & 0xffffffffu);
       if (cnt > 0) {
-        if (v > gmx[k]) {
+        if (cmx[k] == 0 || v > gmx[k]) {
           gmx[k] = v;
           cmx[k] = cnt;
         } else if (v == gmx[k])
@@ -1171,18 +1169,41 @@ __device__ void exchange_minmax(const ActionParams &p, Ctl &ctl, const Tile &tl,
       }
     }
   if (lane == 0) {
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 2; k++) {  // pack.go:66-86: min starts at MaxFloat64, max at 0
       ctl.trk[k].mn = cmn[k] > 0 ? gmn[k] : DBL_MAX;
-      ctl.trk[k].mx = cmx[k] > 0 ? gmx[k] : 0.0;
+      ctl.trk[k].mx = (cmx[k] > 0 && gmx[k] > 0) ? gmx[k] : 0.0;
       ctl.trk[k].cnt_mn = (int)cmn[k];
       ctl.trk[k].cnt_mx = (int)cmx[k];
       ctl.trk[k].dirty = 0;
     }
+    ctl.seq = seq + 1;
+    ctl.n_delta = 0;
   }
+  __syncwarp();
+}
+
+// FLUSH issued by lane 0 alone from inside sequential code (delta list full; rare)
+__device__ void seq_flush_deltas(Seq &q) {
+  const ActionParams &p = *q.p;
+  Ctl &c = *q.ctl;
+  build_decision_words(c, DK_FLUSH, 0);
+  __threadfence();
+  unsigned long long *rec = p.dbuf + (size_t)(c.seq & 1) * kDecWords * 2;
+  for (int i = 0; i < kDecWords; i++) st_relaxed_b128(rec + 2 * i, c.dw[i], (unsigned long long)c.seq);
+  unsigned long long *buf = p.xbuf + (size_t)(c.seq & 1) * kMaxGrid * kSlotWords;
+  const unsigned int tag = c.seq & 0xffffffu;
+  for (int cta = 0; cta < p.grid - 1; cta++) {
+    unsigned long long lo, hi;
+    do {
+      ld_relaxed_b128(buf + (size_t)cta * kSlotWords, lo, hi);
+    } while ((unsigned int)(hi >> 40) != tag);
+  }
+  c.seq++;
+  c.n_delta = 0;
 }
 
 // =============================================================================================
-// sequencer steps (thread 0)
+// sequencer steps (lane 0)
 // =============================================================================================
 // InitializeWithJobs (input_jobs.go:21-68) in canonical order: leaf queues ascending, jobs of a queue in
 // JobOrderFn order (the Go map order is unspecified).
@@ -1197,18 +1218,18 @@ __device__ void seq_init_job_order(Seq &q) {
   }
 }
 
-// builds ctl.dec for task t; returns false when the task cannot be placed at all
-__device__ bool seq_prepare_task(Seq &q, int t) {
+// builds ctl.dec for task t of `job`; returns false when the task cannot be placed at all
+__device__ bool seq_prepare_task(Seq &q, int t, int job) {
   const DevSnap &s = *q.s;
   Ctl &c = *q.ctl;
   double rq[KAI_MAX_RES];
   for (int r = 0; r < KAI_MAX_RES; r++) rq[r] = r < s.R ? __ldg(&s.t_req[(size_t)t * s.R + r]) : 0.0;
+  int nominated = s.t_nominated ? __ldg(&s.t_nominated[t]) : -1;
+  int pred_class = s.t_pred_class ? __ldg(&s.t_pred_class[t]) : -1;
   bool gpu_task = rq[KAI_RES_GPU] > 0;
   // predicates.go:196-200 -> capacity_policy.go:51-61 with node_info.go:734-744
   double creq[QR] = {rq[KAI_RES_CPU], rq[KAI_RES_MEM], gpu_task ? 1.0 : 0.0};
-  if (over_capacity(q, __ldg(&s.t_job[t]), creq)) return false;
-  int nominated = s.t_nominated ? __ldg(&s.t_nominated[t]) : -1;
-  int pred_class = s.t_pred_class ? __ldg(&s.t_pred_class[t]) : -1;
+  if (over_capacity(q, job, creq)) return false;
   bool empty = !(rq[KAI_RES_GPU] > 0.01) && !(rq[KAI_RES_CPU] >= 10) && !(rq[KAI_RES_MEM] >= 10.0 * 1024 * 1024);
   for (int r = 3; r < s.R; r++)
     if (rq[r] >= 10) empty = false;
@@ -1271,7 +1292,7 @@ __device__ void seq_apply_batched(Seq &q, int t) {
 }
 
 __device__ void record_visit(Seq &q, int job, int outcome) {
-  if (q.is_cta0 && q.n_visits < q.visits_cap) {
+  if (q.n_visits < q.visits_cap) {
     q.visits[q.n_visits].job = job;
     q.visits[q.n_visits].outcome = outcome;
   }
@@ -1279,26 +1300,29 @@ __device__ void record_visit(Seq &q, int job, int outcome) {
 }
 
 // =============================================================================================
-// the kernel
+// scanner CTA
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ ActionParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ Ctl ctl;
-  __shared__ Tile tile;
-  __shared__ Seq seq;
-  __shared__ Cand sh_warp[kThreads / 32];
-  __shared__ double sh_d[(kThreads / 32) * 4];
-  __shared__ int sh_i[(kThreads / 32) * 4];
-  const DevSnap &s = p.s;
-  const int tid = threadIdx.x;
+struct ScanShared {
+  unsigned long long dw[kDecWords];
+  Decision dec;
+  Track trk[2];
+  int kind, n_delta, batching;
+  int2 delta[kMaxDelta];
+  unsigned char mine[kMaxDelta];
+  double dreq[kMaxDelta][KAI_MAX_RES];
+};
 
-  // ---- carve the node tile, the hot replica arrays and the cold replica arena ----
+__device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *sh_warp, double *sh_d, int *sh_i,
+                             ScanShared &sh, Tile &tile) {
+  const DevSnap &s = p.s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int my = blockIdx.x - 1;
   if (tid == 0) {
     int npc = p.nodes_per_cta;
     unsigned char *ptr = smem;
     tile.npc = npc;
     tile.R = s.R;
-    tile.base = p.node_base + blockIdx.x * npc;
+    tile.base = p.node_base + my * npc;
     int end = min(p.node_base + p.node_count, tile.base + npc);
     tile.count = max(0, end - tile.base);
     tile.I = (double *)ptr;
@@ -1314,8 +1338,177 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
     tile.rank = (int *)ptr;
     ptr += sizeof(int) * npc;
     tile.flags = (uint32_t *)ptr;
-    unsigned char *a = p.replica_arena + (size_t)blockIdx.x * p.replica_bytes;
-    unsigned char *h = p.hot_in_smem ? smem + p.tile_bytes : a;
+  }
+  __syncthreads();
+  for (int ln = tid; ln < tile.count; ln += blockDim.x) {
+    int n = tile.base + ln;
+    for (int r = 0; r < s.R; r++) {
+      tile.I[r * tile.npc + ln] = s.idle[(size_t)r * s.N + n];
+      tile.L[r * tile.npc + ln] = s.rel[(size_t)r * s.N + n];
+    }
+    tile.Agpu[ln] = s.alloc[(size_t)KAI_RES_GPU * s.N + n];
+    tile.Acpu[ln] = s.alloc[(size_t)KAI_RES_CPU * s.N + n];
+    tile.gpu_count[ln] = s.gpu_count[n];
+    tile.rank[ln] = s.name_rank[n];
+    tile.flags[ln] = s.nflags[n];
+  }
+  __syncthreads();
+  unsigned int seq = p.seq0;
+  for (;;) {
+    // ---- wait for decision record `seq` ----
+    if (warp == 0) {
+      if (lane < kDecWords) {
+        const unsigned long long *rec = p.dbuf + (size_t)(seq & 1) * kDecWords * 2 + 2 * lane;
+        unsigned long long lo, hi;
+        do {
+          ld_relaxed_b128(rec, lo, hi);
+        } while (hi != (unsigned long long)seq);
+        sh.dw[lane] = lo;
+      }
+      __threadfence();  // acquire side: the delta list written before the record is now visible
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long w0 = sh.dw[0];
+      Decision &d = sh.dec;
+      sh.kind = (int)(w0 & 0xff);
+      d.res = (int)((w0 >> 8) & 0xff);
+      d.strategy = (int)((w0 >> 16) & 0xff);
+      unsigned int bits = (unsigned int)((w0 >> 24) & 0xff);
+      sh.n_delta = (int)((w0 >> 32) & 0xffff);
+      d.gpu_task = (bits & DB_GPU_TASK) ? 1 : 0;
+      d.best_effort = (bits & DB_BEST_EFFORT) ? 1 : 0;
+      d.pipeline_only = (bits & DB_PIPELINE_ONLY) ? 1 : 0;
+      sh.batching = (bits & DB_BATCHING) ? 1 : 0;
+      d.nominated = (int)(unsigned int)(sh.dw[1] & 0xffffffffu);
+      d.pred_class = (int)(unsigned int)(sh.dw[1] >> 32);
+      for (int r = 0; r < KAI_MAX_RES; r++) d.req[r] = __longlong_as_double((long long)sh.dw[2 + r]);
+      for (int k = 0; k < 2; k++) {
+        sh.trk[k].mn = __longlong_as_double((long long)sh.dw[10 + 2 * k]);
+        sh.trk[k].mx = __longlong_as_double((long long)sh.dw[11 + 2 * k]);
+        sh.trk[k].cnt_mn = (int)(unsigned int)(sh.dw[14 + k] & 0xffffffffu);
+        sh.trk[k].cnt_mx = (int)(unsigned int)(sh.dw[14 + k] >> 32);
+        sh.trk[k].dirty = (bits & (k == 0 ? DB_DIRTY0 : DB_DIRTY1)) ? 1 : 0;
+      }
+      int tk = d.res == KAI_RES_GPU ? 0 : 1;
+      d.mn = sh.trk[tk].mn;
+      d.mx = sh.trk[tk].mx;
+      d.task = -1;
+    }
+    __syncthreads();
+    // ---- apply the node deltas that belong to this tile (loads in parallel, application in list order) ----
+    const int nd = sh.n_delta;
+    if (nd > 0) {
+      const int2 *dl = p.delta + (size_t)(seq & 1) * kMaxDelta;
+      for (int e = tid; e < nd; e += blockDim.x) {
+        int2 en = __ldcg(dl + e);
+        sh.delta[e] = en;
+        int node = en.x & 0x0fffffff;
+        int ln = node - tile.base;
+        bool mine = ln >= 0 && ln < tile.count;
+        sh.mine[e] = mine ? 1 : 0;
+        if (mine)
+          for (int r = 0; r < s.R; r++) sh.dreq[e][r] = __ldg(&s.t_req[(size_t)en.y * s.R + r]);
+      }
+      __syncthreads();
+      if (warp == 0 && lane < s.R) {
+        for (int e = 0; e < nd; e++) {
+          if (!sh.mine[e]) continue;
+          int2 en = sh.delta[e];
+          int ln = (en.x & 0x0fffffff) - tile.base;
+          apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], (en.x >> 28) & 7, sh.dreq[e][lane]);
+        }
+      }
+      __syncthreads();
+    }
+    const int kind = sh.kind;
+    if (kind == DK_DONE) break;
+    unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
+    if (kind == DK_SCAN) {
+      Cand local = scan_tile(tile, sh.dec, s, sh_warp);
+      if (tid == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching);
+    } else if (kind == DK_MINMAX) {
+      double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
+      for (int ln = tid; ln < tile.count; ln += blockDim.x)
+        for (int k = 0; k < 2; k++) {
+          int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
+          double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
+          if (overall == 0) continue;
+          double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
+          if (cur < mn[k]) mn[k] = cur;
+          if (cur > mx[k]) mx[k] = cur;
+        }
+      for (int k = 0; k < 2; k++)
+        for (int o = 16; o > 0; o >>= 1) {
+          mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+          mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+      if (lane == 0) {
+        sh_d[warp * 4 + 0] = mn[0];
+        sh_d[warp * 4 + 1] = mx[0];
+        sh_d[warp * 4 + 2] = mn[1];
+        sh_d[warp * 4 + 3] = mx[1];
+      }
+      __syncthreads();
+      for (int w = 0; w < nw; w++) {
+        mn[0] = fmin(mn[0], sh_d[w * 4 + 0]);
+        mx[0] = fmax(mx[0], sh_d[w * 4 + 1]);
+        mn[1] = fmin(mn[1], sh_d[w * 4 + 2]);
+        mx[1] = fmax(mx[1], sh_d[w * 4 + 3]);
+      }
+      int c[4] = {0, 0, 0, 0};
+      for (int ln = tid; ln < tile.count; ln += blockDim.x)
+        for (int k = 0; k < 2; k++) {
+          int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
+          double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
+          if (overall == 0) continue;
+          double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
+          if (cur == mn[k]) c[2 * k]++;
+          if (cur == mx[k]) c[2 * k + 1]++;
+        }
+      for (int i = 0; i < 4; i++)
+        for (int o = 16; o > 0; o >>= 1) c[i] += __shfl_xor_sync(0xffffffffu, c[i], o);
+      if (lane == 0)
+        for (int i = 0; i < 4; i++) sh_i[warp * 4 + i] = c[i];
+      __syncthreads();
+      if (tid == 0) {
+        int tot[4] = {0, 0, 0, 0};
+        for (int w = 0; w < nw; w++)
+          for (int i = 0; i < 4; i++) tot[i] += sh_i[w * 4 + i];
+        unsigned long long tag = seq;
+        slot = p.mmbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
+        st_relaxed_b128(slot + 0, (unsigned long long)__double_as_longlong(mn[0]), (tag << 32) | (unsigned int)tot[0]);
+        st_relaxed_b128(slot + 2, (unsigned long long)__double_as_longlong(mx[0]), (tag << 32) | (unsigned int)tot[1]);
+        st_relaxed_b128(slot + 4, (unsigned long long)__double_as_longlong(mn[1]), (tag << 32) | (unsigned int)tot[2]);
+        st_relaxed_b128(slot + 6, (unsigned long long)__double_as_longlong(mx[1]), (tag << 32) | (unsigned int)tot[3]);
+      }
+    } else {  // DK_FLUSH: acknowledge
+      if (tid == 0) {
+        unsigned long long hi = ((unsigned long long)(seq & 0xffffffu) << 40) | (unsigned long long)kRankNone;
+        st_relaxed_b128(slot, (unsigned long long)__double_as_longlong(-1.0), hi);
+      }
+    }
+    seq++;
+    __syncthreads();
+  }
+  // ---- DONE: write the tile back to the session tables ----
+  for (int ln = tid; ln < tile.count; ln += blockDim.x) {
+    int n = tile.base + ln;
+    for (int r = 0; r < s.R; r++) {
+      s.idle[(size_t)r * s.N + n] = tile.I[r * tile.npc + ln];
+      s.rel[(size_t)r * s.N + n] = tile.L[r * tile.npc + ln];
+    }
+  }
+}
+
+// =============================================================================================
+// sequencer CTA
+// =============================================================================================
+__device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &ctl, Seq &seq) {
+  const DevSnap &s = p.s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    unsigned char *h = p.hot_in_smem ? smem : s.hot_global;
     auto take_from = [](unsigned char *&base, size_t bytes) {
       unsigned char *r = base;
       base += (bytes + 15) & ~(size_t)15;
@@ -1332,30 +1525,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
     rp.child_heap = (int *)take_from(h, sizeof(int) * s.Q);
     rp.root_heap = (int *)take_from(h, sizeof(int) * (s.n_top + 1));
     rp.qn_flags = (unsigned char *)take_from(h, s.Q);
-    if (!p.hot_in_smem) a = h;
-    rp.t_status = (int *)take_from(a, sizeof(int) * s.T);
-    rp.t_node = (int *)take_from(a, sizeof(int) * s.T);
-    rp.t_node_status = (int *)take_from(a, sizeof(int) * s.T);
-    rp.t_virtual = (unsigned char *)take_from(a, s.T);
-    rp.ps_active_alloc = (int *)take_from(a, sizeof(int) * s.S);
-    rp.ps_pending = (int *)take_from(a, sizeof(int) * s.S);
-    rp.ps_pipelined = (int *)take_from(a, sizeof(int) * s.S);
-    rp.j_req = (double *)take_from(a, sizeof(double) * QR * s.J);
-    rp.j_req_valid = (unsigned char *)take_from(a, s.J);
-    rp.j_key = (unsigned long long *)take_from(a, sizeof(unsigned long long) * s.J);
-    rp.leaf_heap = (int *)take_from(a, sizeof(int) * s.J);
-    rp.ops = (Op *)take_from(a, sizeof(Op) * p.ops_cap);
-    rp.tta = (int *)take_from(a, sizeof(int) * (s.max_job_tasks + 1));
-    rp.ps_order = (int *)take_from(a, sizeof(int) * (s.max_job_podsets + 1));
+    // cold state = the session arrays themselves
+    rp.t_status = s.t_status;
+    rp.t_node = s.t_node;
+    rp.t_node_status = s.t_node_status;
+    rp.t_virtual = s.t_virtual;
+    rp.ps_active_alloc = s.ps_cnt0;
+    rp.ps_pending = s.ps_cnt0 + s.S;
+    rp.ps_pipelined = s.ps_cnt0 + 2 * s.S;
+    rp.j_req = s.j_req;
+    rp.j_req_valid = s.j_req_valid;
+    rp.j_key = s.j_key0;
+    rp.leaf_heap = s.leaf_sorted;
+    rp.ops = s.ops;
+    rp.tta = s.tta;
+    rp.ps_order = s.ps_order;
     seq.s = &p.s;
     seq.cfg = &p.cfg;
-    seq.tile = &tile;
+    seq.p = &p;
+    seq.tile = nullptr;
     seq.ctl = &ctl;
     seq.n_ops = 0;
     seq.ops_cap = p.ops_cap;
     seq.root_len = 0;
     seq.batching = p.batching;
-    seq.is_cta0 = blockIdx.x == 0;
+    seq.is_cta0 = true;
     seq.pods_placed = seq.pods_evicted = seq.sweeps = seq.nodes_scanned = seq.n_visits = 0;
     seq.minmax_exchanges = seq.batched = 0;
     seq.visits = p.visits;
@@ -1363,48 +1557,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
     seq.error = 0;
     seq.t_pop = seq.t_prep = seq.t_scan = seq.t_xchg = seq.t_apply = seq.t_finish = seq.t_init = 0;
     ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
+    ctl.trk[0].mn = ctl.trk[1].mn = DBL_MAX;
+    ctl.trk[0].mx = ctl.trk[1].mx = 0;
+    ctl.trk[0].cnt_mn = ctl.trk[0].cnt_mx = ctl.trk[1].cnt_mn = ctl.trk[1].cnt_mx = 0;
     ctl.batch.valid = 0;
-    ctl.dec.pipeline_only = 0;
+    for (int r = 0; r < KAI_MAX_RES; r++) ctl.dec.req[r] = 0;
+    ctl.dec.pipeline_only = ctl.dec.res = ctl.dec.strategy = ctl.dec.gpu_task = ctl.dec.best_effort = 0;
+    ctl.dec.nominated = ctl.dec.pred_class = -1;
     ctl.seq = p.seq0;
+    ctl.n_delta = 0;
     ctl.stop = 0;
   }
   __syncthreads();
   long long tk0 = clock64();
-
-  // ---- load the tile (coalesced per resource row) and the replica state ----
-  for (int ln = tid; ln < tile.count; ln += blockDim.x) {
-    int n = tile.base + ln;
-    for (int r = 0; r < s.R; r++) {
-      tile.I[r * tile.npc + ln] = s.idle[(size_t)r * s.N + n];
-      tile.L[r * tile.npc + ln] = s.rel[(size_t)r * s.N + n];
-    }
-    tile.Agpu[ln] = s.alloc[(size_t)KAI_RES_GPU * s.N + n];
-    tile.Acpu[ln] = s.alloc[(size_t)KAI_RES_CPU * s.N + n];
-    tile.gpu_count[ln] = s.gpu_count[n];
-    tile.rank[ln] = s.name_rank[n];
-    tile.flags[ln] = s.nflags[n];
-  }
   {
     Replica &rp = seq.rp;
     for (int i = tid; i < QR * s.Q; i += blockDim.x) {
       rp.q_alloc[i] = s.q_alloc[i];
       rp.q_alloc_np[i] = s.q_alloc_np[i];
-    }
-    for (int i = tid; i < s.T; i += blockDim.x) {
-      rp.t_status[i] = s.t_status[i];
-      rp.t_node[i] = s.t_node[i];
-      rp.t_node_status[i] = s.t_node_status[i];
-      rp.t_virtual[i] = s.t_virtual[i];
-    }
-    for (int i = tid; i < s.S; i += blockDim.x) {
-      rp.ps_active_alloc[i] = s.ps_cnt0[i];
-      rp.ps_pending[i] = s.ps_cnt0[s.S + i];
-      rp.ps_pipelined[i] = s.ps_cnt0[2 * s.S + i];
-    }
-    for (int i = tid; i < s.J; i += blockDim.x) {
-      rp.j_req_valid[i] = 0;
-      rp.j_key[i] = s.j_key0[i];
-      rp.leaf_heap[i] = s.leaf_sorted[i];
     }
     for (int i = tid; i < s.Q; i += blockDim.x) {
       int b = s.q_job_begin[i];
@@ -1417,13 +1587,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
     }
   }
   __syncthreads();
-  if (tid == 0) seq_init_job_order(seq);
-  __syncthreads();
-  if (tid == 0) seq.t_init = clock64() - tk0;
+  if (tid >= 32) return;  // the sequencer proper is warp 0
+  if (lane == 0) {
+    seq_init_job_order(seq);
+    seq.t_init = clock64() - tk0;
+  }
+  __syncwarp();
 
   // ---- allocate action main loop (actions/allocate/allocate.go:46-111) ----
   for (;;) {
-    if (tid == 0) {
+    if (lane == 0) {
       long long tk = clock64();
       int job = pop_next_job(seq);
       ctl.job = job;
@@ -1446,66 +1619,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
       if (seq.error) ctl.stop = 1;
       seq.t_pop += clock64() - tk;
     }
-    __syncthreads();
+    __syncwarp();
     if (ctl.job < 0 || ctl.stop) break;
     bool job_success = ctl.job_ok != 0;
     if (job_success) {
       const int n_items = ctl.n_items;
       for (int k = 0; k < n_items; k++) {
-        if (tid == 0) {
+        if (lane == 0) {
           long long tk = clock64();
           int t = seq.rp.tta[k];
-          ctl.item_ok = seq_prepare_task(seq, t) ? 1 : 0;
+          ctl.item_ok = seq_prepare_task(seq, t, ctl.job) ? 1 : 0;
           if (ctl.item_ok && ctl.use_batch) seq_apply_batched(seq, t);
           if (ctl.need_minmax) seq.minmax_exchanges++;
           seq.t_prep += clock64() - tk;
         }
-        __syncthreads();
+        __syncwarp();
         if (!ctl.item_ok) {
           job_success = false;
           break;
         }
         if (ctl.use_batch) continue;  // placed without a sweep (same-node batching)
-        if (ctl.need_minmax) {
-          unsigned int sq = ctl.seq;
-          exchange_minmax(p, ctl, tile, sq, sh_d, sh_i);
-          __syncthreads();
-          if (tid == 0) ctl.seq = sq + 1;
-          __syncthreads();
-        }
-        if (tid == 0) {
-          int tk = ctl.dec.gpu_task ? 0 : 1;
-          ctl.dec.mn = ctl.trk[tk].mn;
-          ctl.dec.mx = ctl.trk[tk].mx;
-        }
-        __syncthreads();
         long long tk1 = clock64();
-        Cand local = scan_tile(tile, ctl.dec, s, sh_warp);
-        if (tid < 32) {
-          long long tk2 = clock64();
-          local.score = __shfl_sync(0xffffffffu, local.score, 0);
-          local.rank = __shfl_sync(0xffffffffu, local.rank, 0);
-          local.ln = __shfl_sync(0xffffffffu, local.ln, 0);
-          unsigned int sq = ctl.seq;
-          exchange_candidates(p, ctl, tile, ctl.dec, local, sq, p.batching);
-          if (tid == 0) {
-            long long tk3 = clock64();
-            ctl.seq = sq + 1;
-            seq_apply_winner(seq, ctl.dec.task);
-            long long tk4 = clock64();
-            seq.t_scan += tk2 - tk1;
-            seq.t_xchg += tk3 - tk2;
-            seq.t_apply += tk4 - tk3;
-          }
+        if (ctl.need_minmax) {
+          seq_publish(p, ctl, DK_MINMAX);
+          seq_gather_minmax(p, ctl);
         }
-        __syncthreads();
+        seq_publish(p, ctl, DK_SCAN);
+        seq_gather_candidates(p, ctl);
+        if (lane == 0) {
+          long long tk3 = clock64();
+          seq_apply_winner(seq, ctl.dec.task);
+          long long tk4 = clock64();
+          seq.t_xchg += tk3 - tk1;
+          seq.t_apply += tk4 - tk3;
+        }
+        __syncwarp();
         if (!ctl.item_ok) {
           job_success = false;
           break;
         }
       }
     }
-    if (tid == 0) {
+    if (lane == 0) {
       long long tk = clock64();
       int job = ctl.job;
       if (job_success) {
@@ -1520,50 +1675,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
       if (seq.error) ctl.stop = 1;
       seq.t_finish += clock64() - tk;
     }
-    __syncthreads();
+    __syncwarp();
     if (ctl.stop) break;
   }
+  // ---- DONE record (carries the last deltas), write back the hot per-queue state and the counters ----
+  seq_publish(p, ctl, DK_DONE);
+  for (int i = lane; i < QR * s.Q; i += 32) {
+    s.q_alloc[i] = seq.rp.q_alloc[i];
+    s.q_alloc_np[i] = seq.rp.q_alloc_np[i];
+  }
+  if (lane == 0) {
+    p.counters[0] = seq.n_visits;
+    p.counters[1] = seq.sweeps;
+    p.counters[2] = seq.nodes_scanned;
+    p.counters[3] = seq.pods_placed;
+    p.counters[4] = seq.pods_evicted;
+    p.counters[5] = seq.minmax_exchanges;
+    p.counters[6] = seq.error;
+    p.counters[7] = ctl.seq + 1;
+    p.counters[8] = seq.t_init;
+    p.counters[9] = seq.t_pop;
+    p.counters[10] = seq.t_prep;
+    p.counters[11] = seq.t_scan;
+    p.counters[12] = seq.t_xchg;
+    p.counters[13] = seq.t_apply;
+    p.counters[14] = seq.t_finish;
+    p.counters[15] = seq.batched;
+  }
+}
 
-  // ---- write back: tiles by their owners, session state and counters by CTA 0 ----
-  __syncthreads();
-  for (int ln = tid; ln < tile.count; ln += blockDim.x) {
-    int n = tile.base + ln;
-    for (int r = 0; r < s.R; r++) {
-      s.idle[(size_t)r * s.N + n] = tile.I[r * tile.npc + ln];
-      s.rel[(size_t)r * s.N + n] = tile.L[r * tile.npc + ln];
-    }
-  }
-  if (blockIdx.x == 0) {
-    Replica &rp = seq.rp;
-    for (int i = tid; i < QR * s.Q; i += blockDim.x) {
-      s.q_alloc[i] = rp.q_alloc[i];
-      s.q_alloc_np[i] = rp.q_alloc_np[i];
-    }
-    for (int i = tid; i < s.T; i += blockDim.x) {
-      s.t_status[i] = rp.t_status[i];
-      s.t_node[i] = rp.t_node[i];
-      s.t_node_status[i] = rp.t_node_status[i];
-      s.t_virtual[i] = rp.t_virtual[i];
-    }
-    if (tid == 0) {
-      p.counters[0] = seq.n_visits;
-      p.counters[1] = seq.sweeps;
-      p.counters[2] = seq.nodes_scanned;
-      p.counters[3] = seq.pods_placed;
-      p.counters[4] = seq.pods_evicted;
-      p.counters[5] = seq.minmax_exchanges;
-      p.counters[6] = seq.error;
-      p.counters[7] = ctl.seq;
-      p.counters[8] = seq.t_init;
-      p.counters[9] = seq.t_pop;
-      p.counters[10] = seq.t_prep;
-      p.counters[11] = seq.t_scan;
-      p.counters[12] = seq.t_xchg;
-      p.counters[13] = seq.t_apply;
-      p.counters[14] = seq.t_finish;
-      p.counters[15] = seq.batched;
-    }
-  }
+// =============================================================================================
+// the kernel
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ ActionParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctl ctl;
+  __shared__ Tile tile;
+  __shared__ Seq seq;
+  __shared__ ScanShared scan_sh;
+  __shared__ Cand sh_warp[kThreads / 32];
+  __shared__ double sh_d[(kThreads / 32) * 4];
+  __shared__ int sh_i[(kThreads / 32) * 4];
+  if (blockIdx.x == 0)
+    sequencer_main(p, smem, ctl, seq);
+  else
+    scanner_main(p, smem, sh_warp, sh_d, sh_i, scan_sh, tile);
 }
 
 }  // namespace kai

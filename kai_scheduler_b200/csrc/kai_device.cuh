@@ -19,6 +19,8 @@ constexpr int QR = KAI_QRES;
 constexpr int kThreads = 512;          // threads per CTA of the action kernel
 constexpr int kMaxGrid = 1024;         // exchange slots per GPU
 constexpr uint32_t kNoRank = 0xFFFFFFFFu;
+constexpr int kDecWords = 16;         // tagged words of one decision record
+constexpr int kMaxDelta = 256;        // node deltas carried by one decision record
 
 constexpr int kActiveUsed = KAI_POD_ALLOCATED | KAI_POD_PIPELINED | KAI_POD_BINDING | KAI_POD_BOUND |
                             KAI_POD_RUNNING | KAI_POD_RELEASING;
@@ -77,6 +79,12 @@ struct DevSnap {
   int *leaf_sorted;            // [J] eligible jobs per leaf queue (arena offsets q_job_begin) in JobOrderFn order
   int *leaf_count;             // [Q]
   int *ps_cnt0;                // [3][S] tasks per podset: active-allocated, pending, pipelined
+  double *j_req;               // [J][3] cached GetTasksToAllocateInitResource
+  unsigned char *j_req_valid;  // [J]
+  Op *ops;                     // [ops_cap] statement log
+  int *tta;                    // [max_job_tasks + 1]
+  int *ps_order;               // [max_job_podsets + 1]
+  unsigned char *hot_global;   // hot arrays when they do not fit in shared memory
 };
 
 // Cached comparator inputs of one queue node (plugins/proportion/queue_order/queue_order.go:19-73)
@@ -86,8 +94,9 @@ struct QKey {
   unsigned char over, starved, viol, valid;
 };
 
-// Per-CTA replica of the mutable session state.  The "hot" arrays live in shared memory when they
-// fit (ActionParams.hot_in_smem), everything else in the per-CTA global arena.
+// Mutable state the sequencer CTA works on.  The "hot" per-queue arrays live in its shared memory when
+// they fit (ActionParams.hot_in_smem), otherwise in global memory; the cold arrays are the session
+// arrays in HBM/L2 themselves (single copy).
 struct Replica {
   // hot: per queue
   double *q_alloc, *q_alloc_np;  // [3][Q]
@@ -119,9 +128,9 @@ struct ActionParams {
   int nodes_per_cta;    // node rows per CTA (tile height)
   int node_base;        // first node row of this GPU's shard
   int node_count;       // node rows of this GPU's shard
-  unsigned char *replica_arena;  // grid * replica_bytes
-  size_t replica_bytes;
   int ops_cap;
+  unsigned long long *dbuf;  // decision record: [2][kDecWords] tagged 128-bit words (sequencer -> scanners)
+  int2 *delta;               // node delta list: [2][kMaxDelta] (node|code<<28, task)
   unsigned long long *xbuf;  // exchange slots: [2][kMaxGrid][8] u64 (tagged 128-bit words A, B, C, D)
   unsigned long long *mmbuf; // min/max exchange: [2][kMaxGrid][8] u64
   kai_job_visit *visits;     // [visits_cap]

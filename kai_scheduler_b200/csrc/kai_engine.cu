@@ -100,7 +100,8 @@ struct kai_engine {
   size_t smem_bytes = 0, replica_bytes = 0, tile_bytes = 0, hot_bytes = 0;
   bool hot_in_smem = false;
   int ops_cap = 0, visits_cap = 0;
-  unsigned long long *xbuf = nullptr, *mmbuf = nullptr;
+  unsigned long long *xbuf = nullptr, *mmbuf = nullptr, *dbuf = nullptr;
+  int2 *delta = nullptr;
   long long *counters = nullptr;
   kai_job_visit *d_visits = nullptr;
   double *fs_w = nullptr, *fs_rr = nullptr;
@@ -353,6 +354,15 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   size_t o_qla = reserve_up(QN * 8);
   size_t o_jkey = reserve_up((size_t)std::max(J, 1) * 8), o_leafs = reserve_up((size_t)std::max(J, 1) * 4);
   size_t o_leafc = reserve_up((size_t)std::max(Q, 1) * 4), o_pscnt = reserve_up((size_t)3 * std::max(S, 1) * 4);
+  size_t o_jreq = reserve_up((size_t)std::max(J, 1) * QR * 8), o_jreqv = reserve_up((size_t)std::max(J, 1));
+  const int ops_cap = 4 * max_job_tasks + 64;
+  size_t o_ops = reserve_up(sizeof(Op) * (size_t)ops_cap);
+  size_t o_tta = reserve_up((size_t)(max_job_tasks + 1) * 4), o_psord = reserve_up((size_t)(max_job_podsets + 1) * 4);
+  auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  // hot per-queue sequencer arrays — must match the carving in sequencer_main
+  const size_t hot = 2 * a16(sizeof(double) * QR * Q) + a16(sizeof(QKey) * (size_t)Q) + 5 * a16(sizeof(int) * (size_t)Q) +
+                     a16(sizeof(int) * (size_t)(top.size() + 1)) + a16((size_t)Q);
+  size_t o_hot = reserve_up(hot + 16);
   const size_t zero_begin = o_tvirt, zero_bytes = up - o_tvirt;
 
   CK(e->dsnap.reserve(up + 256));
@@ -482,61 +492,46 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   ds.leaf_sorted = (int *)(d + o_leafs);
   ds.leaf_count = (int *)(d + o_leafc);
   ds.ps_cnt0 = (int *)(d + o_pscnt);
+  ds.j_req = (double *)(d + o_jreq);
+  ds.j_req_valid = (unsigned char *)(d + o_jreqv);
+  ds.ops = (Op *)(d + o_ops);
+  ds.tta = (int *)(d + o_tta);
+  ds.ps_order = (int *)(d + o_psord);
+  ds.hot_global = d + o_hot;
 
   // ---------------- launch geometry of the action kernel ----------------
+  // CTA 0 = sequencer, CTAs 1..grid-1 = scanners that split the node rows
   int grid = std::min(e->num_sms, kMaxGrid);
   if (const char *g = getenv("KAI_GRID")) {
     int v = atoi(g);
-    if (v >= 1) grid = std::min(v, grid);
+    if (v >= 2) grid = std::min(v, grid);
   }
-  if (N > 0) grid = std::min(grid, N);  // at least one node per CTA when possible
-  grid = std::max(grid, 1);
-  if (const char *g = getenv("KAI_GRID_EXACT")) {  // tests: force CTAs without nodes as well
+  if (N > 0) grid = std::min(grid, N + 1);  // at least one node per scanner when possible
+  grid = std::max(grid, 2);
+  if (const char *g = getenv("KAI_GRID_EXACT")) {  // tests: force scanners without nodes as well
     int v = atoi(g);
-    if (v >= 1) grid = std::min(std::min(v, e->num_sms), kMaxGrid);
+    if (v >= 2) grid = std::min(std::min(v, e->num_sms), kMaxGrid);
   }
-  int npc = std::max(1, (N + grid - 1) / grid);
+  int npc = std::max(1, (N + (grid - 1) - 1) / (grid - 1));
   npc = (npc + 1) & ~1;  // keep the int arrays 8-byte aligned
   size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4), 16);
-  if (tile_bytes > (size_t)e->max_smem_optin - 4096)
+  const size_t smem_limit = (size_t)e->max_smem_optin - 24 * 1024;  // static shared memory of k_action
+  if (tile_bytes > smem_limit)
     return e->fail(KAI_ERR_UNSUPPORTED, "node tile does not fit in shared memory (N too large for one GPU tile)");
-  auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  // hot replica arrays — must match the carving in k_action
-  size_t hot = 2 * a16(sizeof(double) * QR * Q) + a16(sizeof(QKey) * (size_t)Q) + 5 * a16(sizeof(int) * (size_t)Q) +
-               a16(sizeof(int) * (size_t)(ds.n_top + 1)) + a16((size_t)Q);
-  bool hot_in_smem = tile_bytes + hot <= (size_t)e->max_smem_optin - 4096;
+  bool hot_in_smem = hot <= smem_limit;
   if (getenv("KAI_NO_SMEM_HOT")) hot_in_smem = false;
   e->grid = grid;
   e->npc = npc;
   e->tile_bytes = tile_bytes;
   e->hot_bytes = hot;
   e->hot_in_smem = hot_in_smem;
-  e->smem_bytes = tile_bytes + (hot_in_smem ? hot : 0);
-  e->ops_cap = 4 * max_job_tasks + 64;
+  e->smem_bytes = std::max(tile_bytes, hot_in_smem ? hot : (size_t)0);
+  e->ops_cap = ops_cap;
   e->visits_cap = std::max(16, 2 * J + T + 16);
-  {  // cold replica layout — must match the carving in k_action
-    size_t b = hot_in_smem ? 0 : hot;
-    auto take = [&](size_t bytes) { b += a16(bytes); };
-    take(sizeof(int) * (size_t)T);
-    take(sizeof(int) * (size_t)T);
-    take(sizeof(int) * (size_t)T);
-    take((size_t)T);
-    take(sizeof(int) * (size_t)S);
-    take(sizeof(int) * (size_t)S);
-    take(sizeof(int) * (size_t)S);
-    take(sizeof(double) * QR * (size_t)J);
-    take((size_t)J);
-    take(sizeof(unsigned long long) * (size_t)J);
-    take(sizeof(int) * (size_t)J);
-    take(sizeof(Op) * (size_t)e->ops_cap);
-    take(sizeof(int) * (size_t)(max_job_tasks + 1));
-    take(sizeof(int) * (size_t)(max_job_podsets + 1));
-    e->replica_bytes = align_up(b, 256);
-  }
-  CK(e->dreplica.reserve(e->replica_bytes * grid + 256));
   {
     size_t xb = (size_t)2 * kMaxGrid * 8 * 8;
-    size_t misc = 2 * xb + 256 + sizeof(long long) * 16 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096;
+    size_t misc = 2 * xb + 256 + sizeof(long long) * 16 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
+                  sizeof(unsigned long long) * 2 * kDecWords * 2 + sizeof(int2) * 2 * kMaxDelta + 1024;
     CK(e->dmisc.reserve(misc));
     e->xbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
     e->mmbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
@@ -544,6 +539,9 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     e->d_visits = e->dmisc.take<kai_job_visit>(e->visits_cap);
     e->fs_w = e->dmisc.take<double>(QN + 1);
     e->fs_rr = e->dmisc.take<double>(QN + 1);
+    e->dbuf = e->dmisc.take<unsigned long long>(2 * kDecWords * 2);
+    e->delta = e->dmisc.take<int2>(2 * kMaxDelta);
+    CK(cudaMemsetAsync(e->dbuf, 0, sizeof(unsigned long long) * 2 * kDecWords * 2, e->stream));
     CK(cudaMemsetAsync(e->xbuf, 0, xb, e->stream));
     CK(cudaMemsetAsync(e->mmbuf, 0, xb, e->stream));
     e->seq = 2;
@@ -651,8 +649,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   p.nodes_per_cta = e->npc;
   p.node_base = 0;
   p.node_count = e->N;
-  p.replica_arena = e->dreplica.base;
-  p.replica_bytes = e->replica_bytes;
+  p.dbuf = e->dbuf;
+  p.delta = e->delta;
   p.ops_cap = e->ops_cap;
   p.xbuf = e->xbuf;
   p.mmbuf = e->mmbuf;
