@@ -183,6 +183,7 @@ struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   int visits_cap;
   int error;
   long long t_pop, t_prep, t_scan, t_xchg, t_apply, t_finish, t_init;  // clock64 phase totals (thread 0)
+  long long t_key, n_key, t_tta, t_heap;
 };
 
 __device__ __forceinline__ double &q_alloc(Seq &q, int r, int qi) { return q.rp.q_alloc[(size_t)r * q.s->Q + qi]; }
@@ -571,6 +572,8 @@ __device__ int best_job(Seq &q, int qi) {  // :283-292 getBestJobFromNode
 __device__ const QKey &queue_key(Seq &q, int qi) {
   QKey &k = q.rp.qkey[qi];
   if (k.valid) return k;
+  long long tkk = clock64();
+  q.n_key++;
   const DevSnap &s = *q.s;
   const double *req = job_init_resource(q, best_job(q, qi));
   bool over = true, starved = true, viol = false;
@@ -596,6 +599,7 @@ __device__ const QKey &queue_key(Seq &q, int qi) {
   k.drf = dr;
   k.priority = __ldg(&s.q_priority[qi]);
   k.valid = 1;
+  q.t_key += clock64() - tkk;
   return k;
 }
 __device__ bool node_less(Seq &q, int l, int r) {  // :256-278 buildNodeOrderFn (pending order)
@@ -1000,6 +1004,26 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
 // =============================================================================================
 // sequencer <-> scanner protocol
 // =============================================================================================
+// Watchdog for the spin waits: a wait that does not complete within ~2^22 polls records (code, seq, who)
+// in counters[24..27], raises the abort flag and lets every waiter fall through so that the kernel ends
+// and the host reports KAI_ERR_CUDA instead of hanging the GPU.
+struct Spin {
+  unsigned int n = 0;
+  __device__ __forceinline__ bool expired(const ActionParams &p, int code, unsigned int seq, int who) {
+    if ((++n & 0x3ffu) != 0) return false;
+    volatile long long *c = p.counters;
+    if (c[24] != 0) return true;
+    if (n >= (1u << 22)) {
+      if (atomicCAS((unsigned long long *)&p.counters[24], 0ull, (unsigned long long)code) == 0ull) {
+        c[25] = seq;
+        c[26] = who;
+        c[27] = blockIdx.x;
+      }
+      return true;
+    }
+    return false;
+  }
+};
 // decision record words (each stored as {data, tag}):
 //   0  kind | res<<8 | strategy<<16 | bits<<24 | n_delta<<32      1  nominated | pred_class<<32
 //   2..9 req[0..7]      10,11 gpu tracker mn,mx      12,13 cpu tracker mn,mx
@@ -1045,9 +1069,12 @@ __device__ void seq_gather_candidates(const ActionParams &p, Ctl &ctl) {
   for (int c = lane; c < p.grid - 1; c += 32) {
     const unsigned long long *slot = buf + (size_t)c * kSlotWords;
     unsigned long long lo, hi;
-    do {
-      ld_relaxed_b128(slot, lo, hi);
-    } while ((unsigned int)(hi >> 40) != tag);
+    {
+      Spin spin;
+      do {
+        ld_relaxed_b128(slot, lo, hi);
+      } while (((unsigned int)(hi >> 40) != tag) && !spin.expired(p, 1, (unsigned int)seq, (int)(c)));
+    }
     double sc = __longlong_as_double((long long)lo);
     uint32_t rk = (uint32_t)(hi & 0xffffffu);
     if (better(sc, rk, bs, brank)) {
@@ -1083,18 +1110,24 @@ __device__ void seq_gather_candidates(const ActionParams &p, Ctl &ctl) {
         double a = 0;
         if (f & WF_A_LT_MN) {  // a new global minimum: fetch its value
           unsigned long long lo, hi;
-          do {
-            ld_relaxed_b128(slot + 2 + 2 * k, lo, hi);
-          } while ((unsigned int)hi != tag);
+          {
+            Spin spin;
+            do {
+              ld_relaxed_b128(slot + 2 + 2 * k, lo, hi);
+            } while (((unsigned int)hi != tag) && !spin.expired(p, 2, (unsigned int)seq, (int)(bslot)));
+          }
           a = __longlong_as_double((long long)lo);
         }
         if (f) track_decrease(ctl.trk[k], f, a);
       }
       if (repeat) {
         unsigned long long lo, hi;
-        do {
-          ld_relaxed_b128(slot + 6, lo, hi);
-        } while ((unsigned int)hi != tag);
+        {
+          Spin spin;
+          do {
+            ld_relaxed_b128(slot + 6, lo, hi);
+          } while (((unsigned int)hi != tag) && !spin.expired(p, 3, (unsigned int)seq, (int)(bslot)));
+        }
         ctl.batch.valid = 1;
         ctl.batch.node = ctl.win.node;
         ctl.batch.to_idle = (bflags & SLOT_TO_IDLE) ? 1 : 0;
@@ -1121,9 +1154,12 @@ __device__ void seq_gather_minmax(const ActionParams &p, Ctl &ctl) {
     const unsigned long long *slot = buf + (size_t)cta * kSlotWords;
     for (int k = 0; k < 2; k++) {
       unsigned long long lo, hi;
-      do {
-        ld_relaxed_b128(slot + 4 * k, lo, hi);
-      } while ((hi >> 32) != (tag & 0xffffffffu));
+      {
+        Spin spin;
+        do {
+          ld_relaxed_b128(slot + 4 * k, lo, hi);
+        } while (((hi >> 32) != (tag & 0xffffffffu)) && !spin.expired(p, 4, (unsigned int)seq, (int)(cta)));
+      }
       double v = __longlong_as_double((long long)lo);
       int cnt = (int)(hi & 0xffffffffu);
       if (cnt > 0) {
@@ -1133,9 +1169,12 @@ __device__ void seq_gather_minmax(const ActionParams &p, Ctl &ctl) {
         } else if (v == gmn[k])
           cmn[k] += cnt;
       }
-      do {
-        ld_relaxed_b128(slot + 4 * k + 2, lo, hi);
-      } while ((hi >> 32) != (tag & 0xffffffffu));
+      {
+        Spin spin;
+        do {
+          ld_relaxed_b128(slot + 4 * k + 2, lo, hi);
+        } while (((hi >> 32) != (tag & 0xffffffffu)) && !spin.expired(p, 5, (unsigned int)seq, (int)(cta)));
+      }
       v = __longlong_as_double((long long)lo);
       cnt = (int)(hi & 0xffffffffu);
       if (cnt > 0) {
@@ -1194,9 +1233,12 @@ __device__ void seq_flush_deltas(Seq &q) {
   const unsigned int tag = c.seq & 0xffffffu;
   for (int cta = 0; cta < p.grid - 1; cta++) {
     unsigned long long lo, hi;
-    do {
-      ld_relaxed_b128(buf + (size_t)cta * kSlotWords, lo, hi);
-    } while ((unsigned int)(hi >> 40) != tag);
+    {
+      Spin spin;
+      do {
+        ld_relaxed_b128(buf + (size_t)cta * kSlotWords, lo, hi);
+      } while (((unsigned int)(hi >> 40) != tag) && !spin.expired(p, 6, (unsigned int)c.seq, (int)(cta)));
+    }
   }
   c.seq++;
   c.n_delta = 0;
@@ -1360,9 +1402,12 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       if (lane < kDecWords) {
         const unsigned long long *rec = p.dbuf + (size_t)(seq & 1) * kDecWords * 2 + 2 * lane;
         unsigned long long lo, hi;
-        do {
-          ld_relaxed_b128(rec, lo, hi);
-        } while (hi != (unsigned long long)seq);
+        {
+          Spin spin;
+          do {
+            ld_relaxed_b128(rec, lo, hi);
+          } while ((hi != (unsigned long long)seq) && !spin.expired(p, 7, (unsigned int)seq, (int)(lane)));
+        }
         sh.dw[lane] = lo;
       }
       __threadfence();  // acquire side: the delta list written before the record is now visible
@@ -1422,7 +1467,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       __syncthreads();
     }
     const int kind = sh.kind;
-    if (kind == DK_DONE) break;
+    if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
     if (kind == DK_SCAN) {
       Cand local = scan_tile(tile, sh.dec, s, sh_warp);
@@ -1556,6 +1601,7 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     seq.visits_cap = p.visits_cap;
     seq.error = 0;
     seq.t_pop = seq.t_prep = seq.t_scan = seq.t_xchg = seq.t_apply = seq.t_finish = seq.t_init = 0;
+    seq.t_key = seq.n_key = seq.t_tta = seq.t_heap = 0;
     ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
     ctl.trk[0].mn = ctl.trk[1].mn = DBL_MAX;
     ctl.trk[0].mx = ctl.trk[1].mx = 0;
@@ -1605,7 +1651,10 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
       if (job >= 0) {
         seq.n_ops = 0;
         // common/allocate.go:20-36 AllocateJob
+        long long tkt = clock64();
+        seq.t_heap += tkt - tk;
         int n = tasks_to_allocate(seq, job, true, nullptr);
+        seq.t_tta += clock64() - tkt;
         double req[QR] = {0, 0, 0};
         for (int k = 0; k < n; k++)
           for (int r = 0; r < QR; r++) req[r] = __dadd_rn(req[r], __ldg(&s.t_req[(size_t)seq.rp.tta[k] * s.R + r]));
@@ -1616,7 +1665,7 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
           ctl.job_ok = 1;
         }
       }
-      if (seq.error) ctl.stop = 1;
+      if (seq.error || ((volatile long long *)p.counters)[24] != 0) ctl.stop = 1;
       seq.t_pop += clock64() - tk;
     }
     __syncwarp();
@@ -1696,11 +1745,14 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     p.counters[8] = seq.t_init;
     p.counters[9] = seq.t_pop;
     p.counters[10] = seq.t_prep;
-    p.counters[11] = seq.t_scan;
+    p.counters[11] = seq.t_key;
     p.counters[12] = seq.t_xchg;
     p.counters[13] = seq.t_apply;
     p.counters[14] = seq.t_finish;
     p.counters[15] = seq.batched;
+    p.counters[16] = seq.n_key;
+    p.counters[17] = seq.t_tta;
+    p.counters[18] = seq.t_heap;
   }
 }
 

@@ -530,12 +530,12 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->visits_cap = std::max(16, 2 * J + T + 16);
   {
     size_t xb = (size_t)2 * kMaxGrid * 8 * 8;
-    size_t misc = 2 * xb + 256 + sizeof(long long) * 16 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
+    size_t misc = 2 * xb + 256 + sizeof(long long) * 32 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
                   sizeof(unsigned long long) * 2 * kDecWords * 2 + sizeof(int2) * 2 * kMaxDelta + 1024;
     CK(e->dmisc.reserve(misc));
     e->xbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
     e->mmbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
-    e->counters = e->dmisc.take<long long>(16);
+    e->counters = e->dmisc.take<long long>(32);
     e->d_visits = e->dmisc.take<kai_job_visit>(e->visits_cap);
     e->fs_w = e->dmisc.take<double>(QN + 1);
     e->fs_rr = e->dmisc.take<double>(QN + 1);
@@ -668,13 +668,13 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (max_blocks < 1 || max_blocks * e->num_sms < e->grid)
     return e->fail(KAI_ERR_CUDA, "action kernel cannot be made co-resident");
   void *args[] = {(void *)&p};
-  CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 16, e->stream));
+  CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 32, e->stream));
   cudaEventRecord(e->ev[2], e->stream);
   if (e->J > 0) k_prep_jobs<<<std::min(e->num_sms * 8, (e->J + 255) / 256), 256, 0, e->stream>>>(e->ds, 1, 1);
   if (e->Q > 0) k_prep_queues<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->ds);
   CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
   cudaEventRecord(e->ev[3], e->stream);
-  long long c[16];
+  long long c[32];
   CK(cudaMemcpyAsync(c, e->counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   float ms = 0;
@@ -686,10 +686,17 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   e->stats.kernel_launches += 1 + (e->J > 0) + (e->Q > 0);
   e->seq = (unsigned int)c[7];
   if (getenv("KAI_PROFILE")) {
-    const char *nm[] = {"init", "pop", "prepare", "scan", "exchange", "apply", "finish"};
+    const char *nm[] = {"init", "pop", "prepare", "keycalc", "exchange", "apply", "finish"};
     fprintf(stderr, "[kai] action %.3f ms, %lld sweeps, %lld batched placements, %lld minmax exchanges, hot_in_smem=%d; CTA0 thread0 cycles:", ms, c[1], c[15], c[5], (int)e->hot_in_smem);
     for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%lld", nm[i], c[8 + i]);
-    fprintf(stderr, "\n");
+    fprintf(stderr, " n_key=%lld tta=%lld popheap=%lld\n", c[16], c[17], c[18]);
+  }
+  if (c[24] != 0) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "device protocol watchdog: wait code %lld seq %lld who %lld cta %lld (seq0 %u, end seq %lld)",
+             c[24], c[25], c[26], c[27], p.seq0, c[7]);
+    e->loaded = false;
+    return e->fail(KAI_ERR_CUDA, msg);
   }
   if (c[6] != 0) return e->fail(KAI_ERR_CUDA, "device sequencer overflow (statement log)");
   return download(e, out, c[0], c[3], c[4]);
