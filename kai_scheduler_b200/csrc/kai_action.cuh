@@ -50,7 +50,7 @@ __global__ void k_prep_jobs(DevSnap s, int filter_non_pending, int filter_unread
     for (int ps = s.j_ps_begin[j]; ps < s.j_ps_begin[j + 1]; ps++) {
       int act = 0, pend = 0, pipe = 0, alive = 0, gated = 0;
       for (int i = s.ps_task_begin[ps]; i < s.ps_task_begin[ps + 1]; i++) {
-        int st = s.t_status[i];  // tasks of a podset are contiguous; order is irrelevant for counting
+        int st = s.t_status[i];  // tasks of a podset are contiguous
         if (st & kActiveAllocated) act++;
         if (st == KAI_POD_PENDING) pend++;
         if (st == KAI_POD_PIPELINED) pipe++;
@@ -72,24 +72,45 @@ __global__ void k_prep_jobs(DevSnap s, int filter_non_pending, int filter_unread
                     s.q_nchildren[q] == 0;  // input_jobs.go:24-63
     s.j_key0[j] = eligible ? make_job_key(s.j_priority[j], cls, s.j_order_rank[j]) : kKeyNone;
     // GetTasksToAllocateInitResource(job, isRealAllocation=false) (allocation_info.go:87-113) for the common
-    // single-podset job; other jobs are evaluated lazily by the sequencer
+    // single-podset job; other jobs are evaluated lazily by the sequencer.  Tasks of a podset are stored in
+    // TaskOrderFn order (the host renumbers them), so "the first k that should allocate" is a linear scan.
     s.j_req_valid[j] = 0;
-    if (s.j_ps_begin[j + 1] - s.j_ps_begin[j] == 1) {
-      int ps = s.j_ps_begin[j];
+    JobRec rec;
+    rec.req0[0] = rec.req0[1] = rec.req0[2] = 0;
+    rec.n_tta = -1;
+    rec.ps0 = s.j_ps_begin[j];
+    rec.n_podsets = s.j_ps_begin[j + 1] - s.j_ps_begin[j];
+    rec.tb = rec.n_podsets > 0 ? s.ps_task_begin[rec.ps0] : 0;
+    rec.cnt[0] = rec.cnt[1] = rec.cnt[2] = 0;
+    rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+    if (rec.n_podsets == 1) {
+      int ps = rec.ps0;
       int act = s.ps_cnt0[ps], m = s.ps_min[ps];
+      rec.cnt[0] = act;
+      rec.cnt[1] = s.ps_cnt0[s.S + ps];
+      rec.cnt[2] = s.ps_cnt0[2 * s.S + ps];
       int max_tasks = act >= m ? 1 : m - act;
       double sum[QR] = {0, 0, 0};
       int taken = 0;
-      for (int i = s.ps_task_begin[ps]; i < s.ps_task_begin[ps + 1] && taken < max_tasks; i++) {
-        int t = s.ps_sorted_tasks[i];
+      bool prefix = true;  // the selected tasks are exactly the first `taken` tasks and all are Pending
+      for (int t = s.ps_task_begin[ps]; t < s.ps_task_begin[ps + 1] && taken < max_tasks; t++) {
         int st = s.t_status[t];
-        if (!(st == KAI_POD_PENDING || (st == KAI_POD_RELEASING && s.t_virtual[t]))) continue;
+        if (!(st == KAI_POD_PENDING || (st == KAI_POD_RELEASING && s.t_virtual[t]))) {
+          prefix = false;
+          continue;
+        }
+        if (st != KAI_POD_PENDING) prefix = false;
         for (int r = 0; r < QR; r++) sum[r] = __dadd_rn(sum[r], s.t_req[(size_t)t * s.R + r]);
         taken++;
       }
-      for (int r = 0; r < QR; r++) s.j_req[(size_t)j * QR + r] = sum[r];
+      for (int r = 0; r < QR; r++) {
+        s.j_req[(size_t)j * QR + r] = sum[r];
+        rec.req0[r] = sum[r];
+      }
       s.j_req_valid[j] = 1;
+      if (prefix && act == 0 && rec.cnt[2] == 0) rec.n_tta = taken;
     }
+    s.jrec[j] = rec;
   }
 }
 
@@ -156,6 +177,9 @@ struct Ctl {  // sequencer control block (shared memory of CTA 0), written by la
   Track trk[2];  // 0 gpu, 1 cpu
   Batch batch;
   unsigned long long dw[kDecWords];
+  // context of the job being allocated: its podset counters stay here and are written back at the end
+  int ctx_job, ctx_ps, ctx_fresh, ctx_queue, ctx_preempt, ctx_base;
+  int ctx_cnt[3];
 };
 
 struct Tile {  // shared-memory node tile of this CTA
@@ -194,6 +218,20 @@ __device__ __forceinline__ void invalidate_chain(Seq &q, int qi) {
   for (int c = qi; c >= 0; c = __ldg(&q.s->q_parent[c])) q.rp.qkey[c].valid = 0;
 }
 
+__device__ __forceinline__ bool job_touched(const Seq &q, int j) { return (q.rp.touched[j >> 5] >> (j & 31)) & 1u; }
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+// podset status counters: those of the job being allocated live in the control block
+__device__ __forceinline__ int ps_get(const Seq &q, int ps, int which) {
+  if (ps == q.ctl->ctx_ps) return q.ctl->ctx_cnt[which];
+  return q.rp.ps_active_alloc[(size_t)which * q.s->S + ps];
+}
+__device__ __forceinline__ void ps_add(Seq &q, int ps, int which, int d) {
+  if (ps == q.ctl->ctx_ps)
+    q.ctl->ctx_cnt[which] += d;
+  else
+    q.rp.ps_active_alloc[(size_t)which * q.s->S + ps] += d;
+}
+
 // ---- PodInfo helpers ----
 __device__ __forceinline__ bool should_allocate(const Seq &q, int t, bool real) {  // pod_info.go:518-521
   int st = q.rp.t_status[t];
@@ -206,12 +244,11 @@ __device__ void seq_flush_deltas(Seq &q);  // single-threaded FLUSH exchange whe
 __device__ void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
   if (c.n_delta >= kMaxDelta) seq_flush_deltas(q);
-  q.p->delta[(size_t)(c.seq & 1) * kMaxDelta + c.n_delta] = make_int2(node | (code << 28), t);
+  unsigned long long data = (unsigned long long)(unsigned int)(node | (code << 28)) | ((unsigned long long)(unsigned int)t << 32);
+  st_relaxed_b128(q.p->delta + ((size_t)(c.seq & 1) * kMaxDelta + c.n_delta) * 2, data, (unsigned long long)c.seq);
   c.n_delta++;
 }
-__device__ void node_add_task(Seq &q, int t) {
-  int n = q.rp.t_node[t];
-  int st = q.rp.t_status[t];
+__device__ void node_add_task(Seq &q, int t, int n, int st) {  // n = task node, st = task status (just set)
   q.rp.t_node_status[t] = st;
   emit_delta(q, n, st == KAI_POD_RELEASING ? ND_ADD_RELEASING : (st == KAI_POD_PIPELINED ? ND_ADD_PIPELINED : ND_ADD), t);
 }
@@ -232,29 +269,45 @@ __device__ __forceinline__ void apply_delta_row(double &I, double &L, int code, 
 }
 
 // ---- PodGroupInfo.UpdateTaskStatus (job_info.go:253-264) + podset counters ----
-__device__ void set_status(Seq &q, int t, int status) {
-  int old = q.rp.t_status[t];
-  int ps = __ldg(&q.s->t_podset[t]);
-  if (old & kActiveAllocated) q.rp.ps_active_alloc[ps]--;
-  if (status & kActiveAllocated) q.rp.ps_active_alloc[ps]++;
-  if (old == KAI_POD_PENDING) q.rp.ps_pending[ps]--;
-  if (status == KAI_POD_PENDING) q.rp.ps_pending[ps]++;
-  if (old == KAI_POD_PIPELINED) q.rp.ps_pipelined[ps]--;
-  if (status == KAI_POD_PIPELINED) q.rp.ps_pipelined[ps]++;
+// job / old may be passed when the caller already knows them (saves dependent L2 loads)
+__device__ void set_status(Seq &q, int t, int status, int job = -1, int old = -1) {
+  Ctl &c = *q.ctl;
+  if (old < 0) old = q.rp.t_status[t];
+  int j = job >= 0 ? job : __ldg(&q.s->t_job[t]);
+  int ps = (j == c.ctx_job && c.ctx_ps >= 0) ? c.ctx_ps : __ldg(&q.s->t_podset[t]);
+  if (old & kActiveAllocated) ps_add(q, ps, 0, -1);
+  if (status & kActiveAllocated) ps_add(q, ps, 0, +1);
+  if (old == KAI_POD_PENDING) ps_add(q, ps, 1, -1);
+  if (status == KAI_POD_PENDING) ps_add(q, ps, 1, +1);
+  if (old == KAI_POD_PIPELINED) ps_add(q, ps, 2, -1);
+  if (status == KAI_POD_PIPELINED) ps_add(q, ps, 2, +1);
   q.rp.t_status[t] = status;
-  int j = __ldg(&q.s->t_job[t]);
   q.rp.j_req_valid[j] = 0;
-  invalidate_chain(q, __ldg(&q.s->j_queue[j]));  // the job may be the best pending job of its queue chain
+  q.rp.touched[j >> 5] |= 1u << (j & 31);
+  int qi = j == c.ctx_job ? c.ctx_queue : __ldg(&q.s->j_queue[j]);
+  invalidate_chain(q, qi);  // the job may be the best pending job of its queue chain
 }
 
 // ---- proportion event handlers (proportion.go:443-489) ----
-__device__ void queue_allocate(Seq &q, int t, bool add) {
+__device__ void queue_allocate(Seq &q, int t, bool add, int job = -1) {
   const DevSnap &s = *q.s;
-  int j = __ldg(&s.t_job[t]);
-  bool preemptible = (__ldg(&s.j_flags[j]) & KAI_JOB_PREEMPTIBLE) != 0;
+  Ctl &c = *q.ctl;
+  int j = job >= 0 ? job : __ldg(&s.t_job[t]);
+  bool preemptible;
+  int qi;
+  if (j == c.ctx_job) {
+    preemptible = c.ctx_preempt != 0;
+    qi = c.ctx_queue;
+  } else {
+    preemptible = (__ldg(&s.j_flags[j]) & KAI_JOB_PREEMPTIBLE) != 0;
+    qi = __ldg(&s.j_queue[j]);
+  }
   double v[QR];
-  for (int r = 0; r < QR; r++) v[r] = __ldg(&s.t_req[(size_t)t * s.R + r]);
-  for (int qi = __ldg(&s.j_queue[j]); qi >= 0; qi = __ldg(&s.q_parent[qi])) {
+  if (t == c.dec.task)
+    for (int r = 0; r < QR; r++) v[r] = c.dec.req[r];
+  else
+    for (int r = 0; r < QR; r++) v[r] = __ldg(&s.t_req[(size_t)t * s.R + r]);
+  for (; qi >= 0; qi = __ldg(&s.q_parent[qi])) {
     for (int r = 0; r < QR; r++) {
       double &a = q_alloc(q, r, qi);
       a = add ? __dadd_rn(a, v[r]) : __dsub_rn(a, v[r]);
@@ -275,46 +328,40 @@ __device__ void push_op(Seq &q, const Op &op) {
   }
   q.rp.ops[q.n_ops++] = op;
 }
-__device__ void stmt_allocate(Seq &q, int t, int n) {  // :297-358
+// `fresh`: the task belongs to the context job and is known to be Pending / unplaced / not virtual
+__device__ void stmt_place(Seq &q, int t, int n, int kind, bool fresh) {  // :297-358 Allocate, :197-295 Pipeline
   Op op;
-  op.kind = OP_ALLOCATE;
+  op.kind = kind;
   op.task = t;
-  op.prev_status = q.rp.t_status[t];
-  op.prev_node = q.rp.t_node[t];
+  if (fresh) {
+    op.prev_status = KAI_POD_PENDING;
+    op.prev_node = -1;
+    op.prev_virtual = 0;
+  } else {
+    op.prev_status = q.rp.t_status[t];
+    op.prev_node = q.rp.t_node[t];
+    op.prev_virtual = q.rp.t_virtual[t];
+  }
   op.next_node = n;
-  op.prev_virtual = q.rp.t_virtual[t];
   op.undo_index = -1;
   op.pad = 0;
-  set_status(q, t, KAI_POD_ALLOCATED);
+  int job = fresh ? q.ctl->ctx_job : -1;
+  int st = kind == OP_ALLOCATE ? KAI_POD_ALLOCATED : KAI_POD_PIPELINED;
+  set_status(q, t, st, job, op.prev_status);
   q.rp.t_node[t] = n;
-  node_add_task(q, t);
-  queue_allocate(q, t, true);
+  node_add_task(q, t, n, st);
+  queue_allocate(q, t, true, job);
   push_op(q, op);
   q.rp.t_virtual[t] = 1;
 }
+__device__ void stmt_allocate(Seq &q, int t, int n, bool fresh = false) { stmt_place(q, t, n, OP_ALLOCATE, fresh); }
+__device__ void stmt_pipeline(Seq &q, int t, int n, bool fresh = false) { stmt_place(q, t, n, OP_PIPELINE, fresh); }
 __device__ void unallocate(Seq &q, int t, int prev_virtual) {  // :392-427
   set_status(q, t, KAI_POD_PENDING);
   node_remove_task(q, t, q.rp.t_node[t]);
   q.rp.t_node[t] = -1;
   q.rp.t_virtual[t] = (unsigned char)prev_virtual;
   queue_allocate(q, t, false);
-}
-__device__ void stmt_pipeline(Seq &q, int t, int n) {  // :197-295 (task not yet on the node)
-  Op op;
-  op.kind = OP_PIPELINE;
-  op.task = t;
-  op.prev_status = q.rp.t_status[t];
-  op.prev_node = q.rp.t_node[t];
-  op.next_node = n;
-  op.prev_virtual = q.rp.t_virtual[t];
-  op.undo_index = -1;
-  op.pad = 0;
-  set_status(q, t, KAI_POD_PIPELINED);
-  q.rp.t_node[t] = n;
-  node_add_task(q, t);
-  queue_allocate(q, t, true);
-  push_op(q, op);
-  q.rp.t_virtual[t] = 1;
 }
 __device__ void unpipeline(Seq &q, const Op &op) {  // :432-476
   int t = op.task;
@@ -379,7 +426,7 @@ __device__ void stmt_commit(Seq &q) {  // :536-571
 
 // ---- podset / task selection (api/podgroup_info/allocation_info.go) ----
 __device__ bool podset_less(const Seq &q, int a, int b) {  // subgroup_order.go:31-62, name order = index order
-  int ln = q.rp.ps_active_alloc[a], rn = q.rp.ps_active_alloc[b];
+  int ln = ps_get(q, a, 0), rn = ps_get(q, b, 0);
   int lm = __ldg(&q.s->ps_min[a]), rm = __ldg(&q.s->ps_min[b]);
   bool lsat = ln >= lm, rsat = rn >= rm;
   if (!lsat && !rsat) return a < b;
@@ -416,19 +463,19 @@ __device__ int tasks_to_allocate(Seq &q, int job, bool real, double *sum) {
   int nps = sorted_podsets(q, job, order);
   int unsat = 0;
   for (int k = 0; k < nps; k++)
-    if (q.rp.ps_active_alloc[order[k]] < __ldg(&s.ps_min[order[k]])) unsat++;
+    if (ps_get(q, order[k], 0) < __ldg(&s.ps_min[order[k]])) unsat++;
   int max_sets = unsat > 0 ? unsat : 1;
   int n_sets = 0, n = 0;
   if (sum) sum[0] = sum[1] = sum[2] = 0.0;
   for (int k = 0; k < nps && n_sets < max_sets; k++) {
     int ps = order[k];
     int tb = __ldg(&s.ps_task_begin[ps]), te = __ldg(&s.ps_task_begin[ps + 1]);
-    int n_alloc = q.rp.ps_active_alloc[ps];
+    int n_alloc = ps_get(q, ps, 0);
     int m = __ldg(&s.ps_min[ps]);
     int max_tasks = n_alloc >= m ? 1 : m - n_alloc;  // :144-153
     int taken = 0;
     for (int i = tb; i < te && taken < max_tasks; i++) {
-      int t = __ldg(&s.ps_sorted_tasks[i]);
+      int t = i;  // tasks of a podset are stored in TaskOrderFn order
       if (!should_allocate(q, t, real)) continue;
       if (sum)
         for (int r = 0; r < QR; r++) sum[r] = __dadd_rn(sum[r], __ldg(&s.t_req[(size_t)t * s.R + r]));
@@ -442,6 +489,10 @@ __device__ int tasks_to_allocate(Seq &q, int job, bool real, double *sum) {
   return n;
 }
 __device__ const double *job_init_resource(Seq &q, int job) {
+  if (!job_touched(q, job)) {
+    const JobRec *rec = q.s->jrec + job;
+    if (rec->n_podsets == 1) return rec->req0;
+  }
   double *c = q.rp.j_req + (size_t)job * QR;
   if (!q.rp.j_req_valid[job]) {
     tasks_to_allocate(q, job, false, c);
@@ -451,14 +502,14 @@ __device__ const double *job_init_resource(Seq &q, int job) {
 }
 __device__ bool has_tasks_to_allocate(const Seq &q, int job) {  // :18-25 (isRealAllocation = true)
   for (int ps = __ldg(&q.s->j_ps_begin[job]); ps < __ldg(&q.s->j_ps_begin[job + 1]); ps++)
-    if (q.rp.ps_pending[ps] > 0) return true;
+    if (ps_get(q, ps, 1) > 0) return true;
   return false;
 }
 // job_info.go:443-464 ShouldPipelineJob
 __device__ bool should_pipeline_job(const Seq &q, int job) {
   for (int ps = __ldg(&q.s->j_ps_begin[job]); ps < __ldg(&q.s->j_ps_begin[job + 1]); ps++) {
-    int pipe = q.rp.ps_pipelined[ps];
-    if (pipe > 0 && q.rp.ps_active_alloc[ps] - pipe < __ldg(&q.s->ps_min[ps])) return true;
+    int pipe = ps_get(q, ps, 2);
+    if (pipe > 0 && ps_get(q, ps, 0) - pipe < __ldg(&q.s->ps_min[ps])) return true;
   }
   return false;
 }
@@ -535,7 +586,7 @@ __device__ int leaf_pop(Seq &q, int qi) {
 __device__ int elastic_class(const Seq &q, int job) {  // plugins/elastic/elastic.go:50-63
   bool exactly = true;
   for (int ps = __ldg(&q.s->j_ps_begin[job]); ps < __ldg(&q.s->j_ps_begin[job + 1]); ps++) {
-    int n = q.rp.ps_active_alloc[ps], m = __ldg(&q.s->ps_min[ps]);
+    int n = ps_get(q, ps, 0), m = __ldg(&q.s->ps_min[ps]);
     if (n < m) return 0;
     if (n > m) exactly = false;
   }
@@ -752,6 +803,14 @@ __device__ int pop_next_job(Seq &q) {  // :61-88
     ni = get_next_node(q, q.rp.child_heap + __ldg(&q.s->q_child_begin[ni]), q.rp.child_len[ni], ni);
   if (ni < 0) return -1;
   int job = leaf_pop(q, ni);
+  {  // warm L1 for the next pops of this queue
+    int h = q.rp.leaf_head[ni], e = q.rp.leaf_end[ni];
+    if (h < e) {
+      const JobRec *r1 = q.s->jrec + q.rp.leaf_heap[h];
+      prefetch_l1(r1);
+      if (h + 1 < e) prefetch_l1(q.s->jrec + q.rp.leaf_heap[h + 1]);
+    }
+  }
   invalidate_chain(q, ni);
   handle_pop(q, ni);
   return job;
@@ -1048,8 +1107,7 @@ __device__ void build_decision_words(Ctl &c, int kind, int batching) {
 __device__ void seq_publish(const ActionParams &p, Ctl &ctl, int kind) {
   const int lane = threadIdx.x & 31;
   if (lane == 0) {
-    build_decision_words(ctl, kind, p.batching);
-    __threadfence();  // node deltas (plain stores) become visible before the record's tags
+    build_decision_words(ctl, kind, p.batching);  // deltas are self-validating tagged words: no fence
   }
   __syncwarp();
   unsigned long long *rec = p.dbuf + (size_t)(ctl.seq & 1) * kDecWords * 2;
@@ -1226,7 +1284,6 @@ __device__ void seq_flush_deltas(Seq &q) {
   const ActionParams &p = *q.p;
   Ctl &c = *q.ctl;
   build_decision_words(c, DK_FLUSH, 0);
-  __threadfence();
   unsigned long long *rec = p.dbuf + (size_t)(c.seq & 1) * kDecWords * 2;
   for (int i = 0; i < kDecWords; i++) st_relaxed_b128(rec + 2 * i, c.dw[i], (unsigned long long)c.seq);
   unsigned long long *buf = p.xbuf + (size_t)(c.seq & 1) * kMaxGrid * kSlotWords;
@@ -1310,9 +1367,9 @@ __device__ void seq_apply_winner(Seq &q, int t) {
     return;
   }
   if (c.win.flags & SLOT_TO_IDLE)
-    stmt_allocate(q, t, c.win.node);
+    stmt_allocate(q, t, c.win.node, c.ctx_fresh != 0);
   else
-    stmt_pipeline(q, t, c.win.node);
+    stmt_pipeline(q, t, c.win.node, c.ctx_fresh != 0);
   c.item_ok = 1;
 }
 __device__ void seq_apply_batched(Seq &q, int t) {
@@ -1326,9 +1383,9 @@ __device__ void seq_apply_batched(Seq &q, int t) {
   b.idx++;
   b.left--;
   if (b.to_idle)
-    stmt_allocate(q, t, b.node);
+    stmt_allocate(q, t, b.node, c.ctx_fresh != 0);
   else
-    stmt_pipeline(q, t, b.node);
+    stmt_pipeline(q, t, b.node, c.ctx_fresh != 0);
   q.batched++;
   c.item_ok = 1;
 }
@@ -1399,18 +1456,27 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
   for (;;) {
     // ---- wait for decision record `seq` ----
     if (warp == 0) {
-      if (lane < kDecWords) {
-        const unsigned long long *rec = p.dbuf + (size_t)(seq & 1) * kDecWords * 2 + 2 * lane;
+      const unsigned long long *rec0 = p.dbuf + (size_t)(seq & 1) * kDecWords * 2;
+      if (lane == 0) {  // one poller per CTA on word 0 keeps the record's L2 lines cool
+        unsigned long long lo, hi;
+        Spin spin;
+        for (;;) {
+          ld_relaxed_b128(rec0, lo, hi);
+          if (hi == (unsigned long long)seq || spin.expired(p, 7, seq, 0)) break;
+          __nanosleep(20);
+        }
+      }
+      __syncwarp();
+      if (lane < kDecWords) {  // every word is self-validating
         unsigned long long lo, hi;
         {
           Spin spin;
           do {
-            ld_relaxed_b128(rec, lo, hi);
-          } while ((hi != (unsigned long long)seq) && !spin.expired(p, 7, (unsigned int)seq, (int)(lane)));
+            ld_relaxed_b128(rec0 + 2 * lane, lo, hi);
+          } while ((hi != (unsigned long long)seq) && !spin.expired(p, 8, (unsigned int)seq, (int)(lane)));
         }
         sh.dw[lane] = lo;
       }
-      __threadfence();  // acquire side: the delta list written before the record is now visible
     }
     __syncthreads();
     if (tid == 0) {
@@ -1444,9 +1510,16 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     // ---- apply the node deltas that belong to this tile (loads in parallel, application in list order) ----
     const int nd = sh.n_delta;
     if (nd > 0) {
-      const int2 *dl = p.delta + (size_t)(seq & 1) * kMaxDelta;
+      const unsigned long long *dl = p.delta + (size_t)(seq & 1) * kMaxDelta * 2;
       for (int e = tid; e < nd; e += blockDim.x) {
-        int2 en = __ldcg(dl + e);
+        unsigned long long lo, hi;
+        {
+          Spin spin;
+          do {
+            ld_relaxed_b128(dl + 2 * e, lo, hi);
+          } while ((hi != (unsigned long long)seq) && !spin.expired(p, 9, (unsigned int)seq, (int)(e)));
+        }
+        int2 en = make_int2((int)(unsigned int)(lo & 0xffffffffu), (int)(unsigned int)(lo >> 32));
         sh.delta[e] = en;
         int node = en.x & 0x0fffffff;
         int ln = node - tile.base;
@@ -1570,6 +1643,7 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     rp.child_heap = (int *)take_from(h, sizeof(int) * s.Q);
     rp.root_heap = (int *)take_from(h, sizeof(int) * (s.n_top + 1));
     rp.qn_flags = (unsigned char *)take_from(h, s.Q);
+    rp.touched = (unsigned int *)take_from(h, sizeof(unsigned int) * ((s.J + 31) / 32 + 1));
     // cold state = the session arrays themselves
     rp.t_status = s.t_status;
     rp.t_node = s.t_node;
@@ -1610,6 +1684,9 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     for (int r = 0; r < KAI_MAX_RES; r++) ctl.dec.req[r] = 0;
     ctl.dec.pipeline_only = ctl.dec.res = ctl.dec.strategy = ctl.dec.gpu_task = ctl.dec.best_effort = 0;
     ctl.dec.nominated = ctl.dec.pred_class = -1;
+    ctl.dec.task = -1;
+    ctl.ctx_job = ctl.ctx_ps = -1;
+    ctl.ctx_fresh = ctl.ctx_queue = ctl.ctx_preempt = ctl.ctx_base = 0;
     ctl.seq = p.seq0;
     ctl.n_delta = 0;
     ctl.stop = 0;
@@ -1631,6 +1708,7 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
       rp.qn_flags[i] = 0;
       rp.qkey[i].valid = 0;
     }
+    for (int i = tid; i < (s.J + 31) / 32 + 1; i += blockDim.x) rp.touched[i] = 0;
   }
   __syncthreads();
   if (tid >= 32) return;  // the sequencer proper is warp 0
@@ -1650,14 +1728,40 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
       ctl.job_ok = 0;
       if (job >= 0) {
         seq.n_ops = 0;
-        // common/allocate.go:20-36 AllocateJob
         long long tkt = clock64();
         seq.t_heap += tkt - tk;
-        int n = tasks_to_allocate(seq, job, true, nullptr);
-        seq.t_tta += clock64() - tkt;
+        // job context: queue, preemptibility and (single-podset jobs) the podset counters
+        const JobRec rec = s.jrec[job];
+        ctl.ctx_job = job;
+        ctl.ctx_queue = __ldg(&s.j_queue[job]);
+        ctl.ctx_preempt = (__ldg(&s.j_flags[job]) & KAI_JOB_PREEMPTIBLE) ? 1 : 0;
+        ctl.ctx_fresh = (!job_touched(seq, job) && rec.n_tta >= 0) ? 1 : 0;
+        ctl.ctx_ps = -1;
+        if (rec.n_podsets == 1) {
+          if (!job_touched(seq, job)) {
+            ctl.ctx_cnt[0] = rec.cnt[0];
+            ctl.ctx_cnt[1] = rec.cnt[1];
+            ctl.ctx_cnt[2] = rec.cnt[2];
+          } else {
+            for (int w = 0; w < 3; w++) ctl.ctx_cnt[w] = seq.rp.ps_active_alloc[(size_t)w * s.S + rec.ps0];
+          }
+          ctl.ctx_ps = rec.ps0;
+        }
+        // common/allocate.go:20-36 AllocateJob
+        int n;
         double req[QR] = {0, 0, 0};
-        for (int k = 0; k < n; k++)
-          for (int r = 0; r < QR; r++) req[r] = __dadd_rn(req[r], __ldg(&s.t_req[(size_t)seq.rp.tta[k] * s.R + r]));
+        if (ctl.ctx_fresh) {  // GetTasksToAllocate = tasks [tb, tb + n_tta), request sum precomputed
+          n = rec.n_tta;
+          ctl.ctx_base = rec.tb;
+          for (int r = 0; r < QR; r++) req[r] = rec.req0[r];
+          for (int k = 0; k < n; k++) prefetch_l1(s.t_req + (size_t)(rec.tb + k) * s.R);
+        } else {
+          n = tasks_to_allocate(seq, job, true, nullptr);
+          ctl.ctx_base = -1;
+          for (int k = 0; k < n; k++)
+            for (int r = 0; r < QR; r++) req[r] = __dadd_rn(req[r], __ldg(&s.t_req[(size_t)seq.rp.tta[k] * s.R + r]));
+        }
+        seq.t_tta += clock64() - tkt;
         if (!over_capacity(seq, job, req)) {
           // tasks_to_allocate already emits tasks grouped in PodSetOrderFn order, which is the order
           // allocateSubGroupSetOnNodes/allocatePodSet visit them in (common/allocate.go:62-119)
@@ -1676,7 +1780,7 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
       for (int k = 0; k < n_items; k++) {
         if (lane == 0) {
           long long tk = clock64();
-          int t = seq.rp.tta[k];
+          int t = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
           ctl.item_ok = seq_prepare_task(seq, t, ctl.job) ? 1 : 0;
           if (ctl.item_ok && ctl.use_batch) seq_apply_batched(seq, t);
           if (ctl.need_minmax) seq.minmax_exchanges++;
@@ -1721,6 +1825,11 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
         stmt_rollback(seq, 0);  // Discard (statement.go:522-534)
         record_visit(seq, job, 0);
       }
+      if (ctl.ctx_ps >= 0)  // write the podset counters of the job back to the session state
+        for (int w = 0; w < 3; w++) seq.rp.ps_active_alloc[(size_t)w * s.S + ctl.ctx_ps] = ctl.ctx_cnt[w];
+      ctl.ctx_ps = -1;
+      ctl.ctx_job = -1;
+      ctl.ctx_fresh = 0;
       if (seq.error) ctl.stop = 1;
       seq.t_finish += clock64() - tk;
     }

@@ -37,6 +37,18 @@ enum { OP_ALLOCATE = 0, OP_PIPELINE = 1, OP_EVICT = 2, OP_UNDO = 3 };
 // queue-node flags of the job-order tree (actions/utils/job_order_by_queue.go:18-25)
 enum { QN_EXISTS = 1, QN_LINKED = 2, QN_REORDER = 4 };
 
+// Per-job record written by k_prep_jobs (one 64-byte line): everything the sequencer needs to pop, admit
+// and allocate a job whose tasks have not been touched yet in this action.
+struct __align__(64) JobRec {
+  double req0[3];  // GetTasksToAllocateInitResource at action start (valid when n_podsets == 1)
+  int n_tta;       // >= 0: GetTasksToAllocate is exactly tasks [tb, tb + n_tta) (all pending); -1: general path
+  int tb;          // first task of podset ps0
+  int ps0;         // first podset
+  int n_podsets;
+  int cnt[3];      // podset ps0: active-allocated, pending, pipelined task counts at action start
+  int pad[3];
+};
+
 // Immutable (per cycle) device snapshot + session state pointers.  Passed by value to kernels.
 struct DevSnap {
   int R, N, Q, J, S, T, NPC, mask_words;
@@ -65,7 +77,6 @@ struct DevSnap {
   const uint32_t *j_flags;
   // podsets
   const int *ps_min, *ps_task_begin, *ps_job;
-  const int *ps_sorted_tasks;  // [T] tasks of each podset in TaskOrderFn order
   // tasks
   const double *t_req;  // [T][R]
   const int *t_job, *t_podset, *t_nominated, *t_pred_class;
@@ -85,6 +96,7 @@ struct DevSnap {
   int *tta;                    // [max_job_tasks + 1]
   int *ps_order;               // [max_job_podsets + 1]
   unsigned char *hot_global;   // hot arrays when they do not fit in shared memory
+  JobRec *jrec;                // [J]
 };
 
 // Cached comparator inputs of one queue node (plugins/proportion/queue_order/queue_order.go:19-73)
@@ -107,6 +119,7 @@ struct Replica {
   int *child_heap;               // [Q] arena by q_child_begin
   int *root_heap;                // [n_top + 1]
   unsigned char *qn_flags;       // [Q]
+  unsigned int *touched;         // [ceil(J/32)] jobs whose task statuses changed in this action
   // cold
   int *t_status, *t_node, *t_node_status;
   unsigned char *t_virtual;
@@ -130,7 +143,7 @@ struct ActionParams {
   int node_count;       // node rows of this GPU's shard
   int ops_cap;
   unsigned long long *dbuf;  // decision record: [2][kDecWords] tagged 128-bit words (sequencer -> scanners)
-  int2 *delta;               // node delta list: [2][kMaxDelta] (node|code<<28, task)
+  unsigned long long *delta; // node delta list: [2][kMaxDelta] tagged words {node | code<<28 | task<<32, seq}
   unsigned long long *xbuf;  // exchange slots: [2][kMaxGrid][8] u64 (tagged 128-bit words A, B, C, D)
   unsigned long long *mmbuf; // min/max exchange: [2][kMaxGrid][8] u64
   kai_job_visit *visits;     // [visits_cap]

@@ -101,7 +101,9 @@ struct kai_engine {
   bool hot_in_smem = false;
   int ops_cap = 0, visits_cap = 0;
   unsigned long long *xbuf = nullptr, *mmbuf = nullptr, *dbuf = nullptr;
-  int2 *delta = nullptr;
+  unsigned long long *delta = nullptr;
+  std::vector<int> task_perm;
+  std::vector<int32_t> r_tmp_node, r_tmp_status;
   long long *counters = nullptr;
   kai_job_visit *d_visits = nullptr;
   double *fs_w = nullptr, *fs_rr = nullptr;
@@ -280,8 +282,11 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
       });
   }
   // podsets / tasks
-  std::vector<int> ps_job(std::max(S, 1), 0), t_job(std::max(T, 1), 0), t_podset(std::max(T, 1), 0),
-      ps_sorted_tasks(std::max(T, 1), 0);
+  // device task i = caller task perm[i]: the tasks of a podset are renumbered into TaskOrderFn order so that
+  // the kernels never chase an index array (results are scattered back through perm on download)
+  std::vector<int> ps_job(std::max(S, 1), 0), t_job(std::max(T, 1), 0), t_podset(std::max(T, 1), 0);
+  std::vector<int> &perm = e->task_perm;
+  perm.assign(std::max(T, 1), 0);
   int max_job_tasks = 1, max_job_podsets = 1;
   for (int j = 0; j < J; j++) {
     int b = s->job_podset_begin[j], en = s->job_podset_begin[j + 1];
@@ -296,10 +301,10 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
       for (int t = tb; t < te; t++) {
         t_job[t] = j;
         t_podset[t] = ps;
-        ps_sorted_tasks[t] = t;
+        perm[t] = t;
       }
-      std::sort(ps_sorted_tasks.begin() + tb, ps_sorted_tasks.begin() + te,
-                [&](int a, int b2) { return s->task_order_rank[a] < s->task_order_rank[b2]; });
+      std::stable_sort(perm.begin() + tb, perm.begin() + te,
+                       [&](int a, int b2) { return s->task_order_rank[a] < s->task_order_rank[b2]; });
     }
     max_job_tasks = std::max(max_job_tasks, nt);
   }
@@ -338,7 +343,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   size_t o_jor = reserve_up((size_t)std::max(J, 1) * 4), o_jfl = reserve_up((size_t)std::max(J, 1) * 4);
   size_t o_jpb = reserve_up((size_t)(J + 1) * 4);
   size_t o_psmin = reserve_up((size_t)std::max(S, 1) * 4), o_pstb = reserve_up((size_t)(S + 1) * 4);
-  size_t o_psjob = reserve_up((size_t)std::max(S, 1) * 4), o_psst = reserve_up((size_t)std::max(T, 1) * 4);
+  size_t o_psjob = reserve_up((size_t)std::max(S, 1) * 4);
   size_t o_treq = reserve_up((size_t)std::max(T, 1) * R * 8);
   size_t o_tjob = reserve_up((size_t)std::max(T, 1) * 4), o_tps = reserve_up((size_t)std::max(T, 1) * 4);
   size_t o_tnom = s->task_nominated ? reserve_up((size_t)std::max(T, 1) * 4) : 0;
@@ -361,8 +366,10 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
   // hot per-queue sequencer arrays — must match the carving in sequencer_main
   const size_t hot = 2 * a16(sizeof(double) * QR * Q) + a16(sizeof(QKey) * (size_t)Q) + 5 * a16(sizeof(int) * (size_t)Q) +
-                     a16(sizeof(int) * (size_t)(top.size() + 1)) + a16((size_t)Q);
+                     a16(sizeof(int) * (size_t)(top.size() + 1)) + a16((size_t)Q) +
+                     a16(sizeof(unsigned int) * (size_t)((J + 31) / 32 + 1));
   size_t o_hot = reserve_up(hot + 16);
+  size_t o_jrec = reserve_up(sizeof(JobRec) * (size_t)std::max(J, 1));
   const size_t zero_begin = o_tvirt, zero_bytes = up - o_tvirt;
 
   CK(e->dsnap.reserve(up + 256));
@@ -407,18 +414,28 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   put(o_psmin, s->podset_min_available, (size_t)S * 4);
   put(o_pstb, s->podset_task_begin, (size_t)(S + 1) * 4);
   put(o_psjob, ps_job.data(), (size_t)S * 4);
-  put(o_psst, ps_sorted_tasks.data(), (size_t)T * 4);
-  put(o_treq, s->task_req, (size_t)T * R * 8);
+  {
+    double *tr = (double *)(h + o_treq);
+    for (int t = 0; t < T; t++) memcpy(tr + (size_t)t * R, s->task_req + (size_t)perm[t] * R, (size_t)R * 8);
+  }
   put(o_tjob, t_job.data(), (size_t)T * 4);
   put(o_tps, t_podset.data(), (size_t)T * 4);
-  if (s->task_nominated) put(o_tnom, s->task_nominated, (size_t)T * 4);
-  if (s->task_pred_class) put(o_tpc, s->task_pred_class, (size_t)T * 4);
-  put(o_tst, s->task_status, (size_t)T * 4);
+  if (s->task_nominated) {
+    int *x = (int *)(h + o_tnom);
+    for (int t = 0; t < T; t++) x[t] = s->task_nominated[perm[t]];
+  }
+  if (s->task_pred_class) {
+    int *x = (int *)(h + o_tpc);
+    for (int t = 0; t < T; t++) x[t] = s->task_pred_class[perm[t]];
+  }
+  {
+    int *x = (int *)(h + o_tst), *y = (int *)(h + o_tnst);
+    for (int t = 0; t < T; t++) x[t] = y[t] = s->task_status[perm[t]];
+  }
   {
     int *tn = (int *)(h + o_tnode);
-    for (int t = 0; t < T; t++) tn[t] = (s->task_status[t] & kActiveUsed) ? s->task_node[t] : -1;
+    for (int t = 0; t < T; t++) tn[t] = (s->task_status[perm[t]] & kActiveUsed) ? s->task_node[perm[t]] : -1;
   }
-  put(o_tnst, s->task_status, (size_t)T * 4);
   if (o_mask || (s->pred_mask && NPC > 0)) put(o_mask, s->pred_mask, (size_t)NPC * mask_words * 4);
 
   CK(cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, e->stream));
@@ -475,7 +492,6 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   ds.ps_min = (const int *)(d + o_psmin);
   ds.ps_task_begin = (const int *)(d + o_pstb);
   ds.ps_job = (const int *)(d + o_psjob);
-  ds.ps_sorted_tasks = (const int *)(d + o_psst);
   ds.t_req = (const double *)(d + o_treq);
   ds.t_job = (const int *)(d + o_tjob);
   ds.t_podset = (const int *)(d + o_tps);
@@ -498,6 +514,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   ds.tta = (int *)(d + o_tta);
   ds.ps_order = (int *)(d + o_psord);
   ds.hot_global = d + o_hot;
+  ds.jrec = (JobRec *)(d + o_jrec);
 
   // ---------------- launch geometry of the action kernel ----------------
   // CTA 0 = sequencer, CTAs 1..grid-1 = scanners that split the node rows
@@ -531,7 +548,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   {
     size_t xb = (size_t)2 * kMaxGrid * 8 * 8;
     size_t misc = 2 * xb + 256 + sizeof(long long) * 32 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
-                  sizeof(unsigned long long) * 2 * kDecWords * 2 + sizeof(int2) * 2 * kMaxDelta + 1024;
+                  sizeof(unsigned long long) * 2 * kDecWords * 2 + sizeof(unsigned long long) * 2 * kMaxDelta * 2 + 1024;
     CK(e->dmisc.reserve(misc));
     e->xbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
     e->mmbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
@@ -540,7 +557,8 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     e->fs_w = e->dmisc.take<double>(QN + 1);
     e->fs_rr = e->dmisc.take<double>(QN + 1);
     e->dbuf = e->dmisc.take<unsigned long long>(2 * kDecWords * 2);
-    e->delta = e->dmisc.take<int2>(2 * kMaxDelta);
+    e->delta = e->dmisc.take<unsigned long long>(2 * kMaxDelta * 2);
+    CK(cudaMemsetAsync(e->delta, 0, sizeof(unsigned long long) * 2 * kMaxDelta * 2, e->stream));
     CK(cudaMemsetAsync(e->dbuf, 0, sizeof(unsigned long long) * 2 * kDecWords * 2, e->stream));
     CK(cudaMemsetAsync(e->xbuf, 0, xb, e->stream));
     CK(cudaMemsetAsync(e->mmbuf, 0, xb, e->stream));
@@ -588,8 +606,10 @@ static int download(kai_engine *e, kai_result *out, long long n_visits, long lon
   const DevSnap &ds = e->ds;
   const size_t QN = (size_t)QR * e->Q, RN = (size_t)e->R * e->N;
   cudaEventRecord(e->ev[4], e->stream);
-  CK(cudaMemcpyAsync(e->r_task_node.data(), ds.t_node, (size_t)e->T * 4, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(e->r_task_status.data(), ds.t_status, (size_t)e->T * 4, cudaMemcpyDeviceToHost, e->stream));
+  e->r_tmp_node.resize(std::max(e->T, 1));
+  e->r_tmp_status.resize(std::max(e->T, 1));
+  CK(cudaMemcpyAsync(e->r_tmp_node.data(), ds.t_node, (size_t)e->T * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->r_tmp_status.data(), ds.t_status, (size_t)e->T * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(e->r_fair.data(), ds.q_fair, QN * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(e->r_alloc.data(), ds.q_alloc, QN * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(e->r_alloc_np.data(), ds.q_alloc_np, QN * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -604,6 +624,10 @@ static int download(kai_engine *e, kai_result *out, long long n_visits, long lon
                        e->stream));
   cudaEventRecord(e->ev[5], e->stream);
   CK(cudaStreamSynchronize(e->stream));
+  for (int t = 0; t < e->T; t++) {  // device order -> caller order
+    e->r_task_node[e->task_perm[t]] = e->r_tmp_node[t];
+    e->r_task_status[e->task_perm[t]] = e->r_tmp_status[t];
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
   e->stats.download_ms = ms;
