@@ -153,6 +153,9 @@ struct ActionParams {
   int hot_in_smem;      // hot replica arrays carved from dynamic shared memory after the node tile
   size_t tile_bytes, hot_bytes;
   int batching;         // same-node batching of consecutive identical pods (1 = on)
+  int mode;             // 0 = device-resident sequencer (CTA 0), 1 = host-sequenced (CTA 0 relays host records)
+  unsigned long long *h_rec, *h_delta;  // mode 1: decision record / delta words in pinned mapped host memory
+  int spin_log2;        // watchdog: polls before a wait is declared dead
 };
 
 }  // namespace kai

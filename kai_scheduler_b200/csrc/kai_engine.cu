@@ -11,12 +11,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <type_traits>
 #include <string>
 #include <vector>
 
 #include "kai_device.cuh"
 #include "kai_kernels.cuh"  // single translation unit: kernels + host API
 #include "kai_action.cuh"
+#include "kai_host_seq.cuh"
 
 using namespace kai;
 
@@ -88,6 +90,7 @@ struct kai_engine {
   int max_smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_mirror = nullptr;
   bool loaded = false;
 
   DeviceArena dsnap;     // snapshot + session state
@@ -102,6 +105,14 @@ struct kai_engine {
   int ops_cap = 0, visits_cap = 0;
   unsigned long long *xbuf = nullptr, *mmbuf = nullptr, *dbuf = nullptr;
   unsigned long long *delta = nullptr;
+  // host-sequenced mode
+  unsigned long long *h_pinned = nullptr;  // one pinned mapped allocation: rec | delta | slots | mm
+  unsigned long long *h_rec = nullptr, *h_delta = nullptr, *h_slots = nullptr, *h_mm = nullptr;
+  HostBackend hb;
+  DevSnap hs;  // DevSnap whose pointers address the host mirror (the pinned staging buffer)
+  std::vector<unsigned char> hot_host;
+  std::vector<int> rank_to_node_h;
+  size_t dev_only_begin = 0, dev_only_bytes = 0;
   std::vector<int> task_perm;
   std::vector<int32_t> r_tmp_node, r_tmp_status;
   long long *counters = nullptr;
@@ -168,6 +179,19 @@ int kai_engine_create(const kai_config *cfg, kai_engine **out) {
     return KAI_ERR_CUDA;
   }
   for (auto &ev : e->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&e->ev_mirror, cudaEventDisableTiming);
+  {  // pinned, device-mapped protocol buffers of the host-sequenced mode
+    size_t words = (size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords;
+    if (cudaHostAlloc((void **)&e->h_pinned, words * 8, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      delete e;
+      return KAI_ERR_CUDA;
+    }
+    memset(e->h_pinned, 0, words * 8);
+    e->h_rec = e->h_pinned;
+    e->h_delta = e->h_rec + (size_t)2 * kDecWords * 2;
+    e->h_slots = e->h_delta + (size_t)2 * kMaxDelta * 2;
+    e->h_mm = e->h_slots + (size_t)2 * kMaxGrid * kSlotWords;
+  }
   *out = e;
   return KAI_OK;
 }
@@ -181,6 +205,7 @@ void kai_engine_destroy(kai_engine *e) {
   e->dmisc.release();
   e->stage.release();
   e->rstage.release();
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
   for (auto &ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -373,7 +398,10 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   const size_t zero_begin = o_tvirt, zero_bytes = up - o_tvirt;
 
   CK(e->dsnap.reserve(up + 256));
-  CK(e->stage.reserve(upload_bytes + 256));
+  CK(e->stage.reserve(up + 256));  // the staging buffer doubles as the host mirror of the whole arena
+  e->dev_only_begin = zero_begin;
+  e->dev_only_bytes = zero_bytes;
+  e->rank_to_node_h = rank_to_node;
   unsigned char *h = e->stage.host;
   unsigned char *d = e->dsnap.base;
   auto put = [&](size_t off, const void *src, size_t bytes) {
@@ -515,6 +543,28 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   ds.ps_order = (int *)(d + o_psord);
   ds.hot_global = d + o_hot;
   ds.jrec = (JobRec *)(d + o_jrec);
+  {  // host view: every pointer of ds rebased onto the staging buffer (same offsets)
+    static_assert(sizeof(void *) == 8, "64-bit only");
+    e->hs = ds;
+    unsigned char *hb_ = e->stage.host;
+    auto rb = [&](auto &ptr) {
+      if (ptr) {
+        unsigned char *raw = (unsigned char *)ptr;
+        ptr = (std::remove_reference_t<decltype(ptr)>)(hb_ + (raw - d));
+      }
+    };
+    DevSnap &h_ = e->hs;
+    rb(h_.alloc); rb(h_.idle); rb(h_.rel); rb(h_.name_rank); rb(h_.rank_to_node); rb(h_.nflags); rb(h_.gpu_count);
+    rb(h_.foreign); rb(h_.q_parent); rb(h_.q_priority); rb(h_.q_uid_rank); rb(h_.q_nchildren); rb(h_.q_creation);
+    rb(h_.q_deserved); rb(h_.q_limit); rb(h_.q_oqw); rb(h_.q_usage); rb(h_.q_fair); rb(h_.q_request); rb(h_.q_alloc);
+    rb(h_.q_alloc_np); rb(h_.q_child_begin); rb(h_.q_children); rb(h_.top_queues); rb(h_.level_group_begin);
+    rb(h_.level_groups); rb(h_.q_job_begin); rb(h_.q_jobs_sorted); rb(h_.j_queue); rb(h_.j_priority);
+    rb(h_.j_order_rank); rb(h_.j_ps_begin); rb(h_.j_flags); rb(h_.ps_min); rb(h_.ps_task_begin); rb(h_.ps_job);
+    rb(h_.t_req); rb(h_.t_job); rb(h_.t_podset); rb(h_.t_nominated); rb(h_.t_pred_class); rb(h_.t_status);
+    rb(h_.t_node); rb(h_.t_node_status); rb(h_.t_virtual); rb(h_.pred_mask); rb(h_.total); rb(h_.q_allocatable);
+    rb(h_.j_key0); rb(h_.leaf_sorted); rb(h_.leaf_count); rb(h_.ps_cnt0); rb(h_.j_req); rb(h_.j_req_valid);
+    rb(h_.ops); rb(h_.tta); rb(h_.ps_order); rb(h_.hot_global); rb(h_.jrec);
+  }
 
   // ---------------- launch geometry of the action kernel ----------------
   // CTA 0 = sequencer, CTAs 1..grid-1 = scanners that split the node rows
@@ -563,6 +613,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     CK(cudaMemsetAsync(e->xbuf, 0, xb, e->stream));
     CK(cudaMemsetAsync(e->mmbuf, 0, xb, e->stream));
     e->seq = 2;
+    memset(e->h_pinned, 0, ((size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords) * 8);
   }
 
   // ---------------- open session: totals, queue usage, fair share ----------------
@@ -691,16 +742,156 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_action, kThreads, e->smem_bytes));
   if (max_blocks < 1 || max_blocks * e->num_sms < e->grid)
     return e->fail(KAI_ERR_CUDA, "action kernel cannot be made co-resident");
+  const char *mode_env = getenv("KAI_SEQUENCER");
+  const bool host_mode = !(mode_env && strcmp(mode_env, "device") == 0);
+  p.mode = host_mode ? 1 : 0;
+  p.spin_log2 = host_mode ? 26 : 22;
+  if (host_mode) {
+    p.h_rec = e->h_rec;
+    p.h_delta = e->h_delta;
+    p.xbuf = e->h_slots;  // scanners answer straight into pinned host memory
+    p.mmbuf = e->h_mm;
+  }
   void *args[] = {(void *)&p};
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 32, e->stream));
   cudaEventRecord(e->ev[2], e->stream);
   if (e->J > 0) k_prep_jobs<<<std::min(e->num_sms * 8, (e->J + 255) / 256), 256, 0, e->stream>>>(e->ds, 1, 1);
   if (e->Q > 0) k_prep_queues<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->ds);
-  CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
-  cudaEventRecord(e->ev[3], e->stream);
   long long c[32];
-  CK(cudaMemcpyAsync(c, e->counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  memset(c, 0, sizeof(c));
+  if (host_mode) {
+    // host mirror of everything the open-session / prepare kernels produced
+    CK(cudaMemcpyAsync(e->stage.host + e->dev_only_begin, e->dsnap.base + e->dev_only_begin, e->dev_only_bytes,
+                       cudaMemcpyDeviceToHost, e->stream));
+    cudaEventRecord(e->ev_mirror, e->stream);
+    CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
+    cudaEventRecord(e->ev[3], e->stream);
+    // wait for the mirror copy only (the kernel keeps running): event-free trick = query the D2H through an event
+    cudaEvent_t mirror_done = e->ev[4];
+    (void)mirror_done;
+    // the D2H above precedes the kernel in stream order; its completion is observed by polling a sentinel
+    // written last: simplest robust way is a second stream-ordered event recorded before the launch.
+    // (see below: ev_mirror)
+    HostBackend &hb = e->hb;
+    hb.h_rec = e->h_rec;
+    hb.h_delta = e->h_delta;
+    hb.h_slots = e->h_slots;
+    hb.h_mm = e->h_mm;
+    hb.n_scanners = e->grid - 1;
+    hb.batching = p.batching;
+    hb.failed = false;
+    hb.rank_to_node = e->rank_to_node_h.data();
+    CK(cudaEventSynchronize(e->ev_mirror));
+    // ---- sequencer state on the host ----
+    const DevSnap &hs = e->hs;
+    const int Q = e->Q, J = e->J;
+    e->hot_host.assign(e->hot_bytes + 64, 0);
+    Seq &seq = hb.seq;
+    Ctl &ctl = hb.ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    memset(&seq, 0, sizeof(seq));
+    {
+      unsigned char *h = e->hot_host.data();
+      auto take_from = [](unsigned char *&base, size_t bytes) {
+        unsigned char *r = base;
+        base += (bytes + 15) & ~(size_t)15;
+        return r;
+      };
+      Replica &rp = seq.rp;
+      rp.q_alloc = (double *)take_from(h, sizeof(double) * QR * Q);
+      rp.q_alloc_np = (double *)take_from(h, sizeof(double) * QR * Q);
+      rp.qkey = (QKey *)take_from(h, sizeof(QKey) * Q);
+      rp.leaf_head = (int *)take_from(h, sizeof(int) * Q);
+      rp.leaf_end = (int *)take_from(h, sizeof(int) * Q);
+      rp.ovl_len = (int *)take_from(h, sizeof(int) * Q);
+      rp.child_len = (int *)take_from(h, sizeof(int) * Q);
+      rp.child_heap = (int *)take_from(h, sizeof(int) * Q);
+      rp.root_heap = (int *)take_from(h, sizeof(int) * (hs.n_top + 1));
+      rp.qn_flags = (unsigned char *)take_from(h, Q);
+      rp.touched = (unsigned int *)take_from(h, sizeof(unsigned int) * ((J + 31) / 32 + 1));
+      rp.t_status = hs.t_status;
+      rp.t_node = hs.t_node;
+      rp.t_node_status = hs.t_node_status;
+      rp.t_virtual = hs.t_virtual;
+      rp.ps_active_alloc = hs.ps_cnt0;
+      rp.ps_pending = hs.ps_cnt0 + hs.S;
+      rp.ps_pipelined = hs.ps_cnt0 + 2 * hs.S;
+      rp.j_req = hs.j_req;
+      rp.j_req_valid = hs.j_req_valid;
+      rp.j_key = hs.j_key0;
+      rp.leaf_heap = hs.leaf_sorted;
+      rp.ops = hs.ops;
+      rp.tta = hs.tta;
+      rp.ps_order = hs.ps_order;
+      for (int i = 0; i < QR * Q; i++) {
+        rp.q_alloc[i] = hs.q_alloc[i];
+        rp.q_alloc_np[i] = hs.q_alloc_np[i];
+      }
+      for (int i = 0; i < Q; i++) {
+        int b = hs.q_job_begin[i];
+        rp.leaf_head[i] = b;
+        rp.leaf_end[i] = b + (hs.q_nchildren[i] == 0 ? hs.leaf_count[i] : 0);
+      }
+    }
+    seq.s = &e->hs;
+    seq.cfg = &e->cfg;
+    seq.p = &p;
+    seq.delta_base = e->h_delta;
+    seq.host_backend = &hb;
+    seq.ctl = &ctl;
+    seq.ops_cap = e->ops_cap;
+    seq.batching = p.batching;
+    seq.is_cta0 = true;
+    e->r_visits.assign((size_t)e->visits_cap, kai_job_visit{0, 0});
+    seq.visits = e->r_visits.data();
+    seq.visits_cap = e->visits_cap;
+    ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
+    ctl.trk[0].mn = ctl.trk[1].mn = DBL_MAX;
+    ctl.dec.nominated = ctl.dec.pred_class = -1;
+    ctl.dec.task = -1;
+    ctl.ctx_job = ctl.ctx_ps = -1;
+    ctl.seq = p.seq0;
+    hb.run_allocate();
+    CK(cudaStreamSynchronize(e->stream));
+    {
+      long long cd[32];
+      CK(cudaMemcpy(cd, e->counters, sizeof(cd), cudaMemcpyDeviceToHost));
+      for (int i = 24; i < 28; i++) c[i] = cd[i];
+    }
+    c[0] = seq.n_visits;
+    c[1] = seq.sweeps;
+    c[2] = seq.nodes_scanned;
+    c[3] = seq.pods_placed;
+    c[4] = seq.pods_evicted;
+    c[5] = seq.minmax_exchanges;
+    c[6] = seq.error;
+    c[7] = ctl.seq + 1;
+    c[15] = seq.batched;
+    if (hb.failed && c[24] == 0) c[24] = 99;
+    // session state back to the device copies (later actions' prepare kernels and the result download read them)
+    for (int i = 0; i < QR * Q; i++) {
+      hs.q_alloc[i] = seq.rp.q_alloc[i];
+      hs.q_alloc_np[i] = seq.rp.q_alloc_np[i];
+    }
+    auto up = [&](const void *hp, size_t bytes) {
+      size_t off = (const unsigned char *)hp - e->stage.host;
+      return cudaMemcpyAsync(e->dsnap.base + off, hp, bytes, cudaMemcpyHostToDevice, e->stream);
+    };
+    CK(up(hs.t_status, (size_t)e->T * 4));
+    CK(up(hs.t_node, (size_t)e->T * 4));
+    CK(up(hs.t_node_status, (size_t)e->T * 4));
+    CK(up(hs.t_virtual, (size_t)e->T));
+    CK(up(hs.q_alloc, (size_t)QR * Q * 8));
+    CK(up(hs.q_alloc_np, (size_t)QR * Q * 8));
+    if (e->visits_cap > 0 && seq.n_visits > 0)
+      CK(cudaMemcpyAsync(e->d_visits, e->r_visits.data(), sizeof(kai_job_visit) * (size_t)std::min<long long>(seq.n_visits, e->visits_cap),
+                         cudaMemcpyHostToDevice, e->stream));
+  } else {
+    CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
+    cudaEventRecord(e->ev[3], e->stream);
+    CK(cudaMemcpyAsync(c, e->counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]);
   e->stats.action_ms = ms;
@@ -711,7 +902,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   e->seq = (unsigned int)c[7];
   if (getenv("KAI_PROFILE")) {
     const char *nm[] = {"init", "pop", "prepare", "keycalc", "exchange", "apply", "finish"};
-    fprintf(stderr, "[kai] action %.3f ms, %lld sweeps, %lld batched placements, %lld minmax exchanges, hot_in_smem=%d; CTA0 thread0 cycles:", ms, c[1], c[15], c[5], (int)e->hot_in_smem);
+    fprintf(stderr, "[kai] %s-sequenced action %.3f ms, %lld sweeps, %lld batched placements, %lld minmax exchanges, hot_in_smem=%d; CTA0 thread0 cycles:", host_mode ? "host" : "device", ms, c[1], c[15], c[5], (int)e->hot_in_smem);
     for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%lld", nm[i], c[8 + i]);
     fprintf(stderr, " n_key=%lld tta=%lld popheap=%lld\n", c[16], c[17], c[18]);
   }

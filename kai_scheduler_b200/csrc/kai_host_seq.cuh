@@ -1,0 +1,273 @@
+// kai_host_seq.cuh — host backend of the sequencer (host-sequenced mode).
+//
+// The sequencer source (kai_seq.cuh) is compiled for the host as well.  In this mode a CPU thread of
+// libkaigpu.so runs it against a host mirror of the session state while the GPU runs k_action in
+// "scan server" form: CTA 0 relays the decision records the host writes into pinned mapped memory to the
+// scanners' device-side record buffer, the scanners keep their node tiles in shared memory and answer
+// every record with one tagged 128-bit candidate written straight into pinned host memory.
+//
+// Why: measured on B200 (profiles/microbench, profiles/r01_sequencer_modes.md) one GPU lane needs ~20k
+// cycles (10 us) of dependent L1/L2/shared-memory latencies per job for the pointer-chasing part of the
+// cycle (heap pops, DRF keys, statement log); a host core does the same in a few hundred ns.  The O(N)
+// work per allocateTask — the node sweep — stays on the GPU in both modes.
+#pragma once
+#include <chrono>
+#include <cstring>
+
+#include "kai_action.cuh"
+#include "kai_seq.cuh"
+
+namespace kai {
+
+struct HostBackend {
+  // pinned, device-mapped buffers
+  unsigned long long *h_rec = nullptr;    // [2][kDecWords][2]
+  unsigned long long *h_delta = nullptr;  // [2][kMaxDelta][2]
+  unsigned long long *h_slots = nullptr;  // [2][kMaxGrid][kSlotWords]
+  unsigned long long *h_mm = nullptr;     // [2][kMaxGrid][kSlotWords]
+  int n_scanners = 0;
+  int batching = 1;
+  double timeout_s = 20.0;
+  bool failed = false;
+  const int *rank_to_node = nullptr;  // host copy
+  Ctl ctl;
+  Seq seq;
+  long long spins = 0;
+
+  static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  // wait until the 64-bit word at p satisfies pred; false on timeout
+  template <class Pred>
+  bool wait_word(const unsigned long long *p, Pred pred, unsigned long long &out) {
+    unsigned long long v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+    if (pred(v)) {
+      out = v;
+      return true;
+    }
+    double t0 = now();
+    for (unsigned long long it = 0;; it++) {
+      v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+      if (pred(v)) {
+        out = v;
+        return true;
+      }
+      __builtin_ia32_pause();
+      if ((it & 0xffff) == 0xffff && now() - t0 > timeout_s) {
+        failed = true;
+        return false;
+      }
+    }
+  }
+
+  void publish(int kind) {
+    build_decision_words(ctl, kind, batching);
+    unsigned long long *rec = h_rec + (size_t)(ctl.seq & 1) * kDecWords * 2;
+    for (int i = kDecWords - 1; i >= 0; i--) store_tagged(rec + 2 * i, ctl.dw[i], (unsigned long long)ctl.seq);
+  }
+
+  // gather the candidate slots (written by the scanners over PCIe as single 16-byte stores)
+  void gather_candidates() {
+    const unsigned int seq_no = ctl.seq;
+    const unsigned long long *buf = h_slots + (size_t)(seq_no & 1) * kMaxGrid * kSlotWords;
+    const unsigned int tag = seq_no & 0xffffffu;
+    double bs = -1.0;
+    uint32_t brank = kRankNone, bmeta = 0;
+    int bslot = -1;
+    for (int c = 0; c < n_scanners; c++) {
+      const unsigned long long *slot = buf + (size_t)c * kSlotWords;
+      unsigned long long hi;
+      if (!wait_word(slot + 1, [&](unsigned long long v) { return (unsigned int)(v >> 40) == tag; }, hi)) break;
+      unsigned long long lo = __atomic_load_n(slot, __ATOMIC_RELAXED);
+      double sc;
+      memcpy(&sc, &lo, 8);
+      uint32_t rk = (uint32_t)(hi & 0xffffffu);
+      bool better_ = rk != kRankNone && (brank == kRankNone || sc > bs || (sc == bs && rk < brank));
+      if (better_) {
+        bs = sc;
+        brank = rk;
+        bmeta = (uint32_t)((hi >> 24) & 0xffffu);
+        bslot = c;
+      }
+    }
+    uint32_t bflags = bmeta >> 8, repeat = bmeta & 0xffu;
+    ctl.win.score = bs;
+    ctl.win.rank = brank;
+    ctl.win.flags = bflags;
+    ctl.win.node = brank == kRankNone ? -1 : rank_to_node[brank];
+    ctl.batch.valid = 0;
+    if (brank != kRankNone && !failed) {
+      const unsigned long long *slot = buf + (size_t)bslot * kSlotWords;
+      for (int k = 0; k < 2; k++) {
+        uint32_t f = (bflags >> (3 * k)) & 7u;
+        double a = 0;
+        if (f & WF_A_LT_MN) {
+          unsigned long long hi;
+          if (!wait_word(slot + 2 + 2 * k + 1, [&](unsigned long long v) { return (unsigned int)v == tag; }, hi)) break;
+          unsigned long long lo = __atomic_load_n(slot + 2 + 2 * k, __ATOMIC_RELAXED);
+          memcpy(&a, &lo, 8);
+        }
+        if (f) track_decrease(ctl.trk[k], f, a);
+      }
+      if (repeat) {
+        unsigned long long hi;
+        if (wait_word(slot + 7, [&](unsigned long long v) { return (unsigned int)v == tag; }, hi)) {
+          ctl.batch.valid = 1;
+          ctl.batch.node = ctl.win.node;
+          ctl.batch.to_idle = (bflags & SLOT_TO_IDLE) ? 1 : 0;
+          ctl.batch.left = (int)repeat;
+          ctl.batch.idx = 0;
+          ctl.batch.fl = __atomic_load_n(slot + 6, __ATOMIC_RELAXED);
+        }
+      }
+    }
+    ctl.seq = seq_no + 1;
+    ctl.n_delta = 0;
+  }
+
+  void gather_minmax() {
+    const unsigned int seq_no = ctl.seq;
+    const unsigned long long *buf = h_mm + (size_t)(seq_no & 1) * kMaxGrid * kSlotWords;
+    double gmn[2] = {DBL_MAX, DBL_MAX}, gmx[2] = {0, 0};
+    long long cmn[2] = {0, 0}, cmx[2] = {0, 0};
+    for (int c = 0; c < n_scanners && !failed; c++) {
+      const unsigned long long *slot = buf + (size_t)c * kSlotWords;
+      for (int k = 0; k < 2; k++) {
+        unsigned long long hi, lo;
+        double v;
+        if (!wait_word(slot + 4 * k + 1, [&](unsigned long long x) { return (x >> 32) == (unsigned long long)seq_no; }, hi)) break;
+        lo = __atomic_load_n(slot + 4 * k, __ATOMIC_RELAXED);
+        memcpy(&v, &lo, 8);
+        int cnt = (int)(hi & 0xffffffffu);
+        if (cnt > 0) {
+          if (cmn[k] == 0 || v < gmn[k]) {
+            gmn[k] = v;
+            cmn[k] = cnt;
+          } else if (v == gmn[k])
+            cmn[k] += cnt;
+        }
+        if (!wait_word(slot + 4 * k + 3, [&](unsigned long long x) { return (x >> 32) == (unsigned long long)seq_no; }, hi)) break;
+        lo = __atomic_load_n(slot + 4 * k + 2, __ATOMIC_RELAXED);
+        memcpy(&v, &lo, 8);
+        cnt = (int)(hi & 0xffffffffu);
+        if (cnt > 0) {
+          if (cmx[k] == 0 || v > gmx[k]) {
+            gmx[k] = v;
+            cmx[k] = cnt;
+          } else if (v == gmx[k])
+            cmx[k] += cnt;
+        }
+      }
+    }
+    for (int k = 0; k < 2; k++) {  // pack.go:66-86: min starts at MaxFloat64, max at 0
+      ctl.trk[k].mn = cmn[k] > 0 ? gmn[k] : DBL_MAX;
+      ctl.trk[k].mx = (cmx[k] > 0 && gmx[k] > 0) ? gmx[k] : 0.0;
+      ctl.trk[k].cnt_mn = (int)cmn[k];
+      ctl.trk[k].cnt_mx = (int)cmx[k];
+      ctl.trk[k].dirty = 0;
+    }
+    ctl.seq = seq_no + 1;
+    ctl.n_delta = 0;
+  }
+
+  void flush_deltas() {
+    publish(DK_FLUSH);
+    const unsigned int seq_no = ctl.seq;
+    const unsigned long long *buf = h_slots + (size_t)(seq_no & 1) * kMaxGrid * kSlotWords;
+    const unsigned int tag = seq_no & 0xffffffu;
+    for (int c = 0; c < n_scanners; c++) {
+      unsigned long long hi;
+      if (!wait_word(buf + (size_t)c * kSlotWords + 1, [&](unsigned long long v) { return (unsigned int)(v >> 40) == tag; }, hi)) break;
+    }
+    ctl.seq = seq_no + 1;
+    ctl.n_delta = 0;
+  }
+
+  // actions/allocate/allocate.go:46-111 — same steps as sequencer_main of the device-resident mode
+  void run_allocate() {
+    const DevSnap &s = *seq.s;
+    seq_init_job_order(seq);
+    for (;;) {
+      int job = pop_next_job(seq);
+      if (job < 0 || failed) break;
+      seq.n_ops = 0;
+      const JobRec rec = s.jrec[job];
+      ctl.job = job;
+      ctl.ctx_job = job;
+      ctl.ctx_queue = s.j_queue[job];
+      ctl.ctx_preempt = (s.j_flags[job] & KAI_JOB_PREEMPTIBLE) ? 1 : 0;
+      ctl.ctx_fresh = (!job_touched(seq, job) && rec.n_tta >= 0) ? 1 : 0;
+      ctl.ctx_ps = -1;
+      if (rec.n_podsets == 1) {
+        if (!job_touched(seq, job)) {
+          for (int w = 0; w < 3; w++) ctl.ctx_cnt[w] = rec.cnt[w];
+        } else {
+          for (int w = 0; w < 3; w++) ctl.ctx_cnt[w] = seq.rp.ps_active_alloc[(size_t)w * s.S + rec.ps0];
+        }
+        ctl.ctx_ps = rec.ps0;
+      }
+      int n;
+      double req[QR] = {0, 0, 0};
+      if (ctl.ctx_fresh) {
+        n = rec.n_tta;
+        ctl.ctx_base = rec.tb;
+        for (int r = 0; r < QR; r++) req[r] = rec.req0[r];
+      } else {
+        n = tasks_to_allocate(seq, job, true, nullptr);
+        ctl.ctx_base = -1;
+        for (int k = 0; k < n; k++)
+          for (int r = 0; r < QR; r++) req[r] = kadd(req[r], s.t_req[(size_t)seq.rp.tta[k] * s.R + r]);
+      }
+      bool job_success = !over_capacity(seq, job, req);
+      if (job_success) {
+        for (int k = 0; k < n; k++) {
+          int t = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
+          if (!seq_prepare_task(seq, t, job)) {
+            job_success = false;
+            break;
+          }
+          if (ctl.use_batch) {
+            seq_apply_batched(seq, t);
+            continue;
+          }
+          if (ctl.need_minmax) {
+            seq.minmax_exchanges++;
+            publish(DK_MINMAX);
+            gather_minmax();
+          }
+          publish(DK_SCAN);
+          gather_candidates();
+          if (failed) {
+            job_success = false;
+            break;
+          }
+          seq_apply_winner(seq, t);
+          if (!ctl.item_ok) {
+            job_success = false;
+            break;
+          }
+        }
+      }
+      if (job_success) {
+        if (should_pipeline_job(seq, job)) stmt_convert_all_allocated_to_pipelined(seq, job);
+        stmt_commit(seq);
+        record_visit(seq, job, 1);
+        if (has_tasks_to_allocate(seq, job)) push_job(seq, job);
+      } else {
+        stmt_rollback(seq, 0);
+        record_visit(seq, job, 0);
+      }
+      if (ctl.ctx_ps >= 0)
+        for (int w = 0; w < 3; w++) seq.rp.ps_active_alloc[(size_t)w * s.S + ctl.ctx_ps] = ctl.ctx_cnt[w];
+      ctl.ctx_ps = -1;
+      ctl.ctx_job = -1;
+      ctl.ctx_fresh = 0;
+      if (seq.error || failed) break;
+    }
+    publish(DK_DONE);  // carries the last node deltas; the scanners write their tiles back and exit
+  }
+};
+
+inline void host_flush_deltas(Seq &q) { ((HostBackend *)q.host_backend)->flush_deltas(); }
+
+}  // namespace kai

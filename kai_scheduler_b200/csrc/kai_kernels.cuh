@@ -15,6 +15,7 @@
 #include <cstdint>
 
 #include "kai_device.cuh"
+#include "kai_seq.cuh"
 
 namespace kai {
 
@@ -26,31 +27,22 @@ __device__ __forceinline__ void st_relaxed_b128(void *p, unsigned long long lo, 
                "l"(hi)
                : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_b128(void *p, unsigned long long lo, unsigned long long hi) {
+  asm volatile("{ .reg .b128 q; mov.b128 q, {%1, %2}; st.relaxed.sys.global.b128 [%0], q; }" ::"l"(p), "l"(lo),
+               "l"(hi)
+               : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_sys_b128(const void *p, unsigned long long &lo, unsigned long long &hi) {
+  asm volatile("{ .reg .b128 q; ld.relaxed.sys.global.b128 q, [%2]; mov.b128 {%0, %1}, q; }"
+               : "=l"(lo), "=l"(hi)
+               : "l"(p)
+               : "memory");
+}
 __device__ __forceinline__ void ld_relaxed_b128(const void *p, unsigned long long &lo, unsigned long long &hi) {
   asm volatile("{ .reg .b128 q; ld.relaxed.gpu.global.b128 q, [%2]; mov.b128 {%0, %1}, q; }"
                : "=l"(lo), "=l"(hi)
                : "l"(p)
                : "memory");
-}
-
-__device__ __forceinline__ double requestable_share(double max_allowed, double request) {
-  if (max_allowed == KAI_UNLIMITED) return request;
-  return fmin(max_allowed, request);
-}
-// resource_share.go:51-61
-__device__ __forceinline__ double allocatable_share(double deserved, double fair, double max_allowed) {
-  if (deserved == KAI_UNLIMITED) return max_allowed;
-  double a = fmax(deserved, fair);
-  if (max_allowed != KAI_UNLIMITED) a = fmin(max_allowed, a);
-  return a;
-}
-// resource_quantities.go:81-97
-__device__ __forceinline__ int compare_quantities(double q, double o) {
-  if (q == KAI_UNLIMITED) return o == KAI_UNLIMITED ? 0 : 1;
-  if (o == KAI_UNLIMITED) return -1;
-  if (q > o) return 1;
-  if (q < o) return -1;
-  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 #include "kai_oracle.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -903,7 +904,28 @@ struct kai_oracle {
     const int strategy = gpu_task ? cfg.gpu_placement : cfg.cpu_placement;
     // pack.go:66-86 getMinMaxPerNode over the node set passed to allocateTask
     double mn = DBL_MAX, mx = 0;
-    if (strategy == KAI_PLACEMENT_BINPACK) {
+    if (strategy == KAI_PLACEMENT_BINPACK && n_threads > 1 && n_set >= 4096) {
+      pool_start(n_threads);
+      std::vector<double> pmn(n_threads, DBL_MAX), pmx(n_threads, 0.0);
+      std::function<void(int)> mm = [&](int w) {
+        int k0 = (int)((int64_t)n_set * w / n_threads), k1 = (int)((int64_t)n_set * (w + 1) / n_threads);
+        double a = DBL_MAX, b = 0;
+        for (int k = k0; k < k1; k++) {
+          int n = node_set ? (*node_set)[k] : k;
+          if (A(res, n) == 0) continue;
+          double cur = I(res, n) + L(res, n);
+          if (cur < a) a = cur;
+          if (cur > b) b = cur;
+        }
+        pmn[w] = a;
+        pmx[w] = b;
+      };
+      pool_run(mm);
+      for (int w = 0; w < n_threads; w++) {
+        if (pmn[w] < mn) mn = pmn[w];
+        if (pmx[w] > mx) mx = pmx[w];
+      }
+    } else if (strategy == KAI_PLACEMENT_BINPACK) {
       for (int k = 0; k < n_set; k++) {
         int n = node_set ? (*node_set)[k] : k;
         if (A(res, n) == 0) continue;
@@ -940,14 +962,15 @@ struct kai_oracle {
       return b;
     };
     if (n_threads <= 1 || n_set < 4096) return sweep(0, n_set).node;
+    // fan the sweep out over the worker pool (mirrors the reference's goroutine-per-node fan-out,
+    // framework/session.go:243-262, with one slice per host thread)
+    pool_start(n_threads);
     std::vector<Best> part(n_threads);
-    std::vector<std::thread> th;
-    for (int w = 0; w < n_threads; w++)
-      th.emplace_back([&, w] {
-        int k0 = (int)((int64_t)n_set * w / n_threads), k1 = (int)((int64_t)n_set * (w + 1) / n_threads);
-        part[w] = sweep(k0, k1);
-      });
-    for (auto &x : th) x.join();
+    std::function<void(int)> fn = [&](int w) {
+      int k0 = (int)((int64_t)n_set * w / n_threads), k1 = (int)((int64_t)n_set * (w + 1) / n_threads);
+      part[w] = sweep(k0, k1);
+    };
+    pool_run(fn);
     Best b{-1.0, 0, -1};
     for (auto &p : part) {
       if (p.node < 0) continue;
@@ -955,6 +978,50 @@ struct kai_oracle {
     }
     return b.node;
   }
+
+  // ---- minimal spinning worker pool ----
+  std::vector<std::thread> pool;
+  std::atomic<uint64_t> pool_gen{0};
+  std::atomic<int> pool_pending{0};
+  std::atomic<bool> pool_stop{false};
+  const std::function<void(int)> *pool_fn = nullptr;
+  void pool_start(int n) {
+    if ((int)pool.size() == n - 1) return;
+    pool_shutdown();
+    pool_stop = false;
+    const uint64_t gen0 = pool_gen.load(std::memory_order_acquire);
+    for (int w = 1; w < n; w++)
+      pool.emplace_back([this, w, gen0] {
+        uint64_t seen = gen0;
+        for (;;) {
+          uint64_t g;
+          int idle = 0;
+          while ((g = pool_gen.load(std::memory_order_acquire)) == seen) {
+            if (pool_stop.load(std::memory_order_relaxed)) return;
+            if (++idle > 2000) std::this_thread::yield();
+          }
+          seen = g;
+          if (pool_stop.load(std::memory_order_acquire)) return;
+          (*pool_fn)(w);
+          pool_pending.fetch_sub(1, std::memory_order_acq_rel);
+        }
+      });
+  }
+  void pool_run(const std::function<void(int)> &fn) {
+    pool_fn = &fn;
+    pool_pending.store((int)pool.size(), std::memory_order_relaxed);
+    pool_gen.fetch_add(1, std::memory_order_release);
+    fn(0);
+    while (pool_pending.load(std::memory_order_acquire) != 0) {
+    }
+  }
+  void pool_shutdown() {
+    pool_stop = true;
+    pool_gen.fetch_add(1, std::memory_order_release);
+    for (auto &t : pool) t.join();
+    pool.clear();
+  }
+  ~kai_oracle() { pool_shutdown(); }
 
   // ---------------- actions/common/allocate.go ----------------
   // :121-174 allocateTask + allocateTaskToNode
