@@ -98,7 +98,7 @@ def run_reference(args, snap, workload):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, int(os.environ.get("KAI_REF_THREADS", "16")))
     o = Oracle(threads=cores)
     times, placed = [], 0
     for i in range(args.warmup + args.steps):
@@ -117,7 +117,8 @@ def run_reference(args, snap, workload):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "full workload per step (oracle/kai_oracle.cpp, node sweep over all host threads)"},
+                         "sample": "full workload per step (oracle/kai_oracle.cpp; node sweep fanned out over a spinning worker pool, "
+                                   "KAI_REF_THREADS threads, default 16 of %d host cores)" % (os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -142,6 +143,7 @@ def main():
                     f"{kw.get('n_queues', 4)} leaf queues, binpack, allocate action",
         "nodes": kw["n_nodes"], "pods": kw["n_jobs"] * kw.get("tasks_per_job", 1), "queues": kw.get("n_queues", 4),
         "parallelism": "replicas" if args.gpus > 1 else "1 GPU",
+        "sequencer": os.environ.get("KAI_SEQUENCER", "host"),
         "l2_policy": "node tables are re-uploaded (H2D) before every timed step, which replaces the L2-resident copy; "
                      "the action kernel then keeps its node tiles in shared memory",
     }

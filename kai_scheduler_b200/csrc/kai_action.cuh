@@ -257,12 +257,19 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
 constexpr int kSlotWords = 8;
 
 // candidate of this CTA -> slot words, including the same-node repeat analysis (lane 0 of warp 0)
+// Executed by ALL lanes of warp 0 of a scanner.  Lane i evaluates "placement i" on the winning node row
+// (i = 0 is the swept placement, i >= 1 are candidate repeats on the same node); lane 0 then walks the
+// placements in order to simulate the min/max trackers and decides how many repeats it can vouch for.
 __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decision &d, Cand local,
                                   unsigned long long *slot, unsigned int tag, int batching, bool sys) {
+  const int lane = threadIdx.x & 31;
+  local.score = __shfl_sync(0xffffffffu, local.score, 0);
+  local.rank = __shfl_sync(0xffffffffu, local.rank, 0);
+  local.ln = __shfl_sync(0xffffffffu, local.ln, 0);
   uint32_t flags = 0, repeat = 0;
   double a_gpu = 0, a_cpu = 0;
   unsigned long long rep_flags = 0;
-  if (local.rank != kRankNone) {
+  if (local.rank != kRankNone) {  // warp-uniform
     const int ln = local.ln, R = tl.R, n = tl.base + ln;
     double I[KAI_MAX_RES], L[KAI_MAX_RES];
     for (int r = 0; r < R; r++) {
@@ -271,46 +278,69 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
     }
     const double ag = tl.Agpu[ln], ac = tl.Acpu[ln], gc = tl.gpu_count[ln];
     const uint32_t nf = tl.flags[ln];
-    bool fit_i = true;
+    bool fit_i0 = true;
     for (int r = 0; r < R; r++) {
       double rq = d.req[r];
-      if (r >= 3 ? (rq != 0 && rq > I[r]) : (rq > I[r])) fit_i = false;
+      if (r >= 3 ? (rq != 0 && rq > I[r]) : (rq > I[r])) fit_i0 = false;
     }
-    const bool to_idle = !d.pipeline_only && (d.best_effort || fit_i);  // common/allocate.go:165-174
-    if (to_idle) flags |= SLOT_TO_IDLE;
+    const bool to_idle = !d.pipeline_only && (d.best_effort || fit_i0);  // common/allocate.go:165-174
+    // state before placement `lane`: the row after `lane` placements (node_info.go:457-493), same f64 ops
+    // in the same order as the sequential application
+    const int me = lane <= kMaxRepeat ? lane : kMaxRepeat;
+    for (int k = 0; k < me; k++)
+      for (int r = 0; r < R; r++) {
+        if (to_idle)
+          I[r] = __dsub_rn(I[r], d.req[r]);
+        else
+          L[r] = __dsub_rn(L[r], d.req[r]);
+      }
+    bool ok = true;  // placement `lane` is admissible as a repeat
+    if (lane > 0) {
+      double sc;
+      bool fi;
+      if (!node_key(d, R, I, L, 1, ag, ac, gc, nf, n, sc, fi))
+        ok = false;
+      else {
+        bool ti = !d.pipeline_only && (d.best_effort || fi);
+        if (ti != to_idle) ok = false;
+        if (!(sc >= local.score)) ok = false;  // node n must stay the argmax
+      }
+    }
+    double b2[2] = {0, 0}, a2[2] = {0, 0};
+    int has[2] = {0, 0};
+    for (int k = 0; k < 2; k++) {
+      int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
+      double overall = k == 0 ? ag : ac;
+      if (overall == 0 || d.req[res] == 0) continue;
+      has[k] = 1;
+      b2[k] = __dadd_rn(I[res], L[res]);
+      a2[k] = to_idle ? __dadd_rn(__dsub_rn(I[res], d.req[res]), L[res]) : __dadd_rn(I[res], __dsub_rn(L[res], d.req[res]));
+    }
+    // lane 0 walks the placements in order
     Track sim[2] = {trk[0], trk[1]};
     bool stop = false;
-    // placement 0 is the swept one; placements 1..kMaxRepeat are candidate repeats on the same node
+    if (to_idle) flags |= SLOT_TO_IDLE;
     for (int rep = 0; rep <= kMaxRepeat; rep++) {
-      if (rep > 0) {
-        if (!batching || stop) break;
-        double sc;
-        bool fi;
-        if (!node_key(d, R, I, L, 1, ag, ac, gc, nf, n, sc, fi)) break;
-        bool ti = !d.pipeline_only && (d.best_effort || fi);
-        if (ti != to_idle) break;
-        if (!(sc >= local.score)) break;  // node n must stay the argmax
-      }
-      uint32_t f6 = 0;
-      double a2[2] = {0, 0};
+      bool ok_r = __shfl_sync(0xffffffffu, ok ? 1 : 0, rep) != 0;
+      double bb[2], aa[2];
       for (int k = 0; k < 2; k++) {
-        int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
-        double overall = k == 0 ? ag : ac;
-        if (overall == 0 || d.req[res] == 0) continue;
-        double b = __dadd_rn(I[res], L[res]);
-        double a = to_idle ? __dadd_rn(__dsub_rn(I[res], d.req[res]), L[res]) : __dadd_rn(I[res], __dsub_rn(L[res], d.req[res]));
-        uint32_t f = sim[k].dirty ? 0u : track_flags(sim[k], b, a);
+        bb[k] = __shfl_sync(0xffffffffu, b2[k], rep);
+        aa[k] = __shfl_sync(0xffffffffu, a2[k], rep);
+      }
+      if (rep > 0 && (!batching || stop || !ok_r)) break;  // uniform: every lane holds the same sim state
+      uint32_t f6 = 0;
+      for (int k = 0; k < 2; k++) {
+        if (!has[k]) continue;
+        uint32_t f = sim[k].dirty ? 0u : track_flags(sim[k], bb[k], aa[k]);
         f6 |= f << (3 * k);
-        a2[k] = a;
       }
       if (rep > 0 && (f6 & ((WF_A_LT_MN) | (WF_A_LT_MN << 3)))) break;  // a new minimum needs its value: sweep instead
-      // does this placement leave (mn, mx) of the scored resource intact for the following repeats?
       for (int k = 0; k < 2; k++) {
         uint32_t f = (f6 >> (3 * k)) & 7u;
         bool scored = (k == 0) == (d.res == KAI_RES_GPU);
         if (f) {
           Track before = sim[k];
-          track_decrease(sim[k], f, a2[k]);
+          track_decrease(sim[k], f, aa[k]);
           if (scored && d.strategy == KAI_PLACEMENT_BINPACK &&
               (sim[k].dirty || sim[k].mn != before.mn || sim[k].mx != before.mx))
             stop = true;
@@ -318,22 +348,16 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
       }
       if (rep == 0) {
         flags |= f6 & 0x3fu;
-        a_gpu = a2[0];
-        a_cpu = a2[1];
+        a_gpu = aa[0];
+        a_cpu = aa[1];
       } else {
         rep_flags |= (unsigned long long)(f6 & 0x3fu) << (6 * (rep - 1));
         repeat = rep;
       }
-      // apply the placement to the simulated node row (node_info.go:457-493)
-      for (int r = 0; r < R; r++) {
-        if (to_idle)
-          I[r] = __dsub_rn(I[r], d.req[r]);
-        else
-          L[r] = __dsub_rn(L[r], d.req[r]);
-      }
     }
     if (repeat) flags |= SLOT_HAS_REPEAT;
   }
+  if (lane != 0) return;
   auto put = [&](unsigned long long *w, unsigned long long lo, unsigned long long hi2) {
     if (sys)
       st_relaxed_sys_b128(w, lo, hi2);  // slot lives in pinned host memory (host-sequenced mode)
@@ -725,7 +749,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
     if (kind == DK_SCAN) {
       Cand local = scan_tile(tile, sh.dec, s, sh_warp);
-      if (tid == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, p.mode != 0);
+      if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, p.mode != 0);
     } else if (kind == DK_MINMAX) {
       double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
       for (int ln = tid; ln < tile.count; ln += blockDim.x)
@@ -1065,39 +1089,35 @@ __device__ void relay_main(const ActionParams &p) {
   unsigned int seq = p.seq0;
   for (;;) {
     const unsigned long long *hrec = p.h_rec + (size_t)(seq & 1) * kDecWords * 2;
-    unsigned long long w0 = 0;
-    if (lane == 0) {
-      unsigned long long lo, hi;
-      Spin spin;
-      for (;;) {
-        ld_relaxed_sys_b128(hrec, lo, hi);
-        if (hi == (unsigned long long)seq || spin.expired(p, 10, seq, 0)) break;
-      }
-      w0 = lo;
+    const unsigned long long *hdl = p.h_delta + (size_t)(seq & 1) * kMaxDelta * 2;
+    unsigned long long *drec = p.dbuf + (size_t)(seq & 1) * kDecWords * 2;
+    unsigned long long *ddl = p.delta + (size_t)(seq & 1) * kMaxDelta * 2;
+    // lanes 0..15 poll the record words, lanes 16..31 speculatively the first 16 deltas: one PCIe round trip
+    const unsigned long long *src = lane < kDecWords ? hrec + 2 * lane : hdl + 2 * (lane - kDecWords);
+    unsigned long long lo = 0, hi = 0;
+    Spin spin;
+    for (;;) {
+      ld_relaxed_sys_b128(src, lo, hi);
+      unsigned int got = __ballot_sync(0xffffffffu, hi == (unsigned long long)seq);
+      if ((got & 0xffffu) == 0xffffu || spin.expired(p, 10, seq, lane)) break;
     }
-    w0 = __shfl_sync(0xffffffffu, w0, 0);
+    unsigned long long w0 = __shfl_sync(0xffffffffu, lo, 0);
     const int kind = (int)(w0 & 0xff);
     const int nd = (int)((w0 >> 32) & 0xffff);
     // deltas first, then the record words (every word is self-validating, so no ordering is required)
-    const unsigned long long *hdl = p.h_delta + (size_t)(seq & 1) * kMaxDelta * 2;
-    unsigned long long *ddl = p.delta + (size_t)(seq & 1) * kMaxDelta * 2;
-    for (int e = lane; e < nd; e += 32) {
-      unsigned long long lo, hi;
-      Spin spin;
-      do {
-        ld_relaxed_sys_b128(hdl + 2 * e, lo, hi);
-      } while (hi != (unsigned long long)seq && !spin.expired(p, 11, seq, e));
-      st_relaxed_b128(ddl + 2 * e, lo, hi);
+    for (int e = lane - kDecWords; e < nd; e += 32) {
+      if (e < 0) continue;
+      unsigned long long dlo = lo, dhi = hi;
+      if (e >= 32 - kDecWords || dhi != (unsigned long long)seq) {
+        Spin sp2;
+        do {
+          ld_relaxed_sys_b128(hdl + 2 * e, dlo, dhi);
+        } while (dhi != (unsigned long long)seq && !sp2.expired(p, 11, seq, e));
+      }
+      st_relaxed_b128(ddl + 2 * e, dlo, dhi);
     }
-    if (lane < kDecWords) {
-      unsigned long long lo, hi;
-      Spin spin;
-      do {
-        ld_relaxed_sys_b128(hrec + 2 * lane, lo, hi);
-      } while (hi != (unsigned long long)seq && !spin.expired(p, 12, seq, lane));
-      unsigned long long *drec = p.dbuf + (size_t)(seq & 1) * kDecWords * 2;
-      st_relaxed_b128(drec + 2 * lane, lo, hi);
-    }
+    __syncwarp();
+    if (lane < kDecWords) st_relaxed_b128(drec + 2 * lane, lo, hi);
     __syncwarp();
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     seq++;

@@ -54,10 +54,11 @@ def test_allocate_tables_gpu(cid, case):
     assert not errs, f"{case['source']} #{case['index']}: {errs}"
 
 
-@pytest.mark.parametrize("grid", ["1", "3", "148"])
-def test_allocate_tables_forced_grid(grid, monkeypatch):
-    """Same tables with forced CTA counts (including CTAs that own no node) to exercise the slot exchange."""
+@pytest.mark.parametrize("grid,mode", [("2", "host"), ("3", "device"), ("148", "host"), ("148", "device")])
+def test_allocate_tables_forced_grid(grid, mode, monkeypatch):
+    """Same tables with forced CTA counts (including scanners that own no node), both sequencer modes."""
     monkeypatch.setenv("KAI_GRID_EXACT", grid)
+    monkeypatch.setenv("KAI_SEQUENCER", mode)
     for cid, case in ALLOCATE:
         snap, meta = dsl.build_snapshot(case["topology"])
         re_, ro = run_both(snap)
@@ -77,10 +78,11 @@ def test_synthetic_parity(kw):
     assert_same(re_, ro)
 
 
-@pytest.mark.parametrize("env", ["KAI_NO_BATCHING", "KAI_NO_SMEM_HOT"])
+@pytest.mark.parametrize("env", [("KAI_NO_BATCHING", "1"), ("KAI_NO_SMEM_HOT", "1"), ("KAI_SEQUENCER", "device")])
 def test_synthetic_parity_fallback_paths(env, monkeypatch):
-    """Same answers with same-node batching off / with the hot replica arrays in global memory."""
-    monkeypatch.setenv(env, "1")
+    """Same answers with same-node batching off, with the sequencer's hot arrays in global memory, and with the
+    device-resident sequencer (CTA 0) instead of the host-sequenced default."""
+    monkeypatch.setenv(env[0], env[1])
     for kw in (dict(n_nodes=300, n_jobs=400, tasks_per_job=4, n_queues=12),
                dict(n_nodes=257, n_jobs=600, tasks_per_job=3, n_queues=7, mixed=True)):
         snap = synthetic.benchmark_snapshot(**kw)
@@ -157,7 +159,7 @@ def test_config2_full_size_properties():
     full = np.nonzero(used == 8)[0]
     assert len(full) == 5000 and set(snap.node_name_rank[full]) == set(range(5000))
     assert 0 < st.decisions <= 40_000  # sweeps; same-node batching places the rest without a sweep
-    o = Oracle(threads=os.cpu_count() or 1)
+    o = Oracle(threads=min(16, os.cpu_count() or 1))
     o.load(snap)
     ro = o.run("allocate")
     assert_same(res, ro)
