@@ -876,6 +876,8 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     seq.s = &p.s;
     seq.cfg = &p.cfg;
     seq.p = &p;
+    seq.delta_base = p.delta;
+    seq.host_backend = nullptr;
     seq.tile = nullptr;
     seq.ctl = &ctl;
     seq.n_ops = 0;

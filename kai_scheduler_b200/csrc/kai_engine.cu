@@ -905,6 +905,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     fprintf(stderr, "[kai] %s-sequenced action %.3f ms, %lld sweeps, %lld batched placements, %lld minmax exchanges, hot_in_smem=%d; CTA0 thread0 cycles:", host_mode ? "host" : "device", ms, c[1], c[15], c[5], (int)e->hot_in_smem);
     for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%lld", nm[i], c[8 + i]);
     fprintf(stderr, " n_key=%lld tta=%lld popheap=%lld\n", c[16], c[17], c[18]);
+    if (host_mode)
+      fprintf(stderr, "[kai] host sequencer: total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
+              e->hb.t_total * 1e3, e->hb.t_exchange * 1e3, c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
   }
   if (c[24] != 0) {
     char msg[256];

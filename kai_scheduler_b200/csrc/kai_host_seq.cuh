@@ -33,6 +33,7 @@ struct HostBackend {
   Ctl ctl;
   Seq seq;
   long long spins = 0;
+  double t_exchange = 0, t_total = 0;  // seconds: waiting for the GPU / whole action
 
   static double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -186,6 +187,8 @@ struct HostBackend {
   // actions/allocate/allocate.go:46-111 — same steps as sequencer_main of the device-resident mode
   void run_allocate() {
     const DevSnap &s = *seq.s;
+    double t_begin = now();
+    t_exchange = 0;
     seq_init_job_order(seq);
     for (;;) {
       int job = pop_next_job(seq);
@@ -235,8 +238,10 @@ struct HostBackend {
             publish(DK_MINMAX);
             gather_minmax();
           }
+          double tx = now();
           publish(DK_SCAN);
           gather_candidates();
+          t_exchange += now() - tx;
           if (failed) {
             job_success = false;
             break;
@@ -265,6 +270,7 @@ struct HostBackend {
       if (seq.error || failed) break;
     }
     publish(DK_DONE);  // carries the last node deltas; the scanners write their tiles back and exit
+    t_total = now() - t_begin;
   }
 };
 
