@@ -106,21 +106,56 @@ __global__ void k_prep_jobs(DevSnap s, int filter_non_pending, int filter_unread
   }
 }
 
+// One CTA per leaf queue: parallel compaction of the eligible jobs (block scan), then a parallel check that
+// the compacted run is already in JobOrderFn key order (host order is (priority desc, creation, uid); only
+// differing elastic classes inside one priority can break it); if not, thread 0 insertion-sorts the run.
 __global__ void k_prep_queues(DevSnap s) {
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < s.Q; q += gridDim.x * blockDim.x) {
-    int b = s.q_job_begin[q], e = s.q_job_begin[q + 1];
-    int n = 0;
-    int *out = s.leaf_sorted + b;
-    for (int k = b; k < e; k++) {
-      int job = s.q_jobs_sorted[k];
-      unsigned long long key = s.j_key0[job];
-      if (key == kKeyNone) continue;
-      int i = n++;
-      while (i > 0 && key < s.j_key0[out[i - 1]]) {
-        out[i] = out[i - 1];
-        i--;
+  __shared__ int warp_tot[32];
+  __shared__ int base, unsorted;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int b = s.q_job_begin[q], e = s.q_job_begin[q + 1];
+  int *out = s.leaf_sorted + b;
+  if (tid == 0) {
+    base = 0;
+    unsorted = 0;
+  }
+  __syncthreads();
+  for (int k0 = b; k0 < e; k0 += blockDim.x) {
+    int k = k0 + tid;
+    int job = k < e ? s.q_jobs_sorted[k] : -1;
+    bool el = job >= 0 && s.j_key0[job] != kKeyNone;
+    unsigned int m = __ballot_sync(0xffffffffu, el);
+    int pre = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; w++) off += warp_tot[w];
+    if (el) out[off + pre] = job;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < nw; w++) t += warp_tot[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  const int n = base;
+  for (int i = tid + 1; i < n; i += blockDim.x)
+    if (s.j_key0[out[i]] < s.j_key0[out[i - 1]]) unsorted = 1;
+  __syncthreads();
+  if (tid == 0) {
+    if (unsorted) {
+      for (int i = 1; i < n; i++) {
+        int job = out[i];
+        unsigned long long key = s.j_key0[job];
+        int p = i;
+        while (p > 0 && key < s.j_key0[out[p - 1]]) {
+          out[p] = out[p - 1];
+          p--;
+        }
+        out[p] = job;
       }
-      out[i] = job;
     }
     s.leaf_count[q] = n;
   }

@@ -756,7 +756,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 32, e->stream));
   cudaEventRecord(e->ev[2], e->stream);
   if (e->J > 0) k_prep_jobs<<<std::min(e->num_sms * 8, (e->J + 255) / 256), 256, 0, e->stream>>>(e->ds, 1, 1);
-  if (e->Q > 0) k_prep_queues<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->ds);
+  if (e->Q > 0) k_prep_queues<<<e->Q, 256, 0, e->stream>>>(e->ds);
   long long c[32];
   memset(c, 0, sizeof(c));
   if (host_mode) {
