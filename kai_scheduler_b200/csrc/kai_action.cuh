@@ -784,7 +784,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
     if (kind == DK_SCAN) {
       Cand local = scan_tile(tile, sh.dec, s, sh_warp);
-      if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, p.mode != 0);
+      if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, false);
     } else if (kind == DK_MINMAX) {
       double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
       for (int ln = tid; ln < tile.count; ln += blockDim.x)
@@ -836,10 +836,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         unsigned long long tag = seq;
         slot = p.mmbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
         auto put = [&](unsigned long long *w, unsigned long long lo, unsigned long long hi2) {
-          if (p.mode != 0)
-            st_relaxed_sys_b128(w, lo, hi2);
-          else
-            st_relaxed_b128(w, lo, hi2);
+          st_relaxed_b128(w, lo, hi2);
         };
         put(slot + 0, (unsigned long long)__double_as_longlong(mn[0]), (tag << 32) | (unsigned int)tot[0]);
         put(slot + 2, (unsigned long long)__double_as_longlong(mx[0]), (tag << 32) | (unsigned int)tot[1]);
@@ -849,10 +846,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     } else {  // DK_FLUSH: acknowledge
       if (tid == 0) {
         unsigned long long hi = ((unsigned long long)(seq & 0xffffffu) << 40) | (unsigned long long)kRankNone;
-        if (p.mode != 0)
-          st_relaxed_sys_b128(slot, (unsigned long long)__double_as_longlong(-1.0), hi);
-        else
-          st_relaxed_b128(slot, (unsigned long long)__double_as_longlong(-1.0), hi);
+        st_relaxed_b128(slot, (unsigned long long)__double_as_longlong(-1.0), hi);
       }
     }
     seq++;
@@ -1120,6 +1114,134 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
 // relay CTA (host-sequenced mode): forwards the host's decision records and node deltas from pinned mapped
 // host memory (one PCIe reader for the whole GPU) into the device-side record buffer the scanners poll
 // =============================================================================================
+// Reduce the scanners' answers for record `seq` on the GPU and write ONE 64-byte line to host memory (a host
+// core pays ~80 ns per GPU-written cache line it reads; 147 lines per sweep were the bottleneck).
+__device__ void relay_reduce(const ActionParams &p, int kind, unsigned int seq) {
+  const int lane = threadIdx.x & 31;
+  const int n = p.grid - 1;
+  if (kind == DK_SCAN || kind == DK_FLUSH) {
+    const unsigned long long *buf = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
+    const unsigned int tag = seq & 0xffffffu;
+    double bs = -1.0;
+    uint32_t brank = kRankNone;
+    unsigned long long bhi = ((unsigned long long)tag << 40) | (unsigned long long)kRankNone;
+    int bslot = -1;
+    for (int c = lane; c < n; c += 32) {
+      unsigned long long lo, hi;
+      Spin spin;
+      do {
+        ld_relaxed_b128(buf + (size_t)c * kSlotWords, lo, hi);
+      } while ((unsigned int)(hi >> 40) != tag && !spin.expired(p, 13, seq, c));
+      double sc = __longlong_as_double((long long)lo);
+      uint32_t rk = (uint32_t)(hi & 0xffffffu);
+      if (better(sc, rk, bs, brank)) {
+        bs = sc;
+        brank = rk;
+        bhi = hi;
+        bslot = c;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double os = __shfl_xor_sync(0xffffffffu, bs, o);
+      uint32_t orank = __shfl_xor_sync(0xffffffffu, brank, o);
+      unsigned long long ohi = __shfl_xor_sync(0xffffffffu, bhi, o);
+      int osl = __shfl_xor_sync(0xffffffffu, bslot, o);
+      if (better(os, orank, bs, brank)) {
+        bs = os;
+        brank = orank;
+        bhi = ohi;
+        bslot = osl;
+      }
+    }
+    unsigned long long *out = p.h_slot + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
+    if (brank != kRankNone && lane >= 1 && lane <= 3) {  // payload words B, C, D of the winning slot
+      const uint32_t repeat = (uint32_t)((bhi >> 24) & 0xffu);
+      if (lane < 3 || repeat) {
+        unsigned long long lo, hi;
+        Spin spin;
+        do {
+          ld_relaxed_b128(buf + (size_t)bslot * kSlotWords + 2 * lane, lo, hi);
+        } while ((unsigned int)hi != tag && !spin.expired(p, 14, seq, bslot));
+        st_relaxed_sys_b128(out + 2 * lane, lo, hi);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) st_relaxed_sys_b128(out, (unsigned long long)__double_as_longlong(bs), bhi);
+  } else if (kind == DK_MINMAX) {
+    const unsigned long long *buf = p.mmbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
+    const unsigned long long tag = seq;
+    double gmn[2] = {DBL_MAX, DBL_MAX}, gmx[2] = {0, 0};
+    long long cmn[2] = {0, 0}, cmx[2] = {0, 0};
+    for (int cta = lane; cta < n; cta += 32) {
+      const unsigned long long *slot = buf + (size_t)cta * kSlotWords;
+      for (int k = 0; k < 2; k++) {
+        unsigned long long lo, hi;
+        {
+          Spin spin;
+          do {
+            ld_relaxed_b128(slot + 4 * k, lo, hi);
+          } while ((hi >> 32) != (tag & 0xffffffffu) && !spin.expired(p, 15, seq, cta));
+        }
+        double v = __longlong_as_double((long long)lo);
+        int cnt = (int)(hi & 0xffffffffu);
+        if (cnt > 0) {
+          if (cmn[k] == 0 || v < gmn[k]) {
+            gmn[k] = v;
+            cmn[k] = cnt;
+          } else if (v == gmn[k])
+            cmn[k] += cnt;
+        }
+        {
+          Spin spin;
+          do {
+            ld_relaxed_b128(slot + 4 * k + 2, lo, hi);
+          } while ((hi >> 32) != (tag & 0xffffffffu) && !spin.expired(p, 16, seq, cta));
+        }
+        v = __longlong_as_double((long long)lo);
+        cnt = (int)(hi & 0xffffffffu);
+        if (cnt > 0) {
+          if (cmx[k] == 0 || v > gmx[k]) {
+            gmx[k] = v;
+            cmx[k] = cnt;
+          } else if (v == gmx[k])
+            cmx[k] += cnt;
+        }
+      }
+    }
+    for (int k = 0; k < 2; k++)
+      for (int o = 16; o > 0; o >>= 1) {
+        double omn = __shfl_xor_sync(0xffffffffu, gmn[k], o);
+        long long ocmn = __shfl_xor_sync(0xffffffffu, cmn[k], o);
+        double omx = __shfl_xor_sync(0xffffffffu, gmx[k], o);
+        long long ocmx = __shfl_xor_sync(0xffffffffu, cmx[k], o);
+        if (ocmn > 0) {
+          if (cmn[k] == 0 || omn < gmn[k]) {
+            gmn[k] = omn;
+            cmn[k] = ocmn;
+          } else if (omn == gmn[k])
+            cmn[k] += ocmn;
+        }
+        if (ocmx > 0) {
+          if (cmx[k] == 0 || omx > gmx[k]) {
+            gmx[k] = omx;
+            cmx[k] = ocmx;
+          } else if (omx == gmx[k])
+            cmx[k] += ocmx;
+        }
+      }
+    if (lane == 0) {
+      unsigned long long *out = p.h_mmslot + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
+      for (int k = 0; k < 2; k++) {
+        unsigned int c0 = (unsigned int)(cmn[k] > 0x7fffffff ? 0x7fffffff : cmn[k]);
+        unsigned int c1 = (unsigned int)(cmx[k] > 0x7fffffff ? 0x7fffffff : cmx[k]);
+        st_relaxed_sys_b128(out + 4 * k, (unsigned long long)__double_as_longlong(gmn[k]), (tag << 32) | c0);
+        st_relaxed_sys_b128(out + 4 * k + 2, (unsigned long long)__double_as_longlong(gmx[k]), (tag << 32) | c1);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 __device__ void relay_main(const ActionParams &p) {
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
@@ -1157,6 +1279,7 @@ __device__ void relay_main(const ActionParams &p) {
     if (lane < kDecWords) st_relaxed_b128(drec + 2 * lane, lo, hi);
     __syncwarp();
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
+    relay_reduce(p, kind, seq);
     seq++;
   }
 }

@@ -155,6 +155,7 @@ struct ActionParams {
   int batching;         // same-node batching of consecutive identical pods (1 = on)
   int mode;             // 0 = device-resident sequencer (CTA 0), 1 = host-sequenced (CTA 0 relays host records)
   unsigned long long *h_rec, *h_delta;  // mode 1: decision record / delta words in pinned mapped host memory
+  unsigned long long *h_slot, *h_mmslot;  // mode 1: this GPU's reduced answer line [2][kSlotWords] in (shared) host memory
   int spin_log2;        // watchdog: polls before a wait is declared dead
 };
 

@@ -749,8 +749,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (host_mode) {
     p.h_rec = e->h_rec;
     p.h_delta = e->h_delta;
-    p.xbuf = e->h_slots;  // scanners answer straight into pinned host memory
-    p.mmbuf = e->h_mm;
+    p.h_slot = e->h_slots;  // one reduced answer line per GPU (this engine = GPU 0 of 1)
+    p.h_mmslot = e->h_mm;
   }
   void *args[] = {(void *)&p};
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 32, e->stream));
@@ -777,7 +777,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.h_delta = e->h_delta;
     hb.h_slots = e->h_slots;
     hb.h_mm = e->h_mm;
-    hb.n_scanners = e->grid - 1;
+    hb.n_scanners = 1;  // the relay CTA reduces the scanners' answers on the GPU: one line per GPU
     hb.batching = p.batching;
     hb.failed = false;
     hb.rank_to_node = e->rank_to_node_h.data();
