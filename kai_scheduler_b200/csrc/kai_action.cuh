@@ -351,44 +351,56 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
       b2[k] = __dadd_rn(I[res], L[res]);
       a2[k] = to_idle ? __dadd_rn(__dsub_rn(I[res], d.req[res]), L[res]) : __dadd_rn(I[res], __dsub_rn(L[res], d.req[res]));
     }
-    // lane 0 walks the placements in order
-    Track sim[2] = {trk[0], trk[1]};
-    bool stop = false;
+    // Tracker events of placement `lane`.  Within a batch min/max of both resources are constant (the batch
+    // ends before any placement that would move them), so every lane can evaluate its events against the
+    // trackers of the record; only the "last node leaves the max" rule needs a prefix count.
+    uint32_t f6 = 0;
+    for (int k = 0; k < 2; k++) {
+      if (!has[k] || trk[k].dirty) continue;
+      f6 |= track_flags(trk[k], b2[k], a2[k]) << (3 * k);
+    }
+    if (lane > kMaxRepeat) {
+      ok = false;
+      f6 = 0;
+    }
+    const int sk = d.res == KAI_RES_GPU ? 0 : 1;  // scored resource
+    const bool tracked = d.strategy == KAI_PLACEMENT_BINPACK && !trk[sk].dirty;
+    const uint32_t lt_any = (f6 & WF_A_LT_MN) | ((f6 >> 3) & WF_A_LT_MN);
+    const uint32_t eqmx_s = (f6 >> (3 * sk)) & WF_B_EQ_MX;
+    const unsigned ok_mask = __ballot_sync(0xffffffffu, ok);
+    const unsigned lt_mask = __ballot_sync(0xffffffffu, lt_any != 0);
+    const unsigned eq_mask = __ballot_sync(0xffffffffu, eqmx_s != 0);
+    // placement j "stops" the batch after itself if it moves min/max of the scored resource or dirties it
+    const int n_eq_before = __popc(eq_mask & ((1u << lane) - 1));
+    const bool lt_s = ((f6 >> (3 * sk)) & WF_A_LT_MN) != 0;
+    const bool stops = tracked && (lt_s || (eqmx_s && n_eq_before + 1 >= trk[sk].cnt_mx));
+    const unsigned stop_mask = __ballot_sync(0xffffffffu, stops);
+    // repeat i (>= 1) is usable iff ok_i, it establishes no new minimum, and no placement before it stopped
+    int rep_n = 0;
+    if (batching) {
+      for (int i2 = 1; i2 <= kMaxRepeat; i2++) {
+        if (!((ok_mask >> i2) & 1u) || ((lt_mask >> i2) & 1u)) break;
+        if (stop_mask & ((1u << i2) - 1)) break;
+        rep_n = i2;
+      }
+    }
+    repeat = (uint32_t)rep_n;
     if (to_idle) flags |= SLOT_TO_IDLE;
-    for (int rep = 0; rep <= kMaxRepeat; rep++) {
-      bool ok_r = __shfl_sync(0xffffffffu, ok ? 1 : 0, rep) != 0;
-      double bb[2], aa[2];
-      for (int k = 0; k < 2; k++) {
-        bb[k] = __shfl_sync(0xffffffffu, b2[k], rep);
-        aa[k] = __shfl_sync(0xffffffffu, a2[k], rep);
+    {
+      uint32_t f0 = __shfl_sync(0xffffffffu, f6, 0);
+      flags |= f0 & 0x3fu;
+      a_gpu = __shfl_sync(0xffffffffu, a2[0], 0);
+      a_cpu = __shfl_sync(0xffffffffu, a2[1], 0);
+      // pack the event bits of repeats 1..repeat: lane i contributes bits [6(i-1), 6i)
+      unsigned lo32 = 0, hi32 = 0;
+      if (lane >= 1 && lane <= rep_n) {
+        unsigned long long w = (unsigned long long)(f6 & 0x3fu) << (6 * (lane - 1));
+        lo32 = (unsigned)(w & 0xffffffffu);
+        hi32 = (unsigned)(w >> 32);
       }
-      if (rep > 0 && (!batching || stop || !ok_r)) break;  // uniform: every lane holds the same sim state
-      uint32_t f6 = 0;
-      for (int k = 0; k < 2; k++) {
-        if (!has[k]) continue;
-        uint32_t f = sim[k].dirty ? 0u : track_flags(sim[k], bb[k], aa[k]);
-        f6 |= f << (3 * k);
-      }
-      if (rep > 0 && (f6 & ((WF_A_LT_MN) | (WF_A_LT_MN << 3)))) break;  // a new minimum needs its value: sweep instead
-      for (int k = 0; k < 2; k++) {
-        uint32_t f = (f6 >> (3 * k)) & 7u;
-        bool scored = (k == 0) == (d.res == KAI_RES_GPU);
-        if (f) {
-          Track before = sim[k];
-          track_decrease(sim[k], f, aa[k]);
-          if (scored && d.strategy == KAI_PLACEMENT_BINPACK &&
-              (sim[k].dirty || sim[k].mn != before.mn || sim[k].mx != before.mx))
-            stop = true;
-        }
-      }
-      if (rep == 0) {
-        flags |= f6 & 0x3fu;
-        a_gpu = aa[0];
-        a_cpu = aa[1];
-      } else {
-        rep_flags |= (unsigned long long)(f6 & 0x3fu) << (6 * (rep - 1));
-        repeat = rep;
-      }
+      lo32 = __reduce_or_sync(0xffffffffu, lo32);
+      hi32 = __reduce_or_sync(0xffffffffu, hi32);
+      rep_flags = ((unsigned long long)hi32 << 32) | lo32;
     }
     if (repeat) flags |= SLOT_HAS_REPEAT;
   }
@@ -693,7 +705,9 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
   }
   __syncthreads();
   unsigned int seq = p.seq0;
+  long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (;;) {
+    long long c0 = clock64();
     // ---- wait for decision record `seq` ----
     if (warp == 0) {
       const unsigned long long *rec0 = p.dbuf + (size_t)(seq & 1) * kDecWords * 2;
@@ -707,6 +721,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         }
       }
       __syncwarp();
+      if (tid == 0) ts[0] += clock64() - c0;
       if (lane < kDecWords) {  // every word is self-validating
         unsigned long long lo, hi;
         {
@@ -719,34 +734,39 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned long long w0 = sh.dw[0];
+    long long c1 = clock64();
+    if (tid < 32) {  // decode in parallel: lane r writes req[r], lanes 8/9 the trackers, lane 10 the scalars
+      const unsigned long long w0 = sh.dw[0];
+      const unsigned int bits = (unsigned int)((w0 >> 24) & 0xff);
       Decision &d = sh.dec;
-      sh.kind = (int)(w0 & 0xff);
-      d.res = (int)((w0 >> 8) & 0xff);
-      d.strategy = (int)((w0 >> 16) & 0xff);
-      unsigned int bits = (unsigned int)((w0 >> 24) & 0xff);
-      sh.n_delta = (int)((w0 >> 32) & 0xffff);
-      d.gpu_task = (bits & DB_GPU_TASK) ? 1 : 0;
-      d.best_effort = (bits & DB_BEST_EFFORT) ? 1 : 0;
-      d.pipeline_only = (bits & DB_PIPELINE_ONLY) ? 1 : 0;
-      sh.batching = (bits & DB_BATCHING) ? 1 : 0;
-      d.nominated = (int)(unsigned int)(sh.dw[1] & 0xffffffffu);
-      d.pred_class = (int)(unsigned int)(sh.dw[1] >> 32);
-      for (int r = 0; r < KAI_MAX_RES; r++) d.req[r] = __longlong_as_double((long long)sh.dw[2 + r]);
-      for (int k = 0; k < 2; k++) {
+      if (tid < KAI_MAX_RES) d.req[tid] = __longlong_as_double((long long)sh.dw[2 + tid]);
+      if (tid == 8 || tid == 9) {
+        const int k = tid - 8;
         sh.trk[k].mn = __longlong_as_double((long long)sh.dw[10 + 2 * k]);
         sh.trk[k].mx = __longlong_as_double((long long)sh.dw[11 + 2 * k]);
         sh.trk[k].cnt_mn = (int)(unsigned int)(sh.dw[14 + k] & 0xffffffffu);
         sh.trk[k].cnt_mx = (int)(unsigned int)(sh.dw[14 + k] >> 32);
         sh.trk[k].dirty = (bits & (k == 0 ? DB_DIRTY0 : DB_DIRTY1)) ? 1 : 0;
       }
-      int tk = d.res == KAI_RES_GPU ? 0 : 1;
-      d.mn = sh.trk[tk].mn;
-      d.mx = sh.trk[tk].mx;
-      d.task = -1;
+      if (tid == 10) {
+        sh.kind = (int)(w0 & 0xff);
+        d.res = (int)((w0 >> 8) & 0xff);
+        d.strategy = (int)((w0 >> 16) & 0xff);
+        sh.n_delta = (int)((w0 >> 32) & 0xffff);
+        d.gpu_task = (bits & DB_GPU_TASK) ? 1 : 0;
+        d.best_effort = (bits & DB_BEST_EFFORT) ? 1 : 0;
+        d.pipeline_only = (bits & DB_PIPELINE_ONLY) ? 1 : 0;
+        sh.batching = (bits & DB_BATCHING) ? 1 : 0;
+        d.nominated = (int)(unsigned int)(sh.dw[1] & 0xffffffffu);
+        d.pred_class = (int)(unsigned int)(sh.dw[1] >> 32);
+        const int tk = d.res == KAI_RES_GPU ? 0 : 1;
+        d.mn = __longlong_as_double((long long)sh.dw[10 + 2 * tk]);
+        d.mx = __longlong_as_double((long long)sh.dw[11 + 2 * tk]);
+        d.task = -1;
+      }
     }
     __syncthreads();
+    long long c2 = clock64();
     // ---- apply the node deltas that belong to this tile (loads in parallel, application in list order) ----
     const int nd = sh.n_delta;
     if (nd > 0) {
@@ -779,11 +799,14 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       }
       __syncthreads();
     }
+    long long c3 = clock64();
     const int kind = sh.kind;
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
     if (kind == DK_SCAN) {
       Cand local = scan_tile(tile, sh.dec, s, sh_warp);
+      long long c4 = clock64();
+      if (tid == 0) ts[4] += c4 - c3;
       if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, false);
     } else if (kind == DK_MINMAX) {
       double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
@@ -849,9 +872,19 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         st_relaxed_b128(slot, (unsigned long long)__double_as_longlong(-1.0), hi);
       }
     }
+    if (tid == 0) {
+      long long c5 = clock64();
+      ts[1] += c1 - c0;  // poll + words
+      ts[2] += c2 - c1;  // decode
+      ts[3] += c3 - c2;  // deltas
+      ts[5] += c5 - c3;  // scan + publish
+      ts[6]++;
+    }
     seq++;
     __syncthreads();
   }
+  if (tid == 0 && my == 0)
+    for (int i = 0; i < 7; i++) p.counters[32 + i] = ts[i];
   // ---- DONE: write the tile back to the session tables ----
   for (int ln = tid; ln < tile.count; ln += blockDim.x) {
     int n = tile.base + ln;
@@ -1246,6 +1279,7 @@ __device__ void relay_main(const ActionParams &p) {
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   unsigned int seq = p.seq0;
+  long long acc_fwd = 0, acc_wait = 0, acc_red = 0, n_rec = 0;
   for (;;) {
     const unsigned long long *hrec = p.h_rec + (size_t)(seq & 1) * kDecWords * 2;
     const unsigned long long *hdl = p.h_delta + (size_t)(seq & 1) * kMaxDelta * 2;
@@ -1260,6 +1294,7 @@ __device__ void relay_main(const ActionParams &p) {
       unsigned int got = __ballot_sync(0xffffffffu, hi == (unsigned long long)seq);
       if ((got & 0xffffu) == 0xffffu || spin.expired(p, 10, seq, lane)) break;
     }
+    long long tr0 = clock64();
     unsigned long long w0 = __shfl_sync(0xffffffffu, lo, 0);
     const int kind = (int)(w0 & 0xff);
     const int nd = (int)((w0 >> 32) & 0xffff);
@@ -1279,8 +1314,18 @@ __device__ void relay_main(const ActionParams &p) {
     if (lane < kDecWords) st_relaxed_b128(drec + 2 * lane, lo, hi);
     __syncwarp();
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
+    long long tr1 = clock64();
     relay_reduce(p, kind, seq);
+    long long tr2 = clock64();
+    acc_fwd += tr1 - tr0;
+    acc_red += tr2 - tr1;
+    n_rec++;
     seq++;
+  }
+  if (lane == 0) {
+    p.counters[20] = acc_fwd;
+    p.counters[21] = acc_red;
+    p.counters[22] = n_rec;
   }
 }
 

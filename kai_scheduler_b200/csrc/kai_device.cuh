@@ -16,7 +16,7 @@
 namespace kai {
 
 constexpr int QR = KAI_QRES;
-constexpr int kThreads = 512;          // threads per CTA of the action kernel
+constexpr int kThreads = 128;          // threads per CTA of the action kernel (4 warps: cheap barriers/reductions)
 constexpr int kMaxGrid = 1024;         // exchange slots per GPU
 constexpr uint32_t kNoRank = 0xFFFFFFFFu;
 constexpr int kDecWords = 16;         // tagged words of one decision record

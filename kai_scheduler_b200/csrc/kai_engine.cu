@@ -597,12 +597,12 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->visits_cap = std::max(16, 2 * J + T + 16);
   {
     size_t xb = (size_t)2 * kMaxGrid * 8 * 8;
-    size_t misc = 2 * xb + 256 + sizeof(long long) * 32 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
+    size_t misc = 2 * xb + 256 + sizeof(long long) * 48 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
                   sizeof(unsigned long long) * 2 * kDecWords * 2 + sizeof(unsigned long long) * 2 * kMaxDelta * 2 + 1024;
     CK(e->dmisc.reserve(misc));
     e->xbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
     e->mmbuf = e->dmisc.take<unsigned long long>(2 * kMaxGrid * 8);
-    e->counters = e->dmisc.take<long long>(32);
+    e->counters = e->dmisc.take<long long>(48);
     e->d_visits = e->dmisc.take<kai_job_visit>(e->visits_cap);
     e->fs_w = e->dmisc.take<double>(QN + 1);
     e->fs_rr = e->dmisc.take<double>(QN + 1);
@@ -753,11 +753,11 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     p.h_mmslot = e->h_mm;
   }
   void *args[] = {(void *)&p};
-  CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 32, e->stream));
+  CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 48, e->stream));
   cudaEventRecord(e->ev[2], e->stream);
   if (e->J > 0) k_prep_jobs<<<std::min(e->num_sms * 8, (e->J + 255) / 256), 256, 0, e->stream>>>(e->ds, 1, 1);
   if (e->Q > 0) k_prep_queues<<<e->Q, 256, 0, e->stream>>>(e->ds);
-  long long c[32];
+  long long c[48];
   memset(c, 0, sizeof(c));
   if (host_mode) {
     // host mirror of everything the open-session / prepare kernels produced
@@ -854,9 +854,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.run_allocate();
     CK(cudaStreamSynchronize(e->stream));
     {
-      long long cd[32];
+      long long cd[48];
       CK(cudaMemcpy(cd, e->counters, sizeof(cd), cudaMemcpyDeviceToHost));
-      for (int i = 24; i < 28; i++) c[i] = cd[i];
+      for (int i = 20; i < 28; i++) c[i] = cd[i];
+      for (int i = 32; i < 40; i++) c[i] = cd[i];
     }
     c[0] = seq.n_visits;
     c[1] = seq.sweeps;
@@ -908,6 +909,12 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer: total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
               e->hb.t_total * 1e3, e->hb.t_exchange * 1e3, c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
+    if (host_mode && c[22] > 0)
+      fprintf(stderr, "[kai] relay CTA per record: forward %lld cycles, scanners+reduce %lld cycles (%lld records)\n",
+              c[20] / c[22], c[21] / c[22], c[22]);
+    if (host_mode && c[38] > 0)
+      fprintf(stderr, "[kai] scanner 0 per record (cycles): wait-for-record %lld (of which word-0 poll %lld), decode %lld, deltas %lld, scan %lld, scan+publish %lld\n",
+              c[33] / c[38], c[32] / c[38], c[34] / c[38], c[35] / c[38], c[36] / c[38], c[37] / c[38]);
   }
   if (c[24] != 0) {
     char msg[256];

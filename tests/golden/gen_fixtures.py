@@ -243,3 +243,124 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------
+# unit-level known answers
+# ---------------------------------------------------------------------------------------------
+def _num(x, env=None):
+    """Evaluate a resolved literal value to a float (constants, float64(..), simple arithmetic)."""
+    env = env or {}
+    if isinstance(x, bool):
+        return x
+    if isinstance(x, (int, float)):
+        return float(x)
+    if isinstance(x, str):
+        return float(x)
+    if isinstance(x, dict):
+        if "__ident" in x:
+            name = x["__ident"]
+            table = {"scores.MaxHighDensity": 9.0, "commonconstants.UnlimitedResourceQuantity": -1.0,
+                     "constants.UnlimitedResourceQuantity": -1.0}
+            if name in table:
+                return table[name]
+            if name in env:
+                return env[name]
+            raise ValueError(f"unknown identifier {name}")
+        if "__binop" in x:
+            l, r = _num(x["l"], env), _num(x["r"], env)
+            return {"*": l * r, "+": l + r, "-": l - r, "/": l / r}[x["__binop"]]
+        if "__neg" in x:
+            return -_num(x["__neg"], env)
+        if "__call" in x and x["__call"] in ("float64", "float32", "int", "int64") and len(x["args"]) == 1:
+            return _num(x["args"][0], env)
+    raise ValueError(f"cannot evaluate {x!r}")
+
+
+def gen_nodeplacement():
+    """plugins/nodeplacement/nodepack_test.go + nodespread_test.go: exact expected f64 scores per node."""
+    out = {}
+    for fname, kind in (("nodepack_test.go", "binpack"),):
+        src = open(os.path.join(REF, "plugins", "nodeplacement", fname)).read()
+        tables = find_literals(src, "[]testTopologyMetadata")
+        found = []
+
+        def collect(x):
+            if isinstance(x, dict):
+                if "testNodeMetadataMap" in x:
+                    found.append(x)
+                else:
+                    for v in x.values():
+                        collect(v)
+            elif isinstance(x, list):
+                for v in x:
+                    collect(v)
+
+        collect(tables)
+        cases = []
+        for table in [found]:
+            for c in table:
+                nodes = {}
+                for name, nd in c["testNodeMetadataMap"].items():
+                    nodes[name] = {
+                        "allocatable_gpus": float(nd["nodeAllocatableGPUs"]),
+                        "idle_gpus": float(nd["nodeIdleGPUs"]),
+                        "expected_score": _num(nd["nodeExpectedScore"]),
+                    }
+                cases.append({"source": f"pkg/scheduler/plugins/nodeplacement/{fname}", "name": c["name"],
+                              "task": c.get("taskName", ""), "nodes": nodes})
+        out[kind] = cases
+    # nodespread_test.go: anonymous-struct case lists {gpuCount|cpuMillis.., nonAllocated, expected}
+    src = open(os.path.join(REF, "plugins", "nodeplacement", "nodespread_test.go")).read()
+    spread = []
+    for m in re.finditer(r"\{\s*(\w+):\s*([-\d.]+),\s*nonAllocated:\s*([-\d.]+),\s*expected:\s*([-\d.]+),\s*\}", src):
+        spread.append({"source": "pkg/scheduler/plugins/nodeplacement/nodespread_test.go", "count_field": m.group(1),
+                       "count": float(m.group(2)), "non_allocated": float(m.group(3)), "expected_score": float(m.group(4))})
+    out["spread"] = spread
+    with open(os.path.join(HERE, "nodeplacement.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return {k: len(v) for k, v in out.items()}
+
+
+def gen_resource_division():
+    """plugins/proportion/resource_division/resource_division_test.go — the `DescribeTable("two queues", ...)`
+    entries (setResourceShare on GPU with per-entry overrides) transcribed as data."""
+    src = open(os.path.join(REF, "plugins", "proportion", "resource_division", "resource_division_test.go")).read()
+    i = src.index('Context("two queues", func() {')
+    j = src.index('It("divides the remainder even when using priorities"', i)
+    block = src[i:j]
+    base = find_literals(block, "map[common_info.QueueID]*rs.QueueAttributes")[0]
+    if isinstance(base, list):  # `func() map[..]..{ return map[..]..{...} }` parses as [return, {...}]
+        base = [x for x in base if isinstance(x, dict) and "__ident" not in x][0]
+    entries = find_literals(block, "testMetadata")
+    cases = []
+    names = re.findall(r'Entry\("([^"]+)",\s*testMetadata', block)
+    for name, e in zip(names, entries):
+        queues = {}
+        for qid, q in base.items():
+            g = q["QueueResourceShare"]["GPU"]
+            queues[qid] = {"deserved": _num(g["Deserved"]), "fair_share": _num(g["FairShare"]),
+                           "oqw": _num(g["OverQuotaWeight"]), "max_allowed": _num(g["MaxAllowed"]),
+                           "allocated": _num(g["Allocated"]), "request": _num(g["Request"]), "priority": 0}
+        for qid, v in (e.get("maxAllowed") or {}).items():
+            queues[qid]["max_allowed"] = _num(v)
+        for qid, v in (e.get("gpuOverQuotaWeights") or {}).items():
+            queues[qid]["oqw"] = _num(v)
+        for qid, v in (e.get("request") or {}).items():
+            queues[qid]["request"] = _num(v)
+        for qid, v in (e.get("overQuotaPriority") or {}).items():
+            queues[qid]["priority"] = int(_num(v))
+        cases.append({
+            "source": "pkg/scheduler/plugins/proportion/resource_division/resource_division_test.go (two queues table)",
+            "name": name, "total": _num(e["totalGPUs"]), "k_value": 0.0, "queues": queues,
+            "expected_remaining": _num(e.get("expectedRemaining", 0)),
+            "expected_share": {k: _num(v) for k, v in (e.get("expectedShare") or {}).items()},
+        })
+    with open(os.path.join(HERE, "resource_division.json"), "w") as f:
+        json.dump(cases, f, indent=1, sort_keys=True)
+    return len(cases)
+
+
+if __name__ == "__main__":
+    print("nodeplacement:", gen_nodeplacement())
+    print("resource_division two-queues table:", gen_resource_division())

@@ -45,9 +45,10 @@ def tokenize(src: str):
 
 
 class Parser:
-    def __init__(self, toks):
+    def __init__(self, toks, force_types=()):
         self.t = toks
         self.i = 0
+        self.force_types = set(force_types)
 
     def peek(self, o=0):
         return self.t[self.i + o] if self.i + o < len(self.t) else ("eof", "")
@@ -114,6 +115,11 @@ class Parser:
         if v == "&":
             self.eat()
             return self.parse_value()
+        if v == "(":
+            self.eat()
+            inner = self.parse_value()
+            self.eat(")")
+            return self._binop(inner)
         if v == "{":
             return self.parse_literal(None)
         if v == "[" or v == "map" or v == "*":
@@ -146,7 +152,7 @@ class Parser:
             while self.peek()[1] == "." and self.peek(1)[0] == "id":
                 self.eat()
                 name += "." + self.eat()[1]
-            if self.peek()[1] == "{" and self._looks_like_type(name):
+            if self.peek()[1] == "{" and (self._looks_like_type(name) or name in self.force_types):
                 return self.parse_literal(name)
             if self.peek()[1] == "(":
                 return self._binop(self.parse_call(name))
@@ -288,7 +294,7 @@ def find_literals(src: str, type_name: str):
             i += 1
         text = src[start:i + 1]
         toks = tokenize(text)
-        p = Parser(toks)
+        p = Parser(toks, force_types=[type_name.split(']')[-1].lstrip('*')])
         out.append(p.parse_value())
         pos = i + 1
     return out
