@@ -231,12 +231,17 @@ int kai_engine_fair_share(kai_engine *e, kai_result *out);
 
 int kai_engine_stats(kai_engine *e, kai_stats *out);
 
-/* Multi-GPU wiring (one engine per process per GPU).  Each engine exports a
-   64-byte opaque handle of its exchange buffer; after an out-of-band
-   all-gather the full table is handed to every engine. */
+/* Multi-GPU wiring (one engine per process per GPU).  Shard s of
+   shard_count owns node rows kai_shard_range(N, S, s).  The reduced answer line of
+   every GPU lives in one shared host segment: rank 0 creates it and exports its
+   64-byte handle; after an out-of-band broadcast/all-gather (torch.distributed,
+   MPI, ...) every rank passes the handle table (entry 0 is read) to
+   kai_engine_wire_peers.  Results: task bindings / queue tables are identical on
+   all ranks; node tables are valid for the rank's own rows. */
 #define KAI_PEER_HANDLE_BYTES 64
 int kai_engine_export_peer_handle(kai_engine *e, uint8_t handle[KAI_PEER_HANDLE_BYTES]);
 int kai_engine_wire_peers(kai_engine *e, const uint8_t *handles /* [shard_count][64] */);
+int kai_shard_range(int n_nodes, int shard_count, int shard_rank, int *base, int *count);
 
 void kai_engine_destroy(kai_engine *e);
 const char *kai_last_error(const kai_engine *e);

@@ -7,9 +7,14 @@
 //
 // There is NO CPU fallback: without a usable CUDA device kai_engine_create fails.
 #include <algorithm>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <numeric>
 #include <type_traits>
 #include <string>
@@ -109,6 +114,13 @@ struct kai_engine {
   unsigned long long *h_pinned = nullptr;  // one pinned mapped allocation: rec | delta | slots | mm
   unsigned long long *h_rec = nullptr, *h_delta = nullptr, *h_slots = nullptr, *h_mm = nullptr;
   HostBackend hb;
+  // multi-GPU (one engine per process per GPU): the reduced answer lines of all GPUs live in one POSIX shm
+  // segment that every process maps and registers with CUDA; each host sequencer reads all lines.
+  unsigned long long *shm_base = nullptr;  // [slots | mm], each [2][kMaxGrid][kSlotWords]
+  size_t shm_bytes = 0;
+  char shm_name[48] = {0};
+  bool shm_owner = false, shm_registered = false;
+  unsigned long long *shm_dev = nullptr;  // device-side address of the registered segment
   DevSnap hs;  // DevSnap whose pointers address the host mirror (the pinned staging buffer)
   std::vector<unsigned char> hot_host;
   std::vector<int> rank_to_node_h;
@@ -206,6 +218,11 @@ void kai_engine_destroy(kai_engine *e) {
   e->stage.release();
   e->rstage.release();
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  if (e->shm_base) {
+    if (e->shm_registered) cudaHostUnregister(e->shm_base);
+    munmap(e->shm_base, e->shm_bytes);
+    if (e->shm_owner) shm_unlink(e->shm_name);
+  }
   for (auto &ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -612,8 +629,12 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     CK(cudaMemsetAsync(e->dbuf, 0, sizeof(unsigned long long) * 2 * kDecWords * 2, e->stream));
     CK(cudaMemsetAsync(e->xbuf, 0, xb, e->stream));
     CK(cudaMemsetAsync(e->mmbuf, 0, xb, e->stream));
-    e->seq = 2;
-    memset(e->h_pinned, 0, ((size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords) * 8);
+    // sequence numbers stay monotone across snapshots (tags of older cycles can never match); a rare full reset
+    // keeps the 24-bit slot tags unambiguous
+    if (e->seq > (1u << 22) && e->cfg.shard_count == 1) {
+      e->seq = 2;
+      memset(e->h_pinned, 0, ((size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords) * 8);
+    }
   }
 
   // ---------------- open session: totals, queue usage, fair share ----------------
@@ -713,7 +734,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (!e || !out) return KAI_ERR_INVALID;
   if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
   if (action != KAI_ACTION_ALLOCATE) return e->fail(KAI_ERR_UNSUPPORTED, "action not implemented on device yet");
-  if (e->cfg.shard_count != 1) return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU sharding not wired");
+  if (e->cfg.shard_count > 1 && !e->shm_base) return e->fail(KAI_ERR_STATE, "multi-GPU: call kai_engine_wire_peers first");
   CK(cudaSetDevice(e->device));
   ActionParams p;
   memset(&p, 0, sizeof(p));
@@ -722,8 +743,14 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   p.action = (int)action;
   p.grid = e->grid;
   p.nodes_per_cta = e->npc;
-  p.node_base = 0;
-  p.node_count = e->N;
+  {  // node rows of this shard: contiguous index range
+    const int S_ = e->cfg.shard_count, g_ = e->cfg.shard_rank;
+    long long b0 = (long long)e->N * g_ / S_, b1 = (long long)e->N * (g_ + 1) / S_;
+    p.node_base = (int)b0;
+    p.node_count = (int)(b1 - b0);
+    int npc_s = std::max(1, (p.node_count + (e->grid - 1) - 1) / (e->grid - 1));
+    p.nodes_per_cta = std::min(e->npc, (npc_s + 1) & ~1);
+  }
   p.dbuf = e->dbuf;
   p.delta = e->delta;
   p.ops_cap = e->ops_cap;
@@ -744,13 +771,17 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     return e->fail(KAI_ERR_CUDA, "action kernel cannot be made co-resident");
   const char *mode_env = getenv("KAI_SEQUENCER");
   const bool host_mode = !(mode_env && strcmp(mode_env, "device") == 0);
+  if (!host_mode && e->cfg.shard_count > 1) return e->fail(KAI_ERR_UNSUPPORTED, "device-resident sequencer is single-GPU");
   p.mode = host_mode ? 1 : 0;
   p.spin_log2 = host_mode ? 26 : 22;
   if (host_mode) {
     p.h_rec = e->h_rec;
     p.h_delta = e->h_delta;
-    p.h_slot = e->h_slots;  // one reduced answer line per GPU (this engine = GPU 0 of 1)
-    p.h_mmslot = e->h_mm;
+    // one reduced answer line per GPU; with several GPUs the lines live in the shared segment
+    unsigned long long *lines = e->cfg.shard_count > 1 ? e->shm_dev : e->h_slots;
+    unsigned long long *mm_lines = e->cfg.shard_count > 1 ? e->shm_dev + (size_t)2 * kMaxGrid * kSlotWords : e->h_mm;
+    p.h_slot = lines + (size_t)e->cfg.shard_rank * kSlotWords;
+    p.h_mmslot = mm_lines + (size_t)e->cfg.shard_rank * kSlotWords;
   }
   void *args[] = {(void *)&p};
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 48, e->stream));
@@ -775,9 +806,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     HostBackend &hb = e->hb;
     hb.h_rec = e->h_rec;
     hb.h_delta = e->h_delta;
-    hb.h_slots = e->h_slots;
-    hb.h_mm = e->h_mm;
-    hb.n_scanners = 1;  // the relay CTA reduces the scanners' answers on the GPU: one line per GPU
+    hb.h_slots = e->cfg.shard_count > 1 ? e->shm_base : e->h_slots;
+    hb.h_mm = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * kMaxGrid * kSlotWords : e->h_mm;
+    hb.n_scanners = e->cfg.shard_count;  // the relay CTA of every GPU reduces its scanners' answers: one line per GPU
     hb.batching = p.batching;
     hb.failed = false;
     hb.rank_to_node = e->rank_to_node_h.data();
@@ -933,13 +964,64 @@ int kai_engine_stats(kai_engine *e, kai_stats *out) {
   return KAI_OK;
 }
 
+// Multi-GPU wiring.  Rank 0 creates the shared segment and exports its name; every rank (rank 0 included)
+// passes the table of handles (only entry 0 is read) to kai_engine_wire_peers.
+static int shm_map(kai_engine *e, bool create) {
+  const size_t bytes = (size_t)2 * 2 * kMaxGrid * kSlotWords * 8;
+  int fd = shm_open(e->shm_name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+  if (fd < 0) return e->fail(KAI_ERR_INVALID, std::string("shm_open failed for ") + e->shm_name);
+  if (create && ftruncate(fd, (off_t)bytes) != 0) {
+    close(fd);
+    return e->fail(KAI_ERR_INVALID, "ftruncate failed");
+  }
+  void *ptr = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (ptr == MAP_FAILED) return e->fail(KAI_ERR_INVALID, "mmap failed");
+  if (create) memset(ptr, 0, bytes);
+  e->shm_base = (unsigned long long *)ptr;
+  e->shm_bytes = bytes;
+  return KAI_OK;
+}
+
 int kai_engine_export_peer_handle(kai_engine *e, uint8_t handle[KAI_PEER_HANDLE_BYTES]) {
   if (!e || !handle) return KAI_ERR_INVALID;
-  return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU sharding not wired");
+  memset(handle, 0, KAI_PEER_HANDLE_BYTES);
+  if (e->cfg.shard_rank != 0) return KAI_OK;  // only rank 0 owns the segment
+  if (!e->shm_base) {
+    snprintf(e->shm_name, sizeof(e->shm_name), "/kai_b200_%d_%llx", (int)getpid(),
+             (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count());
+    int rc = shm_map(e, true);
+    if (rc != KAI_OK) return rc;
+    e->shm_owner = true;
+  }
+  memcpy(handle, e->shm_name, std::min(sizeof(e->shm_name), (size_t)KAI_PEER_HANDLE_BYTES - 1));
+  return KAI_OK;
 }
+
 int kai_engine_wire_peers(kai_engine *e, const uint8_t *handles) {
   if (!e || !handles) return KAI_ERR_INVALID;
-  return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU sharding not wired");
+  if (e->cfg.shard_count <= 1) return KAI_OK;
+  if (!e->shm_base) {
+    memcpy(e->shm_name, handles, std::min(sizeof(e->shm_name) - 1, (size_t)KAI_PEER_HANDLE_BYTES));
+    if (e->shm_name[0] != '/') return e->fail(KAI_ERR_INVALID, "peer handle 0 does not carry a segment name");
+    int rc = shm_map(e, false);
+    if (rc != KAI_OK) return rc;
+  }
+  if (!e->shm_registered) {
+    CK(cudaSetDevice(e->device));
+    CK(cudaHostRegister(e->shm_base, e->shm_bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    CK(cudaHostGetDevicePointer((void **)&e->shm_dev, e->shm_base, 0));
+    e->shm_registered = true;
+  }
+  return KAI_OK;
+}
+
+int kai_shard_range(int n_nodes, int shard_count, int shard_rank, int *base, int *count) {
+  if (n_nodes < 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count || !base || !count) return KAI_ERR_INVALID;
+  long long b0 = (long long)n_nodes * shard_rank / shard_count, b1 = (long long)n_nodes * (shard_rank + 1) / shard_count;
+  *base = (int)b0;
+  *count = (int)(b1 - b0);
+  return KAI_OK;
 }
 
 }  // extern "C"

@@ -34,14 +34,24 @@ def lib() -> C.CDLL:
         _LIB.kai_engine_export_peer_handle.restype = C.c_int
         _LIB.kai_engine_wire_peers.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
         _LIB.kai_engine_wire_peers.restype = C.c_int
+        _LIB.kai_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _LIB.kai_shard_range.restype = C.c_int
     return _LIB
 
 
 EXPORTED_SYMBOLS = [
     "kai_engine_create", "kai_engine_load_snapshot", "kai_engine_run", "kai_engine_fair_share",
     "kai_engine_stats", "kai_engine_export_peer_handle", "kai_engine_wire_peers", "kai_engine_destroy",
-    "kai_last_error", "kai_abi_version",
+    "kai_last_error", "kai_abi_version", "kai_shard_range",
 ]
+
+
+def shard_range(n_nodes: int, shard_count: int, shard_rank: int):
+    b, c = C.c_int(), C.c_int()
+    rc = lib().kai_shard_range(n_nodes, shard_count, shard_rank, C.byref(b), C.byref(c))
+    if rc != 0:
+        raise EngineError(rc, "kai_shard_range")
+    return b.value, c.value
 
 
 class Engine:
@@ -85,6 +95,16 @@ class Engine:
         s = abi.KaiStats()
         self._check(self._lib.kai_engine_stats(self._h, C.byref(s)))
         return s
+
+    def export_peer_handle(self) -> bytes:
+        buf = (C.c_uint8 * abi.PEER_HANDLE_BYTES)()
+        self._check(self._lib.kai_engine_export_peer_handle(self._h, buf))
+        return bytes(buf)
+
+    def wire_peers(self, handles: list[bytes]):
+        raw = b"".join(h.ljust(abi.PEER_HANDLE_BYTES, b"\0")[:abi.PEER_HANDLE_BYTES] for h in handles)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._check(self._lib.kai_engine_wire_peers(self._h, buf))
 
     def close(self):
         if getattr(self, "_h", None):
