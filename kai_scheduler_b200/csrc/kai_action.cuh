@@ -306,36 +306,68 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
   unsigned long long rep_flags = 0;
   if (local.rank != kRankNone) {  // warp-uniform
     const int ln = local.ln, R = tl.R, n = tl.base + ln;
-    double I[KAI_MAX_RES], L[KAI_MAX_RES];
-    for (int r = 0; r < R; r++) {
-      I[r] = tl.I[r * tl.npc + ln];
-      L[r] = tl.L[r * tl.npc + ln];
+    // the row lives in registers: every index below is a compile-time constant after unrolling
+    double I[KAI_MAX_RES], L[KAI_MAX_RES], rq[KAI_MAX_RES];
+#pragma unroll
+    for (int r = 0; r < KAI_MAX_RES; r++) {
+      I[r] = r < R ? tl.I[r * tl.npc + ln] : 0.0;
+      L[r] = r < R ? tl.L[r * tl.npc + ln] : 0.0;
+      rq[r] = r < R ? d.req[r] : 0.0;
     }
     const double ag = tl.Agpu[ln], ac = tl.Acpu[ln], gc = tl.gpu_count[ln];
     const uint32_t nf = tl.flags[ln];
     bool fit_i0 = true;
-    for (int r = 0; r < R; r++) {
-      double rq = d.req[r];
-      if (r >= 3 ? (rq != 0 && rq > I[r]) : (rq > I[r])) fit_i0 = false;
-    }
+#pragma unroll
+    for (int r = 0; r < KAI_MAX_RES; r++)
+      if (r < R && (r >= 3 ? (rq[r] != 0 && rq[r] > I[r]) : (rq[r] > I[r]))) fit_i0 = false;
     const bool to_idle = !d.pipeline_only && (d.best_effort || fit_i0);  // common/allocate.go:165-174
     // state before placement `lane`: the row after `lane` placements (node_info.go:457-493), same f64 ops
     // in the same order as the sequential application
     const int me = lane <= kMaxRepeat ? lane : kMaxRepeat;
-    for (int k = 0; k < me; k++)
-      for (int r = 0; r < R; r++) {
+    for (int k = 0; k < me; k++) {
+#pragma unroll
+      for (int r = 0; r < KAI_MAX_RES; r++) {
         if (to_idle)
-          I[r] = __dsub_rn(I[r], d.req[r]);
+          I[r] = __dsub_rn(I[r], rq[r]);  // rq[r] = 0 beyond R: exact no-op
         else
-          L[r] = __dsub_rn(L[r], d.req[r]);
+          L[r] = __dsub_rn(L[r], rq[r]);
       }
+    }
     bool ok = true;  // placement `lane` is admissible as a repeat
     if (lane > 0) {
-      double sc;
-      bool fi;
-      if (!node_key(d, R, I, L, 1, ag, ac, gc, nf, n, sc, fi))
+      // FittingNode + NodeOrderFn on the register row (same operations as node_key)
+      bool fit_ri = true, fi = true;
+#pragma unroll
+      for (int r = 0; r < KAI_MAX_RES; r++) {
+        if (r >= R) continue;
+        double avail = __dadd_rn(I[r], L[r]);
+        if (r >= 3) {
+          if (rq[r] != 0 && rq[r] > avail) fit_ri = false;
+          if (rq[r] != 0 && rq[r] > I[r]) fi = false;
+        } else {
+          if (rq[r] > avail) fit_ri = false;
+          if (rq[r] > I[r]) fi = false;
+        }
+      }
+      if (!fit_ri)
         ok = false;
       else {
+        double sc = 0.0;
+        sc = __dadd_rn(sc, (d.best_effort || fi) ? 100.0 : 0.0);
+        sc = __dadd_rn(sc, 0.0);
+        bool cpu_only_node = !(nf & KAI_NODE_NOT_CPU_ONLY) && ag <= 0;
+        sc = __dadd_rn(sc, (!d.gpu_task && cpu_only_node) ? 10.0 : 0.0);
+        sc = __dadd_rn(sc, (d.nominated == n) ? 1000000.0 : 0.0);
+        double cur = d.res == KAI_RES_GPU ? __dadd_rn(I[KAI_RES_GPU], L[KAI_RES_GPU]) : __dadd_rn(I[KAI_RES_CPU], L[KAI_RES_CPU]);
+        double overall = d.res == KAI_RES_GPU ? ag : ac;
+        double place;
+        if (d.strategy == KAI_PLACEMENT_BINPACK) {
+          place = binpack_score(d.mn, d.mx, cur, overall);
+        } else {
+          double cnt = d.res == KAI_RES_GPU ? (double)(long long)gc : overall;
+          place = cnt == 0 ? 0.0 : __ddiv_rn(cur, cnt);
+        }
+        sc = __dadd_rn(sc, place);
         bool ti = !d.pipeline_only && (d.best_effort || fi);
         if (ti != to_idle) ok = false;
         if (!(sc >= local.score)) ok = false;  // node n must stay the argmax
@@ -343,13 +375,19 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
     }
     double b2[2] = {0, 0}, a2[2] = {0, 0};
     int has[2] = {0, 0};
-    for (int k = 0; k < 2; k++) {
-      int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
-      double overall = k == 0 ? ag : ac;
-      if (overall == 0 || d.req[res] == 0) continue;
-      has[k] = 1;
-      b2[k] = __dadd_rn(I[res], L[res]);
-      a2[k] = to_idle ? __dadd_rn(__dsub_rn(I[res], d.req[res]), L[res]) : __dadd_rn(I[res], __dsub_rn(L[res], d.req[res]));
+    {
+      const double Ig = I[KAI_RES_GPU], Lg = L[KAI_RES_GPU], Ic = I[KAI_RES_CPU], Lc = L[KAI_RES_CPU];
+      const double rg = rq[KAI_RES_GPU], rc = rq[KAI_RES_CPU];
+      if (ag != 0 && rg != 0) {
+        has[0] = 1;
+        b2[0] = __dadd_rn(Ig, Lg);
+        a2[0] = to_idle ? __dadd_rn(__dsub_rn(Ig, rg), Lg) : __dadd_rn(Ig, __dsub_rn(Lg, rg));
+      }
+      if (ac != 0 && rc != 0) {
+        has[1] = 1;
+        b2[1] = __dadd_rn(Ic, Lc);
+        a2[1] = to_idle ? __dadd_rn(__dsub_rn(Ic, rc), Lc) : __dadd_rn(Ic, __dsub_rn(Lc, rc));
+      }
     }
     // Tracker events of placement `lane`.  Within a batch min/max of both resources are constant (the batch
     // ends before any placement that would move them), so every lane can evaluate its events against the
