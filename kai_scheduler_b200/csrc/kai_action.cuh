@@ -227,8 +227,10 @@ __device__ __forceinline__ bool node_key(const Decision &d, int R, const double 
 }
 
 // The sweep over this CTA's tile followed by the block argmax on (score desc, name rank asc).
-__device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, Cand *sh_warp) {
+__device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, Cand *sh_warp,
+                          const int *excl = nullptr, int n_excl = 0, int *fit_count = nullptr) {
   Cand best;
+  int n_fit = 0;
   best.score = -1.0;
   best.rank = kRankNone;
   best.ln = -1;
@@ -241,12 +243,21 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
     if (!node_key(d, tl.R, tl.I + ln, tl.L + ln, tl.npc, tl.Agpu[ln], tl.Acpu[ln], tl.gpu_count[ln], tl.flags[ln], n,
                   score, fit_i))
       continue;
+    n_fit++;
+    bool skip = false;
+    for (int x = 0; x < n_excl; x++)
+      if (excl[x] == ln) skip = true;
+    if (skip) continue;
     uint32_t rk = (uint32_t)tl.rank[ln];
     if (better(score, rk, best.score, best.rank)) {
       best.score = score;
       best.rank = rk;
       best.ln = ln;
     }
+  }
+  if (fit_count) {
+    int w = __reduce_add_sync(0xffffffffu, n_fit);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(fit_count, w);
   }
   for (int o = 16; o > 0; o >>= 1) {
     double os = __shfl_down_sync(0xffffffffu, best.score, o);
@@ -296,8 +307,10 @@ constexpr int kSlotWords = 8;
 // (i = 0 is the swept placement, i >= 1 are candidate repeats on the same node); lane 0 then walks the
 // placements in order to simulate the min/max trackers and decides how many repeats it can vouch for.
 __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decision &d, Cand local,
-                                  unsigned long long *slot, unsigned int tag, int batching, bool sys) {
+                                  unsigned long long *slot, unsigned int tag, int batching, bool sys,
+                                  long long *dbg = nullptr) {
   const int lane = threadIdx.x & 31;
+  long long d0 = clock64(), d1 = d0, d2 = d0, d3 = d0;
   local.score = __shfl_sync(0xffffffffu, local.score, 0);
   local.rank = __shfl_sync(0xffffffffu, local.rank, 0);
   local.ln = __shfl_sync(0xffffffffu, local.ln, 0);
@@ -333,6 +346,7 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
           L[r] = __dsub_rn(L[r], rq[r]);
       }
     }
+    d1 = clock64();
     bool ok = true;  // placement `lane` is admissible as a repeat
     if (lane > 0) {
       // FittingNode + NodeOrderFn on the register row (same operations as node_key)
@@ -389,6 +403,7 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
         a2[1] = to_idle ? __dadd_rn(__dsub_rn(Ic, rc), Lc) : __dadd_rn(Ic, __dsub_rn(Lc, rc));
       }
     }
+    d2 = clock64();
     // Tracker events of placement `lane`.  Within a batch min/max of both resources are constant (the batch
     // ends before any placement that would move them), so every lane can evaluate its events against the
     // trackers of the record; only the "last node leaves the max" rule needs a prefix count.
@@ -441,8 +456,14 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
       rep_flags = ((unsigned long long)hi32 << 32) | lo32;
     }
     if (repeat) flags |= SLOT_HAS_REPEAT;
+    d3 = clock64();
   }
   if (lane != 0) return;
+  if (dbg) {
+    dbg[0] += d1 - d0;
+    dbg[1] += d2 - d1;
+    dbg[2] += d3 - d2;
+  }
   auto put = [&](unsigned long long *w, unsigned long long lo, unsigned long long hi2) {
     if (sys)
       st_relaxed_sys_b128(w, lo, hi2);  // slot lives in pinned host memory (host-sequenced mode)
@@ -457,6 +478,107 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
   put(slot, (unsigned long long)__double_as_longlong(local.score), hi);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// top-M answer (host-sequenced mode).  Warp w analyses candidate w: how many further identical pods the row can
+// take while staying at or above its own winning score in the same mode (repeat), and whether it is exhausted
+// afterwards (does not fit any more).  The host merges the lists of all scanners, simulates the min/max trackers
+// itself from the row values (same f64 operations) and consumes the list in key order.
+// ---------------------------------------------------------------------------------------------
+enum { LF_TO_IDLE = 1, LF_EXHAUSTED = 2, LF_MORE = 4, LF_HAS_GPU = 8, LF_HAS_CPU = 16 };
+__device__ void publish_list_candidate(const Tile &tl, const Decision &d, Cand c, bool more, unsigned long long *line0_word,
+                                       unsigned long long *payload_line, unsigned int tag) {
+  const int lane = threadIdx.x & 31;
+  uint32_t flags = more ? LF_MORE : 0u, repeat = 0;
+  double Ig0 = 0, Lg0 = 0, Ic0 = 0, Lc0 = 0;
+  if (c.rank != kRankNone) {  // warp-uniform
+    const int ln = c.ln, R = tl.R, n = tl.base + ln;
+    double I[KAI_MAX_RES], L[KAI_MAX_RES], rq[KAI_MAX_RES];
+#pragma unroll
+    for (int r = 0; r < KAI_MAX_RES; r++) {
+      I[r] = r < R ? tl.I[r * tl.npc + ln] : 0.0;
+      L[r] = r < R ? tl.L[r * tl.npc + ln] : 0.0;
+      rq[r] = r < R ? d.req[r] : 0.0;
+    }
+    Ig0 = I[KAI_RES_GPU];
+    Lg0 = L[KAI_RES_GPU];
+    Ic0 = I[KAI_RES_CPU];
+    Lc0 = L[KAI_RES_CPU];
+    const double ag = tl.Agpu[ln], ac = tl.Acpu[ln], gc = tl.gpu_count[ln];
+    const uint32_t nf = tl.flags[ln];
+    if (ag != 0 && rq[KAI_RES_GPU] != 0) flags |= LF_HAS_GPU;
+    if (ac != 0 && rq[KAI_RES_CPU] != 0) flags |= LF_HAS_CPU;
+    bool fit_i0 = true;
+#pragma unroll
+    for (int r = 0; r < KAI_MAX_RES; r++)
+      if (r < R && (r >= 3 ? (rq[r] != 0 && rq[r] > I[r]) : (rq[r] > I[r]))) fit_i0 = false;
+    const bool to_idle = !d.pipeline_only && (d.best_effort || fit_i0);
+    if (to_idle) flags |= LF_TO_IDLE;
+    const int me = lane <= kMaxRepeat + 1 ? lane : kMaxRepeat + 1;  // row after `me` placements
+    for (int k = 0; k < me; k++) {
+#pragma unroll
+      for (int r = 0; r < KAI_MAX_RES; r++) {
+        if (to_idle)
+          I[r] = __dsub_rn(I[r], rq[r]);
+        else
+          L[r] = __dsub_rn(L[r], rq[r]);
+      }
+    }
+    bool fit_ri = true, fi = true;
+#pragma unroll
+    for (int r = 0; r < KAI_MAX_RES; r++) {
+      if (r >= R) continue;
+      double avail = __dadd_rn(I[r], L[r]);
+      if (r >= 3) {
+        if (rq[r] != 0 && rq[r] > avail) fit_ri = false;
+        if (rq[r] != 0 && rq[r] > I[r]) fi = false;
+      } else {
+        if (rq[r] > avail) fit_ri = false;
+        if (rq[r] > I[r]) fi = false;
+      }
+    }
+    bool ok = fit_ri;
+    if (ok) {
+      double sc = 0.0;
+      sc = __dadd_rn(sc, (d.best_effort || fi) ? 100.0 : 0.0);
+      sc = __dadd_rn(sc, 0.0);
+      bool cpu_only_node = !(nf & KAI_NODE_NOT_CPU_ONLY) && ag <= 0;
+      sc = __dadd_rn(sc, (!d.gpu_task && cpu_only_node) ? 10.0 : 0.0);
+      sc = __dadd_rn(sc, (d.nominated == n) ? 1000000.0 : 0.0);
+      double cur = d.res == KAI_RES_GPU ? __dadd_rn(I[KAI_RES_GPU], L[KAI_RES_GPU]) : __dadd_rn(I[KAI_RES_CPU], L[KAI_RES_CPU]);
+      double overall = d.res == KAI_RES_GPU ? ag : ac;
+      double place;
+      if (d.strategy == KAI_PLACEMENT_BINPACK) {
+        place = binpack_score(d.mn, d.mx, cur, overall);
+      } else {
+        double cnt = d.res == KAI_RES_GPU ? (double)(long long)gc : overall;
+        place = cnt == 0 ? 0.0 : __ddiv_rn(cur, cnt);
+      }
+      sc = __dadd_rn(sc, place);
+      bool ti = !d.pipeline_only && (d.best_effort || fi);
+      if (ti != to_idle) ok = false;
+      if (!(sc >= c.score)) ok = false;
+    }
+    const unsigned ok_mask = __ballot_sync(0xffffffffu, ok);
+    const unsigned fit_mask = __ballot_sync(0xffffffffu, fit_ri);
+    int r_n = 0;
+    for (int i2 = 1; i2 <= kMaxRepeat; i2++) {
+      if (!((ok_mask >> i2) & 1u)) break;
+      r_n = i2;
+    }
+    repeat = (uint32_t)r_n;
+    if (!((fit_mask >> (r_n + 1)) & 1u)) flags |= LF_EXHAUSTED;  // after 1 + repeat placements the row no longer fits
+  }
+  if (lane == 0) {
+    st_relaxed_sys_b128(payload_line + 0, (unsigned long long)__double_as_longlong(Ig0), (unsigned long long)tag);
+    st_relaxed_sys_b128(payload_line + 2, (unsigned long long)__double_as_longlong(Lg0), (unsigned long long)tag);
+    st_relaxed_sys_b128(payload_line + 4, (unsigned long long)__double_as_longlong(Ic0), (unsigned long long)tag);
+    st_relaxed_sys_b128(payload_line + 6, (unsigned long long)__double_as_longlong(Lc0), (unsigned long long)tag);
+    unsigned long long hi = ((unsigned long long)tag << 40) | ((unsigned long long)(flags & 0xffu) << 32) |
+                            ((unsigned long long)(repeat & 0xffu) << 24) | (unsigned long long)(c.rank & 0xffffffu);
+    st_relaxed_sys_b128(line0_word, (unsigned long long)__double_as_longlong(c.score), hi);
+  }
+}
 
 // =============================================================================================
 // sequencer <-> scanner protocol
@@ -698,6 +820,9 @@ struct ScanShared {
   int kind, n_delta, batching;
   int2 delta[kMaxDelta];
   unsigned char mine[kMaxDelta];
+  int fit_count;
+  int excl[kTopM];
+  Cand cands[kTopM];
   double dreq[kMaxDelta][KAI_MAX_RES];
 };
 
@@ -841,11 +966,28 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     const int kind = sh.kind;
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
-    if (kind == DK_SCAN) {
+    if (kind == DK_SCAN && p.topm) {
+      // ---- top-M answer straight into host memory (no relay reduction) ----
+      if (tid == 0) sh.fit_count = 0;
+      __syncthreads();
+      for (int m = 0; m < kTopM; m++) {
+        Cand c = scan_tile(tile, sh.dec, s, sh_warp, sh.excl, m, m == 0 ? &sh.fit_count : nullptr);
+        if (tid == 0) {
+          sh.cands[m] = c;
+          sh.excl[m] = c.ln;
+        }
+        __syncthreads();
+      }
+      if (tid == 0) ts[4] += clock64() - c3;
+      unsigned long long *lines = p.h_list + ((size_t)(seq & 1) * kListScanners + (size_t)(p.scanner_base + my)) * kListLines * kListLineWords;
+      if (warp < kTopM)
+        publish_list_candidate(tile, sh.dec, sh.cands[warp], sh.fit_count > kTopM, lines + 2 * warp,
+                               lines + (size_t)(1 + warp) * kListLineWords, seq & 0xffffffu);
+    } else if (kind == DK_SCAN) {
       Cand local = scan_tile(tile, sh.dec, s, sh_warp);
       long long c4 = clock64();
       if (tid == 0) ts[4] += c4 - c3;
-      if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, false);
+      if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, false, my == 0 ? p.counters + 40 : nullptr);
     } else if (kind == DK_MINMAX) {
       double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
       for (int ln = tid; ln < tile.count; ln += blockDim.x)
@@ -1353,7 +1495,7 @@ __device__ void relay_main(const ActionParams &p) {
     __syncwarp();
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     long long tr1 = clock64();
-    relay_reduce(p, kind, seq);
+    if (!(p.topm && kind == DK_SCAN)) relay_reduce(p, kind, seq);
     long long tr2 = clock64();
     acc_fwd += tr1 - tr0;
     acc_red += tr2 - tr1;

@@ -21,6 +21,10 @@ constexpr int kMaxGrid = 1024;         // exchange slots per GPU
 constexpr uint32_t kNoRank = 0xFFFFFFFFu;
 constexpr int kDecWords = 16;         // tagged words of one decision record
 constexpr int kMaxDelta = 256;        // node deltas carried by one decision record
+constexpr int kTopM = 4;              // candidates every scanner returns per sweep (host-sequenced mode)
+constexpr int kListScanners = 2048;   // scanners of all GPUs of a box (list lines in host memory)
+constexpr int kListLineWords = 8;     // one 64-byte line = 4 tagged words
+constexpr int kListLines = 1 + kTopM; // line 0: the M candidate words, lines 1..M: row values of candidate m
 
 constexpr int kActiveUsed = KAI_POD_ALLOCATED | KAI_POD_PIPELINED | KAI_POD_BINDING | KAI_POD_BOUND |
                             KAI_POD_RUNNING | KAI_POD_RELEASING;
@@ -157,6 +161,9 @@ struct ActionParams {
   unsigned long long *h_rec, *h_delta;  // mode 1: decision record / delta words in pinned mapped host memory
   unsigned long long *h_slot, *h_mmslot;  // mode 1: this GPU's reduced answer line [2][kSlotWords] in (shared) host memory
   int spin_log2;        // watchdog: polls before a wait is declared dead
+  int topm;             // mode 1: scanners answer with their kTopM best rows (0 = single best through the relay)
+  unsigned long long *h_list;  // mode 1: [2][kListScanners][kListLines][kListLineWords] in (shared) host memory
+  int scanner_base;     // global index of this GPU's scanner 0 in h_list
 };
 
 }  // namespace kai

@@ -112,7 +112,7 @@ struct kai_engine {
   unsigned long long *delta = nullptr;
   // host-sequenced mode
   unsigned long long *h_pinned = nullptr;  // one pinned mapped allocation: rec | delta | slots | mm
-  unsigned long long *h_rec = nullptr, *h_delta = nullptr, *h_slots = nullptr, *h_mm = nullptr;
+  unsigned long long *h_rec = nullptr, *h_delta = nullptr, *h_slots = nullptr, *h_mm = nullptr, *h_list = nullptr;
   HostBackend hb;
   // multi-GPU (one engine per process per GPU): the reduced answer lines of all GPUs live in one POSIX shm
   // segment that every process maps and registers with CUDA; each host sequencer reads all lines.
@@ -193,7 +193,8 @@ int kai_engine_create(const kai_config *cfg, kai_engine **out) {
   for (auto &ev : e->ev) cudaEventCreate(&ev);
   cudaEventCreateWithFlags(&e->ev_mirror, cudaEventDisableTiming);
   {  // pinned, device-mapped protocol buffers of the host-sequenced mode
-    size_t words = (size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords;
+    const size_t list_words = (size_t)2 * kListScanners * kListLines * kListLineWords;
+    size_t words = (size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords + list_words;
     if (cudaHostAlloc((void **)&e->h_pinned, words * 8, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
       delete e;
       return KAI_ERR_CUDA;
@@ -203,6 +204,7 @@ int kai_engine_create(const kai_config *cfg, kai_engine **out) {
     e->h_delta = e->h_rec + (size_t)2 * kDecWords * 2;
     e->h_slots = e->h_delta + (size_t)2 * kMaxDelta * 2;
     e->h_mm = e->h_slots + (size_t)2 * kMaxGrid * kSlotWords;
+    e->h_list = e->h_mm + (size_t)2 * kMaxGrid * kSlotWords;
   }
   *out = e;
   return KAI_OK;
@@ -633,7 +635,8 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     // keeps the 24-bit slot tags unambiguous
     if (e->seq > (1u << 22) && e->cfg.shard_count == 1) {
       e->seq = 2;
-      memset(e->h_pinned, 0, ((size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords) * 8);
+      memset(e->h_pinned, 0, ((size_t)2 * kDecWords * 2 + (size_t)2 * kMaxDelta * 2 + (size_t)2 * 2 * kMaxGrid * kSlotWords +
+                              (size_t)2 * kListScanners * kListLines * kListLineWords) * 8);
     }
   }
 
@@ -782,6 +785,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     unsigned long long *mm_lines = e->cfg.shard_count > 1 ? e->shm_dev + (size_t)2 * kMaxGrid * kSlotWords : e->h_mm;
     p.h_slot = lines + (size_t)e->cfg.shard_rank * kSlotWords;
     p.h_mmslot = mm_lines + (size_t)e->cfg.shard_rank * kSlotWords;
+    p.topm = (p.batching && !getenv("KAI_NO_TOPM")) ? 1 : 0;
+    p.h_list = e->cfg.shard_count > 1 ? e->shm_dev + (size_t)2 * 2 * kMaxGrid * kSlotWords : e->h_list;
+    p.scanner_base = e->cfg.shard_rank * (e->grid - 1);
+    if ((long long)e->cfg.shard_count * (e->grid - 1) > kListScanners) p.topm = 0;
   }
   void *args[] = {(void *)&p};
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 48, e->stream));
@@ -809,6 +816,11 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.h_slots = e->cfg.shard_count > 1 ? e->shm_base : e->h_slots;
     hb.h_mm = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * kMaxGrid * kSlotWords : e->h_mm;
     hb.n_scanners = e->cfg.shard_count;  // the relay CTA of every GPU reduces its scanners' answers: one line per GPU
+    hb.topm = p.topm;
+    hb.h_list = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * 2 * kMaxGrid * kSlotWords : e->h_list;
+    hb.n_list_scanners = e->cfg.shard_count * (e->grid - 1);
+    hb.listed = 0;
+    hb.list_invalidate();
     hb.batching = p.batching;
     hb.failed = false;
     hb.rank_to_node = e->rank_to_node_h.data();
@@ -888,7 +900,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       long long cd[48];
       CK(cudaMemcpy(cd, e->counters, sizeof(cd), cudaMemcpyDeviceToHost));
       for (int i = 20; i < 28; i++) c[i] = cd[i];
-      for (int i = 32; i < 40; i++) c[i] = cd[i];
+      for (int i = 32; i < 44; i++) c[i] = cd[i];
     }
     c[0] = seq.n_visits;
     c[1] = seq.sweeps;
@@ -898,7 +910,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     c[5] = seq.minmax_exchanges;
     c[6] = seq.error;
     c[7] = ctl.seq + 1;
-    c[15] = seq.batched;
+    c[15] = seq.batched + hb.listed;
     if (hb.failed && c[24] == 0) c[24] = 99;
     // session state back to the device copies (later actions' prepare kernels and the result download read them)
     for (int i = 0; i < QR * Q; i++) {
@@ -946,6 +958,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     if (host_mode && c[38] > 0)
       fprintf(stderr, "[kai] scanner 0 per record (cycles): wait-for-record %lld (of which word-0 poll %lld), decode %lld, deltas %lld, scan %lld, scan+publish %lld\n",
               c[33] / c[38], c[32] / c[38], c[34] / c[38], c[35] / c[38], c[36] / c[38], c[37] / c[38]);
+    if (host_mode && c[38] > 0)
+      fprintf(stderr, "[kai] publish_candidate of scanner 0 (cycles per record): row+advance %lld, key %lld, events+pack %lld\n",
+              c[40] / c[38], c[41] / c[38], c[42] / c[38]);
   }
   if (c[24] != 0) {
     char msg[256];
@@ -967,7 +982,7 @@ int kai_engine_stats(kai_engine *e, kai_stats *out) {
 // Multi-GPU wiring.  Rank 0 creates the shared segment and exports its name; every rank (rank 0 included)
 // passes the table of handles (only entry 0 is read) to kai_engine_wire_peers.
 static int shm_map(kai_engine *e, bool create) {
-  const size_t bytes = (size_t)2 * 2 * kMaxGrid * kSlotWords * 8;
+  const size_t bytes = ((size_t)2 * 2 * kMaxGrid * kSlotWords + (size_t)2 * kListScanners * kListLines * kListLineWords) * 8;
   int fd = shm_open(e->shm_name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
   if (fd < 0) return e->fail(KAI_ERR_INVALID, std::string("shm_open failed for ") + e->shm_name);
   if (create && ftruncate(fd, (off_t)bytes) != 0) {

@@ -11,8 +11,10 @@
 // cycle (heap pops, DRF keys, statement log); a host core does the same in a few hundred ns.  The O(N)
 // work per allocateTask — the node sweep — stays on the GPU in both modes.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <vector>
 
 #include "kai_action.cuh"
 #include "kai_seq.cuh"
@@ -34,6 +36,21 @@ struct HostBackend {
   Seq seq;
   long long spins = 0;
   double t_exchange = 0, t_total = 0;  // seconds: waiting for the GPU / whole action
+  // ---- top-M candidate lists ----
+  unsigned long long *h_list = nullptr;  // [2][kListScanners][kListLines][kListLineWords]
+  int topm = 0;
+  int n_list_scanners = 0;  // scanners of all GPUs
+  struct ListCand {
+    double score;
+    uint32_t rank, flags;
+    int node, cap, used;
+    double Ig, Lg, Ic, Lc;
+    const unsigned long long *payload;
+    bool loaded;
+  };
+  std::vector<ListCand> list;
+  size_t list_pos = 0, list_valid = 0;
+  long long listed = 0;
 
   static double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -124,6 +141,134 @@ struct HostBackend {
     }
     ctl.seq = seq_no + 1;
     ctl.n_delta = 0;
+  }
+
+  // Gather the top-M answers of every scanner, merge them into one list in key order and mark the prefix that
+  // is provably the global order: entries strictly better than the last reported key of any scanner that has more
+  // fitting rows than it reported.
+  void gather_list() {
+    const unsigned int seq_no = ctl.seq;
+    const unsigned int tag = seq_no & 0xffffffu;
+    const unsigned long long *base = h_list + (size_t)(seq_no & 1) * kListScanners * kListLines * kListLineWords;
+    list.clear();
+    bool have_cut = false;
+    double cut_score = 0;
+    uint32_t cut_rank = 0;
+    for (int c = 0; c < n_list_scanners && !failed; c++) {
+      const unsigned long long *lines = base + (size_t)c * kListLines * kListLineWords;
+      bool more = false;
+      double last_score = 0;
+      uint32_t last_rank = kRankNone;
+      for (int m = 0; m < kTopM; m++) {
+        unsigned long long hi;
+        if (!wait_word(lines + 2 * m + 1, [&](unsigned long long v) { return (unsigned int)(v >> 40) == tag; }, hi)) break;
+        unsigned long long lo = __atomic_load_n(lines + 2 * m, __ATOMIC_RELAXED);
+        uint32_t rk = (uint32_t)(hi & 0xffffffu);
+        uint32_t fl = (uint32_t)((hi >> 32) & 0xffu);
+        if (fl & LF_MORE) more = true;
+        if (rk == kRankNone) continue;
+        ListCand lc;
+        memcpy(&lc.score, &lo, 8);
+        lc.rank = rk;
+        lc.flags = fl;
+        lc.node = rank_to_node[rk];
+        lc.cap = 1 + (int)((hi >> 24) & 0xffu);
+        lc.used = 0;
+        lc.payload = lines + (size_t)(1 + m) * kListLineWords;
+        lc.loaded = false;
+        lc.Ig = lc.Lg = lc.Ic = lc.Lc = 0;
+        list.push_back(lc);
+        last_score = lc.score;
+        last_rank = rk;
+      }
+      if (more && last_rank != kRankNone) {  // an unseen row of this scanner can be at most this good
+        if (!have_cut || last_score > cut_score || (last_score == cut_score && last_rank < cut_rank)) {
+          have_cut = true;
+          cut_score = last_score;
+          cut_rank = last_rank;
+        }
+      }
+    }
+    std::sort(list.begin(), list.end(), [](const ListCand &a, const ListCand &b) {
+      return a.score > b.score || (a.score == b.score && a.rank < b.rank);
+    });
+    list_valid = list.size();
+    if (have_cut)
+      for (size_t i = 0; i < list.size(); i++)
+        if (!(list[i].score > cut_score || (list[i].score == cut_score && list[i].rank <= cut_rank))) {
+          list_valid = i;
+          break;
+        }
+    // the cut row itself was reported (it IS the last reported row of that scanner): it may be used, rows after it not
+    list_pos = 0;
+    ctl.seq = seq_no + 1;
+    ctl.n_delta = 0;
+    ctl.batch.valid = 0;
+  }
+  bool list_available() const { return list_pos < list_valid && list[list_pos].used < list[list_pos].cap; }
+  void list_invalidate() {
+    list_pos = list_valid = 0;
+    list.clear();
+    ctl.batch.valid = 0;
+  }
+  // Place task t on the current list candidate (pack.go / node_info.go arithmetic restated on the reported row
+  // values), update the min/max trackers exactly and decide whether the list stays usable.
+  bool apply_listed(int t) {
+    if (!list_available()) return false;
+    ListCand &lc = list[list_pos];
+    const Decision &d = ctl.dec;
+    if (!lc.loaded) {
+      const unsigned int tag = (ctl.seq - 1) & 0xffffffu;
+      double *dst[4] = {&lc.Ig, &lc.Lg, &lc.Ic, &lc.Lc};
+      for (int w = 0; w < 4; w++) {
+        unsigned long long hi;
+        if (!wait_word(lc.payload + 2 * w + 1, [&](unsigned long long v) { return (unsigned int)v == tag; }, hi)) return false;
+        unsigned long long lo = __atomic_load_n(lc.payload + 2 * w, __ATOMIC_RELAXED);
+        memcpy(dst[w], &lo, 8);
+      }
+      lc.loaded = true;
+    }
+    const bool to_idle = (lc.flags & LF_TO_IDLE) != 0;
+    bool scored_moved = false;
+    for (int k = 0; k < 2; k++) {
+      if (!(lc.flags & (k == 0 ? LF_HAS_GPU : LF_HAS_CPU))) continue;
+      double &I = k == 0 ? lc.Ig : lc.Ic, &L = k == 0 ? lc.Lg : lc.Lc;
+      const double rq = d.req[k == 0 ? KAI_RES_GPU : KAI_RES_CPU];
+      const double b = kadd(I, L);
+      if (to_idle)
+        I = ksub(I, rq);
+      else
+        L = ksub(L, rq);
+      const double a = kadd(I, L);
+      Track &tr = ctl.trk[k];
+      if (tr.dirty) continue;
+      const Track before = tr;
+      uint32_t f = track_flags(tr, b, a);
+      if (f) track_decrease(tr, f, a);
+      const bool scored = (k == 0) == (d.res == KAI_RES_GPU);
+      if (scored && d.strategy == KAI_PLACEMENT_BINPACK && (tr.dirty || tr.mn != before.mn || tr.mx != before.mx))
+        scored_moved = true;
+    }
+    if (to_idle)
+      stmt_allocate(seq, t, lc.node, ctl.ctx_fresh != 0);
+    else
+      stmt_pipeline(seq, t, lc.node, ctl.ctx_fresh != 0);
+    lc.used++;
+    listed++;
+    ctl.item_ok = 1;
+    if (scored_moved) {  // every other key was computed under the old min/max
+      list_invalidate();
+      return true;
+    }
+    if (lc.used >= lc.cap) {
+      if (lc.flags & LF_EXHAUSTED)
+        list_pos++;  // the row no longer fits: the next entry is the reference's next pick
+      else
+        list_invalidate();  // the row could still take pods (cap / mode / score): sweep again
+    }
+    ctl.batch.valid = list_available() ? 1 : 0;
+    ctl.batch.left = 1;
+    return true;
   }
 
   void gather_minmax() {
@@ -230,8 +375,18 @@ struct HostBackend {
             break;
           }
           if (ctl.use_batch) {
-            seq_apply_batched(seq, t);
-            continue;
+            if (topm) {
+              if (apply_listed(t)) continue;
+              ctl.batch.valid = 0;  // list ran dry between prepare and apply: fall through to a sweep
+              ctl.use_batch = 0;
+              if (!seq_prepare_task(seq, t, job)) {
+                job_success = false;
+                break;
+              }
+            } else {
+              seq_apply_batched(seq, t);
+              continue;
+            }
           }
           if (ctl.need_minmax) {
             seq.minmax_exchanges++;
@@ -240,13 +395,23 @@ struct HostBackend {
           }
           double tx = now();
           publish(DK_SCAN);
-          gather_candidates();
+          if (topm)
+            gather_list();
+          else
+            gather_candidates();
           t_exchange += now() - tx;
           if (failed) {
             job_success = false;
             break;
           }
-          seq_apply_winner(seq, t);
+          if (topm) {
+            seq.sweeps++;
+            seq.nodes_scanned += s.N;
+            ctl.item_ok = 0;
+            if (list_available()) apply_listed(t);
+          } else {
+            seq_apply_winner(seq, t);
+          }
           if (!ctl.item_ok) {
             job_success = false;
             break;

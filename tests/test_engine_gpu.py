@@ -78,10 +78,11 @@ def test_synthetic_parity(kw):
     assert_same(re_, ro)
 
 
-@pytest.mark.parametrize("env", [("KAI_NO_BATCHING", "1"), ("KAI_NO_SMEM_HOT", "1"), ("KAI_SEQUENCER", "device")])
+@pytest.mark.parametrize("env", [("KAI_NO_BATCHING", "1"), ("KAI_NO_TOPM", "1"), ("KAI_NO_SMEM_HOT", "1"),
+                                 ("KAI_SEQUENCER", "device")])
 def test_synthetic_parity_fallback_paths(env, monkeypatch):
-    """Same answers with same-node batching off, with the sequencer's hot arrays in global memory, and with the
-    device-resident sequencer (CTA 0) instead of the host-sequenced default."""
+    """Same answers with batching off, with single-candidate answers (no top-M lists), with the sequencer's hot arrays
+    in global memory, and with the device-resident sequencer (CTA 0) instead of the host-sequenced default."""
     monkeypatch.setenv(env[0], env[1])
     for kw in (dict(n_nodes=300, n_jobs=400, tasks_per_job=4, n_queues=12),
                dict(n_nodes=257, n_jobs=600, tasks_per_job=3, n_queues=7, mixed=True)):
