@@ -158,7 +158,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    # N > 1: the node rows are sharded over the GPUs (rank r owns rows kai_shard_range(N, world, r)); every rank
+    # N > 1: the node rows are striped by name rank over the GPUs (kai_shard_range(N, world, r)); every rank
     # runs the same deterministic sequencer, one reduced answer line per GPU per sweep is exchanged through a
     # shared host segment.  Total work is fixed => strong scaling.
     eng = Engine(abi.make_config(device=local, shard_rank=rank, shard_count=world))

@@ -232,7 +232,9 @@ int kai_engine_fair_share(kai_engine *e, kai_result *out);
 int kai_engine_stats(kai_engine *e, kai_stats *out);
 
 /* Multi-GPU wiring (one engine per process per GPU).  Shard s of
-   shard_count owns node rows kai_shard_range(N, S, s).  The reduced answer line of
+   shard_count owns the nodes of name rank s, s + S, s + 2S, ... (kai_shard_range
+   returns first_rank = s and their count): consecutive ranks sit on different GPUs
+   and different scanners, so the best rows of a sweep come from many scanners.  The reduced answer line of
    every GPU lives in one shared host segment: rank 0 creates it and exports its
    64-byte handle; after an out-of-band broadcast/all-gather (torch.distributed,
    MPI, ...) every rank passes the handle table (entry 0 is read) to
@@ -241,7 +243,7 @@ int kai_engine_stats(kai_engine *e, kai_stats *out);
 #define KAI_PEER_HANDLE_BYTES 64
 int kai_engine_export_peer_handle(kai_engine *e, uint8_t handle[KAI_PEER_HANDLE_BYTES]);
 int kai_engine_wire_peers(kai_engine *e, const uint8_t *handles /* [shard_count][64] */);
-int kai_shard_range(int n_nodes, int shard_count, int shard_rank, int *base, int *count);
+int kai_shard_range(int n_nodes, int shard_count, int shard_rank, int *first_rank, int *count);
 
 void kai_engine_destroy(kai_engine *e);
 const char *kai_last_error(const kai_engine *e);

@@ -236,7 +236,7 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
   best.ln = -1;
   const uint32_t *mask = d.pred_class >= 0 ? s.pred_mask + (size_t)d.pred_class * s.mask_words : nullptr;
   for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
-    int n = tl.base + ln;
+    int n = tl.node[ln];
     if (mask && !((__ldg(&mask[n >> 5]) >> (n & 31)) & 1u)) continue;
     double score;
     bool fit_i;
@@ -318,7 +318,7 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
   double a_gpu = 0, a_cpu = 0;
   unsigned long long rep_flags = 0;
   if (local.rank != kRankNone) {  // warp-uniform
-    const int ln = local.ln, R = tl.R, n = tl.base + ln;
+    const int ln = local.ln, R = tl.R, n = tl.node[ln];
     // the row lives in registers: every index below is a compile-time constant after unrolling
     double I[KAI_MAX_RES], L[KAI_MAX_RES], rq[KAI_MAX_RES];
 #pragma unroll
@@ -492,7 +492,7 @@ __device__ void publish_list_candidate(const Tile &tl, const Decision &d, Cand c
   uint32_t flags = more ? LF_MORE : 0u, repeat = 0;
   double Ig0 = 0, Lg0 = 0, Ic0 = 0, Lc0 = 0;
   if (c.rank != kRankNone) {  // warp-uniform
-    const int ln = c.ln, R = tl.R, n = tl.base + ln;
+    const int ln = c.ln, R = tl.R, n = tl.node[ln];
     double I[KAI_MAX_RES], L[KAI_MAX_RES], rq[KAI_MAX_RES];
 #pragma unroll
     for (int r = 0; r < KAI_MAX_RES; r++) {
@@ -607,6 +607,7 @@ struct Spin {
 __device__ void seq_publish(const ActionParams &p, Ctl &ctl, int kind) {
   const int lane = threadIdx.x & 31;
   if (lane == 0) {
+    close_delta(ctl, p.delta);
     build_decision_words(ctl, kind, p.batching);  // deltas are self-validating tagged words: no fence
   }
   __syncwarp();
@@ -783,6 +784,7 @@ __device__ void seq_gather_minmax(const ActionParams &p, Ctl &ctl) {
 __device__ void dev_flush_deltas(Seq &q) {
   const ActionParams &p = *q.p;
   Ctl &c = *q.ctl;
+  close_delta(c, q.delta_base);
   build_decision_words(c, DK_FLUSH, 0);
   unsigned long long *rec = p.dbuf + (size_t)(c.seq & 1) * kDecWords * 2;
   for (int i = 0; i < kDecWords; i++) st_relaxed_b128(rec + 2 * i, c.dw[i], (unsigned long long)c.seq);
@@ -824,6 +826,7 @@ struct ScanShared {
   int excl[kTopM];
   Cand cands[kTopM];
   double dreq[kMaxDelta][KAI_MAX_RES];
+  int dln[kMaxDelta];
 };
 
 __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *sh_warp, double *sh_d, int *sh_i,
@@ -836,9 +839,14 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     unsigned char *ptr = smem;
     tile.npc = npc;
     tile.R = s.R;
-    tile.base = p.node_base + my * npc;
-    int end = min(p.node_base + p.node_count, tile.base + npc);
-    tile.count = max(0, end - tile.base);
+    tile.nscan = p.grid - 1;
+    tile.my = my;
+    tile.nshard = p.cfg.shard_count;
+    tile.shard = p.cfg.shard_rank;
+    {
+      long long first = (long long)my * tile.nshard + tile.shard, step = (long long)tile.nscan * tile.nshard;
+      tile.count = first < s.N ? (int)((s.N - first + step - 1) / step) : 0;
+    }
     tile.I = (double *)ptr;
     ptr += sizeof(double) * s.R * npc;
     tile.L = (double *)ptr;
@@ -852,10 +860,14 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     tile.rank = (int *)ptr;
     ptr += sizeof(int) * npc;
     tile.flags = (uint32_t *)ptr;
+    ptr += sizeof(uint32_t) * npc;
+    tile.node = (int *)ptr;
   }
   __syncthreads();
   for (int ln = tid; ln < tile.count; ln += blockDim.x) {
-    int n = tile.base + ln;
+    const int rk = tile_row_rank(tile, ln);
+    const int n = s.rank_to_node[rk];
+    tile.node[ln] = n;
     for (int r = 0; r < s.R; r++) {
       tile.I[r * tile.npc + ln] = s.idle[(size_t)r * s.N + n];
       tile.L[r * tile.npc + ln] = s.rel[(size_t)r * s.N + n];
@@ -863,7 +875,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     tile.Agpu[ln] = s.alloc[(size_t)KAI_RES_GPU * s.N + n];
     tile.Acpu[ln] = s.alloc[(size_t)KAI_RES_CPU * s.N + n];
     tile.gpu_count[ln] = s.gpu_count[n];
-    tile.rank[ln] = s.name_rank[n];
+    tile.rank[ln] = rk;
     tile.flags[ln] = s.nflags[n];
   }
   __syncthreads();
@@ -940,14 +952,14 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           Spin spin;
           do {
             ld_relaxed_b128(dl + 2 * e, lo, hi);
-          } while ((hi != (unsigned long long)seq) && !spin.expired(p, 9, (unsigned int)seq, (int)(e)));
+          } while (((unsigned int)hi != (unsigned int)seq) && !spin.expired(p, 9, (unsigned int)seq, (int)(e)));
         }
         int2 en = make_int2((int)(unsigned int)(lo & 0xffffffffu), (int)(unsigned int)(lo >> 32));
         sh.delta[e] = en;
-        int node = en.x & 0x0fffffff;
-        int ln = node - tile.base;
-        bool mine = ln >= 0 && ln < tile.count;
+        int ln = 0;
+        bool mine = tile_owns(tile, (unsigned int)(en.x & 0x0fffffff), ln) && ln < tile.count;
         sh.mine[e] = mine ? 1 : 0;
+        sh.dln[e] = ln | ((int)(hi >> 32) << 24);  // repeat count - 1 in the top byte
         if (mine)
           for (int r = 0; r < s.R; r++) sh.dreq[e][r] = __ldg(&s.t_req[(size_t)en.y * s.R + r]);
       }
@@ -956,8 +968,9 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         for (int e = 0; e < nd; e++) {
           if (!sh.mine[e]) continue;
           int2 en = sh.delta[e];
-          int ln = (en.x & 0x0fffffff) - tile.base;
-          apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], (en.x >> 28) & 7, sh.dreq[e][lane]);
+          const int ln = sh.dln[e] & 0xffffff, reps = ((unsigned int)sh.dln[e] >> 24) + 1;
+          for (int k = 0; k < reps; k++)
+            apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], (en.x >> 28) & 7, sh.dreq[e][lane]);
         }
       }
       __syncthreads();
@@ -1067,7 +1080,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     for (int i = 0; i < 7; i++) p.counters[32 + i] = ts[i];
   // ---- DONE: write the tile back to the session tables ----
   for (int ln = tid; ln < tile.count; ln += blockDim.x) {
-    int n = tile.base + ln;
+    int n = tile.node[ln];
     for (int r = 0; r < s.R; r++) {
       s.idle[(size_t)r * s.N + n] = tile.I[r * tile.npc + ln];
       s.rel[(size_t)r * s.N + n] = tile.L[r * tile.npc + ln];
@@ -1147,6 +1160,7 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     ctl.ctx_fresh = ctl.ctx_queue = ctl.ctx_preempt = ctl.ctx_base = 0;
     ctl.seq = p.seq0;
     ctl.n_delta = 0;
+    ctl.last_dcount = 0;
     ctl.stop = 0;
   }
   __syncthreads();
@@ -1482,17 +1496,18 @@ __device__ void relay_main(const ActionParams &p) {
     for (int e = lane - kDecWords; e < nd; e += 32) {
       if (e < 0) continue;
       unsigned long long dlo = lo, dhi = hi;
-      if (e >= 32 - kDecWords || dhi != (unsigned long long)seq) {
+      if (e >= 32 - kDecWords || (unsigned int)dhi != seq) {
         Spin sp2;
         do {
           ld_relaxed_sys_b128(hdl + 2 * e, dlo, dhi);
-        } while (dhi != (unsigned long long)seq && !sp2.expired(p, 11, seq, e));
+        } while ((unsigned int)dhi != seq && !sp2.expired(p, 11, seq, e));
       }
       st_relaxed_b128(ddl + 2 * e, dlo, dhi);
     }
     __syncwarp();
     if (lane < kDecWords) st_relaxed_b128(drec + 2 * lane, lo, hi);
     __syncwarp();
+    if (lane == 0) ((volatile long long *)p.counters)[23] = ((long long)kind << 32) | seq;  // last forwarded record
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     long long tr1 = clock64();
     if (!(p.topm && kind == DK_SCAN)) relay_reduce(p, kind, seq);

@@ -143,11 +143,9 @@ struct ActionParams {
   int action;
   int grid;             // CTAs of this GPU
   int nodes_per_cta;    // node rows per CTA (tile height)
-  int node_base;        // first node row of this GPU's shard
-  int node_count;       // node rows of this GPU's shard
   int ops_cap;
   unsigned long long *dbuf;  // decision record: [2][kDecWords] tagged 128-bit words (sequencer -> scanners)
-  unsigned long long *delta; // node delta list: [2][kMaxDelta] tagged words {node | code<<28 | task<<32, seq}
+  unsigned long long *delta; // node delta list: [2][kMaxDelta] tagged words {name_rank(node) | code<<28 | task<<32, seq}
   unsigned long long *xbuf;  // exchange slots: [2][kMaxGrid][8] u64 (tagged 128-bit words A, B, C, D)
   unsigned long long *mmbuf; // min/max exchange: [2][kMaxGrid][8] u64
   kai_job_visit *visits;     // [visits_cap]

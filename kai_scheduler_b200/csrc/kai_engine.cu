@@ -592,15 +592,16 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     int v = atoi(g);
     if (v >= 2) grid = std::min(v, grid);
   }
-  if (N > 0) grid = std::min(grid, N + 1);  // at least one node per scanner when possible
+  const int n_shard_rows = (N + e->cfg.shard_count - 1) / e->cfg.shard_count;  // rows of the largest shard
+  if (N > 0) grid = std::min(grid, n_shard_rows + 1);  // at least one node per scanner when possible
   grid = std::max(grid, 2);
   if (const char *g = getenv("KAI_GRID_EXACT")) {  // tests: force scanners without nodes as well
     int v = atoi(g);
     if (v >= 2) grid = std::min(std::min(v, e->num_sms), kMaxGrid);
   }
-  int npc = std::max(1, (N + (grid - 1) - 1) / (grid - 1));
+  int npc = std::max(1, (n_shard_rows + (grid - 1) - 1) / (grid - 1));
   npc = (npc + 1) & ~1;  // keep the int arrays 8-byte aligned
-  size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4), 16);
+  size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4), 16);
   const size_t smem_limit = (size_t)e->max_smem_optin - 24 * 1024;  // static shared memory of k_action
   if (tile_bytes > smem_limit)
     return e->fail(KAI_ERR_UNSUPPORTED, "node tile does not fit in shared memory (N too large for one GPU tile)");
@@ -746,14 +747,6 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   p.action = (int)action;
   p.grid = e->grid;
   p.nodes_per_cta = e->npc;
-  {  // node rows of this shard: contiguous index range
-    const int S_ = e->cfg.shard_count, g_ = e->cfg.shard_rank;
-    long long b0 = (long long)e->N * g_ / S_, b1 = (long long)e->N * (g_ + 1) / S_;
-    p.node_base = (int)b0;
-    p.node_count = (int)(b1 - b0);
-    int npc_s = std::max(1, (p.node_count + (e->grid - 1) - 1) / (e->grid - 1));
-    p.nodes_per_cta = std::min(e->npc, (npc_s + 1) & ~1);
-  }
   p.dbuf = e->dbuf;
   p.delta = e->delta;
   p.ops_cap = e->ops_cap;
@@ -967,7 +960,18 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     snprintf(msg, sizeof(msg), "device protocol watchdog: wait code %lld seq %lld who %lld cta %lld (seq0 %u, end seq %lld)",
              c[24], c[25], c[26], c[27], p.seq0, c[7]);
     e->loaded = false;
-    return e->fail(KAI_ERR_CUDA, msg);
+    std::string m2 = msg;
+    if (host_mode) {
+      char b2[96];
+      snprintf(b2, sizeof(b2), "; relay last forwarded kind %lld seq %lld; host trace:", c[23] >> 32, c[23] & 0xffffffff);
+      m2 += b2;
+      unsigned int n0 = e->hb.trace_n > 16 ? e->hb.trace_n - 16 : 0;
+      for (unsigned int i = n0; i < e->hb.trace_n; i++) {
+        snprintf(b2, sizeof(b2), " (%u k%d nd%d)", e->hb.trace_seq[i & 63], e->hb.trace_kind[i & 63], e->hb.trace_nd[i & 63]);
+        m2 += b2;
+      }
+    }
+    return e->fail(KAI_ERR_CUDA, m2);
   }
   if (c[6] != 0) return e->fail(KAI_ERR_CUDA, "device sequencer overflow (statement log)");
   return download(e, out, c[0], c[3], c[4]);
@@ -1031,11 +1035,11 @@ int kai_engine_wire_peers(kai_engine *e, const uint8_t *handles) {
   return KAI_OK;
 }
 
-int kai_shard_range(int n_nodes, int shard_count, int shard_rank, int *base, int *count) {
-  if (n_nodes < 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count || !base || !count) return KAI_ERR_INVALID;
-  long long b0 = (long long)n_nodes * shard_rank / shard_count, b1 = (long long)n_nodes * (shard_rank + 1) / shard_count;
-  *base = (int)b0;
-  *count = (int)(b1 - b0);
+int kai_shard_range(int n_nodes, int shard_count, int shard_rank, int *first_rank, int *count) {
+  if (n_nodes < 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count || !first_rank || !count) return KAI_ERR_INVALID;
+  // name-rank stripes: shard s owns the nodes of name rank s, s + S, s + 2S, ...
+  *first_rank = shard_rank;
+  *count = shard_rank < n_nodes ? (n_nodes - shard_rank + shard_count - 1) / shard_count : 0;
   return KAI_OK;
 }
 

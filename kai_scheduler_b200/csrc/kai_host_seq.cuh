@@ -78,7 +78,16 @@ struct HostBackend {
     }
   }
 
+  int trace_kind[64];
+  unsigned int trace_seq[64];
+  int trace_nd[64];
+  unsigned int trace_n = 0;
   void publish(int kind) {
+    trace_kind[trace_n & 63] = kind;
+    trace_seq[trace_n & 63] = ctl.seq;
+    trace_nd[trace_n & 63] = ctl.n_delta;
+    trace_n++;
+    close_delta(ctl, seq.delta_base);
     build_decision_words(ctl, kind, batching);
     unsigned long long *rec = h_rec + (size_t)(ctl.seq & 1) * kDecWords * 2;
     for (int i = kDecWords - 1; i >= 0; i--) store_tagged(rec + 2 * i, ctl.dw[i], (unsigned long long)ctl.seq);
@@ -201,10 +210,12 @@ struct HostBackend {
         }
     // the cut row itself was reported (it IS the last reported row of that scanner): it may be used, rows after it not
     list_pos = 0;
+    list_tag = tag;
     ctl.seq = seq_no + 1;
     ctl.n_delta = 0;
     ctl.batch.valid = 0;
   }
+  unsigned int list_tag = 0;
   bool list_available() const { return list_pos < list_valid && list[list_pos].used < list[list_pos].cap; }
   void list_invalidate() {
     list_pos = list_valid = 0;
@@ -218,7 +229,7 @@ struct HostBackend {
     ListCand &lc = list[list_pos];
     const Decision &d = ctl.dec;
     if (!lc.loaded) {
-      const unsigned int tag = (ctl.seq - 1) & 0xffffffu;
+      const unsigned int tag = list_tag;  // the sweep that produced the list (a FLUSH may have advanced ctl.seq since)
       double *dst[4] = {&lc.Ig, &lc.Lg, &lc.Ic, &lc.Lc};
       for (int w = 0; w < 4; w++) {
         unsigned long long hi;

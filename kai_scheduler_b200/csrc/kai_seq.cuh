@@ -142,6 +142,8 @@ struct Ctl {  // sequencer control block (shared memory of CTA 0), written by la
   int job, n_items, job_ok, item_ok, need_minmax, use_batch, stop;
   unsigned int seq;  // sequence number of the next decision record
   int n_delta;       // node deltas queued for the next record
+  unsigned int last_dkey;  // last queued delta: rank | code << 28, its first task and its repeat count
+  int last_dtask, last_dcount;
   Decision dec;
   Winner win;
   Track trk[2];  // 0 gpu, 1 cpu
@@ -158,8 +160,22 @@ struct Tile {  // shared-memory node tile of this CTA
   double *gpu_count;    // [npc]
   int *rank;            // [npc]
   uint32_t *flags;      // [npc]
-  int npc, base, count, R;
+  int *node;            // [npc] node index of the row
+  int npc, count, R;
+  // Rows are striped by NAME RANK over the GPUs of the box and over the scanners of a GPU: row j of scanner `my`
+  // of shard `shard` is the node of name rank (j * nscan + my) * nshard + shard.  Consecutive ranks land on
+  // different scanners, so the global top-K rows of a sweep come from ~K different scanners.
+  int nscan, my, nshard, shard;
 };
+KAI_HD inline int tile_row_rank(const Tile &tl, int ln) { return (ln * tl.nscan + tl.my) * tl.nshard + tl.shard; }
+KAI_HD inline bool tile_owns(const Tile &tl, unsigned int rank, int &ln) {
+  unsigned int q = rank / (unsigned int)tl.nshard;
+  if (rank - q * (unsigned int)tl.nshard != (unsigned int)tl.shard) return false;
+  unsigned int j = q / (unsigned int)tl.nscan;
+  if (q - j * (unsigned int)tl.nscan != (unsigned int)tl.my) return false;
+  ln = (int)j;
+  return true;
+}
 
 struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   const DevSnap *s;
@@ -219,12 +235,38 @@ KAI_HD inline bool should_allocate(const Seq &q, int t, bool real) {  // pod_inf
 // ---- node mutations (node_info.go:457-551) are queued as deltas for the scanner that owns the node ----
 enum { ND_ADD = 0, ND_ADD_PIPELINED = 1, ND_ADD_RELEASING = 2, ND_REM = 3, ND_REM_PIPELINED = 4, ND_REM_RELEASING = 5 };
 KAI_HD void seq_flush_deltas(Seq &q);  // FLUSH exchange when the delta list is full (backend specific)
+// Every delta word is written exactly once (readers validate it by its tag only): the newest entry stays pending in
+// the control block, so that consecutive deltas of the same kind on the same row with bit-identical requests can be
+// folded into it as a repeat count (tag word bits 32+; the owner applies the same subtraction `count` times, in
+// order).  close_delta() writes the pending entry; the backends call it before a record is published.
+KAI_HD void close_delta(Ctl &c, unsigned long long *delta_base) {
+  if (c.n_delta > 0 && c.last_dcount > 0) {
+    unsigned long long data = (unsigned long long)c.last_dkey | ((unsigned long long)(unsigned int)c.last_dtask << 32);
+    store_tagged(delta_base + ((size_t)(c.seq & 1) * kMaxDelta + c.n_delta - 1) * 2, data,
+                 (unsigned long long)c.seq | ((unsigned long long)(c.last_dcount - 1) << 32));
+  }
+  c.last_dcount = 0;
+}
 KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
+  // the delta names the node by its NAME RANK: that is what decides which scanner owns the row
+  const unsigned int key = (unsigned int)(kldg(&q.s->name_rank[node]) | (code << 28));
+  if (c.n_delta > 0 && c.last_dcount > 0 && c.last_dkey == key && c.last_dcount < 255) {
+    const int R = q.s->R;
+    const double *a = q.s->t_req + (size_t)c.last_dtask * R, *b = q.s->t_req + (size_t)t * R;
+    bool same = true;
+    for (int r = 0; r < R; r++) same = same && kbits(kldg(&a[r])) == kbits(kldg(&b[r]));
+    if (same) {
+      c.last_dcount++;
+      return;
+    }
+  }
+  close_delta(c, q.delta_base);
   if (c.n_delta >= kMaxDelta) seq_flush_deltas(q);
-  unsigned long long data = (unsigned long long)(unsigned int)(node | (code << 28)) | ((unsigned long long)(unsigned int)t << 32);
-  store_tagged(q.delta_base + ((size_t)(c.seq & 1) * kMaxDelta + c.n_delta) * 2, data, (unsigned long long)c.seq);
   c.n_delta++;
+  c.last_dkey = key;
+  c.last_dtask = t;
+  c.last_dcount = 1;
 }
 KAI_HD void node_add_task(Seq &q, int t, int n, int st) {  // n = task node, st = task status (just set)
   q.rp.t_node_status[t] = st;

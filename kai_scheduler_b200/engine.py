@@ -47,11 +47,18 @@ EXPORTED_SYMBOLS = [
 
 
 def shard_range(n_nodes: int, shard_count: int, shard_rank: int):
+    """(first_rank, count): shard `shard_rank` owns the nodes of NAME RANK first_rank + k * shard_count, k < count."""
     b, c = C.c_int(), C.c_int()
     rc = lib().kai_shard_range(n_nodes, shard_count, shard_rank, C.byref(b), C.byref(c))
     if rc != 0:
         raise EngineError(rc, "kai_shard_range")
     return b.value, c.value
+
+
+def shard_node_mask(node_name_rank, shard_count: int, shard_rank: int):
+    """Boolean mask over node indices: the rows whose idle/releasing tables engine `shard_rank` returns."""
+    import numpy as np
+    return (np.asarray(node_name_rank) % shard_count) == shard_rank
 
 
 class Engine:

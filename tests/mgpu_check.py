@@ -39,11 +39,13 @@ def main():
         o = Oracle()
         o.load(snap)
         ref = o.run("allocate")
-        base, count = engine.shard_range(snap.n_nodes, world, rank)
+        own = engine.shard_node_mask(snap.node_name_rank, world, rank)
+        first, count = engine.shard_range(snap.n_nodes, world, rank)
         same = (np.array_equal(res.task_node, ref.task_node) and np.array_equal(res.task_status, ref.task_status)
                 and np.array_equal(res.visits, ref.visits) and np.array_equal(res.queue_allocated, ref.queue_allocated)
-                and np.array_equal(res.node_idle[:, base:base + count], ref.node_idle[:, base:base + count])
-                and np.array_equal(res.node_releasing[:, base:base + count], ref.node_releasing[:, base:base + count]))
+                and first == rank and int(own.sum()) == count
+                and np.array_equal(res.node_idle[:, own], ref.node_idle[:, own])
+                and np.array_equal(res.node_releasing[:, own], ref.node_releasing[:, own]))
         print(f"rank {rank}/{world} {kw}: {'OK' if same else 'MISMATCH'} placed {res.pods_placed} sweeps {eng.stats().decisions}",
               flush=True)
         ok = ok and same

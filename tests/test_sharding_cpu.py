@@ -1,12 +1,13 @@
 """Host-side logic of the multi-GPU path, on CPU with gloo (world_size 2).
 
 The data path of the sharded mode needs GPUs; what is checked here is what does not: every rank derives the same
-disjoint, covering node ranges from kai_shard_range, and the peer-handle table travels through torch.distributed
+disjoint, covering name-rank stripes from kai_shard_range, and the peer-handle table travels through torch.distributed
 the way bench.py does it (rank 0 exports, broadcast, every rank receives the same bytes).
 """
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -48,10 +49,10 @@ def test_shard_ranges_agree_across_ranks(n_nodes):
         p.join(timeout=60)
         assert p.exitcode == 0
     got.sort()
-    # disjoint, covering, contiguous
-    assert got[0][1] == 0
-    assert got[0][1] + got[0][2] == got[1][1]
-    assert got[1][1] + got[1][2] == n_nodes
+    # name-rank stripes: shard r owns ranks r, r + world, ...: disjoint and covering
+    assert got[0][1] == 0 and got[1][1] == 1
+    assert got[0][2] + got[1][2] == n_nodes
+    assert got[0][2] == (n_nodes + 1) // 2
     # both ranks hold rank 0's handle
     assert got[0][3] == got[1][3] and got[0][3].startswith(b"/kai_b200_test_segment")
 
@@ -59,9 +60,12 @@ def test_shard_ranges_agree_across_ranks(n_nodes):
 def test_shard_range_many():
     for n in (0, 1, 7, 148, 50_000):
         for s in (1, 2, 4, 8):
-            nxt = 0
+            owned = np.zeros(n, dtype=np.int32)
             for r in range(s):
                 b, c = engine.shard_range(n, s, r)
-                assert b == nxt and c >= 0
-                nxt = b + c
-            assert nxt == n
+                assert b == r and c >= 0
+                owned[b::s][:c] += 1
+                assert len(owned[b::s]) == c
+                mask = engine.shard_node_mask(np.arange(n), s, r)
+                assert int(mask.sum()) == c
+            assert (owned == 1).all()
