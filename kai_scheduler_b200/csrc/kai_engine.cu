@@ -810,6 +810,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.h_mm = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * kMaxGrid * kSlotWords : e->h_mm;
     hb.n_scanners = e->cfg.shard_count;  // the relay CTA of every GPU reduces its scanners' answers: one line per GPU
     hb.topm = p.topm;
+    hb.prof = getenv("KAI_PROFILE") != nullptr;
+    for (int i = 0; i < 8; i++) hb.t_sec[i] = 0;
     hb.h_list = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * 2 * kMaxGrid * kSlotWords : e->h_list;
     hb.n_list_scanners = e->cfg.shard_count * (e->grid - 1);
     hb.listed = 0;
@@ -945,6 +947,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer: total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
               e->hb.t_total * 1e3, e->hb.t_exchange * 1e3, c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
+    if (host_mode)
+      fprintf(stderr, "[kai] host sequencer rdtsc Mcycles: pop %.2f admit %.2f place(+sweeps) %.2f finish %.2f loop %.2f\n",
+              e->hb.t_sec[0] / 1e6, e->hb.t_sec[1] / 1e6, e->hb.t_sec[2] / 1e6, e->hb.t_sec[3] / 1e6, e->hb.t_sec[4] / 1e6);
     if (host_mode && c[22] > 0)
       fprintf(stderr, "[kai] relay CTA per record: forward %lld cycles, scanners+reduce %lld cycles (%lld records)\n",
               c[20] / c[22], c[21] / c[22], c[22]);

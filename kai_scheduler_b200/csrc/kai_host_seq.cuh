@@ -78,6 +78,8 @@ struct HostBackend {
     }
   }
 
+  bool prof = false;
+  unsigned long long t_sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rdtsc: pop, admit, place (incl. sweeps), finish, loop
   int trace_kind[64];
   unsigned int trace_seq[64];
   int trace_nd[64];
@@ -346,8 +348,17 @@ struct HostBackend {
     double t_begin = now();
     t_exchange = 0;
     seq_init_job_order(seq);
+    unsigned long long tk = prof ? __builtin_ia32_rdtsc() : 0;
+    auto lap = [&](int i) {
+      if (!prof) return;
+      unsigned long long t = __builtin_ia32_rdtsc();
+      t_sec[i] += t - tk;
+      tk = t;
+    };
     for (;;) {
+      lap(4);
       int job = pop_next_job(seq);
+      lap(0);
       if (job < 0 || failed) break;
       seq.n_ops = 0;
       const JobRec rec = s.jrec[job];
@@ -378,6 +389,7 @@ struct HostBackend {
           for (int r = 0; r < QR; r++) req[r] = kadd(req[r], s.t_req[(size_t)seq.rp.tta[k] * s.R + r]);
       }
       bool job_success = !over_capacity(seq, job, req);
+      lap(1);
       if (job_success) {
         for (int k = 0; k < n; k++) {
           int t = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
@@ -429,6 +441,7 @@ struct HostBackend {
           }
         }
       }
+      lap(2);
       if (job_success) {
         if (should_pipeline_job(seq, job)) stmt_convert_all_allocated_to_pipelined(seq, job);
         stmt_commit(seq);
@@ -443,6 +456,7 @@ struct HostBackend {
       ctl.ctx_ps = -1;
       ctl.ctx_job = -1;
       ctl.ctx_fresh = 0;
+      lap(3);
       if (seq.error || failed) break;
     }
     publish(DK_DONE);  // carries the last node deltas; the scanners write their tiles back and exit
