@@ -360,22 +360,41 @@ struct Task {
   int job = -1, podset = -1, status = 0, node = -1, order_rank = 0, nominated = -1, pred_class = -1;
   double req[KAI_MAX_RES] = {0};
   bool is_virtual = false;  // PodInfo.IsVirtualStatus
-  int node_status = 0;      // status of the clone stored in NodeInfo.PodInfos (node_info.go:400-402)
-  bool on_node = false;
+  // NodeInfo.PodInfos holds a CLONE of the task per node (node_info.go:400-402).  A task evicted from node A and
+  // pipelined to node B in the same statement sits on both (Releasing on A, Pipelined on B): at most two entries.
+  int on_node[2] = {-1, -1};
+  int on_status[2] = {0, 0};
+  int find_on(int n) const { return on_node[0] == n ? 0 : (on_node[1] == n ? 1 : -1); }
 };
 struct PodSet {
   int job = -1, min_available = 0;
   std::vector<int> tasks;
 };
-struct Job {
-  int queue = -1, priority = 0, order_rank = 0;
-  bool preemptible = false;
-  std::vector<int> podsets;
-  // inner caches (job_info.go:98-101; invalidated on any status change :281-284)
+// inner caches of a PodGroupInfo (job_info.go:98-101; invalidated on any status change :281-284)
+struct TtaCache {
   bool tta_valid = false;
   std::vector<int> tta;
   bool tta_res_valid = false;
   double tta_res[QR] = {0, 0, 0};
+};
+struct Job {
+  int queue = -1, priority = 0, order_rank = 0;
+  bool preemptible = false;
+  int signature = -1;  // GetSchedulingConstraintsSignature class (job_info.go:547-570); -1 = unique
+  std::vector<int> podsets;
+  TtaCache cache;
+};
+// PodGroupInfo.CloneWithTasks (job_info.go:477-510): a clone owns copies of the PodSets, so its per-podset counters,
+// its PodStatusIndex, its Allocated sum and its inner caches are FROZEN at clone time (statement operations update
+// the session's job, found by UID, never the clone), while the PodInfo objects it holds are the ones the statement
+// mutates, so task statuses read through a clone are live.  Views with id < NJ are the session's jobs themselves.
+struct View {
+  int job = -1;
+  std::vector<std::vector<int>> ps_tasks;  // members per podset (index = position in Job::podsets)
+  std::vector<int> ps_min, ps_active_alloc, ps_active_used;
+  int active_alloc_total = 0, n_pending = 0;
+  double allocated[QR] = {0, 0, 0};
+  TtaCache cache;
 };
 
 struct Op {  // framework/statement.go operations
@@ -411,6 +430,7 @@ struct kai_oracle {
   std::vector<uint32_t> pred_mask;
   double total[QR] = {0, 0, 0};
   bool loaded = false;
+  bool use_signatures = false;  // SchedulerParams.UseSchedulingSignatures (options.go:120; tests: false)
   int n_threads = 1;
 
   // results
@@ -472,8 +492,12 @@ struct kai_oracle {
   void node_add_task(int ti) {
     Task &t = T[ti];
     int n = t.node;
-    t.node_status = t.status;
-    t.on_node = true;
+    {
+      int e = t.find_on(n);
+      if (e < 0) e = t.on_node[0] < 0 ? 0 : 1;
+      t.on_node[e] = n;
+      t.on_status[e] = t.status;
+    }
     for (int r = 0; r < R; r++) {
       switch (t.status) {
         case KAI_POD_RELEASING:
@@ -492,7 +516,7 @@ struct kai_oracle {
   void node_remove_task(int ti, int n) {
     Task &t = T[ti];
     for (int r = 0; r < R; r++) {
-      switch (t.node_status) {
+      switch (t.on_status[t.find_on(n) < 0 ? 0 : t.find_on(n)]) {
         case KAI_POD_RELEASING:
           L(r, n) -= t.req[r];
           I(r, n) += t.req[r];
@@ -504,15 +528,83 @@ struct kai_oracle {
           I(r, n) += t.req[r];
       }
     }
-    t.on_node = false;
+    {
+      int e = t.find_on(n);
+      if (e >= 0) t.on_node[e] = -1;
+    }
   }
 
   // ---------------- PodGroupInfo ----------------
   void set_status(int ti, int status) {  // job_info.go:253-264 UpdateTaskStatus
     Task &t = T[ti];
     t.status = status;
-    J[t.job].tta_valid = false;
-    J[t.job].tta_res_valid = false;
+    J[t.job].cache.tta_valid = false;
+    J[t.job].cache.tta_res_valid = false;
+  }
+  // ---------------- views (see struct View) ----------------
+  std::vector<View> views;
+  bool is_clone(int v) const { return v >= NJ; }
+  int vjob(int v) const { return v < NJ ? v : views[v - NJ].job; }
+  TtaCache &vcache(int v) { return v < NJ ? J[v].cache : views[v - NJ].cache; }
+  int v_nps(int v) const { return (int)J[vjob(v)].podsets.size(); }
+  int v_min(int v, int k) const { return v < NJ ? PS[J[v].podsets[k]].min_available : views[v - NJ].ps_min[k]; }
+  int v_active_alloc(int v, int k) const {
+    return v < NJ ? podset_count(PS[J[v].podsets[k]], kActiveAllocated) : views[v - NJ].ps_active_alloc[k];
+  }
+  int v_active_used(int v, int k) const {
+    return v < NJ ? podset_count(PS[J[v].podsets[k]], kActiveUsed) : views[v - NJ].ps_active_used[k];
+  }
+  const std::vector<int> &v_ps_tasks(int v, int k) const {
+    return v < NJ ? PS[J[v].podsets[k]].tasks : views[v - NJ].ps_tasks[k];
+  }
+  std::vector<int> v_all_tasks(int v) const {  // GetAllPodsMap: canonical order = podset, then task index
+    std::vector<int> out;
+    for (int k = 0; k < v_nps(v); k++)
+      for (int ti : v_ps_tasks(v, k)) out.push_back(ti);
+    return out;
+  }
+  int v_active_alloc_total(int v) const {  // GetActiveAllocatedTasksCount (job_info.go:286-297)
+    if (v >= NJ) return views[v - NJ].active_alloc_total;
+    return job_count(J[v], kActiveAllocated);
+  }
+  int v_pending_count(int v) const { return v < NJ ? job_count(J[v], KAI_POD_PENDING) : views[v - NJ].n_pending; }
+  void v_allocated(int v, double *out) const {  // PodGroupInfo.Allocated (job_info.go:245-250), cpu/mem/gpu
+    if (v >= NJ) {
+      for (int r = 0; r < QR; r++) out[r] += views[v - NJ].allocated[r];
+      return;
+    }
+    for (int s2 : J[v].podsets)
+      for (int ti : PS[s2].tasks)
+        if (T[ti].status & kAllocatedStatuses)
+          for (int r = 0; r < QR; r++) out[r] += T[ti].req[r];
+  }
+  // CloneWithTasks(tasks) of view `base` (the RootSubGroupSet clone keeps base's minAvailable values)
+  int make_clone(int base, const std::vector<int> &tasks) {
+    View c;
+    c.job = vjob(base);
+    const Job &j = J[c.job];
+    int n = (int)j.podsets.size();
+    c.ps_tasks.assign(n, {});
+    c.ps_min.resize(n);
+    c.ps_active_alloc.assign(n, 0);
+    c.ps_active_used.assign(n, 0);
+    for (int k = 0; k < n; k++) c.ps_min[k] = v_min(base, k);
+    for (int ti : tasks) {
+      int k = 0;
+      while (j.podsets[k] != T[ti].podset) k++;
+      c.ps_tasks[k].push_back(ti);
+      if (T[ti].status & kActiveAllocated) {
+        c.ps_active_alloc[k]++;
+        c.active_alloc_total++;
+      }
+      if (T[ti].status & kActiveUsed) c.ps_active_used[k]++;
+      if (T[ti].status == KAI_POD_PENDING) c.n_pending++;
+      if (T[ti].status & kAllocatedStatuses)
+        for (int r = 0; r < QR; r++) c.allocated[r] += T[ti].req[r];
+    }
+    for (auto &v : c.ps_tasks) std::sort(v.begin(), v.end());
+    views.push_back(c);
+    return NJ + (int)views.size() - 1;
   }
   int podset_count(const PodSet &ps, int mask) const {
     int c = 0;
@@ -536,65 +628,99 @@ struct kai_oracle {
   }
 
   // plugins/subgrouporder/subgroup_order.go:31-62 + framework/session_plugins.go:261-270 (name order = index order)
-  bool podset_less(int a, int b) const {
-    const PodSet &l = PS[a], &r = PS[b];
-    int ln = podset_count(l, kActiveAllocated), rn = podset_count(r, kActiveAllocated);
-    bool lsat = ln >= l.min_available, rsat = rn >= r.min_available;
-    if (!lsat && !rsat) return a < b;
+  bool podset_less_v(int v, int ka, int kb) const {
+    int ln = v_active_alloc(v, ka), rn = v_active_alloc(v, kb);
+    int lmin = v_min(v, ka), rmin = v_min(v, kb);
+    bool lsat = ln >= lmin, rsat = rn >= rmin;
+    if (!lsat && !rsat) return ka < kb;
     if (!lsat) return true;
     if (!rsat) return false;
-    double lr = (double)ln / (double)l.min_available;
-    double rr = (double)rn / (double)r.min_available;
+    double lr = (double)ln / (double)lmin;
+    double rr = (double)rn / (double)rmin;
     if (lr < rr) return true;
     if (rr < lr) return false;
-    return a < b;
+    return ka < kb;
+  }
+  std::vector<int> ordered_podsets(int v) const {  // positions in Job::podsets, PodSetOrderFn order
+    std::vector<int> sets(v_nps(v));
+    for (int k = 0; k < (int)sets.size(); k++) sets[k] = k;
+    std::sort(sets.begin(), sets.end(), [&](int a, int b) { return podset_less_v(v, a, b); });
+    return sets;
   }
 
   // api/podgroup_info/allocation_info.go:27-54 GetTasksToAllocate
-  const std::vector<int> &tasks_to_allocate(int ji, bool real) {
-    Job &j = J[ji];
-    if (j.tta_valid) return j.tta;
+  const std::vector<int> &tasks_to_allocate(int v, bool real) {
+    TtaCache &c = vcache(v);
+    if (c.tta_valid) return c.tta;
     std::vector<int> out;
-    std::vector<int> sets = j.podsets;
-    std::sort(sets.begin(), sets.end(), [&](int a, int b) { return podset_less(a, b); });
+    std::vector<int> sets = ordered_podsets(v);
     // :165-177 getMaxNumSubGroupsToAllocate
     int unsat = 0;
-    for (int s : j.podsets)
-      if (podset_count(PS[s], kActiveAllocated) < PS[s].min_available) unsat++;
+    for (int k = 0; k < v_nps(v); k++)
+      if (v_active_alloc(v, k) < v_min(v, k)) unsat++;
     int max_sets = unsat > 0 ? unsat : 1;
     int n_sets = 0;
-    for (size_t k = 0; k < sets.size() && n_sets < max_sets; k++) {
-      const PodSet &ps = PS[sets[k]];
+    for (size_t i = 0; i < sets.size() && n_sets < max_sets; i++) {
+      int k = sets[i];
       std::vector<int> cand;
-      for (int ti : ps.tasks)
+      for (int ti : v_ps_tasks(v, k))
         if (should_allocate(T[ti], real)) cand.push_back(ti);
       if (cand.empty()) continue;
       std::sort(cand.begin(), cand.end(), [&](int a, int b) { return T[a].order_rank < T[b].order_rank; });
       // :144-153 getNumTasksToAllocate
-      int n_alloc = podset_count(ps, kActiveAllocated);
+      int n_alloc = v_active_alloc(v, k);
       int max_tasks;
-      if (n_alloc >= ps.min_available)
+      if (n_alloc >= v_min(v, k))
         max_tasks = std::min((int)cand.size(), 1);
       else
-        max_tasks = ps.min_available - n_alloc;
+        max_tasks = v_min(v, k) - n_alloc;
       for (int k2 = 0; k2 < (int)cand.size() && k2 < max_tasks; k2++) out.push_back(cand[k2]);
       n_sets++;
     }
-    j.tta = out;
-    j.tta_valid = true;
-    return j.tta;
+    TtaCache &c2 = vcache(v);
+    c2.tta = out;
+    c2.tta_valid = true;
+    return c2.tta;
   }
   // allocation_info.go:87-113 GetTasksToAllocateInitResource, quantified (proportion/utils/utils.go:11-13)
-  const double *tasks_to_allocate_init_resource(int ji, bool real) {
-    Job &j = J[ji];
-    if (j.tta_res_valid) return j.tta_res;
+  const double *tasks_to_allocate_init_resource(int v, bool real) {
+    if (vcache(v).tta_res_valid) return vcache(v).tta_res;
     double acc[QR] = {0, 0, 0};
-    for (int ti : tasks_to_allocate(ji, real))
+    std::vector<int> tta = tasks_to_allocate(v, real);
+    for (int ti : tta)
       if (should_allocate(T[ti], real))
         for (int r = 0; r < QR; r++) acc[r] += T[ti].req[r];
-    for (int r = 0; r < QR; r++) j.tta_res[r] = acc[r];
-    j.tta_res_valid = true;
-    return j.tta_res;
+    TtaCache &c = vcache(v);
+    for (int r = 0; r < QR; r++) c.tta_res[r] = acc[r];
+    c.tta_res_valid = true;
+    return c.tta_res;
+  }
+  // api/podgroup_info/eviction_info.go:13-90 GetTasksToEvict: reverse podset order, reverse task order
+  std::vector<int> tasks_to_evict(int v, bool &has_more) {
+    std::vector<int> sets(v_nps(v));
+    for (int k = 0; k < (int)sets.size(); k++) sets[k] = k;
+    std::sort(sets.begin(), sets.end(), [&](int a, int b) { return podset_less_v(v, b, a); });
+    int max_sets = (int)sets.size();  // :49-60 getNumOfSubGroupsToEvict
+    for (int k = 0; k < v_nps(v); k++)
+      if (v_active_alloc(v, k) > v_min(v, k)) {
+        max_sets = 1;
+        break;
+      }
+    std::vector<int> out;
+    int n_sets = 0;
+    for (size_t i = 0; i < sets.size() && n_sets < max_sets; i++) {
+      int k = sets[i];
+      std::vector<int> cand;
+      for (int ti : v_ps_tasks(v, k))
+        if (T[ti].status & kActiveAllocated) cand.push_back(ti);
+      std::sort(cand.begin(), cand.end(), [&](int a, int b) { return T[a].order_rank > T[b].order_rank; });
+      int n_alloc = v_active_alloc(v, k);  // :62-68 getMaxTasksToEvict
+      int max_tasks = n_alloc > v_min(v, k) ? 1 : n_alloc;
+      for (int k2 = 0; k2 < (int)cand.size() && k2 < max_tasks; k2++) out.push_back(cand[k2]);
+      n_sets++;
+    }
+    has_more = (int)out.size() < v_active_alloc_total(v);
+    return out;
   }
   bool has_tasks_to_allocate(int ji, bool real) const {  // allocation_info.go:18-25
     for (int s : J[ji].podsets)
@@ -725,7 +851,7 @@ struct kai_oracle {
   // :197-295 Pipeline
   void stmt_pipeline(int ti, int n, bool update_if_exists) {
     Task &t = T[ti];
-    bool found_on_node = t.on_node && t.node == n;
+    bool found_on_node = t.find_on(n) >= 0;
     if (found_on_node && !update_if_exists) {
       stmt_unevict(ti);
       return;
@@ -782,8 +908,13 @@ struct kai_oracle {
     Task &t = T[op.task];
     set_status(op.task, op.prev_status);
     t.is_virtual = op.prev_virtual;
-    node_remove_task(op.task, t.node);  // UpdateTask on previous node
-    node_add_task(op.task);
+    {  // UpdateTask on the node the task was evicted from
+      int keep = t.node;
+      t.node = op.prev_node;
+      node_remove_task(op.task, op.prev_node);
+      node_add_task(op.task);
+      t.node = keep;
+    }
     queue_allocate(op.task, +1);
   }
   // :652-663 operationValid
@@ -875,8 +1006,8 @@ struct kai_oracle {
       const Op &op = ops[i];
       if (op.kind == Op::ALLOCATE) {
         T[op.task].status = KAI_POD_BINDING;  // updatePodOnSession: node clone keeps accounting (default branch)
-        T[op.task].node_status = KAI_POD_BINDING;
-        J[T[op.task].job].tta_valid = J[T[op.task].job].tta_res_valid = false;
+        if (T[op.task].find_on(T[op.task].node) >= 0) T[op.task].on_status[T[op.task].find_on(T[op.task].node)] = KAI_POD_BINDING;
+        J[T[op.task].job].cache.tta_valid = J[T[op.task].job].cache.tta_res_valid = false;
         pods_placed++;
       } else if (op.kind == Op::PIPELINE) {
         pods_placed++;
@@ -1032,6 +1163,7 @@ struct kai_oracle {
     double req[QR] = {t.req[KAI_RES_CPU], t.req[KAI_RES_MEM], task_requires_gpu(t) ? 1.0 : 0.0};
     if (over_capacity(t.job, req)) return false;
     int n = pick_node(ti, node_set);
+    if (getenv("KAI_ORACLE_TRACE")) fprintf(stderr, "[solver]       task %d -> node %d (pipeline_only %d)\n", ti, n, (int)pipeline_only);
     if (n < 0) return false;
     if (!pipeline_only && is_task_allocatable(t, n))
       stmt_allocate(ti, n);
@@ -1040,17 +1172,19 @@ struct kai_oracle {
     return true;
   }
   // :20-119 AllocateJob (flat root SubGroupSet; topology subsetting = single node set)
-  bool allocate_job(int ji, const std::vector<int> *node_set, bool pipeline_only) {
-    std::vector<int> tta = tasks_to_allocate(ji, !pipeline_only);
+  // `v` is a view: the session's job or a clone (partial job representative of the solver)
+  bool allocate_job(int v, const std::vector<int> *node_set, bool pipeline_only) {
+    std::vector<int> tta = tasks_to_allocate(v, !pipeline_only);
+    const int ji = vjob(v);
     // capacity_policy.go:26-36 IsJobOverQueueCapacity
     double req[QR] = {0, 0, 0};
     for (int ti : tta)
       for (int r = 0; r < QR; r++) req[r] += T[ti].req[r];
     if (over_capacity(ji, req)) return false;
     int cp = stmt_checkpoint();
-    std::vector<int> sets = J[ji].podsets;
-    std::sort(sets.begin(), sets.end(), [&](int a, int b) { return podset_less(a, b); });
-    for (int s : sets) {
+    std::vector<int> sets = ordered_podsets(v);
+    for (int k : sets) {
+      const int s = J[ji].podsets[k];
       int cp2 = stmt_checkpoint();
       bool ok = true;
       for (int ti : tta) {
@@ -1095,24 +1229,24 @@ struct kai_oracle {
     std::vector<std::vector<int>> popped_by_queue;
 
     // plugins/elastic/elastic.go:50-63 minAvailableState
-    void min_available_state(int ji, bool &below, bool &above, bool &exactly) const {
+    void min_available_state(int v, bool &below, bool &above, bool &exactly) const {
       exactly = true;
-      for (int s : o->J[ji].podsets) {
-        int n = o->podset_count(o->PS[s], kActiveAllocated);
-        if (n < o->PS[s].min_available) {
+      for (int k = 0; k < o->v_nps(v); k++) {
+        int n = o->v_active_alloc(v, k);
+        if (n < o->v_min(v, k)) {
           below = true;
           above = false;
           exactly = false;
           return;
         }
-        if (n > o->PS[s].min_available) exactly = false;
+        if (n > o->v_min(v, k)) exactly = false;
       }
       below = false;
       above = !exactly;
     }
     // framework/session_plugins.go:227-242 JobOrderFn = priority, elastic, creation, UID
     bool job_less(int l, int r) const {
-      const Job &lj = o->J[l], &rj = o->J[r];
+      const Job &lj = o->J[o->vjob(l)], &rj = o->J[o->vjob(r)];
       if (lj.priority > rj.priority) return true;  // plugins/priority/priority.go:41-54
       if (lj.priority < rj.priority) return false;
       bool lb, la, le, rb, ra, re;
@@ -1159,11 +1293,7 @@ struct kai_oracle {
       int q = nodes[leaf].queue;
       std::vector<int> v = popped_by_queue[q];
       if (!nodes[leaf].children.empty()) v.push_back(nodes[leaf].children.peek());
-      for (int ji : v)
-        for (int s : o->J[ji].podsets)
-          for (int ti : o->PS[s].tasks)
-            if (o->T[ti].status & kAllocatedStatuses)  // job_info.go:245-250 PodGroupInfo.Allocated
-              for (int r = 0; r < QR; r++) out[r] += o->T[ti].req[r];
+      for (int vi : v) o->v_allocated(vi, out);  // job_info.go:245-250 PodGroupInfo.Allocated
     }
     void init(kai_oracle *oracle, bool victims) {
       o = oracle;
@@ -1217,8 +1347,8 @@ struct kai_oracle {
       }
       if (is_new) ensure_chain(pn);
     }
-    void push_job(int ji) {  // :90-119
-      int q = o->J[ji].queue;
+    void push_job(int ji) {  // :90-119 (ji is a view id)
+      int q = o->J[o->vjob(ji)].queue;
       if (!o->Q[q].children.empty()) return;
       int leaf = queue_node[q];
       bool needs_linking = leaf < 0;
@@ -1293,6 +1423,721 @@ struct kai_oracle {
     for (int q = 0; q < NQ; q++) {
       std::sort(by_queue[q].begin(), by_queue[q].end(), [&](int a, int b) { return jo.job_less(a, b); });
       for (int ji : by_queue[q]) jo.push_job(ji);
+    }
+  }
+
+
+  // =====================================================================================================
+  // Victim-selection solver shared by reclaim and consolidation
+  // (actions/common/solvers/{job_solver,pod_scenario_builder,by_pod_solver}.go, scenario/*.go,
+  //  accumulated_scenario_filters/idle_gpus/*.go, actions/common/action.go).
+  // Go map iteration orders are resolved canonically: ascending node / job / queue index.
+  // =====================================================================================================
+  enum { SOLVER_RECLAIM = 0, SOLVER_CONSOLIDATION = 1 };
+
+  // input_jobs.go:21-68 with an explicit job set (views) and the option flags
+  struct OrderOpts {
+    bool filter_unready = false, filter_non_pending = false, filter_non_preemptible = false,
+         filter_non_active_allocated = false;
+  };
+  void init_jobs_order_views(JobsOrder &jo, const std::vector<int> &vs, const OrderOpts &op) {
+    std::vector<std::vector<int>> by_queue(NQ);
+    for (int v : vs) {
+      const Job &j = J[vjob(v)];
+      if (op.filter_unready && !job_ready(j)) continue;
+      if (op.filter_non_pending && v_pending_count(v) == 0) continue;
+      if (op.filter_non_preemptible && !j.preemptible) continue;
+      if (op.filter_non_active_allocated) {
+        bool active = false;
+        for (int ti : v_all_tasks(v))
+          if (T[ti].status & kActiveAllocated) active = true;
+        if (!active) continue;
+      }
+      if (j.queue < 0) continue;
+      if (!Q[j.queue].children.empty()) continue;
+      by_queue[j.queue].push_back(v);
+    }
+    for (int q = 0; q < NQ; q++) {
+      std::sort(by_queue[q].begin(), by_queue[q].end(),
+                [&](int a, int b) { return jo.victim_queue ? jo.job_less(b, a) : jo.job_less(a, b); });
+      for (int v : by_queue[q]) jo.push_job(v);
+    }
+  }
+
+  struct Scenario {  // scenario/base_scenario.go + by_node_scenario.go
+    int preemptor = -1;  // partial job representative (view)
+    std::vector<int> pending_tasks, potential_tasks, recorded_jobs, recorded_tasks;
+    std::map<int, std::vector<int>> victims;       // job -> victim tasks in append order (api.VictimInfo.Tasks)
+    std::map<int, std::vector<int>> task_groups;   // job -> task-group representatives (views)
+    std::map<int, std::vector<int>> jobs_by_node;  // node -> jobs with potential victims on it
+  };
+  void scenario_append_group(Scenario &sc, const std::vector<int> &tasks) {  // base_scenario.go:112-128
+    int ji = T[tasks[0]].job;
+    int group = make_clone(ji, tasks);
+    sc.task_groups[ji].push_back(group);
+    auto &vt = sc.victims[ji];
+    vt.insert(vt.end(), tasks.begin(), tasks.end());
+  }
+  void scenario_add_potential(Scenario &sc, const std::vector<int> &tasks) {  // by_node_scenario.go:52-57
+    if (tasks.empty()) return;
+    sc.potential_tasks.insert(sc.potential_tasks.end(), tasks.begin(), tasks.end());
+    scenario_append_group(sc, tasks);
+    for (int ti : tasks) {
+      auto &v = sc.jobs_by_node[T[ti].node];
+      if (std::find(v.begin(), v.end(), T[ti].job) == v.end()) v.push_back(T[ti].job);
+    }
+  }
+  void scenario_init(Scenario &sc, int partial, const std::vector<int> &recorded_jobs) {  // base_scenario.go:34-67
+    sc = Scenario();
+    sc.preemptor = partial;
+    sc.pending_tasks = v_all_tasks(partial);
+    sc.recorded_jobs = recorded_jobs;
+    for (int rv : recorded_jobs) scenario_append_group(sc, v_all_tasks(rv));
+    for (int rv : recorded_jobs)
+      for (int ti : v_all_tasks(rv)) sc.recorded_tasks.push_back(ti);
+  }
+  std::vector<int> scenario_victims_from_node(const Scenario &sc, int node) {  // by_node_scenario.go:59-80
+    std::vector<int> out;
+    auto it = sc.jobs_by_node.find(node);
+    if (it == sc.jobs_by_node.end()) return out;
+    std::vector<int> jobs = it->second;
+    std::sort(jobs.begin(), jobs.end());
+    for (int ji : jobs) {
+      auto g = sc.task_groups.find(ji);
+      if (g == sc.task_groups.end()) continue;
+      for (int group : g->second)
+        for (int ti : v_all_tasks(group)) out.push_back(ti);
+    }
+    return out;
+  }
+
+  // accumulated_scenario_filters/idle_gpus/idle_gpus.go: top-k nodes by idle+releasing GPUs (+ GPUs freed by the
+  // accumulated victims), greedy first-fit of the pending tasks' GPU requests sorted descending
+  struct IdleGpusFilter {
+    std::vector<double> idle;  // per node
+    int k = 0;
+    std::vector<char> seen;  // per task: already accounted as victim
+    bool active = false;
+  };
+  void idle_filter_init(IdleGpusFilter &f, const Scenario &sc) {
+    f.idle.assign(N, 0.0);
+    for (int n = 0; n < N; n++) f.idle[n] = I(KAI_RES_GPU, n) + L(KAI_RES_GPU, n);
+    f.k = (int)sc.pending_tasks.size();
+    f.seen.assign(NT, 0);
+    f.active = true;
+    idle_filter_update(f, sc);
+  }
+  void idle_filter_update(IdleGpusFilter &f, const Scenario &sc) {
+    for (const std::vector<int> *lst : {&sc.recorded_tasks, &sc.potential_tasks})
+      for (int ti : *lst) {
+        if (T[ti].node < 0 || f.seen[ti]) continue;
+        f.seen[ti] = 1;
+        if (N > 0) f.idle[T[ti].node] += T[ti].req[KAI_RES_GPU];
+      }
+  }
+  bool idle_filter_check(IdleGpusFilter &f, const Scenario &sc) {
+    idle_filter_update(f, sc);
+    std::vector<double> req;
+    for (int ti : sc.pending_tasks) req.push_back(T[ti].req[KAI_RES_GPU]);
+    std::sort(req.begin(), req.end(), std::greater<double>());
+    std::vector<double> cap = f.idle;
+    std::sort(cap.begin(), cap.end(), std::greater<double>());
+    if ((int)cap.size() > f.k) cap.resize(f.k);
+    std::vector<double> used(cap.size(), 0.0);
+    for (double required : req) {  // common.go:34-64 greedyMatchRequirements
+      if (required == 0) return true;
+      bool matched = false;
+      for (size_t h = 0; h < cap.size(); h++) {
+        if (cap[h] < required) break;
+        if (cap[h] - used[h] >= required) {
+          used[h] += required;
+          matched = true;
+          break;
+        }
+      }
+      if (!matched) return false;
+    }
+    return true;
+  }
+
+  struct SolveState {
+    std::vector<int> recorded_jobs, recorded_tasks;
+  };
+  struct SolveResult {
+    bool has = false, solved = false;
+    std::vector<int> victim_tasks, victim_jobs;
+  };
+  int solver_kind = SOLVER_RECLAIM;
+  int solver_reclaimer_job = -1;
+  std::vector<QueueAttr> sim_queues;  // proportion.go:131-136 jobSimulationQueues
+
+  // plugins/proportion/reclaimable/reclaimable.go:29-51
+  bool can_reclaim_resources(int ji) {
+    const Job &j = J[ji];
+    const double *req = tasks_to_allocate_init_resource(ji, false);
+    const QueueAttr &q = Q[j.queue];
+    for (int r = 0; r < QR; r++)
+      if (compare_quantities(q.s[r].allocated + req[r], q.s[r].fair) > 0) return false;
+    if (j.preemptible) return true;
+    for (int r = 0; r < QR; r++)
+      if (compare_quantities(q.s[r].alloc_np + req[r], q.s[r].deserved) > 0) return false;
+    return true;
+  }
+  // reclaimable.go:234-263 getLeveledQueues
+  void leveled_queues(const std::vector<QueueAttr> &QS, int reclaimer_q, int reclaimee_q, int &a, int &b) {
+    std::vector<int> pa, pb;
+    for (int q = reclaimer_q; q >= 0; q = QS[q].parent) pa.insert(pa.begin(), q);
+    for (int q = reclaimee_q; q >= 0; q = QS[q].parent) pb.insert(pb.begin(), q);
+    size_t n = std::min(pa.size(), pb.size());
+    a = b = -1;
+    for (size_t i = 0; i < n; i++) {
+      a = pa[i];
+      b = pb[i];
+      if (a != b) break;
+    }
+  }
+  struct Quant {
+    double v[QR];
+  };
+  static bool quant_le(const double *a, const double *b) {
+    for (int r = 0; r < QR; r++)
+      if (compare_quantities(a[r], b[r]) > 0) return false;
+    return true;
+  }
+  // strategies/strategies.go:18-91
+  bool fits_reclaim_strategy(const std::vector<QueueAttr> &QS, const double *reclaimer_req, int reclaimer_q,
+                             int reclaimee_q, const double *remaining) {
+    double allocatable[QR], deserved[QR];
+    for (int r = 0; r < QR; r++) {
+      allocatable[r] = allocatable_share(QS[reclaimee_q].s[r]);
+      deserved[r] = QS[reclaimee_q].s[r].deserved;
+    }
+    if (!quant_le(remaining, allocatable)) return true;  // MaintainFairShareStrategy
+    double want[QR], rdes[QR];                           // GuaranteeDeservedQuotaStrategy
+    for (int r = 0; r < QR; r++) {
+      want[r] = QS[reclaimer_q].s[r].allocated + reclaimer_req[r];
+      rdes[r] = QS[reclaimer_q].s[r].deserved;
+    }
+    if (!quant_le(want, rdes)) return false;
+    if (quant_le(remaining, deserved)) return false;
+    return true;
+  }
+  static double saturation_ratio(double allocated, double fair) {  // reclaimable.go:222-232
+    if (fair == 0) return allocated > 0 ? INFINITY : 0.0;
+    if (fair == KAI_UNLIMITED) return 0.0;
+    return allocated / fair;
+  }
+  // reclaimable.go:53-220 Reclaimable on the queue snapshot taken at OnJobSolutionStart
+  bool reclaimable(const std::vector<QueueAttr> &QS, int reclaimer_q, bool reclaimer_preemptible,
+                   const double *reclaimer_req, const std::map<int, std::vector<Quant>> &by_queue) {
+    std::map<int, Quant> remaining;
+    std::map<int, unsigned> involved;  // bit r set = resource r involved
+    auto get_remaining = [&](int q) -> Quant & {
+      auto it = remaining.find(q);
+      if (it == remaining.end()) {
+        Quant x;
+        for (int r = 0; r < QR; r++) x.v[r] = QS[q].s[r].allocated;
+        it = remaining.emplace(q, x).first;
+      }
+      return it->second;
+    };
+    auto involved_of = [&](const std::vector<Quant> &rs) {
+      unsigned m = 0;
+      for (const Quant &x : rs)
+        for (int r = 0; r < QR; r++)
+          if (x.v[r] > 0) m |= 1u << r;
+      return m;
+    };
+    for (const auto &kv : by_queue) {
+      int reclaimee_leaf = kv.first;
+      int lq, eq;
+      leveled_queues(QS, reclaimer_q, reclaimee_leaf, lq, eq);
+      involved[reclaimee_leaf] = involved_of(kv.second);
+      get_remaining(eq);
+      for (const Quant &res : kv.second) {
+        if (!fits_reclaim_strategy(QS, reclaimer_req, lq, eq, get_remaining(eq).v)) return false;
+        for (int q = reclaimee_leaf; q >= 0; q = QS[q].parent) {  // subtractReclaimedResources
+          Quant &rem = get_remaining(q);
+          for (int r = 0; r < QR; r++) rem.v[r] -= res.v[r];
+          if (involved.count(q))
+            involved[q] |= involved[reclaimee_leaf];
+          else
+            involved[q] = involved[reclaimee_leaf];
+        }
+      }
+    }
+    // reclaimingQueuesRemainWithinBoundaries
+    unsigned reclaimer_involved = 0;
+    for (int r = 0; r < QR; r++)
+      if (reclaimer_req[r] > 0) reclaimer_involved |= 1u << r;
+    for (int rq = reclaimer_q; rq >= 0; rq = QS[rq].parent) {
+      Quant mine;
+      auto it = remaining.find(rq);
+      if (it != remaining.end()) {
+        for (int r = 0; r < QR; r++) it->second.v[r] += reclaimer_req[r];  // the map entry itself is updated
+        mine = it->second;
+      } else {
+        for (int r = 0; r < QR; r++) mine.v[r] = QS[rq].s[r].allocated + reclaimer_req[r];
+      }
+      std::vector<int> sib_ids;
+      for (const auto &kv : remaining) sib_ids.push_back(kv.first);
+      for (int sib : sib_ids) {
+        if (QS[sib].parent != QS[rq].parent || sib == rq) continue;
+        const Quant &sr = remaining[sib];
+        unsigned inv = (involved.count(sib) ? involved[sib] : 0u) | reclaimer_involved;
+        for (int r = 0; r < QR; r++) {
+          if (!(inv & (1u << r))) continue;
+          double rf = QS[rq].s[r].fair, sf = QS[sib].s[r].fair;
+          if (rf == KAI_UNLIMITED && sf == KAI_UNLIMITED) continue;
+          double ratio_r = saturation_ratio(mine.v[r], rf), ratio_s = saturation_ratio(sr.v[r], sf);
+          if (ratio_r > 1 && sf > 0 && ratio_r * cfg.saturation_multiplier >= ratio_s) return false;
+        }
+      }
+      if (reclaimer_preemptible) continue;
+      for (int r = 0; r < QR; r++)
+        if (compare_quantities(QS[rq].s[r].alloc_np + reclaimer_req[r], QS[rq].s[r].deserved) > 0) return false;
+    }
+    return true;
+  }
+  // proportion.go:143-240 reclaimableFn / getVictimResources / splitVictimTasks / getResources
+  bool reclaim_validator(const Scenario &sc) {
+    const Job &rj = J[vjob(sc.preemptor)];
+    const double *req = tasks_to_allocate_init_resource(sc.preemptor, false);
+    std::map<int, std::vector<Quant>> by_queue;
+    for (const auto &kv : sc.victims) {
+      const Job &vj = J[kv.first];
+      std::vector<Quant> res;
+      std::vector<int> core, elastic;
+      for (size_t k = 0; k < vj.podsets.size(); k++) {
+        std::vector<int> sub;
+        for (int ti : kv.second)
+          if (T[ti].podset == vj.podsets[k]) sub.push_back(ti);
+        if (sub.empty()) continue;
+        int mn = PS[vj.podsets[k]].min_available;
+        for (size_t i = 0; i < sub.size(); i++) ((int)i < mn ? core : elastic).push_back(sub[i]);
+      }
+      auto get_resources = [&](const std::vector<int> &tasks, Quant &out) {
+        int n = 0;
+        for (int r = 0; r < QR; r++) out.v[r] = 0;
+        for (int ti : tasks) {
+          if (cfg.allow_consolidating_reclaim && (T[ti].status & kActiveAllocated)) continue;
+          n++;
+          for (int r = 0; r < QR; r++) out.v[r] += T[ti].req[r];
+        }
+        return n > 0;
+      };
+      for (int ti : elastic) {
+        Quant x;
+        if (get_resources({ti}, x)) res.push_back(x);
+      }
+      Quant x;
+      if (get_resources(core, x)) res.push_back(x);
+      if (res.empty()) continue;
+      auto &dst = by_queue[vj.queue];
+      dst.insert(dst.end(), res.begin(), res.end());
+    }
+    return reclaimable(sim_queues, rj.queue, rj.preemptible, req, by_queue);
+  }
+  // consolidation.go:108-117 allPodsReallocated
+  bool consolidation_validator(const Scenario &sc) {
+    for (const auto &kv : sc.victims)
+      for (int ti : kv.second)
+        if (T[ti].status == KAI_POD_RELEASING) return false;
+    return true;
+  }
+
+  // actions/common/action.go:67-122 GetJobsToAllocate + TryToVirtuallyAllocatePreemptorAndGetVictims
+  bool try_virtually_allocate(const Scenario &sc, const std::vector<int> &nodes, const std::vector<int> &victim_tasks) {
+    const int pj = vjob(sc.preemptor);
+    std::vector<char> is_victim_job(NJ, 0), in_set(NJ, 0);
+    std::vector<int> vs;
+    for (int ji = 0; ji < NJ; ji++)
+      if (job_count(J[ji], KAI_POD_PENDING) > 0) in_set[ji] = 1;
+    for (int ti : victim_tasks) {
+      in_set[T[ti].job] = 1;
+      is_victim_job[T[ti].job] = 1;
+    }
+    in_set[pj] = 1;
+    for (int ji = 0; ji < NJ; ji++)
+      if (in_set[ji]) vs.push_back(ji == pj ? sc.preemptor : ji);
+    JobsOrder jo;
+    jo.init(this, false);
+    init_jobs_order_views(jo, vs, OrderOpts());
+    bool preemptor_allocated = false;
+    while (!jo.is_empty()) {
+      int v = jo.pop_next_job();
+      if (v < 0) break;
+      int ji = vjob(v);
+      if (!is_victim_job[ji] && ji != pj) continue;
+      if (getenv("KAI_ORACLE_TRACE")) fprintf(stderr, "[solver]     sim pops job %d%s\n", ji, ji == pj ? " (preemptor)" : "");
+      tasks_to_allocate_init_resource(v, false);
+      if (ji != pj) {
+        allocate_job(v, &nodes, true);
+        continue;
+      }
+      if (!allocate_job(v, &nodes, true)) return false;
+      preemptor_allocated = true;
+    }
+    return preemptor_allocated;
+  }
+
+  // by_pod_solver.go:124-143,229-253 runSimulation + tryScenarioWithEvictedVictims + handleScenarioSolution
+  SolveResult run_simulation(Scenario &sc, const std::vector<char> &feasible, const std::vector<int> &victim_tasks) {
+    SolveResult res;
+    std::vector<int> nodes;
+    for (int n = 0; n < N; n++)
+      if (feasible[n]) nodes.push_back(n);
+    if (!try_virtually_allocate(sc, nodes, victim_tasks)) return res;  // has = false: keep looking
+    std::vector<int> preempted, pipelined;
+    for (int ti : victim_tasks) {
+      if (T[ti].status == KAI_POD_RELEASING)
+        preempted.push_back(ti);
+      else if (T[ti].status == KAI_POD_PIPELINED)
+        pipelined.push_back(ti);
+    }
+    res.has = true;
+    bool valid = solver_kind == SOLVER_RECLAIM ? reclaim_validator(sc) : consolidation_validator(sc);
+    if (!valid) {
+      stmt_discard();
+      return res;
+    }
+    res.victim_tasks = preempted;
+    res.victim_tasks.insert(res.victim_tasks.end(), pipelined.begin(), pipelined.end());
+    // getVictimJobsFromVictimTasks: the task-group representatives that hold the victim tasks
+    std::map<int, std::vector<int>> groups;
+    for (int ti : res.victim_tasks) {
+      int ji = T[ti].job;
+      bool exists = false;
+      for (int g : groups[ji]) {
+        std::vector<int> gt = v_all_tasks(g);
+        if (std::find(gt.begin(), gt.end(), ti) != gt.end()) exists = true;
+      }
+      if (exists) continue;
+      for (int g : sc.task_groups[ji]) {
+        std::vector<int> gt = v_all_tasks(g);
+        if (std::find(gt.begin(), gt.end(), ti) != gt.end()) {
+          groups[ji].push_back(g);
+          break;
+        }
+      }
+    }
+    for (auto &kv : groups) res.victim_jobs.insert(res.victim_jobs.end(), kv.second.begin(), kv.second.end());
+    res.solved = true;
+    return res;
+  }
+
+  // by_pod_solver.go:69-122,145-201 byPodSolver.solve
+  SolveResult bypod_solve(Scenario &sc, std::vector<char> &feasible) {
+    ops.clear();  // session.Statement()
+    for (int ti : sc.recorded_tasks) stmt_evict(ti);
+    if (sc.potential_tasks.empty()) {
+      if (!sc.recorded_tasks.empty()) {
+        SolveResult r = run_simulation(sc, feasible, sc.recorded_tasks);
+        if (r.has) return r;
+      }
+    } else {
+      int latest = T[sc.potential_tasks.back()].job;
+      std::vector<int> nodes;  // getNodesOfJob: distinct nodes of all pods of the job (canonical: ascending index)
+      for (int s2 : J[latest].podsets)
+        for (int ti : PS[s2].tasks)
+          if (T[ti].node >= 0 && std::find(nodes.begin(), nodes.end(), T[ti].node) == nodes.end())
+            nodes.push_back(T[ti].node);
+      std::sort(nodes.begin(), nodes.end());
+      for (int node : nodes) {
+        int cp = stmt_checkpoint();
+        std::vector<int> potential = scenario_victims_from_node(sc, node);
+        for (int ti : potential) stmt_evict(ti);
+        std::vector<int> added;
+        for (int ti : potential)
+          if (!feasible[T[ti].node]) {
+            feasible[T[ti].node] = 1;
+            added.push_back(T[ti].node);
+          }
+        std::vector<int> victim_tasks = sc.recorded_tasks;
+        victim_tasks.insert(victim_tasks.end(), potential.begin(), potential.end());
+        SolveResult r = run_simulation(sc, feasible, victim_tasks);
+        if (r.has) return r;
+        for (int n : added) feasible[n] = 0;
+        stmt_rollback(cp);
+      }
+    }
+    stmt_discard();
+    SolveResult none;
+    none.has = true;
+    return none;
+  }
+
+  // the victims queue of the action (reclaim.go:121-143 / consolidation.go:119-157 + utils/action.go:20-52)
+  void build_victims_queue(JobsOrder &jo, int pending_job) {
+    jo.init(this, true);
+    std::vector<int> vs;
+    OrderOpts op;
+    if (solver_kind == SOLVER_RECLAIM) {
+      op.filter_non_preemptible = true;
+      op.filter_non_active_allocated = true;
+      for (int ji = 0; ji < NJ; ji++) {
+        if (J[ji].queue == J[pending_job].queue) continue;
+        vs.push_back(ji);  // ReclaimVictimFilter: minruntime protection is not modelled (always unprotected)
+      }
+    } else {
+      int counter = 0;
+      for (int ji = 0; ji < NJ; ji++) {
+        bool alive = false;
+        for (int s2 : J[ji].podsets)
+          for (int ti : PS[s2].tasks)
+            if (T[ti].status & kAlive) alive = true;
+        if (!alive) continue;
+        if (!J[ji].preemptible) continue;
+        if (ji == pending_job) continue;
+        if (cfg.max_consolidation_preemptees != -1 && counter > cfg.max_consolidation_preemptees) continue;
+        if (job_count(J[ji], kActiveAllocated) == 0) continue;
+        counter++;
+        vs.push_back(ji);
+      }
+    }
+    init_jobs_order_views(jo, vs, op);
+  }
+
+  // job_solver.go:90-118 solvePartialJob + pod_scenario_builder.go
+  SolveResult solve_partial(const SolveState &state, int pending_job, int partial, const std::vector<char> &base_feasible) {
+    std::vector<char> feasible = base_feasible;
+    for (int ti : state.recorded_tasks)
+      if (T[ti].node >= 0) feasible[T[ti].node] = 1;
+    Scenario sc;
+    scenario_init(sc, partial, state.recorded_jobs);
+    std::vector<char> recorded_set(NT, 0);
+    for (int rv : state.recorded_jobs)
+      for (int ti : v_all_tasks(rv)) recorded_set[ti] = 1;
+    JobsOrder victims_queue;
+    build_victims_queue(victims_queue, pending_job);
+    IdleGpusFilter filter;
+    idle_filter_init(filter, sc);
+    bool first = true;
+    for (;;) {
+      bool need_add = !first;
+      first = false;
+      bool have = false;
+      for (;;) {
+        if (need_add) {
+          bool added = false;
+          while (!added) {  // GetNextScenario / addNextPotentialVictims
+            if (victims_queue.is_empty()) break;
+            int next = victims_queue.pop_next_job();
+            if (next < 0) break;
+            bool has_more = false;
+            std::vector<int> tasks = tasks_to_evict(next, has_more);
+            bool recorded_hit = false;
+            for (int ti : tasks)
+              if (recorded_set[ti]) recorded_hit = true;
+            if (recorded_hit) {
+              std::vector<int> remaining;
+              for (int ti : v_all_tasks(next))
+                if (!recorded_set[ti]) remaining.push_back(ti);
+              if (!remaining.empty()) victims_queue.push_job(make_clone(next, remaining));
+              continue;
+            }
+            if (has_more) {
+              std::vector<int> remaining;
+              for (int ti : v_all_tasks(next))
+                if (std::find(tasks.begin(), tasks.end(), ti) == tasks.end()) remaining.push_back(ti);
+              victims_queue.push_job(make_clone(next, remaining));
+            }
+            scenario_add_potential(sc, tasks);
+            added = true;
+          }
+          if (!added) break;
+        }
+        if (idle_filter_check(filter, sc)) {
+          have = true;
+          break;
+        }
+        need_add = true;
+      }
+      if (!have) break;
+      stats.kernel_launches++;  // scenarios simulated (metrics.IncScenarioSimulatedByAction)
+      if (getenv("KAI_ORACLE_TRACE")) {
+        fprintf(stderr, "[solver] job %d partial %zu tasks; recorded:", pending_job, sc.pending_tasks.size());
+        for (int ti : sc.recorded_tasks) fprintf(stderr, " %d", ti);
+        fprintf(stderr, " potential:");
+        for (int ti : sc.potential_tasks) fprintf(stderr, " %d", ti);
+        fprintf(stderr, "\n");
+      }
+      SolveResult r = bypod_solve(sc, feasible);
+      if (getenv("KAI_ORACLE_TRACE")) {
+        fprintf(stderr, "[solver]   -> solved %d victims:", (int)r.solved);
+        for (int ti : r.victim_tasks) fprintf(stderr, " %d(st %d node %d)", ti, T[ti].status, T[ti].node);
+        fprintf(stderr, "\n");
+      }
+      if (r.solved) return r;
+    }
+    SolveResult none;
+    return none;
+  }
+
+  // job_solver.go:47-88 Solve + :120-148 getPartialJobRepresentative
+  bool solve_job(int ji, const std::vector<char> &base_feasible) {
+    SolveState state;
+    int original_active = job_count(J[ji], kActiveUsed);
+    std::vector<int> tta = tasks_to_allocate(ji, false);
+    std::vector<int> pending;
+    bool have_statement = false;
+    for (size_t i = 0; i < tta.size(); i++) {
+      pending.push_back(tta[i]);
+      bool satisfactory = pending.size() == tta.size();
+      int partial = make_clone(ji, pending);
+      {
+        View &pv = views[partial - NJ];
+        for (size_t k = 0; k < pv.ps_tasks.size(); k++)
+          if (!pv.ps_tasks[k].empty()) pv.ps_min[k] = (int)pv.ps_tasks[k].size();
+      }
+      SolveResult r = solve_partial(state, ji, partial, base_feasible);
+      if (!r.solved) {
+        have_statement = false;
+        break;
+      }
+      if (!satisfactory) stmt_discard();
+      have_statement = satisfactory;
+      state.recorded_tasks = r.victim_tasks;
+      state.recorded_jobs = r.victim_jobs;
+    }
+    int active = job_count(J[ji], kActiveUsed);
+    bool solved = true;
+    for (int s2 : J[ji].podsets)  // IsGangSatisfied
+      if (podset_count(PS[s2], kActiveUsed) < PS[s2].min_available) solved = false;
+    if (original_active >= active) solved = false;
+    if (!have_statement) ops.clear();
+    return solved;
+  }
+  // actions/common/feasible_nodes.go:11-26
+  std::vector<char> feasible_nodes_for_job(int ji) {
+    std::vector<char> f(N, 1);
+    for (int s2 : J[ji].podsets)
+      for (int ti : PS[s2].tasks)
+        if (!task_requires_gpu(T[ti])) return f;
+    for (int n = 0; n < N; n++) f[n] = (I(KAI_RES_GPU, n) > 0 || L(KAI_RES_GPU, n) > 0) ? 1 : 0;
+    return f;
+  }
+
+  // actions/common/minimal_job_comparison.go
+  struct MinimalReps {
+    std::map<int, int> rep;  // signature -> job
+  };
+  bool req_less_equal(int a, int b) const {  // ResourceRequirements.LessEqual (resource_requirment.go:126-140)
+    for (int r = 0; r < R; r++) {
+      if (r >= 3) {
+        if (T[a].req[r] != 0 && T[a].req[r] > T[b].req[r]) return false;
+      } else if (T[a].req[r] > T[b].req[r])
+        return false;
+    }
+    return true;
+  }
+  std::vector<int> sorted_pending(int ji) const {  // extractSortedResourceRequests; sort.Slice == insertion sort for n <= 12
+    std::vector<int> v;
+    for (int s2 : J[ji].podsets)
+      for (int ti : PS[s2].tasks)
+        if (T[ti].status == KAI_POD_PENDING) v.push_back(ti);
+    for (size_t i = 1; i < v.size(); i++)
+      for (size_t j2 = i; j2 > 0 && req_less_equal(v[j2], v[j2 - 1]); j2--) std::swap(v[j2], v[j2 - 1]);
+    return v;
+  }
+  bool easier_to_schedule(const MinimalReps &m, int ji) const {
+    if (J[ji].signature < 0) return true;
+    auto it = m.rep.find(J[ji].signature);
+    if (it == m.rep.end()) return true;
+    std::vector<int> a = sorted_pending(ji), b = sorted_pending(it->second);
+    if (a.empty() || b.empty()) return false;
+    if (b.size() > a.size()) return true;
+    for (size_t i = 0; i < a.size(); i++) {
+      if (i >= b.size()) return false;
+      if (req_less_equal(a[i], b[i])) {
+        if (req_less_equal(b[i], a[i])) continue;
+        return true;
+      }
+    }
+    return false;
+  }
+  void update_representative(MinimalReps &m, int ji) const {
+    if (J[ji].signature < 0) return;
+    auto it = m.rep.find(J[ji].signature);
+    if (it != m.rep.end()) {
+      std::vector<int> a = sorted_pending(ji), b = sorted_pending(it->second);
+      bool smaller = !(a.empty() || b.empty()) && a.size() <= b.size();
+      if (smaller)
+        for (size_t i = 0; i < a.size(); i++)
+          if (!req_less_equal(a[i], b[i])) smaller = false;
+      if (!smaller) return;
+    }
+    m.rep[J[ji].signature] = ji;
+  }
+
+  // ---------------- actions/reclaim/reclaim.go:46-119 ----------------
+  void run_reclaim() {
+    solver_kind = SOLVER_RECLAIM;
+    views.clear();
+    JobsOrder jo;
+    jo.init(this, false);
+    init_jobs_order(jo, true, true);
+    std::map<int, MinimalReps> failed_by_queue;
+    while (!jo.is_empty()) {
+      int ji = jo.pop_next_job();
+      if (ji < 0) break;
+      if (!can_reclaim_resources(ji)) continue;
+      MinimalReps &reps = failed_by_queue[J[ji].queue];
+      if (use_signatures && !easier_to_schedule(reps, ji)) continue;
+      tasks_to_allocate_init_resource(ji, false);
+      sim_queues = Q;  // OnJobSolutionStart
+      std::vector<char> feasible = feasible_nodes_for_job(ji);
+      ops.clear();
+      bool ok = solve_job(ji, feasible);
+      if (ok) {
+        stmt_commit();
+        r_visits.push_back({ji, 1});
+      } else {
+        ops.clear();
+        update_representative(reps, ji);
+        r_visits.push_back({ji, 0});
+      }
+    }
+  }
+  // ---------------- actions/consolidation/consolidation.go:32-106 ----------------
+  void run_consolidation() {
+    solver_kind = SOLVER_CONSOLIDATION;
+    views.clear();
+    if (cfg.max_consolidation_preemptees == 0) return;
+    JobsOrder jo;
+    jo.init(this, false);
+    {
+      std::vector<int> vs;
+      for (int ji = 0; ji < NJ; ji++) vs.push_back(ji);
+      OrderOpts op;
+      op.filter_non_pending = op.filter_unready = op.filter_non_preemptible = true;
+      init_jobs_order_views(jo, vs, op);
+    }
+    MinimalReps reps;
+    while (!jo.is_empty()) {
+      int ji = jo.pop_next_job();
+      if (ji < 0) break;
+      if (use_signatures && !easier_to_schedule(reps, ji)) continue;
+      tasks_to_allocate_init_resource(ji, false);
+      // utils/action.go:130-160 IsEnoughGPUsAllocatableForJob
+      double sum = 0, want = 0;
+      for (int n = 0; n < N; n++)
+        if (nflags[n] & KAI_NODE_READY) sum += I(KAI_RES_GPU, n), sum += L(KAI_RES_GPU, n);
+      for (int ti : tasks_to_allocate(ji, false)) want += T[ti].req[KAI_RES_GPU];
+      bool ok = false;
+      ops.clear();
+      if (sum >= want) {
+        std::vector<char> feasible = feasible_nodes_for_job(ji);
+        ok = solve_job(ji, feasible);
+      }
+      if (ok) {
+        stmt_commit();
+        r_visits.push_back({ji, 1});
+      } else {
+        ops.clear();
+        update_representative(reps, ji);
+        r_visits.push_back({ji, 0});
+      }
     }
   }
 
@@ -1444,9 +2289,11 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
         tk.order_rank = s->task_order_rank[t];
         tk.nominated = s->task_nominated ? s->task_nominated[t] : -1;
         tk.pred_class = s->task_pred_class ? s->task_pred_class[t] : -1;
-        tk.on_node = (tk.status & kActiveUsed) && tk.node >= 0;
-        tk.node_status = tk.status;
-        if (!tk.on_node && !(tk.status & kActiveUsed)) tk.node = -1;
+        bool on = (tk.status & kActiveUsed) && tk.node >= 0;
+        tk.on_node[0] = on ? tk.node : -1;
+        tk.on_node[1] = -1;
+        tk.on_status[0] = tk.status;
+        if (!on && !(tk.status & kActiveUsed)) tk.node = -1;
       }
     }
   }
@@ -1468,6 +2315,12 @@ int kai_oracle_run(kai_oracle *o, kai_action action, kai_result *out) {
   switch (action) {
     case KAI_ACTION_ALLOCATE:
       o->run_allocate();
+      break;
+    case KAI_ACTION_RECLAIM:
+      o->run_reclaim();
+      break;
+    case KAI_ACTION_CONSOLIDATION:
+      o->run_consolidation();
       break;
     default:
       o->err = "action not implemented by the oracle";

@@ -113,6 +113,7 @@ def build_snapshot(topo: dict):
     job_podset_begin = [0]
     podset_min, podset_task_begin = [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_job = [], [], [], [], [], []
+    t_fixture_node = []
     for ji, job in enumerate(jobs):
         job_names.append(job["Name"])
         job_queue.append(qindex.get(job.get("QueueName", ""), -1))
@@ -168,6 +169,9 @@ def build_snapshot(topo: dict):
                 t_rank.append(order_rank[k])
                 t_names.append(f"{job['Name']}-{k}")
                 t_job.append(ji)
+                # a fixture may name a node on a Pending task; PodInfo.NodeName keeps it and the reference's
+                # matcher compares it (test_utils.go:236-244) although it never reaches the algorithm
+                t_fixture_node.append(node if t_node[-1] < 0 else "")
             podset_task_begin.append(len(t_status))
         job_podset_begin.append(len(podset_min))
     # job order rank under (CreationTimestamp, UID)
@@ -215,7 +219,7 @@ def build_snapshot(topo: dict):
     )
     meta = {
         "node_names": node_names, "job_names": job_names, "task_names": t_names,
-        "task_job": np.array(t_job, dtype=np.int32), "queue_names": qnames,
+        "task_job": np.array(t_job, dtype=np.int32), "queue_names": qnames, "task_fixture_node": t_fixture_node,
     }
     return snap, meta
 
@@ -236,7 +240,7 @@ def check_expectations(topo: dict, meta: dict, res: "abi.Result", snap: "abi.Sna
             if st != exp.get("Status"):
                 errs.append(f"job {jname} task {meta['task_names'][t]}: status {st}, expected {exp.get('Status')}")
             want = exp.get("NodeName") or ""
-            got = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else ""
+            got = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else meta["task_fixture_node"][t]
             if want and got != want:
                 errs.append(f"job {jname} task {meta['task_names'][t]}: node {got!r}, expected {want!r}")
             gpus += snap.task_req[t, 2]
@@ -251,7 +255,7 @@ def check_expectations(topo: dict, meta: dict, res: "abi.Result", snap: "abi.Sna
         if st != exp.get("Status"):
             errs.append(f"task {tname}: status {st}, expected {exp.get('Status')}")
         want = exp.get("NodeName") or ""
-        got = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else ""
+        got = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else meta["task_fixture_node"][t]
         if want and got != want:
             errs.append(f"task {tname}: node {got!r}, expected {want!r}")
     for nname, exp in (topo.get("ExpectedNodesResources") or {}).items():

@@ -23,6 +23,23 @@ def test_allocate_tables(cid, case):
     assert not errs, f"{case['source']} #{case['index']} {case['name']}: {errs}"
 
 
+RECLAIM = action_cases(["reclaim__"], single_action="reclaim")
+CONSOLIDATION = action_cases(["consolidation__"], single_action="consolidation")
+
+
+@pytest.mark.parametrize("cid,case", RECLAIM + CONSOLIDATION, ids=[c[0] for c in RECLAIM + CONSOLIDATION])
+def test_solver_tables(cid, case):
+    """reclaim (40+5+9+11+6 tables) and consolidation (20+6): victims Releasing, preemptor Pipelined, moved victims
+    Pipelined on their new node — the victim SETS the reference's tests pin."""
+    snap, meta = dsl.build_snapshot(case["topology"])
+    o = Oracle()
+    o.load(snap)
+    res = o.run(case["actions"][0])
+    errs = dsl.check_expectations(case["topology"], meta, res, snap)
+    assert not errs, f"{case['source']} #{case['index']} {case['name']}: {errs}"
+
+
 def test_case_counts():
+    assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 24
     # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
     assert len(ALLOCATE) == 41
