@@ -237,6 +237,7 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
   const uint32_t *mask = d.pred_class >= 0 ? s.pred_mask + (size_t)d.pred_class * s.mask_words : nullptr;
   for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
     int n = tl.node[ln];
+    if (d.restricted && !(tl.flags[ln] & kTileFeas)) continue;
     if (mask && !((__ldg(&mask[n >> 5]) >> (n & 31)) & 1u)) continue;
     double score;
     bool fit_i;
@@ -251,6 +252,74 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
     uint32_t rk = (uint32_t)tl.rank[ln];
     if (better(score, rk, best.score, best.rank)) {
       best.score = score;
+      best.rank = rk;
+      best.ln = ln;
+    }
+  }
+  if (fit_count) {
+    int w = __reduce_add_sync(0xffffffffu, n_fit);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(fit_count, w);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double os = __shfl_down_sync(0xffffffffu, best.score, o);
+    uint32_t orank = __shfl_down_sync(0xffffffffu, best.rank, o);
+    int oln = __shfl_down_sync(0xffffffffu, best.ln, o);
+    if (better(os, orank, best.score, best.rank)) {
+      best.score = os;
+      best.rank = orank;
+      best.ln = oln;
+    }
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh_warp[warp] = best;
+  __syncthreads();
+  if (warp == 0) {
+    int nw = blockDim.x >> 5;
+    Cand c;
+    if (lane < nw)
+      c = sh_warp[lane];
+    else {
+      c.score = -1.0;
+      c.rank = kRankNone;
+      c.ln = -1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double os = __shfl_down_sync(0xffffffffu, c.score, o);
+      uint32_t orank = __shfl_down_sync(0xffffffffu, c.rank, o);
+      int oln = __shfl_down_sync(0xffffffffu, c.ln, o);
+      if (better(os, orank, c.score, c.rank)) {
+        c.score = os;
+        c.rank = orank;
+        c.ln = oln;
+      }
+    }
+    best = c;
+  }
+  return best;  // valid on thread 0
+}
+
+// Block argmax on (idle + releasing GPUs desc, name rank asc) over the rows strictly after the cutoff.
+__device__ Cand scan_tile_topk(const Tile &tl, const Decision &d, Cand *sh_warp, const int *excl, int n_excl,
+                               int *fit_count) {
+  Cand best;
+  int n_fit = 0;
+  best.score = -1.0;
+  best.rank = kRankNone;
+  best.ln = -1;
+  const bool has_cut = d.req[2] != 0.0;
+  const double cut_key = d.req[0];
+  const uint32_t cut_rank = (uint32_t)d.req[1];
+  for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
+    double key = __dadd_rn(tl.I[KAI_RES_GPU * tl.npc + ln], tl.L[KAI_RES_GPU * tl.npc + ln]);
+    uint32_t rk = (uint32_t)tl.rank[ln];
+    if (has_cut && !(key < cut_key || (key == cut_key && rk > cut_rank))) continue;
+    n_fit++;
+    bool skip = false;
+    for (int x = 0; x < n_excl; x++)
+      if (excl[x] == ln) skip = true;
+    if (skip) continue;
+    if (better(key, rk, best.score, best.rank)) {
+      best.score = key;
       best.rank = rk;
       best.ln = ln;
     }
@@ -819,7 +888,7 @@ struct ScanShared {
   unsigned long long dw[kDecWords];
   Decision dec;
   Track trk[2];
-  int kind, n_delta, batching;
+  int kind, n_delta, batching, xbits;
   int2 delta[kMaxDelta];
   unsigned char mine[kMaxDelta];
   int fit_count;
@@ -928,6 +997,8 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         d.res = (int)((w0 >> 8) & 0xff);
         d.strategy = (int)((w0 >> 16) & 0xff);
         sh.n_delta = (int)((w0 >> 32) & 0xffff);
+        sh.xbits = (int)((w0 >> 48) & 0xffff);
+        d.restricted = (sh.xbits & XB_RESTRICT) ? 1 : 0;
         d.gpu_task = (bits & DB_GPU_TASK) ? 1 : 0;
         d.best_effort = (bits & DB_BEST_EFFORT) ? 1 : 0;
         d.pipeline_only = (bits & DB_PIPELINE_ONLY) ? 1 : 0;
@@ -960,7 +1031,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         bool mine = tile_owns(tile, (unsigned int)(en.x & 0x0fffffff), ln) && ln < tile.count;
         sh.mine[e] = mine ? 1 : 0;
         sh.dln[e] = ln | ((int)(hi >> 32) << 24);  // repeat count - 1 in the top byte
-        if (mine)
+        if (mine && ((en.x >> 28) & 7) < ND_FEAS_SET)
           for (int r = 0; r < s.R; r++) sh.dreq[e][r] = __ldg(&s.t_req[(size_t)en.y * s.R + r]);
       }
       __syncthreads();
@@ -969,9 +1040,22 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           if (!sh.mine[e]) continue;
           int2 en = sh.delta[e];
           const int ln = sh.dln[e] & 0xffffff, reps = ((unsigned int)sh.dln[e] >> 24) + 1;
+          const int code = (en.x >> 28) & 7;
+          if (code >= ND_FEAS_SET) {
+            if (lane == 0) tile.flags[ln] = code == ND_FEAS_SET ? (tile.flags[ln] | kTileFeas) : (tile.flags[ln] & ~kTileFeas);
+            continue;
+          }
           for (int k = 0; k < reps; k++)
-            apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], (en.x >> 28) & 7, sh.dreq[e][lane]);
+            apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], code, sh.dreq[e][lane]);
         }
+      }
+      __syncthreads();
+    }
+    if (sh.xbits & (XB_SNAP_ALL | XB_SNAP_GPUFREE)) {  // common.FeasibleNodesForJob (feasible_nodes.go:11-26)
+      const bool all = (sh.xbits & XB_SNAP_ALL) != 0;
+      for (int ln = tid; ln < tile.count; ln += blockDim.x) {
+        bool in = all || tile.I[KAI_RES_GPU * tile.npc + ln] > 0 || tile.L[KAI_RES_GPU * tile.npc + ln] > 0;
+        tile.flags[ln] = in ? (tile.flags[ln] | kTileFeas) : (tile.flags[ln] & ~kTileFeas);
       }
       __syncthreads();
     }
@@ -996,6 +1080,27 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       if (warp < kTopM)
         publish_list_candidate(tile, sh.dec, sh.cands[warp], sh.fit_count > kTopM, lines + 2 * warp,
                                lines + (size_t)(1 + warp) * kListLineWords, seq & 0xffffffu);
+    } else if (kind == DK_TOPK) {
+      // ---- accumulated_scenario_filters/idle_gpus: rows by idle + releasing GPUs, descending (name rank ascending
+      //      among equals), strictly after the cutoff (req[0] = key, req[1] = rank, req[2] = cutoff present) ----
+      if (tid == 0) sh.fit_count = 0;
+      __syncthreads();
+      for (int m = 0; m < kTopM; m++) {
+        Cand c = scan_tile_topk(tile, sh.dec, sh_warp, sh.excl, m, m == 0 ? &sh.fit_count : nullptr);
+        if (tid == 0) {
+          sh.cands[m] = c;
+          sh.excl[m] = c.ln;
+        }
+        __syncthreads();
+      }
+      unsigned long long *lines = p.h_list + ((size_t)(seq & 1) * kListScanners + (size_t)(p.scanner_base + my)) * kListLines * kListLineWords;
+      if (tid < kTopM) {
+        const Cand c = sh.cands[tid];
+        const uint32_t flags = sh.fit_count > kTopM ? LF_MORE : 0u;
+        unsigned long long hi = ((unsigned long long)(seq & 0xffffffu) << 40) | ((unsigned long long)flags << 32) |
+                                (unsigned long long)(c.rank == kRankNone ? kRankNone : (c.rank & 0xffffffu));
+        st_relaxed_sys_b128(lines + 2 * tid, (unsigned long long)__double_as_longlong(c.score), hi);
+      }
     } else if (kind == DK_SCAN) {
       Cand local = scan_tile(tile, sh.dec, s, sh_warp);
       long long c4 = clock64();
@@ -1008,6 +1113,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
           double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
           if (overall == 0) continue;
+          if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
           double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
           if (cur < mn[k]) mn[k] = cur;
           if (cur > mx[k]) mx[k] = cur;
@@ -1036,6 +1142,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
           double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
           if (overall == 0) continue;
+          if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
           double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
           if (cur == mn[k]) c[2 * k]++;
           if (cur == mx[k]) c[2 * k + 1]++;
@@ -1161,6 +1268,8 @@ __device__ void sequencer_main(const ActionParams &p, unsigned char *smem, Ctl &
     ctl.seq = p.seq0;
     ctl.n_delta = 0;
     ctl.last_dcount = 0;
+    ctl.xbits = 0;
+    ctl.dec.restricted = 0;
     ctl.stop = 0;
   }
   __syncthreads();
@@ -1510,7 +1619,7 @@ __device__ void relay_main(const ActionParams &p) {
     if (lane == 0) ((volatile long long *)p.counters)[23] = ((long long)kind << 32) | seq;  // last forwarded record
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     long long tr1 = clock64();
-    if (!(p.topm && kind == DK_SCAN)) relay_reduce(p, kind, seq);
+    if (!((p.topm && kind == DK_SCAN) || kind == DK_TOPK)) relay_reduce(p, kind, seq);
     long long tr2 = clock64();
     acc_fwd += tr1 - tr0;
     acc_red += tr2 - tr1;

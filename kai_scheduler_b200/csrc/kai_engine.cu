@@ -24,6 +24,7 @@
 #include "kai_kernels.cuh"  // single translation unit: kernels + host API
 #include "kai_action.cuh"
 #include "kai_host_seq.cuh"
+#include "kai_solver.cuh"
 
 using namespace kai;
 
@@ -124,6 +125,9 @@ struct kai_engine {
   DevSnap hs;  // DevSnap whose pointers address the host mirror (the pinned staging buffer)
   std::vector<unsigned char> hot_host;
   std::vector<int> rank_to_node_h;
+  // solver actions: second NodeInfo.PodInfos entry of a task (evicted from A, pipelined to B), mirror of the GPU column
+  std::vector<int> on_other_node, on_other_status;
+  std::vector<double> h_ig, h_lg;
   size_t dev_only_begin = 0, dev_only_bytes = 0;
   std::vector<int> task_perm;
   std::vector<int32_t> r_tmp_node, r_tmp_status;
@@ -674,6 +678,8 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->r_idle.assign(RN, 0);
   e->r_rel.assign(RN, 0);
   e->r_visits.clear();
+  e->on_other_node.clear();
+  e->on_other_status.clear();
   e->loaded = true;
   return KAI_OK;
 }
@@ -737,7 +743,8 @@ int kai_engine_fair_share(kai_engine *e, kai_result *out) {
 int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (!e || !out) return KAI_ERR_INVALID;
   if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
-  if (action != KAI_ACTION_ALLOCATE) return e->fail(KAI_ERR_UNSUPPORTED, "action not implemented on device yet");
+  const bool solver_action = action == KAI_ACTION_RECLAIM || action == KAI_ACTION_CONSOLIDATION;
+  if (action != KAI_ACTION_ALLOCATE && !solver_action) return e->fail(KAI_ERR_UNSUPPORTED, "unknown action");
   if (e->cfg.shard_count > 1 && !e->shm_base) return e->fail(KAI_ERR_STATE, "multi-GPU: call kai_engine_wire_peers first");
   CK(cudaSetDevice(e->device));
   ActionParams p;
@@ -768,6 +775,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   const char *mode_env = getenv("KAI_SEQUENCER");
   const bool host_mode = !(mode_env && strcmp(mode_env, "device") == 0);
   if (!host_mode && e->cfg.shard_count > 1) return e->fail(KAI_ERR_UNSUPPORTED, "device-resident sequencer is single-GPU");
+  if (solver_action && (!host_mode || e->cfg.shard_count > 1))
+    return e->fail(KAI_ERR_UNSUPPORTED, "reclaim / consolidation run host-sequenced on one GPU");
   p.mode = host_mode ? 1 : 0;
   p.spin_log2 = host_mode ? 26 : 22;
   if (host_mode) {
@@ -794,6 +803,14 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     // host mirror of everything the open-session / prepare kernels produced
     CK(cudaMemcpyAsync(e->stage.host + e->dev_only_begin, e->dsnap.base + e->dev_only_begin, e->dev_only_bytes,
                        cudaMemcpyDeviceToHost, e->stream));
+    if (solver_action) {  // GPU column of Idle / Releasing as the previous action left it (point look-ups on the host)
+      e->h_ig.resize(e->N);
+      e->h_lg.resize(e->N);
+      if (e->N > 0) {
+        CK(cudaMemcpyAsync(e->h_ig.data(), e->ds.idle + (size_t)KAI_RES_GPU * e->N, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_lg.data(), e->ds.rel + (size_t)KAI_RES_GPU * e->N, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
+      }
+    }
     cudaEventRecord(e->ev_mirror, e->stream);
     CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
     cudaEventRecord(e->ev[3], e->stream);
@@ -889,8 +906,54 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     ctl.dec.task = -1;
     ctl.ctx_job = ctl.ctx_ps = -1;
     ctl.seq = p.seq0;
-    hb.run_allocate();
+    long long solver_scenarios = 0, solver_topk = 0;
+    if (!solver_action) {
+      hb.run_allocate();
+    } else if (!p.topm) {
+      hb.publish(DK_DONE);
+      CK(cudaStreamSynchronize(e->stream));
+      return e->fail(KAI_ERR_UNSUPPORTED, "reclaim / consolidation need the top-M list transport (KAI_NO_TOPM / KAI_NO_BATCHING unset)");
+    } else {
+      const int T = e->T;
+      if ((int)e->on_other_node.size() != T) {
+        e->on_other_node.assign(T, -1);
+        e->on_other_status.assign(T, 0);
+      }
+      std::vector<int> n0(T), s0(T);
+      for (int t = 0; t < T; t++) {
+        bool on = (hs.t_status[t] & kActiveUsed) && hs.t_node[t] >= 0;
+        n0[t] = on ? hs.t_node[t] : -1;
+        s0[t] = hs.t_node_status[t];
+      }
+      double t_begin = HostBackend::now();
+      Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status, e->h_ig, e->h_lg);
+      if (action == KAI_ACTION_RECLAIM)
+        solver.run_reclaim();
+      else
+        solver.run_consolidation();
+      hb.publish(DK_DONE);
+      hb.t_total = HostBackend::now() - t_begin;
+      solver_scenarios = solver.scenarios;
+      solver_topk = solver.topk_sweeps;
+      // one status per task for the allocate path: the entry on the task's current node; the other entry persists
+      for (int t = 0; t < T; t++) {
+        int cur = hs.t_node[t];
+        if (n0[t] >= 0 && n0[t] != cur && e->on_other_node[t] == cur) {
+          std::swap(n0[t], e->on_other_node[t]);
+          std::swap(s0[t], e->on_other_status[t]);
+        }
+        if (n0[t] >= 0 && n0[t] == cur)
+          hs.t_node_status[t] = s0[t];
+        else if (n0[t] >= 0 && e->on_other_node[t] < 0) {  // only a stale entry on another node: keep it as "other"
+          e->on_other_node[t] = n0[t];
+          e->on_other_status[t] = s0[t];
+        }
+      }
+    }
     CK(cudaStreamSynchronize(e->stream));
+    if (solver_action && getenv("KAI_PROFILE"))
+      fprintf(stderr, "[kai] solver: %lld scenarios simulated, %lld node sweeps, %lld top-k sweeps, %lld minmax exchanges\n",
+              solver_scenarios, seq.sweeps, solver_topk, seq.minmax_exchanges);
     {
       long long cd[48];
       CK(cudaMemcpy(cd, e->counters, sizeof(cd), cudaMemcpyDeviceToHost));

@@ -212,12 +212,14 @@ struct HostBackend {
         }
     // the cut row itself was reported (it IS the last reported row of that scanner): it may be used, rows after it not
     list_pos = 0;
+    list_more = have_cut;
     list_tag = tag;
     ctl.seq = seq_no + 1;
     ctl.n_delta = 0;
     ctl.batch.valid = 0;
   }
   unsigned int list_tag = 0;
+  bool list_more = false;  // some scanner has more qualifying rows than it reported
   bool list_available() const { return list_pos < list_valid && list[list_pos].used < list[list_pos].cap; }
   void list_invalidate() {
     list_pos = list_valid = 0;

@@ -117,6 +117,7 @@ struct Decision {
   double req[KAI_MAX_RES];
   double mn, mx;
   int task, res, strategy, gpu_task, pipeline_only, nominated, pred_class, best_effort;
+  int restricted;  // sweep only the rows of the current feasible-node set (solver simulations)
 };
 
 // tracker event bits per resource (gpu bits 0-2, cpu bits 3-5)
@@ -135,13 +136,18 @@ struct Batch {  // same-node batching state
   unsigned long long fl;  // 6 tracker-event bits per repeat
 };
 
-enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4 };
+enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4, DK_TOPK = 5 };
+// extra record bits (word 0 bits 48..63).  XB_SNAP_*: after the deltas of the record, every scanner recomputes the
+// feasible-set bit of its rows (common.FeasibleNodesForJob: all nodes / nodes with idle or releasing GPUs).
+enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4 };
+constexpr uint32_t kTileFeas = 1u << 30;  // tile flag bit: row belongs to the feasible-node set
 enum { DB_GPU_TASK = 1, DB_BEST_EFFORT = 2, DB_PIPELINE_ONLY = 4, DB_BATCHING = 8, DB_DIRTY0 = 16, DB_DIRTY1 = 32 };
 
 struct Ctl {  // sequencer control block (shared memory of CTA 0), written by lane 0
   int job, n_items, job_ok, item_ok, need_minmax, use_batch, stop;
   unsigned int seq;  // sequence number of the next decision record
   int n_delta;       // node deltas queued for the next record
+  unsigned int xbits;  // XB_* bits of the next record
   unsigned int last_dkey;  // last queued delta: rank | code << 28, its first task and its repeat count
   int last_dtask, last_dcount;
   Decision dec;
@@ -233,7 +239,8 @@ KAI_HD inline bool should_allocate(const Seq &q, int t, bool real) {  // pod_inf
 }
 
 // ---- node mutations (node_info.go:457-551) are queued as deltas for the scanner that owns the node ----
-enum { ND_ADD = 0, ND_ADD_PIPELINED = 1, ND_ADD_RELEASING = 2, ND_REM = 3, ND_REM_PIPELINED = 4, ND_REM_RELEASING = 5 };
+enum { ND_ADD = 0, ND_ADD_PIPELINED = 1, ND_ADD_RELEASING = 2, ND_REM = 3, ND_REM_PIPELINED = 4, ND_REM_RELEASING = 5,
+       ND_FEAS_SET = 6, ND_FEAS_CLR = 7 };  // 6, 7: feasible-set membership of the row (no task attached)
 KAI_HD void seq_flush_deltas(Seq &q);  // FLUSH exchange when the delta list is full (backend specific)
 // Every delta word is written exactly once (readers validate it by its tag only): the newest entry stays pending in
 // the control block, so that consecutive deltas of the same kind on the same row with bit-identical requests can be
@@ -251,7 +258,7 @@ KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
   // the delta names the node by its NAME RANK: that is what decides which scanner owns the row
   const unsigned int key = (unsigned int)(kldg(&q.s->name_rank[node]) | (code << 28));
-  if (c.n_delta > 0 && c.last_dcount > 0 && c.last_dkey == key && c.last_dcount < 255) {
+  if (code < ND_FEAS_SET && c.n_delta > 0 && c.last_dcount > 0 && c.last_dkey == key && c.last_dcount < 255) {
     const int R = q.s->R;
     const double *a = q.s->t_req + (size_t)c.last_dtask * R, *b = q.s->t_req + (size_t)t * R;
     bool same = true;
@@ -873,7 +880,8 @@ KAI_HD void build_decision_words(Ctl &c, int kind, int batching) {
                             (d.pipeline_only ? DB_PIPELINE_ONLY : 0) | (batching ? DB_BATCHING : 0) |
                             (c.trk[0].dirty ? DB_DIRTY0 : 0) | (c.trk[1].dirty ? DB_DIRTY1 : 0);
   c.dw[0] = (unsigned long long)kind | ((unsigned long long)d.res << 8) | ((unsigned long long)d.strategy << 16) |
-            (bits << 24) | ((unsigned long long)c.n_delta << 32);
+            (bits << 24) | ((unsigned long long)c.n_delta << 32) |
+            ((unsigned long long)((c.xbits & 0xfffeu) | (d.restricted ? XB_RESTRICT : 0u)) << 48);
   c.dw[1] = (unsigned long long)(unsigned int)d.nominated | ((unsigned long long)(unsigned int)d.pred_class << 32);
   for (int r = 0; r < KAI_MAX_RES; r++) c.dw[2 + r] = kbits(d.req[r]);
   for (int k = 0; k < 2; k++) {

@@ -54,6 +54,30 @@ def test_allocate_tables_gpu(cid, case):
     assert not errs, f"{case['source']} #{case['index']}: {errs}"
 
 
+SOLVER = action_cases(["reclaim__"], single_action="reclaim") + action_cases(["consolidation__"], single_action="consolidation")
+
+
+@pytest.mark.parametrize("cid,case", SOLVER, ids=[c[0] for c in SOLVER])
+def test_solver_tables_gpu(cid, case):
+    """reclaim / consolidation: victim sets, moved victims and preemptor bindings against the oracle AND the
+    reference's expectations (65 + 24 tables)."""
+    snap, meta = dsl.build_snapshot(case["topology"])
+    re_, ro = run_both(snap, action=case["actions"][0])
+    assert_same(re_, ro)
+    assert re_.pods_evicted == ro.pods_evicted
+    errs = dsl.check_expectations(case["topology"], meta, re_, snap)
+    assert not errs, f"{case['source']} #{case['index']}: {errs}"
+
+
+@pytest.mark.parametrize("grid", ["2", "5", "148"])
+def test_solver_tables_forced_grid(grid, monkeypatch):
+    monkeypatch.setenv("KAI_GRID_EXACT", grid)
+    for cid, case in SOLVER:
+        snap, meta = dsl.build_snapshot(case["topology"])
+        re_, ro = run_both(snap, action=case["actions"][0])
+        assert_same(re_, ro)
+
+
 @pytest.mark.parametrize("grid,mode", [("2", "host"), ("3", "device"), ("148", "host"), ("148", "device")])
 def test_allocate_tables_forced_grid(grid, mode, monkeypatch):
     """Same tables with forced CTA counts (including scanners that own no node), both sequencer modes."""
