@@ -92,7 +92,7 @@ def dist_env():
     return rank, world, local
 
 
-def run_reference(args, snap, workload):
+def run_reference(args, snap, workload, actions=("allocate",)):
     """--impl reference: CPU oracle with all host threads on the same config/metric."""
     from oracle_lib import Oracle
     rank, world, _ = dist_env()
@@ -104,11 +104,14 @@ def run_reference(args, snap, workload):
     for i in range(args.warmup + args.steps):
         o.load(snap)
         t0 = time.perf_counter()
-        res = o.run("allocate")
+        moved = 0
+        for a in actions:
+            res = o.run(a)
+            moved += res.pods_placed + res.pods_evicted
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
-            placed += res.pods_placed
+            placed += moved
     total = sum(times)
     value = placed / total
     line = {
@@ -130,25 +133,33 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--config", default="config2", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--config", default="config2", choices=sorted(synthetic.CONFIG_ACTIONS))
     ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "off"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = dist_env()
 
-    kw = synthetic.CONFIGS[args.config]
-    snap = synthetic.benchmark_snapshot(**kw)
+    actions = synthetic.CONFIG_ACTIONS[args.config]
+    snap = synthetic.config_snapshot(args.config)
+    if args.config in synthetic.CONFIGS:
+        kw = synthetic.CONFIGS[args.config]
+        desc = (f"{args.config}: {kw['n_nodes']} nodes x {kw['n_jobs']} jobs x {kw.get('tasks_per_job', 1)} pods, "
+                f"{kw.get('n_queues', 4)} leaf queues, binpack, allocate action")
+    else:
+        kw = synthetic.RECLAIM_CONFIGS[args.config]
+        desc = (f"{args.config}: {snap.n_nodes} nodes x 8 GPUs, {int((snap.task_status == abi.POD_RUNNING).sum())} running 1-GPU pods "
+                f"in over-quota queues, {int((snap.task_status == abi.POD_PENDING).sum())} pending reclaimer pods; actions {'+'.join(actions)}"
+                " (pods = placed + evicted)")
     workload = {
-        "workload": f"{args.config}: {kw['n_nodes']} nodes x {kw['n_jobs']} jobs x {kw.get('tasks_per_job', 1)} pods, "
-                    f"{kw.get('n_queues', 4)} leaf queues, binpack, allocate action",
-        "nodes": kw["n_nodes"], "pods": kw["n_jobs"] * kw.get("tasks_per_job", 1), "queues": kw.get("n_queues", 4),
+        "workload": desc,
+        "nodes": snap.n_nodes, "pods": int(snap.task_status.shape[0]), "queues": int(snap.queue_parent.shape[0]),
         "parallelism": f"nodes sharded by range over {args.gpus} GPUs, one sequencer replica per rank" if args.gpus > 1 else "1 GPU",
         "sequencer": os.environ.get("KAI_SEQUENCER", "host"),
         "l2_policy": "node tables are re-uploaded (H2D) before every timed step, which replaces the L2-resident copy; "
                      "the action kernel then keeps its node tiles in shared memory",
     }
     if args.impl == "reference":
-        run_reference(args, snap, workload)
+        run_reference(args, snap, workload, actions)
         return
 
     import torch
@@ -178,10 +189,18 @@ def main():
         """returns (device_ms, e2e_s, pods, stats)"""
         t0 = time.perf_counter()
         eng.load_c(c_snap, snap.n_res)       # H2D of the whole snapshot + open-session kernels
-        r = eng.run("allocate", copy=False)  # action kernel + D2H of the results
+        dev, moved, launches_, alg_, act_ = 0.0, 0, 0, 0, 0.0
+        for a in actions:
+            r = eng.run(a, copy=False)       # action kernel + D2H of the results
+            st = eng.stats()
+            dev += st.action_ms
+            moved += int(r.pods_placed) + int(r.pods_evicted)
+            launches_ = int(st.kernel_launches)
+            alg_ += int(st.algorithmic_bytes)
+            act_ += st.action_ms
         e2e = time.perf_counter() - t0
-        st = eng.stats()
-        return st.open_session_ms + st.action_ms, e2e, int(r.pods_placed), st, r
+        st.kernel_launches, st.algorithmic_bytes, st.action_ms = launches_, alg_, act_
+        return st.open_session_ms + dev, e2e, moved, st, r
 
     for _ in range(max(args.warmup, 3) if args.steps > 0 else 0):
         one_step()
@@ -235,10 +254,15 @@ def main():
             o = Oracle(threads=1)
             o.load(snap)
             t0 = time.perf_counter()
-            ro = o.run("allocate")
+            moved = 0
+            for a in actions:
+                ro = o.run(a)
+                moved += ro.pods_placed + ro.pods_evicted
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": ro.pods_placed / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"one full {args.config} allocate cycle, scalar oracle, {dt:.2f} s",
+            if args.config in synthetic.REFERENCE_PUBLISHED_MS:
+                line["reference_published_ms_per_op"] = synthetic.REFERENCE_PUBLISHED_MS[args.config]
+            line["cpu_baseline"] = {"value": moved / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"one full {args.config} cycle ({'+'.join(actions)}), scalar oracle, {dt:.2f} s",
                                     "host_cores_available": os.cpu_count()}
         print(json.dumps(line))
     eng.close()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KAI_ABI_VERSION 1
+#define KAI_ABI_VERSION 2
 #define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
 #define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
 #define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
@@ -109,6 +109,11 @@ typedef struct kai_config {
      snapshot; the exchange buffer is wired with kai_engine_wire_peers(). */
   int32_t shard_rank;
   int32_t shard_count;
+  /* SchedulerParams.UseSchedulingSignatures (cmd/scheduler/app/options/options.go:120; production default true, the
+     reference's action tests run with false): reclaim / consolidation skip jobs that are "not easier to schedule" than
+     a job with the same kai_snapshot.job_signature that already failed (actions/common/minimal_job_comparison.go). */
+  int32_t use_scheduling_signatures;
+  int32_t reserved0;
 } kai_config;
 
 /*
@@ -170,6 +175,10 @@ typedef struct kai_snapshot {
   /* ---- host-evaluated predicates (k8s Filters, node conditions, MIG rules):
          bit n of row c set = node n passes for predicate class c ---- */
   const uint32_t *pred_mask; /* [n_pred_classes][(N+31)/32] */
+
+  /* ---- PodGroupInfo.GetSchedulingConstraintsSignature (job_info.go:547-570) as a class id: jobs with equal
+         signatures get equal ids; -1 = unique.  NULL = all -1. ---- */
+  const int32_t *job_signature; /* [J] */
 } kai_snapshot;
 
 /* One entry per job popped by an action, in visiting order. */

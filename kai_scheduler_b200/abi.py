@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-KAI_ABI_VERSION = 1
+KAI_ABI_VERSION = 2
 KAI_MAX_RES = 8
 KAI_QRES = 3
 RES_CPU, RES_MEM, RES_GPU, RES_PODS = 0, 1, 2, 3
@@ -54,6 +54,8 @@ class KaiConfig(C.Structure):
         ("allow_consolidating_reclaim", C.c_int32),
         ("shard_rank", C.c_int32),
         ("shard_count", C.c_int32),
+        ("use_scheduling_signatures", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -71,6 +73,7 @@ class KaiSnapshot(C.Structure):
         ("task_status", _ip), ("task_node", _ip), ("task_req", _dp), ("task_order_rank", _ip),
         ("task_nominated", _ip), ("task_pred_class", _ip),
         ("pred_mask", _up),
+        ("job_signature", _ip),
     ]
 
 
@@ -99,9 +102,11 @@ class KaiStats(C.Structure):
 
 def make_config(device: int = 0, gpu_placement: int = PLACEMENT_BINPACK, cpu_placement: int = PLACEMENT_BINPACK,
                 k_value: float = 1.0, saturation_multiplier: float = 1.0, max_consolidation_preemptees: int = -1,
-                allow_consolidating_reclaim: bool = True, shard_rank: int = 0, shard_count: int = 1) -> KaiConfig:
+                allow_consolidating_reclaim: bool = True, shard_rank: int = 0, shard_count: int = 1,
+                use_scheduling_signatures: bool = False) -> KaiConfig:
     return KaiConfig(KAI_ABI_VERSION, device, gpu_placement, cpu_placement, k_value, saturation_multiplier,
-                     max_consolidation_preemptees, int(allow_consolidating_reclaim), shard_rank, shard_count)
+                     max_consolidation_preemptees, int(allow_consolidating_reclaim), shard_rank, shard_count,
+                     int(use_scheduling_signatures), 0)
 
 
 def _arr(a, dtype):
@@ -142,6 +147,7 @@ class Snapshot:
     task_nominated: np.ndarray | None = None
     task_pred_class: np.ndarray | None = None
     pred_mask: np.ndarray | None = None  # [C, ceil(N/32)] u32
+    job_signature: np.ndarray | None = None  # [J] i32 scheduling-constraints signature class, -1 = unique
     names: dict = field(default_factory=dict)  # optional: node/job/task/queue names for reporting
     _keep: list = field(default_factory=list, repr=False)
 
@@ -224,6 +230,7 @@ class Snapshot:
         s.task_nominated = p(self.task_nominated, np.int32, _ip)
         s.task_pred_class = p(self.task_pred_class, np.int32, _ip)
         s.pred_mask = p(self.pred_mask, np.uint32, _up)
+        s.job_signature = p(self.job_signature, np.int32, _ip)
         self._keep = keep
         return s
 

@@ -1065,6 +1065,68 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
     if (kind == DK_SCAN && p.topm) {
       // ---- top-M answer straight into host memory (no relay reduction) ----
+      if (sh.xbits & XB_FUSED_MM) {
+        // pack.go:66-86 over the current node set: local extremes -> device slots -> every scanner reduces all slots
+        double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
+        for (int ln = tid; ln < tile.count; ln += blockDim.x)
+          for (int k = 0; k < 2; k++) {
+            int res = k == 0 ? KAI_RES_GPU : KAI_RES_CPU;
+            double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
+            if (overall == 0) continue;
+            if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
+            double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
+            if (cur < mn[k]) mn[k] = cur;
+            if (cur > mx[k]) mx[k] = cur;
+          }
+        for (int k = 0; k < 2; k++)
+          for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+          }
+        if (lane == 0) {
+          sh_d[warp * 4 + 0] = mn[0];
+          sh_d[warp * 4 + 1] = mx[0];
+          sh_d[warp * 4 + 2] = mn[1];
+          sh_d[warp * 4 + 3] = mx[1];
+        }
+        __syncthreads();
+        unsigned long long *mmbase = p.mmbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
+        if (tid < 4) {
+          double v = tid & 1 ? 0.0 : DBL_MAX;
+          for (int w = 0; w < nw; w++) v = tid & 1 ? fmax(v, sh_d[w * 4 + tid]) : fmin(v, sh_d[w * 4 + tid]);
+          st_relaxed_b128(mmbase + (size_t)my * kSlotWords + 2 * tid, (unsigned long long)__double_as_longlong(v),
+                          (unsigned long long)seq);
+        }
+        __syncthreads();
+        double g[4] = {DBL_MAX, 0.0, DBL_MAX, 0.0};
+        for (int c = tid; c < p.grid - 1; c += blockDim.x)
+          for (int i = 0; i < 4; i++) {
+            unsigned long long lo, hi;
+            Spin spin;
+            do {
+              ld_relaxed_b128(mmbase + (size_t)c * kSlotWords + 2 * i, lo, hi);
+            } while (hi != (unsigned long long)seq && !spin.expired(p, 14, seq, c));
+            double v = __longlong_as_double((long long)lo);
+            g[i] = i & 1 ? fmax(g[i], v) : fmin(g[i], v);
+          }
+        for (int i = 0; i < 4; i++)
+          for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, g[i], o);
+            g[i] = i & 1 ? fmax(g[i], ov) : fmin(g[i], ov);
+          }
+        if (lane == 0)
+          for (int i = 0; i < 4; i++) sh_d[16 + warp * 4 + i] = g[i];
+        __syncthreads();
+        if (tid == 0) {
+          for (int w = 1; w < nw; w++)
+            for (int i = 0; i < 4; i++)
+              g[i] = i & 1 ? fmax(g[i], sh_d[16 + w * 4 + i]) : fmin(g[i], sh_d[16 + w * 4 + i]);
+          const int k = sh.dec.res == KAI_RES_GPU ? 0 : 1;
+          sh.dec.mn = g[2 * k];
+          sh.dec.mx = g[2 * k + 1];
+        }
+        __syncthreads();
+      }
       if (tid == 0) sh.fit_count = 0;
       __syncthreads();
       for (int m = 0; m < kTopM; m++) {
@@ -1643,7 +1705,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
   __shared__ Seq seq;
   __shared__ ScanShared scan_sh;
   __shared__ Cand sh_warp[kThreads / 32];
-  __shared__ double sh_d[(kThreads / 32) * 4];
+  __shared__ double sh_d[(kThreads / 32) * 8];
   __shared__ int sh_i[(kThreads / 32) * 4];
   if (blockIdx.x == 0) {
     if (p.mode != 0)

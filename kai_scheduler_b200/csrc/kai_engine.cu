@@ -128,6 +128,7 @@ struct kai_engine {
   // solver actions: second NodeInfo.PodInfos entry of a task (evicted from A, pipelined to B), mirror of the GPU column
   std::vector<int> on_other_node, on_other_status;
   std::vector<double> h_ig, h_lg;
+  std::vector<int> job_signature;
   size_t dev_only_begin = 0, dev_only_bytes = 0;
   std::vector<int> task_perm;
   std::vector<int32_t> r_tmp_node, r_tmp_status;
@@ -680,6 +681,8 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->r_visits.clear();
   e->on_other_node.clear();
   e->on_other_status.clear();
+  e->job_signature.clear();
+  if (s->job_signature) e->job_signature.assign(s->job_signature, s->job_signature + s->n_jobs);
   e->loaded = true;
   return KAI_OK;
 }
@@ -927,6 +930,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       }
       double t_begin = HostBackend::now();
       Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status, e->h_ig, e->h_lg);
+      solver.use_signatures = e->cfg.use_scheduling_signatures != 0;
+      solver.job_signature = e->job_signature.empty() ? nullptr : e->job_signature.data();
       if (action == KAI_ACTION_RECLAIM)
         solver.run_reclaim();
       else

@@ -139,7 +139,9 @@ struct Batch {  // same-node batching state
 enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4, DK_TOPK = 5 };
 // extra record bits (word 0 bits 48..63).  XB_SNAP_*: after the deltas of the record, every scanner recomputes the
 // feasible-set bit of its rows (common.FeasibleNodesForJob: all nodes / nodes with idle or releasing GPUs).
-enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4 };
+// XB_FUSED_MM: the scanners exchange their local binpack min/max among themselves (device slots) before scoring, so a
+// sweep over a changed node set needs no separate MINMAX round trip through the host.
+enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4, XB_FUSED_MM = 8 };
 constexpr uint32_t kTileFeas = 1u << 30;  // tile flag bit: row belongs to the feasible-node set
 enum { DB_GPU_TASK = 1, DB_BEST_EFFORT = 2, DB_PIPELINE_ONLY = 4, DB_BATCHING = 8, DB_DIRTY0 = 16, DB_DIRTY1 = 32 };
 

@@ -492,14 +492,11 @@ struct Solver {
     d.restricted = 1;
     d.task = t;
     ctl.batch.valid = 0;
-    if (d.strategy == KAI_PLACEMENT_BINPACK) {  // pack.go:66-86 over the node set of this simulation
-      ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
-      seq.minmax_exchanges++;
-      hb.publish(DK_MINMAX);
-      hb.gather_minmax();
-      if (hb.failed) return -1;
-    }
+    // pack.go:66-86 over the node set of this simulation: the scanners exchange their extremes among themselves
+    ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
+    ctl.xbits = d.strategy == KAI_PLACEMENT_BINPACK ? XB_FUSED_MM : 0;
     hb.publish(DK_SCAN);
+    ctl.xbits = 0;
     hb.gather_list();
     sweeps++;
     seq.sweeps++;

@@ -113,6 +113,75 @@ def benchmark_snapshot(n_nodes: int, n_jobs: int, tasks_per_job: int = 1, n_queu
         task_order_rank=task_order_rank)
 
 
+def reclaim_snapshot(n_nodes: int, running_per_node: int = 8, gpus_per_node: int = 8, victim_queues: int = 1,
+                     reclaimer_jobs: int = 1, reclaimer_tasks: int | None = None, reclaimer_gpus: float = 8.0,
+                     node_prefix: str = "node") -> abi.Snapshot:
+    """Victim-selection workloads.
+
+    Defaults = buildReclaimTopology of BenchmarkReclaimLargeJobs_<N>Node
+    (pkg/scheduler/actions/integration_tests/reclaim/reclaim_benchmark_test.go:66-147): N nodes x 8 GPUs, N*8 running
+    1-GPU Train jobs (job i on node i % N) in queue-0 (deserved 0, over-quota weight 0), one pending "very-large-job"
+    of N/10 tasks x 8 GPUs in queue-1 (deserved all GPUs); no departments => the DSL's `default` department.
+    `victim_queues` / `reclaimer_jobs` widen it towards BASELINE config 5 (running pods in several over-quota
+    queues, many pending reclaimers).
+    """
+    R = 4
+    N = n_nodes
+    alloc = np.empty((R, N), dtype=np.float64)
+    alloc[0], alloc[1], alloc[2], alloc[3] = 2e7, 2e10, float(gpus_per_node), 110.0
+    name_rank = _name_rank(node_prefix, N)
+    flags = np.full(N, abi.NODE_READY, dtype=np.uint32)
+    n_run = N * running_per_node
+    if reclaimer_tasks is None:
+        reclaimer_tasks = max(1, N // 10)
+    # queues: victim queues first, then the reclaimer queue, then the default department
+    nq = victim_queues + 1
+    Q = nq + 1
+    parent = np.array([nq] * nq + [-1], dtype=np.int32)
+    prio = np.full(Q, 100, dtype=np.int32)
+    creation = np.concatenate([np.arange(nq) * 60, [0]]).astype(np.int64)
+    qnames = np.array([f"queue-{i}" for i in range(nq)] + ["default"], dtype=object)
+    uid_rank = np.empty(Q, dtype=np.int32)
+    uid_rank[np.argsort(qnames, kind="stable")] = np.arange(Q, dtype=np.int32)
+    deserved = np.full((3, Q), -1.0)
+    limit = np.full((3, Q), -1.0)
+    oqw = np.ones((3, Q))
+    deserved[2, :victim_queues] = 0.0
+    deserved[2, victim_queues] = float(N * gpus_per_node)
+    oqw[2, :nq] = 0.0
+    deserved[2, nq] = -1.0   # default department: DeservedGPUs -1, OverQuotaWeight = DeservedGPUs
+    oqw[2, nq] = -1.0
+
+    J = n_run + reclaimer_jobs
+    T = n_run + reclaimer_jobs * reclaimer_tasks
+    job_queue = np.concatenate([np.arange(n_run) % victim_queues, np.full(reclaimer_jobs, victim_queues)]).astype(np.int32)
+    job_prio = np.full(J, 50, dtype=np.int32)
+    job_order_rank = np.arange(J, dtype=np.int32)
+    job_flags = np.full(J, abi.JOB_PREEMPTIBLE, dtype=np.uint32)
+    job_podset_begin = np.arange(J + 1, dtype=np.int32)
+    podset_min = np.concatenate([np.ones(n_run), np.full(reclaimer_jobs, reclaimer_tasks)]).astype(np.int32)
+    podset_task_begin = np.concatenate([np.arange(n_run), n_run + np.arange(reclaimer_jobs + 1) * reclaimer_tasks]).astype(np.int32)
+    task_status = np.concatenate([np.full(n_run, abi.POD_RUNNING), np.full(T - n_run, abi.POD_PENDING)]).astype(np.int32)
+    task_node = np.concatenate([np.arange(n_run) % N, np.full(T - n_run, -1)]).astype(np.int32)
+    req = np.empty((T, R), dtype=np.float64)
+    req[:, 0], req[:, 1], req[:, 3] = 1000.0, 1e9, 1.0
+    req[:n_run, 2] = 1.0
+    req[n_run:, 2] = reclaimer_gpus
+    task_order_rank = np.concatenate([np.zeros(n_run), np.tile(_name_rank("", reclaimer_tasks), reclaimer_jobs)]).astype(np.int32)
+    idle = alloc.copy()
+    for r in range(R):
+        np.subtract.at(idle[r], task_node[:n_run], req[:n_run, r])
+    rel = np.zeros((R, N), dtype=np.float64)
+    return abi.Snapshot(
+        n_res=R, node_allocatable=alloc, node_idle=idle, node_releasing=rel, node_name_rank=name_rank,
+        node_flags=flags, queue_parent=parent, queue_priority=prio, queue_creation=creation,
+        queue_uid_rank=uid_rank, queue_deserved=deserved, queue_limit=limit, queue_oqw=oqw,
+        job_queue=job_queue, job_priority=job_prio, job_order_rank=job_order_rank, job_flags=job_flags,
+        job_podset_begin=job_podset_begin, podset_min_available=podset_min,
+        podset_task_begin=podset_task_begin, task_status=task_status, task_node=task_node, task_req=req,
+        task_order_rank=task_order_rank)
+
+
 # The BASELINE.json configs (SURVEY.md §8d)
 CONFIGS = {
     # name: kwargs
@@ -121,7 +190,21 @@ CONFIGS = {
     "config3": dict(n_nodes=50_000, n_jobs=50_000, tasks_per_job=4, n_queues=1000),
     "config3-mixed": dict(n_nodes=50_000, n_jobs=50_000, tasks_per_job=4, n_queues=1000, mixed=True),
 }
+# victim-selection workloads: BenchmarkReclaimLargeJobs_<N>Node (reference numbers in BASELINE.md) and a
+# config-5-shaped full cycle (running pods in over-quota queues + pending reclaimers)
+RECLAIM_CONFIGS = {
+    **{f"reclaim-large-{n}": dict(n_nodes=n) for n in (10, 50, 100, 200, 500, 1000)},
+    "cycle5-small": dict(n_nodes=200, running_per_node=8, victim_queues=4, reclaimer_jobs=100, reclaimer_tasks=2,
+                         reclaimer_gpus=4.0),
+}
+CONFIG_ACTIONS = {**{k: ["allocate"] for k in CONFIGS}, **{k: ["reclaim"] for k in RECLAIM_CONFIGS},
+                  "cycle5-small": ["allocate", "consolidation", "reclaim"]}
+# ms/op the reference publishes for BenchmarkReclaimLargeJobs (other hardware, includes BuildSession)
+REFERENCE_PUBLISHED_MS = {"reclaim-large-10": 104.4, "reclaim-large-50": 130.2, "reclaim-large-100": 241.2,
+                          "reclaim-large-200": 816.0, "reclaim-large-500": 8970.0}
 
 
 def config_snapshot(name: str) -> abi.Snapshot:
+    if name in RECLAIM_CONFIGS:
+        return reclaim_snapshot(**RECLAIM_CONFIGS[name])
     return benchmark_snapshot(**CONFIGS[name])

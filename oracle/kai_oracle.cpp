@@ -2213,6 +2213,7 @@ int kai_oracle_create(const kai_config *cfg, kai_oracle **out) {
   if (!cfg || !out || cfg->abi_version != KAI_ABI_VERSION) return KAI_ERR_INVALID;
   kai_oracle *o = new kai_oracle();
   o->cfg = *cfg;
+  o->use_signatures = cfg->use_scheduling_signatures != 0;
   memset(&o->stats, 0, sizeof(o->stats));
   *out = o;
   return KAI_OK;
@@ -2274,6 +2275,7 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
     jb.priority = s->job_priority[j];
     jb.order_rank = s->job_order_rank[j];
     jb.preemptible = (s->job_flags[j] & KAI_JOB_PREEMPTIBLE) != 0;
+    jb.signature = s->job_signature ? s->job_signature[j] : -1;
     for (int ps = s->job_podset_begin[j]; ps < s->job_podset_begin[j + 1]; ps++) {
       jb.podsets.push_back(ps);
       o->PS[ps].job = j;

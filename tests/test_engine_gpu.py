@@ -69,6 +69,47 @@ def test_solver_tables_gpu(cid, case):
     assert not errs, f"{case['source']} #{case['index']}: {errs}"
 
 
+@pytest.mark.parametrize("kw", [
+    dict(n_nodes=10), dict(n_nodes=50), dict(n_nodes=100),          # BenchmarkReclaimLargeJobs_{10,50,100}Node
+    dict(n_nodes=40, victim_queues=3, reclaimer_jobs=6, reclaimer_tasks=2, reclaimer_gpus=4.0),  # config-5 shape
+    dict(n_nodes=64, running_per_node=6, victim_queues=2, reclaimer_jobs=20, reclaimer_tasks=1, reclaimer_gpus=2.0),
+])
+@pytest.mark.parametrize("action", ["reclaim", "consolidation"])
+def test_solver_synthetic(kw, action):
+    snap = synthetic.reclaim_snapshot(**kw)
+    re_, ro = run_both(snap, action=action)
+    assert_same(re_, ro)
+    assert re_.pods_evicted == ro.pods_evicted
+
+
+@pytest.mark.parametrize("action", ["reclaim", "consolidation"])
+def test_solver_scheduling_signatures(action):
+    """UseSchedulingSignatures = true (production default): jobs not easier than a failed representative are skipped."""
+    snap = synthetic.reclaim_snapshot(n_nodes=24, running_per_node=8, victim_queues=2, reclaimer_jobs=30,
+                                      reclaimer_tasks=2, reclaimer_gpus=5.0)
+    snap.job_signature = np.where(snap.job_queue == 2, 7, -1).astype(np.int32)
+    cfg = abi.make_config(use_scheduling_signatures=True)
+    re_, ro = run_both(snap, action=action, cfg=cfg)
+    assert_same(re_, ro)
+    re2, _ = run_both(snap, action=action)
+    assert len(re_.visits) <= len(re2.visits)
+
+
+def test_full_cycle_allocate_consolidation_reclaim():
+    """One scheduling cycle: the three actions in the default order on ONE session (state carries over)."""
+    snap = synthetic.reclaim_snapshot(n_nodes=48, running_per_node=7, victim_queues=2, reclaimer_jobs=12,
+                                      reclaimer_tasks=2, reclaimer_gpus=3.0)
+    e = Engine()
+    e.load(snap)
+    o = Oracle()
+    o.load(snap)
+    for action in ("allocate", "consolidation", "reclaim"):
+        re_, ro = e.run(action), o.run(action)
+        assert_same(re_, ro)
+        assert re_.pods_evicted == ro.pods_evicted
+    e.close()
+
+
 @pytest.mark.parametrize("grid", ["2", "5", "148"])
 def test_solver_tables_forced_grid(grid, monkeypatch):
     monkeypatch.setenv("KAI_GRID_EXACT", grid)
