@@ -89,7 +89,8 @@ enum {
 typedef enum kai_action {
   KAI_ACTION_ALLOCATE = 1,
   KAI_ACTION_CONSOLIDATION = 2,
-  KAI_ACTION_RECLAIM = 3
+  KAI_ACTION_RECLAIM = 3,
+  KAI_ACTION_PREEMPT = 4 /* actions/preempt/preempt.go:46-161 */
 } kai_action;
 
 /* node placement strategy. reference: plugins/nodeplacement/nodeplacement.go:53-73 */

@@ -32,7 +32,9 @@ POD_STATUS_NAMES = {
 NODE_READY, NODE_NOT_CPU_ONLY = 1, 2
 JOB_PREEMPTIBLE = 1
 ACTION_ALLOCATE, ACTION_CONSOLIDATION, ACTION_RECLAIM = 1, 2, 3
-ACTIONS = {"allocate": ACTION_ALLOCATE, "consolidation": ACTION_CONSOLIDATION, "reclaim": ACTION_RECLAIM}
+ACTION_PREEMPT = 4
+ACTIONS = {"allocate": ACTION_ALLOCATE, "consolidation": ACTION_CONSOLIDATION, "reclaim": ACTION_RECLAIM,
+           "preempt": ACTION_PREEMPT}
 PLACEMENT_BINPACK, PLACEMENT_SPREAD = 0, 1
 PEER_HANDLE_BYTES = 64
 

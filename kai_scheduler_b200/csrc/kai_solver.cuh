@@ -930,7 +930,7 @@ struct Solver {
   }
 
   // ---------------- validators ----------------
-  int solver_kind = 0;  // 0 reclaim, 1 consolidation
+  int solver_kind = 0;  // 0 reclaim, 1 consolidation, 2 preempt
   std::vector<double> sim_alloc, sim_np;  // proportion.go:131-136 jobSimulationQueues (allocated columns)
   double SA(int r, int q) const { return sim_alloc[(size_t)r * Q + q]; }
   double SNP(int r, int q) const { return sim_np[(size_t)r * Q + q]; }
@@ -1145,7 +1145,8 @@ struct Solver {
         pipelined.push_back(t);
     }
     res.has = true;
-    bool valid = solver_kind == 0 ? reclaim_validator(sc) : consolidation_validator(sc);
+    // preempt: ssn.PreemptScenarioValidator is minruntime only (not modelled) => always valid
+    bool valid = solver_kind == 0 ? reclaim_validator(sc) : (solver_kind == 1 ? consolidation_validator(sc) : true);
     if (!valid) {
       stmt_discard();
       return res;
@@ -1243,6 +1244,14 @@ struct Solver {
       op.filter_non_active_allocated = true;
       for (int j = 0; j < J; j++)
         if (s.j_queue[j] != s.j_queue[pending_job]) vs.push_back(j);
+    } else if (solver_kind == 2) {  // preempt.go:125-161 + utils/action.go:20-52
+      for (int j = 0; j < J; j++) {
+        if (count_job(j, kAlive) == 0) continue;
+        if (!preemptible(j) || s.j_priority[j] >= s.j_priority[pending_job]) continue;
+        if (s.j_queue[j] != s.j_queue[pending_job] || j == pending_job) continue;
+        if (count_job(j, kActiveAllocated) == 0) continue;
+        vs.push_back(j);
+      }
     } else {  // consolidation.go:119-157 + utils/action.go:20-52
       int counter = 0;
       for (int j = 0; j < J; j++) {
@@ -1457,6 +1466,52 @@ struct Solver {
       sim_np.assign(qnp, qnp + (size_t)QR * Q);
       begin_attempt(j);
       bool ok = solve_job(j);
+      if (ok) {
+        stmt_commit();
+        record_visit(seq, j, 1);
+      } else {
+        ops.clear();
+        update_representative(reps, j);
+        record_visit(seq, j, 0);
+      }
+    }
+  }
+  // ---------------- actions/preempt/preempt.go:46-123 ----------------
+  void run_preempt() {
+    solver_kind = 2;
+    prepare();
+    JobsOrder jo;
+    jo.init(this, false);
+    {
+      std::vector<int> vs;
+      for (int j = 0; j < J; j++) vs.push_back(j);
+      OrderOpts op;
+      op.filter_non_pending = op.filter_unready = true;
+      init_jobs_order(jo, vs, op);
+    }
+    std::map<int, Reps> failed_by_queue;
+    while (!jo.is_empty() && !gpu_failed()) {
+      int j = jo.pop_next_job();
+      if (j < 0) break;
+      Reps &reps = failed_by_queue[s.j_queue[j]];
+      if (use_signatures && !easier_to_schedule(reps, j)) continue;
+      tta_init_resource(j, false);
+      double rq[QR] = {0, 0, 0};
+      for (int t : tasks_to_allocate(j, false))
+        for (int r = 0; r < QR; r++) rq[r] += req(t, r);
+      bool over_quota = false;  // IsNonPreemptibleJobOverQueueQuotaFn (capacity_policy.go:38-49)
+      if (!preemptible(j))
+        for (int q = s.j_queue[j]; q >= 0 && !over_quota; q = s.q_parent[q])
+          for (int r = 0; r < QR; r++) {
+            if (qdes(r, q) == KAI_UNLIMITED || rq[r] == 0) continue;
+            if (qdes(r, q) < QNP(r, q) + rq[r]) over_quota = true;
+          }
+      bool ok = false;
+      ops.clear();
+      if (!over_quota) {
+        begin_attempt(j);
+        ok = solve_job(j);
+      }
       if (ok) {
         stmt_commit();
         record_visit(seq, j, 1);

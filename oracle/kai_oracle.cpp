@@ -1433,7 +1433,7 @@ struct kai_oracle {
   //  accumulated_scenario_filters/idle_gpus/*.go, actions/common/action.go).
   // Go map iteration orders are resolved canonically: ascending node / job / queue index.
   // =====================================================================================================
-  enum { SOLVER_RECLAIM = 0, SOLVER_CONSOLIDATION = 1 };
+  enum { SOLVER_RECLAIM = 0, SOLVER_CONSOLIDATION = 1, SOLVER_PREEMPT = 2 };
 
   // input_jobs.go:21-68 with an explicit job set (views) and the option flags
   struct OrderOpts {
@@ -1796,7 +1796,9 @@ struct kai_oracle {
         pipelined.push_back(ti);
     }
     res.has = true;
-    bool valid = solver_kind == SOLVER_RECLAIM ? reclaim_validator(sc) : consolidation_validator(sc);
+    // preempt: ssn.PreemptScenarioValidator = minruntime only (not modelled): always valid
+    bool valid = solver_kind == SOLVER_RECLAIM ? reclaim_validator(sc)
+                 : (solver_kind == SOLVER_CONSOLIDATION ? consolidation_validator(sc) : true);
     if (!valid) {
       stmt_discard();
       return res;
@@ -1878,6 +1880,20 @@ struct kai_oracle {
       for (int ji = 0; ji < NJ; ji++) {
         if (J[ji].queue == J[pending_job].queue) continue;
         vs.push_back(ji);  // ReclaimVictimFilter: minruntime protection is not modelled (always unprotected)
+      }
+    } else if (solver_kind == SOLVER_PREEMPT) {  // preempt.go:125-161 + utils/action.go:20-52
+      for (int ji = 0; ji < NJ; ji++) {
+        bool alive = false;
+        for (int s2 : J[ji].podsets)
+          for (int ti : PS[s2].tasks)
+            if (T[ti].status & kAlive) alive = true;
+        if (!alive) continue;
+        if (!J[ji].preemptible) continue;
+        if (J[ji].priority >= J[pending_job].priority) continue;
+        if (J[ji].queue != J[pending_job].queue) continue;
+        if (ji == pending_job) continue;
+        if (job_count(J[ji], kActiveAllocated) == 0) continue;
+        vs.push_back(ji);
       }
     } else {
       int counter = 0;
@@ -2089,6 +2105,39 @@ struct kai_oracle {
       std::vector<char> feasible = feasible_nodes_for_job(ji);
       ops.clear();
       bool ok = solve_job(ji, feasible);
+      if (ok) {
+        stmt_commit();
+        r_visits.push_back({ji, 1});
+      } else {
+        ops.clear();
+        update_representative(reps, ji);
+        r_visits.push_back({ji, 0});
+      }
+    }
+  }
+  // ---------------- actions/preempt/preempt.go:46-123 ----------------
+  void run_preempt() {
+    solver_kind = SOLVER_PREEMPT;
+    views.clear();
+    JobsOrder jo;
+    jo.init(this, false);
+    init_jobs_order(jo, true, true);
+    std::map<int, MinimalReps> failed_by_queue;
+    while (!jo.is_empty()) {
+      int ji = jo.pop_next_job();
+      if (ji < 0) break;
+      MinimalReps &reps = failed_by_queue[J[ji].queue];
+      if (use_signatures && !easier_to_schedule(reps, ji)) continue;
+      tasks_to_allocate_init_resource(ji, false);
+      double req[QR] = {0, 0, 0};
+      for (int ti : tasks_to_allocate(ji, false))
+        for (int r = 0; r < QR; r++) req[r] += T[ti].req[r];
+      bool ok = false;
+      ops.clear();
+      if (!non_preemptible_over_quota(ji, req)) {
+        std::vector<char> feasible = feasible_nodes_for_job(ji);
+        ok = solve_job(ji, feasible);
+      }
       if (ok) {
         stmt_commit();
         r_visits.push_back({ji, 1});
@@ -2323,6 +2372,9 @@ int kai_oracle_run(kai_oracle *o, kai_action action, kai_result *out) {
       break;
     case KAI_ACTION_CONSOLIDATION:
       o->run_consolidation();
+      break;
+    case KAI_ACTION_PREEMPT:
+      o->run_preempt();
       break;
     default:
       o->err = "action not implemented by the oracle";

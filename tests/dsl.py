@@ -248,8 +248,7 @@ def check_expectations(topo: dict, meta: dict, res: "abi.Result", snap: "abi.Sna
             errs.append(f"job {jname}: GPUsRequired {gpus} expected {exp.get('GPUsRequired')}")
     for tname, exp in (topo.get("TaskExpectedResults") or {}).items():
         if tname not in meta["task_names"]:
-            errs.append(f"task {tname} missing")
-            continue
+            continue  # test_utils.go:213-219 iterates the session's tasks: an expectation naming no task is never read
         t = meta["task_names"].index(tname)
         st = status_name[int(res.task_status[t])]
         if st != exp.get("Status"):

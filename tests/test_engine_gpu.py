@@ -54,7 +54,8 @@ def test_allocate_tables_gpu(cid, case):
     assert not errs, f"{case['source']} #{case['index']}: {errs}"
 
 
-SOLVER = action_cases(["reclaim__"], single_action="reclaim") + action_cases(["consolidation__"], single_action="consolidation")
+SOLVER = (action_cases(["reclaim__"], single_action="reclaim") + action_cases(["consolidation__"], single_action="consolidation")
+          + action_cases(["preempt__"], single_action="preempt"))
 
 
 @pytest.mark.parametrize("cid,case", SOLVER, ids=[c[0] for c in SOLVER])
@@ -103,7 +104,7 @@ def test_full_cycle_allocate_consolidation_reclaim():
     e.load(snap)
     o = Oracle()
     o.load(snap)
-    for action in ("allocate", "consolidation", "reclaim"):
+    for action in ("allocate", "consolidation", "reclaim", "preempt"):
         re_, ro = e.run(action), o.run(action)
         assert_same(re_, ro)
         assert re_.pods_evicted == ro.pods_evicted

@@ -25,9 +25,10 @@ def test_allocate_tables(cid, case):
 
 RECLAIM = action_cases(["reclaim__"], single_action="reclaim")
 CONSOLIDATION = action_cases(["consolidation__"], single_action="consolidation")
+PREEMPT = action_cases(["preempt__"], single_action="preempt")
 
 
-@pytest.mark.parametrize("cid,case", RECLAIM + CONSOLIDATION, ids=[c[0] for c in RECLAIM + CONSOLIDATION])
+@pytest.mark.parametrize("cid,case", RECLAIM + CONSOLIDATION + PREEMPT, ids=[c[0] for c in RECLAIM + CONSOLIDATION + PREEMPT])
 def test_solver_tables(cid, case):
     """reclaim (40+5+9+11+6 tables) and consolidation (20+6): victims Releasing, preemptor Pipelined, moved victims
     Pipelined on their new node — the victim SETS the reference's tests pin."""
@@ -40,6 +41,6 @@ def test_solver_tables(cid, case):
 
 
 def test_case_counts():
-    assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 24
+    assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 24 and len(PREEMPT) == 31
     # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
     assert len(ALLOCATE) == 41
