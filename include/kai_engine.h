@@ -90,7 +90,8 @@ typedef enum kai_action {
   KAI_ACTION_ALLOCATE = 1,
   KAI_ACTION_CONSOLIDATION = 2,
   KAI_ACTION_RECLAIM = 3,
-  KAI_ACTION_PREEMPT = 4 /* actions/preempt/preempt.go:46-161 */
+  KAI_ACTION_PREEMPT = 4,           /* actions/preempt/preempt.go:46-161 */
+  KAI_ACTION_STALEGANGEVICTION = 5  /* actions/stalegangeviction/stalegangeviction.go:29-95 */
 } kai_action;
 
 /* node placement strategy. reference: plugins/nodeplacement/nodeplacement.go:53-73 */
@@ -114,7 +115,10 @@ typedef struct kai_config {
      reference's action tests run with false): reclaim / consolidation skip jobs that are "not easier to schedule" than
      a job with the same kai_snapshot.job_signature that already failed (actions/common/minimal_job_comparison.go). */
   int32_t use_scheduling_signatures;
-  int32_t reserved0;
+  /* SchedulerParams.GlobalDefaultStalenessGracePeriod in seconds: < 0 = stale gangs are never evicted, 0 = evicted in
+     the cycle that finds them stale (the reference's tests); > 0 needs per-job staleness timestamps, which the
+     snapshot does not carry: treated as "not yet". */
+  int32_t staleness_grace_period_s;
 } kai_config;
 
 /*

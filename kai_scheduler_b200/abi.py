@@ -33,8 +33,9 @@ NODE_READY, NODE_NOT_CPU_ONLY = 1, 2
 JOB_PREEMPTIBLE = 1
 ACTION_ALLOCATE, ACTION_CONSOLIDATION, ACTION_RECLAIM = 1, 2, 3
 ACTION_PREEMPT = 4
+ACTION_STALEGANGEVICTION = 5
 ACTIONS = {"allocate": ACTION_ALLOCATE, "consolidation": ACTION_CONSOLIDATION, "reclaim": ACTION_RECLAIM,
-           "preempt": ACTION_PREEMPT}
+           "preempt": ACTION_PREEMPT, "stalegangeviction": ACTION_STALEGANGEVICTION}
 PLACEMENT_BINPACK, PLACEMENT_SPREAD = 0, 1
 PEER_HANDLE_BYTES = 64
 
@@ -57,7 +58,7 @@ class KaiConfig(C.Structure):
         ("shard_rank", C.c_int32),
         ("shard_count", C.c_int32),
         ("use_scheduling_signatures", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("staleness_grace_period_s", C.c_int32),
     ]
 
 
@@ -105,10 +106,10 @@ class KaiStats(C.Structure):
 def make_config(device: int = 0, gpu_placement: int = PLACEMENT_BINPACK, cpu_placement: int = PLACEMENT_BINPACK,
                 k_value: float = 1.0, saturation_multiplier: float = 1.0, max_consolidation_preemptees: int = -1,
                 allow_consolidating_reclaim: bool = True, shard_rank: int = 0, shard_count: int = 1,
-                use_scheduling_signatures: bool = False) -> KaiConfig:
+                use_scheduling_signatures: bool = False, staleness_grace_period_s: int = 0) -> KaiConfig:
     return KaiConfig(KAI_ABI_VERSION, device, gpu_placement, cpu_placement, k_value, saturation_multiplier,
                      max_consolidation_preemptees, int(allow_consolidating_reclaim), shard_rank, shard_count,
-                     int(use_scheduling_signatures), 0)
+                     int(use_scheduling_signatures), staleness_grace_period_s)
 
 
 def _arr(a, dtype):

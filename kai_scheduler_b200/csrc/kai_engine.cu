@@ -746,7 +746,8 @@ int kai_engine_fair_share(kai_engine *e, kai_result *out) {
 int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (!e || !out) return KAI_ERR_INVALID;
   if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
-  const bool solver_action = action == KAI_ACTION_RECLAIM || action == KAI_ACTION_CONSOLIDATION || action == KAI_ACTION_PREEMPT;
+  const bool solver_action = action == KAI_ACTION_RECLAIM || action == KAI_ACTION_CONSOLIDATION || action == KAI_ACTION_PREEMPT ||
+                             action == KAI_ACTION_STALEGANGEVICTION;
   if (action != KAI_ACTION_ALLOCATE && !solver_action) return e->fail(KAI_ERR_UNSUPPORTED, "unknown action");
   if (e->cfg.shard_count > 1 && !e->shm_base) return e->fail(KAI_ERR_STATE, "multi-GPU: call kai_engine_wire_peers first");
   CK(cudaSetDevice(e->device));
@@ -936,6 +937,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         solver.run_reclaim();
       else if (action == KAI_ACTION_PREEMPT)
         solver.run_preempt();
+      else if (action == KAI_ACTION_STALEGANGEVICTION)
+        solver.run_stale_gang_eviction();
       else
         solver.run_consolidation();
       hb.publish(DK_DONE);

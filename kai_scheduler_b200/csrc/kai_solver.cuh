@@ -1476,6 +1476,28 @@ struct Solver {
       }
     }
   }
+  // ---------------- actions/stalegangeviction/stalegangeviction.go:29-95 ----------------
+  void run_stale_gang_eviction() {
+    prepare();
+    if (cfg.staleness_grace_period_s != 0) return;
+    for (int j = 0; j < J && !gpu_failed(); j++) {
+      if (count_job(j, KAI_POD_SUCCEEDED) > 0 || count_job(j, kActiveUsed) == 0) continue;  // job_info.go:417-432
+      bool stale = false;
+      for (int ps = ps_begin(j); ps < ps_end(j); ps++)
+        if (count_ps(ps, kActiveUsed) < s.ps_min[ps]) stale = true;
+      if (!stale) continue;
+      for (int ps = ps_begin(j); ps < ps_end(j); ps++)
+        for (int t = pst_begin(ps); t < pst_end(ps); t++) {
+          if (!(st[t] & kActiveAllocated)) continue;
+          set_status(t, KAI_POD_RELEASING);  // framework/session.go:127-150 Session.Evict
+          node_remove_task(t, tn[t]);
+          node_add_task(t);
+          queue_allocate(t, false);
+          seq.pods_evicted++;
+        }
+      record_visit(seq, j, 1);
+    }
+  }
   // ---------------- actions/preempt/preempt.go:46-123 ----------------
   void run_preempt() {
     solver_kind = 2;

@@ -2115,6 +2115,30 @@ struct kai_oracle {
       }
     }
   }
+  // ---------------- actions/stalegangeviction/stalegangeviction.go:29-95 ----------------
+  void run_stale_gang_eviction() {
+    if (cfg.staleness_grace_period_s != 0) return;  // < 0: never; > 0: needs staleness timestamps (not in the snapshot)
+    for (int ji = 0; ji < NJ; ji++) {
+      const Job &j = J[ji];
+      if (job_count(j, KAI_POD_SUCCEEDED) > 0) continue;  // job_info.go:417-432 IsStale
+      if (job_count(j, kActiveUsed) == 0) continue;
+      bool stale = false;
+      for (int s2 : j.podsets)
+        if (podset_count(PS[s2], kActiveUsed) < PS[s2].min_available) stale = true;
+      if (!stale) continue;
+      for (int s2 : j.podsets)
+        for (int ti : PS[s2].tasks) {
+          if (!(T[ti].status & kActiveAllocated)) continue;
+          // framework/session.go:127-150 Session.Evict: Releasing on the same node, deallocate handlers
+          set_status(ti, KAI_POD_RELEASING);
+          node_remove_task(ti, T[ti].node);
+          node_add_task(ti);
+          queue_allocate(ti, -1);
+          pods_evicted++;
+        }
+      r_visits.push_back({ji, 1});
+    }
+  }
   // ---------------- actions/preempt/preempt.go:46-123 ----------------
   void run_preempt() {
     solver_kind = SOLVER_PREEMPT;
@@ -2375,6 +2399,9 @@ int kai_oracle_run(kai_oracle *o, kai_action action, kai_result *out) {
       break;
     case KAI_ACTION_PREEMPT:
       o->run_preempt();
+      break;
+    case KAI_ACTION_STALEGANGEVICTION:
+      o->run_stale_gang_eviction();
       break;
     default:
       o->err = "action not implemented by the oracle";

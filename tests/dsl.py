@@ -264,3 +264,68 @@ def check_expectations(topo: dict, meta: dict, res: "abi.Result", snap: "abi.Sna
         if res.node_releasing[2, n] != float(exp.get("ReleasingGPUs", 0) or 0):
             errs.append(f"node {nname}: releasing GPUs {res.node_releasing[2, n]} expected {exp.get('ReleasingGPUs')}")
     return errs
+
+
+# ---------------- multi-round integration harness (integration_tests_utils.go:41-140) ----------------
+class _SnapshotAsResult:
+    """MatchExpectedAndRealTasks on a freshly built session (prepareSessionForMatch): the snapshot itself."""
+
+    def __init__(self, snap):
+        self.task_status = snap.task_status
+        self.task_node = snap.task_node
+        self.node_idle = snap.node_idle
+        self.node_releasing = snap.node_releasing
+
+
+def _carry_over(topo: dict, meta: dict, res):
+    """runSchedulerOneRound's write-back of the session into the test topology (:96-125)."""
+    status_name = {v: k for k, v in abi.POD_STATUS_NAMES.items()}
+    jobs = {j["Name"]: j for j in topo["Jobs"]}
+    for t, tname in enumerate(meta["task_names"]):
+        jname, k = tname.rsplit("-", 1)
+        job = jobs[jname]
+        task = job["Tasks"][int(k)]
+        st = status_name[int(res.task_status[t])]
+        node = meta["node_names"][res.task_node[t]] if res.task_node[t] >= 0 else (task.get("NodeName") or "")
+        if st == "Releasing":
+            if job.get("DeleteJobInTest"):
+                task["NodeName"], task["State"] = node, "Releasing"
+            else:
+                task["NodeName"], task["State"] = "", "Pending"
+        elif st == "Pipelined":
+            task["NodeName"], task["State"] = "", "Pending"
+        elif st == "Binding":
+            task["NodeName"], task["State"] = node, "Running"
+        else:
+            task["NodeName"], task["State"] = node, st
+
+
+def run_integration_case(case: dict, make_runner):
+    """make_runner() -> object with load(snap) / run(action).  Returns the list of mismatches."""
+    import copy
+    topo = copy.deepcopy(case["topology"])
+    for j in topo["Jobs"]:
+        j["Tasks"] = [dict(t or {}) for t in j["Tasks"]]
+    until = case.get("rounds_until_match") or 2
+    after = case.get("rounds_after_match") or 5
+
+    def one_round():
+        snap, meta = build_snapshot(topo)
+        r = make_runner()
+        r.load(snap)
+        res = None
+        for a in case["actions"]:
+            res = r.run(a)
+        if hasattr(r, "close"):
+            r.close()
+        _carry_over(topo, meta, res)
+        return snap, meta, res
+
+    for _ in range(until):
+        one_round()
+    snap, meta = build_snapshot(topo)
+    errs = [f"after {until} rounds: {e}" for e in check_expectations(topo, meta, _SnapshotAsResult(snap), snap)]
+    for i in range(after):
+        snap, meta, res = one_round()
+        errs += [f"stability round {i}: {e}" for e in check_expectations(topo, meta, res, snap)]
+    return errs

@@ -70,6 +70,43 @@ def test_solver_tables_gpu(cid, case):
     assert not errs, f"{case['source']} #{case['index']}: {errs}"
 
 
+INTEGRATION = action_cases(["integration_tests__"])
+
+
+@pytest.mark.parametrize("cid,case", INTEGRATION, ids=[c[0] for c in INTEGRATION])
+def test_integration_tables_gpu(cid, case):
+    """The reference's multi-action, multi-round integration tables through the engine: allocate, consolidation,
+    reclaim, preempt, stalegangeviction on one session per round; expectations of the reference + every round's
+    final state equal to the oracle's."""
+    import copy
+    e_case, o_case = copy.deepcopy(case), copy.deepcopy(case)
+    seen = {"e": [], "o": []}
+
+    class Tap:
+        def __init__(self, inner, key):
+            self.inner, self.key = inner, key
+
+        def load(self, snap):
+            self.inner.load(snap)
+
+        def run(self, action):
+            r = self.inner.run(action)
+            seen[self.key].append((r.task_status.copy(), r.task_node.copy(), r.node_idle.copy(), r.queue_allocated.copy()))
+            return r
+
+        def close(self):
+            if hasattr(self.inner, "close"):
+                self.inner.close()
+
+    errs = dsl.run_integration_case(e_case, lambda: Tap(Engine(), "e"))
+    assert not errs, f"{case['source']} #{case['index']}: {errs[:3]}"
+    dsl.run_integration_case(o_case, lambda: Tap(Oracle(), "o"))
+    assert len(seen["e"]) == len(seen["o"])
+    for a, b in zip(seen["e"], seen["o"]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+
+
 @pytest.mark.parametrize("kw", [
     dict(n_nodes=10), dict(n_nodes=50), dict(n_nodes=100),          # BenchmarkReclaimLargeJobs_{10,50,100}Node
     dict(n_nodes=40, victim_queues=3, reclaimer_jobs=6, reclaimer_tasks=2, reclaimer_gpus=4.0),  # config-5 shape

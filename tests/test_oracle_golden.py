@@ -40,7 +40,19 @@ def test_solver_tables(cid, case):
     assert not errs, f"{case['source']} #{case['index']} {case['name']}: {errs}"
 
 
+INTEGRATION = action_cases(["integration_tests__"])
+
+
+@pytest.mark.parametrize("cid,case", INTEGRATION, ids=[c[0] for c in INTEGRATION])
+def test_integration_tables(cid, case):
+    """actions/integration_tests/**: allocate, consolidation, reclaim, preempt, stalegangeviction on a session that is
+    rebuilt every round from the previous round's outcome (integration_tests_utils.go:41-140)."""
+    errs = dsl.run_integration_case(case, lambda: Oracle())
+    assert not errs, f"{case['source']} #{case['index']} {case['name']}: {errs[:3]}"
+
+
 def test_case_counts():
+    assert len(INTEGRATION) == 58
     assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 24 and len(PREEMPT) == 31
     # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
     assert len(ALLOCATE) == 41
