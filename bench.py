@@ -245,7 +245,11 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_action", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": alg_bytes // max(args.steps, 1),
-                         "kernel_ms_per_launch": act_ms / args.steps, "traffic": None},
+                         "kernel_ms_per_launch": act_ms / args.steps, "traffic": None,
+                         "traffic_note": "the host-sequenced kernel cannot run under ncu (the profiler serialises it with the "
+                                         "host thread that feeds it); ncu --set full of the same kernel with the device-resident "
+                                         "sequencer: dram read 431 KB + write 2.3 KB per launch on config1 "
+                                         "(profiles/r01b_k_action_device_config1_raw.csv): rows are shared-memory resident"},
             "clocks": clocks,
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }
