@@ -1063,9 +1063,8 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     const int kind = sh.kind;
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
-    if (kind == DK_SCAN && p.topm) {
-      // ---- top-M answer straight into host memory (no relay reduction) ----
-      if (sh.xbits & XB_FUSED_MM) {
+    if (kind == DK_SCAN && (sh.xbits & XB_FUSED_MM)) {
+      {
         // pack.go:66-86 over the current node set: local extremes -> device slots -> every scanner reduces all slots
         double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
         for (int ln = tid; ln < tile.count; ln += blockDim.x)
@@ -1127,6 +1126,9 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         }
         __syncthreads();
       }
+    }
+    if (kind == DK_SCAN && p.topm && !(sh.xbits & XB_SINGLE)) {
+      // ---- top-M answer straight into host memory (no relay reduction) ----
       if (tid == 0) sh.fit_count = 0;
       __syncthreads();
       for (int m = 0; m < kTopM; m++) {
@@ -1681,7 +1683,8 @@ __device__ void relay_main(const ActionParams &p) {
     if (lane == 0) ((volatile long long *)p.counters)[23] = ((long long)kind << 32) | seq;  // last forwarded record
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     long long tr1 = clock64();
-    if (!((p.topm && kind == DK_SCAN) || kind == DK_TOPK)) relay_reduce(p, kind, seq);
+    const unsigned int xb = (unsigned int)((w0 >> 48) & 0xffff);
+    if (!((p.topm && kind == DK_SCAN && !(xb & XB_SINGLE)) || kind == DK_TOPK)) relay_reduce(p, kind, seq);
     long long tr2 = clock64();
     acc_fwd += tr1 - tr0;
     acc_red += tr2 - tr1;

@@ -836,6 +836,11 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.h_list = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * 2 * kMaxGrid * kSlotWords : e->h_list;
     hb.n_list_scanners = e->cfg.shard_count * (e->grid - 1);
     hb.listed = 0;
+    hb.batch_is_single = false;
+    hb.list_yield_ema = 8.0;
+    hb.list_served = -1;
+    hb.single_streak = 0;
+    hb.single_sweeps = 0;
     hb.list_invalidate();
     hb.batching = p.batching;
     hb.failed = false;
@@ -943,6 +948,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         solver.run_consolidation();
       hb.publish(DK_DONE);
       hb.t_total = HostBackend::now() - t_begin;
+      if (getenv("KAI_PROFILE"))
+        fprintf(stderr, "[kai] solver host profile: %lld simulations; sweeps %.1f ms, simulation set-up %.1f ms, evicting recorded victims %.1f ms, victims queues %.1f ms\n",
+                solver.simulations, solver.t_sweeps * 1e3, solver.t_sim_setup * 1e3, solver.t_evict * 1e3, solver.t_victims_queue * 1e3);
       solver_scenarios = solver.scenarios;
       solver_topk = solver.topk_sweeps;
       // one status per task for the allocate path: the entry on the task's current node; the other entry persists
@@ -1020,6 +1028,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer: total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
               e->hb.t_total * 1e3, e->hb.t_exchange * 1e3, c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
+    if (host_mode) fprintf(stderr, "[kai] sweeps answered with a single row (XB_SINGLE): %lld\n", e->hb.single_sweeps);
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer rdtsc Mcycles: pop %.2f admit %.2f place(+sweeps) %.2f finish %.2f loop %.2f\n",
               e->hb.t_sec[0] / 1e6, e->hb.t_sec[1] / 1e6, e->hb.t_sec[2] / 1e6, e->hb.t_sec[3] / 1e6, e->hb.t_sec[4] / 1e6);

@@ -219,7 +219,17 @@ struct HostBackend {
     ctl.batch.valid = 0;
   }
   unsigned int list_tag = 0;
-  bool list_more = false;  // some scanner has more qualifying rows than it reported
+  bool list_more = false;
+  bool batch_is_single = false;  // ctl.batch comes from a single-winner answer (same-node repeats), not from a list
+  double list_yield_ema = 8.0;   // pods served per list, recent average
+  long long list_served = -1;
+  unsigned int single_streak = 0;
+  long long single_sweeps = 0;
+  void list_invalidate_keep_batch() {
+    list_pos = list_valid = 0;
+    list.clear();
+    single_sweeps++;
+  }  // some scanner has more qualifying rows than it reported
   bool list_available() const { return list_pos < list_valid && list[list_pos].used < list[list_pos].cap; }
   void list_invalidate() {
     list_pos = list_valid = 0;
@@ -270,6 +280,7 @@ struct HostBackend {
       stmt_pipeline(seq, t, lc.node, ctl.ctx_fresh != 0);
     lc.used++;
     listed++;
+    list_served++;
     ctl.item_ok = 1;
     if (scored_moved) {  // every other key was computed under the old min/max
       list_invalidate();
@@ -400,7 +411,7 @@ struct HostBackend {
             break;
           }
           if (ctl.use_batch) {
-            if (topm) {
+            if (topm && !batch_is_single) {
               if (apply_listed(t)) continue;
               ctl.batch.valid = 0;  // list ran dry between prepare and apply: fall through to a sweep
               ctl.use_batch = 0;
@@ -419,17 +430,30 @@ struct HostBackend {
             gather_minmax();
           }
           double tx = now();
+          // Lists pay off when one sweep serves many pods.  When the recent lists served ~1 pod each (a different
+          // request on almost every job) the sweep is asked to answer with the single best row instead (XB_SINGLE:
+          // one scan round, one reduced line); every 128th sweep probes the list form again.
+          bool as_list = topm != 0;
+          if (as_list && list_yield_ema < 1.5 && (++single_streak & 127) != 0) as_list = false;
+          ctl.xbits = (topm && !as_list) ? XB_SINGLE : 0;
           publish(DK_SCAN);
-          if (topm)
+          ctl.xbits = 0;
+          if (as_list) {
+            if (list_served >= 0) list_yield_ema = 0.75 * list_yield_ema + 0.25 * (double)list_served;
             gather_list();
-          else
+            list_served = 0;
+            batch_is_single = false;
+          } else {
             gather_candidates();
+            batch_is_single = true;
+            if (topm) list_invalidate_keep_batch();
+          }
           t_exchange += now() - tx;
           if (failed) {
             job_success = false;
             break;
           }
-          if (topm) {
+          if (as_list) {
             seq.sweeps++;
             seq.nodes_scanned += s.N;
             ctl.item_ok = 0;

@@ -141,7 +141,9 @@ enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4, DK_TOPK = 5 };
 // feasible-set bit of its rows (common.FeasibleNodesForJob: all nodes / nodes with idle or releasing GPUs).
 // XB_FUSED_MM: the scanners exchange their local binpack min/max among themselves (device slots) before scoring, so a
 // sweep over a changed node set needs no separate MINMAX round trip through the host.
-enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4, XB_FUSED_MM = 8 };
+// XB_SINGLE: answer this SCAN with the single best row through the relay's reduction (cheaper sweep when the
+// list would be used once: heterogeneous requests, solver simulations) instead of the top-M lists.
+enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4, XB_FUSED_MM = 8, XB_SINGLE = 16 };
 constexpr uint32_t kTileFeas = 1u << 30;  // tile flag bit: row belongs to the feasible-node set
 enum { DB_GPU_TASK = 1, DB_BEST_EFFORT = 2, DB_PIPELINE_ONLY = 4, DB_BATCHING = 8, DB_DIRTY0 = 16, DB_DIRTY1 = 32 };
 

@@ -21,6 +21,7 @@
 #include <cmath>
 #include <functional>
 #include <map>
+#include <set>
 #include <vector>
 
 #include "kai_host_seq.cuh"
@@ -101,7 +102,8 @@ struct Solver {
   };
   std::vector<SOp> ops;
 
-  long long sweeps = 0, scenarios = 0, topk_sweeps = 0;
+  long long sweeps = 0, scenarios = 0, topk_sweeps = 0, simulations = 0;
+  double t_sweeps = 0, t_sim_setup = 0, t_evict = 0, t_victims_queue = 0;
 
   Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1,
          std::vector<double> &ig, std::vector<double> &lg)
@@ -370,7 +372,7 @@ struct Solver {
     tn[t] = n;
     node_add_task(t);
     queue_allocate(t, true);
-    ops.push_back(op);
+    ops_push(op);
     tvirt[t] = 1;
   }
   void unpipeline(const SOp &op) {  // :432-476
@@ -388,7 +390,7 @@ struct Solver {
     node_remove_task(t, tn[t]);
     node_add_task(t);
     queue_allocate(t, false);
-    ops.push_back(op);
+    ops_push(op);
     tvirt[t] = 1;
   }
   void unevict(const SOp &op) {  // :156-195
@@ -402,10 +404,23 @@ struct Solver {
     tn[t] = keep;
     queue_allocate(t, true);
   }
-  bool op_valid(int i) const {  // :652-663
-    for (int u = 0; u < (int)ops.size(); u++)
-      if (ops[u].kind == OPK_UNDO && ops[u].undo_index == i) return !op_valid(u);
-    return true;
+  // :652-663 operationValid: decided by the FIRST undo operation that targets i (statement.go scans from the start
+  // and returns at the first match), kept here as an index instead of a scan
+  std::vector<int> first_undo;
+  bool op_valid(int i) const {
+    int u = i < (int)first_undo.size() ? first_undo[i] : -1;
+    return u < 0 ? true : !op_valid(u);
+  }
+  void ops_push(const SOp &op) {
+    ops.push_back(op);
+    first_undo.push_back(-1);
+    if (op.kind == OPK_UNDO && first_undo[op.undo_index] < 0) first_undo[op.undo_index] = (int)ops.size() - 1;
+  }
+  void ops_truncate(int n) {
+    for (int u = (int)ops.size() - 1; u >= n; u--)
+      if (ops[u].kind == OPK_UNDO && ops[u].undo_index < n && first_undo[ops[u].undo_index] == u) first_undo[ops[u].undo_index] = -1;
+    ops.resize(n);
+    first_undo.resize(n);
   }
   void undo_operation(int index) {  // :597-643
     if (!op_valid(index)) return;
@@ -416,7 +431,7 @@ struct Solver {
       case OPK_UNDO: redo_operation(op.undo_index); break;
       default: break;
     }
-    ops.push_back(SOp{OPK_UNDO, -1, 0, -1, -1, 0, index});
+    ops_push(SOp{OPK_UNDO, -1, 0, -1, -1, 0, index});
   }
   void redo_operation(int index) {
     SOp op = ops[index];
@@ -438,11 +453,11 @@ struct Solver {
   int stmt_checkpoint() const { return (int)ops.size(); }
   void stmt_rollback(int cp) {
     for (int i = (int)ops.size() - 1; i >= cp; i--) undo_operation(i);
-    ops.resize(cp);
+    ops_truncate(cp);
   }
   void stmt_discard() {
     for (int i = (int)ops.size() - 1; i >= 0; i--) undo_operation(i);
-    ops.clear();
+    ops_truncate(0);
   }
   void stmt_commit() {  // :536-571: pipelines keep Pipelined, evictions keep Releasing and stop being virtual
     for (int i = 0; i < (int)ops.size(); i++) {
@@ -454,7 +469,7 @@ struct Solver {
         tvirt[ops[i].task] = 0;
       }
     }
-    ops.clear();
+    ops_truncate(0);
   }
 
   // ---------------- capacity policy (proportion/capacity_policy) ----------------
@@ -494,15 +509,17 @@ struct Solver {
     ctl.batch.valid = 0;
     // pack.go:66-86 over the node set of this simulation: the scanners exchange their extremes among themselves
     ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
-    ctl.xbits = d.strategy == KAI_PLACEMENT_BINPACK ? XB_FUSED_MM : 0;
+    ctl.xbits = (d.strategy == KAI_PLACEMENT_BINPACK ? XB_FUSED_MM : 0) | XB_SINGLE;  // only the winner is needed
+    const double t0 = HostBackend::now();
     hb.publish(DK_SCAN);
     ctl.xbits = 0;
-    hb.gather_list();
+    hb.gather_candidates();
+    t_sweeps += HostBackend::now() - t0;
     sweeps++;
     seq.sweeps++;
     seq.nodes_scanned += N;
-    if (hb.failed || hb.list.empty()) return -1;
-    return hb.list[0].node;
+    if (hb.failed) return -1;
+    return ctl.win.node;
   }
   // the k rows with most idle + releasing GPUs (values, descending); pages of top-M lists until k are known
   std::vector<std::pair<double, int>> sweep_topk_idle(int k, unsigned int snap_bits) {
@@ -885,22 +902,35 @@ struct Solver {
   struct IdleFilter {
     int k = 0;
     std::map<int, double> value;  // nodes of the base top-k and nodes that received victims' GPUs
+    std::multiset<double, std::greater<double>> sorted;  // the same values, descending (incremental, like orderedInsert)
     std::vector<char> seen;       // per task
+    size_t n_rec_done = 0, n_pot_done = 0;
   };
   void idle_filter_account(IdleFilter &f, const Scenario &sc) {
+    // recorded victims never change within a builder and potential victims are append-only: only new entries
     for (const std::vector<int> *lst : {&sc.recorded_tasks, &sc.potential_tasks})
-      for (int t : *lst) {
+      for (size_t i = (lst == &sc.recorded_tasks ? f.n_rec_done : f.n_pot_done); i < lst->size(); i++) {
+        const int t = (*lst)[i];
         if (tn[t] < 0 || f.seen[t]) continue;
         f.seen[t] = 1;
         auto it = f.value.find(tn[t]);
-        if (it == f.value.end()) it = f.value.emplace(tn[t], start_Ig(tn[t]) + start_Lg(tn[t])).first;
+        if (it == f.value.end())
+          it = f.value.emplace(tn[t], start_Ig(tn[t]) + start_Lg(tn[t])).first;
+        else
+          f.sorted.erase(f.sorted.find(it->second));
         it->second += req(t, KAI_RES_GPU);
+        f.sorted.insert(it->second);
       }
+    f.n_rec_done = sc.recorded_tasks.size();
+    f.n_pot_done = sc.potential_tasks.size();
   }
   void idle_filter_init(IdleFilter &f, const Scenario &sc, unsigned int snap_bits) {
     f.k = (int)sc.pending_tasks.size();
     f.seen.assign(T, 0);
-    for (auto &kv : sweep_topk_idle(f.k, snap_bits)) f.value[kv.second] = kv.first;
+    for (auto &kv : sweep_topk_idle(f.k, snap_bits)) {
+      f.value[kv.second] = kv.first;
+      f.sorted.insert(kv.first);
+    }
     idle_filter_account(f, sc);
   }
   bool idle_filter_check(IdleFilter &f, const Scenario &sc) {
@@ -909,9 +939,7 @@ struct Solver {
     for (int t : sc.pending_tasks) rq.push_back(req(t, KAI_RES_GPU));
     std::sort(rq.begin(), rq.end(), std::greater<double>());
     std::vector<double> cap;
-    for (auto &kv : f.value) cap.push_back(kv.second);
-    std::sort(cap.begin(), cap.end(), std::greater<double>());
-    if ((int)cap.size() > f.k) cap.resize(f.k);
+    for (auto it = f.sorted.begin(); it != f.sorted.end() && (int)cap.size() < f.k; ++it) cap.push_back(*it);
     std::vector<double> used(cap.size(), 0.0);
     for (double required : rq) {
       if (required == 0) return true;
@@ -1099,6 +1127,8 @@ struct Solver {
   // ---------------- simulation (actions/common/action.go:67-122) ----------------
   bool try_virtually_allocate(const Scenario &sc, const std::vector<int> &victim_tasks) {
     const int pj = vjob(sc.preemptor);
+    simulations++;
+    const double t_setup0 = HostBackend::now();
     std::vector<char> is_victim_job(J, 0), in_set(J, 0);
     for (int j = 0; j < J; j++)
       if (count_job(j, KAI_POD_PENDING) > 0) in_set[j] = 1;
@@ -1113,6 +1143,7 @@ struct Solver {
     JobsOrder jo;
     jo.init(this, false);
     init_jobs_order(jo, vs, OrderOpts());
+    t_sim_setup += HostBackend::now() - t_setup0;
     bool preemptor_allocated = false;
     while (!jo.is_empty() && !gpu_failed()) {
       int v = jo.pop_next_job();
@@ -1199,8 +1230,12 @@ struct Solver {
   }
 
   SolveResult bypod_solve(Scenario &sc) {  // by_pod_solver.go:69-122,145-201
-    ops.clear();
-    for (int t : sc.recorded_tasks) stmt_evict(t);
+    ops_truncate(0);
+    {
+      const double t0 = HostBackend::now();
+      for (int t : sc.recorded_tasks) stmt_evict(t);
+      t_evict += HostBackend::now() - t0;
+    }
     if (sc.potential_tasks.empty()) {
       if (!sc.recorded_tasks.empty()) {
         SolveResult r = run_simulation(sc, sc.recorded_tasks);
@@ -1284,7 +1319,11 @@ struct Solver {
     std::vector<char> recorded_set(T, 0);
     for (int t : sc.recorded_tasks) recorded_set[t] = 1;
     JobsOrder victims_queue;
-    build_victims_queue(victims_queue, pending_job);
+    {
+      const double t0 = HostBackend::now();
+      build_victims_queue(victims_queue, pending_job);
+      t_victims_queue += HostBackend::now() - t0;
+    }
     IdleFilter filter;
     idle_filter_init(filter, sc, pending_snap_bits);
     pending_snap_bits = 0;
@@ -1366,7 +1405,7 @@ struct Solver {
     for (int ps = ps_begin(j); ps < ps_end(j); ps++)
       if (count_ps(ps, kActiveUsed) < s.ps_min[ps]) solved = false;
     if (original_active >= active) solved = false;
-    if (!have_statement) ops.clear();
+    if (!have_statement) ops_truncate(0);
     return solved;
   }
   // starts a job attempt: the next TOPK record snapshots FeasibleNodesForJob (feasible_nodes.go:11-26)
@@ -1435,7 +1474,7 @@ struct Solver {
   void prepare() {
     job_cache.assign(J, Cache());
     feas_extra.assign(N, 0);
-    ops.clear();
+    ops_truncate(0);
     free_ready = 0;  // once per action, from the mirror of the GPU column the action starts with
     for (int n = 0; n < N; n++)
       if (s.nflags[n] & KAI_NODE_READY) free_ready += hIg[n] + hLg[n];
@@ -1470,7 +1509,7 @@ struct Solver {
         stmt_commit();
         record_visit(seq, j, 1);
       } else {
-        ops.clear();
+        ops_truncate(0);
         update_representative(reps, j);
         record_visit(seq, j, 0);
       }
@@ -1529,7 +1568,7 @@ struct Solver {
             if (qdes(r, q) < QNP(r, q) + rq[r]) over_quota = true;
           }
       bool ok = false;
-      ops.clear();
+      ops_truncate(0);
       if (!over_quota) {
         begin_attempt(j);
         ok = solve_job(j);
@@ -1538,7 +1577,7 @@ struct Solver {
         stmt_commit();
         record_visit(seq, j, 1);
       } else {
-        ops.clear();
+        ops_truncate(0);
         update_representative(reps, j);
         record_visit(seq, j, 0);
       }
@@ -1568,7 +1607,7 @@ struct Solver {
       double sum = free_ready, want = 0;
       for (int t : tasks_to_allocate(j, false)) want += req(t, KAI_RES_GPU);
       bool ok = false;
-      ops.clear();
+      ops_truncate(0);
       if (sum >= want) {
         begin_attempt(j);
         ok = solve_job(j);
@@ -1577,7 +1616,7 @@ struct Solver {
         stmt_commit();
         record_visit(seq, j, 1);
       } else {
-        ops.clear();
+        ops_truncate(0);
         update_representative(reps, j);
         record_visit(seq, j, 0);
       }

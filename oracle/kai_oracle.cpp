@@ -23,6 +23,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -918,12 +919,24 @@ struct kai_oracle {
     queue_allocate(op.task, +1);
   }
   // :652-663 operationValid
-  bool op_valid(int i) {
-    for (int u = 0; u < (int)ops.size(); u++) {
-      if (ops[u].kind != Op::UNDO) continue;
-      if (ops[u].undo_index == i) return !op_valid(u);
+  // decided by the FIRST undo operation that targets i (the reference scans from the start and returns at the first
+  // match); the index is rebuilt lazily when the log changed since it was last used
+  std::vector<int> first_undo;
+  size_t first_undo_built = 0;
+  void sync_first_undo() {
+    if (first_undo_built > ops.size()) {
+      first_undo.assign(ops.size(), -1);
+      first_undo_built = 0;
     }
-    return true;
+    first_undo.resize(ops.size(), -1);
+    for (size_t u = first_undo_built; u < ops.size(); u++)
+      if (ops[u].kind == Op::UNDO && first_undo[ops[u].undo_index] < 0) first_undo[ops[u].undo_index] = (int)u;
+    first_undo_built = ops.size();
+  }
+  bool op_valid_rec(int i) const { return first_undo[i] < 0 ? true : !op_valid_rec(first_undo[i]); }
+  bool op_valid(int i) {
+    sync_first_undo();
+    return op_valid_rec(i);
   }
   // :597-643 undoOperation
   void undo_operation(int index) {
@@ -979,10 +992,12 @@ struct kai_oracle {
   void stmt_rollback(int cp) {                       // :48-61
     for (int i = (int)ops.size() - 1; i >= cp; i--) undo_operation(i);
     ops.resize(cp);
+    first_undo_built = (size_t)-1;
   }
   void stmt_discard() {  // :522-534
     for (int i = (int)ops.size() - 1; i >= 0; i--) undo_operation(i);
     ops.clear();
+    first_undo_built = (size_t)-1;
   }
   // :483-520 ConvertAllAllocatedToPipelined
   void stmt_convert_all_allocated_to_pipelined(int ji) {
@@ -998,6 +1013,7 @@ struct kai_oracle {
     for (auto &op : ops)
       if (!(op.kind == Op::ALLOCATE && T[op.task].job == ji)) keep.push_back(op);
     ops = keep;
+    first_undo_built = (size_t)-1;
   }
   // :536-571 Commit: allocate -> BindPod -> Binding (session.go:111-125); pipeline/evict keep their session status
   void stmt_commit() {
@@ -1016,6 +1032,7 @@ struct kai_oracle {
       }
     }
     ops.clear();
+    first_undo_built = (size_t)-1;
   }
 
   // ---------------- node ordering + fitting (framework/session.go:201-264,466-485) ----------------
@@ -1515,34 +1532,46 @@ struct kai_oracle {
   // accumulated victims), greedy first-fit of the pending tasks' GPU requests sorted descending
   struct IdleGpusFilter {
     std::vector<double> idle;  // per node
+    std::multiset<double, std::greater<double>> sorted;  // the same values, descending (the reference keeps its
+                                                          // top-k list incrementally: orderedInsert, idle_gpus.go:210-247)
     int k = 0;
+    size_t n_rec_done = 0, n_pot_done = 0;
     std::vector<char> seen;  // per task: already accounted as victim
     bool active = false;
   };
   void idle_filter_init(IdleGpusFilter &f, const Scenario &sc) {
     f.idle.assign(N, 0.0);
     for (int n = 0; n < N; n++) f.idle[n] = I(KAI_RES_GPU, n) + L(KAI_RES_GPU, n);
+    f.sorted.clear();
+    for (int n = 0; n < N; n++) f.sorted.insert(f.idle[n]);
     f.k = (int)sc.pending_tasks.size();
     f.seen.assign(NT, 0);
     f.active = true;
     idle_filter_update(f, sc);
   }
   void idle_filter_update(IdleGpusFilter &f, const Scenario &sc) {
+    // recorded victims never change within a builder and potential victims are append-only: only new entries
     for (const std::vector<int> *lst : {&sc.recorded_tasks, &sc.potential_tasks})
-      for (int ti : *lst) {
+      for (size_t i = (lst == &sc.recorded_tasks ? f.n_rec_done : f.n_pot_done); i < lst->size(); i++) {
+        int ti = (*lst)[i];
         if (T[ti].node < 0 || f.seen[ti]) continue;
         f.seen[ti] = 1;
-        if (N > 0) f.idle[T[ti].node] += T[ti].req[KAI_RES_GPU];
+        if (N > 0) {
+          f.sorted.erase(f.sorted.find(f.idle[T[ti].node]));
+          f.idle[T[ti].node] += T[ti].req[KAI_RES_GPU];
+          f.sorted.insert(f.idle[T[ti].node]);
+        }
       }
+    f.n_rec_done = sc.recorded_tasks.size();
+    f.n_pot_done = sc.potential_tasks.size();
   }
   bool idle_filter_check(IdleGpusFilter &f, const Scenario &sc) {
     idle_filter_update(f, sc);
     std::vector<double> req;
     for (int ti : sc.pending_tasks) req.push_back(T[ti].req[KAI_RES_GPU]);
     std::sort(req.begin(), req.end(), std::greater<double>());
-    std::vector<double> cap = f.idle;
-    std::sort(cap.begin(), cap.end(), std::greater<double>());
-    if ((int)cap.size() > f.k) cap.resize(f.k);
+    std::vector<double> cap;
+    for (auto it = f.sorted.begin(); it != f.sorted.end() && (int)cap.size() < f.k; ++it) cap.push_back(*it);
     std::vector<double> used(cap.size(), 0.0);
     for (double required : req) {  // common.go:34-64 greedyMatchRequirements
       if (required == 0) return true;
@@ -1830,7 +1859,8 @@ struct kai_oracle {
 
   // by_pod_solver.go:69-122,145-201 byPodSolver.solve
   SolveResult bypod_solve(Scenario &sc, std::vector<char> &feasible) {
-    ops.clear();  // session.Statement()
+    ops.clear();
+    first_undo_built = (size_t)-1;  // session.Statement()
     for (int ti : sc.recorded_tasks) stmt_evict(ti);
     if (sc.potential_tasks.empty()) {
       if (!sc.recorded_tasks.empty()) {
@@ -2021,7 +2051,10 @@ struct kai_oracle {
     for (int s2 : J[ji].podsets)  // IsGangSatisfied
       if (podset_count(PS[s2], kActiveUsed) < PS[s2].min_available) solved = false;
     if (original_active >= active) solved = false;
-    if (!have_statement) ops.clear();
+    if (!have_statement) {
+      ops.clear();
+      first_undo_built = (size_t)-1;
+    }
     return solved;
   }
   // actions/common/feasible_nodes.go:11-26
@@ -2104,12 +2137,14 @@ struct kai_oracle {
       sim_queues = Q;  // OnJobSolutionStart
       std::vector<char> feasible = feasible_nodes_for_job(ji);
       ops.clear();
+      first_undo_built = (size_t)-1;
       bool ok = solve_job(ji, feasible);
       if (ok) {
         stmt_commit();
         r_visits.push_back({ji, 1});
       } else {
         ops.clear();
+        first_undo_built = (size_t)-1;
         update_representative(reps, ji);
         r_visits.push_back({ji, 0});
       }
@@ -2158,6 +2193,7 @@ struct kai_oracle {
         for (int r = 0; r < QR; r++) req[r] += T[ti].req[r];
       bool ok = false;
       ops.clear();
+      first_undo_built = (size_t)-1;
       if (!non_preemptible_over_quota(ji, req)) {
         std::vector<char> feasible = feasible_nodes_for_job(ji);
         ok = solve_job(ji, feasible);
@@ -2167,6 +2203,7 @@ struct kai_oracle {
         r_visits.push_back({ji, 1});
       } else {
         ops.clear();
+        first_undo_built = (size_t)-1;
         update_representative(reps, ji);
         r_visits.push_back({ji, 0});
       }
@@ -2199,6 +2236,7 @@ struct kai_oracle {
       for (int ti : tasks_to_allocate(ji, false)) want += T[ti].req[KAI_RES_GPU];
       bool ok = false;
       ops.clear();
+      first_undo_built = (size_t)-1;
       if (sum >= want) {
         std::vector<char> feasible = feasible_nodes_for_job(ji);
         ok = solve_job(ji, feasible);
@@ -2208,6 +2246,7 @@ struct kai_oracle {
         r_visits.push_back({ji, 1});
       } else {
         ops.clear();
+        first_undo_built = (size_t)-1;
         update_representative(reps, ji);
         r_visits.push_back({ji, 0});
       }
@@ -2223,6 +2262,7 @@ struct kai_oracle {
       int ji = jo.pop_next_job();
       if (ji < 0) break;
       ops.clear();
+      first_undo_built = (size_t)-1;
       bool ok = allocate_job(ji, nullptr, false);
       if (ok) {
         if (should_pipeline_job(ji)) stmt_convert_all_allocated_to_pipelined(ji);
