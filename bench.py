@@ -245,6 +245,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_action", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": alg_bytes // max(args.steps, 1),
+                         # the naive path sweeps every node for every pod; executed sweeps are what
+                         # `achieved` counts, this is the same workload in the reference's own terms
+                         "naive_equivalent_bytes_per_launch": int(snap.n_nodes) * int(pods_all // max(args.steps, 1)) * BYTES_PER_NODE,
                          "kernel_ms_per_launch": act_ms / args.steps, "traffic": None,
                          "traffic_note": "the host-sequenced kernel cannot run under ncu (the profiler serialises it with the "
                                          "host thread that feeds it); ncu --set full of the same kernel with the device-resident "

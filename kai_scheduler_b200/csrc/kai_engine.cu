@@ -951,6 +951,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       if (getenv("KAI_PROFILE"))
         fprintf(stderr, "[kai] solver host profile: %lld simulations; sweeps %.1f ms, simulation set-up %.1f ms, evicting recorded victims %.1f ms, victims queues %.1f ms\n",
                 solver.simulations, solver.t_sweeps * 1e3, solver.t_sim_setup * 1e3, solver.t_evict * 1e3, solver.t_victims_queue * 1e3);
+      if (getenv("KAI_PROFILE"))
+        fprintf(stderr, "[kai] solver host profile: scenario loop: victims pop %.1f ms, tasks_to_evict %.1f, add potential %.1f, filter %.1f, filter init (top-k sweep) %.1f, by-pod solve %.1f\n",
+                solver.t_vq_pop * 1e3, solver.t_tte * 1e3, solver.t_addp * 1e3, solver.t_filter * 1e3, solver.t_finit * 1e3, solver.t_bypod * 1e3);
       solver_scenarios = solver.scenarios;
       solver_topk = solver.topk_sweeps;
       // one status per task for the allocate path: the entry on the task's current node; the other entry persists

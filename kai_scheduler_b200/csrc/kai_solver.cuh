@@ -103,7 +103,7 @@ struct Solver {
   std::vector<SOp> ops;
 
   long long sweeps = 0, scenarios = 0, topk_sweeps = 0, simulations = 0;
-  double t_sweeps = 0, t_sim_setup = 0, t_evict = 0, t_victims_queue = 0;
+  double t_sweeps = 0, t_sim_setup = 0, t_evict = 0, t_victims_queue = 0, t_vq_pop = 0, t_tte = 0, t_addp = 0, t_filter = 0, t_bypod = 0, t_finit = 0;
 
   Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1,
          std::vector<double> &ig, std::vector<double> &lg)
@@ -905,6 +905,7 @@ struct Solver {
     std::multiset<double, std::greater<double>> sorted;  // the same values, descending (incremental, like orderedInsert)
     std::vector<char> seen;       // per task
     size_t n_rec_done = 0, n_pot_done = 0;
+    std::vector<double> rq;  // GPU requests of the pending tasks, descending
   };
   void idle_filter_account(IdleFilter &f, const Scenario &sc) {
     // recorded victims never change within a builder and potential victims are append-only: only new entries
@@ -935,9 +936,12 @@ struct Solver {
   }
   bool idle_filter_check(IdleFilter &f, const Scenario &sc) {
     idle_filter_account(f, sc);
-    std::vector<double> rq;
-    for (int t : sc.pending_tasks) rq.push_back(req(t, KAI_RES_GPU));
-    std::sort(rq.begin(), rq.end(), std::greater<double>());
+    if (f.rq.empty() && !sc.pending_tasks.empty()) {  // the pending tasks of a builder never change
+      for (int t : sc.pending_tasks) f.rq.push_back(req(t, KAI_RES_GPU));
+      std::sort(f.rq.begin(), f.rq.end(), std::greater<double>());
+    }
+    const std::vector<double> &rq = f.rq;
+    if (!rq.empty() && rq[0] != 0 && (f.sorted.empty() || *f.sorted.begin() < rq[0])) return false;  // first requirement unmatched
     std::vector<double> cap;
     for (auto it = f.sorted.begin(); it != f.sorted.end() && (int)cap.size() < f.k; ++it) cap.push_back(*it);
     std::vector<double> used(cap.size(), 0.0);
@@ -1325,7 +1329,9 @@ struct Solver {
       t_victims_queue += HostBackend::now() - t0;
     }
     IdleFilter filter;
+    const double tfi = HostBackend::now();
     idle_filter_init(filter, sc, pending_snap_bits);
+    t_finit += HostBackend::now() - tfi;
     pending_snap_bits = 0;
     bool first = true;
     while (!gpu_failed()) {
@@ -1336,10 +1342,14 @@ struct Solver {
           bool added = false;
           while (!added) {
             if (victims_queue.is_empty()) break;
+            double tq = HostBackend::now();
             int next = victims_queue.pop_next_job();
+            t_vq_pop += HostBackend::now() - tq;
             if (next < 0) break;
             bool has_more = false;
+            tq = HostBackend::now();
             std::vector<int> tasks = tasks_to_evict(next, has_more);
+            t_tte += HostBackend::now() - tq;
             bool hit = false;
             for (int t : tasks)
               if (recorded_set[t]) hit = true;
@@ -1356,12 +1366,17 @@ struct Solver {
                 if (std::find(tasks.begin(), tasks.end(), t) == tasks.end()) remaining.push_back(t);
               victims_queue.push_job(make_clone(next, remaining));
             }
+            tq = HostBackend::now();
             scenario_add_potential(sc, tasks);
+            t_addp += HostBackend::now() - tq;
             added = true;
           }
           if (!added) break;
         }
-        if (idle_filter_check(filter, sc)) {
+        const double tf = HostBackend::now();
+        const bool fc = idle_filter_check(filter, sc);
+        t_filter += HostBackend::now() - tf;
+        if (fc) {
           have = true;
           break;
         }
@@ -1369,7 +1384,9 @@ struct Solver {
       }
       if (!have) break;
       scenarios++;
+      const double tb = HostBackend::now();
       SolveResult r = bypod_solve(sc);
+      t_bypod += HostBackend::now() - tb;
       if (r.solved) return r;
     }
     return SolveResult();
