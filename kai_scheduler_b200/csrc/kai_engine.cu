@@ -918,10 +918,6 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     long long solver_scenarios = 0, solver_topk = 0;
     if (!solver_action) {
       hb.run_allocate();
-    } else if (!p.topm) {
-      hb.publish(DK_DONE);
-      CK(cudaStreamSynchronize(e->stream));
-      return e->fail(KAI_ERR_UNSUPPORTED, "reclaim / consolidation need the top-M list transport (KAI_NO_TOPM / KAI_NO_BATCHING unset)");
     } else {
       const int T = e->T;
       if ((int)e->on_other_node.size() != T) {

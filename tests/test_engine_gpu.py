@@ -148,9 +148,11 @@ def test_full_cycle_allocate_consolidation_reclaim():
     e.close()
 
 
-@pytest.mark.parametrize("grid", ["2", "5", "148"])
-def test_solver_tables_forced_grid(grid, monkeypatch):
+@pytest.mark.parametrize("grid,env", [("2", None), ("5", "KAI_NO_TOPM"), ("148", None), ("148", "KAI_NO_BATCHING")])
+def test_solver_tables_forced_grid(grid, env, monkeypatch):
     monkeypatch.setenv("KAI_GRID_EXACT", grid)
+    if env:
+        monkeypatch.setenv(env, "1")
     for cid, case in SOLVER:
         snap, meta = dsl.build_snapshot(case["topology"])
         re_, ro = run_both(snap, action=case["actions"][0])
