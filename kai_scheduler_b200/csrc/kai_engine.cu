@@ -128,6 +128,7 @@ struct kai_engine {
   // solver actions: second NodeInfo.PodInfos entry of a task (evicted from A, pipelined to B), mirror of the GPU column
   std::vector<int> on_other_node, on_other_status;
   std::vector<double> h_ig, h_lg;
+  bool mirror_valid = false;  // h_ig / h_lg followed every delta since the load (host-sequenced actions only)
   std::vector<int> job_signature;
   size_t dev_only_begin = 0, dev_only_bytes = 0;
   std::vector<int> task_perm;
@@ -682,6 +683,9 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->on_other_node.clear();
   e->on_other_status.clear();
   e->job_signature.clear();
+  e->h_ig.assign(s->node_idle + (size_t)KAI_RES_GPU * s->n_nodes, s->node_idle + (size_t)(KAI_RES_GPU + 1) * s->n_nodes);
+  e->h_lg.assign(s->node_releasing + (size_t)KAI_RES_GPU * s->n_nodes, s->node_releasing + (size_t)(KAI_RES_GPU + 1) * s->n_nodes);
+  e->mirror_valid = true;
   if (s->job_signature) e->job_signature.assign(s->job_signature, s->job_signature + s->n_jobs);
   e->loaded = true;
   return KAI_OK;
@@ -779,8 +783,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   const char *mode_env = getenv("KAI_SEQUENCER");
   const bool host_mode = !(mode_env && strcmp(mode_env, "device") == 0);
   if (!host_mode && e->cfg.shard_count > 1) return e->fail(KAI_ERR_UNSUPPORTED, "device-resident sequencer is single-GPU");
-  if (solver_action && (!host_mode || e->cfg.shard_count > 1))
-    return e->fail(KAI_ERR_UNSUPPORTED, "reclaim / consolidation run host-sequenced on one GPU");
+  if (solver_action && !host_mode) return e->fail(KAI_ERR_UNSUPPORTED, "reclaim / consolidation / preempt run host-sequenced");
+  if (solver_action && e->cfg.shard_count > 1 && !e->mirror_valid)
+    return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU solver actions need every earlier action of the cycle to be host-sequenced");
+  if (!host_mode) e->mirror_valid = false;
   p.mode = host_mode ? 1 : 0;
   p.spin_log2 = host_mode ? 26 : 22;
   if (host_mode) {
@@ -807,7 +813,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     // host mirror of everything the open-session / prepare kernels produced
     CK(cudaMemcpyAsync(e->stage.host + e->dev_only_begin, e->dsnap.base + e->dev_only_begin, e->dev_only_bytes,
                        cudaMemcpyDeviceToHost, e->stream));
-    if (solver_action) {  // GPU column of Idle / Releasing as the previous action left it (point look-ups on the host)
+    if (solver_action && !e->mirror_valid) {  // a device-sequenced action ran before: re-read the GPU column (one GPU)
       e->h_ig.resize(e->N);
       e->h_lg.resize(e->N);
       if (e->N > 0) {
@@ -902,6 +908,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     seq.p = &p;
     seq.delta_base = e->h_delta;
     seq.host_backend = &hb;
+    seq.mirror_ig = e->h_ig.data();
+    seq.mirror_lg = e->h_lg.data();
     seq.ctl = &ctl;
     seq.ops_cap = e->ops_cap;
     seq.batching = p.batching;
@@ -930,6 +938,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         n0[t] = on ? hs.t_node[t] : -1;
         s0[t] = hs.t_node_status[t];
       }
+      e->mirror_valid = true;  // from here on the host-sequenced deltas keep it in step
       double t_begin = HostBackend::now();
       Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status, e->h_ig, e->h_lg);
       solver.use_signatures = e->cfg.use_scheduling_signatures != 0;

@@ -193,6 +193,8 @@ struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   const ActionParams *p;
   unsigned long long *delta_base;  // tagged node-delta words [2][kMaxDelta] (device memory or pinned host memory)
   void *host_backend;               // host-sequenced mode: HostBackend*
+  double *mirror_ig, *mirror_lg;    // host-sequenced mode: GPU column of Idle / Releasing of ALL nodes, kept in step with
+                                    // the deltas (point look-ups of the solver; identical on every rank)
   Replica rp;
   Tile *tile;
   Ctl *ctl;
@@ -246,6 +248,18 @@ KAI_HD inline bool should_allocate(const Seq &q, int t, bool real) {  // pod_inf
 enum { ND_ADD = 0, ND_ADD_PIPELINED = 1, ND_ADD_RELEASING = 2, ND_REM = 3, ND_REM_PIPELINED = 4, ND_REM_RELEASING = 5,
        ND_FEAS_SET = 6, ND_FEAS_CLR = 7 };  // 6, 7: feasible-set membership of the row (no task attached)
 KAI_HD void seq_flush_deltas(Seq &q);  // FLUSH exchange when the delta list is full (backend specific)
+// applied by the owning scanner to its tile row (lane r handles resource r)
+KAI_HD inline void apply_delta_row(double &I, double &L, int code, double v) {
+  switch (code) {
+    case ND_ADD: I = ksub(I, v); break;
+    case ND_ADD_PIPELINED: L = ksub(L, v); break;
+    case ND_ADD_RELEASING: L = kadd(L, v); I = ksub(I, v); break;
+    case ND_REM: I = kadd(I, v); break;
+    case ND_REM_PIPELINED: L = kadd(L, v); break;
+    case ND_REM_RELEASING: L = ksub(L, v); I = kadd(I, v); break;
+  }
+}
+
 // Every delta word is written exactly once (readers validate it by its tag only): the newest entry stays pending in
 // the control block, so that consecutive deltas of the same kind on the same row with bit-identical requests can be
 // folded into it as a repeat count (tag word bits 32+; the owner applies the same subtraction `count` times, in
@@ -260,6 +274,10 @@ KAI_HD void close_delta(Ctl &c, unsigned long long *delta_base) {
 }
 KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
+#ifndef __CUDA_ARCH__
+  if (q.mirror_ig && code < ND_FEAS_SET)
+    apply_delta_row(q.mirror_ig[node], q.mirror_lg[node], code, q.s->t_req[(size_t)t * q.s->R + KAI_RES_GPU]);
+#endif
   // the delta names the node by its NAME RANK: that is what decides which scanner owns the row
   const unsigned int key = (unsigned int)(kldg(&q.s->name_rank[node]) | (code << 28));
   if (code < ND_FEAS_SET && c.n_delta > 0 && c.last_dcount > 0 && c.last_dkey == key && c.last_dcount < 255) {
@@ -287,18 +305,6 @@ KAI_HD void node_remove_task(Seq &q, int t, int n) {
   int st = q.rp.t_node_status[t];
   emit_delta(q, n, st == KAI_POD_RELEASING ? ND_REM_RELEASING : (st == KAI_POD_PIPELINED ? ND_REM_PIPELINED : ND_REM), t);
 }
-// applied by the owning scanner to its tile row (lane r handles resource r)
-KAI_HD inline void apply_delta_row(double &I, double &L, int code, double v) {
-  switch (code) {
-    case ND_ADD: I = ksub(I, v); break;
-    case ND_ADD_PIPELINED: L = ksub(L, v); break;
-    case ND_ADD_RELEASING: L = kadd(L, v); I = ksub(I, v); break;
-    case ND_REM: I = kadd(I, v); break;
-    case ND_REM_PIPELINED: L = kadd(L, v); break;
-    case ND_REM_RELEASING: L = ksub(L, v); I = kadd(I, v); break;
-  }
-}
-
 // ---- PodGroupInfo.UpdateTaskStatus (job_info.go:253-264) + podset counters ----
 // job / old may be passed when the caller already knows them (saves dependent L2 loads)
 KAI_HD void set_status(Seq &q, int t, int status, int job = -1, int old = -1) {

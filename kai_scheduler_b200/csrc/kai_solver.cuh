@@ -322,9 +322,8 @@ struct Solver {
   void node_delta(int t, int n, int code) {
     touch(n);
     const double before = hIg[n] + hLg[n];
-    apply_delta_row(hIg[n], hLg[n], code, req(t, KAI_RES_GPU));
+    emit_delta(seq, n, code, t);  // also applies the delta to the mirror (hIg / hLg are seq.mirror_ig / mirror_lg)
     if (s.nflags[n] & KAI_NODE_READY) free_ready += (hIg[n] + hLg[n]) - before;
-    emit_delta(seq, n, code, t);
   }
   void node_add_task(int t) {  // node_info.go:457-493 with the task's current status
     int n = tn[t], status = st[t];
@@ -509,7 +508,14 @@ struct Solver {
     ctl.batch.valid = 0;
     // pack.go:66-86 over the node set of this simulation: the scanners exchange their extremes among themselves
     ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
-    ctl.xbits = (d.strategy == KAI_PLACEMENT_BINPACK ? XB_FUSED_MM : 0) | XB_SINGLE;  // only the winner is needed
+    const bool one_gpu = cfg.shard_count <= 1;
+    if (!one_gpu && d.strategy == KAI_PLACEMENT_BINPACK) {  // several GPUs: the extremes travel through the host
+      seq.minmax_exchanges++;
+      hb.publish(DK_MINMAX);
+      hb.gather_minmax();
+      if (hb.failed) return -1;
+    }
+    ctl.xbits = ((one_gpu && d.strategy == KAI_PLACEMENT_BINPACK) ? XB_FUSED_MM : 0) | XB_SINGLE;  // only the winner is needed
     const double t0 = HostBackend::now();
     hb.publish(DK_SCAN);
     ctl.xbits = 0;

@@ -49,6 +49,23 @@ def main():
         print(f"rank {rank}/{world} {kw}: {'OK' if same else 'MISMATCH'} placed {res.pods_placed} sweeps {eng.stats().decisions}",
               flush=True)
         ok = ok and same
+    # one whole cycle (allocate, consolidation, reclaim, preempt, stalegangeviction) on node-striped GPUs
+    for kw in (dict(n_nodes=48, running_per_node=7, victim_queues=2, reclaimer_jobs=12, reclaimer_tasks=2, reclaimer_gpus=3.0),
+               dict(n_nodes=100), dict(n_nodes=333, running_per_node=8, victim_queues=3, reclaimer_jobs=9, reclaimer_tasks=3, reclaimer_gpus=4.0)):
+        snap = synthetic.reclaim_snapshot(**kw)
+        eng.load(snap)
+        o = Oracle()
+        o.load(snap)
+        own = engine.shard_node_mask(snap.node_name_rank, world, rank)
+        for action in ("allocate", "consolidation", "reclaim", "preempt", "stalegangeviction"):
+            res, ref = eng.run(action), o.run(action)
+            same = (np.array_equal(res.task_node, ref.task_node) and np.array_equal(res.task_status, ref.task_status)
+                    and np.array_equal(res.visits, ref.visits) and np.array_equal(res.queue_allocated, ref.queue_allocated)
+                    and res.pods_evicted == ref.pods_evicted
+                    and np.array_equal(res.node_idle[:, own], ref.node_idle[:, own])
+                    and np.array_equal(res.node_releasing[:, own], ref.node_releasing[:, own]))
+            print(f"rank {rank}/{world} cycle {kw} {action}: {'OK' if same else 'MISMATCH'} placed {res.pods_placed} evicted {res.pods_evicted}", flush=True)
+            ok = ok and same
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
