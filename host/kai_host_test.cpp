@@ -1,0 +1,107 @@
+// kai_host_test — drives the C++ mirror of the reference's Action surface the way the reference's own tests do
+// (pkg/scheduler/test_utils/test_utils.go:40-119 BuildSession + RunTests): reads a cluster description, builds a
+// framework::Session, resolves the Actions from the registry by name, executes them in order and prints the tasks.
+//
+// input (text, one record per line; written by tests/test_host_cpp.py from the transcribed reference tables):
+//   R <n_res>
+//   queue <uid> <parent|-> <priority> <creation> <d0 d1 d2> <l0 l1 l2> <w0 w1 w2>
+//   node <name> <allocatable x R>
+//   job <uid> <queue> <priority> <preemptible 0/1> <creation>
+//   podset <job> <name> <minAvailable>
+//   task <job> <podset> <uid> <status> <node|-> <order key> <req x R>
+//   actions <name> ...
+// output: one line per task "<uid> <status> <node|->", then "cache <binds> <evictions> <pipelines>".
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "kai_host.hpp"
+
+using namespace kai_host;
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s <case file> | --registry\n", argv[0]);
+    return 2;
+  }
+  gpuengine::RegisterAll();
+  if (std::string(argv[1]) == "--registry") {  // no GPU needed: the registry resolves every default action name
+    for (const char *n : {"allocate", "consolidation", "reclaim", "preempt", "stalegangeviction"})
+      printf("%s %s\n", n, framework::GetAction(n) ? "registered" : "missing");
+    printf("unknown %s\n", framework::GetAction("unknown") ? "registered" : "missing");
+    return 0;
+  }
+  std::ifstream in(argv[1]);
+  framework::Session ssn;
+  std::vector<std::string> actions;
+  int R = 4;
+  std::string line;
+  std::vector<std::shared_ptr<api::PodInfo>> all_tasks;
+  while (std::getline(in, line)) {
+    std::istringstream ls(line);
+    std::string kind;
+    ls >> kind;
+    if (kind == "R") {
+      ls >> R;
+    } else if (kind == "queue") {
+      auto q = std::make_shared<api::QueueInfo>();
+      std::string parent;
+      ls >> q->UID >> parent >> q->Priority >> q->CreationTimestamp;
+      q->ParentQueue = parent == "-" ? "" : parent;
+      for (double &v : q->Deserved) ls >> v;
+      for (double &v : q->Limit) ls >> v;
+      for (double &v : q->OverQuotaWeight) ls >> v;
+      ssn.ClusterInfo.Queues[q->UID] = q;
+    } else if (kind == "node") {
+      auto n = std::make_shared<api::NodeInfo>();
+      ls >> n->Name;
+      n->Allocatable.resize(R);
+      for (double &v : n->Allocatable) ls >> v;
+      n->Idle = n->Allocatable;
+      n->Releasing.assign(R, 0.0);
+      ssn.ClusterInfo.Nodes[n->Name] = n;
+    } else if (kind == "job") {
+      auto j = std::make_shared<api::PodGroupInfo>();
+      int pre;
+      ls >> j->UID >> j->Queue >> j->Priority >> pre >> j->CreationTimestamp;
+      j->Preemptible = pre != 0;
+      ssn.ClusterInfo.PodGroupInfos[j->UID] = j;
+    } else if (kind == "podset") {
+      std::string job;
+      api::PodSet ps;
+      ls >> job >> ps.Name >> ps.MinAvailable;
+      ssn.ClusterInfo.PodGroupInfos[job]->PodSets.push_back(ps);
+    } else if (kind == "task") {
+      auto t = std::make_shared<api::PodInfo>();
+      std::string node;
+      ls >> t->Job >> t->SubGroupName >> t->UID >> t->Status >> node >> t->OrderKey;
+      t->ResReq.resize(R);
+      for (double &v : t->ResReq) ls >> v;
+      t->NodeName = node == "-" ? "" : node;
+      ssn.ClusterInfo.PodGroupInfos[t->Job]->Tasks.push_back(t);
+      all_tasks.push_back(t);
+      // nodes_fake/nodes.go:213-223: tasks in an active-used state are added to their node
+      if (pod_status::IsActiveUsedStatus(t->Status) && ssn.ClusterInfo.Nodes.count(t->NodeName))
+        ssn.ClusterInfo.Nodes[t->NodeName]->AddTask(t);
+    } else if (kind == "actions") {
+      std::string a;
+      while (ls >> a) actions.push_back(a);
+    }
+  }
+  for (const std::string &name : actions) {
+    auto action = framework::GetAction(name);  // scheduler.go:129-136 runOnce: for _, action := range actions
+    if (!action) {
+      fprintf(stderr, "failed to find Action %s\n", name.c_str());
+      return 3;
+    }
+    action->Execute(ssn);
+    if (!ssn.LastError().empty()) {
+      fprintf(stderr, "engine error in %s: %s\n", name.c_str(), ssn.LastError().c_str());
+      return 4;
+    }
+  }
+  for (auto &t : all_tasks) printf("%s %d %s\n", t->UID.c_str(), t->Status, t->NodeName.empty() ? "-" : t->NodeName.c_str());
+  printf("cache %d %d %d\n", ssn.cache.Binds, ssn.cache.Evictions, ssn.cache.Pipelines);
+  return 0;
+}

@@ -1,0 +1,95 @@
+"""The C++ host side above the C ABI (host/kai_host.hpp): the reference's Action / Session surface mirrored in C++
+(the reference's host language, Go, has no toolchain in this image).  The driver host/kai_host_test builds a
+framework::Session from a cluster description, resolves the Actions by name from the registry and executes them, like
+pkg/scheduler/test_utils RunTests; the expectations are the reference's own tables.
+"""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import dsl
+from fixtures import action_cases
+from kai_scheduler_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "host", "kai_host_test")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "kai_scheduler_b200", "csrc")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host")], stdout=subprocess.DEVNULL)
+
+
+def test_registry_resolves_default_actions():
+    """framework.RegisterAction / GetAction semantics (framework/plugins.go:47-62): no GPU needed."""
+    _build()
+    out = subprocess.run([BIN, "--registry"], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[:6] == ["allocate registered", "consolidation registered", "reclaim registered", "preempt registered",
+                       "stalegangeviction registered", "unknown missing"]
+
+
+def write_case(path, snap: abi.Snapshot, meta: dict, actions):
+    R, N, Q = snap.n_res, snap.n_nodes, int(snap.queue_parent.shape[0])
+    qn = meta["queue_names"]
+    with open(path, "w") as f:
+        f.write(f"R {R}\n")
+        for q in range(Q):
+            parent = qn[snap.queue_parent[q]] if snap.queue_parent[q] >= 0 else "-"
+            vals = " ".join(repr(float(x)) for tab in (snap.queue_deserved, snap.queue_limit, snap.queue_oqw) for x in tab[:, q])
+            f.write(f"queue {qn[q]} {parent} {int(snap.queue_priority[q])} {int(snap.queue_creation[q])} {vals}\n")
+        for n in range(N):
+            f.write(f"node {meta['node_names'][n]} " + " ".join(repr(float(x)) for x in snap.node_allocatable[:, n]) + "\n")
+        for j, name in enumerate(meta["job_names"]):
+            pre = 1 if snap.job_flags[j] & abi.JOB_PREEMPTIBLE else 0
+            f.write(f"job {name} {qn[snap.job_queue[j]]} {int(snap.job_priority[j])} {pre} {int(snap.job_order_rank[j])}\n")
+            for ps in range(snap.job_podset_begin[j], snap.job_podset_begin[j + 1]):
+                f.write(f"podset {name} ps{ps - snap.job_podset_begin[j]:03d} {int(snap.podset_min_available[ps])}\n")
+        for j, name in enumerate(meta["job_names"]):
+            for ps in range(snap.job_podset_begin[j], snap.job_podset_begin[j + 1]):
+                for t in range(snap.podset_task_begin[ps], snap.podset_task_begin[ps + 1]):
+                    node = meta["node_names"][snap.task_node[t]] if snap.task_node[t] >= 0 else "-"
+                    req = " ".join(repr(float(x)) for x in snap.task_req[t])
+                    f.write(f"task {name} ps{ps - snap.job_podset_begin[j]:03d} {meta['task_names'][t]} {int(snap.task_status[t])} "
+                            f"{node} {int(snap.task_order_rank[t])} {req}\n")
+        f.write("actions " + " ".join(actions) + "\n")
+
+
+class _Res:
+    pass
+
+
+CASES = (action_cases(["allocate__"], single_action="allocate")[:12] + action_cases(["reclaim__"], single_action="reclaim")[:12]
+         + action_cases(["consolidation__"], single_action="consolidation")[:8] + action_cases(["preempt__"], single_action="preempt")[:8])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid,case", CASES, ids=[c[0] for c in CASES])
+def test_reference_tables_through_cpp_shim(cid, case):
+    _build()
+    snap, meta = dsl.build_snapshot(case["topology"])
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "case.txt")
+        write_case(path, snap, meta, case["actions"])
+        out = subprocess.run([BIN, path], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().split("\n")]
+    by_name = {l[0]: l for l in lines if l[0] != "cache"}
+    res = _Res()
+    res.task_status = np.array([int(by_name[n][1]) for n in meta["task_names"]], dtype=np.int32)
+    nidx = {n: i for i, n in enumerate(meta["node_names"])}
+    res.task_node = np.array([nidx.get(by_name[n][2], -1) for n in meta["task_names"]], dtype=np.int32)
+    topo = dict(case["topology"])
+    topo.pop("ExpectedNodesResources", None)  # the C++ session replays statuses / bindings; node tables stay in the engine
+    res.node_idle = res.node_releasing = None
+    errs = dsl.check_expectations(topo, meta, res, snap)
+    assert not errs, f"{case['source']} #{case['index']}: {errs}"
+    # CacheMocking caps (test_utils.go CacheRequirements): binds / evictions / pipelines must not exceed them
+    cache = [l for l in lines if l[0] == "cache"][0]
+    caps = ((case["topology"].get("Mocks") or {}).get("CacheRequirements") or {})
+    for key, got in (("NumberOfCacheBinds", int(cache[1])), ("NumberOfCacheEvictions", int(cache[2])),
+                     ("NumberOfPipelineActions", int(cache[3]))):
+        if caps.get(key) is not None:
+            assert got <= caps[key], (key, got, caps[key])
