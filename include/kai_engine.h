@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KAI_ABI_VERSION 2
+#define KAI_ABI_VERSION 3
 #define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
 #define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
 #define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
@@ -184,6 +184,21 @@ typedef struct kai_snapshot {
   /* ---- PodGroupInfo.GetSchedulingConstraintsSignature (job_info.go:547-570) as a class id: jobs with equal
          signatures get equal ids; -1 = unique.  NULL = all -1. ---- */
   const int32_t *job_signature; /* [J] */
+
+  /* ---- Topology CRs (pkg/apis/kai/v1alpha1 Topology; plugins/topology/topology_plugin.go:57-110).
+         Levels of topology k = [topology_level_begin[k], topology_level_begin[k+1]) in Spec.Levels order (top level
+         first).  node_domain[l][n] = the node's domain at level l: dense ids per level assigned in ascending
+         DomainID order (DomainID = the label values of the levels down to l joined by ".", topology_structs.go:76-82),
+         -1 = the node lacks that label (a node missing any level is outside the topology, common.go:63-70).
+         Constraints of the job's root SubGroupSet (api/topology_info): job_topology[j] = topology index or -1,
+         job_required_level / job_preferred_level = level index inside that topology (0 = top) or -1. ---- */
+  int32_t n_topologies;
+  int32_t reserved1;
+  const int32_t *topology_level_begin; /* [n_topologies + 1] */
+  const int32_t *node_domain;          /* [n_levels_total][N] */
+  const int32_t *job_topology;         /* [J]; NULL = no constraints */
+  const int32_t *job_required_level;   /* [J] */
+  const int32_t *job_preferred_level;  /* [J] */
 } kai_snapshot;
 
 /* One entry per job popped by an action, in visiting order. */

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-KAI_ABI_VERSION = 2
+KAI_ABI_VERSION = 3
 KAI_MAX_RES = 8
 KAI_QRES = 3
 RES_CPU, RES_MEM, RES_GPU, RES_PODS = 0, 1, 2, 3
@@ -77,6 +77,9 @@ class KaiSnapshot(C.Structure):
         ("task_nominated", _ip), ("task_pred_class", _ip),
         ("pred_mask", _up),
         ("job_signature", _ip),
+        ("n_topologies", C.c_int32), ("reserved1", C.c_int32),
+        ("topology_level_begin", _ip), ("node_domain", _ip),
+        ("job_topology", _ip), ("job_required_level", _ip), ("job_preferred_level", _ip),
     ]
 
 
@@ -151,6 +154,11 @@ class Snapshot:
     task_pred_class: np.ndarray | None = None
     pred_mask: np.ndarray | None = None  # [C, ceil(N/32)] u32
     job_signature: np.ndarray | None = None  # [J] i32 scheduling-constraints signature class, -1 = unique
+    topology_level_begin: np.ndarray | None = None  # [n_topologies + 1]
+    node_domain: np.ndarray | None = None           # [n_levels_total, N] i32
+    job_topology: np.ndarray | None = None          # [J] i32, -1 none
+    job_required_level: np.ndarray | None = None    # [J] i32
+    job_preferred_level: np.ndarray | None = None   # [J] i32
     names: dict = field(default_factory=dict)  # optional: node/job/task/queue names for reporting
     _keep: list = field(default_factory=list, repr=False)
 
@@ -234,6 +242,12 @@ class Snapshot:
         s.task_pred_class = p(self.task_pred_class, np.int32, _ip)
         s.pred_mask = p(self.pred_mask, np.uint32, _up)
         s.job_signature = p(self.job_signature, np.int32, _ip)
+        s.n_topologies = 0 if self.topology_level_begin is None else int(len(self.topology_level_begin) - 1)
+        s.topology_level_begin = p(self.topology_level_begin, np.int32, _ip)
+        s.node_domain = p(self.node_domain, np.int32, _ip)
+        s.job_topology = p(self.job_topology, np.int32, _ip)
+        s.job_required_level = p(self.job_required_level, np.int32, _ip)
+        s.job_preferred_level = p(self.job_preferred_level, np.int32, _ip)
         self._keep = keep
         return s
 

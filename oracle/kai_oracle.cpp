@@ -1101,6 +1101,10 @@ struct kai_oracle {
           score += binpack_score(mn, mx, cur, A(res, n));
         else
           score += spread_score(cur, res == KAI_RES_GPU ? (double)(int64_t)gpu_count[n] : A(res, n));
+        if (!topo_scores.empty()) {  // topology/node_scoring.go:17-34: last NodeOrderFn; a node without an entry
+          if (topo_scores[n] < 0) continue;  // makes NodeOrderFn fail => the node is dropped (session.go:247-251)
+          score += topo_scores[n];
+        }
         if (b.node < 0 || score > b.score || (score == b.score && name_rank[n] < b.rank)) {
           b.score = score;
           b.rank = name_rank[n];
@@ -1171,6 +1175,318 @@ struct kai_oracle {
   }
   ~kai_oracle() { pool_shutdown(); }
 
+
+  // =====================================================================================================
+  // plugins/topology: domain tree (topology_plugin.go:57-110), subSetNodesFn (job_filtering.go:34-112) and the
+  // preferred-level node scores (node_scoring.go:36-53).  Scope: the constraint of the job's root SubGroupSet;
+  // PodSets carry no constraint of their own.  Children of a domain that sortTree never reaches keep ascending
+  // DomainID order (the reference: node map iteration order).
+  // =====================================================================================================
+  struct TopoDom {
+    int level = -1;  // global level index, -1 = root
+    int id = 0;
+    std::vector<int> children, nodes;
+    int alloc_pods = -1;               // allocatablePodsNotSet
+    double free[KAI_MAX_RES] = {0};    // IdleOrReleasingResources
+  };
+  struct Topo {
+    int lb = 0, le = 0;
+    std::vector<TopoDom> doms;  // doms[0] = root
+    std::vector<std::vector<int>> dom_at;  // [level - lb][id] -> index into doms
+    std::vector<char> node_in;  // node carries every level label
+  };
+  std::vector<Topo> topos;
+  std::vector<int> topo_level_begin, node_domain, job_topology, job_req_level, job_pref_level;
+  std::vector<double> topo_scores;  // subGroupNodeScores of the job being allocated: per node, -1 = no entry; empty = none
+  int ND(int level, int n) const { return node_domain[(size_t)level * N + n]; }
+  void build_topologies() {
+    topos.clear();
+    int nt = (int)topo_level_begin.size() - 1;
+    for (int k = 0; k < nt; k++) {
+      Topo tp;
+      tp.lb = topo_level_begin[k];
+      tp.le = topo_level_begin[k + 1];
+      tp.doms.emplace_back();
+      tp.node_in.assign(N, 0);
+      tp.dom_at.assign(tp.le - tp.lb, {});
+      for (int l = tp.lb; l < tp.le; l++) {
+        int mx = -1;
+        for (int n = 0; n < N; n++) mx = std::max(mx, ND(l, n));
+        tp.dom_at[l - tp.lb].assign(mx + 1, -1);
+      }
+      for (int n = 0; n < N; n++) {
+        bool in = tp.le > tp.lb;
+        for (int l = tp.lb; l < tp.le; l++)
+          if (ND(l, n) < 0) in = false;
+        if (!in) continue;
+        tp.node_in[n] = 1;
+        tp.doms[0].nodes.push_back(n);
+        int parent = 0;
+        for (int l = tp.lb; l < tp.le; l++) {
+          int &di = tp.dom_at[l - tp.lb][ND(l, n)];
+          if (di < 0) {
+            di = (int)tp.doms.size();
+            tp.doms.emplace_back();
+            tp.doms[di].level = l;
+            tp.doms[di].id = ND(l, n);
+            tp.doms[parent].children.push_back(di);
+          }
+          tp.doms[di].nodes.push_back(n);
+          parent = di;
+        }
+      }
+      for (auto &d : tp.doms)  // canonical child order where the reference has map order: ascending DomainID
+        std::sort(d.children.begin(), d.children.end(), [&](int a, int b) { return tp.doms[a].id < tp.doms[b].id; });
+      topos.push_back(tp);
+    }
+  }
+  // job_filtering.go:445-486 getJobRatioToFreeResources on ResourceList quantities (Quantity.Value() of a milli
+  // quantity rounds up: cpu in whole cores; memory in bytes; scalar resources other than pods like cpu)
+  double job_ratio_to_free(const double *tasks_res, const TopoDom &d) const {
+    double ratio = 0.0;
+    bool empty = true;
+    for (int r = 0; r < R; r++)
+      if (tasks_res[r] > 0) empty = false;
+    if (empty) return 0.0;
+    if (tasks_res[KAI_RES_GPU] > 0) ratio = std::max(ratio, tasks_res[KAI_RES_GPU] / d.free[KAI_RES_GPU]);
+    for (int r = 0; r < R; r++) {
+      if (r == KAI_RES_GPU || r == 3) continue;  // gpus handled above; "pods" ignored for bin-packing
+      int64_t tq = r == KAI_RES_MEM ? (int64_t)tasks_res[r] : (int64_t)std::ceil((double)(int64_t)tasks_res[r] / 1000.0);
+      if (tq == 0) continue;
+      int64_t fq = r == KAI_RES_MEM ? (int64_t)d.free[r] : (int64_t)std::ceil((double)(int64_t)d.free[r] / 1000.0);
+      double rr = fq == 0 ? 1000.0 : (double)tq / (double)fq;
+      ratio = std::max(ratio, rr);
+    }
+    return ratio;
+  }
+  bool check_job_domain_fit(const double *tasks_res, int tasks_count, const TopoDom &d) const {  // :302-320
+    if (d.alloc_pods != -1) return d.alloc_pods >= tasks_count;
+    return !(job_ratio_to_free(tasks_res, d) > 1.0);
+  }
+  void calc_subtree_free(Topo &tp, int di) {  // :191-211
+    TopoDom &d = tp.doms[di];
+    if (d.children.empty()) {
+      for (int n : d.nodes)
+        for (int r = 0; r < R; r++) {
+          d.free[r] += I(r, n);
+          d.free[r] += L(r, n);
+        }
+      return;
+    }
+    for (int c : d.children) {
+      calc_subtree_free(tp, c);
+      for (int r = 0; r < R; r++) tp.doms[di].free[r] += tp.doms[c].free[r];
+    }
+  }
+  // :213-247 calcNodeAccommodation with the shared, growing list of test pods (k-th = (k-1)-th + max pod)
+  int calc_subtree_allocatable(Topo &tp, int di, const double *max_pod, std::vector<std::vector<double>> &test_pods, int n_tasks) {
+    TopoDom &d = tp.doms[di];
+    d.alloc_pods = 0;
+    if (d.children.empty()) {
+      for (int n : d.nodes) {
+        bool only_pods = true;  // maxPodResources.LessEqual(onePodOnly)
+        for (int r = 0; r < R; r++)
+          if (r == 3 ? max_pod[r] > 1 : max_pod[r] > 0) only_pods = false;
+        if (only_pods) {
+          d.alloc_pods += n_tasks;
+          continue;
+        }
+        auto fits_pod = [&](const std::vector<double> &rq) {
+          for (int r = 0; r < R; r++) {
+            double avail = I(r, n) + L(r, n);
+            if (r >= 3) {
+              if (rq[r] != 0 && rq[r] > avail) return false;
+            } else if (rq[r] > avail)
+              return false;
+          }
+          return true;
+        };
+        int cnt = 0;
+        for (auto &tpod : test_pods) {
+          if (fits_pod(tpod))
+            cnt++;
+          else
+            break;
+        }
+        if (cnt == (int)test_pods.size()) {
+          for (;;) {
+            std::vector<double> next = test_pods.back();
+            for (int r = 0; r < R; r++) next[r] += max_pod[r];
+            test_pods.push_back(next);
+            if (fits_pod(next))
+              cnt++;
+            else
+              break;
+          }
+        }
+        d.alloc_pods += cnt;
+      }
+      return d.alloc_pods;
+    }
+    for (int c : d.children) {
+      int a = calc_subtree_allocatable(tp, c, max_pod, test_pods, n_tasks);
+      tp.doms[di].alloc_pods += a;
+    }
+    return tp.doms[di].alloc_pods;
+  }
+  void sort_tree(Topo &tp, int di, const double *tasks_res, int max_depth_level) {  // :396-420
+    if (max_depth_level == -2) return;
+    TopoDom &d = tp.doms[di];
+    std::vector<std::pair<double, int>> keyed;
+    for (int c : d.children) keyed.push_back({job_ratio_to_free(tasks_res, tp.doms[c]), c});
+    std::stable_sort(keyed.begin(), keyed.end(), [&](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+      if (a.first != b.first) return a.first > b.first;
+      return tp.doms[a.second].id < tp.doms[b.second].id;
+    });
+    for (size_t i = 0; i < keyed.size(); i++) tp.doms[di].children[i] = keyed[i].second;
+    if (tp.doms[di].level == max_depth_level) return;
+    std::vector<int> ch = tp.doms[di].children;
+    for (int c : ch) sort_tree(tp, c, tasks_res, max_depth_level);
+  }
+  void level_domains(const Topo &tp, int di, int level, std::vector<int> &out) const {  // node_scoring.go:55-68
+    if (tp.doms[di].level == level) {
+      out.push_back(di);
+      return;
+    }
+    for (int c : tp.doms[di].children) level_domains(tp, c, level, out);
+  }
+  // subSetNodesFn for the root SubGroupSet of the view's job.  ok = false: error / no node set (job fails).
+  std::vector<std::vector<int>> subset_nodes(int v, const std::vector<int> &tasks, const std::vector<int> &node_set, bool &ok) {
+    ok = true;
+    const int ji = vjob(v);
+    const int k = job_topology.empty() ? -1 : job_topology[ji];
+    if (k == -2) {  // requested topology does not exist
+      return {};
+    }
+    if (k < 0 || tasks.empty()) return {node_set};
+    Topo &tp = topos[k];
+    const int req = job_req_level[ji], pref = job_pref_level[ji];  // level index inside the topology, -1 none, -2 unknown
+    // common.go:17-61 lowestCommonDomainID
+    std::vector<int> valid;
+    for (int n : node_set)
+      if (tp.node_in[n]) valid.push_back(n);
+    int dom = 0;
+    for (int l = tp.lb; l < tp.le; l++) {
+      bool all = !valid.empty();
+      int value = valid.empty() ? -1 : ND(l, valid[0]);
+      for (int n : valid)
+        if (ND(l, n) != value) all = false;
+      if (!all) break;
+      dom = tp.dom_at[l - tp.lb][value];
+      if (pref >= 0 && l - tp.lb == pref) break;
+    }
+    for (auto &d : tp.doms) {  // treeAllocatableCleanup
+      d.alloc_pods = -1;
+      for (int r = 0; r < KAI_MAX_RES; r++) d.free[r] = 0;
+    }
+    calc_subtree_free(tp, dom);
+    // useRepresentorPodsAccounting (:503-527): all tasks use GPUs or none does (pods is the only scalar resource)
+    int gpu_pods = 0;
+    for (int ti : tasks)
+      if (T[ti].req[KAI_RES_GPU] > 0) gpu_pods++;
+    bool scalars_uniform = true;
+    for (int r = 3; r < R; r++) {
+      int c = 0;
+      for (int ti : tasks)
+        if (T[ti].req[r] != 0) c++;
+      if (c != 0 && c != (int)tasks.size()) scalars_uniform = false;
+    }
+    if ((gpu_pods == (int)tasks.size() || gpu_pods == 0) && scalars_uniform) {
+      std::vector<double> max_pod(R, 0.0);
+      for (int ti : tasks)
+        for (int r = 0; r < R; r++) max_pod[r] = std::max(max_pod[r], T[ti].req[r]);
+      std::vector<std::vector<double>> test_pods{max_pod};
+      calc_subtree_allocatable(tp, dom, max_pod.data(), test_pods, (int)tasks.size());
+    }
+    double tasks_res[KAI_MAX_RES] = {0};
+    for (int ti : tasks)
+      for (int r = 0; r < R; r++) tasks_res[r] += T[ti].req[r];
+    const int tasks_count = (int)tasks.size();
+    if (!check_job_domain_fit(tasks_res, tasks_count, tp.doms[dom])) return {};
+    if (req == -2 || pref == -2 || (req < 0 && pref < 0)) {  // calculateRelevantDomainLevels errors
+      ok = false;
+      return {};
+    }
+    const int max_depth = pref >= 0 ? tp.lb + pref : tp.lb + req;
+    sort_tree(tp, dom, tasks_res, max_depth);
+    if (pref >= 0) {  // node_scoring.go:36-53 calculateNodeScores
+      topo_scores.assign(N, -1.0);
+      std::vector<int> lvl;
+      level_domains(tp, dom, tp.lb + pref, lvl);
+      for (size_t i = 0; i < lvl.size(); i++) {
+        double score = ((double)(i + 1) / (double)lvl.size()) * 10;
+        double normalized = std::floor(score) * 10000.0;
+        for (int n : tp.doms[lvl[i]].nodes) topo_scores[n] = normalized;
+      }
+    }
+    // :249-300 getJobAllocatableDomains; levels from the lowest up: start at preferred / required, stop after required
+    std::vector<int> relevant;  // global level index, -1 = root
+    {
+      bool found_pref = false, found_req = false;
+      for (int l = tp.le - 1; l >= tp.lb - 1; l--) {
+        int li = l >= tp.lb ? l - tp.lb : -1;
+        if (l >= tp.lb && pref >= 0 && li == pref) found_pref = true;
+        if (l >= tp.lb && req >= 0 && li == req) found_req = true;
+        if (found_pref || found_req) relevant.push_back(l >= tp.lb ? l : -1);
+        if (found_req) break;
+      }
+    }
+    std::vector<char> allowed(tp.doms.size(), 1);
+    {
+      bool has_active = false;
+      for (int ps2 = 0; ps2 < v_nps(v); ps2++)
+        if (v_active_alloc(v, ps2) > 0) has_active = true;
+      if (has_active && req >= 0) {  // :269-300 getRelevantDomainsWithAllocatedPods
+        std::fill(allowed.begin(), allowed.end(), 0);
+        std::function<void(int)> mark = [&](int di) {
+          allowed[di] = 1;
+          for (int c : tp.doms[di].children) mark(c);
+        };
+        for (int di : tp.dom_at[req]) {
+          if (di < 0) continue;
+          bool has = false;
+          for (int ti : v_all_tasks(v))
+            if ((T[ti].status & kActiveAllocated) && T[ti].node >= 0 && tp.node_in[T[ti].node] &&
+                tp.dom_at[req][ND(tp.lb + req, T[ti].node)] == di)
+              has = true;
+          if (has) mark(di);
+        }
+      }
+    }
+    std::vector<char> chosen(tp.doms.size(), 0);
+    bool any = false;
+    for (int l : relevant)
+      for (size_t di = 0; di < tp.doms.size(); di++) {
+        if (tp.doms[di].level != l || !allowed[di]) continue;
+        if (!check_job_domain_fit(tasks_res, tasks_count, tp.doms[di])) continue;
+        chosen[di] = 1;
+        any = true;
+      }
+    if (!any) return {};
+    // sortDomainInfos: reverse level order of the (sorted) tree from the root
+    std::vector<std::vector<int>> levels;
+    std::vector<int> cur{0};
+    while (!cur.empty()) {
+      levels.push_back(cur);
+      std::vector<int> next;
+      for (int di : cur)
+        for (int c : tp.doms[di].children) next.push_back(c);
+      cur = next;
+    }
+    std::vector<char> in_valid(N, 0);
+    for (int n : valid) in_valid[n] = 1;
+    std::vector<std::vector<int>> out;
+    for (int li = (int)levels.size() - 1; li >= 0; li--)
+      for (int di : levels[li]) {
+        if (!chosen[di]) continue;
+        std::vector<int> ns;
+        for (int n : tp.doms[di].nodes)
+          if (in_valid[n]) ns.push_back(n);
+        out.push_back(ns);
+      }
+    return out;
+  }
+
   // ---------------- actions/common/allocate.go ----------------
   // :121-174 allocateTask + allocateTaskToNode
   bool allocate_task(int ti, const std::vector<int> *node_set, bool pipeline_only) {
@@ -1198,26 +1514,46 @@ struct kai_oracle {
     for (int ti : tta)
       for (int r = 0; r < QR; r++) req[r] += T[ti].req[r];
     if (over_capacity(ji, req)) return false;
-    int cp = stmt_checkpoint();
-    std::vector<int> sets = ordered_podsets(v);
-    for (int k : sets) {
-      const int s = J[ji].podsets[k];
-      int cp2 = stmt_checkpoint();
-      bool ok = true;
-      for (int ti : tta) {
-        if (T[ti].podset != s) continue;
-        if (!allocate_task(ti, node_set, pipeline_only)) {
-          ok = false;
-          break;
+    topo_scores.clear();  // PreJobAllocation (topology_plugin.go:52-55)
+    // allocateSubGroupSet(root): node sets from SubsetNodesFn, first one that takes the whole job wins
+    std::vector<std::vector<int>> node_sets;
+    const bool constrained = !job_topology.empty() && job_topology[ji] != -1;
+    if (constrained) {
+      std::vector<int> all;
+      if (node_set)
+        all = *node_set;
+      else
+        for (int n = 0; n < N; n++) all.push_back(n);
+      bool ok_sets = true;
+      node_sets = subset_nodes(v, tta, all, ok_sets);
+      if (!ok_sets) return false;
+    }
+    auto on_nodes = [&](const std::vector<int> *ns) {
+      int cp = stmt_checkpoint();
+      std::vector<int> sets = ordered_podsets(v);
+      for (int k : sets) {
+        const int s = J[ji].podsets[k];
+        int cp2 = stmt_checkpoint();
+        bool ok = true;
+        for (int ti : tta) {
+          if (T[ti].podset != s) continue;
+          if (!allocate_task(ti, ns, pipeline_only)) {
+            ok = false;
+            break;
+          }
+        }
+        if (!ok) {
+          stmt_rollback(cp2);
+          stmt_rollback(cp);
+          return false;
         }
       }
-      if (!ok) {
-        stmt_rollback(cp2);
-        stmt_rollback(cp);
-        return false;
-      }
-    }
-    return true;
+      return true;
+    };
+    if (!constrained) return on_nodes(node_set);
+    for (auto &ns : node_sets)
+      if (on_nodes(&ns)) return true;
+    return false;
   }
   // job_info.go:443-464 ShouldPipelineJob
   bool should_pipeline_job(int ji) const {
@@ -2416,6 +2752,25 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
   if (s->pred_mask && o->NPC > 0)
     o->pred_mask.assign(s->pred_mask, s->pred_mask + (size_t)o->NPC * o->mask_words);
   o->open_session();
+  o->topo_level_begin.clear();
+  o->node_domain.clear();
+  o->job_topology.clear();
+  o->job_req_level.clear();
+  o->job_pref_level.clear();
+  o->topos.clear();
+  if (s->n_topologies > 0 && s->topology_level_begin && s->node_domain) {
+    o->topo_level_begin.assign(s->topology_level_begin, s->topology_level_begin + s->n_topologies + 1);
+    size_t nl = (size_t)o->topo_level_begin.back();
+    o->node_domain.assign(s->node_domain, s->node_domain + nl * (size_t)o->N);
+    o->build_topologies();
+  }
+  if (s->job_topology) {
+    o->job_topology.assign(s->job_topology, s->job_topology + o->NJ);
+    o->job_req_level.assign(o->NJ, -1);
+    o->job_pref_level.assign(o->NJ, -1);
+    if (s->job_required_level) o->job_req_level.assign(s->job_required_level, s->job_required_level + o->NJ);
+    if (s->job_preferred_level) o->job_pref_level.assign(s->job_preferred_level, s->job_preferred_level + o->NJ);
+  }
   o->loaded = true;
   o->pods_placed = o->pods_evicted = 0;
   memset(&o->stats, 0, sizeof(o->stats));

@@ -200,6 +200,47 @@ def build_snapshot(topo: dict):
         if topo["Nodes"][name].get("MaxTaskNum") is not None and idle[3, n] < 0:
             idle[3, n] = 0
 
+    # ---- Topology CRs -> per-level domain ids (topology_plugin.go:57-110; DomainID = joined label values) ----
+    topo_kw = {}
+    topologies = topo.get("Topologies") or []
+    if topologies:
+        tnames = [tp["ObjectMeta"]["Name"] for tp in topologies]
+        level_begin = [0]
+        level_labels = []
+        for tp in topologies:
+            labels = [lv["NodeLabel"] for lv in tp["Spec"]["Levels"]]
+            level_labels.append(labels)
+            level_begin.append(level_begin[-1] + len(labels))
+        node_domain = np.full((level_begin[-1], N), -1, dtype=np.int32)
+        for k, labels in enumerate(level_labels):
+            for li in range(len(labels)):
+                ids = {}
+                for n, name in enumerate(node_names):
+                    nl = topo["Nodes"][name].get("Labels") or {}
+                    if any(lb not in nl for lb in labels[:li + 1]):
+                        continue
+                    ids[n] = ".".join(nl[lb] for lb in labels[:li + 1])
+                order = {d: i for i, d in enumerate(sorted(set(ids.values())))}
+                for n, d in ids.items():
+                    node_domain[level_begin[k] + li, n] = order[d]
+        j_topo = np.full(nj, -1, dtype=np.int32)
+        j_req = np.full(nj, -1, dtype=np.int32)
+        j_pref = np.full(nj, -1, dtype=np.int32)
+        for ji, job in enumerate(jobs):
+            tc = (job.get("RootSubGroupSet") or {}).get("topology_constraint")
+            if not tc or not tc.get("Topology"):
+                continue
+            if tc["Topology"] not in tnames:
+                j_topo[ji] = -2  # "Requested topology does not exist" (job_filtering.go:41-47): never schedulable
+                continue
+            k = tnames.index(tc["Topology"])
+            j_topo[ji] = k
+            for key, arr in (("RequiredLevel", j_req), ("PreferredLevel", j_pref)):
+                if tc.get(key):
+                    arr[ji] = level_labels[k].index(tc[key]) if tc[key] in level_labels[k] else -2
+        topo_kw = dict(topology_level_begin=np.array(level_begin, dtype=np.int32), node_domain=node_domain,
+                       job_topology=j_topo, job_required_level=j_req, job_preferred_level=j_pref)
+
     snap = abi.Snapshot(
         n_res=R,
         node_allocatable=alloc, node_idle=idle, node_releasing=rel,
@@ -216,6 +257,7 @@ def build_snapshot(topo: dict):
         podset_task_begin=np.array(podset_task_begin, dtype=np.int32),
         task_status=np.array(t_status, dtype=np.int32), task_node=np.array(t_node, dtype=np.int32),
         task_req=t_req_a, task_order_rank=np.array(t_rank, dtype=np.int32),
+        **topo_kw,
     )
     meta = {
         "node_names": node_names, "job_names": job_names, "task_names": t_names,

@@ -77,7 +77,15 @@ def resolve(x):
             if x["__call"].startswith("test_utils.Create") and len(x["args"]) == 1:
                 return resolve(x["args"][0])
             if x["__call"] == "subgroup_info.NewSubGroupSet":
-                return {"__unsupported": "inline SubGroupSet constructor (topology constraint)"}
+                # inline root set: NewSubGroupSet(RootSubGroupSetName, &TopologyConstraintInfo{...} | nil); the default
+                # podset (minAvailable = len(Tasks)) is added by jobs_fake.BuildJobInfo (jobs.go:117-134)
+                args = [resolve(a) for a in x["args"]]
+                tc = args[1] if len(args) > 1 else None
+                if isinstance(tc, dict) and set(tc) - {"__type"} <= {"Topology", "RequiredLevel", "PreferredLevel"}:
+                    return {"podsets": [], "topology_constraint": {k: v for k, v in tc.items() if k != "__type"}}
+                if tc is None or tc == {"__ident": "nil"}:
+                    return {"podsets": []}
+                return {"__unsupported": "inline SubGroupSet constructor"}
             return {"__call": x["__call"], "args": [resolve(a) for a in x["args"]]}
         if "__func" in x:
             return parse_subgroup_func(x["__func"])
@@ -125,8 +133,9 @@ def find_unresolved(x, path=""):
 
 def classify(topo: dict) -> str | None:
     """Return a skip reason if the case uses features outside the engine's scope, else None."""
-    if topo.get("Topologies"):
-        return "topology CRs"
+    for tp in topo.get("Topologies") or []:
+        if not (isinstance(tp, dict) and (tp.get("Spec") or {}).get("Levels")):
+            return "topology CR without levels"
     mocks = topo.get("Mocks") or {}
     if isinstance(mocks, dict) and mocks.get("SchedulerConf"):
         return "custom SchedulerConf"
@@ -135,12 +144,16 @@ def classify(topo: dict) -> str | None:
     for key in ("TestDRAObjects", "ResourceClaims", "ResourceSlices", "DeviceClasses"):
         if topo.get(key):
             return "DRA objects"
+    if not isinstance(topo.get("Nodes") or {}, dict):
+        return "nodes built by code"
     for name, node in (topo.get("Nodes") or {}).items():
+        if not isinstance(node, dict):
+            return "node built by code"
         if node.get("MigStrategy") or node.get("MigInstances"):
             return "MIG node"
         if node.get("GpuMemorySynced") is not None or node.get("GPUMemory"):
             return "GPU memory"
-        if node.get("Labels"):
+        if node.get("Labels") and not topo.get("Topologies"):
             return "node labels"
     for job in topo.get("Jobs") or []:
         g = job.get("RequiredGPUsPerTask", 0) or 0

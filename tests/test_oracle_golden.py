@@ -52,7 +52,7 @@ def test_integration_tables(cid, case):
 
 
 def test_case_counts():
-    assert len(INTEGRATION) == 58
-    assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 24 and len(PREEMPT) == 31
+    assert len(INTEGRATION) == 60
+    assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 25 and len(PREEMPT) == 31
     # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
-    assert len(ALLOCATE) == 41
+    assert len(ALLOCATE) == 51  # allocate 21 + gang 6 + elastic 7 + subgroups 7 + topology 10
