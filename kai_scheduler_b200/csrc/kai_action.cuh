@@ -228,7 +228,8 @@ __device__ __forceinline__ bool node_key(const Decision &d, int R, const double 
 
 // The sweep over this CTA's tile followed by the block argmax on (score desc, name rank asc).
 __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, Cand *sh_warp,
-                          const int *excl = nullptr, int n_excl = 0, int *fit_count = nullptr) {
+                          const int *excl = nullptr, int n_excl = 0, int *fit_count = nullptr, int xbits = 0,
+                          int pref_level = -1, const unsigned char *dom_bucket = nullptr) {
   Cand best;
   int n_fit = 0;
   best.score = -1.0;
@@ -238,12 +239,19 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
   for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
     int n = tl.node[ln];
     if (d.restricted && !(tl.flags[ln] & kTileFeas)) continue;
+    if ((xbits & XB_RESTRICT_DOM) && !(tl.flags[ln] & kTileDom)) continue;
     if (mask && !((__ldg(&mask[n >> 5]) >> (n & 31)) & 1u)) continue;
     double score;
     bool fit_i;
     if (!node_key(d, tl.R, tl.I + ln, tl.L + ln, tl.npc, tl.Agpu[ln], tl.Acpu[ln], tl.gpu_count[ln], tl.flags[ln], n,
                   score, fit_i))
       continue;
+    if (pref_level >= 0) {  // topology/node_scoring.go:17-53, the last NodeOrderFn of the default tiers
+      const int dd = tl.dom[pref_level * tl.npc + ln];
+      const unsigned char bk = (dd >= 0 && dd < kDomBuckets) ? dom_bucket[dd] : (unsigned char)255;
+      if (bk == 255) continue;  // no entry: NodeOrderFn fails, the node is dropped (session.go:247-251)
+      score = __dadd_rn(score, __dmul_rn((double)bk, 10000.0));
+    }
     n_fit++;
     bool skip = false;
     for (int x = 0; x < n_excl; x++)
@@ -889,6 +897,8 @@ struct ScanShared {
   Decision dec;
   Track trk[2];
   int kind, n_delta, batching, xbits;
+  int pref_level;                           // topology node scoring: global level index or -1 (off)
+  unsigned char dom_bucket[kDomBuckets];    // bucket per preferred-level domain, 255 = no entry
   int2 delta[kMaxDelta];
   unsigned char mine[kMaxDelta];
   int fit_count;
@@ -931,6 +941,10 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     tile.flags = (uint32_t *)ptr;
     ptr += sizeof(uint32_t) * npc;
     tile.node = (int *)ptr;
+    ptr += sizeof(int) * npc;
+    tile.dom = (int *)ptr;
+    tile.n_dom_levels = p.node_domain ? p.n_dom_levels : 0;
+    sh.pref_level = -1;
   }
   __syncthreads();
   for (int ln = tid; ln < tile.count; ln += blockDim.x) {
@@ -946,6 +960,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     tile.gpu_count[ln] = s.gpu_count[n];
     tile.rank[ln] = rk;
     tile.flags[ln] = s.nflags[n];
+    for (int l = 0; l < tile.n_dom_levels; l++) tile.dom[l * tile.npc + ln] = p.node_domain[(size_t)l * s.N + n];
   }
   __syncthreads();
   unsigned int seq = p.seq0;
@@ -1028,7 +1043,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         int2 en = make_int2((int)(unsigned int)(lo & 0xffffffffu), (int)(unsigned int)(lo >> 32));
         sh.delta[e] = en;
         int ln = 0;
-        bool mine = tile_owns(tile, (unsigned int)(en.x & 0x0fffffff), ln) && ln < tile.count;
+        bool mine = en.x >= 0 && tile_owns(tile, (unsigned int)(en.x & 0x0fffffff), ln) && ln < tile.count;
         sh.mine[e] = mine ? 1 : 0;
         sh.dln[e] = ln | ((int)(hi >> 32) << 24);  // repeat count - 1 in the top byte
         if (mine && ((en.x >> 28) & 7) < ND_FEAS_SET)
@@ -1050,6 +1065,35 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         }
       }
       __syncthreads();
+    }
+    if (nd > 0) {  // extended entries, in list order: topology domain selection and the per-domain score table
+      for (int e = 0; e < nd; e++) {
+        const int2 en = sh.delta[e];
+        if (en.x >= 0) continue;
+        const int kind = (en.x >> 28) & 7;
+        const unsigned int a = (unsigned int)en.x & 0x0fffffffu, b = (unsigned int)en.y;
+        if (kind == EXT_SELECT || kind == EXT_SELECT_ROOT) {
+          for (int ln = tid; ln < tile.count; ln += blockDim.x) {
+            bool in;
+            if (kind == EXT_SELECT) {
+              in = tile.dom[((int)a - 1) * tile.npc + ln] == (int)b;
+            } else {
+              in = true;
+              for (int l = (int)(a & 0xff); l < (int)((a >> 8) & 0xff); l++)
+                if (tile.dom[l * tile.npc + ln] < 0) in = false;
+            }
+            tile.flags[ln] = in ? (tile.flags[ln] | kTileDom) : (tile.flags[ln] & ~kTileDom);
+          }
+        } else if (kind == EXT_SCORE_BEGIN) {
+          for (int i = tid; i < kDomBuckets; i += blockDim.x) sh.dom_bucket[i] = 255;
+          if (tid == 0) sh.pref_level = (int)a;
+        } else if (kind == EXT_SCORE) {
+          if (tid == 0 && a < (unsigned int)kDomBuckets) sh.dom_bucket[a] = (unsigned char)b;
+        } else if (kind == EXT_SCORE_END) {
+          if (tid == 0) sh.pref_level = -1;
+        }
+        __syncthreads();
+      }
     }
     if (sh.xbits & (XB_SNAP_ALL | XB_SNAP_GPUFREE)) {  // common.FeasibleNodesForJob (feasible_nodes.go:11-26)
       const bool all = (sh.xbits & XB_SNAP_ALL) != 0;
@@ -1073,6 +1117,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
             double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
             if (overall == 0) continue;
             if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
+            if ((sh.xbits & XB_RESTRICT_DOM) && !(tile.flags[ln] & kTileDom)) continue;
             double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
             if (cur < mn[k]) mn[k] = cur;
             if (cur > mx[k]) mx[k] = cur;
@@ -1132,7 +1177,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       if (tid == 0) sh.fit_count = 0;
       __syncthreads();
       for (int m = 0; m < kTopM; m++) {
-        Cand c = scan_tile(tile, sh.dec, s, sh_warp, sh.excl, m, m == 0 ? &sh.fit_count : nullptr);
+        Cand c = scan_tile(tile, sh.dec, s, sh_warp, sh.excl, m, m == 0 ? &sh.fit_count : nullptr, sh.xbits, sh.pref_level, sh.dom_bucket);
         if (tid == 0) {
           sh.cands[m] = c;
           sh.excl[m] = c.ln;
@@ -1166,7 +1211,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         st_relaxed_sys_b128(lines + 2 * tid, (unsigned long long)__double_as_longlong(c.score), hi);
       }
     } else if (kind == DK_SCAN) {
-      Cand local = scan_tile(tile, sh.dec, s, sh_warp);
+      Cand local = scan_tile(tile, sh.dec, s, sh_warp, nullptr, 0, nullptr, sh.xbits, sh.pref_level, sh.dom_bucket);
       long long c4 = clock64();
       if (tid == 0) ts[4] += c4 - c3;
       if (warp == 0) publish_candidate(sh.trk, tile, sh.dec, local, slot, seq & 0xffffffu, sh.batching, false, my == 0 ? p.counters + 40 : nullptr);
@@ -1178,6 +1223,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
           if (overall == 0) continue;
           if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
+          if ((sh.xbits & XB_RESTRICT_DOM) && !(tile.flags[ln] & kTileDom)) continue;
           double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
           if (cur < mn[k]) mn[k] = cur;
           if (cur > mx[k]) mx[k] = cur;
@@ -1207,6 +1253,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
           if (overall == 0) continue;
           if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
+          if ((sh.xbits & XB_RESTRICT_DOM) && !(tile.flags[ln] & kTileDom)) continue;
           double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
           if (cur == mn[k]) c[2 * k]++;
           if (cur == mx[k]) c[2 * k + 1]++;

@@ -25,6 +25,8 @@ constexpr int kTopM = 4;              // candidates every scanner returns per sw
 constexpr int kListScanners = 2048;   // scanners of all GPUs of a box (list lines in host memory)
 constexpr int kListLineWords = 8;     // one 64-byte line = 4 tagged words
 constexpr int kListLines = 1 + kTopM; // line 0: the M candidate words, lines 1..M: row values of candidate m
+constexpr int kMaxDomLevels = 8;      // topology levels of all Topology CRs together (rows keep one domain id per level)
+constexpr int kDomBuckets = 4096;     // preferred-level domains that can carry a node score at a time
 
 constexpr int kActiveUsed = KAI_POD_ALLOCATED | KAI_POD_PIPELINED | KAI_POD_BINDING | KAI_POD_BOUND |
                             KAI_POD_RUNNING | KAI_POD_RELEASING;
@@ -162,6 +164,8 @@ struct ActionParams {
   int topm;             // mode 1: scanners answer with their kTopM best rows (0 = single best through the relay)
   unsigned long long *h_list;  // mode 1: [2][kListScanners][kListLines][kListLineWords] in (shared) host memory
   int scanner_base;     // global index of this GPU's scanner 0 in h_list
+  const int *node_domain;  // [n_dom_levels][N] topology domain of every node per level (-1 = label missing), or null
+  int n_dom_levels;
 };
 
 }  // namespace kai

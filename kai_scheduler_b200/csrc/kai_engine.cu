@@ -127,7 +127,10 @@ struct kai_engine {
   std::vector<int> rank_to_node_h;
   // solver actions: second NodeInfo.PodInfos entry of a task (evicted from A, pipelined to B), mirror of the GPU column
   std::vector<int> on_other_node, on_other_status;
-  std::vector<double> h_ig, h_lg;
+  std::vector<double> h_i, h_l;  // host mirror of Idle / Releasing [R][N]
+  int *d_node_domain = nullptr;
+  TopologyHost topo;
+  int n_dom_levels = 0;
   bool mirror_valid = false;  // h_ig / h_lg followed every delta since the load (host-sequenced actions only)
   std::vector<int> job_signature;
   size_t dev_only_begin = 0, dev_only_bytes = 0;
@@ -226,6 +229,7 @@ void kai_engine_destroy(kai_engine *e) {
   e->stage.release();
   e->rstage.release();
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  if (e->d_node_domain) cudaFree(e->d_node_domain);
   if (e->shm_base) {
     if (e->shm_registered) cudaHostUnregister(e->shm_base);
     munmap(e->shm_base, e->shm_bytes);
@@ -607,8 +611,10 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   }
   int npc = std::max(1, (n_shard_rows + (grid - 1) - 1) / (grid - 1));
   npc = (npc + 1) & ~1;  // keep the int arrays 8-byte aligned
-  size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4), 16);
-  const size_t smem_limit = (size_t)e->max_smem_optin - 24 * 1024;  // static shared memory of k_action
+  const int n_dom_levels = (s->n_topologies > 0 && s->topology_level_begin && s->node_domain) ? s->topology_level_begin[s->n_topologies] : 0;
+  if (n_dom_levels > kMaxDomLevels) return e->fail(KAI_ERR_UNSUPPORTED, "more topology levels than kMaxDomLevels");
+  size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4 + (size_t)4 * n_dom_levels), 16);
+  const size_t smem_limit = (size_t)e->max_smem_optin - 28 * 1024;  // static shared memory of k_action
   if (tile_bytes > smem_limit)
     return e->fail(KAI_ERR_UNSUPPORTED, "node tile does not fit in shared memory (N too large for one GPU tile)");
   bool hot_in_smem = hot <= smem_limit;
@@ -683,8 +689,18 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->on_other_node.clear();
   e->on_other_status.clear();
   e->job_signature.clear();
-  e->h_ig.assign(s->node_idle + (size_t)KAI_RES_GPU * s->n_nodes, s->node_idle + (size_t)(KAI_RES_GPU + 1) * s->n_nodes);
-  e->h_lg.assign(s->node_releasing + (size_t)KAI_RES_GPU * s->n_nodes, s->node_releasing + (size_t)(KAI_RES_GPU + 1) * s->n_nodes);
+  e->h_i.assign(s->node_idle, s->node_idle + (size_t)s->n_res * s->n_nodes);
+  e->h_l.assign(s->node_releasing, s->node_releasing + (size_t)s->n_res * s->n_nodes);
+  if (e->d_node_domain) {
+    cudaFree(e->d_node_domain);
+    e->d_node_domain = nullptr;
+  }
+  e->n_dom_levels = n_dom_levels;
+  e->topo.build(s);
+  if (n_dom_levels > 0 && s->n_nodes > 0) {
+    CK(cudaMalloc(&e->d_node_domain, sizeof(int) * (size_t)n_dom_levels * s->n_nodes));
+    CK(cudaMemcpy(e->d_node_domain, s->node_domain, sizeof(int) * (size_t)n_dom_levels * s->n_nodes, cudaMemcpyHostToDevice));
+  }
   e->mirror_valid = true;
   if (s->job_signature) e->job_signature.assign(s->job_signature, s->job_signature + s->n_jobs);
   e->loaded = true;
@@ -770,6 +786,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   p.visits = e->d_visits;
   p.visits_cap = e->visits_cap;
   p.counters = e->counters;
+  p.node_domain = e->d_node_domain;
+  p.n_dom_levels = e->n_dom_levels;
   p.seq0 = e->seq;
   p.hot_in_smem = e->hot_in_smem ? 1 : 0;
   p.tile_bytes = e->tile_bytes;
@@ -787,6 +805,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (solver_action && e->cfg.shard_count > 1 && !e->mirror_valid)
     return e->fail(KAI_ERR_UNSUPPORTED, "multi-GPU solver actions need every earlier action of the cycle to be host-sequenced");
   if (!host_mode) e->mirror_valid = false;
+  if (!host_mode && e->topo.any())
+    for (int j = 0; j < e->J; j++)
+      if (e->topo.constrained(j)) return e->fail(KAI_ERR_UNSUPPORTED, "topology constraints need the host-sequenced mode");
   p.mode = host_mode ? 1 : 0;
   p.spin_log2 = host_mode ? 26 : 22;
   if (host_mode) {
@@ -813,12 +834,12 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     // host mirror of everything the open-session / prepare kernels produced
     CK(cudaMemcpyAsync(e->stage.host + e->dev_only_begin, e->dsnap.base + e->dev_only_begin, e->dev_only_bytes,
                        cudaMemcpyDeviceToHost, e->stream));
-    if (solver_action && !e->mirror_valid) {  // a device-sequenced action ran before: re-read the GPU column (one GPU)
-      e->h_ig.resize(e->N);
-      e->h_lg.resize(e->N);
+    if (!e->mirror_valid) {  // a device-sequenced action ran before: re-read the node tables (one GPU)
+      e->h_i.resize((size_t)e->R * e->N);
+      e->h_l.resize((size_t)e->R * e->N);
       if (e->N > 0) {
-        CK(cudaMemcpyAsync(e->h_ig.data(), e->ds.idle + (size_t)KAI_RES_GPU * e->N, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaMemcpyAsync(e->h_lg.data(), e->ds.rel + (size_t)KAI_RES_GPU * e->N, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_i.data(), e->ds.idle, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_l.data(), e->ds.rel, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
       }
     }
     cudaEventRecord(e->ev_mirror, e->stream);
@@ -852,6 +873,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.failed = false;
     hb.rank_to_node = e->rank_to_node_h.data();
     CK(cudaEventSynchronize(e->ev_mirror));
+    e->mirror_valid = true;  // from here on the host-sequenced deltas keep it in step
     // ---- sequencer state on the host ----
     const DevSnap &hs = e->hs;
     const int Q = e->Q, J = e->J;
@@ -908,8 +930,12 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     seq.p = &p;
     seq.delta_base = e->h_delta;
     seq.host_backend = &hb;
-    seq.mirror_ig = e->h_ig.data();
-    seq.mirror_lg = e->h_lg.data();
+    seq.mirror_i = e->h_i.data();
+    seq.mirror_l = e->h_l.data();
+    e->topo.mI = e->h_i.data();
+    e->topo.mL = e->h_l.data();
+    e->topo.t_req = hs.t_req;
+    seq.topology = e->topo.any() ? &e->topo : nullptr;
     seq.ctl = &ctl;
     seq.ops_cap = e->ops_cap;
     seq.batching = p.batching;
@@ -938,9 +964,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         n0[t] = on ? hs.t_node[t] : -1;
         s0[t] = hs.t_node_status[t];
       }
-      e->mirror_valid = true;  // from here on the host-sequenced deltas keep it in step
       double t_begin = HostBackend::now();
-      Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status, e->h_ig, e->h_lg);
+      Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status);
       solver.use_signatures = e->cfg.use_scheduling_signatures != 0;
       solver.job_signature = e->job_signature.empty() ? nullptr : e->job_signature.data();
       if (action == KAI_ACTION_RECLAIM)
@@ -1068,6 +1093,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     }
     return e->fail(KAI_ERR_CUDA, m2);
   }
+  if (c[6] == 2) return e->fail(KAI_ERR_UNSUPPORTED, "topology: more preferred-level domains than the score table holds (kDomBuckets)");
   if (c[6] != 0) return e->fail(KAI_ERR_CUDA, "device sequencer overflow (statement log)");
   return download(e, out, c[0], c[3], c[4]);
 }

@@ -18,6 +18,7 @@
 
 #include "kai_action.cuh"
 #include "kai_seq.cuh"
+#include "kai_topology.cuh"
 
 namespace kai {
 
@@ -342,6 +343,84 @@ struct HostBackend {
     ctl.n_delta = 0;
   }
 
+  // One sweep answered with the single best row (ctl.dec prepared by the caller): binpack extremes over the row set
+  // of THIS sweep (fused among the scanners on one GPU, through the host when sharded), then the scan.
+  void sweep_single(unsigned int xb) {
+    const bool one_gpu = seq.cfg->shard_count <= 1;
+    const bool binpack = ctl.dec.strategy == KAI_PLACEMENT_BINPACK;
+    ctl.batch.valid = 0;
+    if (!one_gpu && binpack) {
+      seq.minmax_exchanges++;
+      ctl.xbits = xb & XB_RESTRICT_DOM;
+      publish(DK_MINMAX);
+      ctl.xbits = 0;
+      gather_minmax();
+      if (failed) return;
+    }
+    if (one_gpu) ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
+    ctl.xbits = xb | XB_SINGLE | ((one_gpu && binpack) ? XB_FUSED_MM : 0);
+    const int keep = batching;
+    batching = 0;
+    publish(DK_SCAN);
+    batching = keep;
+    ctl.xbits = 0;
+    gather_candidates();
+    ctl.batch.valid = 0;
+    seq.sweeps++;
+    seq.nodes_scanned += seq.s->N;
+  }
+
+  // allocateSubGroupSet for a job whose root SubGroupSet carries a topology constraint (allocate.go:36-60 with
+  // topology.subSetNodesFn): candidate domains in order, the first one that takes every task wins.
+  bool allocate_constrained(TopologyHost &topo, int job, const std::vector<int> &tta) {
+    const DevSnap &s = *seq.s;
+    bool has_active = false;
+    std::vector<int> active_nodes;
+    for (int ps = s.j_ps_begin[job]; ps < s.j_ps_begin[job + 1]; ps++) {
+      if (ps_get(seq, ps, 0) > 0) has_active = true;
+      for (int t = s.ps_task_begin[ps]; t < s.ps_task_begin[ps + 1]; t++)
+        if (seq.rp.t_status[t] & kActiveAllocated) active_nodes.push_back(seq.rp.t_node[t]);
+    }
+    TopologyHost::Result r = topo.subset(job, tta, [](int) { return true; }, has_active, active_nodes);
+    if (!r.ok || r.domains.empty()) return false;
+    list_invalidate();
+    if (!topo.push_scores(seq, r)) {
+      seq.error = 2;
+      return false;
+    }
+    bool placed = false;
+    for (int di : r.domains) {
+      if (failed) break;
+      const int cp = seq.n_ops;
+      topo.select_domain(seq, r, di);
+      bool ok = true;
+      for (int t : tta) {
+        if (!seq_prepare_task(seq, t, job)) {
+          ok = false;
+          break;
+        }
+        ctl.use_batch = 0;
+        sweep_single(XB_RESTRICT_DOM);
+        if (failed || ctl.win.node < 0) {
+          ok = false;
+          break;
+        }
+        if (ctl.win.flags & SLOT_TO_IDLE)
+          stmt_allocate(seq, t, ctl.win.node, ctl.ctx_fresh != 0);
+        else
+          stmt_pipeline(seq, t, ctl.win.node, ctl.ctx_fresh != 0);
+      }
+      if (ok) {
+        placed = true;
+        break;
+      }
+      stmt_rollback(seq, cp);
+    }
+    topo.clear_scores(seq, r);
+    node_state_disturbed(seq);
+    return placed;
+  }
+
   void flush_deltas() {
     publish(DK_FLUSH);
     const unsigned int seq_no = ctl.seq;
@@ -403,7 +482,12 @@ struct HostBackend {
       }
       bool job_success = !over_capacity(seq, job, req);
       lap(1);
-      if (job_success) {
+      TopologyHost *topo = (TopologyHost *)seq.topology;
+      if (job_success && topo && topo->constrained(job)) {
+        std::vector<int> tta(n);
+        for (int k = 0; k < n; k++) tta[k] = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
+        job_success = allocate_constrained(*topo, job, tta);
+      } else if (job_success) {
         for (int k = 0; k < n; k++) {
           int t = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
           if (!seq_prepare_task(seq, t, job)) {

@@ -143,7 +143,18 @@ enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4, DK_TOPK = 5 };
 // sweep over a changed node set needs no separate MINMAX round trip through the host.
 // XB_SINGLE: answer this SCAN with the single best row through the relay's reduction (cheaper sweep when the
 // list would be used once: heterogeneous requests, solver simulations) instead of the top-M lists.
-enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4, XB_FUSED_MM = 8, XB_SINGLE = 16 };
+// XB_RESTRICT_DOM: sweep only the rows of the topology domain selected by the last EXT_SELECT entry.
+enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4, XB_FUSED_MM = 8, XB_SINGLE = 16, XB_RESTRICT_DOM = 32 };
+constexpr uint32_t kTileDom = 1u << 29;  // tile flag bit: row belongs to the selected topology domain
+// Extended delta entries (low word bit 31 set; every scanner applies them, they name no row):
+//   [31]=1 [30:28]=kind [27:0]=a | b
+enum {
+  EXT_SELECT = 0,       // a = level + 1 (global level index), b = domain id: DOM bit = (dom[level][row] == b)
+  EXT_SELECT_ROOT = 1,  // a = lb | le << 8: DOM bit = the row carries every level label of the topology [lb, le)
+  EXT_SCORE_BEGIN = 2,  // a = preferred level (global): clear the per-domain bucket table, scoring on
+  EXT_SCORE = 3,        // a = domain id at the preferred level, b = bucket: node score = bucket * scores.Topology
+  EXT_SCORE_END = 4     // scoring off
+};
 constexpr uint32_t kTileFeas = 1u << 30;  // tile flag bit: row belongs to the feasible-node set
 enum { DB_GPU_TASK = 1, DB_BEST_EFFORT = 2, DB_PIPELINE_ONLY = 4, DB_BATCHING = 8, DB_DIRTY0 = 16, DB_DIRTY1 = 32 };
 
@@ -171,6 +182,8 @@ struct Tile {  // shared-memory node tile of this CTA
   int *rank;            // [npc]
   uint32_t *flags;      // [npc]
   int *node;            // [npc] node index of the row
+  int *dom;             // [n_dom_levels][npc] topology domain per level
+  int n_dom_levels;
   int npc, count, R;
   // Rows are striped by NAME RANK over the GPUs of the box and over the scanners of a GPU: row j of scanner `my`
   // of shard `shard` is the node of name rank (j * nscan + my) * nshard + shard.  Consecutive ranks land on
@@ -193,8 +206,9 @@ struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   const ActionParams *p;
   unsigned long long *delta_base;  // tagged node-delta words [2][kMaxDelta] (device memory or pinned host memory)
   void *host_backend;               // host-sequenced mode: HostBackend*
-  double *mirror_ig, *mirror_lg;    // host-sequenced mode: GPU column of Idle / Releasing of ALL nodes, kept in step with
-                                    // the deltas (point look-ups of the solver; identical on every rank)
+  double *mirror_i, *mirror_l;      // host-sequenced mode: Idle / Releasing [R][N] of ALL nodes, kept in step with the
+                                    // deltas (point look-ups of the solver, topology domain sums; identical on every rank)
+  void *topology;                   // host-sequenced mode: TopologyHost* (or null)
   Replica rp;
   Tile *tile;
   Ctl *ctl;
@@ -275,8 +289,10 @@ KAI_HD void close_delta(Ctl &c, unsigned long long *delta_base) {
 KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
 #ifndef __CUDA_ARCH__
-  if (q.mirror_ig && code < ND_FEAS_SET)
-    apply_delta_row(q.mirror_ig[node], q.mirror_lg[node], code, q.s->t_req[(size_t)t * q.s->R + KAI_RES_GPU]);
+  if (q.mirror_i && code < ND_FEAS_SET)
+    for (int r = 0; r < q.s->R; r++)
+      apply_delta_row(q.mirror_i[(size_t)r * q.s->N + node], q.mirror_l[(size_t)r * q.s->N + node], code,
+                      q.s->t_req[(size_t)t * q.s->R + r]);
 #endif
   // the delta names the node by its NAME RANK: that is what decides which scanner owns the row
   const unsigned int key = (unsigned int)(kldg(&q.s->name_rank[node]) | (code << 28));
@@ -296,6 +312,17 @@ KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   c.last_dkey = key;
   c.last_dtask = t;
   c.last_dcount = 1;
+}
+// extended entry: applied by every scanner (topology domain selection / score table)
+KAI_HD void emit_ext(Seq &q, int kind, unsigned int a, unsigned int b) {
+  Ctl &c = *q.ctl;
+  close_delta(c, q.delta_base);
+  if (c.n_delta >= kMaxDelta) seq_flush_deltas(q);
+  c.n_delta++;
+  c.last_dkey = 0x80000000u | ((unsigned int)kind << 28) | (a & 0x0fffffffu);
+  c.last_dtask = (int)b;
+  c.last_dcount = 1;
+  close_delta(c, q.delta_base);  // written at once; never folded
 }
 KAI_HD void node_add_task(Seq &q, int t, int n, int st) {  // n = task node, st = task status (just set)
   q.rp.t_node_status[t] = st;

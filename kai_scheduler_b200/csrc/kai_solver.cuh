@@ -89,7 +89,7 @@ struct Solver {
   // NodeInfo.PodInfos keeps a clone per node: a task evicted from A and pipelined to B sits on both
   std::vector<int> &on_node0, &on_status0, &on_node1, &on_status1;
   double *qa, *qnp;        // queue allocated / allocated-non-preemptible [3][Q]
-  std::vector<double> &hIg, &hLg;  // host mirror of the GPU column of Idle / Releasing (point look-ups only)
+  double *hIg, *hLg;  // GPU column of the host mirror of Idle / Releasing (seq.mirror_i / mirror_l; point look-ups only)
   // attempt-start values of touched rows (FeasibleNodesForJob and the filter's base map read the state the
   // attempt started from)
   std::vector<int> touched_epoch;
@@ -105,10 +105,11 @@ struct Solver {
   long long sweeps = 0, scenarios = 0, topk_sweeps = 0, simulations = 0;
   double t_sweeps = 0, t_sim_setup = 0, t_evict = 0, t_victims_queue = 0, t_vq_pop = 0, t_tte = 0, t_addp = 0, t_filter = 0, t_bypod = 0, t_finit = 0;
 
-  Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1,
-         std::vector<double> &ig, std::vector<double> &lg)
+  Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1)
       : hb(hb_), seq(hb_.seq), ctl(hb_.ctl), s(*hb_.seq.s), cfg(*hb_.seq.cfg), N(s.N), Q(s.Q), J(s.J), S(s.S), T(s.T),
-        R(s.R), on_node0(n0), on_status0(s0), on_node1(n1), on_status1(s1), hIg(ig), hLg(lg) {
+        R(s.R), on_node0(n0), on_status0(s0), on_node1(n1), on_status1(s1) {
+    hIg = seq.mirror_i + (size_t)KAI_RES_GPU * N;
+    hLg = seq.mirror_l + (size_t)KAI_RES_GPU * N;
     st = seq.rp.t_status;
     tn = seq.rp.t_node;
     tvirt = seq.rp.t_virtual;
@@ -490,6 +491,7 @@ struct Solver {
   // ---------------- GPU sweeps ----------------
   bool gpu_failed() const { return hb.failed; }
   // allocateTask (allocate.go:121-163) in a simulation: one restricted pipeline-only sweep
+  unsigned int sweep_extra_bits = 0;  // XB_RESTRICT_DOM while a topology domain is selected
   int sweep_pick_node(int t) {
     Decision &d = ctl.dec;
     for (int r = 0; r < KAI_MAX_RES; r++) d.req[r] = r < R ? req(t, r) : 0.0;
@@ -508,22 +510,10 @@ struct Solver {
     ctl.batch.valid = 0;
     // pack.go:66-86 over the node set of this simulation: the scanners exchange their extremes among themselves
     ctl.trk[0].dirty = ctl.trk[1].dirty = 1;
-    const bool one_gpu = cfg.shard_count <= 1;
-    if (!one_gpu && d.strategy == KAI_PLACEMENT_BINPACK) {  // several GPUs: the extremes travel through the host
-      seq.minmax_exchanges++;
-      hb.publish(DK_MINMAX);
-      hb.gather_minmax();
-      if (hb.failed) return -1;
-    }
-    ctl.xbits = ((one_gpu && d.strategy == KAI_PLACEMENT_BINPACK) ? XB_FUSED_MM : 0) | XB_SINGLE;  // only the winner is needed
     const double t0 = HostBackend::now();
-    hb.publish(DK_SCAN);
-    ctl.xbits = 0;
-    hb.gather_candidates();
+    hb.sweep_single(sweep_extra_bits);  // only the winner is needed
     t_sweeps += HostBackend::now() - t0;
     sweeps++;
-    seq.sweeps++;
-    seq.nodes_scanned += N;
     if (hb.failed) return -1;
     return ctl.win.node;
   }
@@ -573,6 +563,48 @@ struct Solver {
     for (int t : tta)
       for (int r = 0; r < QR; r++) rq[r] += req(t, r);
     if (over_capacity(j, rq)) return false;
+    TopologyHost *topo = (TopologyHost *)seq.topology;
+    if (topo && topo->constrained(j)) {  // allocateSubGroupSet with topology.subSetNodesFn (job_filtering.go:34-112)
+      bool has_active = false;
+      for (int k = 0; k < v_nps(v); k++)
+        if (v_active_alloc(v, k) > 0) has_active = true;
+      std::vector<int> active_nodes;
+      for (int t : v_all_tasks(v))
+        if (st[t] & kActiveAllocated) active_nodes.push_back(tn[t]);
+      TopologyHost::Result r = topo->subset(j, tta, [&](int n) { return in_base(n) || feas_extra[n]; }, has_active, active_nodes);
+      if (!r.ok || r.domains.empty()) return false;
+      if (!topo->push_scores(seq, r)) {
+        seq.error = 2;
+        return false;
+      }
+      bool placed = false;
+      sweep_extra_bits = XB_RESTRICT_DOM;
+      for (int di : r.domains) {
+        if (gpu_failed()) break;
+        int cp = stmt_checkpoint();
+        topo->select_domain(seq, r, di);
+        bool ok = true;
+        for (int k : ordered_podsets(v)) {
+          int ps = ps_begin(j) + k;
+          for (int t : tta) {
+            if (s.t_podset[t] != ps) continue;
+            if (!allocate_task(t)) {
+              ok = false;
+              break;
+            }
+          }
+          if (!ok) break;
+        }
+        if (ok) {
+          placed = true;
+          break;
+        }
+        stmt_rollback(cp);
+      }
+      sweep_extra_bits = 0;
+      topo->clear_scores(seq, r);
+      return placed;
+    }
     int cp = stmt_checkpoint();
     for (int k : ordered_podsets(v)) {
       int ps = ps_begin(j) + k;

@@ -1,0 +1,363 @@
+// kai_topology.cuh — host side of the topology plugin (row a18) for the host-sequenced engine.
+//
+// Replaces: plugins/topology/topology_plugin.go:57-110 (domain tree from node labels), job_filtering.go:34-527
+// (subSetNodesFn: lowest common domain, per-domain free resources and allocatable pods, bin-packing order of the
+// tree, candidate domains bottom-up) and node_scoring.go:36-68 (preferred-level node scores).  Scope: the topology
+// constraint of the job's root SubGroupSet.
+//
+// Division of work: the host keeps the domain trees and evaluates them against its mirror of the node tables (which
+// follows every node delta); the GPU does what is per (pod, node): the scanners carry one domain id per level and
+// row, an EXT_SELECT entry turns a domain into the row set of the following sweeps (XB_RESTRICT_DOM), and the
+// preferred-level score of a row is a table look-up by its domain id (EXT_SCORE entries), added as the last
+// NodeOrderFn term.  Children of a domain that sortTree never reaches keep ascending DomainID order (the reference:
+// node map iteration order).  Host-only code.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <vector>
+
+#include "kai_seq.cuh"
+
+namespace kai {
+
+struct TopologyHost {
+  struct Dom {
+    int level = -1;  // global level index, -1 = root
+    int id = 0;      // dense id inside the level (ascending DomainID order)
+    std::vector<int> children, nodes;
+    int alloc_pods = -1;  // allocatablePodsNotSet
+    double free[KAI_MAX_RES] = {0};
+  };
+  struct Topo {
+    int lb = 0, le = 0;
+    std::vector<Dom> doms;                 // doms[0] = root
+    std::vector<std::vector<int>> dom_at;  // [level - lb][id] -> index into doms
+    std::vector<char> node_in;
+  };
+  int N = 0, R = 4;
+  std::vector<int> level_begin, node_domain, job_topology, job_req, job_pref;
+  std::vector<Topo> topos;
+  const double *mI = nullptr, *mL = nullptr;  // host mirror of Idle / Releasing [R][N]
+  const double *t_req = nullptr;              // [T][R] (engine task numbering)
+
+  int ND(int level, int n) const { return node_domain[(size_t)level * N + n]; }
+  bool any() const { return !topos.empty() && !job_topology.empty(); }
+  bool constrained(int job) const { return any() && job_topology[job] != -1; }
+  double avail(int r, int n) const { return mI[(size_t)r * N + n] + mL[(size_t)r * N + n]; }
+
+  void build(const kai_snapshot *s) {
+    topos.clear();
+    level_begin.clear();
+    node_domain.clear();
+    job_topology.clear();
+    N = s->n_nodes;
+    R = s->n_res;
+    if (s->n_topologies > 0 && s->topology_level_begin && s->node_domain) {
+      level_begin.assign(s->topology_level_begin, s->topology_level_begin + s->n_topologies + 1);
+      node_domain.assign(s->node_domain, s->node_domain + (size_t)level_begin.back() * N);
+      for (int k = 0; k < s->n_topologies; k++) {
+        Topo tp;
+        tp.lb = level_begin[k];
+        tp.le = level_begin[k + 1];
+        tp.doms.emplace_back();
+        tp.node_in.assign(N, 0);
+        tp.dom_at.assign(tp.le - tp.lb, {});
+        for (int l = tp.lb; l < tp.le; l++) {
+          int mx = -1;
+          for (int n = 0; n < N; n++) mx = std::max(mx, ND(l, n));
+          tp.dom_at[l - tp.lb].assign(mx + 1, -1);
+        }
+        for (int n = 0; n < N; n++) {
+          bool in = tp.le > tp.lb;
+          for (int l = tp.lb; l < tp.le; l++)
+            if (ND(l, n) < 0) in = false;
+          if (!in) continue;
+          tp.node_in[n] = 1;
+          tp.doms[0].nodes.push_back(n);
+          int parent = 0;
+          for (int l = tp.lb; l < tp.le; l++) {
+            int &di = tp.dom_at[l - tp.lb][ND(l, n)];
+            if (di < 0) {
+              di = (int)tp.doms.size();
+              tp.doms.emplace_back();
+              tp.doms[di].level = l;
+              tp.doms[di].id = ND(l, n);
+              tp.doms[parent].children.push_back(di);
+            }
+            tp.doms[di].nodes.push_back(n);
+            parent = di;
+          }
+        }
+        for (auto &d : tp.doms)
+          std::sort(d.children.begin(), d.children.end(), [&](int a, int b) { return tp.doms[a].id < tp.doms[b].id; });
+        topos.push_back(tp);
+      }
+    }
+    if (s->job_topology) {
+      job_topology.assign(s->job_topology, s->job_topology + s->n_jobs);
+      job_req.assign(s->n_jobs, -1);
+      job_pref.assign(s->n_jobs, -1);
+      if (s->job_required_level) job_req.assign(s->job_required_level, s->job_required_level + s->n_jobs);
+      if (s->job_preferred_level) job_pref.assign(s->job_preferred_level, s->job_preferred_level + s->n_jobs);
+    }
+  }
+
+  // job_filtering.go:445-486 getJobRatioToFreeResources (Quantity.Value() of a milli quantity rounds up)
+  double job_ratio_to_free(const double *tasks_res, const Dom &d) const {
+    double ratio = 0.0;
+    bool empty = true;
+    for (int r = 0; r < R; r++)
+      if (tasks_res[r] > 0) empty = false;
+    if (empty) return 0.0;
+    if (tasks_res[KAI_RES_GPU] > 0) ratio = std::max(ratio, tasks_res[KAI_RES_GPU] / d.free[KAI_RES_GPU]);
+    for (int r = 0; r < R; r++) {
+      if (r == KAI_RES_GPU || r == 3) continue;
+      int64_t tq = r == KAI_RES_MEM ? (int64_t)tasks_res[r] : (int64_t)std::ceil((double)(int64_t)tasks_res[r] / 1000.0);
+      if (tq == 0) continue;
+      int64_t fq = r == KAI_RES_MEM ? (int64_t)d.free[r] : (int64_t)std::ceil((double)(int64_t)d.free[r] / 1000.0);
+      double rr = fq == 0 ? 1000.0 : (double)tq / (double)fq;
+      ratio = std::max(ratio, rr);
+    }
+    return ratio;
+  }
+  bool domain_fit(const double *tasks_res, int tasks_count, const Dom &d) const {  // :302-320 checkJobDomainFit
+    if (d.alloc_pods != -1) return d.alloc_pods >= tasks_count;
+    return !(job_ratio_to_free(tasks_res, d) > 1.0);
+  }
+  void subtree_free(Topo &tp, int di) {  // :191-211
+    Dom &d = tp.doms[di];
+    if (d.children.empty()) {
+      for (int n : d.nodes)
+        for (int r = 0; r < R; r++) {
+          d.free[r] += mI[(size_t)r * N + n];
+          d.free[r] += mL[(size_t)r * N + n];
+        }
+      return;
+    }
+    for (int c : d.children) {
+      subtree_free(tp, c);
+      for (int r = 0; r < R; r++) tp.doms[di].free[r] += tp.doms[c].free[r];
+    }
+  }
+  int subtree_allocatable(Topo &tp, int di, const double *max_pod, std::vector<std::vector<double>> &test_pods, int n_tasks) {
+    Dom &d = tp.doms[di];
+    d.alloc_pods = 0;
+    if (d.children.empty()) {
+      bool only_pods = true;
+      for (int r = 0; r < R; r++)
+        if (r == 3 ? max_pod[r] > 1 : max_pod[r] > 0) only_pods = false;
+      for (int n : d.nodes) {
+        if (only_pods) {
+          d.alloc_pods += n_tasks;
+          continue;
+        }
+        auto fits_pod = [&](const std::vector<double> &rq) {
+          for (int r = 0; r < R; r++) {
+            double a = avail(r, n);
+            if (r >= 3) {
+              if (rq[r] != 0 && rq[r] > a) return false;
+            } else if (rq[r] > a)
+              return false;
+          }
+          return true;
+        };
+        int cnt = 0;
+        for (auto &tpod : test_pods) {
+          if (fits_pod(tpod))
+            cnt++;
+          else
+            break;
+        }
+        if (cnt == (int)test_pods.size()) {
+          for (;;) {
+            std::vector<double> next = test_pods.back();
+            for (int r = 0; r < R; r++) next[r] += max_pod[r];
+            test_pods.push_back(next);
+            if (fits_pod(next))
+              cnt++;
+            else
+              break;
+          }
+        }
+        d.alloc_pods += cnt;
+      }
+      return d.alloc_pods;
+    }
+    for (int c : d.children) {
+      int a = subtree_allocatable(tp, c, max_pod, test_pods, n_tasks);
+      tp.doms[di].alloc_pods += a;
+    }
+    return tp.doms[di].alloc_pods;
+  }
+  void sort_tree(Topo &tp, int di, const double *tasks_res, int max_depth_level) {  // :396-420
+    std::vector<std::pair<double, int>> keyed;
+    for (int c : tp.doms[di].children) keyed.push_back({job_ratio_to_free(tasks_res, tp.doms[c]), c});
+    std::stable_sort(keyed.begin(), keyed.end(), [&](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+      if (a.first != b.first) return a.first > b.first;
+      return tp.doms[a.second].id < tp.doms[b.second].id;
+    });
+    for (size_t i = 0; i < keyed.size(); i++) tp.doms[di].children[i] = keyed[i].second;
+    if (tp.doms[di].level == max_depth_level) return;
+    std::vector<int> ch = tp.doms[di].children;
+    for (int c : ch) sort_tree(tp, c, tasks_res, max_depth_level);
+  }
+  void level_domains(const Topo &tp, int di, int level, std::vector<int> &out) const {
+    if (tp.doms[di].level == level) {
+      out.push_back(di);
+      return;
+    }
+    for (int c : tp.doms[di].children) level_domains(tp, c, level, out);
+  }
+
+  struct Result {
+    bool ok = true;            // false: configuration error (the job fails)
+    int topo = -1;
+    std::vector<int> domains;  // candidate domains (indices into topos[topo].doms), in the order to try
+    int pref_level = -1;       // global level index when node scores apply
+    std::vector<std::pair<int, int>> scores;  // (domain id at the preferred level, bucket 0..10)
+  };
+  // subSetNodesFn for the job's root SubGroupSet.  `in_set(n)`: the node set handed to allocate (all nodes, or the
+  // solver's feasible set).  `active_nodes`: nodes of the job's active-allocated pods; has_active: any podset of the
+  // (view of the) job counts active-allocated pods.
+  Result subset(int job, const std::vector<int> &tasks, const std::function<bool(int)> &in_set, bool has_active,
+                const std::vector<int> &active_nodes) {
+    Result res;
+    const int k = job_topology[job];
+    if (k == -2) return res;  // requested topology does not exist: no node set
+    Topo &tp = topos[k];
+    res.topo = k;
+    const int req = job_req[job], pref = job_pref[job];
+    // common.go:17-61 lowestCommonDomainID over nodeSet ∩ topology nodes
+    int dom = 0;
+    {
+      int first = -1;
+      std::vector<char> all(tp.le - tp.lb, 1);
+      std::vector<int> value(tp.le - tp.lb, -1);
+      for (int n : tp.doms[0].nodes) {
+        if (!in_set(n)) continue;
+        if (first < 0) {
+          first = n;
+          for (int l = tp.lb; l < tp.le; l++) value[l - tp.lb] = ND(l, n);
+        } else {
+          for (int l = tp.lb; l < tp.le; l++)
+            if (ND(l, n) != value[l - tp.lb]) all[l - tp.lb] = 0;
+        }
+      }
+      for (int l = tp.lb; l < tp.le && first >= 0; l++) {
+        if (!all[l - tp.lb]) break;
+        dom = tp.dom_at[l - tp.lb][value[l - tp.lb]];
+        if (pref >= 0 && l - tp.lb == pref) break;
+      }
+    }
+    for (auto &d : tp.doms) {  // treeAllocatableCleanup
+      d.alloc_pods = -1;
+      for (int r = 0; r < KAI_MAX_RES; r++) d.free[r] = 0;
+    }
+    subtree_free(tp, dom);
+    int gpu_pods = 0;
+    for (int t : tasks)
+      if (t_req[(size_t)t * R + KAI_RES_GPU] > 0) gpu_pods++;
+    bool scalars_uniform = true;
+    for (int r = 3; r < R; r++) {
+      int c = 0;
+      for (int t : tasks)
+        if (t_req[(size_t)t * R + r] != 0) c++;
+      if (c != 0 && c != (int)tasks.size()) scalars_uniform = false;
+    }
+    if ((gpu_pods == (int)tasks.size() || gpu_pods == 0) && scalars_uniform) {  // useRepresentorPodsAccounting
+      std::vector<double> max_pod(R, 0.0);
+      for (int t : tasks)
+        for (int r = 0; r < R; r++) max_pod[r] = std::max(max_pod[r], t_req[(size_t)t * R + r]);
+      std::vector<std::vector<double>> test_pods{max_pod};
+      subtree_allocatable(tp, dom, max_pod.data(), test_pods, (int)tasks.size());
+    }
+    double tasks_res[KAI_MAX_RES] = {0};
+    for (int t : tasks)
+      for (int r = 0; r < R; r++) tasks_res[r] += t_req[(size_t)t * R + r];
+    const int tasks_count = (int)tasks.size();
+    if (!domain_fit(tasks_res, tasks_count, tp.doms[dom])) return res;
+    if (req == -2 || pref == -2 || (req < 0 && pref < 0)) {
+      res.ok = false;
+      return res;
+    }
+    sort_tree(tp, dom, tasks_res, pref >= 0 ? tp.lb + pref : tp.lb + req);
+    if (pref >= 0) {  // node_scoring.go:36-53
+      res.pref_level = tp.lb + pref;
+      std::vector<int> lvl;
+      level_domains(tp, dom, tp.lb + pref, lvl);
+      for (size_t i = 0; i < lvl.size(); i++) {
+        double score = ((double)(i + 1) / (double)lvl.size()) * 10;
+        res.scores.push_back({tp.doms[lvl[i]].id, (int)std::floor(score)});
+      }
+    }
+    std::vector<int> relevant;
+    {
+      bool found_pref = false, found_req = false;
+      for (int l = tp.le - 1; l >= tp.lb - 1; l--) {
+        int li = l >= tp.lb ? l - tp.lb : -1;
+        if (l >= tp.lb && pref >= 0 && li == pref) found_pref = true;
+        if (l >= tp.lb && req >= 0 && li == req) found_req = true;
+        if (found_pref || found_req) relevant.push_back(l >= tp.lb ? l : -1);
+        if (found_req) break;
+      }
+    }
+    std::vector<char> allowed(tp.doms.size(), 1);
+    if (has_active && req >= 0) {  // :269-300 getRelevantDomainsWithAllocatedPods
+      std::fill(allowed.begin(), allowed.end(), 0);
+      std::function<void(int)> mark = [&](int di) {
+        allowed[di] = 1;
+        for (int c : tp.doms[di].children) mark(c);
+      };
+      for (int n : active_nodes)
+        if (n >= 0 && tp.node_in[n]) mark(tp.dom_at[req][ND(tp.lb + req, n)]);
+    }
+    std::vector<char> chosen(tp.doms.size(), 0);
+    bool any_dom = false;
+    for (int l : relevant)
+      for (size_t di = 0; di < tp.doms.size(); di++) {
+        if (tp.doms[di].level != l || !allowed[di]) continue;
+        if (!domain_fit(tasks_res, tasks_count, tp.doms[di])) continue;
+        chosen[di] = 1;
+        any_dom = true;
+      }
+    if (!any_dom) return res;
+    std::vector<std::vector<int>> levels;  // sortDomainInfos: reverse level order of the sorted tree
+    std::vector<int> cur{0};
+    while (!cur.empty()) {
+      levels.push_back(cur);
+      std::vector<int> next;
+      for (int di : cur)
+        for (int c : tp.doms[di].children) next.push_back(c);
+      cur = next;
+    }
+    for (int li = (int)levels.size() - 1; li >= 0; li--)
+      for (int di : levels[li])
+        if (chosen[di]) res.domains.push_back(di);
+    return res;
+  }
+
+  // ---- GPU side: select a domain as the row set of the following sweeps; publish / clear the score table ----
+  void select_domain(Seq &seq, const Result &r, int di) const {
+    const Topo &tp = topos[r.topo];
+    const Dom &d = tp.doms[di];
+    if (d.level < 0)
+      emit_ext(seq, EXT_SELECT_ROOT, (unsigned int)(tp.lb | (tp.le << 8)), 0);
+    else
+      emit_ext(seq, EXT_SELECT, (unsigned int)(d.level + 1), (unsigned int)d.id);
+  }
+  bool push_scores(Seq &seq, const Result &r) const {  // false: more preferred-level domains than the table holds
+    if (r.pref_level < 0) return true;
+    emit_ext(seq, EXT_SCORE_BEGIN, (unsigned int)r.pref_level, 0);
+    for (auto &kv : r.scores) {
+      if (kv.first >= kDomBuckets) return false;
+      emit_ext(seq, EXT_SCORE, (unsigned int)kv.first, (unsigned int)kv.second);
+    }
+    return true;
+  }
+  void clear_scores(Seq &seq, const Result &r) const {
+    if (r.pref_level >= 0) emit_ext(seq, EXT_SCORE_END, 0, 0);
+  }
+};
+
+}  // namespace kai
