@@ -145,6 +145,10 @@ def main():
         kw = synthetic.CONFIGS[args.config]
         desc = (f"{args.config}: {kw['n_nodes']} nodes x {kw['n_jobs']} jobs x {kw.get('tasks_per_job', 1)} pods, "
                 f"{kw.get('n_queues', 4)} leaf queues, binpack, allocate action")
+    elif args.config in synthetic.TOPOLOGY_CONFIGS:
+        kw = synthetic.TOPOLOGY_CONFIGS[args.config]
+        desc = (f"{args.config}: {snap.n_nodes} nodes on 3 topology tiers (spine/leaf/rack), {kw['n_gangs']} gangs of 2-16 node-exclusive "
+                f"8-GPU pods ({int(snap.task_status.shape[0])} pods), required level leaf|rack, preferred rack; allocate action")
     else:
         kw = synthetic.RECLAIM_CONFIGS[args.config]
         desc = (f"{args.config}: {snap.n_nodes} nodes x 8 GPUs, {int((snap.task_status == abi.POD_RUNNING).sum())} running 1-GPU pods "

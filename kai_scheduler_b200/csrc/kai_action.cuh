@@ -564,7 +564,7 @@ __device__ void publish_candidate(const Track *trk, const Tile &tl, const Decisi
 // ---------------------------------------------------------------------------------------------
 enum { LF_TO_IDLE = 1, LF_EXHAUSTED = 2, LF_MORE = 4, LF_HAS_GPU = 8, LF_HAS_CPU = 16 };
 __device__ void publish_list_candidate(const Tile &tl, const Decision &d, Cand c, bool more, unsigned long long *line0_word,
-                                       unsigned long long *payload_line, unsigned int tag) {
+                                       unsigned long long *payload_line, unsigned int tag, double topo_term = 0.0) {
   const int lane = threadIdx.x & 31;
   uint32_t flags = more ? LF_MORE : 0u, repeat = 0;
   double Ig0 = 0, Lg0 = 0, Ic0 = 0, Lc0 = 0;
@@ -632,6 +632,7 @@ __device__ void publish_list_candidate(const Tile &tl, const Decision &d, Cand c
         place = cnt == 0 ? 0.0 : __ddiv_rn(cur, cnt);
       }
       sc = __dadd_rn(sc, place);
+      sc = __dadd_rn(sc, topo_term);  // the row's topology score is the same for every repeat
       bool ti = !d.pipeline_only && (d.best_effort || fi);
       if (ti != to_idle) ok = false;
       if (!(sc >= c.score)) ok = false;
@@ -1186,9 +1187,15 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       }
       if (tid == 0) ts[4] += clock64() - c3;
       unsigned long long *lines = p.h_list + ((size_t)(seq & 1) * kListScanners + (size_t)(p.scanner_base + my)) * kListLines * kListLineWords;
-      if (warp < kTopM)
+      if (warp < kTopM) {
+        double topo_term = 0.0;
+        if (sh.pref_level >= 0 && sh.cands[warp].rank != kRankNone) {
+          const int dd = tile.dom[sh.pref_level * tile.npc + sh.cands[warp].ln];
+          topo_term = __dmul_rn((double)((dd >= 0 && dd < kDomBuckets) ? sh.dom_bucket[dd] : 0), 10000.0);
+        }
         publish_list_candidate(tile, sh.dec, sh.cands[warp], sh.fit_count > kTopM, lines + 2 * warp,
-                               lines + (size_t)(1 + warp) * kListLineWords, seq & 0xffffffu);
+                               lines + (size_t)(1 + warp) * kListLineWords, seq & 0xffffffu, topo_term);
+      }
     } else if (kind == DK_TOPK) {
       // ---- accumulated_scenario_filters/idle_gpus: rows by idle + releasing GPUs, descending (name rank ascending
       //      among equals), strictly after the cutoff (req[0] = key, req[1] = rank, req[2] = cutoff present) ----

@@ -370,6 +370,78 @@ struct HostBackend {
     seq.nodes_scanned += seq.s->N;
   }
 
+  // allocateTasksOnNodeSet (allocate.go:104-119) for the tasks of the context job: lists / same-node batches while
+  // they apply, a sweep otherwise.  `tasks` = explicit list or null for the context's own range.
+  unsigned int sweep_xbits = 0;  // XB_RESTRICT_DOM while a topology domain is the node set
+  bool place_tasks(int job, int n, const int *tasks = nullptr) {
+    bool job_success = true;
+    for (int k = 0; k < n; k++) {
+      int t = tasks ? tasks[k] : (ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k]);
+      if (!seq_prepare_task(seq, t, job)) {
+        job_success = false;
+        break;
+      }
+      if (ctl.use_batch) {
+        if (topm && !batch_is_single) {
+          if (apply_listed(t)) continue;
+          ctl.batch.valid = 0;  // list ran dry between prepare and apply: fall through to a sweep
+          ctl.use_batch = 0;
+          if (!seq_prepare_task(seq, t, job)) {
+            job_success = false;
+            break;
+          }
+        } else {
+          seq_apply_batched(seq, t);
+          continue;
+        }
+      }
+      if (ctl.need_minmax) {
+        seq.minmax_exchanges++;
+        ctl.xbits = sweep_xbits;
+        publish(DK_MINMAX);
+        ctl.xbits = 0;
+        gather_minmax();
+      }
+      double tx = now();
+      // Lists pay off when one sweep serves many pods.  When the recent lists served ~1 pod each (a different
+      // request on almost every job) the sweep is asked to answer with the single best row instead (XB_SINGLE:
+      // one scan round, one reduced line); every 128th sweep probes the list form again.
+      bool as_list = topm != 0;
+      if (as_list && list_yield_ema < 1.5 && (++single_streak & 127) != 0) as_list = false;
+      ctl.xbits = ((topm && !as_list) ? XB_SINGLE : 0) | sweep_xbits;
+      publish(DK_SCAN);
+      ctl.xbits = 0;
+      if (as_list) {
+        if (list_served >= 0) list_yield_ema = 0.75 * list_yield_ema + 0.25 * (double)list_served;
+        gather_list();
+        list_served = 0;
+        batch_is_single = false;
+      } else {
+        gather_candidates();
+        batch_is_single = true;
+        if (topm) list_invalidate_keep_batch();
+      }
+      t_exchange += now() - tx;
+      if (failed) {
+        job_success = false;
+        break;
+      }
+      if (as_list) {
+        seq.sweeps++;
+        seq.nodes_scanned += seq.s->N;
+        ctl.item_ok = 0;
+        if (list_available()) apply_listed(t);
+      } else {
+        seq_apply_winner(seq, t);
+      }
+      if (!ctl.item_ok) {
+        job_success = false;
+        break;
+      }
+    }
+    return job_success;
+  }
+
   // allocateSubGroupSet for a job whose root SubGroupSet carries a topology constraint (allocate.go:36-60 with
   // topology.subSetNodesFn): candidate domains in order, the first one that takes every task wins.
   bool allocate_constrained(TopologyHost &topo, int job, const std::vector<int> &tta) {
@@ -393,29 +465,18 @@ struct HostBackend {
       if (failed) break;
       const int cp = seq.n_ops;
       topo.select_domain(seq, r, di);
-      bool ok = true;
-      for (int t : tta) {
-        if (!seq_prepare_task(seq, t, job)) {
-          ok = false;
-          break;
-        }
-        ctl.use_batch = 0;
-        sweep_single(XB_RESTRICT_DOM);
-        if (failed || ctl.win.node < 0) {
-          ok = false;
-          break;
-        }
-        if (ctl.win.flags & SLOT_TO_IDLE)
-          stmt_allocate(seq, t, ctl.win.node, ctl.ctx_fresh != 0);
-        else
-          stmt_pipeline(seq, t, ctl.win.node, ctl.ctx_fresh != 0);
-      }
+      node_state_disturbed(seq);  // another row set: the min/max trackers and any list belong to the previous one
+      list_invalidate();
+      sweep_xbits = XB_RESTRICT_DOM;
+      bool ok = place_tasks(job, (int)tta.size(), tta.data());
+      sweep_xbits = 0;
       if (ok) {
         placed = true;
         break;
       }
       stmt_rollback(seq, cp);
     }
+    list_invalidate();
     topo.clear_scores(seq, r);
     node_state_disturbed(seq);
     return placed;
@@ -488,68 +549,7 @@ struct HostBackend {
         for (int k = 0; k < n; k++) tta[k] = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
         job_success = allocate_constrained(*topo, job, tta);
       } else if (job_success) {
-        for (int k = 0; k < n; k++) {
-          int t = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
-          if (!seq_prepare_task(seq, t, job)) {
-            job_success = false;
-            break;
-          }
-          if (ctl.use_batch) {
-            if (topm && !batch_is_single) {
-              if (apply_listed(t)) continue;
-              ctl.batch.valid = 0;  // list ran dry between prepare and apply: fall through to a sweep
-              ctl.use_batch = 0;
-              if (!seq_prepare_task(seq, t, job)) {
-                job_success = false;
-                break;
-              }
-            } else {
-              seq_apply_batched(seq, t);
-              continue;
-            }
-          }
-          if (ctl.need_minmax) {
-            seq.minmax_exchanges++;
-            publish(DK_MINMAX);
-            gather_minmax();
-          }
-          double tx = now();
-          // Lists pay off when one sweep serves many pods.  When the recent lists served ~1 pod each (a different
-          // request on almost every job) the sweep is asked to answer with the single best row instead (XB_SINGLE:
-          // one scan round, one reduced line); every 128th sweep probes the list form again.
-          bool as_list = topm != 0;
-          if (as_list && list_yield_ema < 1.5 && (++single_streak & 127) != 0) as_list = false;
-          ctl.xbits = (topm && !as_list) ? XB_SINGLE : 0;
-          publish(DK_SCAN);
-          ctl.xbits = 0;
-          if (as_list) {
-            if (list_served >= 0) list_yield_ema = 0.75 * list_yield_ema + 0.25 * (double)list_served;
-            gather_list();
-            list_served = 0;
-            batch_is_single = false;
-          } else {
-            gather_candidates();
-            batch_is_single = true;
-            if (topm) list_invalidate_keep_batch();
-          }
-          t_exchange += now() - tx;
-          if (failed) {
-            job_success = false;
-            break;
-          }
-          if (as_list) {
-            seq.sweeps++;
-            seq.nodes_scanned += s.N;
-            ctl.item_ok = 0;
-            if (list_available()) apply_listed(t);
-          } else {
-            seq_apply_winner(seq, t);
-          }
-          if (!ctl.item_ok) {
-            job_success = false;
-            break;
-          }
-        }
+        job_success = place_tasks(job, n);
       }
       lap(2);
       if (job_success) {

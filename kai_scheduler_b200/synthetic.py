@@ -182,6 +182,60 @@ def reclaim_snapshot(n_nodes: int, running_per_node: int = 8, gpus_per_node: int
         task_order_rank=task_order_rank)
 
 
+def topology_snapshot(n_nodes: int, n_gangs: int, nodes_per_rack: int = 16, racks_per_leaf: int = 16, leaves_per_spine: int = 13,
+                      gpus_per_node: int = 8, n_queues: int = 4, seed: int = 0x0C44, min_pods: int = 2, max_pods: int = 16,
+                      running_fraction: float = 0.0) -> abi.Snapshot:
+    """BASELINE config 4: nodes labelled on 3 tiers (spine / leaf / rack; Topology CR levels
+    [spine, leaf, rack]), gangs of seeded 2..16 pods x 8 GPUs (node-exclusive) with
+    topologyConstraint{requiredLevel = leaf | rack, preferredLevel = rack}.  `running_fraction` pre-fills that share of
+    the nodes with one running 8-GPU pod each (so that domains differ in free capacity)."""
+    base = benchmark_snapshot(n_nodes=n_nodes, n_jobs=1, tasks_per_job=1, n_queues=n_queues, gpus_per_node=gpus_per_node)
+    rng = np.random.default_rng(seed)
+    N, R = n_nodes, 4
+    rack = np.arange(N) // nodes_per_rack
+    leaf = rack // racks_per_leaf
+    spine = leaf // leaves_per_spine
+    # DomainID = joined label values; ids must follow ascending DomainID STRING order per level
+    def dense(ids_str):
+        uniq = sorted(set(ids_str))
+        m = {d: i for i, d in enumerate(uniq)}
+        return np.array([m[d] for d in ids_str], dtype=np.int32)
+    spine_id = [f"s{spine[n]}" for n in range(N)]
+    leaf_id = [f"s{spine[n]}.l{leaf[n]}" for n in range(N)]
+    rack_id = [f"s{spine[n]}.l{leaf[n]}.r{rack[n]}" for n in range(N)]
+    node_domain = np.stack([dense(spine_id), dense(leaf_id), dense(rack_id)]).astype(np.int32)
+    sizes = rng.integers(min_pods, max_pods + 1, size=n_gangs)
+    n_run = int(N * running_fraction)
+    run_nodes = rng.choice(N, size=n_run, replace=False) if n_run else np.zeros(0, dtype=np.int64)
+    J = n_gangs + n_run
+    T = int(sizes.sum()) + n_run
+    job_queue = (np.arange(J) % n_queues).astype(np.int32)
+    podset_min = np.concatenate([sizes, np.ones(n_run, dtype=np.int64)]).astype(np.int32)
+    podset_task_begin = np.concatenate([[0], np.cumsum(podset_min)]).astype(np.int32)
+    task_status = np.concatenate([np.full(int(sizes.sum()), abi.POD_PENDING), np.full(n_run, abi.POD_RUNNING)]).astype(np.int32)
+    task_node = np.concatenate([np.full(int(sizes.sum()), -1), run_nodes]).astype(np.int32)
+    req = np.empty((T, R))
+    req[:, 0], req[:, 1], req[:, 2], req[:, 3] = 1000.0, 1e9, float(gpus_per_node), 1.0
+    order = np.concatenate([_name_rank("", int(k)) for k in podset_min]).astype(np.int32)
+    idle = base.node_allocatable.copy()
+    for r in range(R):
+        np.subtract.at(idle[r], run_nodes, req[int(sizes.sum()):, r])
+    required = rng.integers(1, 3, size=J).astype(np.int32)  # 1 = leaf, 2 = rack
+    job_topology = np.concatenate([np.zeros(n_gangs), np.full(n_run, -1)]).astype(np.int32)
+    return abi.Snapshot(
+        n_res=R, node_allocatable=base.node_allocatable, node_idle=idle, node_releasing=np.zeros((R, N)),
+        node_name_rank=base.node_name_rank, node_flags=base.node_flags, queue_parent=base.queue_parent,
+        queue_priority=base.queue_priority, queue_creation=base.queue_creation, queue_uid_rank=base.queue_uid_rank,
+        queue_deserved=base.queue_deserved, queue_limit=base.queue_limit, queue_oqw=base.queue_oqw,
+        job_queue=job_queue, job_priority=np.full(J, 50, dtype=np.int32), job_order_rank=np.arange(J, dtype=np.int32),
+        job_flags=np.full(J, abi.JOB_PREEMPTIBLE, dtype=np.uint32), job_podset_begin=np.arange(J + 1, dtype=np.int32),
+        podset_min_available=podset_min, podset_task_begin=podset_task_begin, task_status=task_status,
+        task_node=task_node, task_req=req, task_order_rank=order,
+        topology_level_begin=np.array([0, 3], dtype=np.int32), node_domain=node_domain, job_topology=job_topology,
+        job_required_level=np.where(job_topology >= 0, required, -1).astype(np.int32),
+        job_preferred_level=np.where(job_topology >= 0, 2, -1).astype(np.int32))
+
+
 # The BASELINE.json configs (SURVEY.md §8d)
 CONFIGS = {
     # name: kwargs
@@ -192,12 +246,17 @@ CONFIGS = {
 }
 # victim-selection workloads: BenchmarkReclaimLargeJobs_<N>Node (reference numbers in BASELINE.md) and a
 # config-5-shaped full cycle (running pods in over-quota queues + pending reclaimers)
+TOPOLOGY_CONFIGS = {
+    "config4-small": dict(n_nodes=4096, n_gangs=600),
+    "config4": dict(n_nodes=50_000, n_gangs=20_000),
+}
 RECLAIM_CONFIGS = {
     **{f"reclaim-large-{n}": dict(n_nodes=n) for n in (10, 50, 100, 200, 500, 1000)},
     "cycle5-small": dict(n_nodes=200, running_per_node=8, victim_queues=4, reclaimer_jobs=100, reclaimer_tasks=2,
                          reclaimer_gpus=4.0),
 }
-CONFIG_ACTIONS = {**{k: ["allocate"] for k in CONFIGS}, **{k: ["reclaim"] for k in RECLAIM_CONFIGS},
+CONFIG_ACTIONS = {**{k: ["allocate"] for k in CONFIGS}, **{k: ["allocate"] for k in TOPOLOGY_CONFIGS},
+                  **{k: ["reclaim"] for k in RECLAIM_CONFIGS},
                   "cycle5-small": ["allocate", "consolidation", "reclaim"]}
 # ms/op the reference publishes for BenchmarkReclaimLargeJobs (other hardware, includes BuildSession)
 REFERENCE_PUBLISHED_MS = {"reclaim-large-10": 104.4, "reclaim-large-50": 130.2, "reclaim-large-100": 241.2,
@@ -207,4 +266,6 @@ REFERENCE_PUBLISHED_MS = {"reclaim-large-10": 104.4, "reclaim-large-50": 130.2, 
 def config_snapshot(name: str) -> abi.Snapshot:
     if name in RECLAIM_CONFIGS:
         return reclaim_snapshot(**RECLAIM_CONFIGS[name])
+    if name in TOPOLOGY_CONFIGS:
+        return topology_snapshot(**TOPOLOGY_CONFIGS[name])
     return benchmark_snapshot(**CONFIGS[name])

@@ -120,6 +120,33 @@ def test_solver_synthetic(kw, action):
     assert re_.pods_evicted == ro.pods_evicted
 
 
+@pytest.mark.parametrize("kw", [
+    dict(n_nodes=512, n_gangs=60, nodes_per_rack=8, racks_per_leaf=4, leaves_per_spine=4, running_fraction=0.3),
+    dict(n_nodes=300, n_gangs=50, nodes_per_rack=5, racks_per_leaf=3, leaves_per_spine=2, running_fraction=0.5, max_pods=6),
+    dict(n_nodes=4096, n_gangs=600),  # config4-small: 16 nodes / rack, 16 racks / leaf
+])
+def test_topology_synthetic(kw):
+    """BASELINE config 4 shape: 3-tier topology, node-exclusive gangs, required leaf|rack + preferred rack."""
+    snap = synthetic.topology_snapshot(**kw)
+    re_, ro = run_both(snap)
+    assert_same(re_, ro)
+    assert re_.pods_placed > 0
+
+
+def test_topology_cycle_with_solver():
+    """topology-constrained pending gangs through consolidation / reclaim simulations as well"""
+    snap = synthetic.topology_snapshot(n_nodes=96, n_gangs=20, nodes_per_rack=4, racks_per_leaf=3, leaves_per_spine=2,
+                                       running_fraction=0.6, max_pods=4)
+    e = Engine()
+    e.load(snap)
+    o = Oracle()
+    o.load(snap)
+    for action in ("allocate", "consolidation", "reclaim", "preempt"):
+        re_, ro = e.run(action), o.run(action)
+        assert_same(re_, ro)
+    e.close()
+
+
 @pytest.mark.parametrize("action", ["reclaim", "consolidation"])
 def test_solver_scheduling_signatures(action):
     """UseSchedulingSignatures = true (production default): jobs not easier than a failed representative are skipped."""
