@@ -834,6 +834,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     // host mirror of everything the open-session / prepare kernels produced
     CK(cudaMemcpyAsync(e->stage.host + e->dev_only_begin, e->dsnap.base + e->dev_only_begin, e->dev_only_bytes,
                        cudaMemcpyDeviceToHost, e->stream));
+    if (!e->mirror_valid) e->topo.live = false;  // the incremental per-domain state is rebuilt from the re-read tables
     if (!e->mirror_valid) {  // a device-sequenced action ran before: re-read the node tables (one GPU)
       e->h_i.resize((size_t)e->R * e->N);
       e->h_l.resize((size_t)e->R * e->N);
@@ -868,6 +869,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.list_served = -1;
     hb.single_streak = 0;
     hb.single_sweeps = 0;
+    hb.n_flush = hb.n_topo_jobs = hb.n_topo_domains = 0;
+    hb.t_topo[0] = hb.t_topo[1] = hb.t_topo[2] = 0;
     hb.list_invalidate();
     hb.batching = p.batching;
     hb.failed = false;
@@ -936,6 +939,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     e->topo.mL = e->h_l.data();
     e->topo.t_req = hs.t_req;
     seq.topology = e->topo.any() ? &e->topo : nullptr;
+    seq.on_node_changed = &TopologyHost::node_changed_hook;
+    e->topo.reset_gpu_state();
     seq.ctl = &ctl;
     seq.ops_cap = e->ops_cap;
     seq.batching = p.batching;
@@ -1061,7 +1066,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer: total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
               e->hb.t_total * 1e3, e->hb.t_exchange * 1e3, c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
-    if (host_mode) fprintf(stderr, "[kai] sweeps answered with a single row (XB_SINGLE): %lld\n", e->hb.single_sweeps);
+    if (host_mode) fprintf(stderr, "[kai] sweeps answered with a single row (XB_SINGLE): %lld; FLUSH records %lld\n", e->hb.single_sweeps, e->hb.n_flush);
+    if (host_mode && e->hb.n_topo_jobs)
+      fprintf(stderr, "[kai] topology: %lld constrained jobs with candidates, %lld domains tried; subSetNodesFn %.1f ms, score table %.1f ms, placing %.1f ms\n",
+              e->hb.n_topo_jobs, e->hb.n_topo_domains, e->hb.t_topo[0] * 1e3, e->hb.t_topo[1] * 1e3, e->hb.t_topo[2] * 1e3);
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer rdtsc Mcycles: pop %.2f admit %.2f place(+sweeps) %.2f finish %.2f loop %.2f\n",
               e->hb.t_sec[0] / 1e6, e->hb.t_sec[1] / 1e6, e->hb.t_sec[2] / 1e6, e->hb.t_sec[3] / 1e6, e->hb.t_sec[4] / 1e6);

@@ -373,6 +373,8 @@ struct HostBackend {
   // allocateTasksOnNodeSet (allocate.go:104-119) for the tasks of the context job: lists / same-node batches while
   // they apply, a sweep otherwise.  `tasks` = explicit list or null for the context's own range.
   unsigned int sweep_xbits = 0;  // XB_RESTRICT_DOM while a topology domain is the node set
+  double t_topo[4] = {0, 0, 0, 0};
+  long long n_topo_jobs = 0, n_topo_domains = 0, n_flush = 0;
   bool place_tasks(int job, int n, const int *tasks = nullptr) {
     bool job_success = true;
     for (int k = 0; k < n; k++) {
@@ -453,10 +455,16 @@ struct HostBackend {
       for (int t = s.ps_task_begin[ps]; t < s.ps_task_begin[ps + 1]; t++)
         if (seq.rp.t_status[t] & kActiveAllocated) active_nodes.push_back(seq.rp.t_node[t]);
     }
-    TopologyHost::Result r = topo.subset(job, tta, [](int) { return true; }, has_active, active_nodes);
+    double tt0 = now();
+    TopologyHost::Result r = topo.subset(job, tta, [](int) { return true; }, has_active, active_nodes, true);
+    t_topo[0] += now() - tt0;
     if (!r.ok || r.domains.empty()) return false;
     list_invalidate();
-    if (!topo.push_scores(seq, r)) {
+    tt0 = now();
+    const bool pushed = topo.push_scores(seq, r);
+    t_topo[1] += now() - tt0;
+    n_topo_jobs++;
+    if (!pushed) {
       seq.error = 2;
       return false;
     }
@@ -468,7 +476,10 @@ struct HostBackend {
       node_state_disturbed(seq);  // another row set: the min/max trackers and any list belong to the previous one
       list_invalidate();
       sweep_xbits = XB_RESTRICT_DOM;
+      tt0 = now();
       bool ok = place_tasks(job, (int)tta.size(), tta.data());
+      t_topo[2] += now() - tt0;
+      n_topo_domains++;
       sweep_xbits = 0;
       if (ok) {
         placed = true;
@@ -483,6 +494,7 @@ struct HostBackend {
   }
 
   void flush_deltas() {
+    n_flush++;
     publish(DK_FLUSH);
     const unsigned int seq_no = ctl.seq;
     const unsigned long long *buf = h_slots + (size_t)(seq_no & 1) * kMaxGrid * kSlotWords;
@@ -549,6 +561,7 @@ struct HostBackend {
         for (int k = 0; k < n; k++) tta[k] = ctl.ctx_base >= 0 ? ctl.ctx_base + k : seq.rp.tta[k];
         job_success = allocate_constrained(*topo, job, tta);
       } else if (job_success) {
+        if (topo) topo->scores_off(seq);  // no NodeOrderFn term from the previous job's topology scores
         job_success = place_tasks(job, n);
       }
       lap(2);

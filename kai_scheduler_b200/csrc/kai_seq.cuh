@@ -209,6 +209,7 @@ struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   double *mirror_i, *mirror_l;      // host-sequenced mode: Idle / Releasing [R][N] of ALL nodes, kept in step with the
                                     // deltas (point look-ups of the solver, topology domain sums; identical on every rank)
   void *topology;                   // host-sequenced mode: TopologyHost* (or null)
+  void (*on_node_changed)(void *topology, int node, const double *before, const double *after);  // Idle+Releasing per resource
   Replica rp;
   Tile *tile;
   Ctl *ctl;
@@ -289,10 +290,16 @@ KAI_HD void close_delta(Ctl &c, unsigned long long *delta_base) {
 KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
 #ifndef __CUDA_ARCH__
-  if (q.mirror_i && code < ND_FEAS_SET)
-    for (int r = 0; r < q.s->R; r++)
-      apply_delta_row(q.mirror_i[(size_t)r * q.s->N + node], q.mirror_l[(size_t)r * q.s->N + node], code,
-                      q.s->t_req[(size_t)t * q.s->R + r]);
+  if (q.mirror_i && code < ND_FEAS_SET) {
+    double before[KAI_MAX_RES], after[KAI_MAX_RES];
+    for (int r = 0; r < q.s->R; r++) {
+      double &mi = q.mirror_i[(size_t)r * q.s->N + node], &ml = q.mirror_l[(size_t)r * q.s->N + node];
+      before[r] = mi + ml;
+      apply_delta_row(mi, ml, code, q.s->t_req[(size_t)t * q.s->R + r]);
+      after[r] = mi + ml;
+    }
+    if (q.on_node_changed && q.topology) q.on_node_changed(q.topology, node, before, after);
+  }
 #endif
   // the delta names the node by its NAME RANK: that is what decides which scanner owns the row
   const unsigned int key = (unsigned int)(kldg(&q.s->name_rank[node]) | (code << 28));

@@ -605,6 +605,7 @@ struct Solver {
       topo->clear_scores(seq, r);
       return placed;
     }
+    if (topo) topo->scores_off(seq);
     int cp = stmt_checkpoint();
     for (int k : ordered_podsets(v)) {
       int ps = ps_begin(j) + k;

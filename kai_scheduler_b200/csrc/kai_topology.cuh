@@ -25,15 +25,18 @@ struct TopologyHost {
   struct Dom {
     int level = -1;  // global level index, -1 = root
     int id = 0;      // dense id inside the level (ascending DomainID order)
+    int parent = -1;
     std::vector<int> children, nodes;
     int alloc_pods = -1;  // allocatablePodsNotSet
     double free[KAI_MAX_RES] = {0};
+    double free_live[KAI_MAX_RES] = {0};  // Σ Idle + Releasing of the domain's nodes, kept incrementally (all levels)
   };
   struct Topo {
     int lb = 0, le = 0;
     std::vector<Dom> doms;                 // doms[0] = root
     std::vector<std::vector<int>> dom_at;  // [level - lb][id] -> index into doms
     std::vector<char> node_in;
+    std::vector<char> lcd_all;  // per level: do all topology nodes share one domain (lowest common domain of the full set)
   };
   int N = 0, R = 4;
   std::vector<int> level_begin, node_domain, job_topology, job_req, job_pref;
@@ -41,13 +44,156 @@ struct TopologyHost {
   const double *mI = nullptr, *mL = nullptr;  // host mirror of Idle / Releasing [R][N]
   const double *t_req = nullptr;              // [T][R] (engine task numbering)
 
+  // ---- incremental state, fed by the node-delta stream (Seq::on_node_changed) ----
+  // The reference recomputes, per constrained job, the free resources of every domain of the subtree and, per node,
+  // how many copies of the job's largest pod fit.  Here the per-leaf-domain sums and, per pod shape ("class"), the
+  // per-node counts and their per-leaf-domain sums are kept up to date as nodes change, so that a job costs
+  // O(domains), not O(nodes).  (Sums of integer-valued quantities: the order of accumulation is immaterial.)
+  bool live = false;
+  std::vector<std::vector<int>> leaf_of;  // [topology][node] -> lowest-level domain (index into doms) or -1
+  struct PodClass {
+    int topo = -1;
+    std::vector<double> max_pod;
+    bool only_pods = false;
+    std::vector<int> cnt;       // [N] calcNodeAccommodation of the node
+    std::vector<int> leaf_cnt;  // [doms] sum over the nodes of the domain (every level)
+    unsigned long long stamp = 0;
+  };
+  std::vector<PodClass> classes;
+  unsigned long long class_clock = 0;
+
   int ND(int level, int n) const { return node_domain[(size_t)level * N + n]; }
+  // job_filtering.go:213-247 calcNodeAccommodation: the k-th test pod is k copies of the largest pod, accumulated
+  int count_node(const std::vector<double> &max_pod, int n) const {
+    double acc[KAI_MAX_RES] = {0};
+    int cnt = 0;
+    for (;;) {
+      for (int r = 0; r < R; r++) acc[r] += max_pod[r];
+      for (int r = 0; r < R; r++) {
+        double a = avail(r, n);
+        if (r >= 3) {
+          if (acc[r] != 0 && acc[r] > a) return cnt;
+        } else if (acc[r] > a)
+          return cnt;
+      }
+      cnt++;
+    }
+  }
+  void ensure_live() {
+    if (live) return;
+    leaf_of.assign(topos.size(), {});
+    for (size_t k = 0; k < topos.size(); k++) {
+      Topo &tp = topos[k];
+      leaf_of[k].assign(N, -1);
+      for (size_t di = 0; di < tp.doms.size(); di++) {
+        Dom &d = tp.doms[di];
+        for (int r = 0; r < KAI_MAX_RES; r++) d.free_live[r] = 0;
+        if (!d.children.empty() || d.level < 0) continue;
+        for (int n : d.nodes) {
+          leaf_of[k][n] = (int)di;
+          for (int r = 0; r < R; r++) {
+            d.free_live[r] += mI[(size_t)r * N + n];
+            d.free_live[r] += mL[(size_t)r * N + n];
+          }
+        }
+      }
+    }
+    for (size_t k = 0; k < topos.size(); k++) {  // aggregate upwards: children have larger indices than parents
+      Topo &tp = topos[k];
+      for (size_t di = tp.doms.size(); di-- > 1;)
+        for (int r = 0; r < R; r++) tp.doms[tp.doms[di].parent].free_live[r] += tp.doms[di].free_live[r];
+    }
+    classes.clear();
+    ratio_classes.clear();
+    cur_ratio = nullptr;
+    dom_ver.assign(topos.size(), {});
+    for (size_t k = 0; k < topos.size(); k++) dom_ver[k].assign(topos[k].doms.size(), 1u);
+    live = true;
+  }
+  static void node_changed_hook(void *self, int node, const double *before, const double *after) {
+    ((TopologyHost *)self)->node_changed(node, before, after);
+  }
+  void node_changed(int node, const double *before, const double *after) {
+    if (!live) return;
+    for (size_t k = 0; k < topos.size(); k++) {
+      int leaf = leaf_of[k][node];
+      if (leaf < 0) continue;
+      for (int d = leaf; d >= 0; d = topos[k].doms[d].parent) {
+        for (int r = 0; r < R; r++) topos[k].doms[d].free_live[r] += after[r] - before[r];
+        dom_ver[k][d]++;
+      }
+    }
+    for (PodClass &c : classes) {
+      int leaf = leaf_of[c.topo][node];
+      if (leaf < 0 || c.only_pods) continue;
+      int nc = count_node(c.max_pod, node);
+      if (nc != c.cnt[node])
+        for (int d = leaf; d >= 0; d = topos[c.topo].doms[d].parent) c.leaf_cnt[d] += nc - c.cnt[node];
+      c.cnt[node] = nc;
+    }
+  }
+  PodClass &pod_class(int k, const std::vector<double> &max_pod) {
+    for (PodClass &c : classes)
+      if (c.topo == k && c.max_pod == max_pod) {
+        c.stamp = ++class_clock;
+        return c;
+      }
+    if (classes.size() >= 4) {  // evict the least recently used shape
+      size_t lru = 0;
+      for (size_t i = 1; i < classes.size(); i++)
+        if (classes[i].stamp < classes[lru].stamp) lru = i;
+      classes.erase(classes.begin() + lru);
+    }
+    classes.emplace_back();
+    PodClass &c = classes.back();
+    c.topo = k;
+    c.max_pod = max_pod;
+    c.stamp = ++class_clock;
+    c.only_pods = true;
+    for (int r = 0; r < R; r++)
+      if (r == 3 ? max_pod[r] > 1 : max_pod[r] > 0) c.only_pods = false;
+    c.cnt.assign(N, 0);
+    c.leaf_cnt.assign(topos[k].doms.size(), 0);
+    if (!c.only_pods)
+      for (int n : topos[k].doms[0].nodes) {
+        c.cnt[n] = count_node(max_pod, n);
+        for (int d = leaf_of[k][n]; d >= 0; d = topos[k].doms[d].parent) c.leaf_cnt[d] += c.cnt[n];
+      }
+    return c;
+  }
+  void subtree_free_live(Topo &tp, int di) {
+    Dom &d = tp.doms[di];
+    if (d.children.empty()) {
+      if (d.level >= 0)
+        for (int r = 0; r < R; r++) d.free[r] = d.free_live[r];
+      return;
+    }
+    for (int c : d.children) {
+      subtree_free_live(tp, c);
+      for (int r = 0; r < R; r++) tp.doms[di].free[r] += tp.doms[c].free[r];
+    }
+  }
+  int subtree_allocatable_live(Topo &tp, int di, const PodClass &c, int n_tasks) {
+    Dom &d = tp.doms[di];
+    d.alloc_pods = 0;
+    if (d.children.empty()) {
+      d.alloc_pods = c.only_pods ? n_tasks * (int)d.nodes.size() : c.leaf_cnt[di];
+      return d.alloc_pods;
+    }
+    for (int ch : d.children) {
+      int a = subtree_allocatable_live(tp, ch, c, n_tasks);
+      tp.doms[di].alloc_pods += a;
+    }
+    return tp.doms[di].alloc_pods;
+  }
   bool any() const { return !topos.empty() && !job_topology.empty(); }
   bool constrained(int job) const { return any() && job_topology[job] != -1; }
   double avail(int r, int n) const { return mI[(size_t)r * N + n] + mL[(size_t)r * N + n]; }
 
   void build(const kai_snapshot *s) {
     topos.clear();
+    live = false;
+    classes.clear();
     level_begin.clear();
     node_domain.clear();
     job_topology.clear();
@@ -83,6 +229,7 @@ struct TopologyHost {
               tp.doms.emplace_back();
               tp.doms[di].level = l;
               tp.doms[di].id = ND(l, n);
+              tp.doms[di].parent = parent;
               tp.doms[parent].children.push_back(di);
             }
             tp.doms[di].nodes.push_back(n);
@@ -190,9 +337,45 @@ struct TopologyHost {
     }
     return tp.doms[di].alloc_pods;
   }
+  // getJobRatioToFreeResources memo: the ratio of a (job resource sum, domain) pair changes only when the domain's
+  // free resources do; `ver` counts those changes (node_changed walks the ancestors)
+  struct RatioClass {
+    std::vector<double> tasks_res;
+    int topo = -1;
+    std::vector<double> ratio;
+    std::vector<unsigned int> ver;
+  };
+  std::vector<RatioClass> ratio_classes;
+  std::vector<std::vector<unsigned int>> dom_ver;  // [topology][dom], starts at 1
+  RatioClass *cur_ratio = nullptr;
+  void select_ratio_class(int k, const double *tasks_res) {
+    for (RatioClass &c : ratio_classes)
+      if (c.topo == k && std::equal(c.tasks_res.begin(), c.tasks_res.end(), tasks_res)) {
+        cur_ratio = &c;
+        return;
+      }
+    if (ratio_classes.size() >= 64) ratio_classes.erase(ratio_classes.begin());
+    ratio_classes.emplace_back();
+    RatioClass &c = ratio_classes.back();
+    c.topo = k;
+    c.tasks_res.assign(tasks_res, tasks_res + R);
+    c.ratio.assign(topos[k].doms.size(), 0.0);
+    c.ver.assign(topos[k].doms.size(), 0u);
+    cur_ratio = &c;
+  }
+  double cached_ratio(int k, const double *tasks_res, int di) {
+    RatioClass &c = *cur_ratio;
+    const unsigned int v = dom_ver[k][di];
+    if (c.ver[di] != v) {
+      c.ratio[di] = job_ratio_to_free(tasks_res, topos[k].doms[di]);
+      c.ver[di] = v;
+    }
+    return c.ratio[di];
+  }
   void sort_tree(Topo &tp, int di, const double *tasks_res, int max_depth_level) {  // :396-420
     std::vector<std::pair<double, int>> keyed;
-    for (int c : tp.doms[di].children) keyed.push_back({job_ratio_to_free(tasks_res, tp.doms[c]), c});
+    const int kk = (int)(&tp - &topos[0]);
+    for (int c : tp.doms[di].children) keyed.push_back({cached_ratio(kk, tasks_res, c), c});
     std::stable_sort(keyed.begin(), keyed.end(), [&](const std::pair<double, int> &a, const std::pair<double, int> &b) {
       if (a.first != b.first) return a.first > b.first;
       return tp.doms[a.second].id < tp.doms[b.second].id;
@@ -221,7 +404,7 @@ struct TopologyHost {
   // solver's feasible set).  `active_nodes`: nodes of the job's active-allocated pods; has_active: any podset of the
   // (view of the) job counts active-allocated pods.
   Result subset(int job, const std::vector<int> &tasks, const std::function<bool(int)> &in_set, bool has_active,
-                const std::vector<int> &active_nodes) {
+                const std::vector<int> &active_nodes, bool all_nodes = false) {
     Result res;
     const int k = job_topology[job];
     if (k == -2) return res;  // requested topology does not exist: no node set
@@ -235,7 +418,13 @@ struct TopologyHost {
       std::vector<char> all(tp.le - tp.lb, 1);
       std::vector<int> value(tp.le - tp.lb, -1);
       for (int n : tp.doms[0].nodes) {
-        if (!in_set(n)) continue;
+        if (all_nodes && first >= 0) {  // every topology node is in the set: only "all equal?" per level matters
+          if ((int)tp.lcd_all.size() == tp.le - tp.lb) {
+            all = tp.lcd_all;
+            break;
+          }
+        }
+        if (!all_nodes && !in_set(n)) continue;
         if (first < 0) {
           first = n;
           for (int l = tp.lb; l < tp.le; l++) value[l - tp.lb] = ND(l, n);
@@ -244,17 +433,48 @@ struct TopologyHost {
             if (ND(l, n) != value[l - tp.lb]) all[l - tp.lb] = 0;
         }
       }
+      if (all_nodes && first >= 0 && (int)tp.lcd_all.size() != tp.le - tp.lb) tp.lcd_all = all;  // computed once per load
       for (int l = tp.lb; l < tp.le && first >= 0; l++) {
         if (!all[l - tp.lb]) break;
         dom = tp.dom_at[l - tp.lb][value[l - tp.lb]];
         if (pref >= 0 && l - tp.lb == pref) break;
       }
     }
+    // gather what checkJobDomainFit(domain) needs first: when the lowest common domain cannot take the job (a full
+    // cluster's tail of pending gangs) nothing below has to be evaluated
+    ensure_live();
+    double tasks_res0[KAI_MAX_RES] = {0};
+    std::vector<double> max_pod0(R, 0.0);
+    int gpu_pods0 = 0;
+    for (int t : tasks) {
+      if (t_req[(size_t)t * R + KAI_RES_GPU] > 0) gpu_pods0++;
+      for (int r = 0; r < R; r++) {
+        tasks_res0[r] += t_req[(size_t)t * R + r];
+        max_pod0[r] = std::max(max_pod0[r], t_req[(size_t)t * R + r]);
+      }
+    }
+    {
+      bool uniform = true;
+      for (int r = 3; r < R; r++) {
+        int c = 0;
+        for (int t : tasks)
+          if (t_req[(size_t)t * R + r] != 0) c++;
+        if (c != 0 && c != (int)tasks.size()) uniform = false;
+      }
+      Dom probe = Dom();
+      for (int r = 0; r < R; r++) probe.free[r] = tp.doms[dom].free_live[r];
+      if ((gpu_pods0 == (int)tasks.size() || gpu_pods0 == 0) && uniform) {
+        PodClass &pc = pod_class(k, max_pod0);
+        probe.alloc_pods = pc.only_pods ? (int)tasks.size() * (int)tp.doms[dom].nodes.size() : pc.leaf_cnt[dom];
+      }
+      if (!domain_fit(tasks_res0, (int)tasks.size(), probe)) return res;
+    }
     for (auto &d : tp.doms) {  // treeAllocatableCleanup
       d.alloc_pods = -1;
       for (int r = 0; r < KAI_MAX_RES; r++) d.free[r] = 0;
     }
-    subtree_free(tp, dom);
+    ensure_live();
+    subtree_free_live(tp, dom);
     int gpu_pods = 0;
     for (int t : tasks)
       if (t_req[(size_t)t * R + KAI_RES_GPU] > 0) gpu_pods++;
@@ -269,8 +489,7 @@ struct TopologyHost {
       std::vector<double> max_pod(R, 0.0);
       for (int t : tasks)
         for (int r = 0; r < R; r++) max_pod[r] = std::max(max_pod[r], t_req[(size_t)t * R + r]);
-      std::vector<std::vector<double>> test_pods{max_pod};
-      subtree_allocatable(tp, dom, max_pod.data(), test_pods, (int)tasks.size());
+      subtree_allocatable_live(tp, dom, pod_class(k, max_pod), (int)tasks.size());
     }
     double tasks_res[KAI_MAX_RES] = {0};
     for (int t : tasks)
@@ -281,6 +500,7 @@ struct TopologyHost {
       res.ok = false;
       return res;
     }
+    select_ratio_class(k, tasks_res);
     sort_tree(tp, dom, tasks_res, pref >= 0 ? tp.lb + pref : tp.lb + req);
     if (pref >= 0) {  // node_scoring.go:36-53
       res.pref_level = tp.lb + pref;
@@ -346,17 +566,62 @@ struct TopologyHost {
     else
       emit_ext(seq, EXT_SELECT, (unsigned int)(d.level + 1), (unsigned int)d.id);
   }
-  bool push_scores(Seq &seq, const Result &r) const {  // false: more preferred-level domains than the table holds
-    if (r.pref_level < 0) return true;
-    emit_ext(seq, EXT_SCORE_BEGIN, (unsigned int)r.pref_level, 0);
-    for (auto &kv : r.scores) {
+  // The scanners keep the per-domain bucket table between jobs; the host remembers what they hold and sends only the
+  // entries that differ (consecutive gangs sort the racks almost identically).  scores_off() before any sweep of a job
+  // without node scores.
+  int gpu_pref_level = -1;
+  std::vector<unsigned char> gpu_bucket;   // what the scanners hold (255 = no entry)
+  std::vector<int> gpu_set;                // domain ids with an entry
+  bool push_scores(Seq &seq, const Result &r) {  // false: more preferred-level domains than the table holds
+    if (r.pref_level < 0) {
+      scores_off(seq);
+      return true;
+    }
+    if (gpu_bucket.empty()) gpu_bucket.assign(kDomBuckets, 255);
+    if (gpu_pref_level != r.pref_level) {
+      emit_ext(seq, EXT_SCORE_BEGIN, (unsigned int)r.pref_level, 0);
+      for (int d : gpu_set) gpu_bucket[d] = 255;
+      gpu_set.clear();
+      gpu_pref_level = r.pref_level;
+    }
+    std::vector<unsigned char> want_mark;
+    for (auto &kv : r.scores)
       if (kv.first >= kDomBuckets) return false;
+    // entries to drop: held by the scanners, absent from the new table
+    std::vector<int> keep;
+    {
+      std::vector<char> in_new(kDomBuckets, 0);
+      for (auto &kv : r.scores) in_new[kv.first] = 1;
+      for (int d : gpu_set) {
+        if (in_new[d]) {
+          keep.push_back(d);
+        } else {
+          emit_ext(seq, EXT_SCORE, (unsigned int)d, 255u);
+          gpu_bucket[d] = 255;
+        }
+      }
+    }
+    gpu_set = keep;
+    for (auto &kv : r.scores) {
+      if (gpu_bucket[kv.first] == (unsigned char)kv.second) continue;
+      if (gpu_bucket[kv.first] == 255) gpu_set.push_back(kv.first);
       emit_ext(seq, EXT_SCORE, (unsigned int)kv.first, (unsigned int)kv.second);
+      gpu_bucket[kv.first] = (unsigned char)kv.second;
     }
     return true;
   }
-  void clear_scores(Seq &seq, const Result &r) const {
-    if (r.pref_level >= 0) emit_ext(seq, EXT_SCORE_END, 0, 0);
+  void scores_off(Seq &seq) {
+    if (gpu_pref_level < 0) return;
+    emit_ext(seq, EXT_SCORE_END, 0, 0);
+    for (int d : gpu_set) gpu_bucket[d] = 255;
+    gpu_set.clear();
+    gpu_pref_level = -1;
+  }
+  void clear_scores(Seq &, const Result &) {}  // the table stays for the next job; scores_off() ends it
+  void reset_gpu_state() {  // a new k_action launch starts with scoring off and an undefined table
+    gpu_pref_level = -1;
+    gpu_set.clear();
+    if (!gpu_bucket.empty()) std::fill(gpu_bucket.begin(), gpu_bucket.end(), 255);
   }
 };
 
