@@ -127,7 +127,8 @@ struct kai_engine {
   std::vector<int> rank_to_node_h;
   // solver actions: second NodeInfo.PodInfos entry of a task (evicted from A, pipelined to B), mirror of the GPU column
   std::vector<int> on_other_node, on_other_status;
-  std::vector<double> h_i, h_l;  // host mirror of Idle / Releasing [R][N]
+  std::vector<double> h_mirror;  // host mirror of Idle / Releasing, node-major [N][2][R]
+  std::vector<double> h_tmp;     // staging for the re-read after a device-sequenced action
   int *d_node_domain = nullptr;
   TopologyHost topo;
   int n_dom_levels = 0;
@@ -689,8 +690,12 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->on_other_node.clear();
   e->on_other_status.clear();
   e->job_signature.clear();
-  e->h_i.assign(s->node_idle, s->node_idle + (size_t)s->n_res * s->n_nodes);
-  e->h_l.assign(s->node_releasing, s->node_releasing + (size_t)s->n_res * s->n_nodes);
+  e->h_mirror.resize((size_t)2 * s->n_res * s->n_nodes);
+  for (int n = 0; n < s->n_nodes; n++)
+    for (int r = 0; r < s->n_res; r++) {
+      e->h_mirror[(size_t)n * 2 * s->n_res + r] = s->node_idle[(size_t)r * s->n_nodes + n];
+      e->h_mirror[(size_t)n * 2 * s->n_res + s->n_res + r] = s->node_releasing[(size_t)r * s->n_nodes + n];
+    }
   if (e->d_node_domain) {
     cudaFree(e->d_node_domain);
     e->d_node_domain = nullptr;
@@ -836,11 +841,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
                        cudaMemcpyDeviceToHost, e->stream));
     if (!e->mirror_valid) e->topo.live = false;  // the incremental per-domain state is rebuilt from the re-read tables
     if (!e->mirror_valid) {  // a device-sequenced action ran before: re-read the node tables (one GPU)
-      e->h_i.resize((size_t)e->R * e->N);
-      e->h_l.resize((size_t)e->R * e->N);
+      e->h_tmp.resize((size_t)2 * e->R * e->N);
       if (e->N > 0) {
-        CK(cudaMemcpyAsync(e->h_i.data(), e->ds.idle, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaMemcpyAsync(e->h_l.data(), e->ds.rel, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_tmp.data(), e->ds.idle, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_tmp.data() + (size_t)e->R * e->N, e->ds.rel, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
       }
     }
     cudaEventRecord(e->ev_mirror, e->stream);
@@ -876,6 +880,13 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.failed = false;
     hb.rank_to_node = e->rank_to_node_h.data();
     CK(cudaEventSynchronize(e->ev_mirror));
+    if (!e->mirror_valid && !e->h_tmp.empty()) {  // re-read tables -> node-major mirror
+      for (int n = 0; n < e->N; n++)
+        for (int r = 0; r < e->R; r++) {
+          e->h_mirror[(size_t)n * 2 * e->R + r] = e->h_tmp[(size_t)r * e->N + n];
+          e->h_mirror[(size_t)n * 2 * e->R + e->R + r] = e->h_tmp[(size_t)(e->R + r) * e->N + n];
+        }
+    }
     e->mirror_valid = true;  // from here on the host-sequenced deltas keep it in step
     // ---- sequencer state on the host ----
     const DevSnap &hs = e->hs;
@@ -933,10 +944,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     seq.p = &p;
     seq.delta_base = e->h_delta;
     seq.host_backend = &hb;
-    seq.mirror_i = e->h_i.data();
-    seq.mirror_l = e->h_l.data();
-    e->topo.mI = e->h_i.data();
-    e->topo.mL = e->h_l.data();
+    seq.mirror = e->h_mirror.data();
+    e->topo.mirror = e->h_mirror.data();
     e->topo.t_req = hs.t_req;
     seq.topology = e->topo.any() ? &e->topo : nullptr;
     seq.on_node_changed = &TopologyHost::node_changed_hook;

@@ -206,8 +206,9 @@ struct Seq {  // sequencer state (lane 0 of warp 0 of CTA 0)
   const ActionParams *p;
   unsigned long long *delta_base;  // tagged node-delta words [2][kMaxDelta] (device memory or pinned host memory)
   void *host_backend;               // host-sequenced mode: HostBackend*
-  double *mirror_i, *mirror_l;      // host-sequenced mode: Idle / Releasing [R][N] of ALL nodes, kept in step with the
-                                    // deltas (point look-ups of the solver, topology domain sums; identical on every rank)
+  double *mirror;                   // host-sequenced mode: Idle / Releasing of ALL nodes, node-major [N][2][R] (one cache
+                                    // line per node), kept in step with the deltas (solver look-ups, topology domain
+                                    // sums; identical on every rank)
   void *topology;                   // host-sequenced mode: TopologyHost* (or null)
   void (*on_node_changed)(void *topology, int node, const double *before, const double *after);  // Idle+Releasing per resource
   Replica rp;
@@ -290,15 +291,21 @@ KAI_HD void close_delta(Ctl &c, unsigned long long *delta_base) {
 KAI_HD void emit_delta(Seq &q, int node, int code, int t) {
   Ctl &c = *q.ctl;
 #ifndef __CUDA_ARCH__
-  if (q.mirror_i && code < ND_FEAS_SET) {
-    double before[KAI_MAX_RES], after[KAI_MAX_RES];
-    for (int r = 0; r < q.s->R; r++) {
-      double &mi = q.mirror_i[(size_t)r * q.s->N + node], &ml = q.mirror_l[(size_t)r * q.s->N + node];
-      before[r] = mi + ml;
-      apply_delta_row(mi, ml, code, q.s->t_req[(size_t)t * q.s->R + r]);
-      after[r] = mi + ml;
+  if (q.mirror && code < ND_FEAS_SET) {
+    const int R_ = q.s->R;
+    double *row = q.mirror + (size_t)node * 2 * R_;
+    const double *rq = q.s->t_req + (size_t)t * R_;
+    if (q.topology) {
+      double before[KAI_MAX_RES], after[KAI_MAX_RES];
+      for (int r = 0; r < R_; r++) {
+        before[r] = row[r] + row[R_ + r];
+        apply_delta_row(row[r], row[R_ + r], code, rq[r]);
+        after[r] = row[r] + row[R_ + r];
+      }
+      q.on_node_changed(q.topology, node, before, after);
+    } else {
+      for (int r = 0; r < R_; r++) apply_delta_row(row[r], row[R_ + r], code, rq[r]);
     }
-    if (q.on_node_changed && q.topology) q.on_node_changed(q.topology, node, before, after);
   }
 #endif
   // the delta names the node by its NAME RANK: that is what decides which scanner owns the row

@@ -89,7 +89,9 @@ struct Solver {
   // NodeInfo.PodInfos keeps a clone per node: a task evicted from A and pipelined to B sits on both
   std::vector<int> &on_node0, &on_status0, &on_node1, &on_status1;
   double *qa, *qnp;        // queue allocated / allocated-non-preemptible [3][Q]
-  double *hIg, *hLg;  // GPU column of the host mirror of Idle / Releasing (seq.mirror_i / mirror_l; point look-ups only)
+  // GPU column of the host mirror of Idle / Releasing (seq.mirror, node-major; point look-ups only)
+  double Ig(int n) const { return seq.mirror[(size_t)n * 2 * R + KAI_RES_GPU]; }
+  double Lg(int n) const { return seq.mirror[(size_t)n * 2 * R + R + KAI_RES_GPU]; }
   // attempt-start values of touched rows (FeasibleNodesForJob and the filter's base map read the state the
   // attempt started from)
   std::vector<int> touched_epoch;
@@ -108,8 +110,6 @@ struct Solver {
   Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1)
       : hb(hb_), seq(hb_.seq), ctl(hb_.ctl), s(*hb_.seq.s), cfg(*hb_.seq.cfg), N(s.N), Q(s.Q), J(s.J), S(s.S), T(s.T),
         R(s.R), on_node0(n0), on_status0(s0), on_node1(n1), on_status1(s1) {
-    hIg = seq.mirror_i + (size_t)KAI_RES_GPU * N;
-    hLg = seq.mirror_l + (size_t)KAI_RES_GPU * N;
     st = seq.rp.t_status;
     tn = seq.rp.t_node;
     tvirt = seq.rp.t_virtual;
@@ -312,19 +312,19 @@ struct Solver {
   void touch(int n) {
     if (touched_epoch[n] != epoch) {
       touched_epoch[n] = epoch;
-      startIg[n] = hIg[n];
-      startLg[n] = hLg[n];
+      startIg[n] = Ig(n);
+      startLg[n] = Lg(n);
     }
   }
-  double start_Ig(int n) const { return touched_epoch[n] == epoch ? startIg[n] : hIg[n]; }
-  double start_Lg(int n) const { return touched_epoch[n] == epoch ? startLg[n] : hLg[n]; }
+  double start_Ig(int n) const { return touched_epoch[n] == epoch ? startIg[n] : Ig(n); }
+  double start_Lg(int n) const { return touched_epoch[n] == epoch ? startLg[n] : Lg(n); }
   int find_on(int t, int n) const { return on_node0[t] == n ? 0 : (on_node1[t] == n ? 1 : -1); }
   double free_ready = 0;  // Σ idle + releasing GPUs over ready nodes (utils/action.go:145-160), kept incrementally
   void node_delta(int t, int n, int code) {
     touch(n);
-    const double before = hIg[n] + hLg[n];
-    emit_delta(seq, n, code, t);  // also applies the delta to the mirror (hIg / hLg are seq.mirror_ig / mirror_lg)
-    if (s.nflags[n] & KAI_NODE_READY) free_ready += (hIg[n] + hLg[n]) - before;
+    const double before = Ig(n) + Lg(n);
+    emit_delta(seq, n, code, t);  // also applies the delta to the mirror (seq.mirror)
+    if (s.nflags[n] & KAI_NODE_READY) free_ready += (Ig(n) + Lg(n)) - before;
   }
   void node_add_task(int t) {  // node_info.go:457-493 with the task's current status
     int n = tn[t], status = st[t];
@@ -1533,7 +1533,7 @@ struct Solver {
     ops_truncate(0);
     free_ready = 0;  // once per action, from the mirror of the GPU column the action starts with
     for (int n = 0; n < N; n++)
-      if (s.nflags[n] & KAI_NODE_READY) free_ready += hIg[n] + hLg[n];
+      if (s.nflags[n] & KAI_NODE_READY) free_ready += Ig(n) + Lg(n);
   }
 
   // ---------------- actions/reclaim/reclaim.go:46-119 ----------------

@@ -41,7 +41,9 @@ struct TopologyHost {
   int N = 0, R = 4;
   std::vector<int> level_begin, node_domain, job_topology, job_req, job_pref;
   std::vector<Topo> topos;
-  const double *mI = nullptr, *mL = nullptr;  // host mirror of Idle / Releasing [R][N]
+  const double *mirror = nullptr;  // host mirror of Idle / Releasing, node-major [N][2][R]
+  double mI_(int r, int n) const { return mirror[(size_t)n * 2 * R + r]; }
+  double mL_(int r, int n) const { return mirror[(size_t)n * 2 * R + R + r]; }
   const double *t_req = nullptr;              // [T][R] (engine task numbering)
 
   // ---- incremental state, fed by the node-delta stream (Seq::on_node_changed) ----
@@ -92,8 +94,8 @@ struct TopologyHost {
         for (int n : d.nodes) {
           leaf_of[k][n] = (int)di;
           for (int r = 0; r < R; r++) {
-            d.free_live[r] += mI[(size_t)r * N + n];
-            d.free_live[r] += mL[(size_t)r * N + n];
+            d.free_live[r] += mI_(r, n);
+            d.free_live[r] += mL_(r, n);
           }
         }
       }
@@ -188,7 +190,7 @@ struct TopologyHost {
   }
   bool any() const { return !topos.empty() && !job_topology.empty(); }
   bool constrained(int job) const { return any() && job_topology[job] != -1; }
-  double avail(int r, int n) const { return mI[(size_t)r * N + n] + mL[(size_t)r * N + n]; }
+  double avail(int r, int n) const { return mI_(r, n) + mL_(r, n); }
 
   void build(const kai_snapshot *s) {
     topos.clear();
@@ -277,8 +279,8 @@ struct TopologyHost {
     if (d.children.empty()) {
       for (int n : d.nodes)
         for (int r = 0; r < R; r++) {
-          d.free[r] += mI[(size_t)r * N + n];
-          d.free[r] += mL[(size_t)r * N + n];
+          d.free[r] += mI_(r, n);
+          d.free[r] += mL_(r, n);
         }
       return;
     }

@@ -66,6 +66,20 @@ def main():
                     and np.array_equal(res.node_releasing[:, own], ref.node_releasing[:, own]))
             print(f"rank {rank}/{world} cycle {kw} {action}: {'OK' if same else 'MISMATCH'} placed {res.pods_placed} evicted {res.pods_evicted}", flush=True)
             ok = ok and same
+    # topology-constrained gangs (config-4 shape) on node-striped GPUs
+    for kw in (dict(n_nodes=512, n_gangs=60, nodes_per_rack=8, racks_per_leaf=4, leaves_per_spine=4, running_fraction=0.3),
+               dict(n_nodes=2048, n_gangs=300)):
+        snap = synthetic.topology_snapshot(**kw)
+        eng.load(snap)
+        res = eng.run("allocate")
+        o = Oracle()
+        o.load(snap)
+        ref = o.run("allocate")
+        own = engine.shard_node_mask(snap.node_name_rank, world, rank)
+        same = (np.array_equal(res.task_node, ref.task_node) and np.array_equal(res.task_status, ref.task_status)
+                and np.array_equal(res.visits, ref.visits) and np.array_equal(res.node_idle[:, own], ref.node_idle[:, own]))
+        print(f"rank {rank}/{world} topology {kw}: {'OK' if same else 'MISMATCH'} placed {res.pods_placed}", flush=True)
+        ok = ok and same
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
