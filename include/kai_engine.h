@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KAI_ABI_VERSION 3
+#define KAI_ABI_VERSION 4
 #define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
 #define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
 #define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
@@ -199,6 +199,23 @@ typedef struct kai_snapshot {
   const int32_t *job_topology;         /* [J]; NULL = no constraints */
   const int32_t *job_required_level;   /* [J] */
   const int32_t *job_preferred_level;  /* [J] */
+
+  /* ---- SubGroupSet tree of every job (api/podgroup_info/subgroup_info/subgroupset.go; allocate.go:36-83 walks it).
+         Sets of job j = [job_sgs_begin[j], job_sgs_begin[j+1]); the first one is the root.  NULL job_sgs_begin =
+         every job has only its root set holding all its PodSets, with the job_* constraint above and no PodSet
+         constraints.  When given, the root's constraint is sgs_* of its entry and job_* are ignored. ---- */
+  int32_t n_subgroup_sets;
+  int32_t reserved2;
+  const int32_t *job_sgs_begin;          /* [J+1] */
+  const int32_t *sgs_parent;             /* [G] global index of the parent set, -1 for a root */
+  const int32_t *sgs_name_rank;          /* [G] rank of the set's name among the sets of its job (SubGroupSetOrderFn) */
+  const int32_t *sgs_topology;           /* [G] topology index, -1 none */
+  const int32_t *sgs_required_level;     /* [G] */
+  const int32_t *sgs_preferred_level;    /* [G] */
+  const int32_t *podset_sgs;             /* [S] global index of the set that holds the PodSet */
+  const int32_t *podset_topology;        /* [S] PodSet's own constraint, -1 none; NULL = none */
+  const int32_t *podset_required_level;  /* [S] */
+  const int32_t *podset_preferred_level; /* [S] */
 } kai_snapshot;
 
 /* One entry per job popped by an action, in visiting order. */

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-KAI_ABI_VERSION = 3
+KAI_ABI_VERSION = 4
 KAI_MAX_RES = 8
 KAI_QRES = 3
 RES_CPU, RES_MEM, RES_GPU, RES_PODS = 0, 1, 2, 3
@@ -80,6 +80,10 @@ class KaiSnapshot(C.Structure):
         ("n_topologies", C.c_int32), ("reserved1", C.c_int32),
         ("topology_level_begin", _ip), ("node_domain", _ip),
         ("job_topology", _ip), ("job_required_level", _ip), ("job_preferred_level", _ip),
+        ("n_subgroup_sets", C.c_int32), ("reserved2", C.c_int32),
+        ("job_sgs_begin", _ip), ("sgs_parent", _ip), ("sgs_name_rank", _ip), ("sgs_topology", _ip),
+        ("sgs_required_level", _ip), ("sgs_preferred_level", _ip), ("podset_sgs", _ip), ("podset_topology", _ip),
+        ("podset_required_level", _ip), ("podset_preferred_level", _ip),
     ]
 
 
@@ -159,6 +163,16 @@ class Snapshot:
     job_topology: np.ndarray | None = None          # [J] i32, -1 none
     job_required_level: np.ndarray | None = None    # [J] i32
     job_preferred_level: np.ndarray | None = None   # [J] i32
+    job_sgs_begin: np.ndarray | None = None         # [J+1] SubGroupSet tree (see include/kai_engine.h)
+    sgs_parent: np.ndarray | None = None
+    sgs_name_rank: np.ndarray | None = None
+    sgs_topology: np.ndarray | None = None
+    sgs_required_level: np.ndarray | None = None
+    sgs_preferred_level: np.ndarray | None = None
+    podset_sgs: np.ndarray | None = None
+    podset_topology: np.ndarray | None = None
+    podset_required_level: np.ndarray | None = None
+    podset_preferred_level: np.ndarray | None = None
     names: dict = field(default_factory=dict)  # optional: node/job/task/queue names for reporting
     _keep: list = field(default_factory=list, repr=False)
 
@@ -248,6 +262,10 @@ class Snapshot:
         s.job_topology = p(self.job_topology, np.int32, _ip)
         s.job_required_level = p(self.job_required_level, np.int32, _ip)
         s.job_preferred_level = p(self.job_preferred_level, np.int32, _ip)
+        s.n_subgroup_sets = 0 if self.sgs_parent is None else int(len(self.sgs_parent))
+        for name in ("job_sgs_begin", "sgs_parent", "sgs_name_rank", "sgs_topology", "sgs_required_level", "sgs_preferred_level",
+                     "podset_sgs", "podset_topology", "podset_required_level", "podset_preferred_level"):
+            setattr(s, name, p(getattr(self, name), np.int32, _ip))
         self._keep = keep
         return s
 

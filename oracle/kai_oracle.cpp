@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <array>
 #include <map>
 #include <set>
 #include <string>
@@ -1101,9 +1102,9 @@ struct kai_oracle {
           score += binpack_score(mn, mx, cur, A(res, n));
         else
           score += spread_score(cur, res == KAI_RES_GPU ? (double)(int64_t)gpu_count[n] : A(res, n));
-        if (!topo_scores.empty()) {  // topology/node_scoring.go:17-34: last NodeOrderFn; a node without an entry
-          if (topo_scores[n] < 0) continue;  // makes NodeOrderFn fail => the node is dropped (session.go:247-251)
-          score += topo_scores[n];
+        if (cur_scores) {  // topology/node_scoring.go:17-34: last NodeOrderFn; a node without an entry
+          if ((*cur_scores)[n] < 0) continue;  // makes NodeOrderFn fail => the node is dropped (session.go:247-251)
+          score += (*cur_scores)[n];
         }
         if (b.node < 0 || score > b.score || (score == b.score && name_rank[n] < b.rank)) {
           b.score = score;
@@ -1197,7 +1198,26 @@ struct kai_oracle {
   };
   std::vector<Topo> topos;
   std::vector<int> topo_level_begin, node_domain, job_topology, job_req_level, job_pref_level;
-  std::vector<double> topo_scores;  // subGroupNodeScores of the job being allocated: per node, -1 = no entry; empty = none
+  // subGroupNodeScores of the job being allocated (topology_plugin.go:26-29): per SubGroup key (set id, or G + podset id)
+  // a per-node table, -1 = no entry.  A task uses the table of its PodSet or of the nearest ancestor set that has one
+  // (node_scoring.go:85-94 getRelevantNodeScores).
+  std::map<int, std::vector<double>> sg_scores;
+  const std::vector<double> *cur_scores = nullptr;
+  // SubGroupSet tree, normalised at load: every job has a root set
+  std::vector<int> set_parent, set_rank, job_root_set, ps_set;
+  std::vector<std::vector<int>> set_children, set_podsets;
+  std::vector<std::array<int, 3>> set_con, ps_con;  // (topology, required level, preferred level)
+  std::vector<char> job_general;                    // nested sets or any topology constraint: walk the tree
+  const std::vector<double> *scores_for_task(int ti) const {
+    const int ps = T[ti].podset;
+    auto it = sg_scores.find((int)set_parent.size() + ps);
+    if (it != sg_scores.end()) return &it->second;
+    for (int g = ps_set[ps]; g >= 0; g = set_parent[g]) {
+      it = sg_scores.find(g);
+      if (it != sg_scores.end()) return &it->second;
+    }
+    return nullptr;
+  }
   int ND(int level, int n) const { return node_domain[(size_t)level * N + n]; }
   void build_topologies() {
     topos.clear();
@@ -1351,16 +1371,18 @@ struct kai_oracle {
     for (int c : tp.doms[di].children) level_domains(tp, c, level, out);
   }
   // subSetNodesFn for the root SubGroupSet of the view's job.  ok = false: error / no node set (job fails).
-  std::vector<std::vector<int>> subset_nodes(int v, const std::vector<int> &tasks, const std::vector<int> &node_set, bool &ok) {
+  // `con` = the SubGroup's (topology, required, preferred); `key` identifies it in sg_scores; `under` = the PodSets below
+  // it (positions in Job::podsets) for the active-pods restriction.
+  std::vector<std::vector<int>> subset_nodes(int v, const std::array<int, 3> &con, int key, const std::vector<int> &under,
+                                             const std::vector<int> &tasks, const std::vector<int> &node_set, bool &ok) {
     ok = true;
-    const int ji = vjob(v);
-    const int k = job_topology.empty() ? -1 : job_topology[ji];
+    const int k = con[0];
     if (k == -2) {  // requested topology does not exist
       return {};
     }
     if (k < 0 || tasks.empty()) return {node_set};
     Topo &tp = topos[k];
-    const int req = job_req_level[ji], pref = job_pref_level[ji];  // level index inside the topology, -1 none, -2 unknown
+    const int req = con[1], pref = con[2];  // level index inside the topology, -1 none, -2 unknown
     // common.go:17-61 lowestCommonDomainID
     std::vector<int> valid;
     for (int n : node_set)
@@ -1410,6 +1432,7 @@ struct kai_oracle {
     const int max_depth = pref >= 0 ? tp.lb + pref : tp.lb + req;
     sort_tree(tp, dom, tasks_res, max_depth);
     if (pref >= 0) {  // node_scoring.go:36-53 calculateNodeScores
+      std::vector<double> &topo_scores = sg_scores[key];
       topo_scores.assign(N, -1.0);
       std::vector<int> lvl;
       level_domains(tp, dom, tp.lb + pref, lvl);
@@ -1434,7 +1457,7 @@ struct kai_oracle {
     std::vector<char> allowed(tp.doms.size(), 1);
     {
       bool has_active = false;
-      for (int ps2 = 0; ps2 < v_nps(v); ps2++)
+      for (int ps2 : under)
         if (v_active_alloc(v, ps2) > 0) has_active = true;
       if (has_active && req >= 0) {  // :269-300 getRelevantDomainsWithAllocatedPods
         std::fill(allowed.begin(), allowed.end(), 0);
@@ -1445,10 +1468,11 @@ struct kai_oracle {
         for (int di : tp.dom_at[req]) {
           if (di < 0) continue;
           bool has = false;
-          for (int ti : v_all_tasks(v))
-            if ((T[ti].status & kActiveAllocated) && T[ti].node >= 0 && tp.node_in[T[ti].node] &&
-                tp.dom_at[req][ND(tp.lb + req, T[ti].node)] == di)
-              has = true;
+          for (int ps2 : under)
+            for (int ti : v_ps_tasks(v, ps2))
+              if ((T[ti].status & kActiveAllocated) && T[ti].node >= 0 && tp.node_in[T[ti].node] &&
+                  tp.dom_at[req][ND(tp.lb + req, T[ti].node)] == di)
+                has = true;
           if (has) mark(di);
         }
       }
@@ -1495,7 +1519,9 @@ struct kai_oracle {
     // whole-GPU pods are checked with GPU = 1, CPU-only pods with GPU = 0; node independent.
     double req[QR] = {t.req[KAI_RES_CPU], t.req[KAI_RES_MEM], task_requires_gpu(t) ? 1.0 : 0.0};
     if (over_capacity(t.job, req)) return false;
+    cur_scores = sg_scores.empty() ? nullptr : scores_for_task(ti);
     int n = pick_node(ti, node_set);
+    cur_scores = nullptr;
     if (getenv("KAI_ORACLE_TRACE")) fprintf(stderr, "[solver]       task %d -> node %d (pipeline_only %d)\n", ti, n, (int)pipeline_only);
     if (n < 0) return false;
     if (!pipeline_only && is_task_allocatable(t, n))
@@ -1514,21 +1540,8 @@ struct kai_oracle {
     for (int ti : tta)
       for (int r = 0; r < QR; r++) req[r] += T[ti].req[r];
     if (over_capacity(ji, req)) return false;
-    topo_scores.clear();  // PreJobAllocation (topology_plugin.go:52-55)
-    // allocateSubGroupSet(root): node sets from SubsetNodesFn, first one that takes the whole job wins
-    std::vector<std::vector<int>> node_sets;
-    const bool constrained = !job_topology.empty() && job_topology[ji] != -1;
-    if (constrained) {
-      std::vector<int> all;
-      if (node_set)
-        all = *node_set;
-      else
-        for (int n = 0; n < N; n++) all.push_back(n);
-      bool ok_sets = true;
-      node_sets = subset_nodes(v, tta, all, ok_sets);
-      if (!ok_sets) return false;
-    }
-    auto on_nodes = [&](const std::vector<int> *ns) {
+    sg_scores.clear();  // PreJobAllocation (topology_plugin.go:52-55)
+    auto on_nodes = [&](const std::vector<int> *ns) {  // flat job: the root's PodSets in PodSetOrderFn order
       int cp = stmt_checkpoint();
       std::vector<int> sets = ordered_podsets(v);
       for (int k : sets) {
@@ -1550,10 +1563,77 @@ struct kai_oracle {
       }
       return true;
     };
-    if (!constrained) return on_nodes(node_set);
-    for (auto &ns : node_sets)
-      if (on_nodes(&ns)) return true;
+    if (job_general.empty() || !job_general[ji]) return on_nodes(node_set);
+    std::vector<int> all;
+    if (node_set)
+      all = *node_set;
+    else
+      for (int n = 0; n < N; n++) all.push_back(n);
+    return alloc_set(v, job_root_set[ji], tta, all, pipeline_only);
+  }
+  // allocate.go:36-83 allocateSubGroupSet / allocateSubGroupSetOnNodes / allocatePodSet on the SubGroupSet tree
+  void podsets_under(int g, int ji, std::vector<int> &out) const {
+    for (int ps : set_podsets[g])
+      for (size_t k = 0; k < J[ji].podsets.size(); k++)
+        if (J[ji].podsets[k] == ps) out.push_back((int)k);
+    for (int c : set_children[g]) podsets_under(c, ji, out);
+  }
+  bool alloc_set(int v, int g, const std::vector<int> &tasks, const std::vector<int> &nodes, bool pipeline_only) {
+    const int ji = vjob(v);
+    std::vector<int> under;
+    podsets_under(g, ji, under);
+    bool ok = true;
+    std::vector<std::vector<int>> node_sets = subset_nodes(v, set_con[g], g, under, tasks, nodes, ok);
+    if (!ok) return false;
+    for (auto &ns : node_sets) {
+      int cp = stmt_checkpoint();
+      if (set_on_nodes(v, g, tasks, ns, pipeline_only)) return true;
+      stmt_rollback(cp);
+    }
     return false;
+  }
+  bool set_on_nodes(int v, int g, const std::vector<int> &tasks, const std::vector<int> &ns, bool pipeline_only) {
+    const int ji = vjob(v);
+    for (int c : set_children[g]) {  // orderedSubGroupSets: by name
+      std::vector<int> under;
+      podsets_under(c, ji, under);
+      std::vector<int> sub;
+      for (int ti : tasks)
+        for (int k : under)
+          if (T[ti].podset == J[ji].podsets[k]) sub.push_back(ti);
+      if (!alloc_set(v, c, sub, ns, pipeline_only)) return false;
+    }
+    std::vector<int> ks;  // orderedPodSets: the set's own PodSets in PodSetOrderFn order
+    for (int ps : set_podsets[g])
+      for (size_t k = 0; k < J[ji].podsets.size(); k++)
+        if (J[ji].podsets[k] == ps) ks.push_back((int)k);
+    std::sort(ks.begin(), ks.end(), [&](int a, int b) { return podset_less_v(v, a, b); });
+    for (int k : ks) {
+      const int ps = J[ji].podsets[k];
+      std::vector<int> pt;
+      for (int ti : tasks)
+        if (T[ti].podset == ps) pt.push_back(ti);
+      bool ok = true;
+      std::vector<std::vector<int>> node_sets = subset_nodes(v, ps_con[ps], (int)set_parent.size() + ps, {k}, pt, ns, ok);
+      if (!ok) return false;
+      bool placed = false;
+      for (auto &ns2 : node_sets) {
+        int cp = stmt_checkpoint();
+        bool all_ok = true;
+        for (int ti : pt)
+          if (!allocate_task(ti, &ns2, pipeline_only)) {
+            all_ok = false;
+            break;
+          }
+        if (all_ok) {
+          placed = true;
+          break;
+        }
+        stmt_rollback(cp);
+      }
+      if (!placed) return false;
+    }
+    return true;
   }
   // job_info.go:443-464 ShouldPipelineJob
   bool should_pipeline_job(int ji) const {
@@ -2764,12 +2844,61 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
     o->node_domain.assign(s->node_domain, s->node_domain + nl * (size_t)o->N);
     o->build_topologies();
   }
-  if (s->job_topology) {
-    o->job_topology.assign(s->job_topology, s->job_topology + o->NJ);
-    o->job_req_level.assign(o->NJ, -1);
-    o->job_pref_level.assign(o->NJ, -1);
-    if (s->job_required_level) o->job_req_level.assign(s->job_required_level, s->job_required_level + o->NJ);
-    if (s->job_preferred_level) o->job_pref_level.assign(s->job_preferred_level, s->job_preferred_level + o->NJ);
+  // SubGroupSet tree, normalised: with no tree in the snapshot every job has one root set holding all its PodSets
+  {
+    const int NJ = o->NJ, NS = o->NS;
+    o->set_parent.clear();
+    o->set_rank.clear();
+    o->set_con.clear();
+    o->job_root_set.assign(NJ, -1);
+    o->ps_set.assign(NS, -1);
+    o->ps_con.assign(NS, std::array<int, 3>{-1, -1, -1});
+    if (s->job_sgs_begin && s->sgs_parent && s->podset_sgs) {
+      const int G = s->n_subgroup_sets;
+      for (int g = 0; g < G; g++) {
+        o->set_parent.push_back(s->sgs_parent[g]);
+        o->set_rank.push_back(s->sgs_name_rank ? s->sgs_name_rank[g] : g);
+        o->set_con.push_back({s->sgs_topology ? s->sgs_topology[g] : -1, s->sgs_required_level ? s->sgs_required_level[g] : -1,
+                              s->sgs_preferred_level ? s->sgs_preferred_level[g] : -1});
+      }
+      for (int j = 0; j < NJ; j++) o->job_root_set[j] = s->job_sgs_begin[j];
+      for (int ps = 0; ps < NS; ps++) {
+        o->ps_set[ps] = s->podset_sgs[ps];
+        if (s->podset_topology)
+          o->ps_con[ps] = {s->podset_topology[ps], s->podset_required_level ? s->podset_required_level[ps] : -1,
+                           s->podset_preferred_level ? s->podset_preferred_level[ps] : -1};
+      }
+    } else {
+      for (int j = 0; j < NJ; j++) {
+        o->job_root_set[j] = (int)o->set_parent.size();
+        o->set_parent.push_back(-1);
+        o->set_rank.push_back(0);
+        o->set_con.push_back({s->job_topology ? s->job_topology[j] : -1, s->job_required_level ? s->job_required_level[j] : -1,
+                              s->job_preferred_level ? s->job_preferred_level[j] : -1});
+        for (int ps : o->J[j].podsets) o->ps_set[ps] = o->job_root_set[j];
+      }
+    }
+    const int G = (int)o->set_parent.size();
+    o->set_children.assign(G, {});
+    o->set_podsets.assign(G, {});
+    for (int g = 0; g < G; g++)
+      if (o->set_parent[g] >= 0) o->set_children[o->set_parent[g]].push_back(g);
+    for (auto &ch : o->set_children)
+      std::sort(ch.begin(), ch.end(), [&](int a, int b) { return o->set_rank[a] < o->set_rank[b]; });
+    for (int ps = 0; ps < NS; ps++)
+      if (o->ps_set[ps] >= 0) o->set_podsets[o->ps_set[ps]].push_back(ps);
+    o->job_general.assign(NJ, 0);
+    std::vector<int> job_of_root(G, -1);
+    for (int j = 0; j < NJ; j++)
+      if (o->job_root_set[j] >= 0) job_of_root[o->job_root_set[j]] = j;
+    for (int g = 0; g < G; g++) {
+      if (o->set_con[g][0] == -1 && o->set_parent[g] < 0) continue;
+      int root = g;
+      while (o->set_parent[root] >= 0) root = o->set_parent[root];
+      if (job_of_root[root] >= 0) o->job_general[job_of_root[root]] = 1;
+    }
+    for (int ps = 0; ps < NS; ps++)
+      if (o->ps_con[ps][0] != -1) o->job_general[o->PS[ps].job] = 1;
   }
   o->loaded = true;
   o->pods_placed = o->pods_evicted = 0;

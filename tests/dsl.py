@@ -114,6 +114,7 @@ def build_snapshot(topo: dict):
     podset_min, podset_task_begin = [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_job = [], [], [], [], [], []
     t_fixture_node = []
+    job_podset_names = []
     for ji, job in enumerate(jobs):
         job_names.append(job["Name"])
         job_queue.append(qindex.get(job.get("QueueName", ""), -1))
@@ -152,6 +153,7 @@ def build_snapshot(topo: dict):
             pr = t.get("Priority")
             order_keys.append((0 if pr is not None else 1, -(pr or 0), uid, k))
         order_rank = {k: r for r, (_, _, _, k) in enumerate(sorted(order_keys))}
+        job_podset_names.append([p_[0] for p_ in podsets])
         for ps_name, ps_min in podsets:
             podset_min.append(ps_min)
             for k, t in enumerate(tasks):
@@ -223,23 +225,62 @@ def build_snapshot(topo: dict):
                 order = {d: i for i, d in enumerate(sorted(set(ids.values())))}
                 for n, d in ids.items():
                     node_domain[level_begin[k] + li, n] = order[d]
-        j_topo = np.full(nj, -1, dtype=np.int32)
-        j_req = np.full(nj, -1, dtype=np.int32)
-        j_pref = np.full(nj, -1, dtype=np.int32)
-        for ji, job in enumerate(jobs):
-            tc = (job.get("RootSubGroupSet") or {}).get("topology_constraint")
+        def con(tc):
+            """TopologyConstraintInfo -> (topology, required level, preferred level) indices; -2 = unknown name"""
             if not tc or not tc.get("Topology"):
-                continue
+                return (-1, -1, -1)
             if tc["Topology"] not in tnames:
-                j_topo[ji] = -2  # "Requested topology does not exist" (job_filtering.go:41-47): never schedulable
-                continue
+                return (-2, -1, -1)  # "Requested topology does not exist" (job_filtering.go:41-47)
             k = tnames.index(tc["Topology"])
-            j_topo[ji] = k
-            for key, arr in (("RequiredLevel", j_req), ("PreferredLevel", j_pref)):
-                if tc.get(key):
-                    arr[ji] = level_labels[k].index(tc[key]) if tc[key] in level_labels[k] else -2
+            lv = []
+            for key in ("RequiredLevel", "PreferredLevel"):
+                lv.append((level_labels[k].index(tc[key]) if tc[key] in level_labels[k] else -2) if tc.get(key) else -1)
+            return (k, lv[0], lv[1])
+
+        # SubGroupSet tree per job: sets in pre-order (root first), PodSets attached to their set
+        job_sgs_begin, sgs_parent, sgs_names, sgs_con = [0], [], [], []
+        ps_sgs = [0] * len(podset_min)
+        ps_con = [(-1, -1, -1)] * len(podset_min)
+        for ji, job in enumerate(jobs):
+            root = job.get("RootSubGroupSet") or {}
+            tree = root.get("tree") or {"name": "root", "constraint": root.get("topology_constraint"), "podsets": [], "groups": []}
+            ps_names = job_podset_names[ji]
+            first_ps = job_podset_begin[ji]
+            placed = set()
+
+            def walk(g, parent):
+                gi = len(sgs_parent)
+                sgs_parent.append(parent)
+                sgs_names.append(g["name"])
+                sgs_con.append(con(g.get("constraint")))
+                for p in g["podsets"]:
+                    k = ps_names.index(p["name"])
+                    ps_sgs[first_ps + k] = gi
+                    ps_con[first_ps + k] = con(p.get("constraint"))
+                    placed.add(p["name"])
+                for c in g["groups"]:
+                    walk(c, gi)
+                return gi
+
+            root_gi = walk(tree, -1)
+            for k, name in enumerate(ps_names):  # the default PodSet (and flat lists) hang off the root
+                if name not in placed:
+                    ps_sgs[first_ps + k] = root_gi
+            job_sgs_begin.append(len(sgs_parent))
+        sgs_name_rank = np.zeros(len(sgs_parent), dtype=np.int32)
+        for ji in range(nj):
+            b, e = job_sgs_begin[ji], job_sgs_begin[ji + 1]
+            order = sorted(range(b, e), key=lambda g: sgs_names[g])
+            for r_, g in enumerate(order):
+                sgs_name_rank[g] = r_
         topo_kw = dict(topology_level_begin=np.array(level_begin, dtype=np.int32), node_domain=node_domain,
-                       job_topology=j_topo, job_required_level=j_req, job_preferred_level=j_pref)
+                       job_sgs_begin=np.array(job_sgs_begin, dtype=np.int32), sgs_parent=np.array(sgs_parent, dtype=np.int32),
+                       sgs_name_rank=sgs_name_rank, sgs_topology=np.array([c[0] for c in sgs_con], dtype=np.int32),
+                       sgs_required_level=np.array([c[1] for c in sgs_con], dtype=np.int32),
+                       sgs_preferred_level=np.array([c[2] for c in sgs_con], dtype=np.int32),
+                       podset_sgs=np.array(ps_sgs, dtype=np.int32), podset_topology=np.array([c[0] for c in ps_con], dtype=np.int32),
+                       podset_required_level=np.array([c[1] for c in ps_con], dtype=np.int32),
+                       podset_preferred_level=np.array([c[2] for c in ps_con], dtype=np.int32))
 
     snap = abi.Snapshot(
         n_res=R,

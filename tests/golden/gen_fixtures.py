@@ -95,25 +95,55 @@ def resolve(x):
     return x
 
 
-_PODSET = re.compile(r'NewPodSet \( "([^"]+)" , (\d+) , (nil|[^)]*)\)')
+_CONSTRAINT = r'(nil|& topology_info \. TopologyConstraintInfo \{ (?:[^{}]*) \})'
+_NEWSET = re.compile(r'(\w+) : = subgroup_info \. NewSubGroupSet \( ((?:"[^"]*")|(?:subgroup_info \. RootSubGroupSetName)) , ' + _CONSTRAINT + r'(?: ,)? \)')
+_ADDPODSET = re.compile(r'(\w+) \. AddPodSet \( subgroup_info \. NewPodSet \( "([^"]+)" , (\d+) , ' + _CONSTRAINT + r'(?: ,)? \) \)')
+_ADDGROUP = re.compile(r'(\w+) \. AddSubGroup \( (\w+) \)')
+_RETURN = re.compile(r'return (\w+) \}')
+_KV = re.compile(r'(\w+) : "([^"]*)"')
+
+
+def _constraint(txt):
+    if txt.strip() == "nil":
+        return None
+    return {k: v for k, v in _KV.findall(txt)}
 
 
 def parse_subgroup_func(body: str):
-    """RootSubGroupSet: func() *SubGroupSet { root := NewSubGroupSet(...); root.AddPodSet(NewPodSet(name, min, nil)) ... }"""
-    n_sets = body.count("NewSubGroupSet")
-    podsets = []
-    unsupported = None
-    for m in _PODSET.finditer(body):
-        podsets.append({"name": m.group(1), "min_available": int(m.group(2))})
-        if m.group(3).strip() != "nil":
-            unsupported = "podset topology constraint"
-    if n_sets > 1:
-        unsupported = "nested SubGroupSets"
-    if "TopologyConstraint" in body:
-        unsupported = "subgroup topology constraint"
-    out = {"podsets": podsets}
-    if unsupported or not podsets:
-        out["__unsupported"] = unsupported or "unparsed RootSubGroupSet"
+    """RootSubGroupSet: func() *SubGroupSet { x := NewSubGroupSet(name, constraint); x.AddPodSet(NewPodSet(name, min,
+    constraint)); root.AddSubGroup(x); ...; return root } -> the SubGroupSet tree."""
+    sets = {}
+    events = []
+    for m in _NEWSET.finditer(body):
+        name = "root" if "RootSubGroupSetName" in m.group(2) else m.group(2).strip('"')
+        events.append((m.start(), "set", m.group(1), name, _constraint(m.group(3))))
+    for m in _ADDPODSET.finditer(body):
+        events.append((m.start(), "podset", m.group(1), m.group(2), int(m.group(3)), _constraint(m.group(4))))
+    for m in _ADDGROUP.finditer(body):
+        events.append((m.start(), "group", m.group(1), m.group(2)))
+    ret = _RETURN.search(body)
+    n_stmt = body.count(": =") + body.count(". AddPodSet") + body.count(". AddSubGroup")
+    if not ret or len(events) != n_stmt:
+        return {"podsets": [], "__unsupported": "unparsed RootSubGroupSet"}
+    for ev in sorted(events):
+        if ev[1] == "set":
+            sets[ev[2]] = {"name": ev[3], "constraint": ev[4], "podsets": [], "groups": []}
+        elif ev[1] == "podset":
+            sets[ev[2]]["podsets"].append({"name": ev[3], "min_available": ev[4], "constraint": ev[5]})
+        else:
+            sets[ev[2]]["groups"].append(sets[ev[3]])
+    root = sets[ret.group(1)]
+
+    def flat(g):
+        out = list(g["podsets"])
+        for c in g["groups"]:
+            out += flat(c)
+        return out
+
+    simple = not root["groups"] and root["constraint"] is None and all(p["constraint"] is None for p in root["podsets"])
+    out = {"podsets": [{"name": p["name"], "min_available": p["min_available"]} for p in flat(root)]}
+    if not simple:
+        out["tree"] = root
     return out
 
 

@@ -55,4 +55,4 @@ def test_case_counts():
     assert len(INTEGRATION) == 60
     assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 25 and len(PREEMPT) == 31
     # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
-    assert len(ALLOCATE) == 51  # allocate 21 + gang 6 + elastic 7 + subgroups 7 + topology 10
+    assert len(ALLOCATE) == 59  # allocate 21 + gang 6 + elastic 7 + subgroups 8 + topology 17
