@@ -236,10 +236,11 @@ __device__ Cand scan_tile(const Tile &tl, const Decision &d, const DevSnap &s, C
   best.rank = kRankNone;
   best.ln = -1;
   const uint32_t *mask = d.pred_class >= 0 ? s.pred_mask + (size_t)d.pred_class * s.mask_words : nullptr;
+  const uint32_t dom_need = dom_need_mask((unsigned int)xbits);
   for (int ln = threadIdx.x; ln < tl.count; ln += blockDim.x) {
     int n = tl.node[ln];
     if (d.restricted && !(tl.flags[ln] & kTileFeas)) continue;
-    if ((xbits & XB_RESTRICT_DOM) && !(tl.flags[ln] & kTileDom)) continue;
+    if ((xbits & XB_RESTRICT_DOM) && (tl.flags[ln] & dom_need) != dom_need) continue;
     if (mask && !((__ldg(&mask[n >> 5]) >> (n & 31)) & 1u)) continue;
     double score;
     bool fit_i;
@@ -1074,16 +1075,18 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
         const int kind = (en.x >> 28) & 7;
         const unsigned int a = (unsigned int)en.x & 0x0fffffffu, b = (unsigned int)en.y;
         if (kind == EXT_SELECT || kind == EXT_SELECT_ROOT) {
+          const int slot = kind == EXT_SELECT ? (int)((a >> 8) & 7u) : (int)((a >> 16) & 7u);
+          const uint32_t bit = kTileDom >> slot;
           for (int ln = tid; ln < tile.count; ln += blockDim.x) {
             bool in;
             if (kind == EXT_SELECT) {
-              in = tile.dom[((int)a - 1) * tile.npc + ln] == (int)b;
+              in = tile.dom[((int)(a & 0xffu) - 1) * tile.npc + ln] == (int)b;
             } else {
               in = true;
               for (int l = (int)(a & 0xff); l < (int)((a >> 8) & 0xff); l++)
                 if (tile.dom[l * tile.npc + ln] < 0) in = false;
             }
-            tile.flags[ln] = in ? (tile.flags[ln] | kTileDom) : (tile.flags[ln] & ~kTileDom);
+            tile.flags[ln] = in ? (tile.flags[ln] | bit) : (tile.flags[ln] & ~bit);
           }
         } else if (kind == EXT_SCORE_BEGIN) {
           for (int i = tid; i < kDomBuckets; i += blockDim.x) sh.dom_bucket[i] = 255;
@@ -1118,7 +1121,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
             double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
             if (overall == 0) continue;
             if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
-            if ((sh.xbits & XB_RESTRICT_DOM) && !(tile.flags[ln] & kTileDom)) continue;
+            if ((sh.xbits & XB_RESTRICT_DOM) && (tile.flags[ln] & dom_need_mask((unsigned int)sh.xbits)) != dom_need_mask((unsigned int)sh.xbits)) continue;
             double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
             if (cur < mn[k]) mn[k] = cur;
             if (cur > mx[k]) mx[k] = cur;
@@ -1230,7 +1233,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
           if (overall == 0) continue;
           if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
-          if ((sh.xbits & XB_RESTRICT_DOM) && !(tile.flags[ln] & kTileDom)) continue;
+          if ((sh.xbits & XB_RESTRICT_DOM) && (tile.flags[ln] & dom_need_mask((unsigned int)sh.xbits)) != dom_need_mask((unsigned int)sh.xbits)) continue;
           double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
           if (cur < mn[k]) mn[k] = cur;
           if (cur > mx[k]) mx[k] = cur;
@@ -1260,7 +1263,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           double overall = k == 0 ? tile.Agpu[ln] : tile.Acpu[ln];
           if (overall == 0) continue;
           if (sh.dec.restricted && !(tile.flags[ln] & kTileFeas)) continue;
-          if ((sh.xbits & XB_RESTRICT_DOM) && !(tile.flags[ln] & kTileDom)) continue;
+          if ((sh.xbits & XB_RESTRICT_DOM) && (tile.flags[ln] & dom_need_mask((unsigned int)sh.xbits)) != dom_need_mask((unsigned int)sh.xbits)) continue;
           double cur = __dadd_rn(tile.I[res * tile.npc + ln], tile.L[res * tile.npc + ln]);
           if (cur == mn[k]) c[2 * k]++;
           if (cur == mx[k]) c[2 * k + 1]++;

@@ -947,6 +947,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     seq.mirror = e->h_mirror.data();
     e->topo.mirror = e->h_mirror.data();
     e->topo.t_req = hs.t_req;
+    e->topo.t_podset = hs.t_podset;
     seq.topology = e->topo.any() ? &e->topo : nullptr;
     seq.on_node_changed = &TopologyHost::node_changed_hook;
     e->topo.reset_gpu_state();

@@ -444,52 +444,46 @@ struct HostBackend {
     return job_success;
   }
 
-  // allocateSubGroupSet for a job whose root SubGroupSet carries a topology constraint (allocate.go:36-60 with
-  // topology.subSetNodesFn): candidate domains in order, the first one that takes every task wins.
-  bool allocate_constrained(TopologyHost &topo, int job, const std::vector<int> &tta) {
-    const DevSnap &s = *seq.s;
-    bool has_active = false;
-    std::vector<int> active_nodes;
-    for (int ps = s.j_ps_begin[job]; ps < s.j_ps_begin[job + 1]; ps++) {
-      if (ps_get(seq, ps, 0) > 0) has_active = true;
+  // AllocateJob for a job with nested SubGroupSets / topology constraints (allocate.go:36-83 with
+  // topology.subSetNodesFn): the SubGroupSet tree is walked by TopoAllocator; this is the session side for the
+  // allocate action (the live job; lists / batching inside a selected row set as usual).
+  struct AllocOps {
+    HostBackend &hb;
+    int job;
+    int active_alloc(int ps) { return ps_get(hb.seq, ps, 0); }
+    void active_nodes(int ps, std::vector<int> &out) {
+      const DevSnap &s = *hb.seq.s;
       for (int t = s.ps_task_begin[ps]; t < s.ps_task_begin[ps + 1]; t++)
-        if (seq.rp.t_status[t] & kActiveAllocated) active_nodes.push_back(seq.rp.t_node[t]);
+        if (hb.seq.rp.t_status[t] & kActiveAllocated) out.push_back(hb.seq.rp.t_node[t]);
     }
+    bool podset_less(int a, int b) { return kai::podset_less(hb.seq, a, b); }
+    int checkpoint() { return hb.seq.n_ops; }
+    void rollback(int cp) { stmt_rollback(hb.seq, cp); }
+    bool place(const std::vector<int> &tasks, unsigned int xbits) {
+      double tt0 = now();
+      node_state_disturbed(hb.seq);  // another row set: the min/max trackers and any list belong to the previous one
+      hb.list_invalidate();
+      hb.sweep_xbits = xbits;
+      bool ok = hb.place_tasks(job, (int)tasks.size(), tasks.data());
+      hb.sweep_xbits = 0;
+      hb.t_topo[2] += now() - tt0;
+      hb.n_topo_domains++;
+      return ok && !hb.failed;
+    }
+    bool extra_in_set(int) { return true; }
+    bool all_nodes() { return true; }
+  };
+  bool allocate_constrained(TopologyHost &topo, int job, const std::vector<int> &tta) {
     double tt0 = now();
-    TopologyHost::Result r = topo.subset(job, tta, [](int) { return true; }, has_active, active_nodes, true);
-    t_topo[0] += now() - tt0;
-    if (!r.ok || r.domains.empty()) return false;
+    AllocOps ops{*this, job};
+    TopoAllocator<AllocOps> ta(topo, seq, ops, job);
     list_invalidate();
-    tt0 = now();
-    const bool pushed = topo.push_scores(seq, r);
-    t_topo[1] += now() - tt0;
     n_topo_jobs++;
-    if (!pushed) {
-      seq.error = 2;
-      return false;
-    }
-    bool placed = false;
-    for (int di : r.domains) {
-      if (failed) break;
-      const int cp = seq.n_ops;
-      topo.select_domain(seq, r, di);
-      node_state_disturbed(seq);  // another row set: the min/max trackers and any list belong to the previous one
-      list_invalidate();
-      sweep_xbits = XB_RESTRICT_DOM;
-      tt0 = now();
-      bool ok = place_tasks(job, (int)tta.size(), tta.data());
-      t_topo[2] += now() - tt0;
-      n_topo_domains++;
-      sweep_xbits = 0;
-      if (ok) {
-        placed = true;
-        break;
-      }
-      stmt_rollback(seq, cp);
-    }
+    bool placed = ta.alloc_set(topo.job_root_set[job], tta);
+    if (ta.unsupported) seq.error = 2;
     list_invalidate();
-    topo.clear_scores(seq, r);
     node_state_disturbed(seq);
+    t_topo[0] += now() - tt0;
     return placed;
   }
 

@@ -145,12 +145,20 @@ enum { DK_SCAN = 1, DK_MINMAX = 2, DK_FLUSH = 3, DK_DONE = 4, DK_TOPK = 5 };
 // list would be used once: heterogeneous requests, solver simulations) instead of the top-M lists.
 // XB_RESTRICT_DOM: sweep only the rows of the topology domain selected by the last EXT_SELECT entry.
 enum { XB_RESTRICT = 1, XB_SNAP_ALL = 2, XB_SNAP_GPUFREE = 4, XB_FUSED_MM = 8, XB_SINGLE = 16, XB_RESTRICT_DOM = 32 };
-constexpr uint32_t kTileDom = 1u << 29;  // tile flag bit: row belongs to the selected topology domain
+constexpr uint32_t kTileDom = 1u << 29;  // tile flag bits 29, 28, 27, 26: row belongs to the domain selected in slot 0..3
+constexpr int kDomSlots = 4;             // nesting depth of SubGroupSet / PodSet constraints the scanners can intersect
+// XB_RESTRICT_DOM sweeps carry the number of active slots in xbits bits 8..10: a row must sit in all of them
+KAI_HD inline uint32_t dom_need_mask(unsigned int xbits) {
+  const unsigned int n = (xbits >> 8) & 7u;
+  uint32_t m = 0;
+  for (unsigned int i = 0; i < n && i < (unsigned int)kDomSlots; i++) m |= kTileDom >> i;
+  return m;
+}
 // Extended delta entries (low word bit 31 set; every scanner applies them, they name no row):
 //   [31]=1 [30:28]=kind [27:0]=a | b
 enum {
-  EXT_SELECT = 0,       // a = level + 1 (global level index), b = domain id: DOM bit = (dom[level][row] == b)
-  EXT_SELECT_ROOT = 1,  // a = lb | le << 8: DOM bit = the row carries every level label of the topology [lb, le)
+  EXT_SELECT = 0,       // a = (level + 1) | slot << 8, b = domain id: slot bit = (dom[level][row] == b)
+  EXT_SELECT_ROOT = 1,  // a = lb | le << 8 | slot << 16: slot bit = the row carries every level label of topology [lb, le)
   EXT_SCORE_BEGIN = 2,  // a = preferred level (global): clear the per-domain bucket table, scoring on
   EXT_SCORE = 3,        // a = domain id at the preferred level, b = bucket: node score = bucket * scores.Topology
   EXT_SCORE_END = 4     // scoring off

@@ -546,6 +546,33 @@ struct Solver {
     return out;
   }
 
+  // session side of TopoAllocator for simulations: views with frozen counters, the solver's statement, the feasible set
+  struct SimOps {
+    Solver &so;
+    int v;
+    int k_of(int ps) const { return ps - so.ps_begin(so.vjob(v)); }
+    int active_alloc(int ps) { return so.v_active_alloc(v, k_of(ps)); }
+    void active_nodes(int ps, std::vector<int> &out) {
+      for (int t : so.v_ps_tasks(v, k_of(ps)))
+        if (so.st[t] & kActiveAllocated) out.push_back(so.tn[t]);
+    }
+    bool podset_less(int a, int b) { return so.podset_less(v, k_of(a), k_of(b)); }
+    int checkpoint() { return so.stmt_checkpoint(); }
+    void rollback(int cp) { so.stmt_rollback(cp); }
+    bool place(const std::vector<int> &tasks, unsigned int xbits) {
+      so.sweep_extra_bits = xbits;
+      bool ok = true;
+      for (int t : tasks)
+        if (!so.allocate_task(t)) {
+          ok = false;
+          break;
+        }
+      so.sweep_extra_bits = 0;
+      return ok && !so.gpu_failed();
+    }
+    bool extra_in_set(int n) { return so.in_base(n) || so.feas_extra[n]; }
+    bool all_nodes() { return false; }
+  };
   // ---------------- actions/common/allocate.go on views, pipeline-only ----------------
   const std::vector<char> *feasible = nullptr;
   bool allocate_task(int t) {
@@ -564,45 +591,12 @@ struct Solver {
       for (int r = 0; r < QR; r++) rq[r] += req(t, r);
     if (over_capacity(j, rq)) return false;
     TopologyHost *topo = (TopologyHost *)seq.topology;
-    if (topo && topo->constrained(j)) {  // allocateSubGroupSet with topology.subSetNodesFn (job_filtering.go:34-112)
-      bool has_active = false;
-      for (int k = 0; k < v_nps(v); k++)
-        if (v_active_alloc(v, k) > 0) has_active = true;
-      std::vector<int> active_nodes;
-      for (int t : v_all_tasks(v))
-        if (st[t] & kActiveAllocated) active_nodes.push_back(tn[t]);
-      TopologyHost::Result r = topo->subset(j, tta, [&](int n) { return in_base(n) || feas_extra[n]; }, has_active, active_nodes);
-      if (!r.ok || r.domains.empty()) return false;
-      if (!topo->push_scores(seq, r)) {
-        seq.error = 2;
-        return false;
-      }
-      bool placed = false;
-      sweep_extra_bits = XB_RESTRICT_DOM;
-      for (int di : r.domains) {
-        if (gpu_failed()) break;
-        int cp = stmt_checkpoint();
-        topo->select_domain(seq, r, di);
-        bool ok = true;
-        for (int k : ordered_podsets(v)) {
-          int ps = ps_begin(j) + k;
-          for (int t : tta) {
-            if (s.t_podset[t] != ps) continue;
-            if (!allocate_task(t)) {
-              ok = false;
-              break;
-            }
-          }
-          if (!ok) break;
-        }
-        if (ok) {
-          placed = true;
-          break;
-        }
-        stmt_rollback(cp);
-      }
+    if (topo && topo->constrained(j)) {  // SubGroupSet tree / topology constraints: allocate.go:36-83 via TopoAllocator
+      SimOps ops{*this, v};
+      TopoAllocator<SimOps> ta(*topo, seq, ops, j);
+      bool placed = ta.alloc_set(topo->job_root_set[j], tta);
+      if (ta.unsupported) seq.error = 2;
       sweep_extra_bits = 0;
-      topo->clear_scores(seq, r);
       return placed;
     }
     if (topo) topo->scores_off(seq);

@@ -14,7 +14,9 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <array>
 #include <functional>
+#include <map>
 #include <vector>
 
 #include "kai_seq.cuh"
@@ -39,7 +41,13 @@ struct TopologyHost {
     std::vector<char> lcd_all;  // per level: do all topology nodes share one domain (lowest common domain of the full set)
   };
   int N = 0, R = 4;
-  std::vector<int> level_begin, node_domain, job_topology, job_req, job_pref;
+  std::vector<int> level_begin, node_domain;
+  // SubGroupSet tree, normalised at load (every job has a root set); constraints = (topology, required, preferred)
+  std::vector<int> set_parent, set_rank, job_root_set, ps_set;
+  std::vector<std::vector<int>> set_children, set_podsets;
+  std::vector<std::array<int, 3>> set_con, ps_con;
+  std::vector<char> job_general;  // nested sets or any topology constraint: the allocation walks the tree
+  const int *t_podset = nullptr;  // [T] (engine task numbering)
   std::vector<Topo> topos;
   const double *mirror = nullptr;  // host mirror of Idle / Releasing, node-major [N][2][R]
   double mI_(int r, int n) const { return mirror[(size_t)n * 2 * R + r]; }
@@ -188,8 +196,12 @@ struct TopologyHost {
     }
     return tp.doms[di].alloc_pods;
   }
-  bool any() const { return !topos.empty() && !job_topology.empty(); }
-  bool constrained(int job) const { return any() && job_topology[job] != -1; }
+  bool any() const {
+    for (char c : job_general)
+      if (c) return true;
+    return false;
+  }
+  bool constrained(int job) const { return !job_general.empty() && job_general[job]; }
   double avail(int r, int n) const { return mI_(r, n) + mL_(r, n); }
 
   void build(const kai_snapshot *s) {
@@ -198,7 +210,6 @@ struct TopologyHost {
     classes.clear();
     level_begin.clear();
     node_domain.clear();
-    job_topology.clear();
     N = s->n_nodes;
     R = s->n_res;
     if (s->n_topologies > 0 && s->topology_level_begin && s->node_domain) {
@@ -243,12 +254,61 @@ struct TopologyHost {
         topos.push_back(tp);
       }
     }
-    if (s->job_topology) {
-      job_topology.assign(s->job_topology, s->job_topology + s->n_jobs);
-      job_req.assign(s->n_jobs, -1);
-      job_pref.assign(s->n_jobs, -1);
-      if (s->job_required_level) job_req.assign(s->job_required_level, s->job_required_level + s->n_jobs);
-      if (s->job_preferred_level) job_pref.assign(s->job_preferred_level, s->job_preferred_level + s->n_jobs);
+    {
+      const int NJ = s->n_jobs, NS = s->n_podsets;
+      set_parent.clear();
+      set_rank.clear();
+      set_con.clear();
+      job_root_set.assign(NJ, -1);
+      ps_set.assign(NS, -1);
+      ps_con.assign(NS, std::array<int, 3>{-1, -1, -1});
+      std::vector<int> ps_job(NS, -1);
+      for (int j = 0; j < NJ; j++)
+        for (int ps = s->job_podset_begin[j]; ps < s->job_podset_begin[j + 1]; ps++) ps_job[ps] = j;
+      if (s->job_sgs_begin && s->sgs_parent && s->podset_sgs) {
+        for (int g = 0; g < s->n_subgroup_sets; g++) {
+          set_parent.push_back(s->sgs_parent[g]);
+          set_rank.push_back(s->sgs_name_rank ? s->sgs_name_rank[g] : g);
+          set_con.push_back({s->sgs_topology ? s->sgs_topology[g] : -1, s->sgs_required_level ? s->sgs_required_level[g] : -1,
+                             s->sgs_preferred_level ? s->sgs_preferred_level[g] : -1});
+        }
+        for (int j = 0; j < NJ; j++) job_root_set[j] = s->job_sgs_begin[j];
+        for (int ps = 0; ps < NS; ps++) {
+          ps_set[ps] = s->podset_sgs[ps];
+          if (s->podset_topology)
+            ps_con[ps] = {s->podset_topology[ps], s->podset_required_level ? s->podset_required_level[ps] : -1,
+                          s->podset_preferred_level ? s->podset_preferred_level[ps] : -1};
+        }
+      } else {
+        for (int j = 0; j < NJ; j++) {
+          job_root_set[j] = (int)set_parent.size();
+          set_parent.push_back(-1);
+          set_rank.push_back(0);
+          set_con.push_back({s->job_topology ? s->job_topology[j] : -1, s->job_required_level ? s->job_required_level[j] : -1,
+                             s->job_preferred_level ? s->job_preferred_level[j] : -1});
+          for (int ps = s->job_podset_begin[j]; ps < s->job_podset_begin[j + 1]; ps++) ps_set[ps] = job_root_set[j];
+        }
+      }
+      const int G = (int)set_parent.size();
+      set_children.assign(G, {});
+      set_podsets.assign(G, {});
+      for (int g = 0; g < G; g++)
+        if (set_parent[g] >= 0) set_children[set_parent[g]].push_back(g);
+      for (auto &ch : set_children) std::sort(ch.begin(), ch.end(), [&](int a, int b) { return set_rank[a] < set_rank[b]; });
+      for (int ps = 0; ps < NS; ps++)
+        if (ps_set[ps] >= 0) set_podsets[ps_set[ps]].push_back(ps);
+      job_general.assign(NJ, 0);
+      std::vector<int> job_of_root(G, -1);
+      for (int j = 0; j < NJ; j++)
+        if (job_root_set[j] >= 0) job_of_root[job_root_set[j]] = j;
+      for (int g = 0; g < G; g++) {
+        if (set_con[g][0] == -1 && set_parent[g] < 0) continue;
+        int root = g;
+        while (set_parent[root] >= 0) root = set_parent[root];
+        if (job_of_root[root] >= 0) job_general[job_of_root[root]] = 1;
+      }
+      for (int ps = 0; ps < NS; ps++)
+        if (ps_con[ps][0] != -1 && ps_job[ps] >= 0) job_general[ps_job[ps]] = 1;
     }
   }
 
@@ -397,6 +457,7 @@ struct TopologyHost {
 
   struct Result {
     bool ok = true;            // false: configuration error (the job fails)
+    bool passthrough = false;  // no constraint (or no tasks): the node set is handed on unchanged
     int topo = -1;
     std::vector<int> domains;  // candidate domains (indices into topos[topo].doms), in the order to try
     int pref_level = -1;       // global level index when node scores apply
@@ -405,21 +466,28 @@ struct TopologyHost {
   // subSetNodesFn for the job's root SubGroupSet.  `in_set(n)`: the node set handed to allocate (all nodes, or the
   // solver's feasible set).  `active_nodes`: nodes of the job's active-allocated pods; has_active: any podset of the
   // (view of the) job counts active-allocated pods.
-  Result subset(int job, const std::vector<int> &tasks, const std::function<bool(int)> &in_set, bool has_active,
-                const std::vector<int> &active_nodes, bool all_nodes = false) {
+  // `base_nodes`: the nodes of the innermost domain already selected further up the SubGroupSet tree (or null = all).
+  Result subset(const std::array<int, 3> &con, const std::vector<int> &tasks, const std::vector<int> *base_nodes,
+                const std::function<bool(int)> &in_set, bool has_active, const std::vector<int> &active_nodes,
+                bool all_nodes = false) {
     Result res;
-    const int k = job_topology[job];
+    const int k = con[0];
     if (k == -2) return res;  // requested topology does not exist: no node set
+    if (k < 0 || tasks.empty()) {
+      res.passthrough = true;
+      return res;
+    }
     Topo &tp = topos[k];
     res.topo = k;
-    const int req = job_req[job], pref = job_pref[job];
+    const int req = con[1], pref = con[2];
     // common.go:17-61 lowestCommonDomainID over nodeSet ∩ topology nodes
     int dom = 0;
     {
       int first = -1;
       std::vector<char> all(tp.le - tp.lb, 1);
       std::vector<int> value(tp.le - tp.lb, -1);
-      for (int n : tp.doms[0].nodes) {
+      for (int n : (base_nodes ? *base_nodes : tp.doms[0].nodes)) {
+        if (base_nodes && !tp.node_in[n]) continue;
         if (all_nodes && first >= 0) {  // every topology node is in the set: only "all equal?" per level matters
           if ((int)tp.lcd_all.size() == tp.le - tp.lb) {
             all = tp.lcd_all;
@@ -560,13 +628,19 @@ struct TopologyHost {
   }
 
   // ---- GPU side: select a domain as the row set of the following sweeps; publish / clear the score table ----
-  void select_domain(Seq &seq, const Result &r, int di) const {
-    const Topo &tp = topos[r.topo];
+  void select_domain(Seq &seq, int topo, int di, int slot) const {
+    const Topo &tp = topos[topo];
     const Dom &d = tp.doms[di];
     if (d.level < 0)
-      emit_ext(seq, EXT_SELECT_ROOT, (unsigned int)(tp.lb | (tp.le << 8)), 0);
+      emit_ext(seq, EXT_SELECT_ROOT, (unsigned int)(tp.lb | (tp.le << 8) | (slot << 16)), 0);
     else
-      emit_ext(seq, EXT_SELECT, (unsigned int)(d.level + 1), (unsigned int)d.id);
+      emit_ext(seq, EXT_SELECT, (unsigned int)((d.level + 1) | (slot << 8)), (unsigned int)d.id);
+  }
+  bool node_in_domain(int topo, int di, int n) const {
+    const Topo &tp = topos[topo];
+    const Dom &d = tp.doms[di];
+    if (!tp.node_in[n]) return false;
+    return d.level < 0 || ND(d.level, n) == d.id;
   }
   // The scanners keep the per-domain bucket table between jobs; the host remembers what they hold and sends only the
   // entries that differ (consecutive gangs sort the racks almost identically).  scores_off() before any sweep of a job
@@ -619,11 +693,119 @@ struct TopologyHost {
     gpu_set.clear();
     gpu_pref_level = -1;
   }
-  void clear_scores(Seq &, const Result &) {}  // the table stays for the next job; scores_off() ends it
   void reset_gpu_state() {  // a new k_action launch starts with scoring off and an undefined table
     gpu_pref_level = -1;
     gpu_set.clear();
     if (!gpu_bucket.empty()) std::fill(gpu_bucket.begin(), gpu_bucket.end(), 255);
+  }
+};
+
+// allocate.go:36-83 allocateSubGroupSet / allocateSubGroupSetOnNodes / allocatePodSet over the SubGroupSet tree of a
+// job, shared by the allocate action (live job) and the solver's simulations (views).  Ops supplies the session side:
+//   int  active_alloc(int ps);  void active_nodes(int ps, std::vector<int>&);  bool podset_less(int a, int b);
+//   int  checkpoint();  void rollback(int cp);  bool place(const std::vector<int> &tasks, unsigned int xbits);
+//   bool extra_in_set(int n);  bool all_nodes();
+template <class Ops>
+struct TopoAllocator {
+  TopologyHost &th;
+  Seq &seq;
+  Ops &ops;
+  int job;
+  std::map<int, TopologyHost::Result> tables;  // subGroupNodeScores of this AllocateJob: key = set id or G + podset id
+  std::vector<std::pair<int, int>> stack;      // (topology, domain) selected on the way down; slot = position
+  bool unsupported = false;
+
+  TopoAllocator(TopologyHost &t, Seq &s, Ops &o, int j) : th(t), seq(s), ops(o), job(j) {}
+  void podsets_under(int g, std::vector<int> &out) const {
+    for (int ps : th.set_podsets[g]) out.push_back(ps);
+    for (int c : th.set_children[g]) podsets_under(c, out);
+  }
+  bool in_set(int n) const {
+    for (auto &e : stack)
+      if (!th.node_in_domain(e.first, e.second, n)) return false;
+    return ops.extra_in_set(n);
+  }
+  TopologyHost::Result subset(const std::array<int, 3> &con, const std::vector<int> &under, const std::vector<int> &tasks) {
+    bool has_active = false;
+    std::vector<int> act;
+    for (int ps : under) {
+      if (ops.active_alloc(ps) > 0) has_active = true;
+      ops.active_nodes(ps, act);
+    }
+    const std::vector<int> *base = stack.empty() ? nullptr : &th.topos[stack.back().first].doms[stack.back().second].nodes;
+    return th.subset(con, tasks, base, [&](int n) { return in_set(n); }, has_active, act, stack.empty() && ops.all_nodes());
+  }
+  // runs `body` once per candidate domain until it succeeds
+  template <class Body>
+  bool over_domains(const TopologyHost::Result &r, Body body) {
+    if (!r.ok) return false;
+    if (r.passthrough) return body();
+    if (r.domains.empty()) return false;
+    if ((int)stack.size() >= kDomSlots) {
+      unsupported = true;
+      return false;
+    }
+    for (int di : r.domains) {
+      const int cp = ops.checkpoint();
+      stack.push_back({r.topo, di});
+      th.select_domain(seq, r.topo, di, (int)stack.size() - 1);
+      const bool ok = body();
+      stack.pop_back();
+      if (ok) return true;
+      if (unsupported) return false;
+      ops.rollback(cp);
+    }
+    return false;
+  }
+  bool alloc_set(int g, const std::vector<int> &tasks) {
+    std::vector<int> under;
+    podsets_under(g, under);
+    TopologyHost::Result r = subset(th.set_con[g], under, tasks);
+    if (r.ok && !r.passthrough && r.pref_level >= 0) tables[g] = r;
+    return over_domains(r, [&]() { return set_on_nodes(g, tasks); });
+  }
+  bool set_on_nodes(int g, const std::vector<int> &tasks) {
+    for (int c : th.set_children[g]) {  // orderedSubGroupSets: by name
+      std::vector<int> under, sub;
+      podsets_under(c, under);
+      for (int t : tasks)
+        for (int ps : under)
+          if (th.t_podset[t] == ps) sub.push_back(t);
+      if (!alloc_set(c, sub)) return false;
+    }
+    std::vector<int> own = th.set_podsets[g];  // orderedPodSets
+    std::sort(own.begin(), own.end(), [&](int a, int b) { return ops.podset_less(a, b); });
+    for (int ps : own) {
+      std::vector<int> pt;
+      for (int t : tasks)
+        if (th.t_podset[t] == ps) pt.push_back(t);
+      TopologyHost::Result r = subset(th.ps_con[ps], {ps}, pt);
+      const int key = (int)th.set_parent.size() + ps;
+      if (r.ok && !r.passthrough && r.pref_level >= 0) tables[key] = r;
+      if (!over_domains(r, [&]() { return place_podset(ps, pt); })) return false;
+    }
+    return true;
+  }
+  bool place_podset(int ps, const std::vector<int> &pt) {
+    if (pt.empty()) return true;
+    // getRelevantNodeScores: the PodSet's own table, else the nearest ancestor set's
+    const TopologyHost::Result *tab = nullptr;
+    auto it = tables.find((int)th.set_parent.size() + ps);
+    if (it != tables.end()) tab = &it->second;
+    for (int g = th.ps_set[ps]; !tab && g >= 0; g = th.set_parent[g]) {
+      it = tables.find(g);
+      if (it != tables.end()) tab = &it->second;
+    }
+    if (tab) {
+      if (!th.push_scores(seq, *tab)) {
+        unsupported = true;
+        return false;
+      }
+    } else {
+      th.scores_off(seq);
+    }
+    const unsigned int xbits = stack.empty() ? 0u : (XB_RESTRICT_DOM | ((unsigned int)stack.size() << 8));
+    return ops.place(pt, xbits);
   }
 };
 
