@@ -839,8 +839,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     // host mirror of everything the open-session / prepare kernels produced
     CK(cudaMemcpyAsync(e->stage.host + e->dev_only_begin, e->dsnap.base + e->dev_only_begin, e->dev_only_bytes,
                        cudaMemcpyDeviceToHost, e->stream));
-    if (!e->mirror_valid) e->topo.live = false;  // the incremental per-domain state is rebuilt from the re-read tables
-    if (!e->mirror_valid) {  // a device-sequenced action ran before: re-read the node tables (one GPU)
+    const bool feed_mirror = solver_action || e->topo.any() || e->cfg.shard_count > 1;
+    const bool refresh_mirror = feed_mirror && !e->mirror_valid;
+    if (refresh_mirror) e->topo.live = false;  // the incremental per-domain state is rebuilt from the re-read tables
+    if (refresh_mirror) {  // a device-sequenced action ran before: re-read the node tables (one GPU)
       e->h_tmp.resize((size_t)2 * e->R * e->N);
       if (e->N > 0) {
         CK(cudaMemcpyAsync(e->h_tmp.data(), e->ds.idle, sizeof(double) * (size_t)e->R * e->N, cudaMemcpyDeviceToHost, e->stream));
@@ -880,14 +882,14 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.failed = false;
     hb.rank_to_node = e->rank_to_node_h.data();
     CK(cudaEventSynchronize(e->ev_mirror));
-    if (!e->mirror_valid && !e->h_tmp.empty()) {  // re-read tables -> node-major mirror
+    if (refresh_mirror && !e->h_tmp.empty()) {  // re-read tables -> node-major mirror
       for (int n = 0; n < e->N; n++)
         for (int r = 0; r < e->R; r++) {
           e->h_mirror[(size_t)n * 2 * e->R + r] = e->h_tmp[(size_t)r * e->N + n];
           e->h_mirror[(size_t)n * 2 * e->R + e->R + r] = e->h_tmp[(size_t)(e->R + r) * e->N + n];
         }
     }
-    e->mirror_valid = true;  // from here on the host-sequenced deltas keep it in step
+    if (feed_mirror) e->mirror_valid = true;  // from here on the host-sequenced deltas keep it in step
     // ---- sequencer state on the host ----
     const DevSnap &hs = e->hs;
     const int Q = e->Q, J = e->J;
@@ -944,7 +946,11 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     seq.p = &p;
     seq.delta_base = e->h_delta;
     seq.host_backend = &hb;
-    seq.mirror = e->h_mirror.data();
+    // The mirror is fed by the delta stream whenever something will read it: solver actions, topology, several GPUs.
+    // A plain single-GPU allocate skips that (one cache line per placement) and marks the mirror stale instead; a
+    // later solver action of the cycle re-reads the node tables from the device.
+    seq.mirror = feed_mirror ? e->h_mirror.data() : nullptr;
+    if (!feed_mirror) e->mirror_valid = false;
     e->topo.mirror = e->h_mirror.data();
     e->topo.t_req = hs.t_req;
     e->topo.t_podset = hs.t_podset;
