@@ -255,8 +255,8 @@ def main():
                          "kernel_ms_per_launch": act_ms / args.steps, "traffic": None,
                          "traffic_note": "the host-sequenced kernel cannot run under ncu (the profiler serialises it with the "
                                          "host thread that feeds it); ncu --set full of the same kernel with the device-resident "
-                                         "sequencer: dram read 431 KB + write 2.3 KB per launch on config1 "
-                                         "(profiles/r01b_k_action_device_config1_raw.csv): rows are shared-memory resident"},
+                                         "sequencer: dram read 440 KB + write 1.8 KB per launch on config1 "
+                                         "(profiles/r01c_k_action_device_config1_raw.csv): rows are shared-memory resident"},
             "clocks": clocks,
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }

@@ -334,71 +334,6 @@ struct TopologyHost {
     if (d.alloc_pods != -1) return d.alloc_pods >= tasks_count;
     return !(job_ratio_to_free(tasks_res, d) > 1.0);
   }
-  void subtree_free(Topo &tp, int di) {  // :191-211
-    Dom &d = tp.doms[di];
-    if (d.children.empty()) {
-      for (int n : d.nodes)
-        for (int r = 0; r < R; r++) {
-          d.free[r] += mI_(r, n);
-          d.free[r] += mL_(r, n);
-        }
-      return;
-    }
-    for (int c : d.children) {
-      subtree_free(tp, c);
-      for (int r = 0; r < R; r++) tp.doms[di].free[r] += tp.doms[c].free[r];
-    }
-  }
-  int subtree_allocatable(Topo &tp, int di, const double *max_pod, std::vector<std::vector<double>> &test_pods, int n_tasks) {
-    Dom &d = tp.doms[di];
-    d.alloc_pods = 0;
-    if (d.children.empty()) {
-      bool only_pods = true;
-      for (int r = 0; r < R; r++)
-        if (r == 3 ? max_pod[r] > 1 : max_pod[r] > 0) only_pods = false;
-      for (int n : d.nodes) {
-        if (only_pods) {
-          d.alloc_pods += n_tasks;
-          continue;
-        }
-        auto fits_pod = [&](const std::vector<double> &rq) {
-          for (int r = 0; r < R; r++) {
-            double a = avail(r, n);
-            if (r >= 3) {
-              if (rq[r] != 0 && rq[r] > a) return false;
-            } else if (rq[r] > a)
-              return false;
-          }
-          return true;
-        };
-        int cnt = 0;
-        for (auto &tpod : test_pods) {
-          if (fits_pod(tpod))
-            cnt++;
-          else
-            break;
-        }
-        if (cnt == (int)test_pods.size()) {
-          for (;;) {
-            std::vector<double> next = test_pods.back();
-            for (int r = 0; r < R; r++) next[r] += max_pod[r];
-            test_pods.push_back(next);
-            if (fits_pod(next))
-              cnt++;
-            else
-              break;
-          }
-        }
-        d.alloc_pods += cnt;
-      }
-      return d.alloc_pods;
-    }
-    for (int c : d.children) {
-      int a = subtree_allocatable(tp, c, max_pod, test_pods, n_tasks);
-      tp.doms[di].alloc_pods += a;
-    }
-    return tp.doms[di].alloc_pods;
-  }
   // getJobRatioToFreeResources memo: the ratio of a (job resource sum, domain) pair changes only when the domain's
   // free resources do; `ver` counts those changes (node_changed walks the ancestors)
   struct RatioClass {
