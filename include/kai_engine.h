@@ -106,9 +106,8 @@ typedef struct kai_config {
   double saturation_multiplier; /* proportion `relcaimerSaturationMultiplier` (proportion.go:68-76) */
   int32_t max_consolidation_preemptees; /* -1 = unlimited (options.go:38) */
   int32_t allow_consolidating_reclaim;  /* options.go:121 */
-  /* node sharding across engines of one box.  shard_count = 1
-     for a single GPU.  Shard s owns node rows [s*N/S, (s+1)*N/S) of the
-     snapshot; the exchange buffer is wired with kai_engine_wire_peers(). */
+  /* node sharding across engines of one box.  shard_count = 1 for a single GPU.  Shard s owns the nodes
+     of name rank s, s + S, s + 2S, ... (kai_shard_range); the exchange segment is wired with kai_engine_wire_peers(). */
   int32_t shard_rank;
   int32_t shard_count;
   /* SchedulerParams.UseSchedulingSignatures (cmd/scheduler/app/options/options.go:120; production default true, the
@@ -265,10 +264,13 @@ int kai_engine_create(const kai_config *cfg, kai_engine **out);
    copies the SoA to HBM and computes totals, queue usage and fair shares. */
 int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *snap);
 
-/* replaces: Action.Execute(ssn) for allocate / consolidation / reclaim
-   (actions/allocate/allocate.go:46-77, actions/consolidation/consolidation.go:32-78,
-   actions/reclaim/reclaim.go:47-100).  Session state persists between calls so
-   that `allocate, consolidation, reclaim` can be run in sequence. */
+/* replaces: Action.Execute(ssn) of the default action list
+   (actions/allocate/allocate.go:46-111, actions/consolidation/consolidation.go:32-106,
+   actions/reclaim/reclaim.go:46-119, actions/preempt/preempt.go:46-123,
+   actions/stalegangeviction/stalegangeviction.go:29-95).  Session state persists between calls so that
+   `allocate, consolidation, reclaim, preempt, stalegangeviction` run in sequence on one loaded snapshot.
+   Errors: KAI_ERR_UNSUPPORTED for combinations the engine does not run (victim-selection actions or topology
+   constraints with KAI_SEQUENCER=device); the session is then unchanged and the caller runs the stock action. */
 int kai_engine_run(kai_engine *e, kai_action action, kai_result *out);
 
 /* replaces: fairshare-simulator's SetResourcesShare call
