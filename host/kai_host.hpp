@@ -48,9 +48,22 @@ struct PodInfo {  // pod_info/pod_info.go:70-112
   long long OrderKey = 0;  // position under TaskOrderFn inside the job (priority, then UID)
   std::string NominatedNodeName;
 };
+struct TopologyConstraintInfo {  // api/topology_info: empty Topology = no constraint
+  std::string Topology, RequiredLevel, PreferredLevel;
+};
 struct PodSet {  // podgroup_info/subgroup_info/podset.go
   std::string Name;
   int MinAvailable = 1;
+  TopologyConstraintInfo TopologyConstraint;
+  std::string ParentSet;  // name of the SubGroupSet holding it ("" = the root)
+};
+struct SubGroupSet {  // podgroup_info/subgroup_info/subgroupset.go (flattened: Parent by name, "" = child of the root)
+  std::string Name, Parent;
+  TopologyConstraintInfo TopologyConstraint;
+};
+struct Topology {  // pkg/apis/kai/v1alpha1 Topology: Spec.Levels[].NodeLabel, top level first
+  std::string Name;
+  std::vector<std::string> Levels;
 };
 struct PodGroupInfo {  // podgroup_info/job_info.go:65-103
   std::string UID, Queue;
@@ -58,6 +71,8 @@ struct PodGroupInfo {  // podgroup_info/job_info.go:65-103
   bool Preemptible = true;
   long long CreationTimestamp = 0;
   std::vector<PodSet> PodSets;  // name order
+  TopologyConstraintInfo RootTopologyConstraint;  // constraint of the RootSubGroupSet
+  std::vector<SubGroupSet> SubGroupSets;          // nested sets below the root (none for most jobs)
   std::vector<std::shared_ptr<PodInfo>> Tasks;
   int SchedulingConstraintsSignature = -1;
 };
@@ -65,6 +80,7 @@ struct NodeInfo {  // node_info/node_info.go:68-105
   std::string Name;
   ResourceVector Allocatable, Idle, Releasing;
   bool Ready = true, NotCpuOnly = false;
+  std::map<std::string, std::string> Labels;
   std::map<std::string, std::shared_ptr<PodInfo>> PodInfos;
   // node_info.go:457-493 addTaskResources
   void AddTask(const std::shared_ptr<PodInfo> &t) {
@@ -91,6 +107,7 @@ struct ClusterInfo {  // cluster_info.go:43-64
   std::map<std::string, std::shared_ptr<NodeInfo>> Nodes;
   std::map<std::string, std::shared_ptr<PodGroupInfo>> PodGroupInfos;
   std::map<std::string, std::shared_ptr<QueueInfo>> Queues;
+  std::vector<Topology> Topologies;
 };
 }  // namespace api
 
@@ -204,6 +221,7 @@ struct Packed {
   kai_snapshot c{};
   std::vector<double> alloc, idle, rel, qd, ql, qw, treq;
   std::vector<int32_t> name_rank, qparent, qprio, quid, jqueue, jprio, jorder, jpsb, psmin, pstb, tstatus, tnode, torder, tnom, jsig;
+  std::vector<int32_t> level_begin, node_domain, jsgs, sgs_parent, sgs_rank, sgs_topo, sgs_req, sgs_pref, ps_sgs, ps_topo, ps_req, ps_pref;
   std::vector<uint32_t> nflags, jflags;
   std::vector<int64_t> qcreation;
 };
@@ -307,6 +325,93 @@ inline void packSnapshot(Session &ssn, Packed &p) {
     }
     p.jpsb.push_back((int32_t)p.psmin.size());
   }
+  // Topology CRs -> per-level dense domain ids in DomainID order (plugins/topology/topology_structs.go:76-82)
+  p.level_begin.assign(1, 0);
+  std::vector<std::vector<std::string>> level_labels;
+  for (auto &tp : ci.Topologies) {
+    level_labels.push_back(tp.Levels);
+    p.level_begin.push_back(p.level_begin.back() + (int32_t)tp.Levels.size());
+  }
+  p.node_domain.assign((size_t)p.level_begin.back() * N, -1);
+  for (size_t k = 0; k < ci.Topologies.size(); k++)
+    for (size_t li = 0; li < level_labels[k].size(); li++) {
+      std::vector<std::string> ids(N);
+      std::vector<char> has(N, 1);
+      for (int n = 0; n < N; n++) {
+        std::string id;
+        for (size_t l2 = 0; l2 <= li; l2++) {
+          auto it = ssn.idx_nodes[n]->Labels.find(level_labels[k][l2]);
+          if (it == ssn.idx_nodes[n]->Labels.end()) {
+            has[n] = 0;
+            break;
+          }
+          id += (l2 ? "." : "") + it->second;
+        }
+        ids[n] = id;
+      }
+      std::vector<std::string> uniq;
+      for (int n = 0; n < N; n++)
+        if (has[n]) uniq.push_back(ids[n]);
+      std::sort(uniq.begin(), uniq.end());
+      uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+      for (int n = 0; n < N; n++)
+        if (has[n])
+          p.node_domain[(size_t)(p.level_begin[k] + li) * N + n] =
+              (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), ids[n]) - uniq.begin());
+    }
+  auto constraint = [&](const api::TopologyConstraintInfo &tc, int32_t &topo, int32_t &req, int32_t &pref) {
+    topo = req = pref = -1;
+    if (tc.Topology.empty()) return;
+    topo = -2;
+    for (size_t k = 0; k < ci.Topologies.size(); k++)
+      if (ci.Topologies[k].Name == tc.Topology) topo = (int32_t)k;
+    if (topo < 0) return;
+    auto level = [&](const std::string &name) -> int32_t {
+      if (name.empty()) return -1;
+      for (size_t l = 0; l < level_labels[topo].size(); l++)
+        if (level_labels[topo][l] == name) return (int32_t)l;
+      return -2;
+    };
+    req = level(tc.RequiredLevel);
+    pref = level(tc.PreferredLevel);
+  };
+  // SubGroupSet tree: root first, then the job's nested sets; PodSets point at their set
+  p.jsgs.assign(1, 0);
+  {
+    int ps_index = 0;
+    for (int j = 0; j < J; j++) {
+      auto &job = *ssn.idx_jobs[j];
+      const int root = (int)p.sgs_parent.size();
+      std::map<std::string, int> set_index;
+      auto add_set = [&](const std::string &name, int parent, const api::TopologyConstraintInfo &tc) {
+        int32_t t, r, q;
+        constraint(tc, t, r, q);
+        set_index[name] = (int)p.sgs_parent.size();
+        p.sgs_parent.push_back(parent);
+        p.sgs_topo.push_back(t);
+        p.sgs_req.push_back(r);
+        p.sgs_pref.push_back(q);
+      };
+      add_set("", -1, job.RootTopologyConstraint);
+      for (auto &g : job.SubGroupSets) add_set(g.Name, g.Parent.empty() ? root : set_index.at(g.Parent), g.TopologyConstraint);
+      std::vector<std::string> names;  // SubGroupSetOrderFn falls back to the name; the root is alone at its level
+      for (auto &g : job.SubGroupSets) names.push_back(g.Name);
+      std::sort(names.begin(), names.end());
+      p.sgs_rank.push_back(0);
+      for (auto &g : job.SubGroupSets)
+        p.sgs_rank.push_back((int32_t)(std::lower_bound(names.begin(), names.end(), g.Name) - names.begin()));
+      for (auto &ps : job.PodSets) {
+        int32_t t, r, q;
+        constraint(ps.TopologyConstraint, t, r, q);
+        p.ps_sgs.push_back(ps.ParentSet.empty() ? root : set_index.at(ps.ParentSet));
+        p.ps_topo.push_back(t);
+        p.ps_req.push_back(r);
+        p.ps_pref.push_back(q);
+        ps_index++;
+      }
+      p.jsgs.push_back((int32_t)p.sgs_parent.size());
+    }
+  }
   kai_snapshot &c = p.c;
   c.abi_version = KAI_ABI_VERSION;
   c.n_res = R;
@@ -340,6 +445,20 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   c.task_order_rank = p.torder.data();
   c.task_nominated = p.tnom.data();
   c.job_signature = p.jsig.data();
+  c.n_topologies = (int32_t)ci.Topologies.size();
+  c.topology_level_begin = p.level_begin.data();
+  c.node_domain = p.node_domain.data();
+  c.n_subgroup_sets = (int32_t)p.sgs_parent.size();
+  c.job_sgs_begin = p.jsgs.data();
+  c.sgs_parent = p.sgs_parent.data();
+  c.sgs_name_rank = p.sgs_rank.data();
+  c.sgs_topology = p.sgs_topo.data();
+  c.sgs_required_level = p.sgs_req.data();
+  c.sgs_preferred_level = p.sgs_pref.data();
+  c.podset_sgs = p.ps_sgs.data();
+  c.podset_topology = p.ps_topo.data();
+  c.podset_required_level = p.ps_req.data();
+  c.podset_preferred_level = p.ps_pref.data();
 }
 
 class gpuAction : public Action {

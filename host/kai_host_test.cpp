@@ -7,7 +7,10 @@
 //   queue <uid> <parent|-> <priority> <creation> <d0 d1 d2> <l0 l1 l2> <w0 w1 w2>
 //   node <name> <allocatable x R>
 //   job <uid> <queue> <priority> <preemptible 0/1> <creation>
-//   podset <job> <name> <minAvailable>
+//   podset <job> <name> <minAvailable> [<parent set|-> <topology|-> <required|-> <preferred|->]
+//   set <job> <name> <parent set|-> <topology|-> <required|-> <preferred|->     (nested SubGroupSets, parents first)
+//   rootconstraint <job> <topology> <required|-> <preferred|->
+//   topology <name> <level label> ...        label <node> <key> <value>
 //   task <job> <podset> <uid> <status> <node|-> <order key> <req x R>
 //   actions <name> ...
 // output: one line per task "<uid> <status> <node|->", then "cache <binds> <evictions> <pipelines>".
@@ -68,10 +71,35 @@ int main(int argc, char **argv) {
       j->Preemptible = pre != 0;
       ssn.ClusterInfo.PodGroupInfos[j->UID] = j;
     } else if (kind == "podset") {
-      std::string job;
+      std::string job, parent, topo, req, pref;
       api::PodSet ps;
       ls >> job >> ps.Name >> ps.MinAvailable;
+      if (ls >> parent >> topo >> req >> pref) {
+        ps.ParentSet = parent == "-" ? "" : parent;
+        if (topo != "-") ps.TopologyConstraint = {topo, req == "-" ? "" : req, pref == "-" ? "" : pref};
+      }
       ssn.ClusterInfo.PodGroupInfos[job]->PodSets.push_back(ps);
+    } else if (kind == "set") {
+      std::string job, parent, topo, req, pref;
+      api::SubGroupSet g;
+      ls >> job >> g.Name >> parent >> topo >> req >> pref;
+      g.Parent = parent == "-" ? "" : parent;
+      if (topo != "-") g.TopologyConstraint = {topo, req == "-" ? "" : req, pref == "-" ? "" : pref};
+      ssn.ClusterInfo.PodGroupInfos[job]->SubGroupSets.push_back(g);
+    } else if (kind == "rootconstraint") {
+      std::string job, topo, req, pref;
+      ls >> job >> topo >> req >> pref;
+      ssn.ClusterInfo.PodGroupInfos[job]->RootTopologyConstraint = {topo, req == "-" ? "" : req, pref == "-" ? "" : pref};
+    } else if (kind == "topology") {
+      api::Topology tp;
+      ls >> tp.Name;
+      std::string lv;
+      while (ls >> lv) tp.Levels.push_back(lv);
+      ssn.ClusterInfo.Topologies.push_back(tp);
+    } else if (kind == "label") {
+      std::string node, key, value;
+      ls >> node >> key >> value;
+      ssn.ClusterInfo.Nodes[node]->Labels[key] = value;
     } else if (kind == "task") {
       auto t = std::make_shared<api::PodInfo>();
       std::string node;

@@ -31,7 +31,7 @@ def test_registry_resolves_default_actions():
                        "stalegangeviction registered", "unknown missing"]
 
 
-def write_case(path, snap: abi.Snapshot, meta: dict, actions):
+def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None):
     R, N, Q = snap.n_res, snap.n_nodes, int(snap.queue_parent.shape[0])
     qn = meta["queue_names"]
     with open(path, "w") as f:
@@ -42,11 +42,48 @@ def write_case(path, snap: abi.Snapshot, meta: dict, actions):
             f.write(f"queue {qn[q]} {parent} {int(snap.queue_priority[q])} {int(snap.queue_creation[q])} {vals}\n")
         for n in range(N):
             f.write(f"node {meta['node_names'][n]} " + " ".join(repr(float(x)) for x in snap.node_allocatable[:, n]) + "\n")
+        for tp in (topo or {}).get("Topologies") or []:
+            f.write(f"topology {tp['ObjectMeta']['Name']} " + " ".join(lv["NodeLabel"] for lv in tp["Spec"]["Levels"]) + "\n")
+        for nname, nd in ((topo or {}).get("Nodes") or {}).items():
+            for k_, v_ in (nd.get("Labels") or {}).items():
+                f.write(f"label {nname} {k_} {v_}\n")
         for j, name in enumerate(meta["job_names"]):
             pre = 1 if snap.job_flags[j] & abi.JOB_PREEMPTIBLE else 0
             f.write(f"job {name} {qn[snap.job_queue[j]]} {int(snap.job_priority[j])} {pre} {int(snap.job_order_rank[j])}\n")
+            jdef = next((jd for jd in (topo or {}).get("Jobs", []) if jd["Name"] == name), {})
+            root = jdef.get("RootSubGroupSet") or {}
+            tree = root.get("tree")
+            ps_parent, ps_tc = {}, {}
+
+            def tc_fields(tc):
+                if not tc or not tc.get("Topology"):
+                    return "- - -"
+                return f"{tc['Topology']} {tc.get('RequiredLevel') or '-'} {tc.get('PreferredLevel') or '-'}"
+
+            if root.get("topology_constraint"):
+                f.write(f"rootconstraint {name} {tc_fields(root['topology_constraint'])}\n")
+            if tree:
+                if tree.get("constraint"):
+                    f.write(f"rootconstraint {name} {tc_fields(tree['constraint'])}\n")
+
+                def walk(g, parent):
+                    for p_ in g["podsets"]:
+                        ps_parent[p_["name"]] = "-" if parent is None else g["name"]
+                        ps_tc[p_["name"]] = p_.get("constraint")
+                    for c in g["groups"]:
+                        f.write(f"set {name} {c['name']} {'-' if parent is None else g['name']} {tc_fields(c.get('constraint'))}\n")
+                        walk(c, g)
+
+                walk(tree, None)
+            # PodSets in name order (= snapshot order); the engine-side name keeps that order
+            real_names = sorted(ps_parent) if ps_parent else []
             for ps in range(snap.job_podset_begin[j], snap.job_podset_begin[j + 1]):
-                f.write(f"podset {name} ps{ps - snap.job_podset_begin[j]:03d} {int(snap.podset_min_available[ps])}\n")
+                k = ps - snap.job_podset_begin[j]
+                extra = ""
+                if real_names and len(real_names) == snap.job_podset_begin[j + 1] - snap.job_podset_begin[j]:
+                    rn = real_names[k]
+                    extra = f" {ps_parent[rn]} {tc_fields(ps_tc[rn])}"
+                f.write(f"podset {name} ps{k:03d} {int(snap.podset_min_available[ps])}{extra}\n")
         for j, name in enumerate(meta["job_names"]):
             for ps in range(snap.job_podset_begin[j], snap.job_podset_begin[j + 1]):
                 for t in range(snap.podset_task_begin[ps], snap.podset_task_begin[ps + 1]):
@@ -61,7 +98,8 @@ class _Res:
     pass
 
 
-CASES = (action_cases(["allocate__"], single_action="allocate")[:12] + action_cases(["reclaim__"], single_action="reclaim")[:12]
+CASES = (action_cases(["allocate__allocateTopology"], single_action="allocate") + action_cases(["allocate__allocate_subgroups"], single_action="allocate")[-2:]
+         + action_cases(["allocate__allocate"], single_action="allocate")[:12] + action_cases(["reclaim__"], single_action="reclaim")[:12]
          + action_cases(["consolidation__"], single_action="consolidation")[:8] + action_cases(["preempt__"], single_action="preempt")[:8])
 
 
@@ -72,7 +110,7 @@ def test_reference_tables_through_cpp_shim(cid, case):
     snap, meta = dsl.build_snapshot(case["topology"])
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "case.txt")
-        write_case(path, snap, meta, case["actions"])
+        write_case(path, snap, meta, case["actions"], case["topology"])
         out = subprocess.run([BIN, path], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     lines = [l.split() for l in out.stdout.strip().split("\n")]
