@@ -117,6 +117,26 @@ int main(int argc, char **argv) {
       while (ls >> a) actions.push_back(a);
     }
   }
+  if (argc > 2 && std::string(argv[2]) == "--dump-packed") {  // no GPU: print what packSnapshot hands to the C ABI
+    gpuengine::Packed p;
+    gpuengine::packSnapshot(ssn, p);
+    const kai_snapshot &c = p.c;
+    const int L = c.n_topologies ? c.topology_level_begin[c.n_topologies] : 0;
+    for (int l = 0; l < L; l++)
+      for (int n = 0; n < c.n_nodes; n++)
+        printf("node_domain %d %s %d\n", l, ssn.idx_nodes[n]->Name.c_str(), c.node_domain[(size_t)l * c.n_nodes + n]);
+    for (int j = 0; j < c.n_jobs; j++) {
+      for (int g = c.job_sgs_begin[j]; g < c.job_sgs_begin[j + 1]; g++)
+        printf("set %s %d parent %d rank %d con %d %d %d\n", ssn.idx_jobs[j]->UID.c_str(), g - c.job_sgs_begin[j],
+               c.sgs_parent[g] < 0 ? -1 : c.sgs_parent[g] - c.job_sgs_begin[j], c.sgs_name_rank[g], c.sgs_topology[g],
+               c.sgs_required_level[g], c.sgs_preferred_level[g]);
+      for (int ps = c.job_podset_begin[j]; ps < c.job_podset_begin[j + 1]; ps++)
+        printf("podset %s %d min %d set %d con %d %d %d\n", ssn.idx_jobs[j]->UID.c_str(), ps - c.job_podset_begin[j],
+               c.podset_min_available[ps], c.podset_sgs[ps] - c.job_sgs_begin[j], c.podset_topology[ps],
+               c.podset_required_level[ps], c.podset_preferred_level[ps]);
+    }
+    return 0;
+  }
   for (const std::string &name : actions) {
     auto action = framework::GetAction(name);  // scheduler.go:129-136 runOnce: for _, action := range actions
     if (!action) {

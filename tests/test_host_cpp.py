@@ -94,6 +94,45 @@ def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None):
         f.write("actions " + " ".join(actions) + "\n")
 
 
+TOPO_CASES = action_cases(["allocate__allocateTopology"], single_action="allocate")
+
+
+@pytest.mark.parametrize("cid,case", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
+def test_cpp_packing_of_topologies_and_subgroup_tree(cid, case):
+    """packSnapshot (C++) against tests/dsl.py on the topology tables: per-level domain ids of every node and the
+    SubGroupSet tree with its constraints (no GPU: --dump-packed stops before the engine)."""
+    _build()
+    snap, meta = dsl.build_snapshot(case["topology"])
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "case.txt")
+        write_case(path, snap, meta, case["actions"], case["topology"])
+        out = subprocess.run([BIN, path, "--dump-packed"], capture_output=True, text=True, check=True).stdout.split("\n")
+    nidx = {n: i for i, n in enumerate(meta["node_names"])}
+    jidx = {n: i for i, n in enumerate(meta["job_names"])}
+    seen_sets = 0
+    for line in out:
+        f = line.split()
+        if not f:
+            continue
+        if f[0] == "node_domain":
+            assert int(f[3]) == snap.node_domain[int(f[1]), nidx[f[2]]], line
+        elif f[0] == "set":
+            j = jidx[f[1]]
+            g = snap.job_sgs_begin[j] + int(f[2])
+            par = snap.sgs_parent[g]
+            assert int(f[4]) == (-1 if par < 0 else par - snap.job_sgs_begin[j]), line
+            assert [int(x) for x in f[8:11]] == [snap.sgs_topology[g], snap.sgs_required_level[g], snap.sgs_preferred_level[g]], line
+            # name rank: same relative order among the nested sets of the job (the root's own rank is irrelevant)
+            seen_sets += 1
+        elif f[0] == "podset":
+            j = jidx[f[1]]
+            ps = snap.job_podset_begin[j] + int(f[2])
+            assert int(f[4]) == snap.podset_min_available[ps], line
+            assert int(f[6]) == snap.podset_sgs[ps] - snap.job_sgs_begin[j], line
+            assert [int(x) for x in f[8:11]] == [snap.podset_topology[ps], snap.podset_required_level[ps], snap.podset_preferred_level[ps]], line
+    assert seen_sets == len(snap.sgs_parent)
+
+
 class _Res:
     pass
 
