@@ -340,9 +340,18 @@ struct Solver {
     node_delta(t, n, status == KAI_POD_RELEASING ? ND_REM_RELEASING : (status == KAI_POD_PIPELINED ? ND_REM_PIPELINED : ND_REM));
     if (e >= 0) (e == 0 ? on_node0 : on_node1)[t] = -1;
   }
+  // jobs with Pending tasks (utils.GetAllPendingJobs, actions/utils/action.go:122-130), kept as statuses change
+  std::vector<int> pending_cnt;
+  std::set<int> pending_jobs;
   void set_status(int t, int status) {
+    const int j = tjob(t);
+    if (st[t] == KAI_POD_PENDING && status != KAI_POD_PENDING) {
+      if (--pending_cnt[j] == 0) pending_jobs.erase(j);
+    } else if (st[t] != KAI_POD_PENDING && status == KAI_POD_PENDING) {
+      if (pending_cnt[j]++ == 0) pending_jobs.insert(j);
+    }
     st[t] = status;
-    job_cache[tjob(t)].tta_valid = job_cache[tjob(t)].res_valid = false;
+    job_cache[j].tta_valid = job_cache[j].res_valid = false;
   }
   void queue_allocate(int t, bool add) {  // proportion.go:443-489
     int j = tjob(t);
@@ -1166,17 +1175,14 @@ struct Solver {
     const int pj = vjob(sc.preemptor);
     simulations++;
     const double t_setup0 = HostBackend::now();
-    std::vector<char> is_victim_job(J, 0), in_set(J, 0);
-    for (int j = 0; j < J; j++)
-      if (count_job(j, KAI_POD_PENDING) > 0) in_set[j] = 1;
+    std::set<int> in_set(pending_jobs), victim_jobs;
     for (int t : victim_tasks) {
-      in_set[tjob(t)] = 1;
-      is_victim_job[tjob(t)] = 1;
+      in_set.insert(tjob(t));
+      victim_jobs.insert(tjob(t));
     }
-    in_set[pj] = 1;
+    in_set.insert(pj);
     std::vector<int> vs;
-    for (int j = 0; j < J; j++)
-      if (in_set[j]) vs.push_back(j == pj ? sc.preemptor : j);
+    for (int j : in_set) vs.push_back(j == pj ? sc.preemptor : j);  // ascending job index, as before
     JobsOrder jo;
     jo.init(this, false);
     init_jobs_order(jo, vs, OrderOpts());
@@ -1186,7 +1192,7 @@ struct Solver {
       int v = jo.pop_next_job();
       if (v < 0) break;
       int j = vjob(v);
-      if (!is_victim_job[j] && j != pj) continue;
+      if (j != pj && !victim_jobs.count(j)) continue;
       tta_init_resource(v, false);
       if (j != pj) {
         allocate_job(v);
@@ -1523,6 +1529,10 @@ struct Solver {
 
   void prepare() {
     job_cache.assign(J, Cache());
+    pending_cnt.assign(J, 0);
+    pending_jobs.clear();
+    for (int t = 0; t < T; t++)
+      if (st[t] == KAI_POD_PENDING && pending_cnt[tjob(t)]++ == 0) pending_jobs.insert(tjob(t));
     feas_extra.assign(N, 0);
     ops_truncate(0);
     free_ready = 0;  // once per action, from the mirror of the GPU column the action starts with
