@@ -75,6 +75,7 @@ struct PodGroupInfo {  // podgroup_info/job_info.go:65-103
   std::vector<SubGroupSet> SubGroupSets;          // nested sets below the root (none for most jobs)
   std::vector<std::shared_ptr<PodInfo>> Tasks;
   int SchedulingConstraintsSignature = -1;
+  double LastStartTimestamp = -1;  // seconds on the session clock; <= 0 = nil (job_info.go:185-193)
 };
 struct NodeInfo {  // node_info/node_info.go:68-105
   std::string Name;
@@ -102,6 +103,7 @@ struct QueueInfo {  // queue_info/queue_info.go:32-43; quota / limit / over-quot
   int Priority = 100;
   long long CreationTimestamp = 0;
   double Deserved[3] = {-1, -1, -1}, Limit[3] = {-1, -1, -1}, OverQuotaWeight[3] = {1, 1, 1};
+  double PreemptMinRuntime = -1, ReclaimMinRuntime = -1;  // seconds; < 0 = nil (*metav1.Duration)
 };
 struct ClusterInfo {  // cluster_info.go:43-64
   std::map<std::string, std::shared_ptr<NodeInfo>> Nodes;
@@ -144,6 +146,7 @@ class Statement {  // framework/statement.go
 class Session {  // framework/session.go:43-98
  public:
   api::ClusterInfo ClusterInfo;
+  double Now = 0;  // the instant min-runtime windows are measured against (time.Now() in plugins/minruntime)
   Cache cache;
   kai_config Config{};
   Session() {
@@ -224,6 +227,7 @@ struct Packed {
   std::vector<int32_t> level_begin, node_domain, jsgs, sgs_parent, sgs_rank, sgs_topo, sgs_req, sgs_pref, ps_sgs, ps_topo, ps_req, ps_pref;
   std::vector<uint32_t> nflags, jflags;
   std::vector<int64_t> qcreation;
+  std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start;
 };
 template <class T, class K>
 std::vector<int32_t> rank_of(const std::vector<T> &items, K key) {  // rank of every item under the key's `<`
@@ -238,6 +242,9 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   ssn.idx_nodes.clear();
   ssn.idx_jobs.clear();
   ssn.idx_tasks.clear();
+  p.q_preempt_mrt.clear();
+  p.q_reclaim_mrt.clear();
+  p.j_last_start.clear();
   ssn.task_job.clear();
   for (auto &kv : ci.Nodes) ssn.idx_nodes.push_back(kv.second);  // std::map: already in byte-wise name order
   const int N = (int)ssn.idx_nodes.size();
@@ -279,6 +286,8 @@ inline void packSnapshot(Session &ssn, Packed &p) {
     p.qparent[q] = qi.ParentQueue.empty() ? -1 : queue_index.at(qi.ParentQueue);
     p.qprio[q] = qi.Priority;
     p.qcreation[q] = qi.CreationTimestamp;
+    p.q_preempt_mrt.push_back(qi.PreemptMinRuntime);
+    p.q_reclaim_mrt.push_back(qi.ReclaimMinRuntime);
     for (int r = 0; r < 3; r++) {
       p.qd[(size_t)r * Q + q] = qi.Deserved[r];
       p.ql[(size_t)r * Q + q] = qi.Limit[r];
@@ -304,6 +313,7 @@ inline void packSnapshot(Session &ssn, Packed &p) {
     p.jprio[j] = job.Priority;
     p.jflags[j] = job.Preemptible ? KAI_JOB_PREEMPTIBLE : 0;
     p.jsig[j] = job.SchedulingConstraintsSignature;
+    p.j_last_start.push_back(job.LastStartTimestamp);
     auto order = rank_of(job.Tasks, [](const std::shared_ptr<api::PodInfo> &t) { return std::make_pair(t->OrderKey, t->UID); });
     for (auto &ps : job.PodSets) {
       p.psmin.push_back(ps.MinAvailable);
@@ -445,6 +455,10 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   c.task_order_rank = p.torder.data();
   c.task_nominated = p.tnom.data();
   c.job_signature = p.jsig.data();
+  c.now_s = ssn.Now;
+  c.queue_preempt_min_runtime_s = p.q_preempt_mrt.data();
+  c.queue_reclaim_min_runtime_s = p.q_reclaim_mrt.data();
+  c.job_last_start_s = p.j_last_start.data();
   c.n_topologies = (int32_t)ci.Topologies.size();
   c.topology_level_begin = p.level_begin.data();
   c.node_domain = p.node_domain.data();

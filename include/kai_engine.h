@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KAI_ABI_VERSION 4
+#define KAI_ABI_VERSION 5
 #define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
 #define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
 #define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
@@ -94,6 +94,9 @@ typedef enum kai_action {
   KAI_ACTION_STALEGANGEVICTION = 5  /* actions/stalegangeviction/stalegangeviction.go:29-95 */
 } kai_action;
 
+/* minruntime `reclaimResolveMethod` (plugins/minruntime/minruntime.go:27-29; resolver.go:83-187) */
+enum { KAI_RESOLVE_LCA = 0, KAI_RESOLVE_QUEUE = 1 };
+
 /* node placement strategy. reference: plugins/nodeplacement/nodeplacement.go:53-73 */
 enum { KAI_PLACEMENT_BINPACK = 0, KAI_PLACEMENT_SPREAD = 1 };
 
@@ -118,6 +121,11 @@ typedef struct kai_config {
      the cycle that finds them stale (the reference's tests); > 0 needs per-job staleness timestamps, which the
      snapshot does not carry: treated as "not yet". */
   int32_t staleness_grace_period_s;
+  /* minruntime plugin arguments (plugins/minruntime/minruntime.go:24-78): `defaultReclaimMinRuntime`,
+     `defaultPreemptMinRuntime` in seconds (negative or unparsable = 0) and `reclaimResolveMethod`. */
+  int32_t reclaim_resolve_method; /* KAI_RESOLVE_LCA (default) or KAI_RESOLVE_QUEUE */
+  double default_reclaim_min_runtime_s;
+  double default_preempt_min_runtime_s;
 } kai_config;
 
 /*
@@ -215,6 +223,16 @@ typedef struct kai_snapshot {
   const int32_t *podset_topology;        /* [S] PodSet's own constraint, -1 none; NULL = none */
   const int32_t *podset_required_level;  /* [S] */
   const int32_t *podset_preferred_level; /* [S] */
+
+  /* ---- min-runtime protection of victims (plugins/minruntime): a non-elastic job whose LastStartTimestamp + the
+         resolved min-runtime lies after `now_s` is not offered as a reclaim / preempt victim; an elastic one may only
+         shrink to its minAvailable.  Durations in seconds, < 0 = not set on that queue (QueueSpec.PreemptMinRuntime /
+         ReclaimMinRuntime are pointers, pkg/apis/scheduling/v2/queue_types.go:40-46); job_last_start_s <= 0 = never
+         started (PodGroupInfo.LastStartTimestamp nil or zero).  NULL arrays = nothing set. ---- */
+  double now_s;                              /* the reference reads time.Now() at every check; one instant per cycle here */
+  const double *queue_preempt_min_runtime_s; /* [Q] */
+  const double *queue_reclaim_min_runtime_s; /* [Q] */
+  const double *job_last_start_s;            /* [J] seconds on the clock of now_s */
 } kai_snapshot;
 
 /* One entry per job popped by an action, in visiting order. */

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-KAI_ABI_VERSION = 4
+KAI_ABI_VERSION = 5
 KAI_MAX_RES = 8
 KAI_QRES = 3
 RES_CPU, RES_MEM, RES_GPU, RES_PODS = 0, 1, 2, 3
@@ -37,6 +37,7 @@ ACTION_STALEGANGEVICTION = 5
 ACTIONS = {"allocate": ACTION_ALLOCATE, "consolidation": ACTION_CONSOLIDATION, "reclaim": ACTION_RECLAIM,
            "preempt": ACTION_PREEMPT, "stalegangeviction": ACTION_STALEGANGEVICTION}
 PLACEMENT_BINPACK, PLACEMENT_SPREAD = 0, 1
+RESOLVE_LCA, RESOLVE_QUEUE = 0, 1
 PEER_HANDLE_BYTES = 64
 
 _dp = C.POINTER(C.c_double)
@@ -59,6 +60,9 @@ class KaiConfig(C.Structure):
         ("shard_count", C.c_int32),
         ("use_scheduling_signatures", C.c_int32),
         ("staleness_grace_period_s", C.c_int32),
+        ("reclaim_resolve_method", C.c_int32),
+        ("default_reclaim_min_runtime_s", C.c_double),
+        ("default_preempt_min_runtime_s", C.c_double),
     ]
 
 
@@ -84,6 +88,8 @@ class KaiSnapshot(C.Structure):
         ("job_sgs_begin", _ip), ("sgs_parent", _ip), ("sgs_name_rank", _ip), ("sgs_topology", _ip),
         ("sgs_required_level", _ip), ("sgs_preferred_level", _ip), ("podset_sgs", _ip), ("podset_topology", _ip),
         ("podset_required_level", _ip), ("podset_preferred_level", _ip),
+        ("now_s", C.c_double), ("queue_preempt_min_runtime_s", _dp), ("queue_reclaim_min_runtime_s", _dp),
+        ("job_last_start_s", _dp),
     ]
 
 
@@ -113,10 +119,13 @@ class KaiStats(C.Structure):
 def make_config(device: int = 0, gpu_placement: int = PLACEMENT_BINPACK, cpu_placement: int = PLACEMENT_BINPACK,
                 k_value: float = 1.0, saturation_multiplier: float = 1.0, max_consolidation_preemptees: int = -1,
                 allow_consolidating_reclaim: bool = True, shard_rank: int = 0, shard_count: int = 1,
-                use_scheduling_signatures: bool = False, staleness_grace_period_s: int = 0) -> KaiConfig:
+                use_scheduling_signatures: bool = False, staleness_grace_period_s: int = 0,
+                reclaim_resolve_method: int = 0, default_reclaim_min_runtime_s: float = 0.0,
+                default_preempt_min_runtime_s: float = 0.0) -> KaiConfig:
     return KaiConfig(KAI_ABI_VERSION, device, gpu_placement, cpu_placement, k_value, saturation_multiplier,
                      max_consolidation_preemptees, int(allow_consolidating_reclaim), shard_rank, shard_count,
-                     int(use_scheduling_signatures), staleness_grace_period_s)
+                     int(use_scheduling_signatures), staleness_grace_period_s, reclaim_resolve_method,
+                     max(0.0, default_reclaim_min_runtime_s), max(0.0, default_preempt_min_runtime_s))
 
 
 def _arr(a, dtype):
@@ -173,6 +182,10 @@ class Snapshot:
     podset_topology: np.ndarray | None = None
     podset_required_level: np.ndarray | None = None
     podset_preferred_level: np.ndarray | None = None
+    now_s: float = 0.0                                   # min-runtime protection (plugins/minruntime)
+    queue_preempt_min_runtime_s: np.ndarray | None = None  # [Q] f64 seconds, < 0 = not set
+    queue_reclaim_min_runtime_s: np.ndarray | None = None
+    job_last_start_s: np.ndarray | None = None             # [J] f64 seconds, <= 0 = never started
     names: dict = field(default_factory=dict)  # optional: node/job/task/queue names for reporting
     _keep: list = field(default_factory=list, repr=False)
 
@@ -266,6 +279,9 @@ class Snapshot:
         for name in ("job_sgs_begin", "sgs_parent", "sgs_name_rank", "sgs_topology", "sgs_required_level", "sgs_preferred_level",
                      "podset_sgs", "podset_topology", "podset_required_level", "podset_preferred_level"):
             setattr(s, name, p(getattr(self, name), np.int32, _ip))
+        s.now_s = float(self.now_s)
+        for name in ("queue_preempt_min_runtime_s", "queue_reclaim_min_runtime_s", "job_last_start_s"):
+            setattr(s, name, p(getattr(self, name), np.float64, _dp))
         self._keep = keep
         return s
 

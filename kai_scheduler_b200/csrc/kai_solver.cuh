@@ -1125,6 +1125,68 @@ struct Solver {
     }
     return true;
   }
+  // ---------------- plugins/minruntime ----------------
+  const double *q_preempt_mrt = nullptr, *q_reclaim_mrt = nullptr, *j_last_start = nullptr;  // see kai_engine.h
+  double now_s = 0;
+  double preempt_min_runtime(int q) const {  // resolver.go:46-67
+    for (int c = q; c >= 0; c = s.q_parent[c])
+      if (q_preempt_mrt && q_preempt_mrt[c] >= 0) return q_preempt_mrt[c];
+    return cfg.default_preempt_min_runtime_s;
+  }
+  double reclaim_min_runtime(int pq, int vq) const {  // resolver.go:69-187
+    if (pq < 0 || vq < 0) return cfg.default_reclaim_min_runtime_s;
+    auto set = [&](int q) { return q_reclaim_mrt && q_reclaim_mrt[q] >= 0; };
+    if (cfg.reclaim_resolve_method == KAI_RESOLVE_QUEUE) {
+      for (int c = vq; c >= 0; c = s.q_parent[c])
+        if (set(c)) return q_reclaim_mrt[c];
+      return cfg.default_reclaim_min_runtime_s;
+    }
+    std::vector<int> pp, vp;  // leaf first
+    for (int c = pq; c >= 0; c = s.q_parent[c]) pp.push_back(c);
+    for (int c = vq; c >= 0; c = s.q_parent[c]) vp.push_back(c);
+    const int np = (int)pp.size(), nv = (int)vp.size();
+    if (pp[np - 1] != vp[nv - 1])  // different top-level queues: the victim's top-level value
+      return set(vp[nv - 1]) ? q_reclaim_mrt[vp[nv - 1]] : cfg.default_reclaim_min_runtime_s;
+    int lca = 0;  // depth (root = 0) of the last common queue, then one step down the victim's path if there is one
+    for (int i = 0; i < (np < nv ? np : nv); i++) {
+      if (pp[np - 1 - i] != vp[nv - 1 - i]) break;
+      lca = i;
+    }
+    if (lca + 1 < nv) lca++;
+    for (int i = lca; i >= 0; i--)
+      if (set(vp[nv - 1 - i])) return q_reclaim_mrt[vp[nv - 1 - i]];
+    return cfg.default_reclaim_min_runtime_s;
+  }
+  bool job_elastic(int j) const {  // job_info.go:408-415
+    for (int ps = ps_begin(j); ps < ps_end(j); ps++)
+      if (s.ps_min[ps] < pst_end(ps) - pst_begin(ps)) return true;
+    return false;
+  }
+  bool minruntime_protected(bool reclaim, int pending_job, int victim) const {  // minruntime.go:147-192
+    if (!j_last_start || !(j_last_start[victim] > 0)) return false;
+    double mrt = reclaim ? reclaim_min_runtime(s.j_queue[pending_job], s.j_queue[victim]) : preempt_min_runtime(s.j_queue[victim]);
+    return now_s < j_last_start[victim] + mrt;
+  }
+  bool minruntime_filter(bool reclaim, int pending_job, int victim) const {  // :93-105
+    return job_elastic(victim) || !minruntime_protected(reclaim, pending_job, victim);
+  }
+  bool minruntime_validator(const Scenario &sc, bool reclaim) const {  // :107-145,206-229
+    if (!j_last_start) return true;
+    int pj = vjob(sc.preemptor);
+    for (const auto &kv : sc.victims) {
+      int vj = kv.first;
+      if (!job_elastic(vj) || !minruntime_protected(reclaim, pj, vj)) continue;
+      for (int ps = ps_begin(vj); ps < ps_end(vj); ps++) {
+        int victims = 0;
+        for (int t : kv.second)
+          if (s.t_podset[t] == ps) victims++;
+        if (!victims) continue;
+        if (s.ps_min[ps] > count_ps(ps, kActiveUsed) - victims) return false;
+      }
+    }
+    return true;
+  }
+
   bool reclaim_validator(const Scenario &sc) {  // proportion.go:143-240
     int rj = vjob(sc.preemptor);
     const double *rq = tta_init_resource(sc.preemptor, false);
@@ -1219,8 +1281,10 @@ struct Solver {
         pipelined.push_back(t);
     }
     res.has = true;
-    // preempt: ssn.PreemptScenarioValidator is minruntime only (not modelled) => always valid
-    bool valid = solver_kind == 0 ? reclaim_validator(sc) : (solver_kind == 1 ? consolidation_validator(sc) : true);
+    // every registered validator must accept (session_plugins.go:135-164): reclaim = proportion + minruntime,
+    // preempt = minruntime, consolidation = its own closure
+    bool valid = solver_kind == 0 ? (reclaim_validator(sc) && minruntime_validator(sc, true))
+                                  : (solver_kind == 1 ? consolidation_validator(sc) : minruntime_validator(sc, false));
     if (!valid) {
       stmt_discard();
       return res;
@@ -1321,13 +1385,14 @@ struct Solver {
       op.filter_non_preemptible = true;
       op.filter_non_active_allocated = true;
       for (int j = 0; j < J; j++)
-        if (s.j_queue[j] != s.j_queue[pending_job]) vs.push_back(j);
+        if (s.j_queue[j] != s.j_queue[pending_job] && minruntime_filter(true, pending_job, j)) vs.push_back(j);
     } else if (solver_kind == 2) {  // preempt.go:125-161 + utils/action.go:20-52
       for (int j = 0; j < J; j++) {
         if (count_job(j, kAlive) == 0) continue;
         if (!preemptible(j) || s.j_priority[j] >= s.j_priority[pending_job]) continue;
         if (s.j_queue[j] != s.j_queue[pending_job] || j == pending_job) continue;
         if (count_job(j, kActiveAllocated) == 0) continue;
+        if (!minruntime_filter(false, pending_job, j)) continue;
         vs.push_back(j);
       }
     } else {  // consolidation.go:119-157 + utils/action.go:20-52

@@ -39,6 +39,7 @@ SUBGROUP_LABEL = "kai.scheduler/subgroup-name"  # constants.go:56
 GPU_COUNT_LABEL = "nvidia.com/gpu.count"  # constants.go:55
 TASK_ORDER_LABEL = "kai.scheduler/task-priority"
 DEFAULT_SUBGROUP = "default-sub-group"
+LAST_START_ANNOTATION = "kai.scheduler/last-start-timestamp"  # constants.go:43
 DEFAULT_QUEUE_PRIORITY = 100  # constants.go:13
 DEFAULT_PODGROUP_PRIORITY = 50  # constants.go:14
 NON_PREEMPTIBLE_THRESHOLD = 100  # pkg/common/podgroup/preemptible.go:10
@@ -105,6 +106,47 @@ def _epoch(ts) -> int:
     if isinstance(ts, (int, float)):
         return int(ts)
     return int(datetime.fromisoformat(str(ts).replace("Z", "+00:00")).timestamp())
+
+
+_DUR_UNITS = {"ns": 1e-9, "us": 1e-6, "µs": 1e-6, "μs": 1e-6, "ms": 1e-3, "s": 1.0, "m": 60.0, "h": 3600.0, "d": 86400.0,
+              "w": 604800.0}
+
+
+def parse_duration(text) -> float:
+    """Go duration string ("1h30m", "1.5s", "2d4h30m", "5w4d12h" — the plugin arguments also take days and weeks,
+    plugins/minruntime/minruntime_test.go:343-351) -> seconds.  A number is taken as nanoseconds (time.Duration's JSON
+    form).  Raises ValueError on anything else ("5", "1h2", "1h-30m")."""
+    if isinstance(text, (int, float)):
+        return float(text) * 1e-9
+    s = str(text).strip()
+    if s in ("0", "+0", "-0"):
+        return 0.0
+    sign = 1.0
+    if s[:1] in "+-":
+        sign = -1.0 if s[0] == "-" else 1.0
+        s = s[1:]
+    if not s:
+        raise ValueError(f"bad duration {text!r}")
+    total, i = 0.0, 0
+    while i < len(s):
+        j = i
+        while j < len(s) and (s[j].isdigit() or s[j] == "."):
+            j += 1
+        if j == i or s[i:j] == ".":
+            raise ValueError(f"bad duration {text!r}")
+        k = j
+        while k < len(s) and not (s[k].isdigit() or s[k] == "."):
+            k += 1
+        unit = s[j:k]
+        if unit not in _DUR_UNITS:
+            raise ValueError(f"bad duration unit in {text!r}")
+        total += float(s[i:j]) * _DUR_UNITS[unit]
+        i = k
+    return sign * total
+
+
+def format_duration(sec: float) -> str:
+    return f"{sec:g}s"
 
 
 def _rfc3339(sec: int) -> str:
@@ -365,6 +407,16 @@ def _parse_config(doc: dict):
                     kw["gpu_placement"] = place[args["gpu"]]
                 if "cpu" in args:
                     kw["cpu_placement"] = place[args["cpu"]]
+            elif p.get("name") == "minruntime":  # plugins/minruntime/minruntime.go:43-78
+                for key, field in (("defaultReclaimMinRuntime", "default_reclaim_min_runtime_s"),
+                                   ("defaultPreemptMinRuntime", "default_preempt_min_runtime_s")):
+                    if key in args:
+                        try:
+                            kw[field] = max(0.0, parse_duration(args[key]))  # unparsable or negative -> 0
+                        except ValueError:
+                            kw[field] = 0.0
+                if args.get("reclaimResolveMethod") == "queue":  # anything else falls back to lca
+                    kw["reclaim_resolve_method"] = abi.RESOLVE_QUEUE
             elif p.get("name") == "proportion":  # plugins/proportion/proportion.go:68-85
                 if "kValue" in args:
                     kw["k_value"] = float(args["kValue"])
@@ -380,12 +432,14 @@ def _parse_config(doc: dict):
 
 
 # ---------------------------------------------------------------- pack
-def pack_cluster(doc: dict, strict: bool = True):
+def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     """ClusterInfo.Snapshot() over the raw objects of a snapshot.json document.
 
     Returns (snapshot, meta, config_kwargs, actions).  meta: node_names, queue_names, job_names, task_names (pod
     names), task_uids, task_job, resource_names, ignored.  Index order: nodes and queues by name, jobs by PodGroup
     name, tasks by PodSet then (creation, UID) — any order is valid for the engine, this one is reproducible.
+    `now` (seconds since the epoch) is the instant min-runtime windows are measured against: the document's own
+    `capturedAt` extension if present, else the argument, else the current time (the reference reads time.Now()).
     """
     raw = doc.get("rawObjects") or {}
     params = doc.get("schedulerParams") or {}
@@ -491,11 +545,15 @@ def pack_cluster(doc: dict, strict: bool = True):
     q_prio = np.zeros(Q, dtype=np.int32)
     q_created = np.zeros(Q, dtype=np.int64)
     q_des, q_lim, q_oqw = np.zeros((3, Q)), np.zeros((3, Q)), np.zeros((3, Q))
+    q_pre_mrt, q_rec_mrt = np.full(Q, -1.0), np.full(Q, -1.0)
     for i, name in enumerate(queue_names):
         spec = qrows[name]
         if spec.get("parentQueue"):
             q_parent[i] = qindex[spec["parentQueue"]]
         q_prio[i] = spec["priority"] if spec.get("priority") is not None else DEFAULT_QUEUE_PRIORITY
+        for arr, key in ((q_pre_mrt, "preemptMinRuntime"), (q_rec_mrt, "reclaimMinRuntime")):
+            if spec.get(key) is not None:  # *metav1.Duration (queue_types.go:40-46)
+                arr[i] = parse_duration(spec[key])
         q_created[i] = spec["_created"]
         res = spec.get("resources") or {}
         for r, key, scale in ((0, "cpu", 1.0), (1, "memory", MEGA), (2, "gpu", 1.0)):
@@ -550,7 +608,7 @@ def pack_cluster(doc: dict, strict: bool = True):
         if row["group"]:
             by_group.setdefault(row["group"], []).append(row)
     pgs = sorted(raw.get("podGroups") or [], key=lambda g: g["metadata"]["name"].encode())
-    job_names, job_queue, job_prio, job_flags, job_created = [], [], [], [], []
+    job_names, job_queue, job_prio, job_flags, job_created, job_last_start = [], [], [], [], [], []
     job_podset_begin, podset_min, podset_task_begin = [0], [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_uids, t_job, t_cons, t_nominated = [], [], [], [], [], [], [], [], []
     job_sgs_begin, sgs_parent, sgs_names, sgs_con, ps_sgs, ps_con = [0], [], [], [], [], []
@@ -571,6 +629,11 @@ def pack_cluster(doc: dict, strict: bool = True):
         job_prio.append(prio)
         job_flags.append(abi.JOB_PREEMPTIBLE if preemptible else 0)
         job_created.append(_epoch(pg["metadata"].get("creationTimestamp")))
+        started = (pg["metadata"].get("annotations") or {}).get(LAST_START_ANNOTATION)
+        try:  # job_info.go:185-193: an unparsable timestamp is ignored
+            job_last_start.append(float(_epoch(started)) if started else -1.0)
+        except ValueError:
+            job_last_start.append(-1.0)
 
         # SubGroup tree: entries with children are sets, the others PodSets
         subgroups = spec.get("subGroups") or []
@@ -724,6 +787,12 @@ def pack_cluster(doc: dict, strict: bool = True):
                   podset_topology=np.array([c[0] for c in ps_con], dtype=np.int32).reshape(-1),
                   podset_required_level=np.array([c[1] for c in ps_con], dtype=np.int32).reshape(-1),
                   podset_preferred_level=np.array([c[2] for c in ps_con], dtype=np.int32).reshape(-1))
+    if (q_pre_mrt >= 0).any() or (q_rec_mrt >= 0).any() or any(v > 0 for v in job_last_start):
+        import time
+        captured = doc.get("capturedAt")
+        kw.update(queue_preempt_min_runtime_s=q_pre_mrt, queue_reclaim_min_runtime_s=q_rec_mrt,
+                  job_last_start_s=np.array(job_last_start, dtype=np.float64).reshape(J),
+                  now_s=float(_epoch(captured)) if captured else (float(now) if now is not None else time.time()))
     usage = _queue_usage(doc, queue_names)
     if usage is not None:
         kw["queue_usage"] = usage
@@ -824,6 +893,9 @@ def dump_cluster(snap: "abi.Snapshot", actions=("allocate",), config: dict | Non
                         "limit": l / scale if (scale != 1.0 and l >= 0) else l,
                         "overQuotaWeight": float(snap.queue_oqw[r, q])}
         spec = {"resources": res, "priority": int(snap.queue_priority[q])}
+        for arr, key in ((snap.queue_preempt_min_runtime_s, "preemptMinRuntime"), (snap.queue_reclaim_min_runtime_s, "reclaimMinRuntime")):
+            if arr is not None and arr[q] >= 0:
+                spec[key] = format_duration(float(arr[q]))
         if snap.queue_parent[q] >= 0:
             spec["parentQueue"] = queue_names[int(snap.queue_parent[q])]
         queues.append({"metadata": {"name": queue_names[q], "creationTimestamp": _rfc3339(_BASE_EPOCH + int(snap.queue_creation[q]))},
@@ -893,9 +965,13 @@ def dump_cluster(snap: "abi.Snapshot", actions=("allocate",), config: dict | Non
                 if sg["name"].startswith("set-") and sg["name"] not in have_children:
                     raise UnsupportedSnapshot("empty SubGroupSet")
             spec["subGroups"] = subgroups
-        pod_groups.append({"metadata": {"name": job_names[j], "namespace": "default",
-                                        "creationTimestamp": _rfc3339(_BASE_EPOCH + int(snap.job_order_rank[j]))},
-                           "spec": spec})
+        pg_md = {"name": job_names[j], "namespace": "default",
+                 "creationTimestamp": _rfc3339(_BASE_EPOCH + int(snap.job_order_rank[j]))}
+        if snap.job_last_start_s is not None and snap.job_last_start_s[j] > 0:
+            if snap.job_last_start_s[j] != int(snap.job_last_start_s[j]):
+                raise UnsupportedSnapshot("sub-second last-start timestamps (RFC 3339 annotation)")
+            pg_md["annotations"] = {LAST_START_ANNOTATION: _rfc3339(int(snap.job_last_start_s[j]))}
+        pod_groups.append({"metadata": pg_md, "spec": spec})
         for ps in range(b, e):
             for t in range(int(snap.podset_task_begin[ps]), int(snap.podset_task_begin[ps + 1])):
                 st = int(snap.task_status[t])
@@ -948,11 +1024,15 @@ def dump_cluster(snap: "abi.Snapshot", actions=("allocate",), config: dict | Non
     # the default tier (conf_util/scheduler_conf_util.go:38-60) without the workload-specific and HTTP plugins
     plugins = [{"name": n} for n in ("predicates", "proportion", "priority", "elastic", "nodeavailability",
                                      "gpusharingorder", "gpupack", "resourcetype", "subgrouporder", "taskorder",
-                                     "nominatednode", "nodeplacement", "topology")]
+                                     "nominatednode", "nodeplacement", "minruntime", "topology")]
     for p in plugins:
         if p["name"] == "nodeplacement":
             p["arguments"] = {"gpu": place[config.get("gpu_placement", abi.PLACEMENT_BINPACK)],
                               "cpu": place[config.get("cpu_placement", abi.PLACEMENT_BINPACK)]}
+        if p["name"] == "minruntime":
+            p["arguments"] = {"defaultReclaimMinRuntime": format_duration(config.get("default_reclaim_min_runtime_s", 0.0)),
+                              "defaultPreemptMinRuntime": format_duration(config.get("default_preempt_min_runtime_s", 0.0)),
+                              "reclaimResolveMethod": "queue" if config.get("reclaim_resolve_method") == abi.RESOLVE_QUEUE else "lca"}
         if p["name"] == "proportion" and ("k_value" in config or "saturation_multiplier" in config):
             p["arguments"] = {"kValue": str(config.get("k_value", 1.0)),
                               "relcaimerSaturationMultiplier": str(config.get("saturation_multiplier", 1.0))}
@@ -967,6 +1047,10 @@ def dump_cluster(snap: "abi.Snapshot", actions=("allocate",), config: dict | Non
            "schedulerParams": params,
            "rawObjects": {"pods": pods, "nodes": nodes, "queues": queues, "podGroups": pod_groups,
                           "bindRequests": bind_requests, "priorityClasses": priority_classes, "topologies": topologies}}
+    if snap.job_last_start_s is not None or snap.queue_preempt_min_runtime_s is not None:
+        if snap.now_s != int(snap.now_s):
+            raise UnsupportedSnapshot("sub-second capture time")
+        doc["capturedAt"] = _rfc3339(int(snap.now_s))  # extension: the reference's tool uses time.Now() at replay
     if snap.queue_usage is not None:
         doc["queueUsage"] = {queue_names[q]: {"cpu": float(snap.queue_usage[0, q]), "memory": float(snap.queue_usage[1, q]),
                                               "gpu": float(snap.queue_usage[2, q])} for q in range(Q)}

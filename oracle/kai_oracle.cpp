@@ -2144,6 +2144,72 @@ struct kai_oracle {
     }
     return true;
   }
+  // ---------------- plugins/minruntime ----------------
+  std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start;  // seconds; < 0 = nil; last start <= 0 = nil
+  double now_s = 0;
+  // resolver.go:46-67 resolvePreemptMinRuntime: first value set on the queue or an ancestor, else the default
+  double preempt_min_runtime(int q) const {
+    for (int c = q; c >= 0; c = Q[c].parent)
+      if (!q_preempt_mrt.empty() && q_preempt_mrt[c] >= 0) return q_preempt_mrt[c];
+    return cfg.default_preempt_min_runtime_s;
+  }
+  double reclaim_min_runtime(int pq, int vq) const {  // resolver.go:69-187
+    if (pq < 0 || vq < 0) return cfg.default_reclaim_min_runtime_s;
+    auto set = [&](int q) { return !q_reclaim_mrt.empty() && q_reclaim_mrt[q] >= 0; };
+    if (cfg.reclaim_resolve_method == KAI_RESOLVE_QUEUE) {  // :88-106
+      for (int c = vq; c >= 0; c = Q[c].parent)
+        if (set(c)) return q_reclaim_mrt[c];
+      return cfg.default_reclaim_min_runtime_s;
+    }
+    std::vector<int> pp, vp;  // getQueueHierarchyPath: root first (:189-203)
+    for (int c = pq; c >= 0; c = Q[c].parent) pp.insert(pp.begin(), c);
+    for (int c = vq; c >= 0; c = Q[c].parent) vp.insert(vp.begin(), c);
+    if (pp[0] != vp[0]) return set(vp[0]) ? q_reclaim_mrt[vp[0]] : cfg.default_reclaim_min_runtime_s;  // :122-131
+    size_t lca = 0, n = std::min(pp.size(), vp.size());
+    for (size_t i = 0; i < n; i++) {
+      if (pp[i] != vp[i]) break;
+      lca = i;
+    }
+    if (lca + 1 < vp.size()) lca++;  // the victim-side child of the common ancestor (:143-145)
+    for (size_t i = lca + 1; i-- > 0;)
+      if (set(vp[i])) return q_reclaim_mrt[vp[i]];
+    return cfg.default_reclaim_min_runtime_s;
+  }
+  bool job_elastic(int ji) const {  // job_info.go:408-415, podset.go:127-129
+    for (int ps : J[ji].podsets)
+      if (PS[ps].min_available < (int)PS[ps].tasks.size()) return true;
+    return false;
+  }
+  // minruntime.go:147-192 isReclaimMinRuntimeProtected / isPreemptMinRuntimeProtected
+  bool minruntime_protected(bool reclaim, int pending_job, int victim) const {
+    if (j_last_start.empty() || !(j_last_start[victim] > 0)) return false;
+    double mrt = reclaim ? reclaim_min_runtime(J[pending_job].queue, J[victim].queue) : preempt_min_runtime(J[victim].queue);
+    return now_s < j_last_start[victim] + mrt;
+  }
+  // minruntime.go:93-105 reclaimFilterFn / preemptFilterFn
+  bool minruntime_filter(bool reclaim, int pending_job, int victim) const {
+    if (job_elastic(victim)) return true;
+    return !minruntime_protected(reclaim, pending_job, victim);
+  }
+  // minruntime.go:107-145 scenario validators + :206-229 validVictimForMinAvailable
+  bool minruntime_validator(const Scenario &sc, bool reclaim) const {
+    int pj = vjob(sc.preemptor);
+    for (const auto &kv : sc.victims) {
+      int vj = kv.first;
+      if (!job_elastic(vj) || !minruntime_protected(reclaim, pj, vj)) continue;
+      for (int ps : J[vj].podsets) {
+        int victims = 0, running = 0;
+        for (int t : kv.second)
+          if (T[t].podset == ps) victims++;
+        if (!victims) continue;
+        for (int t : PS[ps].tasks)
+          if (T[t].status & kActiveUsed) running++;
+        if (PS[ps].min_available > running - victims) return false;
+      }
+    }
+    return true;
+  }
+
   // proportion.go:143-240 reclaimableFn / getVictimResources / splitVictimTasks / getResources
   bool reclaim_validator(const Scenario &sc) {
     const Job &rj = J[vjob(sc.preemptor)];
@@ -2241,9 +2307,10 @@ struct kai_oracle {
         pipelined.push_back(ti);
     }
     res.has = true;
-    // preempt: ssn.PreemptScenarioValidator = minruntime only (not modelled): always valid
-    bool valid = solver_kind == SOLVER_RECLAIM ? reclaim_validator(sc)
-                 : (solver_kind == SOLVER_CONSOLIDATION ? consolidation_validator(sc) : true);
+    // session_plugins.go:135-164: every registered validator must accept (reclaim: proportion + minruntime;
+    // preempt: minruntime only; consolidation passes its own closure)
+    bool valid = solver_kind == SOLVER_RECLAIM ? (reclaim_validator(sc) && minruntime_validator(sc, true))
+                 : (solver_kind == SOLVER_CONSOLIDATION ? consolidation_validator(sc) : minruntime_validator(sc, false));
     if (!valid) {
       stmt_discard();
       return res;
@@ -2325,7 +2392,8 @@ struct kai_oracle {
       op.filter_non_active_allocated = true;
       for (int ji = 0; ji < NJ; ji++) {
         if (J[ji].queue == J[pending_job].queue) continue;
-        vs.push_back(ji);  // ReclaimVictimFilter: minruntime protection is not modelled (always unprotected)
+        if (!minruntime_filter(true, pending_job, ji)) continue;  // ssn.ReclaimVictimFilter (reclaim.go:134-136)
+        vs.push_back(ji);
       }
     } else if (solver_kind == SOLVER_PREEMPT) {  // preempt.go:125-161 + utils/action.go:20-52
       for (int ji = 0; ji < NJ; ji++) {
@@ -2339,6 +2407,7 @@ struct kai_oracle {
         if (J[ji].queue != J[pending_job].queue) continue;
         if (ji == pending_job) continue;
         if (job_count(J[ji], kActiveAllocated) == 0) continue;
+        if (!minruntime_filter(false, pending_job, ji)) continue;  // ssn.PreemptVictimFilter (preempt.go:147-149)
         vs.push_back(ji);
       }
     } else {
@@ -2795,6 +2864,13 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
     }
     if (p >= 0) o->Q[p].children.push_back(q);
   }
+  o->now_s = s->now_s;
+  o->q_preempt_mrt.clear();
+  o->q_reclaim_mrt.clear();
+  o->j_last_start.clear();
+  if (s->queue_preempt_min_runtime_s) o->q_preempt_mrt.assign(s->queue_preempt_min_runtime_s, s->queue_preempt_min_runtime_s + o->NQ);
+  if (s->queue_reclaim_min_runtime_s) o->q_reclaim_mrt.assign(s->queue_reclaim_min_runtime_s, s->queue_reclaim_min_runtime_s + o->NQ);
+  if (s->job_last_start_s) o->j_last_start.assign(s->job_last_start_s, s->job_last_start_s + o->NJ);
   o->J.assign(o->NJ, Job());
   o->PS.assign(o->NS, PodSet());
   o->T.assign(o->NT, Task());
@@ -2985,6 +3061,15 @@ double kai_oracle_set_resource_share(int n, double total, double k_value, const 
   double rem = set_resource_share(total, k_value, Q, group, 0);
   for (int i = 0; i < n; i++) fair_share[i] = Q[i].s[0].fair;
   return rem;
+}
+
+// plugins/minruntime/resolver.go on the loaded snapshot's queue tree: reclaim != 0 -> getReclaimMinRuntime(method of
+// the config, pending queue, victim queue), else getPreemptMinRuntime(victim queue); -1 = nil queue
+double kai_oracle_min_runtime(kai_oracle *o, int reclaim, int pending_queue, int victim_queue) {
+  return reclaim ? o->reclaim_min_runtime(pending_queue, victim_queue) : o->preempt_min_runtime(victim_queue);
+}
+int kai_oracle_min_runtime_protected(kai_oracle *o, int reclaim, int pending_job, int victim_job) {
+  return o->minruntime_filter(reclaim != 0, pending_job, victim_job) ? 0 : 1;
 }
 
 int kai_oracle_queue_order(const double *l_share, const double *r_share, int l_priority, int r_priority,

@@ -55,6 +55,12 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
                            const double *l_job_req, const double *r_job_req,
                            const double *total);
 
+/* plugins/minruntime/resolver.go on the loaded snapshot's queue tree: getReclaimMinRuntime (method of the config)
+   for (pending queue, victim queue) when reclaim != 0, else getPreemptMinRuntime(victim queue); -1 = nil queue. */
+double kai_oracle_min_runtime(kai_oracle *o, int reclaim, int pending_queue, int victim_queue);
+/* !reclaimFilterFn / !preemptFilterFn (minruntime.go:93-105): 1 = the victim job is withheld */
+int kai_oracle_min_runtime_protected(kai_oracle *o, int reclaim, int pending_job, int victim_job);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,10 @@ def lib() -> C.CDLL:
         _LIB.kai_oracle_set_resource_share.restype = C.c_double
         _LIB.kai_oracle_queue_order.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int64, C.c_int64, dp, dp, dp]
         _LIB.kai_oracle_queue_order.restype = C.c_int
+        _LIB.kai_oracle_min_runtime.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _LIB.kai_oracle_min_runtime.restype = C.c_double
+        _LIB.kai_oracle_min_runtime_protected.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _LIB.kai_oracle_min_runtime_protected.restype = C.c_int
     return _LIB
 
 
@@ -71,6 +75,12 @@ class Oracle:
         r = abi.KaiResult()
         self._check(self._lib.kai_oracle_fair_share(self._h, C.byref(r)))
         return abi.Result.from_c(r, self._n_res)
+
+    def min_runtime(self, reclaim: bool, pending_queue: int, victim_queue: int) -> float:
+        return self._lib.kai_oracle_min_runtime(self._h, int(reclaim), pending_queue, victim_queue)
+
+    def min_runtime_protected(self, reclaim: bool, pending_job: int, victim_job: int) -> bool:
+        return bool(self._lib.kai_oracle_min_runtime_protected(self._h, int(reclaim), pending_job, victim_job))
 
     def stats(self) -> abi.KaiStats:
         s = abi.KaiStats()
