@@ -114,6 +114,7 @@ def build_snapshot(topo: dict):
     podset_min, podset_task_begin = [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_job = [], [], [], [], [], []
     t_fixture_node = []
+    t_affinity = []
     job_podset_names = []
     for ji, job in enumerate(jobs):
         job_names.append(job["Name"])
@@ -171,6 +172,7 @@ def build_snapshot(topo: dict):
                 t_rank.append(order_rank[k])
                 t_names.append(f"{job['Name']}-{k}")
                 t_job.append(ji)
+                t_affinity.append(tuple(t.get("NodeAffinityNames") or ()))
                 # a fixture may name a node on a Pending task; PodInfo.NodeName keeps it and the reference's
                 # matcher compares it (test_utils.go:236-244) although it never reaches the algorithm
                 t_fixture_node.append(node if t_node[-1] < 0 else "")
@@ -282,6 +284,28 @@ def build_snapshot(topo: dict):
                        podset_required_level=np.array([c[1] for c in ps_con], dtype=np.int32),
                        podset_preferred_level=np.array([c[2] for c in ps_con], dtype=np.int32))
 
+    # tasks_fake/tasks.go:98-116: NodeAffinityNames = required node affinity `kai.scheduler/type In names`; every fake
+    # node carries that label with its own name unless the fixture overrides it (nodes_fake/nodes.go:182-191).  A k8s
+    # Filter result: handed to the engine as a predicate class.
+    pred_kw = {}
+    if any(t_affinity):
+        def node_type(name):
+            labels = topo["Nodes"][name].get("Labels") or {}
+            return labels.get("tasks_fake.NodeAffinityKey", labels.get("kai.scheduler/type", name))
+        classes, masks = {}, []
+        t_class = np.full(T, -1, dtype=np.int32)
+        words = (N + 31) // 32
+        for t, names in enumerate(t_affinity):
+            if not names:
+                continue
+            if names not in classes:
+                bits = np.zeros(words * 32, dtype=np.uint64)
+                bits[:N] = [node_type(n) in names for n in node_names]
+                masks.append((bits.reshape(words, 32) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32))
+                classes[names] = len(masks) - 1
+            t_class[t] = classes[names]
+        pred_kw = dict(task_pred_class=t_class, pred_mask=np.stack(masks).astype(np.uint32))
+
     snap = abi.Snapshot(
         n_res=R,
         node_allocatable=alloc, node_idle=idle, node_releasing=rel,
@@ -298,7 +322,7 @@ def build_snapshot(topo: dict):
         podset_task_begin=np.array(podset_task_begin, dtype=np.int32),
         task_status=np.array(t_status, dtype=np.int32), task_node=np.array(t_node, dtype=np.int32),
         task_req=t_req_a, task_order_rank=np.array(t_rank, dtype=np.int32),
-        **topo_kw,
+        **topo_kw, **pred_kw,
     )
     meta = {
         "node_names": node_names, "job_names": job_names, "task_names": t_names,

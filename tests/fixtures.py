@@ -20,3 +20,20 @@ def action_cases(prefixes, single_action=None):
                 continue
             out.append((f"{base}[{case['index']}]", case))
     return out
+
+
+def case_config(case, **overrides):
+    """kai_config for a table: the reference's test defaults plus what the table's own SchedulerConf sets
+    (gen_fixtures keeps `nodeplacement` arguments as case["config"])."""
+    from kai_scheduler_b200 import abi
+    place = {"binpack": abi.PLACEMENT_BINPACK, "spread": abi.PLACEMENT_SPREAD}
+    kw = {}
+    for key, value in (case.get("config") or {}).items():
+        kw[key] = place[value] if key.endswith("_placement") else value
+    kw.update(overrides)
+    return abi.make_config(**kw)
+
+
+def case_needs_predicates(case) -> bool:
+    """Tables whose pods carry node affinity: they need pred_mask classes (not in the C++ mirror's text format)."""
+    return any(t.get("NodeAffinityNames") for j in case["topology"].get("Jobs") or [] for t in j.get("Tasks") or [])

@@ -95,7 +95,7 @@ def resolve(x):
     return x
 
 
-_CONSTRAINT = r'(nil|& topology_info \. TopologyConstraintInfo \{ (?:[^{}]*) \})'
+_CONSTRAINT = r'(nil|& topology_info \. TopologyConstraintInfo \{ (?:[^{}]* )?\})'
 _NEWSET = re.compile(r'(\w+) : = subgroup_info \. NewSubGroupSet \( ((?:"[^"]*")|(?:subgroup_info \. RootSubGroupSetName)) , ' + _CONSTRAINT + r'(?: ,)? \)')
 _ADDPODSET = re.compile(r'(\w+) \. AddPodSet \( subgroup_info \. NewPodSet \( "([^"]+)" , (\d+) , ' + _CONSTRAINT + r'(?: ,)? \) \)')
 _ADDGROUP = re.compile(r'(\w+) \. AddSubGroup \( (\w+) \)')
@@ -161,6 +161,44 @@ def find_unresolved(x, path=""):
     return out
 
 
+def evenly_distributed_topology_nodes(zones, spines_per_zone, racks_per_spine, nodes_per_rack, gpus_per_node):
+    """What allocateTopology_test.go's helper buildEvenlyDistributedTopologyNodes (:3162-3188) returns: node<i> in
+    creation order, labelled zone<z> / spine<global index> / rack<global index>."""
+    nodes, node_id = {}, 0
+    for z in range(1, zones + 1):
+        for sp in range(1, spines_per_zone + 1):
+            spine = sp + (z - 1) * spines_per_zone
+            for r in range(1, racks_per_spine + 1):
+                rack = r + (sp - 1) * racks_per_spine + (z - 1) * spines_per_zone * racks_per_spine
+                for _ in range(nodes_per_rack):
+                    nodes[f"node{node_id}"] = {"GPUs": gpus_per_node, "Labels": {
+                        "k8s.io/zone": f"zone{z}", "k8s.io/spine": f"spine{spine}", "k8s.io/rack": f"rack{rack}"}}
+                    node_id += 1
+    return nodes
+
+
+def normalise(topo: dict) -> dict:
+    """Evaluate the two non-literal constructs the action tables use; returns the table's config overrides."""
+    config = {}
+    nodes = topo.get("Nodes")
+    if isinstance(nodes, dict) and nodes.get("__call") == "buildEvenlyDistributedTopologyNodes":
+        topo["Nodes"] = evenly_distributed_topology_nodes(*[int(a) for a in nodes["args"]])
+    mocks = topo.get("Mocks")
+    conf = mocks.get("SchedulerConf") if isinstance(mocks, dict) else None
+    if isinstance(conf, dict):
+        # a SchedulerConf that only sets the nodeplacement strategies (allocate_test.go:1306-1322) maps onto kai_config;
+        # the other plugins of the default tier do not change such a table's outcome
+        plugins = [p for t in conf.get("Tiers") or [] for p in t.get("Plugins") or []]
+        if len(plugins) == 1 and plugins[0].get("Name") == "nodeplacement":
+            strategy = {"constants.SpreadStrategy": "spread", "constants.BinpackStrategy": "binpack"}
+            keys = {"constants.GPUResource": "gpu_placement", "constants.CPUResource": "cpu_placement"}
+            args = plugins[0].get("Arguments") or {}
+            if all(k in keys and isinstance(v, dict) and v.get("__ident") in strategy for k, v in args.items()):
+                config = {keys[k]: strategy[v["__ident"]] for k, v in args.items()}
+                del mocks["SchedulerConf"]
+    return config
+
+
 def classify(topo: dict) -> str | None:
     """Return a skip reason if the case uses features outside the engine's scope, else None."""
     for tp in topo.get("Topologies") or []:
@@ -194,7 +232,7 @@ def classify(topo: dict) -> str | None:
         if job.get("DeleteJobInTest") or job.get("StaleDuration") is not None:
             return "deletion / staleness"
         for t in job.get("Tasks") or []:
-            for k in ("NodeAffinityNames", "PodAffinityLabels", "PodAffinityTopologyKey",
+            for k in ("PodAffinityLabels", "PodAffinityTopologyKey",
                       "PodAntiAffinityTopologyKey", "RequiredMigInstances", "IsLegacyMigTask",
                       "ResourceClaimTemplates", "ResourceClaimNames", "GPUGroups"):
                 if t.get(k):
@@ -269,6 +307,7 @@ def gen_actions():
         out = []
         for i, (topo, r_until, r_after) in enumerate(cases):
             topo.pop("__type", None)
+            config = normalise(topo)
             reason = classify(topo)
             out.append({
                 "source": f"pkg/scheduler/actions/{rel}",
@@ -279,6 +318,7 @@ def gen_actions():
                 "rounds_after_match": r_after,
                 "supported": reason is None,
                 "skip_reason": reason,
+                "config": config,
                 "topology": topo,
             })
         name = rel.replace("/", "__").replace("_test.go", "") + ".json"

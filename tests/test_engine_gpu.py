@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import dsl
-from fixtures import action_cases
+from fixtures import action_cases, case_config
 from kai_scheduler_b200 import abi, synthetic
 from kai_scheduler_b200.engine import Engine
 from oracle_lib import Oracle
@@ -48,7 +48,7 @@ def run_both(snap, action="allocate", cfg=None):
 @pytest.mark.parametrize("cid,case", ALLOCATE, ids=[c[0] for c in ALLOCATE])
 def test_allocate_tables_gpu(cid, case):
     snap, meta = dsl.build_snapshot(case["topology"])
-    re_, ro = run_both(snap)
+    re_, ro = run_both(snap, cfg=case_config(case))
     assert_same(re_, ro)
     errs = dsl.check_expectations(case["topology"], meta, re_, snap)
     assert not errs, f"{case['source']} #{case['index']}: {errs}"
@@ -195,7 +195,7 @@ def test_allocate_tables_forced_grid(grid, mode, monkeypatch):
         if mode == "device" and case["topology"].get("Topologies"):
             continue  # topology constraints run host-sequenced only
         snap, meta = dsl.build_snapshot(case["topology"])
-        re_, ro = run_both(snap)
+        re_, ro = run_both(snap, cfg=case_config(case))
         assert_same(re_, ro)
 
 

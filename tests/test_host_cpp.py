@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import dsl
-from fixtures import action_cases
+from fixtures import action_cases, case_needs_predicates
 from kai_scheduler_b200 import abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -94,7 +94,7 @@ def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None):
         f.write("actions " + " ".join(actions) + "\n")
 
 
-TOPO_CASES = action_cases(["allocate__allocateTopology"], single_action="allocate")
+TOPO_CASES = [c for c in action_cases(["allocate__allocateTopology"], single_action="allocate") if not case_needs_predicates(c[1])]
 
 
 @pytest.mark.parametrize("cid,case", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
@@ -137,7 +137,7 @@ class _Res:
     pass
 
 
-CASES = (action_cases(["allocate__allocateTopology"], single_action="allocate") + action_cases(["allocate__allocate_subgroups"], single_action="allocate")[-2:]
+CASES = (TOPO_CASES + action_cases(["allocate__allocate_subgroups"], single_action="allocate")[-2:]
          + action_cases(["allocate__allocate"], single_action="allocate")[:12] + action_cases(["reclaim__"], single_action="reclaim")[:12]
          + action_cases(["consolidation__"], single_action="consolidation")[:8] + action_cases(["preempt__"], single_action="preempt")[:8])
 

@@ -7,7 +7,7 @@ pkg/scheduler/actions/*/*_test.go by tests/golden/gen_fixtures.py; the assertion
 import pytest
 
 import dsl
-from fixtures import action_cases
+from fixtures import action_cases, case_config
 from oracle_lib import Oracle
 
 ALLOCATE = action_cases(["allocate__"], single_action="allocate")
@@ -16,7 +16,7 @@ ALLOCATE = action_cases(["allocate__"], single_action="allocate")
 @pytest.mark.parametrize("cid,case", ALLOCATE, ids=[c[0] for c in ALLOCATE])
 def test_allocate_tables(cid, case):
     snap, meta = dsl.build_snapshot(case["topology"])
-    o = Oracle()
+    o = Oracle(case_config(case))
     o.load(snap)
     res = o.run("allocate")
     errs = dsl.check_expectations(case["topology"], meta, res, snap)
@@ -53,6 +53,6 @@ def test_integration_tables(cid, case):
 
 def test_case_counts():
     assert len(INTEGRATION) == 60
-    assert len(RECLAIM) == 65 and len(CONSOLIDATION) == 25 and len(PREEMPT) == 31
+    assert len(RECLAIM) == 66 and len(CONSOLIDATION) == 25 and len(PREEMPT) == 31
     # the transcription must not silently lose cases (allocate 21 + gang 6 + elastic 7 + subgroups 7)
-    assert len(ALLOCATE) == 59  # allocate 21 + gang 6 + elastic 7 + subgroups 8 + topology 17
+    assert len(ALLOCATE) == 64  # allocate 22 + gang 6 + elastic 7 + subgroups 8 + topology 21

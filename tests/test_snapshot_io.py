@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import dsl
-from fixtures import action_cases
+from fixtures import action_cases, case_needs_predicates
 from oracle_lib import Oracle
 
 from kai_scheduler_b200 import abi, snapshot_io as sio, synthetic
@@ -278,8 +278,33 @@ TABLES = (action_cases(["allocate__"], single_action="allocate") + action_cases(
 _trip_stats = {"run": 0, "skipped": 0}
 
 
-def _round_trip(snap, actions, names=None, config=None):
+def _affinity_of(case, meta):
+    """{pod name: NodeAffinityNames} and {node name: its `kai.scheduler/type` label} of a table (tasks_fake/tasks.go:98-116,
+    nodes_fake/nodes.go:182-191)."""
+    pods = {}
+    for job in case["topology"].get("Jobs") or []:
+        for k, t in enumerate(job.get("Tasks") or []):
+            if t.get("NodeAffinityNames"):
+                pods[f"{job['Name']}-{k}"] = t["NodeAffinityNames"]
+    if not pods:
+        return None
+    nodes = {}
+    for name, nd in (case["topology"].get("Nodes") or {}).items():
+        labels = nd.get("Labels") or {}
+        nodes[name] = labels.get("tasks_fake.NodeAffinityKey", labels.get("kai.scheduler/type", name))
+    return pods, nodes
+
+
+def _round_trip(snap, actions, names=None, config=None, affinity=None):
     doc = sio.dump_cluster(snap, actions=actions, names=names, config=config)
+    if affinity:
+        pods, nodes = affinity
+        for node in doc["rawObjects"]["nodes"]:
+            node["metadata"]["labels"]["kai.scheduler/type"] = nodes[node["metadata"]["name"]]
+        for pod in doc["rawObjects"]["pods"]:
+            if pod["metadata"]["name"] in pods:
+                pod["spec"]["affinity"] = {"nodeAffinity": {"requiredDuringSchedulingIgnoredDuringExecution": {"nodeSelectorTerms": [
+                    {"matchExpressions": [{"key": "kai.scheduler/type", "operator": "In", "values": pods[pod["metadata"]["name"]]}]}]}}}
     buf = io.BytesIO()
     sio.write_snapshot_zip(buf, doc)
     return sio.pack_cluster(sio.read_snapshot_zip(buf.getvalue()))
@@ -288,8 +313,13 @@ def _round_trip(snap, actions, names=None, config=None):
 @pytest.mark.parametrize("cid,case", TABLES, ids=[c[0] for c in TABLES])
 def test_reference_tables_through_the_wire_format(cid, case):
     snap, meta = dsl.build_snapshot(case["topology"])
+    place = {"binpack": abi.PLACEMENT_BINPACK, "spread": abi.PLACEMENT_SPREAD}
+    config = {k: place[v] for k, v in (case.get("config") or {}).items()}
+    if case_needs_predicates(case):  # the table's node affinity goes back into the pods, the packer re-derives the masks
+        snap.task_pred_class = snap.pred_mask = None
     try:
-        snap2, meta2, kw, actions = _round_trip(snap, case["actions"], names=meta)
+        snap2, meta2, kw, actions = _round_trip(snap, case["actions"], names=meta, config=config,
+                                                affinity=_affinity_of(case, meta))
     except sio.UnsupportedSnapshot as e:  # tables that start from session-only statuses (Allocated / Pipelined)
         _trip_stats["skipped"] += 1
         pytest.skip(str(e))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import dsl
-from fixtures import action_cases
+from fixtures import action_cases, case_needs_predicates
 from kai_scheduler_b200 import abi, snapshot_io as sio, snapshot_tool, synthetic
 from kai_scheduler_b200.engine import Engine
 from oracle_lib import Oracle
@@ -55,7 +55,8 @@ def test_replay_tool_on_synthetic_zip(name, capsys):
     assert [r.get("action") for r in records[1:]] == list(actions)
 
 
-TOPOLOGY_TABLES = action_cases(["allocate__allocateTopology"], single_action="allocate")
+TOPOLOGY_TABLES = [c for c in action_cases(["allocate__allocateTopology"], single_action="allocate")
+                   if not case_needs_predicates(c[1])]  # predicate classes have no raw-object form in dump_cluster
 
 
 @pytest.mark.parametrize("cid,case", TOPOLOGY_TABLES, ids=[c[0] for c in TOPOLOGY_TABLES])
