@@ -92,14 +92,14 @@ def dist_env():
     return rank, world, local
 
 
-def run_reference(args, snap, workload, actions=("allocate",)):
+def run_reference(args, snap, workload, actions=("allocate",), engine_kw=None):
     """--impl reference: CPU oracle with all host threads on the same config/metric."""
     from oracle_lib import Oracle
     rank, world, _ = dist_env()
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, int(os.environ.get("KAI_REF_THREADS", "16")))
-    o = Oracle(threads=cores)
+    o = Oracle(abi.make_config(**(engine_kw or {})), threads=cores)
     times, placed = [], 0
     for i in range(args.warmup + args.steps):
         o.load(snap)
@@ -117,7 +117,7 @@ def run_reference(args, snap, workload, actions=("allocate",)):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "recorded snapshot" if args.snapshot else "synthetic",
         "config": workload,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "full workload per step (oracle/kai_oracle.cpp; node sweep fanned out over a spinning worker pool, "
@@ -135,13 +135,25 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="config2", choices=sorted(synthetic.CONFIG_ACTIONS))
     ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "off"])
+    ap.add_argument("--snapshot", default=None,
+                    help="time a recorded cluster instead of a synthetic config: a zip of the reference's snapshot "
+                         "plugin (kai_scheduler_b200/snapshot_io.py); actions and plugin arguments come from the file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = dist_env()
 
     actions = synthetic.CONFIG_ACTIONS[args.config]
-    snap = synthetic.config_snapshot(args.config)
-    if args.config in synthetic.CONFIGS:
+    engine_kw = {}
+    if args.snapshot:
+        from kai_scheduler_b200 import snapshot_io
+        snap, _meta, engine_kw, actions = snapshot_io.pack_cluster(snapshot_io.read_snapshot_zip(args.snapshot))
+        desc = (f"snapshot {os.path.basename(args.snapshot)}: {snap.n_nodes} nodes, {snap.n_jobs} pod groups, "
+                f"{int(snap.task_status.shape[0])} pods; actions {'+'.join(actions)}")
+    else:
+        snap = synthetic.config_snapshot(args.config)
+    if args.snapshot:
+        pass
+    elif args.config in synthetic.CONFIGS:
         kw = synthetic.CONFIGS[args.config]
         desc = (f"{args.config}: {kw['n_nodes']} nodes x {kw['n_jobs']} jobs x {kw.get('tasks_per_job', 1)} pods, "
                 f"{kw.get('n_queues', 4)} leaf queues, binpack, allocate action")
@@ -163,7 +175,7 @@ def main():
                      "the action kernel then keeps its node tiles in shared memory",
     }
     if args.impl == "reference":
-        run_reference(args, snap, workload, actions)
+        run_reference(args, snap, workload, actions, engine_kw)
         return
 
     import torch
@@ -176,7 +188,7 @@ def main():
     # N > 1: the node rows are striped by name rank over the GPUs (kai_shard_range(N, world, r)); every rank
     # runs the same deterministic sequencer, one reduced answer line per GPU per sweep is exchanged through a
     # shared host segment.  Total work is fixed => strong scaling.
-    eng = Engine(abi.make_config(device=local, shard_rank=rank, shard_count=world))
+    eng = Engine(abi.make_config(device=local, shard_rank=rank, shard_count=world, **engine_kw))
     if world > 1:
         handles = [eng.export_peer_handle() if rank == 0 else b""]
         dist.broadcast_object_list(handles, src=0)
@@ -241,7 +253,7 @@ def main():
             "metric": METRIC, "value": pods_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "data": "recorded snapshot" if args.snapshot else "synthetic",
             "config": workload,
             "e2e": {"value": pods_all / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -262,7 +274,7 @@ def main():
         }
         if args.cpu_baseline != "off" and args.gpus == 1:
             from oracle_lib import Oracle
-            o = Oracle(threads=1)
+            o = Oracle(abi.make_config(**engine_kw), threads=1)
             o.load(snap)
             t0 = time.perf_counter()
             moved = 0
