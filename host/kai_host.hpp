@@ -47,6 +47,9 @@ struct PodInfo {  // pod_info/pod_info.go:70-112
   ResourceVector ResReq;
   long long OrderKey = 0;  // position under TaskOrderFn inside the job (priority, then UID)
   std::string NominatedNodeName;
+  // required node affinity `kai.scheduler/type In NodeAffinityNames` (the only k8s Filter the reference's test DSL
+  // produces, tasks_fake/tasks.go:98-116); the shim evaluates such node-local filters into pred_mask classes
+  std::vector<std::string> NodeAffinityNames;
 };
 struct TopologyConstraintInfo {  // api/topology_info: empty Topology = no constraint
   std::string Topology, RequiredLevel, PreferredLevel;
@@ -228,6 +231,8 @@ struct Packed {
   std::vector<uint32_t> nflags, jflags;
   std::vector<int64_t> qcreation;
   std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start;
+  std::vector<int32_t> tpred;
+  std::vector<uint32_t> pred_mask;
 };
 template <class T, class K>
 std::vector<int32_t> rank_of(const std::vector<T> &items, K key) {  // rank of every item under the key's `<`
@@ -245,6 +250,9 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   p.q_preempt_mrt.clear();
   p.q_reclaim_mrt.clear();
   p.j_last_start.clear();
+  p.tpred.clear();
+  p.pred_mask.clear();
+  std::map<std::vector<std::string>, int> pred_classes;
   ssn.task_job.clear();
   for (auto &kv : ci.Nodes) ssn.idx_nodes.push_back(kv.second);  // std::map: already in byte-wise name order
   const int N = (int)ssn.idx_nodes.size();
@@ -329,6 +337,25 @@ inline void packSnapshot(Session &ssn, Packed &p) {
         p.torder.push_back(order[k]);
         auto nom = node_index.find(t->NominatedNodeName);
         p.tnom.push_back(nom == node_index.end() ? -1 : nom->second);
+        if (t->NodeAffinityNames.empty()) {
+          p.tpred.push_back(-1);
+        } else {  // one predicate class per distinct constraint; bit n = node n passes the filter
+          auto it = pred_classes.find(t->NodeAffinityNames);
+          if (it == pred_classes.end()) {
+            const int words = (N + 31) / 32;
+            p.pred_mask.resize(p.pred_mask.size() + words, 0u);
+            uint32_t *row = p.pred_mask.data() + p.pred_mask.size() - words;
+            for (int n = 0; n < N; n++) {
+              auto &labels = ssn.idx_nodes[n]->Labels;
+              auto lt = labels.find("kai.scheduler/type");
+              const std::string &type = lt == labels.end() ? ssn.idx_nodes[n]->Name : lt->second;
+              if (std::find(t->NodeAffinityNames.begin(), t->NodeAffinityNames.end(), type) != t->NodeAffinityNames.end())
+                row[n >> 5] |= 1u << (n & 31);
+            }
+            it = pred_classes.emplace(t->NodeAffinityNames, (int)pred_classes.size()).first;
+          }
+          p.tpred.push_back(it->second);
+        }
         for (int r = 0; r < R; r++) p.treq.push_back(t->ResReq[r]);
       }
       p.pstb.push_back((int32_t)p.tstatus.size());
@@ -454,6 +481,11 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   c.task_req = p.treq.data();
   c.task_order_rank = p.torder.data();
   c.task_nominated = p.tnom.data();
+  c.n_pred_classes = (int32_t)pred_classes.size();
+  if (!pred_classes.empty()) {
+    c.task_pred_class = p.tpred.data();
+    c.pred_mask = p.pred_mask.data();
+  }
   c.job_signature = p.jsig.data();
   c.now_s = ssn.Now;
   c.queue_preempt_min_runtime_s = p.q_preempt_mrt.data();

@@ -112,6 +112,23 @@ int main(int argc, char **argv) {
       // nodes_fake/nodes.go:213-223: tasks in an active-used state are added to their node
       if (pod_status::IsActiveUsedStatus(t->Status) && ssn.ClusterInfo.Nodes.count(t->NodeName))
         ssn.ClusterInfo.Nodes[t->NodeName]->AddTask(t);
+    } else if (kind == "affinity") {  // affinity <pod> <name>...
+      std::string pod, name;
+      ls >> pod;
+      for (auto &t : all_tasks)
+        if (t->UID == pod)
+          while (ls >> name) t->NodeAffinityNames.push_back(name);
+    } else if (kind == "conf") {  // conf <gpu placement> <cpu placement> <default reclaim s> <default preempt s> <method> <now>
+      ls >> ssn.Config.gpu_placement >> ssn.Config.cpu_placement >> ssn.Config.default_reclaim_min_runtime_s >>
+          ssn.Config.default_preempt_min_runtime_s >> ssn.Config.reclaim_resolve_method >> ssn.Now;
+    } else if (kind == "queuemrt") {  // queuemrt <queue> <preempt s | -1> <reclaim s | -1>
+      std::string q;
+      ls >> q;
+      ls >> ssn.ClusterInfo.Queues[q]->PreemptMinRuntime >> ssn.ClusterInfo.Queues[q]->ReclaimMinRuntime;
+    } else if (kind == "jobstart") {  // jobstart <job> <last start s | -1>
+      std::string j;
+      ls >> j;
+      ls >> ssn.ClusterInfo.PodGroupInfos[j]->LastStartTimestamp;
     } else if (kind == "actions") {
       std::string a;
       while (ls >> a) actions.push_back(a);
@@ -134,6 +151,13 @@ int main(int argc, char **argv) {
         printf("podset %s %d min %d set %d con %d %d %d\n", ssn.idx_jobs[j]->UID.c_str(), ps - c.job_podset_begin[j],
                c.podset_min_available[ps], c.podset_sgs[ps] - c.job_sgs_begin[j], c.podset_topology[ps],
                c.podset_required_level[ps], c.podset_preferred_level[ps]);
+    }
+    for (int t = 0; t < c.n_tasks; t++) {
+      if (!c.task_pred_class || c.task_pred_class[t] < 0) continue;
+      printf("pred %s %d", ssn.idx_tasks[t]->UID.c_str(), c.task_pred_class[t]);
+      const int words = (c.n_nodes + 31) / 32;
+      for (int w = 0; w < words; w++) printf(" %u", c.pred_mask[(size_t)c.task_pred_class[t] * words + w]);
+      printf("\n");
     }
     return 0;
   }

@@ -31,7 +31,7 @@ def test_registry_resolves_default_actions():
                        "stalegangeviction registered", "unknown missing"]
 
 
-def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None):
+def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None, cfg: dict | None = None):
     R, N, Q = snap.n_res, snap.n_nodes, int(snap.queue_parent.shape[0])
     qn = meta["queue_names"]
     with open(path, "w") as f:
@@ -46,6 +46,7 @@ def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None):
             f.write(f"topology {tp['ObjectMeta']['Name']} " + " ".join(lv["NodeLabel"] for lv in tp["Spec"]["Levels"]) + "\n")
         for nname, nd in ((topo or {}).get("Nodes") or {}).items():
             for k_, v_ in (nd.get("Labels") or {}).items():
+                k_ = "kai.scheduler/type" if k_ == "tasks_fake.NodeAffinityKey" else k_
                 f.write(f"label {nname} {k_} {v_}\n")
         for j, name in enumerate(meta["job_names"]):
             pre = 1 if snap.job_flags[j] & abi.JOB_PREEMPTIBLE else 0
@@ -91,10 +92,23 @@ def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None):
                     req = " ".join(repr(float(x)) for x in snap.task_req[t])
                     f.write(f"task {name} ps{ps - snap.job_podset_begin[j]:03d} {meta['task_names'][t]} {int(snap.task_status[t])} "
                             f"{node} {int(snap.task_order_rank[t])} {req}\n")
+        for jd in (topo or {}).get("Jobs") or []:
+            for k, t in enumerate(jd.get("Tasks") or []):
+                if t.get("NodeAffinityNames"):
+                    f.write(f"affinity {jd['Name']}-{k} " + " ".join(t["NodeAffinityNames"]) + "\n")
+        cfg = cfg or {}
+        f.write(f"conf {cfg.get('gpu_placement', 0)} {cfg.get('cpu_placement', 0)} {cfg.get('default_reclaim_min_runtime_s', 0.0)!r} "
+                f"{cfg.get('default_preempt_min_runtime_s', 0.0)!r} {cfg.get('reclaim_resolve_method', 0)} {float(snap.now_s)!r}\n")
+        if snap.queue_preempt_min_runtime_s is not None:
+            for q in range(Q):
+                f.write(f"queuemrt {qn[q]} {float(snap.queue_preempt_min_runtime_s[q])!r} {float(snap.queue_reclaim_min_runtime_s[q])!r}\n")
+        if snap.job_last_start_s is not None:
+            for j, name in enumerate(meta["job_names"]):
+                f.write(f"jobstart {name} {float(snap.job_last_start_s[j])!r}\n")
         f.write("actions " + " ".join(actions) + "\n")
 
 
-TOPO_CASES = [c for c in action_cases(["allocate__allocateTopology"], single_action="allocate") if not case_needs_predicates(c[1])]
+TOPO_CASES = action_cases(["allocate__allocateTopology"], single_action="allocate")
 
 
 @pytest.mark.parametrize("cid,case", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
@@ -131,6 +145,16 @@ def test_cpp_packing_of_topologies_and_subgroup_tree(cid, case):
             assert int(f[6]) == snap.podset_sgs[ps] - snap.job_sgs_begin[j], line
             assert [int(x) for x in f[8:11]] == [snap.podset_topology[ps], snap.podset_required_level[ps], snap.podset_preferred_level[ps]], line
     assert seen_sets == len(snap.sgs_parent)
+    if case_needs_predicates(case):
+        masks = {}
+        for line in out:
+            f = line.split()
+            if f and f[0] == "pred":  # pred <pod> <class> <mask words...>
+                masks[f[1]] = [int(x) for x in f[3:]]
+        for t, name in enumerate(meta["task_names"]):
+            c = snap.task_pred_class[t]
+            want = [] if c < 0 else [int(x) for x in snap.pred_mask[c]]
+            assert masks.get(name, []) == want, name
 
 
 class _Res:
@@ -138,7 +162,9 @@ class _Res:
 
 
 CASES = (TOPO_CASES + action_cases(["allocate__allocate_subgroups"], single_action="allocate")[-2:]
-         + action_cases(["allocate__allocate"], single_action="allocate")[:12] + action_cases(["reclaim__"], single_action="reclaim")[:12]
+         + action_cases(["allocate__allocate"], single_action="allocate")[:12]
+         + [c for c in action_cases(["allocate__", "reclaim__"]) if c[1].get("config") or case_needs_predicates(c[1])][:4]
+         + action_cases(["reclaim__"], single_action="reclaim")[:12]
          + action_cases(["consolidation__"], single_action="consolidation")[:8] + action_cases(["preempt__"], single_action="preempt")[:8])
 
 
@@ -149,7 +175,9 @@ def test_reference_tables_through_cpp_shim(cid, case):
     snap, meta = dsl.build_snapshot(case["topology"])
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "case.txt")
-        write_case(path, snap, meta, case["actions"], case["topology"])
+        place = {"binpack": 0, "spread": 1}
+        write_case(path, snap, meta, case["actions"], case["topology"],
+                   cfg={k: place[v] for k, v in (case.get("config") or {}).items()})
         out = subprocess.run([BIN, path], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     lines = [l.split() for l in out.stdout.strip().split("\n")]
@@ -170,3 +198,33 @@ def test_reference_tables_through_cpp_shim(cid, case):
                      ("NumberOfPipelineActions", int(cache[3]))):
         if caps.get(key) is not None:
             assert got <= caps[key], (key, got, caps[key])
+
+
+import minruntime_cases as mc  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", mc.CASES, ids=[c[0] for c in mc.CASES])
+def test_min_runtime_through_cpp_shim(case):
+    """QueueInfo.{Preempt,Reclaim}MinRuntime, PodGroupInfo.LastStartTimestamp and the plugin arguments packed by the C++
+    mirror: the replayed session must end where the oracle ends."""
+    from oracle_lib import Oracle
+    _build()
+    first = None
+    if "@first" in case[5]:
+        snap, meta, cfg = mc.build(next(c for c in mc.CASES if c[0] == "reclaim-unprotected"))
+        o = Oracle(cfg)
+        o.load(snap)
+        first = [n for n, st in mc.outcome(o.run("reclaim"), meta).items() if st == "Releasing"][0].rsplit("-", 1)[0]
+    snap, meta, cfg = mc.build(case, first)
+    o = Oracle(cfg)
+    o.load(snap)
+    want = o.run(case[2])
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "case.txt")
+        write_case(path, snap, meta, [case[2]], case[1], cfg=case[3])
+        out = subprocess.run([BIN, path], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    by_name = {l.split()[0]: l.split() for l in out.stdout.strip().split("\n") if not l.startswith("cache")}
+    got_status = [int(by_name[n][1]) for n in meta["task_names"]]
+    assert got_status == [int(x) for x in want.task_status]
