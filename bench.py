@@ -224,6 +224,7 @@ def main():
     sampler.start()
     barrier()
     dev_ms, e2e_s, pods, launches, alg_bytes, act_ms, d2h = 0.0, 0.0, 0, 0, 0, 0.0, 0
+    phase_ms = {"upload": 0.0, "open_session": 0.0, "action": 0.0, "download": 0.0}
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         d, e, p, st, r = one_step()
@@ -233,6 +234,10 @@ def main():
         launches += int(st.kernel_launches)
         alg_bytes += int(st.algorithmic_bytes)
         act_ms += st.action_ms
+        phase_ms["upload"] += st.upload_ms
+        phase_ms["open_session"] += st.open_session_ms
+        phase_ms["action"] += st.action_ms
+        phase_ms["download"] += st.download_ms  # of the last action of the step
         d2h = (r.n_tasks * 8 + r.n_visits * 8 + r.n_queues * 3 * 8 * 4 + r.n_nodes * snap.n_res * 8 * 2 + 24)
     barrier()
     wall = time.perf_counter() - t_wall0
@@ -256,7 +261,9 @@ def main():
             "data": "recorded snapshot" if args.snapshot else "synthetic",
             "config": workload,
             "e2e": {"value": pods_all / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    # engine-side phases of one step (kai_engine_stats); the rest of e2e is marshalling in the caller
+                    "phases_ms": {k: v / max(args.steps, 1) for k, v in phase_ms.items()}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_action", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
