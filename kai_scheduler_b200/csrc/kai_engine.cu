@@ -616,6 +616,13 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   npc = (npc + 1) & ~1;  // keep the int arrays 8-byte aligned
   const int n_dom_levels = (s->n_topologies > 0 && s->topology_level_begin && s->node_domain) ? s->topology_level_begin[s->n_topologies] : 0;
   if (n_dom_levels > kMaxDomLevels) return e->fail(KAI_ERR_UNSUPPORTED, "more topology levels than kMaxDomLevels");
+  // a GPU request with a fractional part is a shared-GPU pod (gpu_resource_requirment.go:52-54,230-234): it needs the
+  // per-GPU-group tables of gpu_sharing_node_info.go, which this ABI does not carry; refuse instead of treating the
+  // fraction as a plain quantity
+  for (int t = 0; t < s->n_tasks; t++) {
+    const double g = s->task_req[(size_t)t * R + KAI_RES_GPU];
+    if (g != (double)(long long)g) return e->fail(KAI_ERR_UNSUPPORTED, "fractional GPU request: GPU sharing is outside this engine's scope");
+  }
   size_t tile_bytes = align_up((size_t)npc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4 + (size_t)4 * n_dom_levels), 16);
   const size_t smem_limit = (size_t)e->max_smem_optin - 28 * 1024;  // static shared memory of k_action
   if (tile_bytes > smem_limit)

@@ -2864,6 +2864,13 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
     }
     if (p >= 0) o->Q[p].children.push_back(q);
   }
+  for (int t = 0; t < s->n_tasks; t++) {  // same refusal as the engine: shared-GPU pods are not restated here
+    const double g = s->task_req[(size_t)t * s->n_res + KAI_RES_GPU];
+    if (g != (double)(long long)g) {
+      o->err = "fractional GPU request: GPU sharing is outside this oracle's scope";
+      return KAI_ERR_UNSUPPORTED;
+    }
+  }
   o->now_s = s->now_s;
   o->q_preempt_mrt.clear();
   o->q_reclaim_mrt.clear();

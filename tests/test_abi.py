@@ -50,3 +50,18 @@ def test_invalid_arguments():
     h = C.c_void_p()
     assert lib.kai_engine_create(C.byref(cfg), C.byref(h)) == abi.ERR_INVALID
     assert lib.kai_engine_create(None, C.byref(h)) == abi.ERR_INVALID
+
+
+def test_fractional_gpu_requests_are_refused():
+    """Shared-GPU pods need tables the ABI does not carry: both libraries must refuse them, not approximate."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_lib import Oracle
+    from kai_scheduler_b200 import synthetic
+    snap = synthetic.benchmark_snapshot(4, 3, n_queues=1)
+    snap.task_req = snap.task_req.copy()
+    snap.task_req[1, 2] = 0.5
+    o = Oracle()
+    with pytest.raises(RuntimeError, match="fractional GPU"):
+        o.load(snap)

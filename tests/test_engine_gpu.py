@@ -298,3 +298,14 @@ def test_config2_full_size_properties():
     o.load(snap)
     ro = o.run("allocate")
     assert_same(res, ro)
+
+
+def test_fractional_gpu_requests_are_refused_gpu():
+    from kai_scheduler_b200.engine import EngineError
+    snap = synthetic.benchmark_snapshot(4, 3, n_queues=1)
+    snap.task_req = snap.task_req.copy()
+    snap.task_req[1, 2] = 0.5
+    e = Engine()
+    with pytest.raises(EngineError, match="fractional GPU"):
+        e.load(snap)
+    e.close()
