@@ -2017,16 +2017,17 @@ struct kai_oracle {
   std::vector<QueueAttr> sim_queues;  // proportion.go:131-136 jobSimulationQueues
 
   // plugins/proportion/reclaimable/reclaimable.go:29-51
-  bool can_reclaim_resources(int ji) {
-    const Job &j = J[ji];
-    const double *req = tasks_to_allocate_init_resource(ji, false);
-    const QueueAttr &q = Q[j.queue];
+  static bool can_reclaim_from_share(const QueueAttr &q, const double *req, bool preemptible) {
     for (int r = 0; r < QR; r++)
       if (compare_quantities(q.s[r].allocated + req[r], q.s[r].fair) > 0) return false;
-    if (j.preemptible) return true;
+    if (preemptible) return true;
     for (int r = 0; r < QR; r++)
       if (compare_quantities(q.s[r].alloc_np + req[r], q.s[r].deserved) > 0) return false;
     return true;
+  }
+  bool can_reclaim_resources(int ji) {
+    const Job &j = J[ji];
+    return can_reclaim_from_share(Q[j.queue], tasks_to_allocate_init_resource(ji, false), j.preemptible);
   }
   // reclaimable.go:234-263 getLeveledQueues
   void leveled_queues(const std::vector<QueueAttr> &QS, int reclaimer_q, int reclaimee_q, int &a, int &b) {
@@ -3068,6 +3069,53 @@ double kai_oracle_set_resource_share(int n, double total, double k_value, const 
   double rem = set_resource_share(total, k_value, Q, group, 0);
   for (int i = 0; i < n; i++) fair_share[i] = Q[i].s[0].fair;
   return rem;
+}
+
+// plugins/proportion/reclaimable/reclaimable.go on an explicit queue table (unit-level entry points for the reference's
+// reclaimable_test.go).  share[q][r][5] = {Deserved, FairShare, Allocated, AllocatedNotPreemptible, MaxAllowed}, r in KAI_Q_*.
+static void fill_queue_table(kai_oracle &o, int n, const int32_t *parent, const double *share, double saturation_multiplier) {
+  o.cfg.saturation_multiplier = saturation_multiplier;
+  o.NQ = n;
+  o.Q.assign(n, QueueAttr());
+  for (int q = 0; q < n; q++) {
+    o.Q[q].parent = parent[q];
+    for (int r = 0; r < QR; r++) {
+      const double *x = share + ((size_t)q * QR + r) * 5;
+      o.Q[q].s[r].deserved = x[0];
+      o.Q[q].s[r].fair = x[1];
+      o.Q[q].s[r].allocated = x[2];
+      o.Q[q].s[r].alloc_np = x[3];
+      o.Q[q].s[r].max_allowed = x[4];
+    }
+  }
+}
+// Reclaimable.CanReclaimResources (reclaimable.go:29-51) for one queue: share[3][4], req[3]
+int kai_oracle_can_reclaim_resources(const double *share, const double *req, int preemptible) {
+  QueueAttr q;
+  for (int r = 0; r < QR; r++) {
+    q.s[r].deserved = share[r * 4 + 0];
+    q.s[r].fair = share[r * 4 + 1];
+    q.s[r].allocated = share[r * 4 + 2];
+    q.s[r].alloc_np = share[r * 4 + 3];
+  }
+  return kai_oracle::can_reclaim_from_share(q, req, preemptible != 0) ? 1 : 0;
+}
+// Reclaimable.Reclaimable (reclaimable.go:53-232): victims = (leaf queue, resources[3]) in the order given
+int kai_oracle_reclaimable(int n_queues, const int32_t *parent, const double *share, double saturation_multiplier,
+                           int reclaimer_queue, int preemptible, const double *req, int n_victims,
+                           const int32_t *victim_queue, const double *victim_res) {
+  kai_config cfg{};
+  cfg.abi_version = KAI_ABI_VERSION;
+  kai_oracle o;
+  o.cfg = cfg;
+  fill_queue_table(o, n_queues, parent, share, saturation_multiplier);
+  std::map<int, std::vector<kai_oracle::Quant>> by_queue;
+  for (int i = 0; i < n_victims; i++) {
+    kai_oracle::Quant x;
+    for (int r = 0; r < QR; r++) x.v[r] = victim_res[(size_t)i * QR + r];
+    by_queue[victim_queue[i]].push_back(x);
+  }
+  return o.reclaimable(o.Q, reclaimer_queue, preemptible != 0, req, by_queue) ? 1 : 0;
 }
 
 // plugins/minruntime/resolver.go on the loaded snapshot's queue tree: reclaim != 0 -> getReclaimMinRuntime(method of

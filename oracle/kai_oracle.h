@@ -55,6 +55,15 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
                            const double *l_job_req, const double *r_job_req,
                            const double *total);
 
+/* plugins/proportion/reclaimable/reclaimable.go:29-51 CanReclaimResources for one queue: share[3][4] =
+   {Deserved, FairShare, Allocated, AllocatedNotPreemptible} per resource (cpu, memory, gpu), req[3]. */
+int kai_oracle_can_reclaim_resources(const double *share, const double *req, int preemptible);
+/* reclaimable.go:53-232 Reclaimable on an explicit queue tree: share[n_queues][3][5] = the four fields above +
+   MaxAllowed, victims =
+   (leaf queue, resources[3]) in the given order. */
+int kai_oracle_reclaimable(int n_queues, const int32_t *parent, const double *share, double saturation_multiplier,
+                           int reclaimer_queue, int preemptible, const double *req, int n_victims,
+                           const int32_t *victim_queue, const double *victim_res);
 /* plugins/minruntime/resolver.go on the loaded snapshot's queue tree: getReclaimMinRuntime (method of the config)
    for (pending queue, victim queue) when reclaim != 0, else getPreemptMinRuntime(victim queue); -1 = nil queue. */
 double kai_oracle_min_runtime(kai_oracle *o, int reclaim, int pending_queue, int victim_queue);

@@ -457,3 +457,33 @@ def gen_resource_division():
 if __name__ == "__main__":
     print("nodeplacement:", gen_nodeplacement())
     print("resource_division two-queues table:", gen_resource_division())
+
+
+def gen_can_reclaim():
+    """plugins/proportion/reclaimable/reclaimable_test.go:34-531 — the two literal tables of `CanReclaimResources`
+    (preemptible and non-preemptible reclaimer) -> tests/golden/can_reclaim_resources.json."""
+    import re
+    path = os.path.join(REF, "plugins", "proportion", "reclaimable", "reclaimable_test.go")
+    src = open(path).read()
+    blk = src[src.index('var _ = Describe("Can Reclaim Resources"'):src.index('var _ = Describe("Reclaimable - Single department"')]
+    infos = find_literals(blk, "ReclaimerInfo")
+    queues = [q for q in find_literals(blk, "rs.QueueAttributes") if isinstance(q, dict) and "QueueResourceShare" in q]
+    expected = re.findall(r'canReclaim:\s*(true|false)', blk)
+    names = re.findall(r'\bname:\s*"([^"]*)"', blk)
+    assert len(infos) == len(queues) == len(expected) == len(names)
+    out = []
+    for name, info, queue, exp in zip(names, infos, queues, expected):
+        req = [_num(a) for a in info["RequiredResources"]["args"]]  # NewResource(milliCPU, memory, gpus)
+        share = {}
+        for res in ("CPU", "Memory", "GPU"):
+            rs_ = queue["QueueResourceShare"].get(res) or {}
+            share[res] = {k: _num(rs_.get(k, 0)) for k in ("Deserved", "FairShare", "Allocated", "AllocatedNotPreemptible")}
+        out.append({"name": name, "req": req, "preemptible": bool(info.get("IsPreemptable", False)), "share": share,
+                    "can_reclaim": exp == "true"})
+    with open(os.path.join(HERE, "can_reclaim_resources.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return len(out)
+
+
+if __name__ == "__main__":
+    print("can_reclaim_resources:", gen_can_reclaim())
