@@ -224,6 +224,8 @@ double divide_up_to_fair_share(double total, double k, std::vector<QueueAttr> &Q
   return total;
 }
 
+double divide_over_quota_resource(double remaining, double k, std::vector<QueueAttr> &Q, const std::vector<int> &group, int r);
+
 // :33-43 setResourceShare for one sibling group and one resource
 double set_resource_share(double total, double k, std::vector<QueueAttr> &Q, const std::vector<int> &group, int r) {
   // :92-109 setDeservedResource
@@ -237,7 +239,11 @@ double set_resource_share(double total, double k, std::vector<QueueAttr> &Q, con
     remaining -= amount;
   }
   if (!(remaining > 0)) return 0;
-  // :111-144 divideOverQuotaResource; :146-162 getQueuesByPriority (priorities descending)
+  return divide_over_quota_resource(remaining, k, Q, group, r);
+}
+
+// :111-144 divideOverQuotaResource; :146-162 getQueuesByPriority (priorities descending)
+double divide_over_quota_resource(double remaining, double k, std::vector<QueueAttr> &Q, const std::vector<int> &group, int r) {
   std::map<int, std::vector<int>, std::greater<int>> by_prio;
   for (int q : group) by_prio[Q[q].priority].push_back(q);
   std::map<int, std::map<int, double>, std::greater<int>> rem;
@@ -3067,6 +3073,31 @@ double kai_oracle_set_resource_share(int n, double total, double k_value, const 
     group.push_back(i);
   }
   double rem = set_resource_share(total, k_value, Q, group, 0);
+  for (int i = 0; i < n; i++) fair_share[i] = Q[i].s[0].fair;
+  return rem;
+}
+
+// divideOverQuotaResource (resource_division.go:111-144) alone, on FairShare values the caller has set; same arrays
+double kai_oracle_divide_over_quota(int n, double amount, double k_value, const double *deserved, const double *limit,
+                                    const double *oqw, const double *request, const double *usage,
+                                    const int32_t *priority, const int64_t *creation, const int32_t *uid_rank,
+                                    double *fair_share) {
+  std::vector<QueueAttr> Q(n);
+  std::vector<int> group;
+  for (int i = 0; i < n; i++) {
+    Q[i].priority = priority[i];
+    Q[i].creation = creation[i];
+    Q[i].uid_rank = uid_rank[i];
+    Share &s = Q[i].s[0];
+    s.deserved = deserved[i];
+    s.max_allowed = limit[i];
+    s.oqw = oqw[i];
+    s.request = request[i];
+    s.usage = usage ? usage[i] : 0;
+    s.fair = fair_share[i];
+    group.push_back(i);
+  }
+  double rem = divide_over_quota_resource(amount, k_value, Q, group, 0);
   for (int i = 0; i < n; i++) fair_share[i] = Q[i].s[0].fair;
   return rem;
 }

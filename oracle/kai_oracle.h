@@ -45,6 +45,13 @@ double kai_oracle_set_resource_share(int n, double total, double k_value,
                                      const double *usage, const int32_t *priority,
                                      const int64_t *creation, const int32_t *uid_rank,
                                      double *fair_share);
+/* resource_division.go:111-144 divideOverQuotaResource alone (FairShare preset by the caller); same arrays */
+double kai_oracle_divide_over_quota(int n, double amount, double k_value,
+                                    const double *deserved, const double *limit,
+                                    const double *oqw, const double *request,
+                                    const double *usage, const int32_t *priority,
+                                    const int64_t *creation, const int32_t *uid_rank,
+                                    double *fair_share);
 /* plugins/proportion/queue_order/queue_order.go:19-73 for two queues described by
    8-field ResourceShare rows [3][8] = {Deserved,FairShare,MaxAllowed,OverQuotaWeight,
    Allocated,AllocatedNotPreemptible,Request,Usage}; job requirement vectors [3].

@@ -487,3 +487,41 @@ def gen_can_reclaim():
 
 if __name__ == "__main__":
     print("can_reclaim_resources:", gen_can_reclaim())
+
+
+def gen_set_resources_share():
+    """plugins/proportion/resource_division/resource_division_test.go:1111-2020 — the data-driven `SetResourcesShare`
+    table (contexts x cases; three resources per queue) -> tests/golden/set_resources_share.json."""
+    path = os.path.join(REF, "plugins", "proportion", "resource_division", "resource_division_test.go")
+    src = open(path).read()
+    blk = src[src.index('tests := map[string]map[string]struct {'):src.index('for contextName, contextData := range tests')]
+    # give the anonymous struct type a name so that the literal parser sees a typed composite literal
+    blk = 'tests := map[string]map[string]caseT' + blk[blk.index('}{') + 1:]
+    top = find_literals(blk, 'map[string]map[string]caseT')[0]
+    fields = ("Deserved", "FairShare", "OverQuotaWeight", "MaxAllowed", "Allocated", "Request")
+    out = []
+    for ctx, cases in top.items():
+        if ctx.startswith("__"):
+            continue
+        for name, case in cases.items():
+            if name.startswith("__"):
+                continue
+            queues = {}
+            for qid, q in case["queues"].items():
+                if qid.startswith("__"):
+                    continue
+                share = q.get("QueueResourceShare") or {}
+                queues[qid] = {"priority": int(_num(q.get("Priority", 0))),
+                               **{res: {f: _num((share.get(res) or {}).get(f, 0)) for f in fields} for res in ("GPU", "CPU", "Memory")}}
+            total = {k.split(".")[-1]: _num(v) for k, v in case["totalResources"].items() if not k.startswith("__")}
+            expected = {qid: {res: _num(((q.get("QueueResourceShare") or {}).get(res) or {}).get("FairShare", 0))
+                              for res in ("GPU", "CPU", "Memory")}
+                        for qid, q in case["expectedShare"].items() if not qid.startswith("__")}
+            out.append({"context": ctx, "name": name, "queues": queues, "total": total, "expected": expected})
+    with open(os.path.join(HERE, "set_resources_share.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return len(out)
+
+
+if __name__ == "__main__":
+    print("set_resources_share:", gen_set_resources_share())

@@ -64,3 +64,126 @@ def test_set_resource_share_two_queues(case):
     for i, qid in enumerate(ids):
         if qid in case["expected_share"]:
             assert fair[i] == case["expected_share"][qid], f"queue {qid}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# resource_division_test.go:26-223 — the single-queue / two-queue "sanity" contexts (Ginkgo BeforeEach fixture + a
+# mutation per `It`), transcribed by hand: (line, fixture overrides, amount, expected remaining, expected FairShare)
+# ---------------------------------------------------------------------------------------------------------------
+def _division(fn_name, queues, amount, k_value=0.0):
+    n = len(queues)
+    dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+
+    def arr(key, dt=np.float64):
+        return np.array([q[key] for q in queues], dtype=dt)
+
+    deserved, limit, oqw, request, fair = arr("Deserved"), arr("MaxAllowed"), arr("OverQuotaWeight"), arr("Request"), arr("FairShare")
+    usage, prio = np.zeros(n), np.array([q.get("Priority", 100) for q in queues], dtype=np.int32)
+    creation, uid_rank = np.zeros(n, dtype=np.int64), np.arange(n, dtype=np.int32)
+    fn = getattr(lib(), fn_name)
+    fn.argtypes = [C.c_int, C.c_double, C.c_double, dp, dp, dp, dp, dp, ip, lp, ip, dp]
+    fn.restype = C.c_double
+    rem = fn(n, amount, k_value, deserved.ctypes.data_as(dp), limit.ctypes.data_as(dp), oqw.ctypes.data_as(dp),
+             request.ctypes.data_as(dp), usage.ctypes.data_as(dp), prio.ctypes.data_as(ip), creation.ctypes.data_as(lp),
+             uid_rank.ctypes.data_as(ip), fair.ctypes.data_as(dp))
+    return rem, fair.tolist()
+
+
+WITHIN_QUOTA = dict(Deserved=3, FairShare=0, OverQuotaWeight=0, MaxAllowed=-1, Request=2)  # :31-47
+SET_RESOURCE_SHARE_SINGLE = [
+    (50, {}, 2, 0, 2), (55, {}, 3, 1, 2), (60, {"MaxAllowed": 2}, 3, 1, 2), (66, {}, 1, 0, 2), (71, {"Request": 5}, 7, 4, 3),
+    (77, {"Deserved": 1.5}, 2, 0.5, 1.5), (83, {"Request": 1.5}, 2, 0.5, 1.5), (89, {"Deserved": 0}, 2, 2, 0),
+]
+
+
+@pytest.mark.parametrize("line,override,total,remaining,fair", SET_RESOURCE_SHARE_SINGLE, ids=[f"L{c[0]}" for c in SET_RESOURCE_SHARE_SINGLE])
+def test_set_resource_share_single_queue(line, override, total, remaining, fair):
+    rem, got = _division("kai_oracle_set_resource_share", [dict(WITHIN_QUOTA, **override)], total)
+    assert rem == remaining and got == [fair]
+
+
+OVER_QUOTA = dict(Deserved=3, FairShare=3, OverQuotaWeight=1, MaxAllowed=-1, Request=5)  # :102-118
+DIVIDE_OVER_QUOTA_SINGLE = [
+    (121, {}, 2, 0, 5), (126, {}, 3, 1, 5), (131, {"MaxAllowed": 4}, 2, 1, 4), (137, {"OverQuotaWeight": 0}, 2, 2, 3),
+    (143, {"Request": 4.5}, 2, 0.5, 4.5), (149, {}, 0.5, 0, 3.5), (154, {"Deserved": 0, "FairShare": 0}, 6, 1, 5),
+    (161, {}, 0, 0, 3), (167, {"OverQuotaWeight": 0}, 10, 10, 3),
+]
+
+
+@pytest.mark.parametrize("line,override,amount,remaining,fair", DIVIDE_OVER_QUOTA_SINGLE, ids=[f"L{c[0]}" for c in DIVIDE_OVER_QUOTA_SINGLE])
+def test_divide_over_quota_single_queue(line, override, amount, remaining, fair):
+    rem, got = _division("kai_oracle_divide_over_quota", [dict(OVER_QUOTA, **override)], amount)
+    assert rem == remaining and got == [fair]
+
+
+def test_divide_over_quota_two_queues_zero_weight():  # :176-223
+    q1 = dict(OVER_QUOTA, OverQuotaWeight=0)
+    q2 = dict(OVER_QUOTA, Request=3)
+    rem, got = _division("kai_oracle_divide_over_quota", [q1, q2], 10)
+    assert rem == 10 and got[0] == 3
+
+
+# resource_division_test.go:559-697 "three queues / no pre-allocated resources" (CPU; the memory contexts :877-1015
+# repeat the same numbers): (line, per-queue overrides, total, expected FairShare of queues 1..3); remaining is 0
+THREE = dict(Deserved=5000, FairShare=0, OverQuotaWeight=5000, MaxAllowed=-1, Request=5000)  # :564-612
+THREE_QUEUES = [
+    (619, [{}, {}, {}], 10000, [5000, 5000, 5000]),
+    (633, [{"Request": 6000}] * 3, 18000, [6000, 6000, 6000]),
+    (647, [{"Request": 7000}, {"Request": 2000}, {"Request": 2000}], 10000, [6000, 2000, 2000]),
+    (655, [{"Request": 7000}, {"Request": 5000}, {"Request": 2000}], 10000, [5000, 5000, 2000]),
+    (671, [{"Request": 7000, "MaxAllowed": 7000}, {"Request": 2000}, {"Request": 2000}], 10000, [6000, 2000, 2000]),
+    (689, [{}, {"Deserved": 0}, {}], 10000, [5000, 0, 5000]),
+]
+
+
+@pytest.mark.parametrize("line,overrides,total,fair", THREE_QUEUES, ids=[f"L{c[0]}" for c in THREE_QUEUES])
+def test_set_resource_share_three_queues(line, overrides, total, fair):
+    rem, got = _division("kai_oracle_set_resource_share", [dict(THREE, **o) for o in overrides], total)
+    assert rem == 0 and got == fair
+
+
+# :699-787 "all resources allocated between 2 queues": the same fixture with Allocated = 5000 on queues 1 and 2 —
+# Allocated does not enter the division (GetRequestableShare, resource_share.go:40-45), so only the numbers are kept.
+# None = the reference does not assert that queue.
+THREE_QUEUES_ALLOCATED = [
+    (706, [{}, {}, {}], [5000, 5000, 5000]),
+    (720, [{"Request": 7000}, {"Request": 2000}, {"Request": 2000}], [6000, 2000, 2000]),
+    (727, [{"Request": 7000}, {"Request": 5000}, {"Request": 2000}], [5000, 5000, 2000]),
+    (743, [{"Request": 7000, "MaxAllowed": 7000}, {"Request": 2000}, {"Request": 2000}], [6000, 2000, 2000]),
+    (750, [{"Request": 7000, "MaxAllowed": 7000}, {"Request": 5000}, {"Request": 2000}], [5000, 5000, 2000]),
+    (773, [{"Request": 10000}, {"Deserved": 0}, {"Request": 10000}], [5000, None, 5000]),
+    (780, [{}, {"Deserved": 0}, {}], [5000, None, 5000]),
+]
+
+
+@pytest.mark.parametrize("line,overrides,fair", THREE_QUEUES_ALLOCATED, ids=[f"L{c[0]}" for c in THREE_QUEUES_ALLOCATED])
+def test_set_resource_share_three_queues_allocated(line, overrides, fair):
+    rem, got = _division("kai_oracle_set_resource_share", [dict(THREE, **o) for o in overrides], 10000)
+    assert rem == 0
+    for g, w in zip(got, fair):
+        assert w is None or g == w
+
+
+# resource_division_test.go:1111-2020 — the data-driven SetResourcesShare table (10 cases over 4 contexts, three
+# resources per queue), transcribed mechanically into tests/golden/set_resources_share.json
+SET_RESOURCES_SHARE = json.load(open(os.path.join(GOLDEN, "set_resources_share.json")))
+
+
+@pytest.mark.parametrize("case", SET_RESOURCES_SHARE, ids=[f"{c['context']}: {c['name']}" for c in SET_RESOURCES_SHARE])
+def test_set_resources_share_table(case):
+    ids = sorted(case["queues"])
+    total_key = {"GPU": "GpuResource", "CPU": "CpuResource", "Memory": "MemoryResource"}
+    for res in ("GPU", "CPU", "Memory"):
+        queues = [dict(case["queues"][i][res], Priority=case["queues"][i]["priority"]) for i in ids]
+        rem, got = _division("kai_oracle_set_resource_share", queues, case["total"].get(total_key[res], 0.0))
+        for i, qid in enumerate(ids):
+            if qid in case["expected"]:
+                assert got[i] == case["expected"][qid][res], f"{res} share of queue {qid}"
+
+
+def test_divides_the_remainder_even_when_using_priorities():  # resource_division_test.go:401-470
+    base = dict(FairShare=0, OverQuotaWeight=2, MaxAllowed=-1)
+    queues = [dict(base, Deserved=2, Request=5, Priority=2), dict(base, Deserved=2, Request=5, Priority=2),
+              dict(base, Deserved=1, Request=0, Priority=1)]
+    rem, got = _division("kai_oracle_set_resource_share", queues, 5)
+    assert rem == 0.0 and got == [3, 2, 0]
