@@ -187,3 +187,40 @@ def test_divides_the_remainder_even_when_using_priorities():  # resource_divisio
               dict(base, Deserved=1, Request=0, Priority=1)]
     rem, got = _division("kai_oracle_set_resource_share", queues, 5)
     assert rem == 0.0 and got == [3, 2, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# queue_order_test.go:44-300 TestGetQueueOrderResult (6 cases), transcribed by hand.  A row is the 8-field
+# ResourceShare {Deserved, FairShare, MaxAllowed, OverQuotaWeight, Allocated, AllocatedNotPreemptible, Request, Usage};
+# CPU and memory rows are zero-valued.  The two GPU-memory cases ask for `devices x gpuMemory / minNodeGPUMemory`
+# GPUs (GetTasksToAllocateInitResource with minNodeGPUMemory = 10000): 2 x 0.5 vs 2 x 1.0, and 4 x 0.8 vs 4 x 0.2.
+# ---------------------------------------------------------------------------------------------------------------
+def _gpu_row(deserved, fair, allocated, request):
+    return [deserved, fair, -1, 1, allocated, 0, request, 0]
+
+
+L_FIRST, R_FIRST = -1, 1
+QUEUE_ORDER = [
+    ("fair share starvation", _gpu_row(2, 99, 20, 99), _gpu_row(2, 2, 0, 2), 0, 0, 0, 0, 0, R_FIRST),
+    ("quota starvation beats priority", _gpu_row(2, 99, 20, 99), _gpu_row(2, 2, 0, 2), 1, 0, 0, 0, 0, R_FIRST),
+    ("priority when both are satisfied", _gpu_row(2, 99, 20, 99), _gpu_row(2, 2, 3, 99), 1, 0, 0, 0, 0, L_FIRST),
+    ("priority, quota < rQueue < fair share", _gpu_row(2, 99, 20, 99), _gpu_row(2, 80, 3, 99), 1, 0, 0, 0, 0, L_FIRST),
+    ("lower GPU-memory request first", _gpu_row(50, 50, 40, 50), _gpu_row(50, 50, 40, 50), 0, 0, 1.0, 2.0, 100, L_FIRST),
+    ("higher GPU-memory request later", _gpu_row(50, 50, 40, 50), _gpu_row(50, 50, 40, 50), 0, 0, 3.2, 0.8, 100, R_FIRST),
+]
+
+
+@pytest.mark.parametrize("name,l_gpu,r_gpu,l_prio,r_prio,l_req,r_req,total_gpu,expected", QUEUE_ORDER, ids=[c[0] for c in QUEUE_ORDER])
+def test_queue_order_result(name, l_gpu, r_gpu, l_prio, r_prio, l_req, r_req, total_gpu, expected):
+    dp = C.POINTER(C.c_double)
+
+    def rows(gpu):
+        a = np.zeros((3, 8))
+        a[2] = gpu
+        return a
+
+    l, r = rows(l_gpu), rows(r_gpu)
+    lreq, rreq, total = np.array([0.0, 0.0, l_req]), np.array([0.0, 0.0, r_req]), np.array([0.0, 0.0, float(total_gpu)])
+    got = lib().kai_oracle_queue_order(l.ctypes.data_as(dp), r.ctypes.data_as(dp), l_prio, r_prio, 0, 0,
+                                       lreq.ctypes.data_as(dp), rreq.ctypes.data_as(dp), total.ctypes.data_as(dp))
+    assert got == expected
