@@ -309,3 +309,18 @@ def test_fractional_gpu_requests_are_refused_gpu():
     with pytest.raises(EngineError, match="fractional GPU"):
         e.load(snap)
     e.close()
+
+
+def test_job_order_unit_cases_gpu():
+    """The pop orders of actions/utils/job_order_by_queue_test.go (tests/test_job_order_units.py) on the engine: the
+    visiting order of an allocate run where nothing fits, against the oracle and the reference's expected order."""
+    import test_job_order_units as ju
+    cases = [(c[1], c[2], c[3]) for c in ju.HIERARCHY]
+    cases.append(({"test-queue": "test-parent", "test-parent": ""},
+                  [("p150", 150, "test-queue"), ("p255", 255, "test-queue"), ("p160", 160, "test-queue"), ("p200", 200, "test-queue")],
+                  ["p255", "p200", "p160", "p150"]))
+    for queues, jobs, expected in cases:
+        snap = ju.order_snapshot(queues, jobs)
+        re_, ro = run_both(snap)
+        assert_same(re_, ro)
+        assert [jobs[int(j)][0] for j, _ in re_.visits] == expected

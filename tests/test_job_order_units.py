@@ -1,0 +1,84 @@
+"""JobsOrderByQueues (actions/utils/job_order_by_queue.go) + the job / queue comparators, pinned on the reference's own
+unit tests (CPU): the pop order of actions/utils/job_order_by_queue_test.go, observed as the visiting order of an
+`allocate` run on a cluster where nothing fits (a failed attempt changes no queue state, so visits = pops).
+
+The reference's sessions there register priority + elastic JobOrderFns and no queue-order plugin: queues fall back to
+(CreationTimestamp, UID) with all timestamps equal (framework/session_plugins.go:284-299).  On the production path the
+proportion plugin is registered and its last resort is creation time alone, "not before" meaning the right-hand queue
+(queue_order.go:235-240) — for equal timestamps that is not an order at all and the pop order is heap mechanics.  The
+cases are therefore run with distinct creation times that follow the UID order: both comparators then give the order
+the reference's tests expect, and every share comparison before that ties because nothing has any resources.
+"""
+import numpy as np
+import pytest
+
+from kai_scheduler_b200 import abi
+from oracle_lib import Oracle
+
+
+def order_snapshot(queues: dict, jobs: list):
+    """queues: name -> parent name ("" = top level); jobs: (name, priority, queue[, creation rank])."""
+    qnames = list(queues)
+    qi = {n: i for i, n in enumerate(qnames)}
+    Q, J = len(qnames), len(jobs)
+    uid_rank = np.argsort(np.argsort(np.array(qnames, dtype=object))).astype(np.int32)
+    # JobOrderFn ends with (CreationTimestamp, UID): the tests leave both unset, jobs of one queue differ by priority
+    job_rank = np.array([j[3] if len(j) > 3 else i for i, j in enumerate(jobs)], dtype=np.int32)
+    zeros = np.zeros((4, 1))
+    snap = abi.Snapshot(
+        n_res=4, node_allocatable=zeros.copy(), node_idle=zeros.copy(), node_releasing=zeros.copy(),
+        node_name_rank=np.zeros(1, dtype=np.int32), node_flags=np.full(1, abi.NODE_READY, dtype=np.uint32),
+        queue_parent=np.array([qi.get(queues[n], -1) for n in qnames], dtype=np.int32),
+        queue_priority=np.full(Q, 100, dtype=np.int32), queue_creation=uid_rank.astype(np.int64), queue_uid_rank=uid_rank,
+        queue_deserved=np.full((3, Q), -1.0), queue_limit=np.full((3, Q), -1.0), queue_oqw=np.ones((3, Q)),
+        job_queue=np.array([qi[j[2]] for j in jobs], dtype=np.int32), job_priority=np.array([j[1] for j in jobs], dtype=np.int32),
+        job_order_rank=job_rank, job_flags=np.full(J, abi.JOB_PREEMPTIBLE, dtype=np.uint32),
+        job_podset_begin=np.arange(J + 1, dtype=np.int32), podset_min_available=np.ones(J, dtype=np.int32),
+        podset_task_begin=np.arange(J + 1, dtype=np.int32), task_status=np.full(J, abi.POD_PENDING, dtype=np.int32),
+        task_node=np.full(J, -1, dtype=np.int32), task_req=np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (J, 1)),
+        task_order_rank=np.zeros(J, dtype=np.int32))
+    return snap
+
+
+def pop_order(queues, jobs):
+    o = Oracle()
+    o.load(order_snapshot(queues, jobs))
+    res = o.run("allocate")
+    assert res.pods_placed == 0
+    return [jobs[int(j)][0] for j, _ in res.visits]
+
+
+def test_numerical_priority_within_same_queue():  # job_order_by_queue_test.go:42-144
+    queues = {"test-queue": "test-parent", "test-parent": ""}
+    jobs = [("p150", 150, "test-queue"), ("p255", 255, "test-queue"), ("p160", 160, "test-queue"), ("p200", 200, "test-queue")]
+    assert pop_order(queues, jobs) == ["p255", "p200", "p160", "p150"]
+
+
+HIERARCHY = [  # TestNLevelQueueHierarchy, job_order_by_queue_test.go:798-975 (push-job cases initialise the same tree)
+    ("three level hierarchy", {"root": "", "dept1": "root", "dept2": "root", "team1": "dept1", "team2": "dept1", "team3": "dept2"},
+     [("job1-team1-p100", 100, "team1"), ("job2-team2-p200", 200, "team2"), ("job3-team3-p150", 150, "team3"),
+      ("job4-team1-p250", 250, "team1")],
+     ["job4-team1-p250", "job1-team1-p100", "job2-team2-p200", "job3-team3-p150"]),
+    ("four level hierarchy", {"org": "", "div1": "org", "dept1": "div1", "team1": "dept1"}, [("deep-job", 100, "team1")], ["deep-job"]),
+    ("single level hierarchy", {"default": ""}, [("job1-default-p100", 100, "default"), ("job2-default-p200", 200, "default")],
+     ["job2-default-p200", "job1-default-p100"]),
+    ("two level hierarchy", {"root": "", "leaf1": "root", "leaf2": "root"},
+     [("job1-leaf1-p100", 100, "leaf1"), ("job2-leaf2-p200", 200, "leaf2")], ["job1-leaf1-p100", "job2-leaf2-p200"]),
+    ("mixed depth hierarchy", {"root": "", "leaf1": "root", "dept": "root", "team": "dept"},
+     [("job1-shallow-p150", 150, "leaf1"), ("job2-deep-p200", 200, "team")], ["job2-deep-p200", "job1-shallow-p150"]),
+    ("multiple root queues", {"root1": "", "leaf1": "root1", "root2": "", "leaf2": "root2"},
+     [("job1-root1-p100", 100, "leaf1"), ("job2-root2-p200", 200, "leaf2")], ["job1-root1-p100", "job2-root2-p200"]),
+    ("multiple single level root queues", {"queue-a": "", "queue-b": "", "queue-c": ""},
+     [("job-a-p100", 100, "queue-a"), ("job-b-p300", 300, "queue-b"), ("job-c-p200", 200, "queue-c")],
+     ["job-a-p100", "job-b-p300", "job-c-p200"]),
+    ("push job builds n-level tree", {"root": "", "dept": "root", "team": "dept"},
+     [("job1-p100", 100, "team"), ("job2-p200", 200, "team")], ["job2-p200", "job1-p100"]),
+    ("push job to single level queue", {"default": ""}, [("pushed-job", 100, "default")], ["pushed-job"]),
+    ("tree cleanup after all jobs popped", {"root": "", "dept1": "root", "dept2": "root", "team1": "dept1", "team2": "dept2"},
+     [("job1-team1", 200, "team1"), ("job2-team2", 100, "team2")], ["job1-team1", "job2-team2"]),
+]
+
+
+@pytest.mark.parametrize("name,queues,jobs,expected", HIERARCHY, ids=[c[0] for c in HIERARCHY])
+def test_n_level_queue_hierarchy(name, queues, jobs, expected):
+    assert pop_order(queues, jobs) == expected
