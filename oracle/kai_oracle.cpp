@@ -3102,6 +3102,21 @@ double kai_oracle_divide_over_quota(int n, double amount, double k_value, const 
   return rem;
 }
 
+// podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in
+// attempt order; real_allocation = the isRealAllocation argument; virtual_mask = tasks whose Releasing status is virtual
+int kai_oracle_tasks_to_allocate(kai_oracle *o, int job, int real_allocation, int32_t *out, int cap) {
+  if (!o || job < 0 || job >= o->NJ) return -1;
+  o->vcache(job).tta_valid = false;
+  const std::vector<int> &t = o->tasks_to_allocate(job, real_allocation != 0);
+  for (size_t i = 0; i < t.size() && (int)i < cap; i++) out[i] = t[i];
+  return (int)t.size();
+}
+int kai_oracle_set_task_virtual(kai_oracle *o, int task, int is_virtual) {  // PodInfo.IsVirtualStatus
+  if (!o || task < 0 || task >= o->NT) return -1;
+  o->T[task].is_virtual = is_virtual != 0;
+  return 0;
+}
+
 // plugins/proportion/reclaimable/reclaimable.go on an explicit queue table (unit-level entry points for the reference's
 // reclaimable_test.go).  share[q][r][5] = {Deserved, FairShare, Allocated, AllocatedNotPreemptible, MaxAllowed}, r in KAI_Q_*.
 static void fill_queue_table(kai_oracle &o, int n, const int32_t *parent, const double *share, double saturation_multiplier) {

@@ -62,6 +62,10 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
                            const double *l_job_req, const double *r_job_req,
                            const double *total);
 
+/* podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in attempt
+   order (returns the count); kai_oracle_set_task_virtual sets PodInfo.IsVirtualStatus of a task first if needed. */
+int kai_oracle_tasks_to_allocate(kai_oracle *o, int job, int real_allocation, int32_t *out, int cap);
+int kai_oracle_set_task_virtual(kai_oracle *o, int task, int is_virtual);
 /* plugins/proportion/reclaimable/reclaimable.go:29-51 CanReclaimResources for one queue: share[3][4] =
    {Deserved, FairShare, Allocated, AllocatedNotPreemptible} per resource (cpu, memory, gpu), req[3]. */
 int kai_oracle_can_reclaim_resources(const double *share, const double *req, int preemptible);
