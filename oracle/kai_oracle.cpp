@@ -1994,8 +1994,12 @@ struct kai_oracle {
     std::sort(req.begin(), req.end(), std::greater<double>());
     std::vector<double> cap;
     for (auto it = f.sorted.begin(); it != f.sorted.end() && (int)cap.size() < f.k; ++it) cap.push_back(*it);
+    return greedy_match_requirements(req, cap);
+  }
+  // idle_gpus/common.go:34-64 greedyMatchRequirements: requirements and holder capacities both sorted descending
+  static bool greedy_match_requirements(const std::vector<double> &req, const std::vector<double> &cap) {
     std::vector<double> used(cap.size(), 0.0);
-    for (double required : req) {  // common.go:34-64 greedyMatchRequirements
+    for (double required : req) {
       if (required == 0) return true;
       bool matched = false;
       for (size_t h = 0; h < cap.size(); h++) {
@@ -3100,6 +3104,11 @@ double kai_oracle_divide_over_quota(int n, double amount, double k_value, const 
   double rem = divide_over_quota_resource(amount, k_value, Q, group, 0);
   for (int i = 0; i < n; i++) fair_share[i] = Q[i].s[0].fair;
   return rem;
+}
+
+// idle_gpus/common.go:34-64 greedyMatchRequirements (both arrays sorted descending by the caller)
+int kai_oracle_greedy_match(int n_req, const double *req, int n_holders, const double *capacity) {
+  return kai_oracle::greedy_match_requirements(std::vector<double>(req, req + n_req), std::vector<double>(capacity, capacity + n_holders)) ? 1 : 0;
 }
 
 // podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in

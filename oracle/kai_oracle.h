@@ -62,6 +62,8 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
                            const double *l_job_req, const double *r_job_req,
                            const double *total);
 
+/* accumulated_scenario_filters/idle_gpus/common.go:34-64 greedyMatchRequirements; both arrays sorted descending */
+int kai_oracle_greedy_match(int n_req, const double *req, int n_holders, const double *capacity);
 /* podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in attempt
    order (returns the count); kai_oracle_set_task_virtual sets PodInfo.IsVirtualStatus of a task first if needed. */
 int kai_oracle_tasks_to_allocate(kai_oracle *o, int job, int real_allocation, int32_t *out, int cap);

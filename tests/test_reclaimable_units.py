@@ -169,3 +169,28 @@ def test_multiple_hierarchy_levels():
     q["d1"]["CPU"] = [0, 1000, 3000, 0, 0]
     q["d2"]["CPU"] = [0, 1000, 1000, 0, 0]
     assert reclaimable(q, "d1-project-1", [("d2-project-1", 1.0)]) is True
+
+
+# ------------------------------------------------------------------------------------------------- idle-GPU filter
+# accumulated_scenario_filters/idle_gpus/idle_gpus_test.go:106-199 Test_greedyMatchRequirements: (requirements,
+# holder capacities in the holders' order, want)
+GREEDY = [
+    ("empty requirements always match", [], [1.0], True),
+    ("zero requirements are skipped", [0, 0], [], True),
+    ("single requirement matched to holder", [0.5], [1.0], True),
+    ("single requirement exceeds holder capacity", [0.5], [0.0], False),
+    ("virtual allocation prevents double-use of same holder", [1.0, 0.5], [1.0], False),
+    ("bin-packing: two requirements fit in one holder", [1.0, 0.5], [1.5], True),
+    ("second holder used after first is saturated", [1.0, 1.0], [2.0, 1.0], True),
+    ("early termination: best holder below requirement", [2.0], [1.0], False),
+]
+
+
+@pytest.mark.parametrize("name,req,cap,want", GREEDY, ids=[c[0] for c in GREEDY])
+def test_greedy_match_requirements(name, req, cap, want):
+    l = lib()
+    dp = C.POINTER(C.c_double)
+    l.kai_oracle_greedy_match.argtypes = [C.c_int, dp, C.c_int, dp]
+    _r, pr = _dp(req if req else [0.0])
+    _c, pc = _dp(cap if cap else [0.0])
+    assert bool(l.kai_oracle_greedy_match(len(req), pr, len(cap), pc)) == want
