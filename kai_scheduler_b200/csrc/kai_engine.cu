@@ -327,16 +327,36 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     }
     for (int q = 0; q < Q; q++) q_job_begin[q + 1] = q_job_begin[q] + cnt[q];
     std::vector<int> fill(q_job_begin.begin(), q_job_begin.end() - 1);
-    for (int j = 0; j < J; j++) {
+    // job_order_rank is a rank (a permutation of 0..J-1) in every well-formed snapshot: walk the jobs in rank order so
+    // that each queue's list is already ordered by rank, then only a stable pass on priority is left (a no-op when the
+    // priorities of a queue are already non-increasing, the common case).  Anything else falls back to a full sort.
+    std::vector<int> by_rank(std::max(J, 1), -1);
+    bool ranks_are_a_permutation = true;
+    for (int j = 0; j < J && ranks_are_a_permutation; j++) {
+      int rk = s->job_order_rank[j];
+      if (rk < 0 || rk >= J || by_rank[rk] != -1)
+        ranks_are_a_permutation = false;
+      else
+        by_rank[rk] = j;
+    }
+    for (int k = 0; k < J; k++) {
+      int j = ranks_are_a_permutation ? by_rank[k] : k;
       int q = s->job_queue[j];
       if (q < 0 || q_nchildren[q] != 0) continue;
       q_jobs_sorted[fill[q]++] = j;
     }
-    for (int q = 0; q < Q; q++)
-      std::sort(q_jobs_sorted.begin() + q_job_begin[q], q_jobs_sorted.begin() + q_job_begin[q + 1], [&](int a, int b) {
-        if (s->job_priority[a] != s->job_priority[b]) return s->job_priority[a] > s->job_priority[b];
-        return s->job_order_rank[a] < s->job_order_rank[b];
-      });
+    auto by_priority = [&](int a, int b) { return s->job_priority[a] > s->job_priority[b]; };
+    for (int q = 0; q < Q; q++) {
+      auto b = q_jobs_sorted.begin() + q_job_begin[q], en = q_jobs_sorted.begin() + q_job_begin[q + 1];
+      if (ranks_are_a_permutation) {
+        if (!std::is_sorted(b, en, by_priority)) std::stable_sort(b, en, by_priority);
+      } else {
+        std::sort(b, en, [&](int a, int b2) {
+          if (s->job_priority[a] != s->job_priority[b2]) return s->job_priority[a] > s->job_priority[b2];
+          return s->job_order_rank[a] < s->job_order_rank[b2];
+        });
+      }
+    }
   }
   // podsets / tasks
   // device task i = caller task perm[i]: the tasks of a podset are renumbered into TaskOrderFn order so that
