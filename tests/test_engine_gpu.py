@@ -324,3 +324,24 @@ def test_job_order_unit_cases_gpu():
         re_, ro = run_both(snap)
         assert_same(re_, ro)
         assert [jobs[int(j)][0] for j, _ in re_.visits] == expected
+
+
+@pytest.mark.parametrize("k_value", [0.5, 2.0])
+def test_historical_usage_and_k_value(k_value):
+    """Time-based fair share inputs: per-queue historical usage and the proportion plugin's kValue
+    enter calcShareWeights (resource_division.go:224-251); over-subscribed queues so that the over-quota split decides
+    who gets placed."""
+    snap = synthetic.benchmark_snapshot(n_nodes=48, n_jobs=700, tasks_per_job=1, n_queues=8)
+    rng = np.random.default_rng(11)
+    Q = snap.n_queues
+    snap.queue_usage = rng.choice(np.array([0.0, 0.05, 0.125, 0.25, 0.5]), size=(3, Q))
+    snap.queue_deserved = snap.queue_deserved.copy()
+    snap.queue_deserved[2, :8] = 16.0  # 8 leaf queues x 16 deserved GPUs < 384 GPUs: the rest is over-quota share
+    cfg = abi.make_config(k_value=k_value)
+    re_, ro = run_both(snap, cfg=cfg)
+    assert_same(re_, ro)
+    plain = Oracle(abi.make_config())
+    snap2 = synthetic.benchmark_snapshot(n_nodes=48, n_jobs=700, tasks_per_job=1, n_queues=8)
+    snap2.queue_deserved = snap.queue_deserved
+    plain.load(snap2)
+    assert not np.array_equal(plain.run("allocate").queue_fair_share, ro.queue_fair_share)  # usage is not vacuous
