@@ -2061,22 +2061,30 @@ struct kai_oracle {
     return true;
   }
   // strategies/strategies.go:18-91
-  bool fits_reclaim_strategy(const std::vector<QueueAttr> &QS, const double *reclaimer_req, int reclaimer_q,
-                             int reclaimee_q, const double *remaining) {
-    double allocatable[QR], deserved[QR];
+  // strategies/strategies.go:42-57 MaintainFairShareStrategy.Reclaimable
+  static bool maintain_fair_share(const QueueAttr &reclaimee, const double *remaining) {
+    double allocatable[QR];
+    for (int r = 0; r < QR; r++) allocatable[r] = allocatable_share(reclaimee.s[r]);
+    return !quant_le(remaining, allocatable);
+  }
+  // strategies/strategies.go:59-91 GuaranteeDeservedQuotaStrategy.Reclaimable + reclaimerWillGoOverQuota
+  static bool guarantee_deserved_quota(const QueueAttr &reclaimer, const QueueAttr &reclaimee, const double *reclaimer_req,
+                                       const double *remaining) {
+    double want[QR], rdes[QR], deserved[QR];
     for (int r = 0; r < QR; r++) {
-      allocatable[r] = allocatable_share(QS[reclaimee_q].s[r]);
-      deserved[r] = QS[reclaimee_q].s[r].deserved;
-    }
-    if (!quant_le(remaining, allocatable)) return true;  // MaintainFairShareStrategy
-    double want[QR], rdes[QR];                           // GuaranteeDeservedQuotaStrategy
-    for (int r = 0; r < QR; r++) {
-      want[r] = QS[reclaimer_q].s[r].allocated + reclaimer_req[r];
-      rdes[r] = QS[reclaimer_q].s[r].deserved;
+      want[r] = reclaimer.s[r].allocated + reclaimer_req[r];
+      rdes[r] = reclaimer.s[r].deserved;
+      deserved[r] = reclaimee.s[r].deserved;
     }
     if (!quant_le(want, rdes)) return false;
     if (quant_le(remaining, deserved)) return false;
     return true;
+  }
+  // strategies/strategies.go:15-30 FitsReclaimStrategy: any strategy accepts
+  bool fits_reclaim_strategy(const std::vector<QueueAttr> &QS, const double *reclaimer_req, int reclaimer_q,
+                             int reclaimee_q, const double *remaining) {
+    return maintain_fair_share(QS[reclaimee_q], remaining) ||
+           guarantee_deserved_quota(QS[reclaimer_q], QS[reclaimee_q], reclaimer_req, remaining);
   }
   static double saturation_ratio(double allocated, double fair) {  // reclaimable.go:222-232
     if (fair == 0) return allocated > 0 ? INFINITY : 0.0;
@@ -3155,6 +3163,27 @@ int kai_oracle_can_reclaim_resources(const double *share, const double *req, int
   }
   return kai_oracle::can_reclaim_from_share(q, req, preemptible != 0) ? 1 : 0;
 }
+// strategies.go: one reclaim strategy on two queue rows (share[3][5] each, as above) and a remaining share[3];
+// strategy 0 = MaintainFairShareStrategy, 1 = GuaranteeDeservedQuotaStrategy
+int kai_oracle_reclaim_strategy(int strategy, const double *reclaimer_share, const double *reclaimee_share,
+                                const double *reclaimer_req, const double *remaining) {
+  QueueAttr er, ee;
+  for (int r = 0; r < QR; r++)
+    for (int side = 0; side < 2; side++) {
+      const double *x = (side ? reclaimee_share : reclaimer_share) + (size_t)r * 5;
+      Share &sh = (side ? ee : er).s[r];
+      sh.deserved = x[0];
+      sh.fair = x[1];
+      sh.allocated = x[2];
+      sh.alloc_np = x[3];
+      sh.max_allowed = x[4];
+    }
+  return (strategy == 0 ? kai_oracle::maintain_fair_share(ee, remaining)
+                        : kai_oracle::guarantee_deserved_quota(er, ee, reclaimer_req, remaining))
+             ? 1
+             : 0;
+}
+
 // Reclaimable.Reclaimable (reclaimable.go:53-232): victims = (leaf queue, resources[3]) in the order given
 int kai_oracle_reclaimable(int n_queues, const int32_t *parent, const double *share, double saturation_multiplier,
                            int reclaimer_queue, int preemptible, const double *req, int n_victims,

@@ -354,7 +354,8 @@ def _num(x, env=None):
         if "__ident" in x:
             name = x["__ident"]
             table = {"scores.MaxHighDensity": 9.0, "commonconstants.UnlimitedResourceQuantity": -1.0,
-                     "constants.UnlimitedResourceQuantity": -1.0}
+                     "constants.UnlimitedResourceQuantity": -1.0,
+                     "resource_info.MinMemory": 10.0 * 1024 * 1024}  # api/resource_info/base_resources.go:18
             if name in table:
                 return table[name]
             if name in env:
@@ -525,3 +526,43 @@ def gen_set_resources_share():
 
 if __name__ == "__main__":
     print("set_resources_share:", gen_set_resources_share())
+
+
+def gen_reclaim_strategies():
+    """plugins/proportion/reclaimable/strategies/strategies_test.go:22-806 — the three literal tables (MaintainFairShare,
+    MaintainFairShare multi-resource, GuaranteeDeservedQuota) -> tests/golden/reclaim_strategies.json."""
+    path = os.path.join(REF, "plugins", "proportion", "reclaimable", "strategies", "strategies_test.go")
+    src = open(path).read()
+    fields = ("Deserved", "FairShare", "Allocated", "AllocatedNotPreemptible", "MaxAllowed")
+
+    def queue(q):
+        share = (q or {}).get("QueueResourceShare") or {}
+        return {res: {f: _num((share.get(res) or {}).get(f, 0)) for f in fields} for res in ("CPU", "Memory", "GPU")}
+
+    out = []
+    pos = 0
+    for ctx in ("Maintain Fair Share Strategy", "Maintain Fair Share Strategy - Multi Resource", "Guarantee Deserved Quota Strategy"):
+        a = src.index(f'Context("{ctx}"', pos)
+        a = src.index("tests := map[string]struct {", a)
+        b = src.index("strategy := &", a)
+        pos = b
+        blk = src[a:b]
+        blk = "tests := map[string]caseT" + blk[blk.index("}{") + 1:]
+        table = find_literals(blk, "map[string]caseT")[0]
+        for name, case in table.items():
+            if name.startswith("__"):
+                continue
+            rec = {"context": ctx, "name": name, "reclaimer": queue(case.get("reclaimerQueue")),
+                   "reclaimee": queue(case.get("reclaimeeQueue")), "expected": bool(case["expected"])}
+            if case.get("remainingResourceShare") is not None:
+                rec["remaining"] = {k.split(".")[-1]: _num(v) for k, v in case["remainingResourceShare"].items() if not k.startswith("__")}
+            if case.get("reclaimerResources") is not None:
+                rec["reclaimer_req"] = [_num(x) for x in case["reclaimerResources"]["args"]]
+            out.append(rec)
+    with open(os.path.join(HERE, "reclaim_strategies.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return len(out)
+
+
+if __name__ == "__main__":
+    print("reclaim_strategies:", gen_reclaim_strategies())

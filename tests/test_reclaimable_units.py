@@ -194,3 +194,32 @@ def test_greedy_match_requirements(name, req, cap, want):
     _r, pr = _dp(req if req else [0.0])
     _c, pc = _dp(cap if cap else [0.0])
     assert bool(l.kai_oracle_greedy_match(len(req), pr, len(cap), pc)) == want
+
+
+# ------------------------------------------------------------------------------------------------- reclaim strategies
+# strategies_test.go:22-806: three literal tables, transcribed mechanically (tests/golden/reclaim_strategies.json).
+# Where the Go test passes `reclaimeeQueue.GetAllocatedShare()` as the remaining share, that is the Allocated column.
+STRATEGIES = json.load(open(os.path.join(GOLDEN, "reclaim_strategies.json")))
+FIELDS5 = ("Deserved", "FairShare", "Allocated", "AllocatedNotPreemptible", "MaxAllowed")
+
+
+@pytest.mark.parametrize("case", STRATEGIES, ids=[f"{c['context']}: {c['name']}" for c in STRATEGIES])
+def test_reclaim_strategies(case):
+    l = lib()
+    dp = C.POINTER(C.c_double)
+    l.kai_oracle_reclaim_strategy.argtypes = [C.c_int, dp, dp, dp, dp]
+    rows = lambda q: [[q[r][f] for f in FIELDS5] for r in RES]  # noqa: E731
+    _a, pa = _dp(rows(case["reclaimer"]))
+    _b, pb = _dp(rows(case["reclaimee"]))
+    _q, pq = _dp(case.get("reclaimer_req", [0.0, 0.0, 0.0]))
+    if "remaining" in case:
+        remaining = [case["remaining"].get(k, 0.0) for k in ("CpuResource", "MemoryResource", "GpuResource")]
+    else:
+        remaining = [case["reclaimee"][r]["Allocated"] for r in RES]
+    _m, pm = _dp(remaining)
+    strategy = 1 if case["context"].startswith("Guarantee") else 0
+    assert bool(l.kai_oracle_reclaim_strategy(strategy, pa, pb, pq, pm)) == case["expected"]
+
+
+def test_reclaim_strategy_tables_are_complete():
+    assert len(STRATEGIES) == 24
