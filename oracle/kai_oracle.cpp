@@ -3163,6 +3163,20 @@ int kai_oracle_can_reclaim_resources(const double *share, const double *req, int
   }
   return kai_oracle::can_reclaim_from_share(q, req, preemptible != 0) ? 1 : 0;
 }
+// capacity_policy.go:26-84 on an explicit queue tree (share[q][3][5] as above): mode 0 = resultsOverLimit +
+// resultsWithNonPreemptibleOverQuota (IsJobOverQueueCapacity / IsTaskAllocationOnNodeOverCapacity), mode 1 = the quota
+// check alone (IsNonPreemptibleJobOverQuota); returns IsSchedulable
+int kai_oracle_capacity_schedulable(int n_queues, const int32_t *parent, const double *share, int queue, int preemptible,
+                                    const double *req, int mode) {
+  kai_oracle o;
+  fill_queue_table(o, n_queues, parent, share, 1.0);
+  o.NJ = 1;
+  o.J.assign(1, Job());
+  o.J[0].queue = queue;
+  o.J[0].preemptible = preemptible != 0;
+  return (mode == 0 ? o.over_capacity(0, req) : o.non_preemptible_over_quota(0, req)) ? 0 : 1;
+}
+
 // strategies.go: one reclaim strategy on two queue rows (share[3][5] each, as above) and a remaining share[3];
 // strategy 0 = MaintainFairShareStrategy, 1 = GuaranteeDeservedQuotaStrategy
 int kai_oracle_reclaim_strategy(int strategy, const double *reclaimer_share, const double *reclaimee_share,

@@ -71,6 +71,10 @@ int kai_oracle_set_task_virtual(kai_oracle *o, int task, int is_virtual);
 /* plugins/proportion/reclaimable/reclaimable.go:29-51 CanReclaimResources for one queue: share[3][4] =
    {Deserved, FairShare, Allocated, AllocatedNotPreemptible} per resource (cpu, memory, gpu), req[3]. */
 int kai_oracle_can_reclaim_resources(const double *share, const double *req, int preemptible);
+/* capacity_policy.go:26-84 on an explicit queue tree (share[n_queues][3][5] as for kai_oracle_reclaimable): mode 0 =
+   limit + non-preemptible quota checks, mode 1 = the quota check alone; returns IsSchedulable. */
+int kai_oracle_capacity_schedulable(int n_queues, const int32_t *parent, const double *share, int queue, int preemptible,
+                                    const double *req, int mode);
 /* reclaimable/strategies/strategies.go: strategy 0 = MaintainFairShareStrategy (:42-57), 1 = GuaranteeDeservedQuota
    (:59-91) on two queue rows share[3][5] = {Deserved, FairShare, Allocated, AllocatedNotPreemptible, MaxAllowed}. */
 int kai_oracle_reclaim_strategy(int strategy, const double *reclaimer_share, const double *reclaimee_share,

@@ -566,3 +566,55 @@ def gen_reclaim_strategies():
 
 if __name__ == "__main__":
     print("reclaim_strategies:", gen_reclaim_strategies())
+
+
+def gen_capacity_policy():
+    """plugins/proportion/capacity_policy/capacity_policy_test.go:24-1080 — the four literal tables (IsJobOverQueueCapacity
+    x2, IsNonPreemptibleJobOverQuota, IsTaskAllocationOnNodeOverCapacity) -> tests/golden/capacity_policy.json."""
+    path = os.path.join(REF, "plugins", "proportion", "capacity_policy", "capacity_policy_test.go")
+    src = open(path).read()
+    # `NewPodSet(..).WithPodInfos(map)` is a method chain the literal parser does not read: fold it into one call
+    src = re.sub(r'subgroup_info\.NewPodSet\(([^()]*)\)\.\s*WithPodInfos\(', r'podsetWithPods(\1, ', src)
+    fields = ("Deserved", "FairShare", "Allocated", "AllocatedNotPreemptible", "MaxAllowed")
+    modes = ["IsJobOverQueueCapacity", "IsJobOverQueueCapacity", "IsNonPreemptibleJobOverQuota", "IsTaskAllocationOnNodeOverCapacity"]
+    out, pos = [], 0
+    for mode in modes:
+        a = src.index("tests := map[string]struct {", pos)
+        b = src.index("for name, data := range tests", a)
+        pos = b
+        blk = src[a:b]
+        table = find_literals("tests := map[string]caseT" + blk[blk.index("}{") + 1:], "map[string]caseT")[0]
+        for name, case in table.items():
+            if name.startswith("__"):
+                continue
+            queues = {}
+            for qid, q in case["queues"].items():
+                if qid.startswith("__"):
+                    continue
+                share = q.get("QueueResourceShare") or {}
+                queues[qid] = {"parent": q.get("ParentQueue", ""),
+                               **{res: {f: _num((share.get(res) or {}).get(f, 0)) for f in fields} for res in ("CPU", "Memory", "GPU")}}
+            job = case["job"]
+            pods = list(job["PodSets"].values())[0]["args"][3]
+            req = [0.0, 0.0, 0.0]  # (cpu, memory, gpu) summed over the pending pods = getRequiredQuota
+            for pid, pod in pods.items():
+                if pid.startswith("__") or (pod.get("Status") or {}).get("__ident") != "pod_status.Pending":
+                    continue
+                rr = pod["ResReq"]
+                if rr["__call"].endswith("NewResourceRequirementsWithGpus"):
+                    req[2] += _num(rr["args"][0])
+                else:  # NewResourceRequirements(gpus, milliCpus, memory)
+                    req[2] += _num(rr["args"][0])
+                    req[0] += _num(rr["args"][1])
+                    req[1] += _num(rr["args"][2])
+            pre = (job.get("Preemptibility") or {}).get("__ident", "")
+            out.append({"function": mode, "name": name, "queues": queues, "queue": job["Queue"], "req": req,
+                        # PodGroupInfo.IsPreemptibleJob(): the zero value of Preemptibility is not "preemptible"
+                        "preemptible": pre.endswith(".Preemptible"), "schedulable": bool(case["expectedResult"])})
+    with open(os.path.join(HERE, "capacity_policy.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return len(out)
+
+
+if __name__ == "__main__":
+    print("capacity_policy:", gen_capacity_policy())

@@ -223,3 +223,28 @@ def test_reclaim_strategies(case):
 
 def test_reclaim_strategy_tables_are_complete():
     assert len(STRATEGIES) == 24
+
+
+# ------------------------------------------------------------------------------------------------- capacity policy
+# capacity_policy_test.go:24-1080: four literal tables (14 cases), transcribed mechanically
+# (tests/golden/capacity_policy.json); the job's requirement is getRequiredQuota over its pending pods
+CAPACITY = json.load(open(os.path.join(GOLDEN, "capacity_policy.json")))
+
+
+@pytest.mark.parametrize("case", CAPACITY, ids=[f"{c['function']}: {c['name']}" for c in CAPACITY])
+def test_capacity_policy(case):
+    l = lib()
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    l.kai_oracle_capacity_schedulable.argtypes = [C.c_int, ip, dp, C.c_int, C.c_int, dp, C.c_int]
+    names = list(case["queues"])
+    idx = {n: i for i, n in enumerate(names)}
+    _p, pp = _ip([idx.get(case["queues"][n]["parent"], -1) for n in names])
+    _s, ps = _dp([[[case["queues"][n][r][f] for f in FIELDS5] for r in RES] for n in names])
+    _r, pr = _dp(case["req"])
+    mode = 1 if case["function"] == "IsNonPreemptibleJobOverQuota" else 0
+    got = l.kai_oracle_capacity_schedulable(len(names), pp, ps, idx[case["queue"]], int(case["preemptible"]), pr, mode)
+    assert bool(got) == case["schedulable"]
+
+
+def test_capacity_policy_tables_are_complete():
+    assert len(CAPACITY) == 14
