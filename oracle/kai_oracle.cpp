@@ -276,6 +276,13 @@ double divide_over_quota_resource(double remaining, double k, std::vector<QueueA
   return remaining;
 }
 
+// plugins/topology/node_scoring.go:36-53: nodes of the i-th of n preferred-level domains (in sorted-tree order) score
+// floor((i+1)/n * 10) * scores.Topology (plugins/scores/scores.go)
+double topology_position_score(int i, int n) {
+  double score = ((double)(i + 1) / (double)n) * 10;
+  return std::floor(score) * 10000.0;
+}
+
 // ---------------------------------------------------------------------------
 // plugins/proportion/queue_order/queue_order.go:19-73
 // job_req: QuantifyResource(GetTasksToAllocateInitResource(job,..,false)) of the best pending job
@@ -1443,8 +1450,7 @@ struct kai_oracle {
       std::vector<int> lvl;
       level_domains(tp, dom, tp.lb + pref, lvl);
       for (size_t i = 0; i < lvl.size(); i++) {
-        double score = ((double)(i + 1) / (double)lvl.size()) * 10;
-        double normalized = std::floor(score) * 10000.0;
+        double normalized = topology_position_score((int)i, (int)lvl.size());
         for (int n : tp.doms[lvl[i]].nodes) topo_scores[n] = normalized;
       }
     }
@@ -3064,6 +3070,7 @@ double kai_oracle_binpack_score(double mn, double mx, double cur, double overall
   return binpack_score(mn, mx, cur, overall);
 }
 double kai_oracle_spread_score(double non_allocated, double count) { return spread_score(non_allocated, count); }
+double kai_oracle_topology_position_score(int i, int n) { return topology_position_score(i, n); }
 
 double kai_oracle_set_resource_share(int n, double total, double k_value, const double *deserved,
                                      const double *limit, const double *oqw, const double *request,

@@ -36,6 +36,8 @@ const char *kai_oracle_last_error(const kai_oracle *o);
 double kai_oracle_binpack_score(double min_alloc, double max_alloc, double cur, double node_overall);
 /* plugins/nodeplacement/spread.go:16-36 */
 double kai_oracle_spread_score(double non_allocated, double resource_count);
+/* plugins/topology/node_scoring.go:36-53: score of the nodes of the i-th of n preferred-level domains */
+double kai_oracle_topology_position_score(int i, int n);
 /* plugins/proportion/resource_division/resource_division.go:33-43 setResourceShare
    on ONE sibling group and ONE resource; arrays of length n; fair_share is in/out.
    returns the remaining amount. */

@@ -224,3 +224,12 @@ def test_queue_order_result(name, l_gpu, r_gpu, l_prio, r_prio, l_req, r_req, to
     got = lib().kai_oracle_queue_order(l.ctypes.data_as(dp), r.ctypes.data_as(dp), l_prio, r_prio, 0, 0,
                                        lreq.ctypes.data_as(dp), rreq.ctypes.data_as(dp), total.ctypes.data_as(dp))
     assert got == expected
+
+
+# plugins/topology/node_scoring_test.go:106-257 TestCalculateNodeScores: the score of the nodes of the i-th of n
+# preferred-level domains in sorted-tree order, in units of scores.Topology (= 10000, plugins/scores/scores.go)
+@pytest.mark.parametrize("n,expected", [(1, [10.0]), (3, [3.0, 6.0, 10.0]), (4, [2.0, 5.0, 7.0, 10.0]), (2, [5.0, 10.0])])
+def test_topology_position_scores(n, expected):
+    fn = lib().kai_oracle_topology_position_score
+    fn.argtypes, fn.restype = [C.c_int, C.c_int], C.c_double
+    assert [fn(i, n) for i in range(n)] == [e * 10000.0 for e in expected]
