@@ -395,3 +395,55 @@ def test_synthetic_configs_round_trip(name):
         node_a = np.where(ra.task_node >= 0, snap.node_name_rank[np.maximum(ra.task_node, 0)], -1)
         assert np.array_equal(node_a[perm], rb.task_node), act
         assert ra.pods_placed == rb.pods_placed and ra.pods_evicted == rb.pods_evicted
+
+
+# ---------------------------------------------------------------------------------------------- node_info fit test
+# api/node_info/node_info_test.go:677-794 TestIsTaskAllocatable: node allocatable, running pods and a candidate pod as
+# Kubernetes quantities -> does the pod fit the node's Idle resources.  Run through the whole wire path: the packer's
+# Quantity arithmetic and request computation (incl. pod overhead), then one allocate cycle on the oracle.
+# (node allocatable, [running pod requests], candidate requests, candidate overhead, expected)
+def _rl(cpu, mem, gpu=None, pods=None):
+    rl = {"cpu": cpu, "memory": mem}
+    if gpu is not None:
+        rl["nvidia.com/gpu"] = gpu
+    if pods is not None:
+        rl["pods"] = pods
+    return rl
+
+
+IS_TASK_ALLOCATABLE = [
+    ("add pod with not enough cpu and memory", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")], _rl("2000m", "2G"), None, False),
+    ("add pod with not enough cpu - 1 millicpu", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")], _rl("1001m", "1G"), None, False),
+    ("add pod with not enough memory - 1 Kb", _rl("2000m", "2G", pods="110"), [_rl("1000m", "2G")], _rl("1000m", "1Ki"), None, False),
+    ("add pod with enough cpu and memory", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")], _rl("1000m", "1G"), None, True),
+    ("task in capacity but not in available", _rl("1000m", "1G", pods="110"), [_rl("1000m", "1G")], _rl("1000m", "1G"), None, False),
+    ("missing gpu", _rl("2000m", "2G", pods="110"), [], _rl("1000m", "1G", gpu="1"), None, False),
+    ("already used gpu so missing gpu", _rl("2000m", "2G", "1", "110"), [_rl("1000m", "1G", gpu="1")], _rl("1000m", "1G", gpu="1"), None, False),
+    ("enough cpu memory and gpu", _rl("2000m", "2G", "2", "110"), [_rl("1000m", "1G", gpu="1")], _rl("1000m", "1G", gpu="1"), None, True),
+    ("pod with overhead that fits without overhead but not with overhead", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")],
+     _rl("500m", "500M"), _rl("600m", "600M"), False),
+    ("pod with overhead that doesn't fit even without overhead", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")],
+     _rl("1500m", "1500M"), _rl("100m", "100M"), False),
+    ("pod without overhead that doesn't fit", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")], _rl("1500m", "1500M"), None, False),
+    ("pod with overhead that fits with overhead", _rl("2000m", "2G", pods="110"), [_rl("1000m", "1G")],
+     _rl("500m", "500M"), _rl("100m", "100M"), True),
+]
+
+
+@pytest.mark.parametrize("name,node,running,candidate,overhead,expected", IS_TASK_ALLOCATABLE, ids=[c[0] for c in IS_TASK_ALLOCATABLE])
+def test_is_task_allocatable_through_the_wire_format(name, node, running, candidate, overhead, expected):
+    pods = [_pod(f"p{i}", "running", "Running", "n1", requests=r) for i, r in enumerate(running)]
+    extra = {"overhead": overhead} if overhead else {}
+    pods.append(_pod("podToAllocate", "candidate", requests=candidate, **extra))
+    doc = {"config": {"actions": "allocate"}, "schedulerParams": {"fullHierarchyFairness": True},
+           "rawObjects": {"pods": pods,
+                          "nodes": [{"metadata": {"name": "n1"}, "spec": {}, "status": {"allocatable": node}}],
+                          "queues": [_queue("q", gpu=(-1, -1, 1))],
+                          "podGroups": [{"metadata": {"name": g, "namespace": "ns"}, "spec": {"queue": "q", "minMember": 1}}
+                                        for g in ("running", "candidate")]}}
+    snap, meta, kw, actions = sio.pack_cluster(doc)
+    o = Oracle(abi.make_config(**kw))
+    o.load(snap)
+    res = o.run("allocate")
+    t = meta["task_names"].index("podToAllocate")
+    assert (res.task_status[t] == abi.POD_BINDING) == expected
