@@ -3170,6 +3170,42 @@ int kai_oracle_can_reclaim_resources(const double *share, const double *req, int
   }
   return kai_oracle::can_reclaim_from_share(q, req, preemptible != 0) ? 1 : 0;
 }
+// proportion.setFairShare (proportion.go:403-423) on an explicit queue tree: the level recursion over
+// resource_division.SetResourcesShare.  in[q][3][4] = {Deserved, MaxAllowed, OverQuotaWeight, Request} per resource,
+// fair_share[q][3] is written
+int kai_oracle_set_fair_share_tree(int n_queues, const int32_t *parent, const int32_t *priority, const int64_t *creation,
+                                   const int32_t *uid_rank, const double *in, const double *total, double k_value,
+                                   double *fair_share) {
+  kai_oracle o;
+  o.cfg.k_value = k_value;
+  o.NQ = n_queues;
+  o.Q.assign(n_queues, QueueAttr());
+  for (int q = 0; q < n_queues; q++) {
+    o.Q[q].parent = parent[q];
+    o.Q[q].priority = priority[q];
+    o.Q[q].creation = creation[q];
+    o.Q[q].uid_rank = uid_rank[q];
+    for (int r = 0; r < QR; r++) {
+      const double *x = in + ((size_t)q * QR + r) * 4;
+      o.Q[q].s[r].deserved = x[0];
+      o.Q[q].s[r].max_allowed = x[1];
+      o.Q[q].s[r].oqw = x[2];
+      o.Q[q].s[r].request = x[3];
+    }
+  }
+  std::vector<int> top;
+  for (int q = 0; q < n_queues; q++) {
+    if (parent[q] >= 0)
+      o.Q[parent[q]].children.push_back(q);
+    else
+      top.push_back(q);
+  }
+  o.set_fair_share_for_queues(total, top);
+  for (int q = 0; q < n_queues; q++)
+    for (int r = 0; r < QR; r++) fair_share[(size_t)q * QR + r] = o.Q[q].s[r].fair;
+  return 0;
+}
+
 // capacity_policy.go:26-84 on an explicit queue tree (share[q][3][5] as above): mode 0 = resultsOverLimit +
 // resultsWithNonPreemptibleOverQuota (IsJobOverQueueCapacity / IsTaskAllocationOnNodeOverCapacity), mode 1 = the quota
 // check alone (IsNonPreemptibleJobOverQuota); returns IsSchedulable

@@ -73,6 +73,11 @@ int kai_oracle_set_task_virtual(kai_oracle *o, int task, int is_virtual);
 /* plugins/proportion/reclaimable/reclaimable.go:29-51 CanReclaimResources for one queue: share[3][4] =
    {Deserved, FairShare, Allocated, AllocatedNotPreemptible} per resource (cpu, memory, gpu), req[3]. */
 int kai_oracle_can_reclaim_resources(const double *share, const double *req, int preemptible);
+/* proportion.setFairShare (proportion.go:403-423) on an explicit queue tree: in[n_queues][3][4] = {Deserved, MaxAllowed,
+   OverQuotaWeight, Request}; fair_share[n_queues][3] is written. */
+int kai_oracle_set_fair_share_tree(int n_queues, const int32_t *parent, const int32_t *priority, const int64_t *creation,
+                                   const int32_t *uid_rank, const double *in, const double *total, double k_value,
+                                   double *fair_share);
 /* capacity_policy.go:26-84 on an explicit queue tree (share[n_queues][3][5] as for kai_oracle_reclaimable): mode 0 =
    limit + non-preemptible quota checks, mode 1 = the quota check alone; returns IsSchedulable. */
 int kai_oracle_capacity_schedulable(int n_queues, const int32_t *parent, const double *share, int queue, int preemptible,

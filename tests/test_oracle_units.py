@@ -233,3 +233,59 @@ def test_topology_position_scores(n, expected):
     fn = lib().kai_oracle_topology_position_score
     fn.argtypes, fn.restype = [C.c_int, C.c_int], C.c_double
     assert [fn(i, n) for i in range(n)] == [e * 10000.0 for e in expected]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# proportion_test.go:265-523 "Set fair share for 2 hierarchy queues - simplified": the level recursion of setFairShare
+# (proportion.go:403-423) over d1{q1}, d2{q2}; every queue starts with GPU {Deserved 2, OverQuotaWeight 1, Request 100,
+# MaxAllowed unlimited}.  (line, total GPUs, deserved / weight / priority overrides, expected fair share)
+# ---------------------------------------------------------------------------------------------------------------
+TWO_LEVELS = [
+    (380, 4, {}, {}, {}, {"d1": 2, "q1": 2, "d2": 2, "q2": 2}),
+    (393, 4, {"d1": 3, "d2": 1}, {}, {}, {"d1": 3, "q1": 3, "d2": 1, "q2": 2}),
+    (410, 12, {"d1": 3, "d2": 1}, {}, {}, {"d1": 7, "q1": 7, "d2": 5, "q2": 5}),
+    (427, 12, {"d1": 3, "d2": 1}, {"d1": 1, "d2": 7}, {}, {"d1": 4, "q1": 4, "d2": 8, "q2": 8}),
+    (448, 12, {"d1": 3, "d2": 1}, {"d1": 7, "d2": 1}, {}, {"d1": 10, "q1": 10, "d2": 2, "q2": 2}),
+    (469, 12, {"d1": 1, "q1": 1, "d2": 1, "q2": 1}, {"d1": 7, "d2": 1}, {"d1": 1, "d2": 2}, {"d1": 1, "q1": 1, "d2": 11, "q2": 11}),
+    (496, 12, {"d1": 1, "q1": 1, "d2": 1, "q2": 1}, {"d1": 1, "d2": 7}, {"d1": 2, "d2": 1}, {"d1": 11, "q1": 11, "d2": 1, "q2": 1}),
+]
+
+
+def fair_share_tree(queues, total_gpu, k_value=0.0):
+    """queues: name -> dict(parent, priority, GPU=(Deserved, MaxAllowed, OverQuotaWeight, Request)); GPU shares back."""
+    names = list(queues)
+    idx = {n: i for i, n in enumerate(names)}
+    n = len(names)
+    dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    parent = np.array([idx.get(queues[q]["parent"], -1) for q in names], dtype=np.int32)
+    prio = np.array([queues[q].get("priority", 0) for q in names], dtype=np.int32)
+    creation = np.zeros(n, dtype=np.int64)
+    uid = np.argsort(np.argsort(np.array(names, dtype=object))).astype(np.int32)
+    rows = np.zeros((n, 3, 4))
+    for i, q in enumerate(names):
+        rows[i, 2] = queues[q]["GPU"]
+    total = np.array([0.0, 0.0, float(total_gpu)])
+    out = np.zeros((n, 3))
+    fn = lib().kai_oracle_set_fair_share_tree
+    fn.argtypes = [C.c_int, ip, ip, lp, ip, dp, dp, C.c_double, dp]
+    assert fn(n, parent.ctypes.data_as(ip), prio.ctypes.data_as(ip), creation.ctypes.data_as(lp), uid.ctypes.data_as(ip),
+              rows.ctypes.data_as(dp), total.ctypes.data_as(dp), k_value, out.ctypes.data_as(dp)) == 0
+    return {q: out[i, 2] for i, q in enumerate(names)}
+
+
+@pytest.mark.parametrize("line,total,deserved,weight,priority,expected", TWO_LEVELS, ids=[f"L{c[0]}" for c in TWO_LEVELS])
+def test_set_fair_share_two_levels(line, total, deserved, weight, priority, expected):
+    queues = {q: {"parent": p, "priority": priority.get(q, 0), "GPU": (deserved.get(q, 2), -1, weight.get(q, 1), 100)}
+              for q, p in (("d1", ""), ("q1", "d1"), ("d2", ""), ("q2", "d2"))}
+    assert fair_share_tree(queues, total) == expected
+
+
+def test_set_fair_share_multi_hierarchy():  # proportion_test.go:43-262 (two literal cases; OverQuotaWeight 0 unless given)
+    q = lambda parent, deserved, request, oqw=0: {"parent": parent, "GPU": (deserved, -1, oqw, request)}  # noqa: E731
+    got = fair_share_tree({"top-queue": q("", 3, 3), "mid-queue": q("top-queue", 3, 3), "leaf-queue-1": q("mid-queue", 2, 2),
+                           "leaf-queue-2": q("mid-queue", 1, 1)}, 3)
+    assert got == {"top-queue": 3, "mid-queue": 3, "leaf-queue-1": 2, "leaf-queue-2": 1}
+    got = fair_share_tree({"top-queue-1": q("", 2, 2), "child-queue-1": q("top-queue-1", 1, 1), "child-queue-2": q("top-queue-1", 1, 1),
+                           "top-queue-2": q("", 2, 2), "child-queue-3": q("top-queue-2", 0, 0),
+                           "child-queue-4": q("top-queue-2", 1, 2, oqw=1)}, 4)
+    assert got == {"top-queue-1": 2, "child-queue-1": 1, "child-queue-2": 1, "top-queue-2": 2, "child-queue-3": 0, "child-queue-4": 2}
