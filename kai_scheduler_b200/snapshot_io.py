@@ -242,6 +242,14 @@ def _pod_request(pod: dict, names: _ResourceNames) -> dict:
     return total
 
 
+KAI_UTILITY_APPS = ("kai-resource-reservation", "scaling-pod")  # conf/global_config.go:25-26
+
+
+def _is_kai_utility_pod(pod: dict) -> bool:
+    """pod_info.IsKaiUtilityPod (api/pod_info/utility_pods.go): GPU reservation and scale-adjust pods, by `app` label."""
+    return (pod["metadata"].get("labels") or {}).get("app") in KAI_UTILITY_APPS
+
+
 def _task_status(pod: dict, bind_request) -> int:
     """getTaskStatus (pod_info.go:414-446)."""
     phase = (pod.get("status") or {}).get("phase", "")
@@ -501,7 +509,7 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
         if row["status"] == abi.POD_RELEASING:
             rel[:, n] += vec
         sched = (row["pod"].get("spec") or {}).get("schedulerName", "")
-        if sched != scheduler_name:  # proportion.go:276-286 (KAI utility pods are not modelled)
+        if sched != scheduler_name and not _is_kai_utility_pod(row["pod"]):  # proportion.go:276-286
             foreign[0, n] += vec[0]
             foreign[1, n] += vec[1]
             foreign[2, n] += vec[2]

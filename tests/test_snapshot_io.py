@@ -447,3 +447,41 @@ def test_is_task_allocatable_through_the_wire_format(name, node, running, candid
     res = o.run("allocate")
     t = meta["task_names"].index("podToAllocate")
     assert (res.task_status[t] == abi.POD_BINDING) == expected
+
+
+# ---------------------------------------------------------------------------------------------- cluster totals
+# plugins/proportion/proportion_test.go:526-800 "Get Node Resources" (getNodeResources, proportion.go:258-289): what one
+# node contributes to the fair-share totals.  (name, allocatable, pods = (scheduler, phase, labels, requests), want)
+def _npod(i, scheduler, phase, requests, labels=None, on_node=True):
+    p = _pod(f"pod-{i}", None, phase, "n1" if on_node else None, requests=requests, schedulerName=scheduler)
+    p["metadata"]["labels"].update(labels or {})
+    return p
+
+
+NODE_RESOURCES = [
+    ("cpu + memory node", _rl("8000m", "10G"), [], [8000, 1e10, 0]),
+    ("gpu node", _rl("8000m", "10G", gpu="2"), [], [8000, 1e10, 2]),
+    ("ignore extra resources", {"A": "4"}, [], [0, 0, 0]),
+    ("Count out resources for non-related pods", _rl("8000m", "10G"),
+     [("kai-scheduler", "Running", None, _rl("2", "2G")), ("default-scheduler", "Running", None, _rl("1", "1G"))], [7000, 9e9, 0]),
+    ("consider reservation pods", _rl("8000m", "10G"),
+     [("kai-scheduler", "Running", None, _rl("2", "2G")), ("default-scheduler", "Running", None, _rl("1", "1G")),
+      ("default-scheduler", "Running", {"app": "kai-resource-reservation"}, _rl("1", "1G"))], [7000, 9e9, 0]),
+    ("consider scaler pods", _rl("8000m", "10G"),
+     [("kai-scheduler", "Running", None, _rl("2", "2G")), ("default-scheduler", "Running", None, _rl("1", "1G")),
+      ("default-scheduler", "Running", {"app": "scaling-pod"}, _rl("1", "1G"))], [7000, 9e9, 0]),
+    ("Do not count out resources for non-related pods if non active", _rl("8000m", "10G"),
+     [("default-scheduler", "Pending", None, _rl("1", "1G")), ("default-scheduler", "Succeeded", None, _rl("1", "1G"))], [8000, 1e10, 0]),
+]
+
+
+@pytest.mark.parametrize("name,allocatable,pods,want", NODE_RESOURCES, ids=[c[0] for c in NODE_RESOURCES])
+def test_node_resources_for_fair_share_totals(name, allocatable, pods, want):
+    raw_pods = [_npod(i, sched, phase, req, labels, on_node=phase == "Running") for i, (sched, phase, labels, req) in enumerate(pods)]
+    doc = {"config": {"actions": "allocate"}, "schedulerParams": {"fullHierarchyFairness": True},
+           "rawObjects": {"pods": raw_pods, "nodes": [{"metadata": {"name": "n1"}, "spec": {}, "status": {"allocatable": allocatable}}],
+                          "queues": [_queue("q")], "podGroups": []}}
+    snap, meta, kw, _ = sio.pack_cluster(doc)
+    o = Oracle(abi.make_config(**kw))
+    o.load(snap)
+    assert o.fair_share().total_resource.tolist() == [float(x) for x in want]
