@@ -457,8 +457,20 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     ignored: list = []
     names = _ResourceNames()
 
+    # SchedulingNodePoolParams.GetLabelSelector (conf/scheduler_conf.go:95-112): the partition selector the listers of
+    # nodes, queues and pod groups apply (cache/cluster_info/data_lister/kubernetes_lister.go:101-117); pods are not
+    # filtered, the ones of other partitions simply find no node
+    part = params.get("partitionParams") or {}
+    pool_key, pool_value = part.get("NodePoolLabelKey") or "", part.get("NodePoolLabelValue") or ""
+
+    def in_partition(obj) -> bool:
+        if not pool_key:
+            return True
+        labels = obj["metadata"].get("labels") or {}
+        return labels.get(pool_key) == pool_value if pool_value else pool_key not in labels
+
     # ---- nodes (cluster_info.go:230-260, node_info.go:107-152) ----
-    nodes = sorted(raw.get("nodes") or [], key=lambda n: n["metadata"]["name"].encode())
+    nodes = sorted((n for n in raw.get("nodes") or [] if in_partition(n)), key=lambda n: n["metadata"]["name"].encode())
     node_names = [n["metadata"]["name"] for n in nodes]
     nindex = {n: i for i, n in enumerate(node_names)}
     if len(nindex) != len(nodes):
@@ -525,7 +537,7 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
                 pass
 
     # ---- queues (cache/cluster_info/queue.go:56-140) ----
-    queues_raw = {q["metadata"]["name"]: q for q in raw.get("queues") or []}
+    queues_raw = {q["metadata"]["name"]: q for q in raw.get("queues") or [] if in_partition(q)}
     qrows = {}
     if params.get("fullHierarchyFairness"):
         for name, q in queues_raw.items():
@@ -615,7 +627,7 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     for row in pod_rows:
         if row["group"]:
             by_group.setdefault(row["group"], []).append(row)
-    pgs = sorted(raw.get("podGroups") or [], key=lambda g: g["metadata"]["name"].encode())
+    pgs = sorted((g for g in raw.get("podGroups") or [] if in_partition(g)), key=lambda g: g["metadata"]["name"].encode())
     job_names, job_queue, job_prio, job_flags, job_created, job_last_start = [], [], [], [], [], []
     job_podset_begin, podset_min, podset_task_begin = [0], [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_uids, t_job, t_cons, t_nominated = [], [], [], [], [], [], [], [], []

@@ -485,3 +485,97 @@ def test_node_resources_for_fair_share_totals(name, allocatable, pods, want):
     o = Oracle(abi.make_config(**kw))
     o.load(snap)
     assert o.fair_share().total_resource.tolist() == [float(x) for x in want]
+
+
+# ---------------------------------------------------------------------------------------------- cluster_info_test.go
+def _cluster(nodes=(), pods=(), queues=(), pod_groups=(), priority_classes=(), params=None):
+    return {"config": {"actions": "allocate"}, "schedulerParams": dict({"fullHierarchyFairness": True}, **(params or {})),
+            "rawObjects": {"nodes": list(nodes), "pods": list(pods), "queues": list(queues), "podGroups": list(pod_groups),
+                           "priorityClasses": list(priority_classes)}}
+
+
+def _cpu_node(name, labels=None):
+    return {"metadata": {"name": name, "labels": labels or {}}, "spec": {}, "status": {"allocatable": {"cpu": "10", "pods": "110"}}}
+
+
+def _cpu_pod(name, node, phase="Running"):
+    return {"metadata": {"name": name, "namespace": "ns", "uid": name}, "spec": {"nodeName": node, "containers": [
+        {"resources": {"requests": {"cpu": "2"}}}]}, "status": {"phase": phase}}
+
+
+def test_snapshot_nodes():  # cache/cluster_info/cluster_info_test.go:244-501 TestSnapshotNodes (BasicUsage, Finished job, node pool)
+    snap, meta, _, _ = sio.pack_cluster(_cluster(nodes=[_cpu_node("node-1")], pods=[_cpu_pod("p", "node-1")]))
+    assert snap.node_idle[:, 0].tolist() == [8000, 0, 0, 109] and snap.node_releasing[:, 0].tolist() == [0, 0, 0, 0]
+    snap, _, _, _ = sio.pack_cluster(_cluster(nodes=[_cpu_node("node-1")], pods=[_cpu_pod("p", "node-1", "Succeeded")]))
+    assert snap.node_idle[:, 0].tolist() == [10000, 0, 0, 110]
+    pool = {"partitionParams": {"NodePoolLabelKey": "pool", "NodePoolLabelValue": "pool-a"}}
+    snap, meta, _, _ = sio.pack_cluster(_cluster(
+        nodes=[_cpu_node("node-1", {"pool": "pool-a"}), _cpu_node("node-2", {"pool": "pool-b"})],
+        pods=[_cpu_pod("p1", "node-1"), _cpu_pod("p2", "node-2")], params=pool))
+    assert meta["node_names"] == ["node-1"] and snap.node_idle[:, 0].tolist() == [8000, 0, 0, 109]
+
+
+def test_snapshot_queues_and_flat_hierarchy():  # cluster_info_test.go:1326-1480
+    def q(name, parent=None, labels=None, gpu=None):
+        spec = {"resources": {"gpu": gpu or {"quota": 2}}}
+        if parent:
+            spec["parentQueue"] = parent
+        return {"metadata": {"name": name, "labels": labels or {}}, "spec": spec}
+
+    # TestSnapshotQueues: the default partition selector is "label absent" -> the queue of another node pool is dropped
+    doc = _cluster(queues=[q("department0", gpu={"quota": 4}), q("department0-a", labels={"nodepool": "nodepool-a"}),
+                           q("queue0", parent="department0")], params={"partitionParams": {"NodePoolLabelKey": "nodepool"}})
+    snap, meta, _, _ = sio.pack_cluster(doc)
+    assert meta["queue_names"] == ["department0", "queue0"] and list(snap.queue_parent) == [-1, 0]
+    assert snap.queue_deserved[2].tolist() == [4, 2]
+    # TestSnapshotFlatHierarchy: fullHierarchyFairness off -> a synthetic `default` parent (quota -1, weight 1, limit -1),
+    # the departments dropped, their queues re-parented
+    dept = {"quota": 4, "overQuotaWeight": 2, "limit": 10}
+    lab = {"nodepool": "nodepool-a"}
+    doc = _cluster(queues=[q("department0", labels=lab, gpu=dept), q("department1", labels=lab, gpu=dept),
+                           q("queue0", "department0", lab, {}), q("queue1", "department1", lab, {})],
+                   params={"fullHierarchyFairness": False,
+                           "partitionParams": {"NodePoolLabelKey": "nodepool", "NodePoolLabelValue": "nodepool-a"}})
+    snap, meta, _, _ = sio.pack_cluster(doc)
+    assert meta["queue_names"] == ["default", "queue0", "queue1"] and list(snap.queue_parent) == [-1, 0, 0]
+    assert snap.queue_deserved[:, 0].tolist() == [-1, -1, -1] and snap.queue_limit[:, 0].tolist() == [-1, -1, -1]
+    assert snap.queue_oqw[:, 0].tolist() == [1, 1, 1]
+
+
+def test_pod_group_priority_resolution():  # cluster_info_test.go:1482-1506,1660-1731
+    def pg(name, cls=None):
+        spec = {"queue": "q"}
+        if cls:
+            spec["priorityClassName"] = cls
+        return {"metadata": {"name": name, "namespace": "ns"}, "spec": spec}
+
+    def prio(classes):
+        snap, meta, _, _ = sio.pack_cluster(_cluster(queues=[_queue("q")], pod_groups=[pg("with-class", "my-priority"), pg("without")],
+                                                      priority_classes=classes))
+        return dict(zip(meta["job_names"], snap.job_priority.tolist()))
+
+    # TestGetPodGroupPriority / TestGetDefaultPriorityNotExists: the named class wins, no global default -> 50
+    assert prio([{"metadata": {"name": "my-priority"}, "value": 2}]) == {"with-class": 2, "without": 50}
+    # TestGetDefaultPriority: a globalDefault class is the fallback
+    assert prio([{"metadata": {"name": "my-priority"}, "value": 2, "globalDefault": True}]) == {"with-class": 2, "without": 2}
+    # TestGetPodGroupPriorityNotExistingPriority / TestGetDefaultPriorityWithError: unknown class -> the default (50 here)
+    assert prio([]) == {"with-class": 50, "without": 50}
+
+
+def test_snapshot_pod_groups():  # cluster_info_test.go:957-1275 BasicUsage / NotExistingQueue + job_info.go:200-216
+    pod = {"metadata": {"name": "test-pod", "namespace": "ns", "uid": "test-pod", "annotations": {sio.POD_GROUP_ANNOTATION: "podGroup-0"}},
+           "spec": {"containers": []}, "status": {"phase": "Pending"}}
+    pg = {"metadata": {"name": "podGroup-0", "uid": "ABC"}, "spec": {"queue": "queue-0"}}
+    snap, meta, _, _ = sio.pack_cluster(_cluster(queues=[_queue("queue-0")], pods=[pod], pod_groups=[pg]))
+    assert meta["job_names"] == ["podGroup-0"] and list(snap.job_queue) == [0] and list(snap.podset_min_available) == [1]
+    assert meta["task_names"] == ["test-pod"] and snap.task_req[0].tolist() == [0, 0, 0, 1]
+    pg["spec"]["queue"] = "queue-1"  # NotExistingQueue: the job is kept, without a queue (and gets a fit error upstream)
+    snap, meta, _, _ = sio.pack_cluster(_cluster(queues=[_queue("queue-0")], pods=[pod], pod_groups=[pg]))
+    assert list(snap.job_queue) == [-1] and meta["task_names"] == ["test-pod"]
+    # minMember feeds the default PodSet, SubGroups replace it (setSubGroups)
+    pg["spec"] = {"queue": "queue-0", "minMember": 3}
+    snap, _, _, _ = sio.pack_cluster(_cluster(queues=[_queue("queue-0")], pods=[pod], pod_groups=[pg]))
+    assert list(snap.podset_min_available) == [3]
+    pg["spec"] = {"queue": "queue-0", "minMember": 3, "subGroups": [{"name": "a", "minMember": 2}, {"name": "b"}]}
+    snap, meta, _, _ = sio.pack_cluster(_cluster(queues=[_queue("queue-0")], pods=[pod], pod_groups=[pg]))
+    assert list(snap.podset_min_available) == [2, 1] and meta["task_names"] == []  # the unlabelled pod matches no PodSet
