@@ -627,7 +627,27 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     for row in pod_rows:
         if row["group"]:
             by_group.setdefault(row["group"], []).append(row)
-    pgs = sorted((g for g in raw.get("podGroups") or [] if in_partition(g)), key=lambda g: g["metadata"]["name"].encode())
+    def up_for_scheduler(pg) -> bool:
+        """isPodGroupUpForScheduler (cluster_info.go:585-602): a pod group with a scheduling backoff that this node
+        pool already marked unschedulable (its last SchedulingCondition names the pool) is left out."""
+        backoff = (pg.get("spec") or {}).get("schedulingBackoff")
+        if backoff is None or int(backoff) == -1:  # utils.NoSchedulingBackoff, also the default
+            return True
+        last, last_id = None, None
+        for cond in (pg.get("status") or {}).get("schedulingConditions") or []:  # utils.GetLastSchedulingCondition
+            try:
+                cid = int(cond.get("transitionID", ""))
+            except ValueError:
+                cid = -1
+            if last is None or cid > last_id:
+                last, last_id = cond, cid
+        if last is None:
+            return True
+        pool = (pg["metadata"].get("labels") or {}).get(pool_key) or "default"  # utils.GetNodePoolNameFromLabels
+        return (last.get("nodePool") or "") != pool
+
+    pgs = sorted((g for g in raw.get("podGroups") or [] if in_partition(g) and up_for_scheduler(g)),
+                 key=lambda g: g["metadata"]["name"].encode())
     job_names, job_queue, job_prio, job_flags, job_created, job_last_start = [], [], [], [], [], []
     job_podset_begin, podset_min, podset_task_begin = [0], [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_uids, t_job, t_cons, t_nominated = [], [], [], [], [], [], [], [], []

@@ -579,3 +579,31 @@ def test_snapshot_pod_groups():  # cluster_info_test.go:957-1275 BasicUsage / No
     pg["spec"] = {"queue": "queue-0", "minMember": 3, "subGroups": [{"name": "a", "minMember": 2}, {"name": "b"}]}
     snap, meta, _, _ = sio.pack_cluster(_cluster(queues=[_queue("queue-0")], pods=[pod], pod_groups=[pg]))
     assert list(snap.podset_min_available) == [2, 1] and meta["task_names"] == []  # the unlabelled pod matches no PodSet
+
+
+UP_FOR_SCHEDULER = [  # cluster_info_test.go:1825-1926 TestIsPodGroupUpForScheduler: (backoff, pool label, last condition's pool, kept)
+    ("Infinite schedulingBackoff", -1, "nodepoola", "nodepoola", True),
+    ("Nil schedulingBackoff", None, "nodepoolb", "nodepoolb", True),
+    ("No last scheduling condition", 1, "nodepoolb", None, True),
+    ("No last scheduling condition - default node pool", 1, "default", None, True),
+    ("unassigned by condition from different node pool", 1, "nodepoola", "different-nodepool", True),
+    ("unassigned by condition", 1, "nodepoolc", "nodepoolc", False),
+    ("unassigned by condition - default node pool", 1, "default", "different-nodepool", True),
+    ("unassigned by condition - default node pool 2", 1, "nodepoolc", "default", True),
+    ("unassigned by condition - default node pool (same)", 1, "default", "default", False),
+]
+
+
+@pytest.mark.parametrize("name,backoff,pool,last_pool,kept", UP_FOR_SCHEDULER, ids=[c[0] for c in UP_FOR_SCHEDULER])
+def test_is_pod_group_up_for_scheduler(name, backoff, pool, last_pool, kept):
+    key = "kai.scheduler/node-pool"
+    pg = {"metadata": {"name": "test-pg", "labels": {} if pool in ("default", "") else {key: pool}}, "spec": {"queue": "q"},
+          "status": {"schedulingConditions": [] if last_pool is None else [{"nodePool": last_pool}]}}
+    if backoff is not None:
+        pg["spec"]["schedulingBackoff"] = backoff
+    # the scheduler of the pool the pod group lives in: value = the pool ("" selects unlabelled objects, the default pool)
+    params = {"partitionParams": {"NodePoolLabelKey": key, "NodePoolLabelValue": "" if pool == "default" else pool}}
+    queue = _queue("q")
+    queue["metadata"]["labels"] = dict(pg["metadata"]["labels"])
+    _, meta, _, _ = sio.pack_cluster(_cluster(queues=[queue], pod_groups=[pg], params=params))
+    assert (meta["job_names"] == ["test-pg"]) == kept
