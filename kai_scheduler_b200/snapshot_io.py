@@ -242,6 +242,17 @@ def _pod_request(pod: dict, names: _ResourceNames) -> dict:
     return total
 
 
+def _bind_request_failed(br: dict) -> bool:
+    """BindRequestInfo.IsFailed (api/bindrequest_info/binrequest_info.go:84-92): failed for good once the attempts reach
+    the backoff limit (or no limit is set)."""
+    status, spec = br.get("status") or {}, br.get("spec") or {}
+    if status.get("phase") != "Failed":
+        return False
+    if spec.get("backoffLimit") is None:
+        return True
+    return int(status.get("failedAttempts", 0) or 0) >= int(spec["backoffLimit"])
+
+
 KAI_UTILITY_APPS = ("kai-resource-reservation", "scaling-pod")  # conf/global_config.go:25-26
 
 
@@ -492,6 +503,8 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     for pod in pods:
         md = pod["metadata"]
         br = bind_requests.get((md.get("namespace", ""), md["name"]))
+        if br is not None and _bind_request_failed(br):  # BindRequestMap.GetBindRequestForPod (binrequest_info.go:16-27)
+            br = None
         status = _task_status(pod, br)
         node_name = (pod.get("spec") or {}).get("nodeName") or (br["spec"]["selectedNode"] if br else "")
         pod_rows.append(dict(pod=pod, status=status, node=nindex.get(node_name, -1), req=_pod_request(pod, names),

@@ -8,6 +8,7 @@ Three kinds of evidence:
     oracle: the table's expected bindings must still hold after the trip through raw Kubernetes objects.
 """
 import io
+import json
 import os
 import tempfile
 
@@ -607,3 +608,38 @@ def test_is_pod_group_up_for_scheduler(name, backoff, pool, last_pool, kept):
     queue["metadata"]["labels"] = dict(pg["metadata"]["labels"])
     _, meta, _, _ = sio.pack_cluster(_cluster(queues=[queue], pod_groups=[pg], params=params))
     assert (meta["job_names"] == ["test-pg"]) == kept
+
+
+def _bind_doc(requests, extra_pods=()):
+    pod = {"metadata": {"name": "pod-1", "namespace": "namespace-1", "uid": "pod-1", "annotations": {sio.POD_GROUP_ANNOTATION: "podgroup-1"}},
+           "spec": {"containers": [{"resources": {"requests": {"cpu": "2"}}}]}, "status": {"phase": "Pending"}}
+    pods = [pod]
+    for name in extra_pods:
+        other = json.loads(json.dumps(pod))
+        other["metadata"]["name"] = other["metadata"]["uid"] = name
+        pods.append(other)
+    doc = _cluster(nodes=[{"metadata": {"name": "node-1"}, "spec": {}, "status": {"allocatable": {"cpu": "10"}}}], pods=pods,
+                   queues=[{"metadata": {"name": "queue-0"}, "spec": {}}],
+                   pod_groups=[{"metadata": {"name": "podgroup-1", "namespace": "namespace-1"}, "spec": {"queue": "queue-0"}}])
+    doc["rawObjects"]["bindRequests"] = requests
+    return doc
+
+
+def test_bind_requests():  # cache/cluster_info/cluster_info_test.go:503-955 TestBindRequests
+    def br(pod="pod-1", node="node-1", **kw):
+        spec = {"podName": pod, "selectedNode": node}
+        if "backoff" in kw:
+            spec["backoffLimit"] = kw["backoff"]
+        status = {"phase": kw["phase"], "failedAttempts": kw.get("failed", 0)} if "phase" in kw else {}
+        return {"metadata": {"name": "my-pod-1234", "namespace": "namespace-1"}, "spec": spec, "status": status}
+
+    def outcome(requests, extra=()):
+        snap, meta, _, _ = sio.pack_cluster(_bind_doc(requests, extra))
+        t = meta["task_names"].index("pod-1")
+        return int(snap.task_status[t]), snap.node_idle[0, 0]
+
+    assert outcome([br()]) == (abi.POD_BINDING, 8000)  # :547 waiting for binding: the node already holds the pod's CPU
+    assert outcome([br(backoff=5, phase="Failed", failed=2)]) == (abi.POD_BINDING, 8000)  # :593 failing, below the limit
+    assert outcome([br(backoff=5, phase="Failed", failed=5)]) == (abi.POD_PENDING, 10000)  # :644 reached the limit: stale
+    assert outcome([br(pod="not-pod-1")], extra=["not-pod-1"]) == (abi.POD_PENDING, 8000)  # :696 the request is another pod's
+    assert outcome([br(node="node-2", phase="Failed")]) == (abi.POD_PENDING, 10000)  # :749 unknown node: not for this snapshot
