@@ -3121,6 +3121,21 @@ double kai_oracle_divide_over_quota(int n, double amount, double k_value, const 
   return rem;
 }
 
+// actions/common/minimal_job_comparison.go on two jobs of the loaded snapshot that share a signature:
+// MinimalJobRepresentatives{representative}.IsEasierToSchedule(job) (:27-36,50-81)
+int kai_oracle_job_easier_to_schedule(kai_oracle *o, int job, int representative) {
+  kai_oracle::MinimalReps m;
+  m.rep[o->J[representative].signature] = representative;
+  return o->easier_to_schedule(m, job) ? 1 : 0;
+}
+// ... and UpdateRepresentative(job) (:38-48,83-105): 1 = the job replaced the representative
+int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int representative) {
+  kai_oracle::MinimalReps m;
+  m.rep[o->J[representative].signature] = representative;
+  o->update_representative(m, job);
+  return m.rep[o->J[representative].signature] == job ? 1 : 0;
+}
+
 // idle_gpus/common.go:34-64 greedyMatchRequirements (both arrays sorted descending by the caller)
 int kai_oracle_greedy_match(int n_req, const double *req, int n_holders, const double *capacity) {
   return kai_oracle::greedy_match_requirements(std::vector<double>(req, req + n_req), std::vector<double>(capacity, capacity + n_holders)) ? 1 : 0;

@@ -64,6 +64,10 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
                            const double *l_job_req, const double *r_job_req,
                            const double *total);
 
+/* actions/common/minimal_job_comparison.go on two jobs of the loaded snapshot with equal job_signature:
+   IsEasierToSchedule(job) against `representative`, and whether UpdateRepresentative(job) replaces it. */
+int kai_oracle_job_easier_to_schedule(kai_oracle *o, int job, int representative);
+int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int representative);
 /* accumulated_scenario_filters/idle_gpus/common.go:34-64 greedyMatchRequirements; both arrays sorted descending */
 int kai_oracle_greedy_match(int n_req, const double *req, int n_holders, const double *capacity);
 /* podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in attempt
