@@ -82,3 +82,62 @@ HIERARCHY = [  # TestNLevelQueueHierarchy, job_order_by_queue_test.go:798-975 (p
 @pytest.mark.parametrize("name,queues,jobs,expected", HIERARCHY, ids=[c[0] for c in HIERARCHY])
 def test_n_level_queue_hierarchy(name, queues, jobs, expected):
     assert pop_order(queues, jobs) == expected
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# plugins/elastic/elastic_test.go:18-512 TestJobOrderFn: the elastic comparator (elastic.go:25-65) between two pod groups
+# (minAvailable, pod statuses) -> -1 (left first) / 0 / 1.  Observed as the pop order of two jobs of one queue with equal
+# priority, run with both creation orders: a 0 lets the older job go first, -1 / 1 do not care about age.  Every job gets
+# one extra Pending pod so that allocate visits it; Pending pods are not active-allocated, the compared state is unchanged.
+# ---------------------------------------------------------------------------------------------------------------
+RUNNING, ALLOCATED, BOUND, RELEASING = abi.POD_RUNNING, abi.POD_ALLOCATED, abi.POD_BOUND, abi.POD_RELEASING
+ELASTIC = [
+    ("no pods", 0, [], 0, [], 0),
+    ("running single pod", 1, [RUNNING], 1, [RUNNING], 0),
+    ("allocated pod counts as allocated", 1, [ALLOCATED], 1, [RUNNING], 0),
+    ("bound pod counts as allocated", 1, [BOUND], 1, [RUNNING], 0),
+    ("releasing pod doesn't count as allocated", 1, [RELEASING], 1, [RUNNING], -1),
+    ("pod group with min pods against pod group with no pods", 1, [RUNNING], 1, [], 1),
+    ("less than min against min", 2, [RUNNING], 2, [RUNNING, RUNNING], -1),
+    ("less than min against more than min", 2, [RUNNING], 2, [RUNNING, RUNNING, RUNNING], -1),
+    ("min against more than min", 1, [RUNNING], 1, [RUNNING, RUNNING], -1),
+    ("min against less than min", 1, [RUNNING], 3, [RUNNING, RUNNING], 1),
+    ("more than min against min", 1, [RUNNING, RUNNING], 1, [RUNNING], 1),
+    ("more than min against min (named 'less than min' in the Go table)", 1, [RUNNING, RUNNING], 1, [RUNNING], 1),
+]
+
+
+def _elastic_order(l_min, l_st, r_min, r_st, l_is_older):
+    statuses = [l_st + [abi.POD_PENDING], r_st + [abi.POD_PENDING]]
+    flat = np.array(statuses[0] + statuses[1], dtype=np.int32)
+    T = len(flat)
+    on_node = flat != abi.POD_PENDING
+    alloc = np.array([[0.0], [0.0], [0.0], [float(on_node.sum())]])  # every pod slot is taken: nothing fits
+    idle = alloc.copy()
+    idle[3, 0] = 0.0
+    rel = np.zeros((4, 1))
+    rel[3, 0] = float((flat == RELEASING).sum())
+    snap = abi.Snapshot(
+        n_res=4, node_allocatable=alloc, node_idle=idle, node_releasing=rel, node_name_rank=np.zeros(1, dtype=np.int32),
+        node_flags=np.full(1, abi.NODE_READY, dtype=np.uint32), queue_parent=np.array([-1], dtype=np.int32),
+        queue_priority=np.array([100], dtype=np.int32), queue_creation=np.zeros(1, dtype=np.int64),
+        queue_uid_rank=np.zeros(1, dtype=np.int32), queue_deserved=np.full((3, 1), -1.0), queue_limit=np.full((3, 1), -1.0),
+        queue_oqw=np.ones((3, 1)), job_queue=np.zeros(2, dtype=np.int32), job_priority=np.full(2, 50, dtype=np.int32),
+        job_order_rank=np.array([0, 1] if l_is_older else [1, 0], dtype=np.int32),
+        job_flags=np.full(2, abi.JOB_PREEMPTIBLE, dtype=np.uint32), job_podset_begin=np.arange(3, dtype=np.int32),
+        podset_min_available=np.array([l_min, r_min], dtype=np.int32),
+        podset_task_begin=np.array([0, len(statuses[0]), T], dtype=np.int32), task_status=flat,
+        task_node=np.where(on_node, 0, -1).astype(np.int32), task_req=np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (T, 1)),
+        task_order_rank=np.concatenate([np.arange(len(statuses[0])), np.arange(len(statuses[1]))]).astype(np.int32))
+    o = Oracle()
+    o.load(snap)
+    res = o.run("allocate")  # (a Releasing pod's slot may take one Pending pod: only the first pop is read)
+    return [int(j) for j, _ in res.visits]
+
+
+@pytest.mark.parametrize("name,l_min,l_st,r_min,r_st,want", ELASTIC, ids=[c[0] for c in ELASTIC])
+def test_elastic_job_order(name, l_min, l_st, r_min, r_st, want):
+    for l_is_older in (True, False):
+        first = _elastic_order(l_min, l_st, r_min, r_st, l_is_older)[0]
+        expected_first = 0 if want < 0 else (1 if want > 0 else (0 if l_is_older else 1))
+        assert first == expected_first, f"l_is_older={l_is_older}"
