@@ -139,3 +139,28 @@ ALLOCATABLE = [
 def test_num_allocatable_tasks(name, statuses, real, virtual, want):
     tasks = [(f"task-{i}", s) for i, s in enumerate(statuses)]
     assert len(tasks_to_allocate({"sg": (16, tasks)}, real=real, virtual=virtual, with_default=False)) == want
+
+
+# plugins/subgrouporder/subgroup_order_test.go:30-102 TestSubGroupOrderFn: PodSetOrderFn (subgroup_order.go:31-62) between
+# two PodSets (minAvailable, allocated pods) -> left / right / equal.  Observed through GetTasksToAllocate: each PodSet
+# also holds one Pending pod and the first task returned comes from the PodSet that orders first; "equal" falls back to
+# the name order, so every case runs with both name orders.
+L, R_, EQ = -1, 1, 0
+SUBGROUP_ORDER = [
+    ("both below minAvailable, should be equal", 3, 1, 4, 2, EQ),
+    ("left below, right above minAvailable", 3, 1, 3, 5, L),
+    ("right below, left above minAvailable", 3, 5, 3, 1, R_),
+    ("both above minAvailable, left lower allocation ratio", 2, 4, 4, 9, L),
+    ("both above minAvailable, right lower allocation ratio", 2, 10, 4, 9, R_),
+    ("both above minAvailable, equal allocation ratio", 2, 4, 4, 8, EQ),
+]
+
+
+@pytest.mark.parametrize("name,l_min,l_alloc,r_min,r_alloc,want", SUBGROUP_ORDER, ids=[c[0] for c in SUBGROUP_ORDER])
+def test_subgroup_order(name, l_min, l_alloc, r_min, r_alloc, want):
+    for l_name, r_name in (("a-left", "b-right"), ("b-left", "a-right")):
+        podsets = {l_name: (l_min, [(f"{l_name}-{i}", A) for i in range(l_alloc)] + [(f"{l_name}-pending", P)]),
+                   r_name: (r_min, [(f"{r_name}-{i}", A) for i in range(r_alloc)] + [(f"{r_name}-pending", P)])}
+        first = tasks_to_allocate(podsets, with_default=False)[0]
+        expected = l_name if want == L else (r_name if want == R_ else min(l_name, r_name))
+        assert first == f"{expected}-pending", (l_name, r_name)

@@ -643,3 +643,25 @@ def test_bind_requests():  # cache/cluster_info/cluster_info_test.go:503-955 Tes
     assert outcome([br(backoff=5, phase="Failed", failed=5)]) == (abi.POD_PENDING, 10000)  # :644 reached the limit: stale
     assert outcome([br(pod="not-pod-1")], extra=["not-pod-1"]) == (abi.POD_PENDING, 8000)  # :696 the request is another pod's
     assert outcome([br(node="node-2", phase="Failed")]) == (abi.POD_PENDING, 10000)  # :749 unknown node: not for this snapshot
+
+
+def test_task_order_fn():  # plugins/taskorder/task_order_test.go:17-53 + session_plugins.go:244-259 (creation, then UID)
+    def order(l_label, r_label):
+        def pod(name, label):
+            p = _pod(name, "g")
+            if label is not None:
+                p["metadata"]["labels"][sio.TASK_ORDER_LABEL] = label
+            return p
+        doc = _cluster(queues=[_queue("q")], pods=[pod("l", l_label), pod("r", r_label)],
+                       pod_groups=[{"metadata": {"name": "g", "namespace": "ns"}, "spec": {"queue": "q"}}])
+        snap, meta, _, _ = sio.pack_cluster(doc)
+        rank = dict(zip(meta["task_names"], snap.task_order_rank.tolist()))
+        return -1 if rank["l"] < rank["r"] else 1
+
+    # TaskOrderFn(l, r): 1 / 0 / -1; a 0 falls through to creation (equal here) and then the UID ("uid-l" < "uid-r")
+    assert order("1", "2") == 1      # the higher task-priority goes first
+    assert order("2", "2") == -1     # equal -> UID
+    assert order("2", "1") == -1
+    assert order(None, "1") == 1     # a labelled pod precedes an unlabelled one
+    assert order("1", None) == -1
+    assert order(None, None) == -1   # equal -> UID
