@@ -185,6 +185,17 @@ class _ResourceNames:
         return self.index[name]
 
 
+def _is_scalar_resource_name(name: str) -> bool:
+    """k8s_internal.IsScalarResourceName (k8s_internal/kubernetes_helpers.go:12-15) over the v1helper predicates of
+    k8s.io/kubernetes v1.34.2 (not vendored; published rules): extended resources (a domain-qualified name outside
+    kubernetes.io/ and not starting with `requests.`), hugepages-*, kubernetes.io/-prefixed native resources and
+    attachable-volumes-*."""
+    if name.startswith("hugepages-") or name.startswith("attachable-volumes-") or "kubernetes.io/" in name:
+        return True
+    native = "/" not in name
+    return not native and not name.startswith("requests.")
+
+
 def _is_mig(name: str) -> bool:
     return name.startswith("nvidia.com/mig-")
 
@@ -216,8 +227,10 @@ def _resource_list(rl: dict, names: _ResourceNames, request: bool, what: str) ->
             continue
         elif name in ("ephemeral-storage", "storage"):
             v, k = quantity_value(q), names.slot(name)
-        else:
+        elif _is_scalar_resource_name(name):
             v, k = quantity_milli_value(q), names.slot(name)  # scalar resources are kept in milli-units
+        else:
+            continue  # not a resource the scheduler accounts (resource_requirment.go:61-69)
         if v != 0:
             out[k] = out.get(k, 0) + v
     return out

@@ -665,3 +665,14 @@ def test_task_order_fn():  # plugins/taskorder/task_order_test.go:17-53 + sessio
     assert order(None, "1") == 1     # a labelled pod precedes an unlabelled one
     assert order("1", None) == -1
     assert order(None, None) == -1   # equal -> UID
+
+
+def test_requirements_from_resource_list():  # api/resource_info/resource_requirment_test.go:14-72
+    names = sio._ResourceNames()
+    rl = lambda d: sio._resource_list(d, names, True, "test")  # noqa: E731
+    assert rl({"cpu": "1", "memory": "5G"}) == {0: 1000, 1: 5_000_000_000}
+    assert rl({"cpu": "-1"}) == {0: -1000}
+    assert rl({"nvidia.com/gpu": "1"}) == {2: 1} and rl({"amd.com/gpu": "2"}) == {2: 2}
+    assert rl({"kai.scheduler/test-resource": "1"}) == {4: 1000} and names.names[4] == "kai.scheduler/test-resource"
+    assert rl({"unsupported": "2"}) == {}  # not a scalar resource name: not counted
+    assert rl({"hugepages-2Mi": "1", "attachable-volumes-x": "1", "requests.foo/bar": "1"}) == {5: 1000, 6: 1000}
