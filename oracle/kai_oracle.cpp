@@ -87,6 +87,16 @@ struct GoHeap {
   void fix(int i) {
     if (!down(i, len())) up(i);
   }
+  T remove(int i) {  // heap.Remove
+    int n = len() - 1;
+    if (n != i) {
+      std::swap(items[i], items[n]);
+      if (!down(i, n)) up(i);
+    }
+    T x = items.back();
+    items.pop_back();
+    return x;
+  }
   const T &peek() const { return items[0]; }
 };
 
@@ -3134,6 +3144,38 @@ int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int represent
   m.rep[o->J[representative].signature] = representative;
   o->update_representative(m, job);
   return m.rep[o->J[representative].signature] == job ? 1 : 0;
+}
+
+// scheduler_util.PriorityQueue (priority_queue.go:50-118) over container/heap, on ints with `<`: ops[i] = 0 push(vals[i])
+// (with the max-size eviction heap.Remove(maxQueueSize) when max_size >= 0), 1 pop, 2 peek, 3 set items[0] = vals[i]
+// and Fix(0), 4 len; out[i] receives the popped / peeked value or the length (INT32_MIN when the queue is empty)
+void kai_oracle_priority_queue_exercise(int max_size, int n_ops, const int32_t *ops, const int32_t *vals, int32_t *out) {
+  GoHeap<int> h;
+  h.less = [](const int &a, const int &b) { return a < b; };
+  for (int i = 0; i < n_ops; i++) {
+    out[i] = INT32_MIN;
+    switch (ops[i]) {
+      case 0:
+        h.push(vals[i]);
+        if (max_size >= 0 && h.len() > max_size) h.remove(max_size);
+        break;
+      case 1:
+        if (!h.empty()) out[i] = h.pop();
+        break;
+      case 2:
+        if (!h.empty()) out[i] = h.peek();
+        break;
+      case 3:
+        if (!h.empty()) {
+          h.items[0] = vals[i];
+          h.fix(0);
+        }
+        break;
+      case 4:
+        out[i] = h.len();
+        break;
+    }
+  }
 }
 
 // idle_gpus/common.go:34-64 greedyMatchRequirements (both arrays sorted descending by the caller)

@@ -68,6 +68,9 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
    IsEasierToSchedule(job) against `representative`, and whether UpdateRepresentative(job) replaces it. */
 int kai_oracle_job_easier_to_schedule(kai_oracle *o, int job, int representative);
 int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int representative);
+/* scheduler_util.PriorityQueue (priority_queue.go:50-118) over the oracle's container/heap restatement, ints with `<`:
+   ops 0 push(val) (+ max-size eviction when max_size >= 0), 1 pop, 2 peek, 3 items[0] = val; Fix(0), 4 len. */
+void kai_oracle_priority_queue_exercise(int max_size, int n_ops, const int32_t *ops, const int32_t *vals, int32_t *out);
 /* accumulated_scenario_filters/idle_gpus/common.go:34-64 greedyMatchRequirements; both arrays sorted descending */
 int kai_oracle_greedy_match(int n_req, const double *req, int n_holders, const double *capacity);
 /* podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in attempt

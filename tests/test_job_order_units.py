@@ -141,3 +141,41 @@ def test_elastic_job_order(name, l_min, l_st, r_min, r_st, want):
         first = _elastic_order(l_min, l_st, r_min, r_st, l_is_older)[0]
         expected_first = 0 if want < 0 else (1 if want > 0 else (0 if l_is_older else 1))
         assert first == expected_first, f"l_is_older={l_is_older}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scheduler_util/priority_queue_test.go:13-305: the PriorityQueue every job / queue / task order is built on, over the
+# oracle's restatement of Go's container/heap (push, pop, peek, fix, and the max-size eviction)
+# ---------------------------------------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+
+from oracle_lib import lib  # noqa: E402
+
+PUSH, POP, PEEK, FIX0, LEN = 0, 1, 2, 3, 4
+EMPTY = -(2 ** 31)
+
+
+def pq(ops, max_size=-1):
+    n = len(ops)
+    o = np.array([x[0] for x in ops], dtype=np.int32)
+    v = np.array([x[1] if len(x) > 1 else 0 for x in ops], dtype=np.int32)
+    out = np.zeros(n, dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    fn = lib().kai_oracle_priority_queue_exercise
+    fn.argtypes, fn.restype = [C.c_int, C.c_int, ip, ip, ip], None
+    fn(max_size, n, o.ctypes.data_as(ip), v.ctypes.data_as(ip), out.ctypes.data_as(ip))
+    return out.tolist()
+
+
+def test_priority_queue_push_and_pop():  # :13-108
+    assert pq([(PUSH, 2), (PUSH, 3), (PUSH, 1), (LEN,), (POP,)])[-2:] == [3, 1]            # add item
+    assert pq([(PUSH, 1), (PUSH, 3), (PUSH, 2), (LEN,), (POP,)])[-2:] == [3, 1]            # add less prioritized item
+    assert pq([(PUSH, 2), (PUSH, 3), (PUSH, 4), (PUSH, 1), (LEN,), (POP,)], max_size=2)[-2:] == [2, 1]  # limited queue size
+
+
+def test_priority_queue_peek_fix_len():  # :110-305
+    assert pq([(PUSH, 2), (PUSH, 3), (LEN,), (PEEK,), (LEN,)])[-3:] == [2, 2, 2]           # basic peek
+    assert pq([(LEN,), (PEEK,), (POP,)]) == [0, EMPTY, EMPTY]                               # no items
+    assert pq([(PUSH, 2), (PUSH, 3), (FIX0, 4), (PEEK,)])[-1] == 3                          # basic fix
+    order = pq([(PUSH, v) for v in (5, 1, 4, 2, 3)] + [(POP,)] * 5)[-5:]
+    assert order == [1, 2, 3, 4, 5]
