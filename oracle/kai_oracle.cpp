@@ -3146,6 +3146,36 @@ int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int represent
   return m.rep[o->J[representative].signature] == job ? 1 : 0;
 }
 
+// framework.Statement (statement.go) on the loaded snapshot: kinds[i] = 0 Evict(task), 1 Pipeline(task, node,
+// updateTaskIfExistsOnNode = true), 2 Allocate(task, node), 3 undoOperation(index = task[i]), 4 Discard; read the
+// outcome with kai_oracle_fair_share
+int kai_oracle_statement_exercise(kai_oracle *o, int n_ops, const int32_t *kinds, const int32_t *task, const int32_t *node) {
+  if (!o || !o->loaded) return KAI_ERR_STATE;
+  for (int i = 0; i < n_ops; i++) {
+    switch (kinds[i]) {
+      case 0:
+        if (o->T[task[i]].node < 0) return KAI_ERR_INVALID;  // "node doesn't exist in session" (statement.go:70-74)
+        o->stmt_evict(task[i]);
+        break;
+      case 1:
+        o->stmt_pipeline(task[i], node[i], true);
+        break;
+      case 2:
+        o->stmt_allocate(task[i], node[i]);
+        break;
+      case 3:
+        o->undo_operation(task[i]);
+        break;
+      case 4:
+        o->stmt_discard();
+        break;
+      default:
+        return KAI_ERR_INVALID;
+    }
+  }
+  return KAI_OK;
+}
+
 // scheduler_util.PriorityQueue (priority_queue.go:50-118) over container/heap, on ints with `<`: ops[i] = 0 push(vals[i])
 // (with the max-size eviction heap.Remove(maxQueueSize) when max_size >= 0), 1 pop, 2 peek, 3 set items[0] = vals[i]
 // and Fix(0), 4 len; out[i] receives the popped / peeked value or the length (INT32_MIN when the queue is empty)

@@ -1,0 +1,124 @@
+"""framework.Statement (statement.go:36-663) restated in the oracle, checked on the scenarios of statement_test.go
+(CPU): Evict / Pipeline / Allocate, their undo, and the undo of an undo, on the reference's own fixture shapes
+(`TestStatement_*`, whole-GPU cases; the fractional ones need GPU sharing).  The Go tests compare the task, the job's
+Allocated and the node's Idle / Used / Releasing before and after; here the same quantities are the task status /
+node, the queue's allocated GPUs and the node tables.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import dsl
+from kai_scheduler_b200 import abi
+from oracle_lib import Oracle, lib
+
+EVICT, PIPELINE, ALLOCATE, UNDO = 0, 1, 2, 3
+
+
+def session(jobs, gpus=2):
+    topo = {"Nodes": {"node0": {"GPUs": gpus}}, "Queues": [{"Name": "queue0", "DeservedGPUs": gpus}], "Jobs": jobs}
+    snap, meta = dsl.build_snapshot(topo)
+    o = Oracle()
+    o.load(snap)
+    return o, snap, meta
+
+
+def job(name, state, node=None, gpus=1):
+    task = {"State": state}
+    if node:
+        task["NodeName"] = node
+    return {"Name": name, "RequiredGPUsPerTask": gpus, "QueueName": "queue0", "Priority": 50, "Tasks": [task]}
+
+
+def exercise(o, ops):
+    ip = C.POINTER(C.c_int32)
+    fn = lib().kai_oracle_statement_exercise
+    fn.argtypes = [C.c_void_p, C.c_int, ip, ip, ip]
+    k = np.array([x[0] for x in ops], dtype=np.int32)
+    t = np.array([x[1] for x in ops], dtype=np.int32)
+    n = np.array([x[2] if len(x) > 2 else -1 for x in ops], dtype=np.int32)
+    return fn(o._h, len(ops), k.ctypes.data_as(ip), t.ctypes.data_as(ip), n.ctypes.data_as(ip))
+
+
+def state(o):
+    r = o.fair_share()
+    return (r.task_status.tolist(), r.task_node.tolist(), r.node_idle[2].tolist(), r.node_releasing[2].tolist(),
+            r.queue_allocated[2].tolist(), r.node_idle[3].tolist())
+
+
+def test_evict_then_unevict_restores_everything():  # TestStatement_Evict_Unevict (:27-154)
+    o, _, _ = session([job("running_job0", "Running", "node0")])
+    before = state(o)
+    assert exercise(o, [(EVICT, 0), (UNDO, 0)]) == 0
+    assert state(o) == before
+    assert before[4][0] == 1 and before[2] == [1.0]  # jobGpuAllocation 1, one of two GPUs used
+
+
+def test_evict():  # TestStatement_Evict (:156-305)
+    o, _, _ = session([job("pending_job0", "Pending")])
+    assert exercise(o, [(EVICT, 0)]) != 0  # "node doesn't exist in session": a Pending pod cannot be evicted
+    o, _, _ = session([job("running_job0", "Running", "node0")])
+    before = state(o)
+    assert exercise(o, [(EVICT, 0)]) == 0
+    st, node, idle, rel, qalloc, idle_pods = state(o)
+    assert st == [abi.POD_RELEASING] and node == [0]
+    assert idle == before[2] and rel == [1.0]      # still Used on the node, now also Releasing
+    assert qalloc[0] == 0.0                        # proportion's deallocate handler ran (statement.go:101-110)
+
+
+def test_evict_undo_undo():  # TestStatement_Evict_Undo_Undo (:307-460): undoing the undo evicts again
+    o, _, _ = session([job("running_job0", "Running", "node0")])
+    exercise(o, [(EVICT, 0)])
+    evicted = state(o)
+    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 0
+    assert state(o) == evicted
+
+
+def test_pipeline_then_unpipeline_restores_everything():  # TestStatement_Pipeline_Unpipeline (:462-693)
+    o, _, _ = session([job("releasing_job0", "Releasing", "node0"), job("pending_job0", "Pending")], gpus=1)
+    before = state(o)
+    assert exercise(o, [(PIPELINE, 1, 0), (UNDO, 0)]) == 0
+    assert state(o) == before
+
+
+def test_pipeline():  # TestStatement_Pipeline (:695-822): the pod takes the releasing GPU
+    o, _, _ = session([job("releasing_job0", "Releasing", "node0"), job("pending_job0", "Pending")], gpus=1)
+    before = state(o)
+    assert before[3] == [1.0] and before[2] == [0.0]
+    assert exercise(o, [(PIPELINE, 1, 0)]) == 0
+    st, node, idle, rel, qalloc, _ = state(o)
+    assert st == [abi.POD_RELEASING, abi.POD_PIPELINED] and node == [0, 0]
+    assert idle == [0.0] and rel == [0.0]          # Releasing -= request (node_info.go:483-488)
+    assert qalloc[0] == before[4][0] + 1
+
+
+def test_pipeline_undo_undo():  # TestStatement_Pipeline_Undo_Undo (:824-958)
+    o, _, _ = session([job("releasing_job0", "Releasing", "node0"), job("pending_job0", "Pending")], gpus=1)
+    exercise(o, [(PIPELINE, 1, 0)])
+    pipelined = state(o)
+    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 0
+    assert state(o) == pipelined
+
+
+def test_allocate_then_unallocate_restores_everything():  # TestStatement_Allocate_Unallocate (:960-1064)
+    o, _, _ = session([job("pending_job0", "Pending")])
+    before = state(o)
+    assert exercise(o, [(ALLOCATE, 0, 0), (UNDO, 0)]) == 0
+    assert state(o) == before
+
+
+def test_allocate():  # TestStatement_Allocate (:1066-1170)
+    o, _, _ = session([job("pending_job0", "Pending")])
+    assert exercise(o, [(ALLOCATE, 0, 0)]) == 0
+    st, node, idle, rel, qalloc, idle_pods = state(o)
+    assert st == [abi.POD_ALLOCATED] and node == [0] and idle == [1.0] and rel == [0.0] and qalloc[0] == 1.0
+    assert idle_pods == [109.0]
+
+
+def test_allocate_undo_undo():  # TestStatement_Allocate_Undo_Undo (:1172-1282)
+    o, _, _ = session([job("pending_job0", "Pending")])
+    exercise(o, [(ALLOCATE, 0, 0)])
+    allocated = state(o)
+    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 0
+    assert state(o) == allocated
