@@ -540,8 +540,16 @@ struct kai_oracle {
   // :515-551 removeTaskResources — uses the status of the clone stored on the node
   void node_remove_task(int ti, int n) {
     Task &t = T[ti];
+    // NodeInfo.RemoveTask (:495-513) fails without touching anything when the pod is not on the node; callers that
+    // continue with an add (UpdateTask in unevict, statement.go:171-183) then simply add it.  Happens when a task was
+    // evicted, pipelined back onto its own node with updateTaskIfExistsOnNode and both are rolled back
+    // (statement_checkpoint_test.go "rollback evict pipeline").
+    if (t.find_on(n) < 0) {
+      if (getenv("KAI_ORACLE_COUNT_MISSING")) fprintf(stderr, "[oracle] remove of a task that is not on the node\n");
+      return;
+    }
     for (int r = 0; r < R; r++) {
-      switch (t.on_status[t.find_on(n) < 0 ? 0 : t.find_on(n)]) {
+      switch (t.on_status[t.find_on(n)]) {
         case KAI_POD_RELEASING:
           L(r, n) -= t.req[r];
           I(r, n) += t.req[r];
@@ -3147,8 +3155,9 @@ int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int represent
 }
 
 // framework.Statement (statement.go) on the loaded snapshot: kinds[i] = 0 Evict(task), 1 Pipeline(task, node,
-// updateTaskIfExistsOnNode = true), 2 Allocate(task, node), 3 undoOperation(index = task[i]), 4 Discard; read the
-// outcome with kai_oracle_fair_share
+// updateTaskIfExistsOnNode = true), 2 Allocate(task, node), 3 undoOperation(index = task[i]), 4 Discard, 5 Pipeline with
+// updateTaskIfExistsOnNode = false, 6 Rollback(checkpoint = task[i]); returns the operation count (= Checkpoint()) or a
+// negative error; read the outcome with kai_oracle_fair_share
 int kai_oracle_statement_exercise(kai_oracle *o, int n_ops, const int32_t *kinds, const int32_t *task, const int32_t *node) {
   if (!o || !o->loaded) return KAI_ERR_STATE;
   for (int i = 0; i < n_ops; i++) {
@@ -3169,11 +3178,17 @@ int kai_oracle_statement_exercise(kai_oracle *o, int n_ops, const int32_t *kinds
       case 4:
         o->stmt_discard();
         break;
+      case 5:  // Pipeline(task, node, updateTaskIfExistsOnNode = false)
+        o->stmt_pipeline(task[i], node[i], false);
+        break;
+      case 6:  // Rollback(checkpoint = task[i]) (statement.go:48-61)
+        o->stmt_rollback(task[i]);
+        break;
       default:
         return KAI_ERR_INVALID;
     }
   }
-  return KAI_OK;
+  return (int)o->ops.size();  // = what Checkpoint() would return now
 }
 
 // scheduler_util.PriorityQueue (priority_queue.go:50-118) over container/heap, on ints with `<`: ops[i] = 0 push(vals[i])

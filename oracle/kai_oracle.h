@@ -69,7 +69,9 @@ int kai_oracle_queue_order(const double *l_share, const double *r_share,
 int kai_oracle_job_easier_to_schedule(kai_oracle *o, int job, int representative);
 int kai_oracle_job_replaces_representative(kai_oracle *o, int job, int representative);
 /* framework.Statement operations on the loaded snapshot (statement.go): kinds 0 Evict(task), 1 Pipeline(task, node),
-   2 Allocate(task, node), 3 undoOperation(index in task[]), 4 Discard; the state is read with kai_oracle_fair_share. */
+   2 Allocate(task, node), 3 undoOperation(index in task[]), 4 Discard, 5 Pipeline(update = false), 6 Rollback(checkpoint in
+   task[]); returns the number of operations in the log (= Checkpoint()) or a negative error; the state is read with
+   kai_oracle_fair_share. */
 int kai_oracle_statement_exercise(kai_oracle *o, int n_ops, const int32_t *kinds, const int32_t *task, const int32_t *node);
 /* scheduler_util.PriorityQueue (priority_queue.go:50-118) over the oracle's container/heap restatement, ints with `<`:
    ops 0 push(val) (+ max-size eviction when max_size >= 0), 1 pop, 2 peek, 3 items[0] = val; Fix(0), 4 len. */

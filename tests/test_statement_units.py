@@ -13,7 +13,7 @@ import dsl
 from kai_scheduler_b200 import abi
 from oracle_lib import Oracle, lib
 
-EVICT, PIPELINE, ALLOCATE, UNDO = 0, 1, 2, 3
+EVICT, PIPELINE, ALLOCATE, UNDO, DISCARD, PIPELINE_NO_UPDATE, ROLLBACK = 0, 1, 2, 3, 4, 5, 6
 
 
 def session(jobs, gpus=2):
@@ -50,17 +50,17 @@ def state(o):
 def test_evict_then_unevict_restores_everything():  # TestStatement_Evict_Unevict (:27-154)
     o, _, _ = session([job("running_job0", "Running", "node0")])
     before = state(o)
-    assert exercise(o, [(EVICT, 0), (UNDO, 0)]) == 0
+    assert exercise(o, [(EVICT, 0), (UNDO, 0)]) == 2
     assert state(o) == before
     assert before[4][0] == 1 and before[2] == [1.0]  # jobGpuAllocation 1, one of two GPUs used
 
 
 def test_evict():  # TestStatement_Evict (:156-305)
     o, _, _ = session([job("pending_job0", "Pending")])
-    assert exercise(o, [(EVICT, 0)]) != 0  # "node doesn't exist in session": a Pending pod cannot be evicted
+    assert exercise(o, [(EVICT, 0)]) < 0  # "node doesn't exist in session": a Pending pod cannot be evicted
     o, _, _ = session([job("running_job0", "Running", "node0")])
     before = state(o)
-    assert exercise(o, [(EVICT, 0)]) == 0
+    assert exercise(o, [(EVICT, 0)]) == 1
     st, node, idle, rel, qalloc, idle_pods = state(o)
     assert st == [abi.POD_RELEASING] and node == [0]
     assert idle == before[2] and rel == [1.0]      # still Used on the node, now also Releasing
@@ -71,14 +71,14 @@ def test_evict_undo_undo():  # TestStatement_Evict_Undo_Undo (:307-460): undoing
     o, _, _ = session([job("running_job0", "Running", "node0")])
     exercise(o, [(EVICT, 0)])
     evicted = state(o)
-    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 0
+    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 4  # evict, undo, evict again (the redo), undo
     assert state(o) == evicted
 
 
 def test_pipeline_then_unpipeline_restores_everything():  # TestStatement_Pipeline_Unpipeline (:462-693)
     o, _, _ = session([job("releasing_job0", "Releasing", "node0"), job("pending_job0", "Pending")], gpus=1)
     before = state(o)
-    assert exercise(o, [(PIPELINE, 1, 0), (UNDO, 0)]) == 0
+    assert exercise(o, [(PIPELINE, 1, 0), (UNDO, 0)]) == 2
     assert state(o) == before
 
 
@@ -86,7 +86,7 @@ def test_pipeline():  # TestStatement_Pipeline (:695-822): the pod takes the rel
     o, _, _ = session([job("releasing_job0", "Releasing", "node0"), job("pending_job0", "Pending")], gpus=1)
     before = state(o)
     assert before[3] == [1.0] and before[2] == [0.0]
-    assert exercise(o, [(PIPELINE, 1, 0)]) == 0
+    assert exercise(o, [(PIPELINE, 1, 0)]) == 1
     st, node, idle, rel, qalloc, _ = state(o)
     assert st == [abi.POD_RELEASING, abi.POD_PIPELINED] and node == [0, 0]
     assert idle == [0.0] and rel == [0.0]          # Releasing -= request (node_info.go:483-488)
@@ -97,20 +97,20 @@ def test_pipeline_undo_undo():  # TestStatement_Pipeline_Undo_Undo (:824-958)
     o, _, _ = session([job("releasing_job0", "Releasing", "node0"), job("pending_job0", "Pending")], gpus=1)
     exercise(o, [(PIPELINE, 1, 0)])
     pipelined = state(o)
-    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 0
+    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 4  # evict, undo, evict again (the redo), undo
     assert state(o) == pipelined
 
 
 def test_allocate_then_unallocate_restores_everything():  # TestStatement_Allocate_Unallocate (:960-1064)
     o, _, _ = session([job("pending_job0", "Pending")])
     before = state(o)
-    assert exercise(o, [(ALLOCATE, 0, 0), (UNDO, 0)]) == 0
+    assert exercise(o, [(ALLOCATE, 0, 0), (UNDO, 0)]) == 2
     assert state(o) == before
 
 
 def test_allocate():  # TestStatement_Allocate (:1066-1170)
     o, _, _ = session([job("pending_job0", "Pending")])
-    assert exercise(o, [(ALLOCATE, 0, 0)]) == 0
+    assert exercise(o, [(ALLOCATE, 0, 0)]) == 1
     st, node, idle, rel, qalloc, idle_pods = state(o)
     assert st == [abi.POD_ALLOCATED] and node == [0] and idle == [1.0] and rel == [0.0] and qalloc[0] == 1.0
     assert idle_pods == [109.0]
@@ -120,5 +120,33 @@ def test_allocate_undo_undo():  # TestStatement_Allocate_Undo_Undo (:1172-1282)
     o, _, _ = session([job("pending_job0", "Pending")])
     exercise(o, [(ALLOCATE, 0, 0)])
     allocated = state(o)
-    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 0
+    assert exercise(o, [(UNDO, 0), (UNDO, 1)]) == 4  # evict, undo, evict again (the redo), undo
     assert state(o) == allocated
+
+
+# statement_checkpoint_test.go:30-230 TestStatement_Checkpoint: running_job0 (task 1 after the DSL's priority sort keeps
+# the order: both priority 50 -> running_job0-0 = task 0, pending_job0-0 = task 1) on node0 with 2 GPUs; every sequence
+# is followed by Rollback(checkpoint 0) and must leave jobs and nodes as they were
+RUN_T, PEND_T = 0, 1
+CHECKPOINT = [
+    ("rollback evict", [(EVICT, RUN_T)]),
+    ("rollback allocate", [(ALLOCATE, PEND_T, 0)]),
+    ("rollback pipeline updateIfNeeded true", [(PIPELINE, PEND_T, 0)]),
+    ("rollback pipeline updateIfNeeded false", [(PIPELINE_NO_UPDATE, PEND_T, 0)]),
+    ("rollback allocate evict", [(ALLOCATE, PEND_T, 0), (EVICT, PEND_T)]),
+    ("rollback pipeline evict", [(PIPELINE, PEND_T, 0), (EVICT, PEND_T)]),
+    ("rollback evict pipeline", [(EVICT, RUN_T), (PIPELINE, RUN_T, 0)]),
+    ("rollback pipeline evict update false", [(PIPELINE_NO_UPDATE, PEND_T, 0), (EVICT, PEND_T)]),
+    ("rollback evict pipeline update false", [(EVICT, RUN_T), (PIPELINE_NO_UPDATE, RUN_T, 0)]),
+    ("rollback evict checkpoint pipeline update false", [(EVICT, RUN_T), (PIPELINE_NO_UPDATE, RUN_T, 0), (ROLLBACK, 1)]),
+]
+
+
+@pytest.mark.parametrize("name,ops", CHECKPOINT, ids=[c[0] for c in CHECKPOINT])
+def test_statement_checkpoint_rollback(name, ops):
+    o, _, meta = session([job("running_job0", "Running", "node0"), job("pending_job0", "Pending")])
+    assert meta["task_names"] == ["running_job0-0", "pending_job0-0"]
+    before = state(o)
+    assert exercise(o, ops) >= 1
+    assert exercise(o, [(ROLLBACK, 0)]) >= 0
+    assert state(o) == before
