@@ -533,6 +533,17 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     for n, rl in enumerate(node_alloc):
         for k, v in rl.items():
             alloc[k, n] = float(v)
+    # populateDRAGPUs (cluster_info.go:262-292): GPUs published through DRA ResourceSlices of a GPU driver are added to
+    # the node (NodeInfo.AddDRAGPUs) and mark it as a DRA node
+    dra_node = np.zeros(N, dtype=bool)
+    for sl in raw.get("resourceSlices") or []:
+        spec = sl.get("spec") or {}
+        if spec.get("allNodes") or "gpu" not in str(spec.get("driver", "")).lower():  # resources.IsGPUDeviceClass
+            continue
+        n = nindex.get(spec.get("nodeName") or "", -1)
+        if n >= 0 and spec.get("devices"):
+            alloc[2, n] += float(len(spec["devices"]))
+            dra_node[n] = True
     idle = alloc.copy()
     rel = np.zeros((R, N))
     foreign = np.zeros((3, N))
@@ -552,7 +563,7 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
             foreign[1, n] += vec[1]
             foreign[2, n] += vec[2]
     ready = np.array([_node_ready(n) for n in nodes], dtype=bool)
-    flags = np.where(ready, abi.NODE_READY, 0).astype(np.uint32)
+    flags = (np.where(ready, abi.NODE_READY, 0) | np.where(dra_node, abi.NODE_NOT_CPU_ONLY, 0)).astype(np.uint32)
     gpu_count = alloc[2].copy() if N else np.zeros(0)
     for n, node in enumerate(nodes):  # GetNumberOfGPUsInNode (node_info.go:630-651)
         lv = (node["metadata"].get("labels") or {}).get(GPU_COUNT_LABEL)
@@ -819,9 +830,12 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
     t_class = np.full(T, -1, dtype=np.int32)
     need_mask = not bool(ready.all())
     for t, cons in enumerate(t_cons):
-        key = json.dumps(cons, sort_keys=True)
+        # PredicateByNodeResourcesType (node_info.go:326-333): a device-plugin GPU request is rejected on a DRA node
+        wants_gpu = bool(dra_node.any()) and t_req[t][2] > 0
+        key = json.dumps([cons, wants_gpu], sort_keys=True)
         if key not in class_ids:
-            fits = np.array([bool(ready[n]) and _pod_fits_node(cons, nodes[n]) for n in range(N)], dtype=bool)
+            fits = np.array([bool(ready[n]) and not (wants_gpu and dra_node[n]) and _pod_fits_node(cons, nodes[n])
+                             for n in range(N)], dtype=bool)
             if fits.all() and not need_mask:
                 class_ids[key] = -1
             else:

@@ -676,3 +676,39 @@ def test_requirements_from_resource_list():  # api/resource_info/resource_requir
     assert rl({"kai.scheduler/test-resource": "1"}) == {4: 1000} and names.names[4] == "kai.scheduler/test-resource"
     assert rl({"unsupported": "2"}) == {}  # not a scalar resource name: not counted
     assert rl({"hugepages-2Mi": "1", "attachable-volumes-x": "1", "requests.foo/bar": "1"}) == {5: 1000, 6: 1000}
+
+
+def _slice(name, node, driver, count):  # cluster_info_test.go:2523-2539 createTestResourceSlice
+    return {"metadata": {"name": name}, "spec": {"nodeName": node, "driver": driver, "devices": [{"name": f"device-{i}"} for i in range(count)]}}
+
+
+def test_snapshot_nodes_with_dra_gpus():  # cluster_info_test.go:2411-2521 TestSnapshotNodesWithDRAGPUs
+    def dra(nodes, slices):
+        doc = _cluster(nodes=[{"metadata": {"name": n}, "spec": {}, "status": {"allocatable": {}}} for n in nodes])
+        doc["rawObjects"]["resourceSlices"] = slices
+        snap, meta, _, _ = sio.pack_cluster(doc)
+        return {n: (snap.node_allocatable[2, i], bool(snap.node_flags[i] & abi.NODE_NOT_CPU_ONLY)) for i, n in enumerate(meta["node_names"])}
+
+    assert dra(["node-1"], [_slice("slice-1", "node-1", "nvidia.com/gpu", 4)]) == {"node-1": (4, True)}
+    assert dra(["node-1", "node-2"], [_slice("slice-1", "node-1", "nvidia.com/gpu", 4), _slice("slice-2", "node-2", "nvidia.com/gpu", 8)]) == \
+        {"node-1": (4, True), "node-2": (8, True)}
+    assert dra(["node-1"], []) == {"node-1": (0, False)}
+    assert dra(["node-1"], [_slice("slice-nvidia", "node-1", "nvidia.com/gpu", 4), _slice("slice-amd", "node-1", "amd.com/gpu", 2)]) == \
+        {"node-1": (6, True)}
+    assert dra(["node-1"], [_slice("slice-net", "node-1", "example.com/nic", 3)]) == {"node-1": (0, False)}
+
+
+def test_device_plugin_gpu_pods_avoid_dra_nodes():  # node_info.go:326-333 PredicateByNodeResourcesType
+    doc = _cluster(nodes=[_node("dra-node", gpus=0), _node("plugin-node", gpus=2)], queues=[_queue("q", gpu=(-1, -1, 1))],
+                   pods=[_pod("gpu-pod", "g"), _pod("cpu-pod", "c", requests={"cpu": "1"})],
+                   pod_groups=[{"metadata": {"name": g, "namespace": "ns"}, "spec": {"queue": "q"}} for g in ("g", "c")])
+    doc["rawObjects"]["resourceSlices"] = [_slice("s", "dra-node", "gpu.nvidia.com", 8)]
+    snap, meta, kw, _ = sio.pack_cluster(doc)
+    t = {n: i for i, n in enumerate(meta["task_names"])}
+    gpu_class, cpu_class = snap.task_pred_class[t["gpu-pod"]], snap.task_pred_class[t["cpu-pod"]]
+    assert gpu_class >= 0 and int(snap.pred_mask[gpu_class, 0]) == 0b10  # only plugin-node (index 1)
+    assert cpu_class < 0 or int(snap.pred_mask[cpu_class, 0]) == 0b11
+    o = Oracle(abi.make_config(**kw))
+    o.load(snap)
+    res = o.run("allocate")
+    assert meta["node_names"][res.task_node[t["gpu-pod"]]] == "plugin-node"  # binpack would otherwise prefer... the DRA node is excluded
