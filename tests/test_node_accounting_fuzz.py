@@ -9,6 +9,10 @@ gives for the final task table (pkg/scheduler/api/node_info/node_info.go:337-420
     Pipelined on B (Statement.Pipeline with a different node adds the task to B and leaves A's entry alone,
     framework/statement.go:193-240); the result carries one (node, status) per task, so the entry on A is tracked here.
 
+The proportion plugin's per-queue Allocated / AllocatedNotPreemptible (open-session sum over allocated statuses plus the
+Allocate / Deallocate event handlers, plugins/proportion/proportion.go:347-372, :440-500) must likewise equal the sum over
+the final table's active-allocated tasks, accumulated up the queue's parent chain.
+
 Evicting a Pipelined task is legal (activeAllocatedStatuses includes Pipelined, pod_status.go:66) and can drive Idle below
 zero exactly as in the reference — the invariant is on the arithmetic, not on the sign.
 """
@@ -60,6 +64,10 @@ def test_node_vectors_follow_the_task_table(chunk):
         zero = np.zeros_like(snap.node_idle)
         used, held = _account(zero, zero, req, _entries(status, node, ghosts))
         base_free, base_rel = snap.node_idle - used, snap.node_releasing - held
+        task_job = np.zeros(snap.n_tasks, dtype=int)
+        for j in range(snap.n_jobs):
+            for ps in range(snap.job_podset_begin[j], snap.job_podset_begin[j + 1]):
+                task_job[snap.podset_task_begin[ps]:snap.podset_task_begin[ps + 1]] = j
         o = Oracle(abi.make_config(allow_consolidating_reclaim=True, max_consolidation_preemptees=-1))
         o.load(snap)
         for act in ACTIONS:
@@ -72,4 +80,15 @@ def test_node_vectors_follow_the_task_table(chunk):
             idle, rel = _account(base_free, base_rel, req, _entries(status, node, ghosts))
             np.testing.assert_allclose(res.node_idle, idle, rtol=0, atol=1e-9, err_msg=f"seed {seed} {act} idle")
             np.testing.assert_allclose(res.node_releasing, rel, rtol=0, atol=1e-9, err_msg=f"seed {seed} {act} releasing")
+            alloc, fixed = np.zeros((3, snap.n_queues)), np.zeros((3, snap.n_queues))
+            for t in np.flatnonzero(status & ACTIVE_ALLOCATED):
+                j, q = task_job[t], int(snap.job_queue[task_job[t]])
+                while q >= 0:
+                    alloc[:, q] += req[t, :3]
+                    if not int(snap.job_flags[j]) & abi.JOB_PREEMPTIBLE:
+                        fixed[:, q] += req[t, :3]
+                    q = int(snap.queue_parent[q])
+            np.testing.assert_allclose(res.queue_allocated, alloc, rtol=0, atol=1e-9, err_msg=f"seed {seed} {act} queue allocated")
+            np.testing.assert_allclose(res.queue_allocated_non_preemptible, fixed, rtol=0, atol=1e-9,
+                                       err_msg=f"seed {seed} {act} queue non-preemptible")
         o.close()
