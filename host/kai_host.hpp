@@ -79,6 +79,7 @@ struct PodGroupInfo {  // podgroup_info/job_info.go:65-103
   std::vector<std::shared_ptr<PodInfo>> Tasks;
   int SchedulingConstraintsSignature = -1;
   double LastStartTimestamp = -1;  // seconds on the session clock; <= 0 = nil (job_info.go:185-193)
+  double StaleTimeStamp = -1;      // StalenessInfo.TimeStamp, same clock; <= 0 = nil (job_info.go:174-182)
 };
 struct NodeInfo {  // node_info/node_info.go:68-105
   std::string Name;
@@ -230,7 +231,7 @@ struct Packed {
   std::vector<int32_t> level_begin, node_domain, jsgs, sgs_parent, sgs_rank, sgs_topo, sgs_req, sgs_pref, ps_sgs, ps_topo, ps_req, ps_pref;
   std::vector<uint32_t> nflags, jflags;
   std::vector<int64_t> qcreation;
-  std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start;
+  std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start, j_stale_since;
   std::vector<int32_t> tpred;
   std::vector<uint32_t> pred_mask;
 };
@@ -250,6 +251,7 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   p.q_preempt_mrt.clear();
   p.q_reclaim_mrt.clear();
   p.j_last_start.clear();
+  p.j_stale_since.clear();
   p.tpred.clear();
   p.pred_mask.clear();
   std::map<std::vector<std::string>, int> pred_classes;
@@ -322,6 +324,7 @@ inline void packSnapshot(Session &ssn, Packed &p) {
     p.jflags[j] = job.Preemptible ? KAI_JOB_PREEMPTIBLE : 0;
     p.jsig[j] = job.SchedulingConstraintsSignature;
     p.j_last_start.push_back(job.LastStartTimestamp);
+    p.j_stale_since.push_back(job.StaleTimeStamp);
     auto order = rank_of(job.Tasks, [](const std::shared_ptr<api::PodInfo> &t) { return std::make_pair(t->OrderKey, t->UID); });
     for (auto &ps : job.PodSets) {
       p.psmin.push_back(ps.MinAvailable);
@@ -491,6 +494,7 @@ inline void packSnapshot(Session &ssn, Packed &p) {
   c.queue_preempt_min_runtime_s = p.q_preempt_mrt.data();
   c.queue_reclaim_min_runtime_s = p.q_reclaim_mrt.data();
   c.job_last_start_s = p.j_last_start.data();
+  c.job_stale_since_s = p.j_stale_since.data();
   c.n_topologies = (int32_t)ci.Topologies.size();
   c.topology_level_begin = p.level_begin.data();
   c.node_domain = p.node_domain.data();

@@ -129,6 +129,12 @@ int main(int argc, char **argv) {
       std::string j;
       ls >> j;
       ls >> ssn.ClusterInfo.PodGroupInfos[j]->LastStartTimestamp;
+    } else if (kind == "jobstale") {  // jobstale <job> <stale since s | -1>
+      std::string j;
+      ls >> j;
+      ls >> ssn.ClusterInfo.PodGroupInfos[j]->StaleTimeStamp;
+    } else if (kind == "grace") {  // grace <GlobalDefaultStalenessGracePeriod s | -1>
+      ls >> ssn.Config.staleness_grace_period_s;
     } else if (kind == "actions") {
       std::string a;
       while (ls >> a) actions.push_back(a);
@@ -152,6 +158,10 @@ int main(int argc, char **argv) {
                c.podset_min_available[ps], c.podset_sgs[ps] - c.job_sgs_begin[j], c.podset_topology[ps],
                c.podset_required_level[ps], c.podset_preferred_level[ps]);
     }
+    for (int j = 0; j < c.n_jobs; j++)
+      if (c.job_stale_since_s && c.job_stale_since_s[j] > 0)
+        printf("stale %s %.17g now %.17g grace %d\n", ssn.idx_jobs[j]->UID.c_str(), c.job_stale_since_s[j], c.now_s,
+               ssn.Config.staleness_grace_period_s);
     for (int t = 0; t < c.n_tasks; t++) {
       if (!c.task_pred_class || c.task_pred_class[t] < 0) continue;
       printf("pred %s %d", ssn.idx_tasks[t]->UID.c_str(), c.task_pred_class[t]);

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KAI_ABI_VERSION 5
+#define KAI_ABI_VERSION 6
 #define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
 #define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
 #define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
@@ -118,8 +118,8 @@ typedef struct kai_config {
      a job with the same kai_snapshot.job_signature that already failed (actions/common/minimal_job_comparison.go). */
   int32_t use_scheduling_signatures;
   /* SchedulerParams.GlobalDefaultStalenessGracePeriod in seconds: < 0 = stale gangs are never evicted, 0 = evicted in
-     the cycle that finds them stale (the reference's tests); > 0 needs per-job staleness timestamps, which the
-     snapshot does not carry: treated as "not yet". */
+     the cycle that finds them stale; > 0 = evicted once `now_s - job_stale_since_s >= grace` (a job without a staleness
+     timestamp has just turned stale: not yet).  Production default 60 (cmd/scheduler/app/options/options.go). */
   int32_t staleness_grace_period_s;
   /* minruntime plugin arguments (plugins/minruntime/minruntime.go:24-78): `defaultReclaimMinRuntime`,
      `defaultPreemptMinRuntime` in seconds (negative or unparsable = 0) and `reclaimResolveMethod`. */
@@ -233,6 +233,10 @@ typedef struct kai_snapshot {
   const double *queue_preempt_min_runtime_s; /* [Q] */
   const double *queue_reclaim_min_runtime_s; /* [Q] */
   const double *job_last_start_s;            /* [J] seconds on the clock of now_s */
+  /* ---- stale gangs (actions/stalegangeviction/stalegangeviction.go:42-62): PodGroupInfo.StalenessInfo.TimeStamp, read
+         from the PodGroup's `kai.scheduler/stale-podgroup-timestamp` annotation (job_info.go:174-182), on the clock of
+         now_s; <= 0 = nil (the action stamps time.Now(), i.e. zero time in stale state).  NULL = nil for all jobs. ---- */
+  const double *job_stale_since_s;           /* [J] */
 } kai_snapshot;
 
 /* One entry per job popped by an action, in visiting order. */

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-KAI_ABI_VERSION = 5
+KAI_ABI_VERSION = 6
 KAI_MAX_RES = 8
 KAI_QRES = 3
 RES_CPU, RES_MEM, RES_GPU, RES_PODS = 0, 1, 2, 3
@@ -89,7 +89,7 @@ class KaiSnapshot(C.Structure):
         ("sgs_required_level", _ip), ("sgs_preferred_level", _ip), ("podset_sgs", _ip), ("podset_topology", _ip),
         ("podset_required_level", _ip), ("podset_preferred_level", _ip),
         ("now_s", C.c_double), ("queue_preempt_min_runtime_s", _dp), ("queue_reclaim_min_runtime_s", _dp),
-        ("job_last_start_s", _dp),
+        ("job_last_start_s", _dp), ("job_stale_since_s", _dp),
     ]
 
 
@@ -186,6 +186,7 @@ class Snapshot:
     queue_preempt_min_runtime_s: np.ndarray | None = None  # [Q] f64 seconds, < 0 = not set
     queue_reclaim_min_runtime_s: np.ndarray | None = None
     job_last_start_s: np.ndarray | None = None             # [J] f64 seconds, <= 0 = never started
+    job_stale_since_s: np.ndarray | None = None            # [J] f64 seconds, <= 0 = no staleness timestamp (stalegangeviction)
     names: dict = field(default_factory=dict)  # optional: node/job/task/queue names for reporting
     _keep: list = field(default_factory=list, repr=False)
 
@@ -280,7 +281,7 @@ class Snapshot:
                      "podset_sgs", "podset_topology", "podset_required_level", "podset_preferred_level"):
             setattr(s, name, p(getattr(self, name), np.int32, _ip))
         s.now_s = float(self.now_s)
-        for name in ("queue_preempt_min_runtime_s", "queue_reclaim_min_runtime_s", "job_last_start_s"):
+        for name in ("queue_preempt_min_runtime_s", "queue_reclaim_min_runtime_s", "job_last_start_s", "job_stale_since_s"):
             setattr(s, name, p(getattr(self, name), np.float64, _dp))
         self._keep = keep
         return s

@@ -135,6 +135,7 @@ struct kai_engine {
   bool mirror_valid = false;  // h_ig / h_lg followed every delta since the load (host-sequenced actions only)
   std::vector<int> job_signature;
   std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start;  // plugins/minruntime inputs (host only)
+  std::vector<double> j_stale_since;                               // stalegangeviction input (host only)
   double now_s = 0;
   size_t dev_only_begin = 0, dev_only_bytes = 0;
   std::vector<int> task_perm;
@@ -740,10 +741,12 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->q_preempt_mrt.clear();
   e->q_reclaim_mrt.clear();
   e->j_last_start.clear();
+  e->j_stale_since.clear();
   e->now_s = s->now_s;
   if (s->queue_preempt_min_runtime_s) e->q_preempt_mrt.assign(s->queue_preempt_min_runtime_s, s->queue_preempt_min_runtime_s + s->n_queues);
   if (s->queue_reclaim_min_runtime_s) e->q_reclaim_mrt.assign(s->queue_reclaim_min_runtime_s, s->queue_reclaim_min_runtime_s + s->n_queues);
   if (s->job_last_start_s) e->j_last_start.assign(s->job_last_start_s, s->job_last_start_s + s->n_jobs);
+  if (s->job_stale_since_s) e->j_stale_since.assign(s->job_stale_since_s, s->job_stale_since_s + s->n_jobs);
   e->loaded = true;
   return KAI_OK;
 }
@@ -1028,6 +1031,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       solver.q_preempt_mrt = e->q_preempt_mrt.empty() ? nullptr : e->q_preempt_mrt.data();
       solver.q_reclaim_mrt = e->q_reclaim_mrt.empty() ? nullptr : e->q_reclaim_mrt.data();
       solver.j_last_start = e->j_last_start.empty() ? nullptr : e->j_last_start.data();
+      solver.j_stale_since = e->j_stale_since.empty() ? nullptr : e->j_stale_since.data();
       solver.now_s = e->now_s;
       if (action == KAI_ACTION_RECLAIM)
         solver.run_reclaim();

@@ -1127,6 +1127,7 @@ struct Solver {
   }
   // ---------------- plugins/minruntime ----------------
   const double *q_preempt_mrt = nullptr, *q_reclaim_mrt = nullptr, *j_last_start = nullptr;  // see kai_engine.h
+  const double *j_stale_since = nullptr;                                                      // StalenessInfo.TimeStamp
   double now_s = 0;
   double preempt_min_runtime(int q) const {  // resolver.go:46-67
     for (int c = q; c >= 0; c = s.q_parent[c])
@@ -1643,8 +1644,11 @@ struct Solver {
   // ---------------- actions/stalegangeviction/stalegangeviction.go:29-95 ----------------
   void run_stale_gang_eviction() {
     prepare();
-    if (cfg.staleness_grace_period_s != 0) return;
+    if (cfg.staleness_grace_period_s < 0) return;  // :47-50 negative duration means no eviction
     for (int j = 0; j < J && !gpu_failed(); j++) {
+      // :42-57 nil TimeStamp = stamped now = zero time in stale state; else time.Since(TimeStamp) at the snapshot's instant
+      double in_stale = (j_stale_since && j_stale_since[j] > 0) ? now_s - j_stale_since[j] : 0.0;
+      if (in_stale < double(cfg.staleness_grace_period_s)) continue;
       if (count_job(j, KAI_POD_SUCCEEDED) > 0 || count_job(j, kActiveUsed) == 0) continue;  // job_info.go:417-432
       bool stale = false;
       for (int ps = ps_begin(j); ps < ps_end(j); ps++)

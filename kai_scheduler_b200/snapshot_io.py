@@ -40,6 +40,7 @@ GPU_COUNT_LABEL = "nvidia.com/gpu.count"  # constants.go:55
 TASK_ORDER_LABEL = "kai.scheduler/task-priority"
 DEFAULT_SUBGROUP = "default-sub-group"
 LAST_START_ANNOTATION = "kai.scheduler/last-start-timestamp"  # constants.go:43
+STALE_ANNOTATION = "kai.scheduler/stale-podgroup-timestamp"  # constants.go:42
 DEFAULT_QUEUE_PRIORITY = 100  # constants.go:13
 DEFAULT_PODGROUP_PRIORITY = 50  # constants.go:14
 NON_PREEMPTIBLE_THRESHOLD = 100  # pkg/common/podgroup/preemptible.go:10
@@ -685,7 +686,7 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
 
     pgs = sorted((g for g in raw.get("podGroups") or [] if in_partition(g) and up_for_scheduler(g)),
                  key=lambda g: g["metadata"]["name"].encode())
-    job_names, job_queue, job_prio, job_flags, job_created, job_last_start = [], [], [], [], [], []
+    job_names, job_queue, job_prio, job_flags, job_created, job_last_start, job_stale_since = [], [], [], [], [], [], []
     job_podset_begin, podset_min, podset_task_begin = [0], [], [0]
     t_status, t_node, t_req, t_rank, t_names, t_uids, t_job, t_cons, t_nominated = [], [], [], [], [], [], [], [], []
     job_sgs_begin, sgs_parent, sgs_names, sgs_con, ps_sgs, ps_con = [0], [], [], [], [], []
@@ -711,6 +712,11 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
             job_last_start.append(float(_epoch(started)) if started else -1.0)
         except ValueError:
             job_last_start.append(-1.0)
+        stale = (pg["metadata"].get("annotations") or {}).get(STALE_ANNOTATION)
+        try:  # job_info.go:174-182 StalenessInfo.TimeStamp, an unparsable value is ignored
+            job_stale_since.append(float(_epoch(stale)) if stale else -1.0)
+        except ValueError:
+            job_stale_since.append(-1.0)
 
         # SubGroup tree: entries with children are sets, the others PodSets
         subgroups = spec.get("subGroups") or []
@@ -867,12 +873,14 @@ def pack_cluster(doc: dict, strict: bool = True, now: float | None = None):
                   podset_topology=np.array([c[0] for c in ps_con], dtype=np.int32).reshape(-1),
                   podset_required_level=np.array([c[1] for c in ps_con], dtype=np.int32).reshape(-1),
                   podset_preferred_level=np.array([c[2] for c in ps_con], dtype=np.int32).reshape(-1))
-    if (q_pre_mrt >= 0).any() or (q_rec_mrt >= 0).any() or any(v > 0 for v in job_last_start):
+    if (q_pre_mrt >= 0).any() or (q_rec_mrt >= 0).any() or any(v > 0 for v in job_last_start + job_stale_since):
         import time
         captured = doc.get("capturedAt")
         kw.update(queue_preempt_min_runtime_s=q_pre_mrt, queue_reclaim_min_runtime_s=q_rec_mrt,
                   job_last_start_s=np.array(job_last_start, dtype=np.float64).reshape(J),
                   now_s=float(_epoch(captured)) if captured else (float(now) if now is not None else time.time()))
+        if any(v > 0 for v in job_stale_since):
+            kw["job_stale_since_s"] = np.array(job_stale_since, dtype=np.float64).reshape(J)
     usage = _queue_usage(doc, queue_names)
     if usage is not None:
         kw["queue_usage"] = usage
@@ -1051,6 +1059,10 @@ def dump_cluster(snap: "abi.Snapshot", actions=("allocate",), config: dict | Non
             if snap.job_last_start_s[j] != int(snap.job_last_start_s[j]):
                 raise UnsupportedSnapshot("sub-second last-start timestamps (RFC 3339 annotation)")
             pg_md["annotations"] = {LAST_START_ANNOTATION: _rfc3339(int(snap.job_last_start_s[j]))}
+        if snap.job_stale_since_s is not None and snap.job_stale_since_s[j] > 0:
+            if snap.job_stale_since_s[j] != int(snap.job_stale_since_s[j]):
+                raise UnsupportedSnapshot("sub-second staleness timestamps (RFC 3339 annotation)")
+            pg_md.setdefault("annotations", {})[STALE_ANNOTATION] = _rfc3339(int(snap.job_stale_since_s[j]))
         pod_groups.append({"metadata": pg_md, "spec": spec})
         for ps in range(b, e):
             for t in range(int(snap.podset_task_begin[ps]), int(snap.podset_task_begin[ps + 1])):
@@ -1127,7 +1139,7 @@ def dump_cluster(snap: "abi.Snapshot", actions=("allocate",), config: dict | Non
            "schedulerParams": params,
            "rawObjects": {"pods": pods, "nodes": nodes, "queues": queues, "podGroups": pod_groups,
                           "bindRequests": bind_requests, "priorityClasses": priority_classes, "topologies": topologies}}
-    if snap.job_last_start_s is not None or snap.queue_preempt_min_runtime_s is not None:
+    if snap.job_last_start_s is not None or snap.queue_preempt_min_runtime_s is not None or snap.job_stale_since_s is not None:
         if snap.now_s != int(snap.now_s):
             raise UnsupportedSnapshot("sub-second capture time")
         doc["capturedAt"] = _rfc3339(int(snap.now_s))  # extension: the reference's tool uses time.Now() at replay

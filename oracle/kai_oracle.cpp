@@ -2189,6 +2189,7 @@ struct kai_oracle {
   }
   // ---------------- plugins/minruntime ----------------
   std::vector<double> q_preempt_mrt, q_reclaim_mrt, j_last_start;  // seconds; < 0 = nil; last start <= 0 = nil
+  std::vector<double> j_stale_since;                               // StalenessInfo.TimeStamp, <= 0 = nil
   double now_s = 0;
   // resolver.go:46-67 resolvePreemptMinRuntime: first value set on the queue or an ancestor, else the default
   double preempt_min_runtime(int q) const {
@@ -2680,9 +2681,13 @@ struct kai_oracle {
   }
   // ---------------- actions/stalegangeviction/stalegangeviction.go:29-95 ----------------
   void run_stale_gang_eviction() {
-    if (cfg.staleness_grace_period_s != 0) return;  // < 0: never; > 0: needs staleness timestamps (not in the snapshot)
+    if (cfg.staleness_grace_period_s < 0) return;  // :47-50 negative duration means no eviction
     for (int ji = 0; ji < NJ; ji++) {
       const Job &j = J[ji];
+      // :42-57 a nil TimeStamp is stamped with time.Now(): zero time in stale state, which only a zero grace period lets
+      // through; otherwise time.Since(TimeStamp) on the snapshot's single instant
+      double in_stale = (!j_stale_since.empty() && j_stale_since[ji] > 0) ? now_s - j_stale_since[ji] : 0.0;
+      if (in_stale < double(cfg.staleness_grace_period_s)) continue;
       if (job_count(j, KAI_POD_SUCCEEDED) > 0) continue;  // job_info.go:417-432 IsStale
       if (job_count(j, kActiveUsed) == 0) continue;
       bool stale = false;
@@ -2918,9 +2923,11 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
   o->q_preempt_mrt.clear();
   o->q_reclaim_mrt.clear();
   o->j_last_start.clear();
+  o->j_stale_since.clear();
   if (s->queue_preempt_min_runtime_s) o->q_preempt_mrt.assign(s->queue_preempt_min_runtime_s, s->queue_preempt_min_runtime_s + o->NQ);
   if (s->queue_reclaim_min_runtime_s) o->q_reclaim_mrt.assign(s->queue_reclaim_min_runtime_s, s->queue_reclaim_min_runtime_s + o->NQ);
   if (s->job_last_start_s) o->j_last_start.assign(s->job_last_start_s, s->job_last_start_s + o->NJ);
+  if (s->job_stale_since_s) o->j_stale_since.assign(s->job_stale_since_s, s->job_stale_since_s + o->NJ);
   o->J.assign(o->NJ, Job());
   o->PS.assign(o->NS, PodSet());
   o->T.assign(o->NT, Task());

@@ -32,6 +32,9 @@ def _parse_quantity_cpu(cores: float) -> float:
     return float(cores) * 1000.0
 
 
+DSL_NOW_S = 1.7e9  # the session instant of tables that carry durations
+
+
 def build_snapshot(topo: dict):
     """Return (Snapshot, meta) for a transcribed TestTopologyBasic.
 
@@ -324,6 +327,11 @@ def build_snapshot(topo: dict):
         task_req=t_req_a, task_order_rank=np.array(t_rank, dtype=np.int32),
         **topo_kw, **pred_kw,
     )
+    if any(j.get("StaleDuration") is not None for j in jobs):
+        # jobs_fake/jobs.go:50,92 StaleDuration -> StalenessInfo.TimeStamp = now - duration (seconds in the fixtures)
+        snap.now_s = DSL_NOW_S
+        snap.job_stale_since_s = np.array([DSL_NOW_S - float(j["StaleDuration"]) if j.get("StaleDuration") is not None else -1.0
+                                           for j in jobs], dtype=np.float64)
     meta = {
         "node_names": node_names, "job_names": job_names, "task_names": t_names,
         "task_job": np.array(t_job, dtype=np.int32), "queue_names": qnames, "task_fixture_node": t_fixture_node,

@@ -76,6 +76,8 @@ def resolve(x):
                 return {"podsets": [{"name": "default-sub-group", "min_available": resolve(x["args"][0])}]}
             if x["__call"].startswith("test_utils.Create") and len(x["args"]) == 1:
                 return resolve(x["args"][0])
+            if x["__call"] == "pointer.Duration" and len(x["args"]) == 1:  # seconds (IDENTS: time.Second = 1)
+                return resolve(x["args"][0])
             if x["__call"] == "subgroup_info.NewSubGroupSet":
                 # inline root set: NewSubGroupSet(RootSubGroupSetName, &TopologyConstraintInfo{...} | nil); the default
                 # podset (minAvailable = len(Tasks)) is added by jobs_fake.BuildJobInfo (jobs.go:117-134)
@@ -183,6 +185,10 @@ def normalise(topo: dict) -> dict:
     nodes = topo.get("Nodes")
     if isinstance(nodes, dict) and nodes.get("__call") == "buildEvenlyDistributedTopologyNodes":
         topo["Nodes"] = evenly_distributed_topology_nodes(*[int(a) for a in nodes["args"]])
+    if isinstance(topo.get("Nodes"), dict):
+        for name, node in topo["Nodes"].items():
+            if node == []:  # `"node-1": {}` — an empty TestNodeBasic literal
+                topo["Nodes"][name] = {}
     mocks = topo.get("Mocks")
     conf = mocks.get("SchedulerConf") if isinstance(mocks, dict) else None
     if isinstance(conf, dict):
@@ -229,8 +235,8 @@ def classify(topo: dict) -> str | None:
             return "fractional GPU"
         if job.get("RequiredGpuMemory") or job.get("RequiredMultiFractionDevicesPerTask"):
             return "GPU memory / multi-fraction"
-        if job.get("DeleteJobInTest") or job.get("StaleDuration") is not None:
-            return "deletion / staleness"
+        if job.get("DeleteJobInTest"):
+            return "deletion in test"
         for t in job.get("Tasks") or []:
             for k in ("PodAffinityLabels", "PodAffinityTopologyKey",
                       "PodAntiAffinityTopologyKey", "RequiredMigInstances", "IsLegacyMigTask",
@@ -264,6 +270,8 @@ ACTION_SUITES = [
     ("preempt/preemptGang_test.go", ["preempt"]),
     ("preempt/preempt_elastic_test.go", ["preempt"]),
     ("preempt/preempt_subgroups_test.go", ["preempt"]),
+    # the driver overrides the grace period: ssn.OverrideGlobalDefaultStalenessGracePeriod(60 * time.Second) (:407)
+    ("stalegangeviction/stalegangeviction_test.go", ["stalegangeviction"]),
     # integration tables run the whole default action list for several rounds
     ("integration_tests/allocate/allocate_test.go", ["allocate", "consolidation", "reclaim", "preempt", "stalegangeviction"]),
     ("integration_tests/reclaim/reclaim_test.go", ["allocate", "consolidation", "reclaim", "preempt", "stalegangeviction"]),
@@ -305,9 +313,13 @@ def gen_actions():
             for topo in find_literals(src, "test_utils.TestTopologyBasic"):
                 cases.append((resolve(topo), None, None))
         out = []
+        wrapper_names = re.findall(r'^\t\t\tname:\s*"([^"]*)"', src, flags=re.M)
         for i, (topo, r_until, r_after) in enumerate(cases):
             topo.pop("__type", None)
             config = normalise(topo)
+            if rel.startswith("stalegangeviction/"):
+                config["staleness_grace_period_s"] = 60
+                topo.setdefault("Name", wrapper_names[i])  # the table keeps the name beside the topology (`name:`)
             reason = classify(topo)
             out.append({
                 "source": f"pkg/scheduler/actions/{rel}",

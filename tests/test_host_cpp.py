@@ -105,6 +105,11 @@ def write_case(path, snap: abi.Snapshot, meta: dict, actions, topo=None, cfg: di
         if snap.job_last_start_s is not None:
             for j, name in enumerate(meta["job_names"]):
                 f.write(f"jobstart {name} {float(snap.job_last_start_s[j])!r}\n")
+        if snap.job_stale_since_s is not None:
+            for j, name in enumerate(meta["job_names"]):
+                f.write(f"jobstale {name} {float(snap.job_stale_since_s[j])!r}\n")
+        if "staleness_grace_period_s" in cfg:
+            f.write(f"grace {int(cfg['staleness_grace_period_s'])}\n")
         f.write("actions " + " ".join(actions) + "\n")
 
 
@@ -155,6 +160,26 @@ def test_cpp_packing_of_topologies_and_subgroup_tree(cid, case):
             c = snap.task_pred_class[t]
             want = [] if c < 0 else [int(x) for x in snap.pred_mask[c]]
             assert masks.get(name, []) == want, name
+
+
+STALE_CASES = action_cases(["stalegangeviction__"], single_action="stalegangeviction")
+
+
+@pytest.mark.parametrize("cid,case", STALE_CASES, ids=[c[0] for c in STALE_CASES])
+def test_cpp_packing_of_staleness(cid, case):
+    """PodGroupInfo.StalenessInfo.TimeStamp and the grace period reach the C ABI unchanged (no GPU)."""
+    _build()
+    snap, meta = dsl.build_snapshot(case["topology"])
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "case.txt")
+        write_case(path, snap, meta, case["actions"], case["topology"], cfg=case["config"])
+        out = subprocess.run([BIN, path, "--dump-packed"], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {f[1]: (float(f[2]), float(f[4]), int(f[6])) for f in (l.split() for l in out) if f and f[0] == "stale"}
+    want = {}
+    if snap.job_stale_since_s is not None:
+        want = {n: (float(snap.job_stale_since_s[j]), float(snap.now_s), 60) for j, n in enumerate(meta["job_names"])
+                if snap.job_stale_since_s[j] > 0}
+    assert got == want
 
 
 class _Res:

@@ -275,7 +275,8 @@ def test_identical_pod_groups_share_a_signature():
 
 # ---------------------------------------------------------------------------------------------- reference tables
 TABLES = (action_cases(["allocate__"], single_action="allocate") + action_cases(["reclaim__"], single_action="reclaim")
-          + action_cases(["consolidation__"], single_action="consolidation") + action_cases(["preempt__"], single_action="preempt"))
+          + action_cases(["consolidation__"], single_action="consolidation") + action_cases(["preempt__"], single_action="preempt")
+          + action_cases(["stalegangeviction__"], single_action="stalegangeviction"))
 _trip_stats = {"run": 0, "skipped": 0}
 
 
@@ -315,7 +316,7 @@ def _round_trip(snap, actions, names=None, config=None, affinity=None):
 def test_reference_tables_through_the_wire_format(cid, case):
     snap, meta = dsl.build_snapshot(case["topology"])
     place = {"binpack": abi.PLACEMENT_BINPACK, "spread": abi.PLACEMENT_SPREAD}
-    config = {k: place[v] for k, v in (case.get("config") or {}).items()}
+    config = {k: place[v] if isinstance(v, str) else v for k, v in (case.get("config") or {}).items()}
     if case_needs_predicates(case):  # the table's node affinity goes back into the pods, the packer re-derives the masks
         snap.task_pred_class = snap.pred_mask = None
     try:
