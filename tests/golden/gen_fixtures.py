@@ -630,3 +630,74 @@ def gen_capacity_policy():
 
 if __name__ == "__main__":
     print("capacity_policy:", gen_capacity_policy())
+
+
+def gen_capacity_checks():
+    """plugins/proportion/capacity_policy/max_allowed_check_test.go:38-208 (isOverLimit), :211-459 (resultsOverLimit) and
+    quota_check_test.go:32-130 (isAllocatedNonPreemptibleOverQuota), :132-338 (resultsWithNonPreemptibleOverQuota) ->
+    tests/golden/capacity_checks.json, in the schema of capacity_policy.json (`req` is the table's requested share)."""
+    fields = ("Deserved", "FairShare", "Allocated", "AllocatedNotPreemptible", "MaxAllowed")
+    res_key = {"rs.CpuResource": "CPU", "rs.MemoryResource": "Memory", "rs.GpuResource": "GPU"}
+
+    def quantities(m):
+        m = resolve(m) if m else {}
+        return {res_key[k]: _num(v) for k, v in m.items() if k in res_key}
+
+    def tables(fname):
+        src = open(os.path.join(REF, "plugins", "proportion", "capacity_policy", fname)).read()
+        pos = 0
+        while True:
+            a = src.find("tests := map[string]struct {", pos)
+            if a < 0:
+                return
+            b = src.index("for name, data := range tests", a)
+            pos = b
+            blk = src[a:b]
+            yield find_literals("tests := map[string]caseT" + blk[blk.index("}{") + 1:], "map[string]caseT")[0]
+
+    out = []
+    for fname, flat_fn, tree_fn in (("max_allowed_check_test.go", "isOverLimit", "resultsOverLimit"),
+                                    ("quota_check_test.go", "isAllocatedNonPreemptibleOverQuota", "resultsWithNonPreemptibleOverQuota")):
+        flat, tree = list(tables(fname))
+        limit = flat_fn == "isOverLimit"
+        for name, case in flat.items():
+            if name.startswith("__"):
+                continue
+            # the Ginkgo body writes two fields of one queue's shares (EmptyResource() otherwise) and calls the check
+            a = quantities(case.get("maxAllowed" if limit else "deserved"))
+            b = quantities(case.get("allocated" if limit else "allocatedNonPreemptible"))
+            share = {res: {f: 0.0 for f in fields} for res in ("CPU", "Memory", "GPU")}
+            for res in share:
+                share[res]["MaxAllowed" if limit else "Deserved"] = a.get(res, 0.0)
+                share[res]["Allocated" if limit else "AllocatedNotPreemptible"] = b.get(res, 0.0)
+                if not limit:
+                    share[res]["MaxAllowed"] = -1.0
+            req = quantities(case.get("requestedQuota"))
+            over = bool(case.get("isOverMaxAllowed" if limit else "expectedResult"))
+            out.append({"function": flat_fn, "name": name, "queues": {"queue": {"parent": "", **share}}, "queue": "queue",
+                        "req": [req.get("CPU", 0.0), req.get("Memory", 0.0), req.get("GPU", 0.0)],
+                        "preemptible": limit, "schedulable": not over})
+        for name, case in tree.items():
+            if name.startswith("__"):
+                continue
+            queues = {}
+            for qid, q in case["queues"].items():
+                if qid.startswith("__"):
+                    continue
+                sh = q.get("QueueResourceShare") or {}
+                queues[qid] = {"parent": q.get("ParentQueue", ""),
+                               **{res: {f: _num(resolve((sh.get(res) or {}).get(f, 0))) for f in fields} for res in ("CPU", "Memory", "GPU")}}
+            job = case["job"]
+            req = quantities(case.get("requestedShare"))
+            pre = (job.get("Preemptibility") or {}).get("__ident", "")
+            out.append({"function": tree_fn, "name": name, "queues": queues, "queue": job["Queue"],
+                        "req": [req.get("CPU", 0.0), req.get("Memory", 0.0), req.get("GPU", 0.0)],
+                        # resultsOverLimit does not look at preemptibility; the quota check returns early for a preemptible job
+                        "preemptible": True if limit else pre.endswith(".Preemptible"), "schedulable": bool(case["expectedResult"])})
+    with open(os.path.join(HERE, "capacity_checks.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return len(out)
+
+
+if __name__ == "__main__":
+    print("capacity_checks:", gen_capacity_checks())

@@ -248,3 +248,29 @@ def test_capacity_policy(case):
 
 def test_capacity_policy_tables_are_complete():
     assert len(CAPACITY) == 14
+
+
+# max_allowed_check_test.go (isOverLimit 8, resultsOverLimit 6) and quota_check_test.go (isAllocatedNonPreemptibleOverQuota 4,
+# resultsWithNonPreemptibleOverQuota 5): the two halves of the policy on their own, with the table's requested share
+CHECKS = json.load(open(os.path.join(GOLDEN, "capacity_checks.json")))
+
+
+@pytest.mark.parametrize("case", CHECKS, ids=[f"{c['function']}: {c['name']}" for c in CHECKS])
+def test_capacity_checks(case):
+    l = lib()
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    l.kai_oracle_capacity_schedulable.argtypes = [C.c_int, ip, dp, C.c_int, C.c_int, dp, C.c_int]
+    names = list(case["queues"])
+    idx = {n: i for i, n in enumerate(names)}
+    _p, pp = _ip([idx.get(case["queues"][n]["parent"], -1) for n in names])
+    _s, ps = _dp([[[case["queues"][n][r][f] for f in FIELDS5] for r in RES] for n in names])
+    _r, pr = _dp(case["req"])
+    quota_only = case["function"] in ("isAllocatedNonPreemptibleOverQuota", "resultsWithNonPreemptibleOverQuota")
+    got = l.kai_oracle_capacity_schedulable(len(names), pp, ps, idx[case["queue"]], int(case["preemptible"]), pr, int(quota_only))
+    assert bool(got) == case["schedulable"]
+
+
+def test_capacity_check_tables_are_complete():
+    from collections import Counter
+    assert Counter(c["function"] for c in CHECKS) == {"isOverLimit": 8, "resultsOverLimit": 6,
+                                                      "isAllocatedNonPreemptibleOverQuota": 4, "resultsWithNonPreemptibleOverQuota": 5}
