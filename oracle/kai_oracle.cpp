@@ -3329,6 +3329,32 @@ int kai_oracle_capacity_schedulable(int n_queues, const int32_t *parent, const d
   return (mode == 0 ? o.over_capacity(0, req) : o.non_preemptible_over_quota(0, req)) ? 0 : 1;
 }
 
+void kai_oracle_queue_attributes(const double *share, const double *total, double *out) {
+  QueueAttr q;
+  for (int r = 0; r < QR; r++) {
+    const double *x = share + (size_t)r * 6;
+    q.s[r].deserved = x[0];
+    q.s[r].fair = x[1];
+    q.s[r].allocated = x[2];
+    q.s[r].alloc_np = x[3];
+    q.s[r].max_allowed = x[4];
+    q.s[r].request = x[5];
+  }
+  out[0] = dominant_share(q, total);
+  for (int r = 0; r < QR; r++) {
+    out[1 + r] = allocatable_share(q.s[r]);
+    out[4 + r] = requestable_share(q.s[r]);
+  }
+}
+int kai_oracle_compare_quantities(double a, double b) { return compare_quantities(a, b); }
+int kai_oracle_quantities_relation(int kind, const double *a, const double *b) {
+  if (kind == 1) return q_less_equal(a, b) ? 1 : 0;
+  if (kind == 2) return q_less_equal(b, a) ? 0 : 1;  // :66-68 !other.LessEqual(rq)
+  for (int r = 0; r < QR; r++)                        // :49-56 plain comparison, no "unlimited" handling
+    if (a[r] >= b[r]) return 0;
+  return 1;
+}
+
 // strategies.go: one reclaim strategy on two queue rows (share[3][5] each, as above) and a remaining share[3];
 // strategy 0 = MaintainFairShareStrategy, 1 = GuaranteeDeservedQuotaStrategy
 int kai_oracle_reclaim_strategy(int strategy, const double *reclaimer_share, const double *reclaimee_share,

@@ -104,6 +104,13 @@ int kai_oracle_reclaim_strategy(int strategy, const double *reclaimer_share, con
 int kai_oracle_reclaimable(int n_queues, const int32_t *parent, const double *share, double saturation_multiplier,
                            int reclaimer_queue, int preemptible, const double *req, int n_victims,
                            const int32_t *victim_queue, const double *victim_res);
+/* resource_share/{resource_share,queue_resource_share,resource_quantities}.go on one queue row share[3][6] = {Deserved,
+   FairShare, Allocated, AllocatedNotPreemptible, MaxAllowed, Request}: out[0] = GetDominantResourceShare(total),
+   out[1..3] = GetAllocatableShare per resource, out[4..6] = GetRequestableShare per resource. */
+void kai_oracle_queue_attributes(const double *share, const double *total, double *out);
+/* resource_quantities.go:81-97 compareQuantities; :48-79 Less (kind 0), LessEqual (1), LessInAtLeastOneResource (2) */
+int kai_oracle_compare_quantities(double a, double b);
+int kai_oracle_quantities_relation(int kind, const double *a, const double *b);
 /* plugins/minruntime/resolver.go on the loaded snapshot's queue tree: getReclaimMinRuntime (method of the config)
    for (pending queue, victim queue) when reclaim != 0, else getPreemptMinRuntime(victim queue); -1 = nil queue. */
 double kai_oracle_min_runtime(kai_oracle *o, int reclaim, int pending_queue, int victim_queue);
