@@ -3329,6 +3329,12 @@ int kai_oracle_capacity_schedulable(int n_queues, const int32_t *parent, const d
   return (mode == 0 ? o.over_capacity(0, req) : o.non_preemptible_over_quota(0, req)) ? 0 : 1;
 }
 
+int kai_oracle_feasible_nodes(kai_oracle *o, int job, int32_t *out) {
+  if (!o || job < 0 || job >= o->NJ) return KAI_ERR_INVALID;
+  std::vector<char> f = o->feasible_nodes_for_job(job);
+  for (int n = 0; n < o->N; n++) out[n] = f[n];
+  return KAI_OK;
+}
 void kai_oracle_queue_attributes(const double *share, const double *total, double *out) {
   QueueAttr q;
   for (int r = 0; r < QR; r++) {

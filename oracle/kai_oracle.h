@@ -104,6 +104,8 @@ int kai_oracle_reclaim_strategy(int strategy, const double *reclaimer_share, con
 int kai_oracle_reclaimable(int n_queues, const int32_t *parent, const double *share, double saturation_multiplier,
                            int reclaimer_queue, int preemptible, const double *req, int n_victims,
                            const int32_t *victim_queue, const double *victim_res);
+/* actions/common/feasible_nodes.go:11-26 FeasibleNodesForJob on the loaded snapshot: out[n_nodes] = 1 for kept nodes */
+int kai_oracle_feasible_nodes(kai_oracle *o, int job, int32_t *out);
 /* resource_share/{resource_share,queue_resource_share,resource_quantities}.go on one queue row share[3][6] = {Deserved,
    FairShare, Allocated, AllocatedNotPreemptible, MaxAllowed, Request}: out[0] = GetDominantResourceShare(total),
    out[1..3] = GetAllocatableShare per resource, out[4..6] = GetRequestableShare per resource. */
