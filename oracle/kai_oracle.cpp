@@ -3232,7 +3232,9 @@ void kai_oracle_priority_queue_exercise(int max_size, int n_ops, const int32_t *
 
 // idle_gpus/common.go:34-64 greedyMatchRequirements (both arrays sorted descending by the caller)
 int kai_oracle_greedy_match(int n_req, const double *req, int n_holders, const double *capacity) {
-  return kai_oracle::greedy_match_requirements(std::vector<double>(req, req + n_req), std::vector<double>(capacity, capacity + n_holders)) ? 1 : 0;
+  if (n_req < 0 || n_holders < 0 || (n_req && !req) || (n_holders && !capacity)) return KAI_ERR_INVALID;
+  std::vector<double> r(req, req + n_req), c(capacity, capacity + n_holders);
+  return kai_oracle::greedy_match_requirements(r, c) ? 1 : 0;
 }
 
 // podgroup_info.GetTasksToAllocate (allocation_info.go:27-54) of one job of the loaded snapshot: task indices in
