@@ -336,9 +336,10 @@ struct Solver {
   }
   void node_remove_task(int t, int n) {  // :515-551 with the status of the clone stored on the node
     int e = find_on(t, n);
-    int status = e < 0 ? on_status0[t] : (e == 0 ? on_status0 : on_status1)[t];
+    if (e < 0) return;  // node_info.go:495-501: a pod that is no longer on the node is an error, the node is untouched
+    int status = (e == 0 ? on_status0 : on_status1)[t];
     node_delta(t, n, status == KAI_POD_RELEASING ? ND_REM_RELEASING : (status == KAI_POD_PIPELINED ? ND_REM_PIPELINED : ND_REM));
-    if (e >= 0) (e == 0 ? on_node0 : on_node1)[t] = -1;
+    (e == 0 ? on_node0 : on_node1)[t] = -1;
   }
   // jobs with Pending tasks (utils.GetAllPendingJobs, actions/utils/action.go:122-130), kept as statuses change
   std::vector<int> pending_cnt;

@@ -42,6 +42,10 @@ def _workloads():
     snap.queue_reclaim_min_runtime_s = rng.choice(np.array([-1.0, 0.0, 20.0, 100.0]), size=snap.n_queues)
     snap.queue_preempt_min_runtime_s = rng.choice(np.array([-1.0, 10.0, 100.0]), size=snap.n_queues)
     out["victims-min-runtime"] = (snap, dict(default_reclaim_min_runtime_s=30.0, default_preempt_min_runtime_s=30.0), ["reclaim"])
+    # the full-cycle workload of tests/test_engine_gpu.py (consolidation reaches the RemoveTask no-op, node_info.go:495-513)
+    snap = synthetic.reclaim_snapshot(n_nodes=48, running_per_node=7, victim_queues=2, reclaimer_jobs=12, reclaimer_tasks=2,
+                                      reclaimer_gpus=3.0)
+    out["full-cycle-48"] = (snap, {}, ["allocate", "consolidation", "reclaim", "preempt"])
     snap = synthetic.benchmark_snapshot(n_nodes=48, n_jobs=700, tasks_per_job=1, n_queues=8)
     snap.queue_usage = np.random.default_rng(11).choice(np.array([0.0, 0.05, 0.125, 0.25, 0.5]), size=(3, snap.n_queues))
     out["usage-k2"] = (snap, dict(k_value=2.0), ["allocate"])
