@@ -7,6 +7,7 @@
 //
 // There is NO CPU fallback: without a usable CUDA device kai_engine_create fails.
 #include <algorithm>
+#include <array>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -127,6 +128,7 @@ struct kai_engine {
   std::vector<int> rank_to_node_h;
   // solver actions: second NodeInfo.PodInfos entry of a task (evicted from A, pipelined to B), mirror of the GPU column
   std::vector<int> on_other_node, on_other_status;
+  std::vector<std::array<int, 3>> on_extra;  // (task, node, status) node entries beyond two per task (kai_solver.cuh)
   std::vector<double> h_mirror;  // host mirror of Idle / Releasing, node-major [N][2][R]
   std::vector<double> h_tmp;     // staging for the re-read after a device-sequenced action
   int *d_node_domain = nullptr;
@@ -719,6 +721,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->r_visits.clear();
   e->on_other_node.clear();
   e->on_other_status.clear();
+  e->on_extra.clear();
   e->job_signature.clear();
   e->h_mirror.resize((size_t)2 * s->n_res * s->n_nodes);
   for (int n = 0; n < s->n_nodes; n++)
@@ -1025,7 +1028,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         s0[t] = hs.t_node_status[t];
       }
       double t_begin = HostBackend::now();
-      Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status);
+      Solver solver(hb, n0, s0, e->on_other_node, e->on_other_status, e->on_extra);
       solver.use_signatures = e->cfg.use_scheduling_signatures != 0;
       solver.job_signature = e->job_signature.empty() ? nullptr : e->job_signature.data();
       solver.q_preempt_mrt = e->q_preempt_mrt.empty() ? nullptr : e->q_preempt_mrt.data();
@@ -1052,6 +1055,21 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       solver_scenarios = solver.scenarios;
       solver_topk = solver.topk_sweeps;
       // one status per task for the allocate path: the entry on the task's current node; the other entry persists
+      for (auto &x : e->on_extra) {  // the entry on the task's current node belongs in slot 0
+        const int t = x[0], cur = hs.t_node[t];
+        if (x[1] == cur && n0[t] != cur && e->on_other_node[t] != cur) {
+          if (n0[t] < 0) {
+            n0[t] = x[1];
+            s0[t] = x[2];
+            x[0] = -1;
+          } else {
+            std::swap(n0[t], x[1]);
+            std::swap(s0[t], x[2]);
+          }
+        }
+      }
+      e->on_extra.erase(std::remove_if(e->on_extra.begin(), e->on_extra.end(), [](const std::array<int, 3> &x) { return x[0] < 0; }),
+                        e->on_extra.end());
       for (int t = 0; t < T; t++) {
         int cur = hs.t_node[t];
         if (n0[t] >= 0 && n0[t] != cur && e->on_other_node[t] == cur) {
@@ -1060,9 +1078,13 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         }
         if (n0[t] >= 0 && n0[t] == cur)
           hs.t_node_status[t] = s0[t];
-        else if (n0[t] >= 0 && e->on_other_node[t] < 0) {  // only a stale entry on another node: keep it as "other"
-          e->on_other_node[t] = n0[t];
-          e->on_other_status[t] = s0[t];
+        else if (n0[t] >= 0) {  // only a stale entry on another node: it persists as "other" (or beyond the two slots)
+          if (e->on_other_node[t] < 0) {
+            e->on_other_node[t] = n0[t];
+            e->on_other_status[t] = s0[t];
+          } else {
+            e->on_extra.push_back({t, n0[t], s0[t]});
+          }
         }
       }
     }

@@ -17,6 +17,7 @@
 // host sequencer thread.  Go map iteration orders are resolved canonically (ascending node / job / queue index),
 // like in the oracle.  Host-only code (never compiled for the device).
 #pragma once
+#include <array>
 #include <algorithm>
 #include <cmath>
 #include <functional>
@@ -86,8 +87,11 @@ struct Solver {
   // ---- session state (engine-internal task numbering; tasks of a podset are stored in TaskOrderFn order) ----
   int *st, *tn;            // task status / node (host mirror arrays, written back by the engine)
   unsigned char *tvirt;    // PodInfo.IsVirtualStatus
-  // NodeInfo.PodInfos keeps a clone per node: a task evicted from A and pipelined to B sits on both
+  // NodeInfo.PodInfos keeps a clone per node: a task evicted from A and pipelined to B sits on both (slots 0 and 1); a
+  // victim that an earlier action moved and this one evicts and re-places sits on three or more: `on_extra` holds the
+  // (task, node, status) entries beyond the two slots (rare, linear look-up)
   std::vector<int> &on_node0, &on_status0, &on_node1, &on_status1;
+  std::vector<std::array<int, 3>> &on_extra;
   double *qa, *qnp;        // queue allocated / allocated-non-preemptible [3][Q]
   // GPU column of the host mirror of Idle / Releasing (seq.mirror, node-major; point look-ups only)
   double Ig(int n) const { return seq.mirror[(size_t)n * 2 * R + KAI_RES_GPU]; }
@@ -107,9 +111,10 @@ struct Solver {
   long long sweeps = 0, scenarios = 0, topk_sweeps = 0, simulations = 0;
   double t_sweeps = 0, t_sim_setup = 0, t_evict = 0, t_victims_queue = 0, t_vq_pop = 0, t_tte = 0, t_addp = 0, t_filter = 0, t_bypod = 0, t_finit = 0;
 
-  Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1)
+  Solver(HostBackend &hb_, std::vector<int> &n0, std::vector<int> &s0, std::vector<int> &n1, std::vector<int> &s1,
+         std::vector<std::array<int, 3>> &extra)
       : hb(hb_), seq(hb_.seq), ctl(hb_.ctl), s(*hb_.seq.s), cfg(*hb_.seq.cfg), N(s.N), Q(s.Q), J(s.J), S(s.S), T(s.T),
-        R(s.R), on_node0(n0), on_status0(s0), on_node1(n1), on_status1(s1) {
+        R(s.R), on_node0(n0), on_status0(s0), on_node1(n1), on_status1(s1), on_extra(extra) {
     st = seq.rp.t_status;
     tn = seq.rp.t_node;
     tvirt = seq.rp.t_virtual;
@@ -318,7 +323,13 @@ struct Solver {
   }
   double start_Ig(int n) const { return touched_epoch[n] == epoch ? startIg[n] : Ig(n); }
   double start_Lg(int n) const { return touched_epoch[n] == epoch ? startLg[n] : Lg(n); }
-  int find_on(int t, int n) const { return on_node0[t] == n ? 0 : (on_node1[t] == n ? 1 : -1); }
+  int find_on(int t, int n) const {  // 0 / 1 = slot, 2 + i = on_extra[i], -1 = the task has no entry on node n
+    if (on_node0[t] == n) return 0;
+    if (on_node1[t] == n) return 1;
+    for (size_t i = 0; i < on_extra.size(); i++)
+      if (on_extra[i][0] == t && on_extra[i][1] == n) return 2 + (int)i;
+    return -1;
+  }
   double free_ready = 0;  // Σ idle + releasing GPUs over ready nodes (utils/action.go:145-160), kept incrementally
   void node_delta(int t, int n, int code) {
     touch(n);
@@ -329,17 +340,25 @@ struct Solver {
   void node_add_task(int t) {  // node_info.go:457-493 with the task's current status
     int n = tn[t], status = st[t];
     int e = find_on(t, n);
-    if (e < 0) e = on_node0[t] < 0 ? 0 : 1;
-    (e == 0 ? on_node0 : on_node1)[t] = n;
-    (e == 0 ? on_status0 : on_status1)[t] = status;
+    if (e < 0) e = on_node0[t] < 0 ? 0 : (on_node1[t] < 0 ? 1 : 2 + (int)on_extra.size());
+    if (e >= 2) {
+      if (e - 2 == (int)on_extra.size()) on_extra.push_back({t, n, status});
+      on_extra[e - 2][2] = status;
+    } else {
+      (e == 0 ? on_node0 : on_node1)[t] = n;
+      (e == 0 ? on_status0 : on_status1)[t] = status;
+    }
     node_delta(t, n, status == KAI_POD_RELEASING ? ND_ADD_RELEASING : (status == KAI_POD_PIPELINED ? ND_ADD_PIPELINED : ND_ADD));
   }
   void node_remove_task(int t, int n) {  // :515-551 with the status of the clone stored on the node
     int e = find_on(t, n);
     if (e < 0) return;  // node_info.go:495-501: a pod that is no longer on the node is an error, the node is untouched
-    int status = (e == 0 ? on_status0 : on_status1)[t];
+    int status = e >= 2 ? on_extra[e - 2][2] : (e == 0 ? on_status0 : on_status1)[t];
     node_delta(t, n, status == KAI_POD_RELEASING ? ND_REM_RELEASING : (status == KAI_POD_PIPELINED ? ND_REM_PIPELINED : ND_REM));
-    (e == 0 ? on_node0 : on_node1)[t] = -1;
+    if (e >= 2)
+      on_extra.erase(on_extra.begin() + (e - 2));
+    else
+      (e == 0 ? on_node0 : on_node1)[t] = -1;
   }
   // jobs with Pending tasks (utils.GetAllPendingJobs, actions/utils/action.go:122-130), kept as statuses change
   std::vector<int> pending_cnt;

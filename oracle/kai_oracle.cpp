@@ -386,10 +386,14 @@ struct Task {
   double req[KAI_MAX_RES] = {0};
   bool is_virtual = false;  // PodInfo.IsVirtualStatus
   // NodeInfo.PodInfos holds a CLONE of the task per node (node_info.go:400-402).  A task evicted from node A and
-  // pipelined to node B in the same statement sits on both (Releasing on A, Pipelined on B): at most two entries.
-  int on_node[2] = {-1, -1};
-  int on_status[2] = {0, 0};
-  int find_on(int n) const { return on_node[0] == n ? 0 : (on_node[1] == n ? 1 : -1); }
+  // pipelined to node B in the same statement sits on both (Releasing on A, Pipelined on B); a victim that consolidation
+  // moved and reclaim then evicts and re-places in a simulation sits on three, and so on: one entry per node, unbounded.
+  std::vector<int> on_node, on_status;
+  int find_on(int n) const {
+    for (size_t e = 0; e < on_node.size(); e++)
+      if (on_node[e] == n) return (int)e;
+    return -1;
+  }
 };
 struct PodSet {
   int job = -1, min_available = 0;
@@ -519,8 +523,11 @@ struct kai_oracle {
     int n = t.node;
     {
       int e = t.find_on(n);
-      if (e < 0) e = t.on_node[0] < 0 ? 0 : 1;
-      t.on_node[e] = n;
+      if (e < 0) {
+        e = (int)t.on_node.size();
+        t.on_node.push_back(n);
+        t.on_status.push_back(t.status);
+      }
       t.on_status[e] = t.status;
     }
     for (int r = 0; r < R; r++) {
@@ -563,7 +570,8 @@ struct kai_oracle {
     }
     {
       int e = t.find_on(n);
-      if (e >= 0) t.on_node[e] = -1;
+      t.on_node.erase(t.on_node.begin() + e);
+      t.on_status.erase(t.on_status.begin() + e);
     }
   }
 
@@ -2954,9 +2962,12 @@ int kai_oracle_load_snapshot(kai_oracle *o, const kai_snapshot *s) {
         tk.nominated = s->task_nominated ? s->task_nominated[t] : -1;
         tk.pred_class = s->task_pred_class ? s->task_pred_class[t] : -1;
         bool on = (tk.status & kActiveUsed) && tk.node >= 0;
-        tk.on_node[0] = on ? tk.node : -1;
-        tk.on_node[1] = -1;
-        tk.on_status[0] = tk.status;
+        tk.on_node.clear();
+        tk.on_status.clear();
+        if (on) {
+          tk.on_node.push_back(tk.node);
+          tk.on_status.push_back(tk.status);
+        }
         if (!on && !(tk.status & kActiveUsed)) tk.node = -1;
       }
     }
@@ -3331,6 +3342,20 @@ int kai_oracle_capacity_schedulable(int n_queues, const int32_t *parent, const d
   return (mode == 0 ? o.over_capacity(0, req) : o.non_preemptible_over_quota(0, req)) ? 0 : 1;
 }
 
+int kai_oracle_node_entries(kai_oracle *o, int32_t *task, int32_t *node, int32_t *status, int cap) {
+  if (!o) return -1;
+  int n = 0;
+  for (int t = 0; t < (int)o->T.size(); t++)
+    for (size_t e = 0; e < o->T[t].on_node.size(); e++) {
+      if (n < cap) {
+        task[n] = t;
+        node[n] = o->T[t].on_node[e];
+        status[n] = o->T[t].on_status[e];
+      }
+      n++;
+    }
+  return n;
+}
 int kai_oracle_feasible_nodes(kai_oracle *o, int job, int32_t *out) {
   if (!o || job < 0 || job >= o->NJ) return KAI_ERR_INVALID;
   std::vector<char> f = o->feasible_nodes_for_job(job);

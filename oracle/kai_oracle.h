@@ -118,6 +118,9 @@ int kai_oracle_quantities_relation(int kind, const double *a, const double *b);
 double kai_oracle_min_runtime(kai_oracle *o, int reclaim, int pending_queue, int victim_queue);
 /* !reclaimFilterFn / !preemptFilterFn (minruntime.go:93-105): 1 = the victim job is withheld */
 int kai_oracle_min_runtime_protected(kai_oracle *o, int reclaim, int pending_job, int victim_job);
+/* NodeInfo.PodInfos of all nodes as (task, node, status-of-the-clone) triples (node_info.go:400-402): a task holds one
+   entry per node it sits on.  Returns the number of entries (written up to cap). */
+int kai_oracle_node_entries(kai_oracle *o, int32_t *task, int32_t *node, int32_t *status, int cap);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,20 @@ class Oracle:
     def min_runtime_protected(self, reclaim: bool, pending_job: int, victim_job: int) -> bool:
         return bool(self._lib.kai_oracle_min_runtime_protected(self._h, int(reclaim), pending_job, victim_job))
 
+    def node_entries(self):
+        """(task, node, status) of every clone the nodes hold (NodeInfo.PodInfos)."""
+        import numpy as np
+        fn = self._lib.kai_oracle_node_entries
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3 + [C.c_int]
+        cap = 1 << 16
+        while True:
+            t, n, s = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+            k = fn(self._h, *(a.ctypes.data_as(C.POINTER(C.c_int32)) for a in (t, n, s)), cap)
+            if k <= cap:
+                return list(zip(t[:k].tolist(), n[:k].tolist(), s[:k].tolist()))
+            cap = k
+
     def stats(self) -> abi.KaiStats:
         s = abi.KaiStats()
         self._check(self._lib.kai_oracle_stats(self._h, C.byref(s)))

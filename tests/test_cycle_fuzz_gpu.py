@@ -44,10 +44,13 @@ def test_cycle_fuzz_engine_equals_oracle(chunk):
     dict(n_nodes=48, running_per_node=7, victim_queues=2, reclaimer_jobs=12, reclaimer_tasks=2, reclaimer_gpus=3.0),
     dict(n_nodes=64, running_per_node=7, victim_queues=3, reclaimer_jobs=20, reclaimer_tasks=3, reclaimer_gpus=2.0),
     dict(n_nodes=96, running_per_node=6, victim_queues=4, reclaimer_jobs=24, reclaimer_tasks=2, reclaimer_gpus=3.0),
+    dict(n_nodes=8, running_per_node=6, victim_queues=3, reclaimer_jobs=4, reclaimer_tasks=2, reclaimer_gpus=3.0),
+    dict(n_nodes=24, running_per_node=6, victim_queues=3, reclaimer_jobs=20, reclaimer_tasks=3, reclaimer_gpus=3.0),
 ])
 def test_remove_of_a_task_that_left_its_node(kw):
     """Workloads where consolidation evicts a victim, pipelines it back onto its own node and rolls back: the reference's
-    RemoveTask is then a no-op (node_info.go:495-513) and unevict re-adds the pod (statement.go:171-183)."""
+    RemoveTask is then a no-op (node_info.go:495-513) and unevict re-adds the pod (statement.go:171-183); and workloads
+    where a victim moved by consolidation is evicted and re-placed by reclaim (entries on three nodes)."""
     snap = synthetic.reclaim_snapshot(**kw)
     e, o = Engine(), Oracle()
     e.load(snap)
