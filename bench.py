@@ -1,9 +1,15 @@
 #!/usr/bin/env python
 """bench.py — one JSON line per run (driver contract).
 
-A "step" is one scheduling cycle (proportion OnSessionOpen + allocate Action) over one synthetic
-cluster snapshot.  Default workload at N=1: BASELINE.json configs[1] — 10 000 nodes ("node-%d",
-8 GPUs) / 40 000 pending single-pod 1-GPU jobs / 4 leaf queues under 2 departments, binpack.
+A "step" is one scheduling cycle (proportion OnSessionOpen + the allocate and reclaim Actions) over one synthetic
+cluster snapshot.  Default workload: the configuration BASELINE.json's metric is quoted on (configs[2]) — 50 000 nodes
+("node-%d", 4 GPUs) / 200 000 pending 1-GPU pods in 50 000 gangs of 4 / 1 000 leaf queues under 250 departments, plus
+8 nodes full of running over-quota pods: allocate fills the cluster, the gangs left over reclaim (synthetic.cycle_snapshot).
+`--config config2` is BASELINE.json configs[1] (10 000 nodes / 40 000 pods, allocate).
+
+After the timed loop the engine's outcome of the last step is compared with the CPU oracle on the same snapshot
+(bindings, statuses, victim set, queue shares); the line carries bindings_match / victims_match / max_share_abs_err
+and the process exits non-zero on a mismatch.
 
   value        pods placed per second, device time (CUDA events on the engine's stream) of the open-session
                kernels + the action kernel, snapshot already resident in HBM
@@ -92,20 +98,41 @@ def dist_env():
     return rank, world, local
 
 
+def reference_sample(config, snap, actions):
+    """Bounded sample of the workload for the CPU arm: same cluster (all nodes, all queues), the first gangs of the pending
+    list, sized to a few seconds of oracle time per step so that --steps 20 --warmup 5 ends within minutes."""
+    if config in synthetic.CYCLE_CONFIGS or config in ("config3", "config3-mixed"):
+        kw = dict(synthetic.CYCLE_CONFIGS.get(config) or synthetic.CONFIGS[config])
+        gangs = min(kw["n_jobs"], max(1, int(1.0e9 // (kw["n_nodes"] * kw.get("tasks_per_job", 1)))))
+        kw["n_jobs"] = gangs
+        if config in synthetic.CYCLE_CONFIGS:
+            sample = synthetic.cycle_snapshot(**kw)
+        else:
+            sample = synthetic.benchmark_snapshot(**kw)
+        note = (f"per step: the first {gangs} gangs ({gangs * kw.get('tasks_per_job', 1)} pods) of the pending list on the full "
+                f"{kw['n_nodes']}-node / {int(sample.queue_parent.shape[0])}-queue cluster, allocate action"
+                + (" (the sample leaves free GPUs, so reclaim has no work in it)" if "reclaim" in actions else ""))
+        return sample, ["allocate"], note
+    return snap, list(actions), "full workload per step"
+
+
 def run_reference(args, snap, workload, actions=("allocate",), engine_kw=None):
-    """--impl reference: CPU oracle with all host threads on the same config/metric."""
+    """--impl reference: the CPU restatement of the reference's Go path (oracle/, 'port': no Go toolchain here or on the
+    GPU box) with a pool of host threads, same config / metric, bounded sample per step."""
     from oracle_lib import Oracle
     rank, world, _ = dist_env()
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, int(os.environ.get("KAI_REF_THREADS", "16")))
+    sample, s_actions, note = (snap, list(actions), "full recorded snapshot per step") if args.snapshot else \
+        reference_sample(args.config, snap, actions)
     o = Oracle(abi.make_config(**(engine_kw or {})), threads=cores)
     times, placed = [], 0
     for i in range(args.warmup + args.steps):
-        o.load(snap)
+        o.load(sample)
         t0 = time.perf_counter()
         moved = 0
-        for a in actions:
+        for a in s_actions:
             res = o.run(a)
             moved += res.pods_placed + res.pods_evicted
         dt = time.perf_counter() - t0
@@ -120,8 +147,8 @@ def run_reference(args, snap, workload, actions=("allocate",), engine_kw=None):
         "vs_baseline": None, "dtype": "f64", "data": "recorded snapshot" if args.snapshot else "synthetic",
         "config": workload,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "full workload per step (oracle/kai_oracle.cpp; node sweep fanned out over a spinning worker pool, "
-                                   "KAI_REF_THREADS threads, default 16 of %d host cores)" % (os.cpu_count() or 1)},
+                         "sample": note + "; oracle/kai_oracle.cpp, node sweep fanned out over a worker pool of KAI_REF_THREADS "
+                                   "threads (default 16 of %d host cores)" % (os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -133,7 +160,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--config", default="config2", choices=sorted(synthetic.CONFIG_ACTIONS))
+    ap.add_argument("--config", default="config3-cycle", choices=sorted(synthetic.CONFIG_ACTIONS))
+    ap.add_argument("--parity", default="auto", choices=["auto", "off"],
+                    help="compare the last step's outcome with the CPU oracle (threaded) and exit 1 on a mismatch")
     ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "off"])
     ap.add_argument("--snapshot", default=None,
                     help="time a recorded cluster instead of a synthetic config: a zip of the reference's snapshot "
@@ -153,6 +182,11 @@ def main():
         snap = synthetic.config_snapshot(args.config)
     if args.snapshot:
         pass
+    elif args.config in synthetic.CYCLE_CONFIGS:
+        kw = synthetic.CYCLE_CONFIGS[args.config]
+        desc = (f"{args.config}: {kw['n_nodes']} nodes x {kw['gpus_per_node']} GPUs, {kw['n_jobs']} pending gangs x {kw['tasks_per_job']} "
+                f"1-GPU pods, {kw['n_queues']} leaf queues under {(kw['n_queues'] + 3) // 4} departments (DRF proportion), binpack, "
+                f"{kw['running_nodes']} nodes full of running over-quota pods; actions allocate+reclaim (pods = placed + evicted)")
     elif args.config in synthetic.CONFIGS:
         kw = synthetic.CONFIGS[args.config]
         desc = (f"{args.config}: {kw['n_nodes']} nodes x {kw['n_jobs']} jobs x {kw.get('tasks_per_job', 1)} pods, "
@@ -206,11 +240,14 @@ def main():
         t0 = time.perf_counter()
         eng.load_c(c_snap, snap.n_res)       # H2D of the whole snapshot + open-session kernels
         dev, moved, launches_, alg_, act_ = 0.0, 0, 0, 0, 0.0
+        one_step.evicted, one_step.decisions = 0, 0
         for a in actions:
             r = eng.run(a, copy=False)       # action kernel + D2H of the results
             st = eng.stats()
             dev += st.action_ms
             moved += int(r.pods_placed) + int(r.pods_evicted)
+            one_step.evicted += int(r.pods_evicted)
+            one_step.decisions += int(st.decisions)
             launches_ = int(st.kernel_launches)
             alg_ += int(st.algorithmic_bytes)
             act_ += st.action_ms
@@ -226,8 +263,10 @@ def main():
     dev_ms, e2e_s, pods, launches, alg_bytes, act_ms, d2h = 0.0, 0.0, 0, 0, 0, 0.0, 0
     phase_ms = {"upload": 0.0, "open_session": 0.0, "action": 0.0, "download": 0.0}
     t_wall0 = time.perf_counter()
+    decisions = evicted_e = 0
     for _ in range(args.steps):
         d, e, p, st, r = one_step()
+        decisions, evicted_e = one_step.decisions, one_step.evicted
         dev_ms += d
         e2e_s += e
         pods += p
@@ -242,6 +281,16 @@ def main():
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    last = abi.Result.from_c(r, snap.n_res)  # outcome of the last timed step (copied out of the engine's buffers)
+    ranks_agree = True
+    if world > 1:  # every rank runs the same sequencer over its node stripe: the bindings must be identical everywhere
+        import hashlib
+        h = hashlib.sha256(last.task_node.tobytes() + last.task_status.tobytes()).digest()[:8]
+        mine = torch.tensor([int.from_bytes(h, "little", signed=True)], dtype=torch.int64, device="cuda")
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ranks_agree = bool(lo.item() == hi.item())
 
     # max over ranks of the timed quantities
     if world > 1:
@@ -279,25 +328,58 @@ def main():
             "clocks": clocks,
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }
-        if args.cpu_baseline != "off" and args.gpus == 1:
+        line["decisions_executed"] = int(decisions)
+        ok = True
+        if args.parity != "off" and args.cpu_baseline != "off":
+            # the engine's outcome of the last timed step against the oracle on the same snapshot, once, outside the
+            # timed loop; the oracle run doubles as the CPU baseline (bounded: one cycle)
             from oracle_lib import Oracle
-            o = Oracle(abi.make_config(**engine_kw), threads=1)
+            cores = min(os.cpu_count() or 1, int(os.environ.get("KAI_REF_THREADS", "16")))
+            o = Oracle(abi.make_config(**engine_kw), threads=cores)
             o.load(snap)
             t0 = time.perf_counter()
-            moved = 0
+            moved, evicted_o = 0, 0
             for a in actions:
                 ro = o.run(a)
                 moved += ro.pods_placed + ro.pods_evicted
+                evicted_o += ro.pods_evicted
             dt = time.perf_counter() - t0
+            bindings = bool(np.array_equal(last.task_node, ro.task_node) and np.array_equal(last.task_status, ro.task_status))
+            releasing = abi.POD_STATUS_NAMES["Releasing"]
+            victims = bool(np.array_equal(np.flatnonzero(last.task_status == releasing), np.flatnonzero(ro.task_status == releasing))
+                           and evicted_e == evicted_o)
+            share_err = float(np.max(np.abs(last.queue_fair_share - ro.queue_fair_share))) if last.queue_fair_share.size else 0.0
+            alloc_err = float(np.max(np.abs(last.queue_allocated - ro.queue_allocated))) if last.queue_allocated.size else 0.0
+            if world > 1:  # a rank's result carries its own node stripe only
+                own = (snap.node_name_rank % world) == rank
+                nodes_eq = bool(np.array_equal(last.node_idle[:, own], ro.node_idle[:, own])
+                                and np.array_equal(last.node_releasing[:, own], ro.node_releasing[:, own]))
+            else:
+                nodes_eq = bool(np.array_equal(last.node_idle, ro.node_idle) and np.array_equal(last.node_releasing, ro.node_releasing))
+            line.update({"bindings_match": bindings, "victims_match": victims, "max_share_abs_err": max(share_err, alloc_err),
+                         "node_tables_match": nodes_eq, "pods_moved": {"engine": int(pods_all // max(args.steps, 1)), "oracle": int(moved)}})
+            ok = bindings and victims and nodes_eq and max(share_err, alloc_err) <= 1e-6 and pods_all // max(args.steps, 1) == moved
             if args.config in synthetic.REFERENCE_PUBLISHED_MS:
                 line["reference_published_ms_per_op"] = synthetic.REFERENCE_PUBLISHED_MS[args.config]
-            line["cpu_baseline"] = {"value": moved / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"one full {args.config} cycle ({'+'.join(actions)}), scalar oracle, {dt:.2f} s",
+            line["cpu_baseline"] = {"value": moved / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"one full {args.config} cycle ({'+'.join(actions)}), oracle/kai_oracle.cpp with a pool of "
+                                              f"{cores} threads for the node sweep, {dt:.2f} s (also the parity check of this line)",
                                     "host_cores_available": os.cpu_count()}
+        if world > 1:
+            line["ranks_agree"] = bool(ranks_agree)
+            ok = ok and bool(ranks_agree)
         print(json.dumps(line))
+        if not ok:
+            print("bench: PARITY MISMATCH against the oracle (see bindings_match / victims_match / node_tables_match)", file=sys.stderr)
     eng.close()
     if world > 1:
+        flag = torch.tensor([0 if (rank != 0 or ok) else 1], device="cuda")
+        dist.all_reduce(flag)
         dist.destroy_process_group()
+        if int(flag.item()):
+            sys.exit(1)
+    elif rank == 0 and not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -372,6 +372,7 @@ struct Solver {
     }
     st[t] = status;
     job_cache[j].tta_valid = job_cache[j].res_valid = false;
+    if (s.j_queue[j] >= 0) leaf_epoch[s.j_queue[j]]++;
   }
   void queue_allocate(int t, bool add) {  // proportion.go:443-489
     int j = tjob(t);
@@ -1398,8 +1399,65 @@ struct Solver {
     return none;
   }
 
+  // Victims-queue cache.  The reference rebuilds the victims JobsOrderByQueues for every partial job of every
+  // reclaimer from ALL jobs of the session (reclaim.go:121-143, consolidation.go:119-157) — O(jobs) heap pushes each
+  // time.  Here the eligible victims of a leaf queue are kept in pop order (inverse JobOrderFn = descending packed
+  // key: priority, elastic class, creation / UID rank) and rebuilt only when a task of that queue changed status
+  // since (leaf_epoch).  A sorted run pushed in order IS the heap those pushes build (no sift moves anything), and a
+  // leaf is linked into its ancestors' heaps with its best job on top either way, so the tree below is the one
+  // push_job would have produced, queue by queue in ascending order.
+  std::vector<std::vector<int>> vq_leaf;
+  std::vector<long long> vq_leaf_epoch, leaf_epoch;
+  long long vq_rebuilt = 0, vq_reused = 0;
+  const std::vector<int> &victim_leaf_list(JobsOrder &jo, int q) {
+    if (vq_leaf_epoch[q] == leaf_epoch[q]) {
+      vq_reused++;
+      return vq_leaf[q];
+    }
+    vq_rebuilt++;
+    std::vector<std::pair<unsigned long long, int>> keyed;
+    for (int i = s.q_job_begin[q]; i < s.q_job_begin[q + 1]; i++) {
+      const int j = s.q_jobs_sorted[i];
+      if (!preemptible(j) || count_job(j, kActiveAllocated) == 0) continue;
+      bool below, above, exactly;
+      jo.min_available_state(j, below, above, exactly);
+      keyed.push_back({make_job_key(s.j_priority[j], below ? 0 : (exactly ? 1 : 2), s.j_order_rank[j]), j});
+    }
+    std::sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, int> &a, const std::pair<unsigned long long, int> &b) { return a.first > b.first; });
+    vq_leaf[q].clear();
+    for (auto &kv : keyed) vq_leaf[q].push_back(kv.second);
+    vq_leaf_epoch[q] = leaf_epoch[q];
+    return vq_leaf[q];
+  }
+  bool build_victims_queue_cached(JobsOrder &jo, int pending_job) {
+    if (solver_kind == 2 || j_last_start || getenv("KAI_NO_VICTIM_CACHE")) return false;  // preempt: one queue; min-runtime filters depend on the pair
+    if (solver_kind == 1 && cfg.max_consolidation_preemptees != -1) return false;
+    if (!ops.empty()) return false;  // built on the committed state only
+    const int pq = s.j_queue[pending_job];
+    for (int q = 0; q < Q; q++) {
+      if (s.q_nchildren[q] != 0 || s.q_job_begin[q + 1] == s.q_job_begin[q]) continue;
+      if (solver_kind == 0 && q == pq) continue;  // reclaim.go:126: other queues only
+      const std::vector<int> &lst = victim_leaf_list(jo, q);
+      if (lst.empty()) continue;
+      const int leaf = jo.make_node(q, true);
+      jo.queue_node[q] = leaf;
+      jo.nodes[leaf].children.a = lst;
+      if (solver_kind == 1 && q == pq) {  // consolidation.go:127: every job but the pending one
+        auto &a = jo.nodes[leaf].children.a;
+        a.erase(std::remove(a.begin(), a.end(), pending_job), a.end());
+        if (a.empty()) {
+          jo.queue_node[q] = -1;
+          continue;
+        }
+      }
+      jo.ensure_chain(leaf);
+      jo.mark_ancestors(leaf);
+    }
+    return true;
+  }
   void build_victims_queue(JobsOrder &jo, int pending_job) {
     jo.init(this, true);
+    if (build_victims_queue_cached(jo, pending_job)) return;
     std::vector<int> vs;
     OrderOpts op;
     if (solver_kind == 0) {  // reclaim.go:121-143
@@ -1615,6 +1673,9 @@ struct Solver {
 
   void prepare() {
     job_cache.assign(J, Cache());
+    vq_leaf.assign(Q, {});
+    vq_leaf_epoch.assign(Q, -1);
+    leaf_epoch.assign(Q, 0);
     pending_cnt.assign(J, 0);
     pending_jobs.clear();
     for (int t = 0; t < T; t++)
@@ -1633,8 +1694,7 @@ struct Solver {
     JobsOrder jo;
     jo.init(this, false);
     {
-      std::vector<int> vs;
-      for (int j = 0; j < J; j++) vs.push_back(j);
+      std::vector<int> vs(pending_jobs.begin(), pending_jobs.end());  // filter_non_pending: jobs with Pending tasks only
       OrderOpts op;
       op.filter_non_pending = op.filter_unready = true;
       init_jobs_order(jo, vs, op);
@@ -1693,8 +1753,7 @@ struct Solver {
     JobsOrder jo;
     jo.init(this, false);
     {
-      std::vector<int> vs;
-      for (int j = 0; j < J; j++) vs.push_back(j);
+      std::vector<int> vs(pending_jobs.begin(), pending_jobs.end());  // filter_non_pending: jobs with Pending tasks only
       OrderOpts op;
       op.filter_non_pending = op.filter_unready = true;
       init_jobs_order(jo, vs, op);
@@ -1740,8 +1799,7 @@ struct Solver {
     JobsOrder jo;
     jo.init(this, false);
     {
-      std::vector<int> vs;
-      for (int j = 0; j < J; j++) vs.push_back(j);
+      std::vector<int> vs(pending_jobs.begin(), pending_jobs.end());
       OrderOpts op;
       op.filter_non_pending = op.filter_unready = op.filter_non_preemptible = true;
       init_jobs_order(jo, vs, op);

@@ -113,6 +113,60 @@ def benchmark_snapshot(n_nodes: int, n_jobs: int, tasks_per_job: int = 1, n_queu
         task_order_rank=task_order_rank)
 
 
+def cycle_snapshot(n_nodes: int, n_jobs: int, tasks_per_job: int = 4, n_queues: int = 1000, gpus_per_node: int = 4,
+                   running_nodes: int = 8, victim_queues: int = 2) -> abi.Snapshot:
+    """The allocate + reclaim cycle BASELINE.json's metric names, on the config-3 shape: the many-queues gang benchmark
+    (createBenchmarkTopologyWithManyQueues / ...WithGangJobs, benchmark_test.go:360-473) on a cluster whose GPUs equal
+    the pending demand, with `running_nodes` nodes already full of running 1-GPU Train pods that belong to
+    `victim_queues` leaf queues without quota (deserved 0, over-quota weight 0; department "dept-victims", the
+    over-quota shape of reclaim_benchmark_test.go:66-147).  `allocate` places every gang the free GPUs can take; the
+    gangs left over sit in queues below their deserved quota and `reclaim` evicts the over-quota pods for them."""
+    base = benchmark_snapshot(n_nodes=n_nodes, n_jobs=n_jobs, tasks_per_job=tasks_per_job, n_queues=n_queues,
+                              gpus_per_node=gpus_per_node, named_depts=False)
+    R, N = 4, n_nodes
+    Q0 = int(base.queue_parent.shape[0])
+    n_run = running_nodes * gpus_per_node
+    # queues: [leaf queues | departments] of the base + [victim leaf queues | dept-victims]
+    vq = np.arange(victim_queues) + Q0
+    vdept = Q0 + victim_queues
+    parent = np.concatenate([base.queue_parent, np.full(victim_queues, vdept), [-1]]).astype(np.int32)
+    Q = int(parent.shape[0])
+    prio = np.full(Q, 100, dtype=np.int32)
+    creation = np.concatenate([base.queue_creation, (n_queues + np.arange(victim_queues)) * 60, [10 ** 6]]).astype(np.int64)
+    n_depts = Q0 - n_queues
+    qnames = np.array([f"queue-{i}" for i in range(n_queues)] + [f"dept-{i}" for i in range(n_depts)] +
+                      [f"victims-{i}" for i in range(victim_queues)] + ["dept-victims"], dtype=object)
+    uid_rank = np.empty(Q, dtype=np.int32)
+    uid_rank[np.argsort(qnames, kind="stable")] = np.arange(Q, dtype=np.int32)
+    deserved = np.full((3, Q), -1.0)
+    limit = np.full((3, Q), -1.0)
+    oqw = np.ones((3, Q))
+    deserved[:, :Q0], oqw[:, :Q0] = base.queue_deserved, base.queue_oqw
+    deserved[2, Q0:] = 0.0
+    oqw[2, Q0:] = 0.0
+    J0, T0 = int(base.job_queue.shape[0]), int(base.task_status.shape[0])
+    J, T = J0 + n_run, T0 + n_run
+    run_node = (np.arange(n_run) // gpus_per_node).astype(np.int32)  # node-0 .. node-(running_nodes-1), full
+    req = np.concatenate([base.task_req, np.tile(np.array([[1000.0, 1e9, 1.0, 1.0]]), (n_run, 1))])
+    idle = base.node_allocatable.copy()
+    for r in range(R):
+        np.subtract.at(idle[r], run_node, req[T0:, r])
+    return abi.Snapshot(
+        n_res=R, node_allocatable=base.node_allocatable, node_idle=idle, node_releasing=np.zeros((R, N)),
+        node_name_rank=base.node_name_rank, node_flags=base.node_flags, queue_parent=parent, queue_priority=prio,
+        queue_creation=creation, queue_uid_rank=uid_rank, queue_deserved=deserved, queue_limit=limit, queue_oqw=oqw,
+        job_queue=np.concatenate([base.job_queue, vq[np.arange(n_run) % victim_queues]]).astype(np.int32),
+        job_priority=np.full(J, 50, dtype=np.int32),
+        # running jobs are older than every pending one (they started first)
+        job_order_rank=np.concatenate([n_run + np.arange(J0), np.arange(n_run)]).astype(np.int32),
+        job_flags=np.full(J, abi.JOB_PREEMPTIBLE, dtype=np.uint32), job_podset_begin=np.arange(J + 1, dtype=np.int32),
+        podset_min_available=np.concatenate([base.podset_min_available, np.ones(n_run)]).astype(np.int32),
+        podset_task_begin=np.concatenate([base.podset_task_begin, T0 + 1 + np.arange(n_run)]).astype(np.int32),
+        task_status=np.concatenate([base.task_status, np.full(n_run, abi.POD_RUNNING)]).astype(np.int32),
+        task_node=np.concatenate([base.task_node, run_node]).astype(np.int32), task_req=req,
+        task_order_rank=np.concatenate([base.task_order_rank, np.zeros(n_run)]).astype(np.int32))
+
+
 def reclaim_snapshot(n_nodes: int, running_per_node: int = 8, gpus_per_node: int = 8, victim_queues: int = 1,
                      reclaimer_jobs: int = 1, reclaimer_tasks: int | None = None, reclaimer_gpus: float = 8.0,
                      node_prefix: str = "node") -> abi.Snapshot:
@@ -255,7 +309,12 @@ RECLAIM_CONFIGS = {
     "cycle5-small": dict(n_nodes=200, running_per_node=8, victim_queues=4, reclaimer_jobs=100, reclaimer_tasks=2,
                          reclaimer_gpus=4.0),
 }
-CONFIG_ACTIONS = {**{k: ["allocate"] for k in CONFIGS}, **{k: ["allocate"] for k in TOPOLOGY_CONFIGS},
+# BASELINE.json's metric: one allocate + reclaim cycle over 50k nodes / 200k pending pods / 1k queues (+250 departments)
+CYCLE_CONFIGS = {
+    "config3-cycle": dict(n_nodes=50_000, n_jobs=50_000, tasks_per_job=4, n_queues=1000, gpus_per_node=4, running_nodes=8),
+    "config3-cycle-small": dict(n_nodes=600, n_jobs=600, tasks_per_job=4, n_queues=40, gpus_per_node=4, running_nodes=4),
+}
+CONFIG_ACTIONS = {**{k: ["allocate", "reclaim"] for k in CYCLE_CONFIGS}, **{k: ["allocate"] for k in CONFIGS}, **{k: ["allocate"] for k in TOPOLOGY_CONFIGS},
                   **{k: ["reclaim"] for k in RECLAIM_CONFIGS},
                   "cycle5-small": ["allocate", "consolidation", "reclaim"]}
 # ms/op the reference publishes for BenchmarkReclaimLargeJobs (other hardware, includes BuildSession)
@@ -268,4 +327,6 @@ def config_snapshot(name: str) -> abi.Snapshot:
         return reclaim_snapshot(**RECLAIM_CONFIGS[name])
     if name in TOPOLOGY_CONFIGS:
         return topology_snapshot(**TOPOLOGY_CONFIGS[name])
+    if name in CYCLE_CONFIGS:
+        return cycle_snapshot(**CYCLE_CONFIGS[name])
     return benchmark_snapshot(**CONFIGS[name])
