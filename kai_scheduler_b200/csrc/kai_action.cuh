@@ -904,20 +904,27 @@ struct ScanShared {
   int2 delta[kMaxDelta];
   unsigned char mine[kMaxDelta];
   int fit_count;
+  int ext_dirty;  // launch transport: the preferred-level score table changed in this launch
   int excl[kTopM];
   Cand cands[kTopM];
   double dreq[kMaxDelta][KAI_MAX_RES];
   int dln[kMaxDelta];
 };
 
-__device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *sh_warp, double *sh_d, int *sh_i,
-                             ScanShared &sh, Tile &tile) {
+// LAUNCH = false: persistent scanner (tile in shared memory, records polled from the device-side record buffer until DONE).
+// LAUNCH = true:  one launch = one record (`lrec`, kernel parameter); the tile lives in global memory between launches
+//                 (same layout), DK_LOAD fills it from the session tables, DK_DONE writes it back.  Returns true when
+//                 the record asks for an answer (the caller then runs the last-CTA reduction).
+template <bool LAUNCH>
+__device__ bool scanner_main(const ActionParams &p, const LaunchRec *lrec, unsigned char *smem, Cand *sh_warp, double *sh_d,
+                             int *sh_i, ScanShared &sh, Tile &tile) {
   const DevSnap &s = p.s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int my = blockIdx.x - 1;
+  const int my = LAUNCH ? (int)blockIdx.x : (int)blockIdx.x - 1;
+  unsigned char *gstate = LAUNCH ? p.g_scan_state + (size_t)my * kScanStateBytes : nullptr;
   if (tid == 0) {
     int npc = p.nodes_per_cta;
-    unsigned char *ptr = smem;
+    unsigned char *ptr = LAUNCH ? p.g_tiles + (size_t)my * p.g_tile_stride : smem;
     tile.npc = npc;
     tile.R = s.R;
     tile.nscan = p.grid - 1;
@@ -947,9 +954,14 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     tile.dom = (int *)ptr;
     tile.n_dom_levels = p.node_domain ? p.n_dom_levels : 0;
     sh.pref_level = -1;
+    sh.ext_dirty = 0;
+    if (LAUNCH && (int)(lrec->dw[0] & 0xff) != DK_LOAD) sh.pref_level = *(const int *)gstate;
   }
   __syncthreads();
-  for (int ln = tid; ln < tile.count; ln += blockDim.x) {
+  const bool load_tile = !LAUNCH || (int)(lrec->dw[0] & 0xff) == DK_LOAD;
+  if (LAUNCH && !load_tile && sh.pref_level >= 0)  // the score buckets of the preferred level persist between launches
+    for (int i = tid; i < kDomBuckets; i += blockDim.x) sh.dom_bucket[i] = gstate[16 + i];
+  for (int ln = tid; load_tile && ln < tile.count; ln += blockDim.x) {
     const int rk = tile_row_rank(tile, ln);
     const int n = s.rank_to_node[rk];
     tile.node[ln] = n;
@@ -965,12 +977,19 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     for (int l = 0; l < tile.n_dom_levels; l++) tile.dom[l * tile.npc + ln] = p.node_domain[(size_t)l * s.N + n];
   }
   __syncthreads();
-  unsigned int seq = p.seq0;
+  if (LAUNCH && load_tile) {
+    if (tid == 0) *(int *)gstate = -1;
+    return false;
+  }
+  unsigned int seq = LAUNCH ? lrec->seq : p.seq0;
   long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool wrote_answer = false;
   for (;;) {
     long long c0 = clock64();
     // ---- wait for decision record `seq` ----
-    if (warp == 0) {
+    if (LAUNCH) {
+      if (tid < kDecWords) sh.dw[tid] = lrec->dw[tid];
+    } else if (warp == 0) {
       const unsigned long long *rec0 = p.dbuf + (size_t)(seq & 1) * kDecWords * 2;
       if (lane == 0) {  // one poller per CTA on word 0 keeps the record's L2 lines cool
         unsigned long long lo, hi;
@@ -1036,7 +1055,10 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       const unsigned long long *dl = p.delta + (size_t)(seq & 1) * kMaxDelta * 2;
       for (int e = tid; e < nd; e += blockDim.x) {
         unsigned long long lo, hi;
-        {
+        if (LAUNCH) {
+          lo = (unsigned long long)lrec->dkey[e] | ((unsigned long long)lrec->dtask[e] << 32);
+          hi = (unsigned long long)seq | ((unsigned long long)lrec->dcount[e] << 32);
+        } else {
           Spin spin;
           do {
             ld_relaxed_b128(dl + 2 * e, lo, hi);
@@ -1090,11 +1112,11 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
           }
         } else if (kind == EXT_SCORE_BEGIN) {
           for (int i = tid; i < kDomBuckets; i += blockDim.x) sh.dom_bucket[i] = 255;
-          if (tid == 0) sh.pref_level = (int)a;
+          if (tid == 0) sh.pref_level = (int)a, sh.ext_dirty = 1;
         } else if (kind == EXT_SCORE) {
-          if (tid == 0 && a < (unsigned int)kDomBuckets) sh.dom_bucket[a] = (unsigned char)b;
+          if (tid == 0 && a < (unsigned int)kDomBuckets) sh.dom_bucket[a] = (unsigned char)b, sh.ext_dirty = 1;
         } else if (kind == EXT_SCORE_END) {
-          if (tid == 0) sh.pref_level = -1;
+          if (tid == 0) sh.pref_level = -1, sh.ext_dirty = 1;
         }
         __syncthreads();
       }
@@ -1111,7 +1133,15 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     const int kind = sh.kind;
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
-    if (kind == DK_SCAN && (sh.xbits & XB_FUSED_MM)) {
+    if (LAUNCH && kind == DK_SCAN && (sh.xbits & XB_FUSED_MM)) {
+      // the extremes of this row set were reduced by the MINMAX launch that precedes this one on the stream
+      if (tid == 0) {
+        const int k = sh.dec.res == KAI_RES_GPU ? 0 : 1;
+        sh.dec.mn = p.mm_result[2 * k];
+        sh.dec.mx = p.mm_result[2 * k + 1];
+      }
+      __syncthreads();
+    } else if (kind == DK_SCAN && (sh.xbits & XB_FUSED_MM)) {
       {
         // pack.go:66-86 over the current node set: local extremes -> device slots -> every scanner reduces all slots
         double mn[2] = {DBL_MAX, DBL_MAX}, mx[2] = {0, 0};
@@ -1303,8 +1333,19 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
     }
     seq++;
     __syncthreads();
+    if (LAUNCH) {
+      wrote_answer = true;
+      break;
+    }
   }
-  if (tid == 0 && my == 0)
+  if (LAUNCH) {
+    if (sh.ext_dirty) {  // preferred-level score table of this scanner: back to its global copy
+      for (int i = tid; i < kDomBuckets; i += blockDim.x) gstate[16 + i] = sh.dom_bucket[i];
+      if (tid == 0) *(int *)gstate = sh.pref_level;
+    }
+    if (wrote_answer) return sh.kind != DK_FLUSH;
+  }
+  if (!LAUNCH && tid == 0 && my == 0)
     for (int i = 0; i < 7; i++) p.counters[32 + i] = ts[i];
   // ---- DONE: write the tile back to the session tables ----
   for (int ln = tid; ln < tile.count; ln += blockDim.x) {
@@ -1314,6 +1355,7 @@ __device__ void scanner_main(const ActionParams &p, unsigned char *smem, Cand *s
       s.rel[(size_t)r * s.N + n] = tile.L[r * tile.npc + ln];
     }
   }
+  return false;
 }
 
 // =============================================================================================
@@ -1686,6 +1728,12 @@ __device__ void relay_reduce(const ActionParams &p, int kind, unsigned int seq) 
             cmx[k] += ocmx;
         }
       }
+    if (lane == 0 && p.mm_result) {  // launch transport: the next launch (XB_FUSED_MM sweep) reads the extremes on the device
+      for (int k = 0; k < 2; k++) {
+        p.mm_result[2 * k] = cmn[k] > 0 ? gmn[k] : DBL_MAX;
+        p.mm_result[2 * k + 1] = cmx[k] > 0 ? gmx[k] : 0.0;
+      }
+    }
     if (lane == 0) {
       unsigned long long *out = p.h_mmslot + (size_t)(seq & 1) * kMaxGrid * kSlotWords;
       for (int k = 0; k < 2; k++) {
@@ -1773,7 +1821,166 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
     else
       sequencer_main(p, smem, ctl, seq);
   } else
-    scanner_main(p, smem, sh_warp, sh_d, sh_i, scan_sh, tile);
+    scanner_main<false>(p, nullptr, smem, sh_warp, sh_d, sh_i, scan_sh, tile);
+}
+
+
+// =============================================================================================
+// launch transport: one kernel launch per decision record
+// =============================================================================================
+// Last CTA of a list launch: merge the top-M answers of all scanners (device lines, layout of h_list) into one list in
+// key order, cut it where an unseen row could be better (the best "last reported key" among scanners that have more
+// fitting rows than they reported — the rule HostBackend::gather_list applies), and write the usable prefix as
+// 48-byte entries {score, meta, Ig, Lg, Ic, Lc} + one header word to host memory: the host reads one contiguous list
+// instead of scanners x (1 + M) cache lines.
+struct MergeKey {
+  double score;
+  uint32_t rank;
+  uint32_t src;  // scanner * kTopM + m
+};
+__device__ __forceinline__ bool key_before(const MergeKey &a, const MergeKey &b) {  // a sorts before b
+  if (a.rank == kRankNone) return false;
+  if (b.rank == kRankNone) return true;
+  return a.score > b.score || (a.score == b.score && a.rank < b.rank);
+}
+__device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_payload, MergeKey *keys, Cand *sh_warp,
+                            int *sh_i) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int n_scan = p.grid - 1;
+  const int n_c = n_scan * kTopM;
+  int n_pow = 1;
+  while (n_pow < n_c) n_pow <<= 1;
+  const unsigned long long *base = p.h_list + (size_t)(seq & 1) * kListScanners * kListLines * kListLineWords;
+  // ---- candidates + the cut ----
+  Cand cut;
+  cut.score = -1.0;
+  cut.rank = kRankNone;
+  cut.ln = 0;
+  for (int c = tid; c < n_scan; c += blockDim.x) {
+    const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
+    bool more = false;
+    double last_score = 0;
+    uint32_t last_rank = kRankNone;
+    for (int m = 0; m < kTopM; m++) {
+      unsigned long long lo, hi;
+      ld_relaxed_b128(lines + 2 * m, lo, hi);
+      MergeKey k;
+      k.score = __longlong_as_double((long long)lo);
+      k.rank = (uint32_t)(hi & 0xffffffu);
+      k.src = (uint32_t)(c * kTopM + m);
+      if (((uint32_t)(hi >> 32) & 0xffu) & LF_MORE) more = true;
+      if (k.rank != kRankNone) {
+        last_score = k.score;
+        last_rank = k.rank;
+      }
+      keys[c * kTopM + m] = k;
+    }
+    if (more && last_rank != kRankNone && better(last_score, last_rank, cut.score, cut.rank)) {
+      cut.score = last_score;
+      cut.rank = last_rank;
+    }
+  }
+  for (int i = n_c + tid; i < n_pow; i += blockDim.x) {
+    keys[i].score = -1.0;
+    keys[i].rank = kRankNone;
+    keys[i].src = 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double os = __shfl_xor_sync(0xffffffffu, cut.score, o);
+    uint32_t orank = __shfl_xor_sync(0xffffffffu, cut.rank, o);
+    if (better(os, orank, cut.score, cut.rank)) {
+      cut.score = os;
+      cut.rank = orank;
+    }
+  }
+  if (lane == 0) sh_warp[warp] = cut;
+  __syncthreads();
+  cut = sh_warp[0];
+  for (int w = 1; w < nw; w++)
+    if (better(sh_warp[w].score, sh_warp[w].rank, cut.score, cut.rank)) cut = sh_warp[w];
+  const bool have_cut = cut.rank != kRankNone;
+  // ---- bitonic sort, best key first ----
+  for (int k = 2; k <= n_pow; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n_pow; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const MergeKey a = keys[i], b = keys[l];
+          const bool up = (i & k) == 0;
+          if (up ? key_before(b, a) : key_before(a, b)) {
+            keys[i] = b;
+            keys[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // ---- usable prefix: real entries that are not worse than the cut ----
+  int first_bad = n_c;
+  for (int i = tid; i < n_c; i += blockDim.x) {
+    const MergeKey k = keys[i];
+    bool ok = k.rank != kRankNone;
+    if (ok && have_cut && !(k.score > cut.score || (k.score == cut.score && k.rank <= cut.rank))) ok = false;
+    if (!ok && i < first_bad) first_bad = i;
+  }
+  for (int o = 16; o > 0; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+  if (lane == 0) sh_i[warp] = first_bad;
+  __syncthreads();
+  first_bad = sh_i[0];
+  for (int w = 1; w < nw; w++) first_bad = min(first_bad, sh_i[w]);
+  const int n_out = first_bad;
+  unsigned long long *out = p.h_clist + (size_t)(seq & 1) * kCListWords;
+  for (int i = tid; i < n_out; i += blockDim.x) {
+    const MergeKey k = keys[i];
+    const int c = (int)(k.src / kTopM), m = (int)(k.src % kTopM);
+    const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
+    unsigned long long lo, hi, w[4] = {0, 0, 0, 0};
+    ld_relaxed_b128(lines + 2 * m, lo, hi);
+    if (with_payload) {
+      const unsigned long long *pl = lines + (size_t)(1 + m) * kListLineWords;
+      for (int q = 0; q < 4; q++) {
+        unsigned long long plo, phi;
+        ld_relaxed_b128(pl + 2 * q, plo, phi);
+        w[q] = plo;
+      }
+    }
+    unsigned long long *e = out + 2 + (size_t)i * kCEntryWords;
+    st_relaxed_sys_b128(e, lo, hi);
+    st_relaxed_sys_b128(e + 2, w[0], w[1]);
+    st_relaxed_sys_b128(e + 4, w[2], w[3]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    st_relaxed_sys_b128(out, (unsigned long long)(unsigned int)n_out | (have_cut ? (1ull << 31) : 0ull), (unsigned long long)seq);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_record(const __grid_constant__ ActionParams p, const __grid_constant__ LaunchRec rec) {
+  extern __shared__ __align__(16) unsigned char smem[];  // merge keys of the last CTA
+  __shared__ Tile tile;
+  __shared__ ScanShared scan_sh;
+  __shared__ Cand sh_warp[kThreads / 32];
+  __shared__ double sh_d[(kThreads / 32) * 8];
+  __shared__ int sh_i[(kThreads / 32) * 4];
+  __shared__ int is_last;
+  const bool answers = scanner_main<true>(p, &rec, nullptr, sh_warp, sh_d, sh_i, scan_sh, tile);
+  if (!answers) return;
+  // ---- the last CTA to finish reduces the answers of all scanners and writes the result to host memory ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *p.ticket = 0;  // the next launch follows in stream order
+  const int kind = scan_sh.kind;
+  const unsigned int seq = rec.seq;
+  if (kind == DK_TOPK || (kind == DK_SCAN && p.topm && !(scan_sh.xbits & XB_SINGLE)))
+    merge_lists(p, seq, kind == DK_SCAN, (MergeKey *)smem, sh_warp, sh_i);
+  else if (threadIdx.x < 32)
+    relay_reduce(p, kind, seq);
 }
 
 }  // namespace kai

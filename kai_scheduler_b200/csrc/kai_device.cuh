@@ -166,6 +166,30 @@ struct ActionParams {
   int scanner_base;     // global index of this GPU's scanner 0 in h_list
   const int *node_domain;  // [n_dom_levels][N] topology domain of every node per level (-1 = label missing), or null
   int n_dom_levels;
+  // ---- launch transport (mode 2): one kernel launch per decision record, node tiles resident in global memory ----
+  unsigned char *g_tiles;      // [scanners][g_tile_stride] tiles in the layout of the shared-memory tile
+  size_t g_tile_stride;
+  unsigned char *g_scan_state; // [scanners][kScanStateBytes]: preferred level + per-domain score buckets of each scanner
+  unsigned int *ticket;        // CTAs that finished the current launch (the last one reduces the answers)
+  double *mm_result;           // [4] gpu mn, gpu mx, cpu mn, cpu mx of the last MINMAX launch (read by XB_FUSED_MM sweeps)
+  unsigned long long *h_clist; // this GPU's merged candidate list [2][kCListWords] in (shared) host memory
+};
+
+constexpr int kMergeCap = 2048;                      // candidates the last CTA of a launch can merge (scanners x kTopM)
+constexpr int kCEntryWords = 6;                      // score, meta, Ig, Lg, Ic, Lc
+constexpr int kCListWords = 2 + kMergeCap * kCEntryWords;  // header {count | more << 31, tag} + entries
+constexpr int kScanStateBytes = 16 + kDomBuckets;
+constexpr int kMaxDeltaL = kMaxDelta;
+enum { DK_LOAD = 6 };  // launch transport: load the tiles from the session tables (first launch of an action)
+
+// One decision record of the launch transport, passed by value in the kernel parameter space.
+struct LaunchRec {
+  unsigned long long dw[kDecWords];
+  unsigned int seq;
+  int n_delta;
+  unsigned int dkey[kMaxDeltaL];    // name rank | code << 28, or an extended entry (bit 31)
+  unsigned int dtask[kMaxDeltaL];
+  unsigned char dcount[kMaxDeltaL]; // repeat count - 1
 };
 
 }  // namespace kai

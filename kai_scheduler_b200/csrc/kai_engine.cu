@@ -87,6 +87,12 @@ struct Staging {  // pinned host staging buffer mirrored 1:1 onto a device arena
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
+constexpr int kShmRanks = 16;  // GPUs of one box that can share the exchange segment
+// layout of the shared exchange segment (u64 words): answer lines | min/max lines | top-M lines | merged lists per rank
+size_t shm_clist_offset_words() {
+  return (size_t)2 * 2 * kMaxGrid * kSlotWords + (size_t)2 * kListScanners * kListLines * kListLineWords;
+}
+
 }  // namespace
 
 struct kai_engine {
@@ -116,6 +122,17 @@ struct kai_engine {
   unsigned long long *h_pinned = nullptr;  // one pinned mapped allocation: rec | delta | slots | mm
   unsigned long long *h_rec = nullptr, *h_delta = nullptr, *h_slots = nullptr, *h_mm = nullptr, *h_list = nullptr;
   HostBackend hb;
+  // launch transport (default): one k_record launch per decision record, node tiles resident in global memory
+  DeviceArena dlaunch;
+  int lgrid = 0, lnpc = 0;  // scanners (= CTAs of k_record) and rows per scanner
+  size_t ltile_stride = 0;
+  unsigned char *g_tiles = nullptr, *g_scan_state = nullptr;
+  unsigned long long *d_list = nullptr;
+  unsigned int *ticket = nullptr;
+  double *mm_result = nullptr;
+  unsigned long long *h_clist = nullptr;  // pinned mapped: [2][kCListWords]
+  ActionParams lp;                        // parameters of the running action (launch transport)
+  long long record_launches = 0;
   // multi-GPU (one engine per process per GPU): the reduced answer lines of all GPUs live in one POSIX shm
   // segment that every process maps and registers with CUDA; each host sequencer reads all lines.
   unsigned long long *shm_base = nullptr;  // [slots | mm], each [2][kMaxGrid][kSlotWords]
@@ -220,6 +237,11 @@ int kai_engine_create(const kai_config *cfg, kai_engine **out) {
     e->h_slots = e->h_delta + (size_t)2 * kMaxDelta * 2;
     e->h_mm = e->h_slots + (size_t)2 * kMaxGrid * kSlotWords;
     e->h_list = e->h_mm + (size_t)2 * kMaxGrid * kSlotWords;
+    if (cudaHostAlloc((void **)&e->h_clist, (size_t)2 * kCListWords * 8, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      delete e;
+      return KAI_ERR_CUDA;
+    }
+    memset(e->h_clist, 0, (size_t)2 * kCListWords * 8);
   }
   *out = e;
   return KAI_OK;
@@ -235,6 +257,8 @@ void kai_engine_destroy(kai_engine *e) {
   e->stage.release();
   e->rstage.release();
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  if (e->h_clist) cudaFreeHost(e->h_clist);
+  e->dlaunch.release();
   if (e->d_node_domain) cudaFree(e->d_node_domain);
   if (e->shm_base) {
     if (e->shm_registered) cudaHostUnregister(e->shm_base);
@@ -660,6 +684,34 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->smem_bytes = std::max(tile_bytes, hot_in_smem ? hot : (size_t)0);
   e->ops_cap = ops_cap;
   e->visits_cap = std::max(16, 2 * J + T + 16);
+  {  // launch transport: scanners = CTAs of k_record; the last CTA merges scanners x kTopM candidates (<= kMergeCap)
+    int lg = 1;
+    while (lg * 2 <= std::min(2 * e->num_sms, kMergeCap / kTopM)) lg *= 2;  // 256 on B200: a power of two keeps the merge sort full
+    if (const char *g = getenv("KAI_LAUNCH_GRID")) {
+      int v = atoi(g);
+      if (v >= 1) lg = std::min(v, kMergeCap / kTopM);
+    }
+    if (N > 0) lg = std::min(lg, std::max(1, n_shard_rows));
+    if (const char *g = getenv("KAI_GRID_EXACT")) {  // tests: the same forced geometries as the persistent kernel (grid - 1 scanners)
+      int v = atoi(g);
+      if (v >= 2) lg = std::min(v - 1, kMergeCap / kTopM);
+    }
+    int lnpc = std::max(1, (n_shard_rows + lg - 1) / lg);
+    lnpc = (lnpc + 1) & ~1;
+    e->lgrid = lg;
+    e->lnpc = lnpc;
+    e->ltile_stride = align_up((size_t)lnpc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4 + (size_t)4 * n_dom_levels), 256);
+    const size_t list_words = (size_t)2 * kListScanners * kListLines * kListLineWords;
+    CK(e->dlaunch.reserve((size_t)lg * e->ltile_stride + (size_t)lg * align_up(kScanStateBytes, 256) + list_words * 8 + 4096));
+    e->g_tiles = e->dlaunch.take<unsigned char>((size_t)lg * e->ltile_stride);
+    e->g_scan_state = e->dlaunch.take<unsigned char>((size_t)lg * kScanStateBytes);
+    e->d_list = e->dlaunch.take<unsigned long long>(list_words);
+    e->ticket = e->dlaunch.take<unsigned int>(4);
+    e->mm_result = e->dlaunch.take<double>(4);
+    CK(cudaMemsetAsync(e->d_list, 0, list_words * 8, e->stream));
+    CK(cudaMemsetAsync(e->ticket, 0, 16, e->stream));
+    CK(cudaMemsetAsync(e->mm_result, 0, 32, e->stream));
+  }
   {
     size_t xb = (size_t)2 * kMaxGrid * 8 * 8;
     size_t misc = 2 * xb + 256 + sizeof(long long) * 48 + sizeof(kai_job_visit) * (size_t)e->visits_cap + 2 * QN * 8 + 4096 +
@@ -810,6 +862,30 @@ int kai_engine_fair_share(kai_engine *e, kai_result *out) {
   return download(e, out, 0, 0, 0);
 }
 
+// Launch transport: enqueue the kernel launch(es) of one decision record on the engine's stream.
+static bool engine_launch_record(void *ctx, const LaunchRec &rec) {
+  kai_engine *e = (kai_engine *)ctx;
+  const int kind = (int)(rec.dw[0] & 0xff);
+  const unsigned int xbits = (unsigned int)((rec.dw[0] >> 48) & 0xffff);
+  const size_t dyn = sizeof(MergeKey) * (size_t)kMergeCap;
+  if (kind == DK_SCAN && (xbits & XB_FUSED_MM)) {
+    // pack.go:66-86 over the row set of this sweep: a MINMAX launch (applies the deltas and the feasible-set snapshot,
+    // leaves the reduced extremes in device memory) followed by the sweep itself, back to back on the stream
+    LaunchRec a = rec;
+    a.dw[0] = (rec.dw[0] & ~0xffull) | (unsigned long long)DK_MINMAX;
+    k_record<<<e->lgrid, kThreads, dyn, e->stream>>>(e->lp, a);
+    LaunchRec b = rec;
+    b.n_delta = 0;
+    b.dw[0] = rec.dw[0] & ~(0xffffull << 32) & ~((unsigned long long)(XB_SNAP_ALL | XB_SNAP_GPUFREE) << 48);
+    k_record<<<e->lgrid, kThreads, dyn, e->stream>>>(e->lp, b);
+    e->record_launches += 2;
+  } else {
+    k_record<<<e->lgrid, kThreads, dyn, e->stream>>>(e->lp, rec);
+    e->record_launches++;
+  }
+  return cudaPeekAtLastError() == cudaSuccess;
+}
+
 int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (!e || !out) return KAI_ERR_INVALID;
   if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
@@ -855,7 +931,11 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (!host_mode && e->topo.any())
     for (int j = 0; j < e->J; j++)
       if (e->topo.constrained(j)) return e->fail(KAI_ERR_UNSUPPORTED, "topology constraints need the host-sequenced mode");
-  p.mode = host_mode ? 1 : 0;
+  // transport of the host-sequenced mode: "launch" (default) = one k_record launch per decision record, tiles in global
+  // memory; "persistent" = the cooperative scan-server kernel polling records in pinned host memory
+  const char *tr_env = getenv("KAI_TRANSPORT");
+  const bool launch_mode = host_mode && !(tr_env && strcmp(tr_env, "persistent") == 0);
+  p.mode = host_mode ? (launch_mode ? 2 : 1) : 0;
   p.spin_log2 = host_mode ? 26 : 22;
   if (host_mode) {
     p.h_rec = e->h_rec;
@@ -869,6 +949,21 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     p.h_list = e->cfg.shard_count > 1 ? e->shm_dev + (size_t)2 * 2 * kMaxGrid * kSlotWords : e->h_list;
     p.scanner_base = e->cfg.shard_rank * (e->grid - 1);
     if ((long long)e->cfg.shard_count * (e->grid - 1) > kListScanners) p.topm = 0;
+    if (launch_mode) {
+      if (e->cfg.shard_count > kShmRanks) return e->fail(KAI_ERR_UNSUPPORTED, "more GPUs than the exchange segment holds");
+      p.grid = e->lgrid + 1;  // scanners = grid - 1, as in the persistent kernel
+      p.nodes_per_cta = e->lnpc;
+      p.topm = (p.batching && !getenv("KAI_NO_TOPM")) ? 1 : 0;
+      p.h_list = e->d_list;  // the scanners' top-M lines stay on the device; the last CTA merges them
+      p.scanner_base = 0;
+      p.g_tiles = e->g_tiles;
+      p.g_tile_stride = e->ltile_stride;
+      p.g_scan_state = e->g_scan_state;
+      p.ticket = e->ticket;
+      p.mm_result = e->mm_result;
+      p.h_clist = e->cfg.shard_count > 1 ? e->shm_dev + shm_clist_offset_words() + (size_t)e->cfg.shard_rank * 2 * kCListWords : e->h_clist;
+      p.spin_log2 = 22;
+    }
   }
   void *args[] = {(void *)&p};
   CK(cudaMemsetAsync(e->counters, 0, sizeof(long long) * 48, e->stream));
@@ -892,8 +987,23 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       }
     }
     cudaEventRecord(e->ev_mirror, e->stream);
-    CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
-    cudaEventRecord(e->ev[3], e->stream);
+    if (launch_mode) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MergeKey) * kMergeCap)));
+        attr_set = true;
+      }
+      e->lp = p;
+      e->record_launches = 0;
+      LaunchRec load;
+      memset(&load, 0, sizeof(load));
+      load.dw[0] = (unsigned long long)DK_LOAD;
+      load.seq = p.seq0;
+      if (!engine_launch_record(e, load)) return e->cuda_fail(cudaGetLastError(), "k_record (tile load)");
+    } else {
+      CK(cudaLaunchCooperativeKernel((const void *)k_action, dim3(e->grid), dim3(kThreads), args, e->smem_bytes, e->stream));
+      cudaEventRecord(e->ev[3], e->stream);
+    }
     // wait for the mirror copy only (the kernel keeps running): event-free trick = query the D2H through an event
     cudaEvent_t mirror_done = e->ev[4];
     (void)mirror_done;
@@ -911,6 +1021,12 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     for (int i = 0; i < 8; i++) hb.t_sec[i] = 0;
     hb.h_list = e->cfg.shard_count > 1 ? e->shm_base + (size_t)2 * 2 * kMaxGrid * kSlotWords : e->h_list;
     hb.n_list_scanners = e->cfg.shard_count * (e->grid - 1);
+    hb.launch_mode = launch_mode;
+    hb.launch_fn = &engine_launch_record;
+    hb.launch_ctx = e;
+    hb.launches = 0;
+    hb.n_ranks = e->cfg.shard_count;
+    hb.h_clist = e->cfg.shard_count > 1 ? e->shm_base + shm_clist_offset_words() : e->h_clist;
     hb.listed = 0;
     hb.batch_is_single = false;
     hb.list_yield_ema = 8.0;
@@ -1088,7 +1204,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         }
       }
     }
+    if (launch_mode) cudaEventRecord(e->ev[3], e->stream);  // after the DONE launch: the action's span on the device
     CK(cudaStreamSynchronize(e->stream));
+    if (launch_mode) CK(cudaGetLastError());
     if (solver_action && getenv("KAI_PROFILE"))
       fprintf(stderr, "[kai] solver: %lld scenarios simulated, %lld node sweeps, %lld top-k sweeps, %lld minmax exchanges\n",
               solver_scenarios, seq.sweeps, solver_topk, seq.minmax_exchanges);
@@ -1138,7 +1256,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   e->stats.decisions = c[1];
   e->stats.nodes_scanned = c[2];
   e->stats.algorithmic_bytes = c[2] * ((2 * e->R + 1) * 8 + 4);
-  e->stats.kernel_launches += 1 + (e->J > 0) + (e->Q > 0);
+  e->stats.kernel_launches += (launch_mode ? e->record_launches : 1) + (e->J > 0) + (e->Q > 0);
   e->seq = (unsigned int)c[7];
   if (getenv("KAI_PROFILE")) {
     const char *nm[] = {"init", "pop", "prepare", "keycalc", "exchange", "apply", "finish"};
@@ -1146,8 +1264,9 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%lld", nm[i], c[8 + i]);
     fprintf(stderr, " n_key=%lld tta=%lld popheap=%lld\n", c[16], c[17], c[18]);
     if (host_mode)
-      fprintf(stderr, "[kai] host sequencer: total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
-              e->hb.t_total * 1e3, e->hb.t_exchange * 1e3, c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
+      fprintf(stderr, "[kai] host sequencer (%s transport, %lld record launches): total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
+              launch_mode ? "launch" : "persistent", launch_mode ? e->record_launches : 0LL, e->hb.t_total * 1e3, e->hb.t_exchange * 1e3,
+              c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
     if (host_mode) fprintf(stderr, "[kai] sweeps answered with a single row (XB_SINGLE): %lld; FLUSH records %lld\n", e->hb.single_sweeps, e->hb.n_flush);
     if (host_mode && e->hb.n_topo_jobs)
       fprintf(stderr, "[kai] topology: %lld constrained jobs with candidates, %lld domains tried; subSetNodesFn %.1f ms, score table %.1f ms, placing %.1f ms\n",
@@ -1197,7 +1316,7 @@ int kai_engine_stats(kai_engine *e, kai_stats *out) {
 // Multi-GPU wiring.  Rank 0 creates the shared segment and exports its name; every rank (rank 0 included)
 // passes the table of handles (only entry 0 is read) to kai_engine_wire_peers.
 static int shm_map(kai_engine *e, bool create) {
-  const size_t bytes = ((size_t)2 * 2 * kMaxGrid * kSlotWords + (size_t)2 * kListScanners * kListLines * kListLineWords) * 8;
+  const size_t bytes = (shm_clist_offset_words() + (size_t)kShmRanks * 2 * kCListWords) * 8;
   int fd = shm_open(e->shm_name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
   if (fd < 0) return e->fail(KAI_ERR_INVALID, std::string("shm_open failed for ") + e->shm_name);
   if (create && ftruncate(fd, (off_t)bytes) != 0) {

@@ -85,6 +85,14 @@ struct HostBackend {
   unsigned int trace_seq[64];
   int trace_nd[64];
   unsigned int trace_n = 0;
+  // ---- launch transport: a record is a kernel launch (k_record), the answer one merged line / list per GPU ----
+  bool launch_mode = false;
+  void *launch_ctx = nullptr;
+  bool (*launch_fn)(void *ctx, const LaunchRec &rec) = nullptr;  // kai_engine.cu: enqueues the launch(es) of one record
+  unsigned long long *h_clist = nullptr;  // [ranks][2][kCListWords] merged candidate lists (pinned / shared host memory)
+  int n_ranks = 1;
+  LaunchRec lrec;
+  long long launches = 0;
   void publish(int kind) {
     trace_kind[trace_n & 63] = kind;
     trace_seq[trace_n & 63] = ctl.seq;
@@ -92,6 +100,20 @@ struct HostBackend {
     trace_n++;
     close_delta(ctl, seq.delta_base);
     build_decision_words(ctl, kind, batching);
+    if (launch_mode) {
+      for (int i = 0; i < kDecWords; i++) lrec.dw[i] = ctl.dw[i];
+      lrec.seq = ctl.seq;
+      lrec.n_delta = ctl.n_delta;
+      const unsigned long long *dl = seq.delta_base + (size_t)(ctl.seq & 1) * kMaxDelta * 2;
+      for (int e = 0; e < ctl.n_delta; e++) {
+        lrec.dkey[e] = (unsigned int)(dl[2 * e] & 0xffffffffu);
+        lrec.dtask[e] = (unsigned int)(dl[2 * e] >> 32);
+        lrec.dcount[e] = (unsigned char)((dl[2 * e + 1] >> 32) & 0xffu);
+      }
+      launches++;
+      if (!launch_fn(launch_ctx, lrec)) failed = true;
+      return;
+    }
     unsigned long long *rec = h_rec + (size_t)(ctl.seq & 1) * kDecWords * 2;
     for (int i = kDecWords - 1; i >= 0; i--) store_tagged(rec + 2 * i, ctl.dw[i], (unsigned long long)ctl.seq);
   }
@@ -158,7 +180,67 @@ struct HostBackend {
   // Gather the top-M answers of every scanner, merge them into one list in key order and mark the prefix that
   // is provably the global order: entries strictly better than the last reported key of any scanner that has more
   // fitting rows than it reported.
+  // launch transport: every GPU's last CTA has merged, cut and written its list; merge the lists of the ranks
+  void gather_list_merged() {
+    const unsigned int seq_no = ctl.seq;
+    list.clear();
+    bool have_cut = false;
+    double cut_score = 0;
+    uint32_t cut_rank = 0;
+    for (int r = 0; r < n_ranks && !failed; r++) {
+      const unsigned long long *cl = h_clist + ((size_t)r * 2 + (seq_no & 1)) * kCListWords;
+      unsigned long long hi;
+      if (!wait_word(cl + 1, [&](unsigned long long v) { return v == (unsigned long long)seq_no; }, hi)) break;
+      const unsigned long long head = __atomic_load_n(cl, __ATOMIC_RELAXED);
+      const int n = (int)(head & 0x7fffffffu);
+      const bool more = ((head >> 31) & 1ull) != 0;
+      for (int i = 0; i < n; i++) {
+        const unsigned long long *e = cl + 2 + (size_t)i * kCEntryWords;
+        ListCand lc;
+        memcpy(&lc.score, &e[0], 8);
+        const unsigned long long meta = e[1];
+        lc.rank = (uint32_t)(meta & 0xffffffu);
+        lc.flags = (uint32_t)((meta >> 32) & 0xffu);
+        lc.node = rank_to_node[lc.rank];
+        lc.cap = 1 + (int)((meta >> 24) & 0xffu);
+        lc.used = 0;
+        lc.payload = nullptr;
+        lc.loaded = true;
+        memcpy(&lc.Ig, &e[2], 8);
+        memcpy(&lc.Lg, &e[3], 8);
+        memcpy(&lc.Ic, &e[4], 8);
+        memcpy(&lc.Lc, &e[5], 8);
+        list.push_back(lc);
+      }
+      if (more && n > 0) {  // unseen rows of this GPU are worse than its last listed row
+        const ListCand &last = list.back();
+        if (!have_cut || last.score > cut_score || (last.score == cut_score && last.rank < cut_rank)) {
+          have_cut = true;
+          cut_score = last.score;
+          cut_rank = last.rank;
+        }
+      }
+    }
+    if (n_ranks > 1)
+      std::sort(list.begin(), list.end(), [](const ListCand &a, const ListCand &b) {
+        return a.score > b.score || (a.score == b.score && a.rank < b.rank);
+      });
+    list_valid = list.size();
+    if (have_cut && n_ranks > 1)
+      for (size_t i = 0; i < list.size(); i++)
+        if (!(list[i].score > cut_score || (list[i].score == cut_score && list[i].rank <= cut_rank))) {
+          list_valid = i;
+          break;
+        }
+    list_pos = 0;
+    list_more = have_cut;
+    list_tag = seq_no & 0xffffffu;
+    ctl.seq = seq_no + 1;
+    ctl.n_delta = 0;
+    ctl.batch.valid = 0;
+  }
   void gather_list() {
+    if (launch_mode) return gather_list_merged();
     const unsigned int seq_no = ctl.seq;
     const unsigned int tag = seq_no & 0xffffffu;
     const unsigned long long *base = h_list + (size_t)(seq_no & 1) * kListScanners * kListLines * kListLineWords;
@@ -490,6 +572,11 @@ struct HostBackend {
   void flush_deltas() {
     n_flush++;
     publish(DK_FLUSH);
+    if (launch_mode) {  // stream order: the next launch sees these deltas applied; nothing to wait for
+      ctl.seq++;
+      ctl.n_delta = 0;
+      return;
+    }
     const unsigned int seq_no = ctl.seq;
     const unsigned long long *buf = h_slots + (size_t)(seq_no & 1) * kMaxGrid * kSlotWords;
     const unsigned int tag = seq_no & 0xffffffu;

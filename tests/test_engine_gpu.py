@@ -345,3 +345,23 @@ def test_historical_usage_and_k_value(k_value):
     snap2.queue_deserved = snap.queue_deserved
     plain.load(snap2)
     assert not np.array_equal(plain.run("allocate").queue_fair_share, ro.queue_fair_share)  # usage is not vacuous
+
+
+@pytest.mark.parametrize("grid", [None, "5"])
+def test_tables_persistent_transport(grid, monkeypatch):
+    """The cooperative scan-server kernel (KAI_TRANSPORT=persistent; the default transport is one launch per record)."""
+    monkeypatch.setenv("KAI_TRANSPORT", "persistent")
+    if grid:
+        monkeypatch.setenv("KAI_GRID_EXACT", grid)
+    for cid, case in ALLOCATE:
+        snap, meta = dsl.build_snapshot(case["topology"])
+        re_, ro = run_both(snap, cfg=case_config(case))
+        assert_same(re_, ro)
+    for cid, case in SOLVER:
+        snap, meta = dsl.build_snapshot(case["topology"])
+        re_, ro = run_both(snap, action=case["actions"][0])
+        assert_same(re_, ro)
+    snap = synthetic.benchmark_snapshot(n_nodes=1000, n_jobs=3000, tasks_per_job=2, n_queues=40, mixed=True)
+    assert_same(*run_both(snap))
+    snap = synthetic.config_snapshot("config4-small")
+    assert_same(*run_both(snap))
