@@ -204,9 +204,9 @@ def main():
         "workload": desc,
         "nodes": snap.n_nodes, "pods": int(snap.task_status.shape[0]), "queues": int(snap.queue_parent.shape[0]),
         "parallelism": f"nodes sharded by range over {args.gpus} GPUs, one sequencer replica per rank" if args.gpus > 1 else "1 GPU",
-        "sequencer": os.environ.get("KAI_SEQUENCER", "host"),
-        "l2_policy": "node tables are re-uploaded (H2D) before every timed step, which replaces the L2-resident copy; "
-                     "the action kernel then keeps its node tiles in shared memory",
+        "sequencer": os.environ.get("KAI_SEQUENCER", "host"), "transport": os.environ.get("KAI_TRANSPORT", "launch"),
+        "l2_policy": "the whole snapshot is re-uploaded (H2D) before every timed step; within a step the node tiles "
+                     "(76 B x nodes, 3.8 MB at 50 000 nodes) stay L2-resident between the sweep launches by design",
     }
     if args.impl == "reference":
         run_reference(args, snap, workload, actions, engine_kw)
@@ -300,9 +300,21 @@ def main():
         pods_all = pods  # every rank places the same pods (replicated sequencer over sharded nodes)
     else:
         pods_all = pods
+    # dominant kernel: k_record, one launch per node-table sweep.  Its duration is measured live: back-to-back launches of
+    # one list sweep over this rank's node rows, CUDA events on the engine's stream (kai_engine_time_sweeps)
+    sweep_ms, sweep_rows = eng.time_sweeps(200) if args.steps > 0 else (0.0, 0)
     if rank == 0:
         peak, which = measured_peak_gbs()
-        achieved = (alg_bytes / args.steps) / (act_ms / args.steps * 1e-3) / 1e9 if act_ms > 0 else 0.0
+        sweep_bytes = sweep_rows * BYTES_PER_NODE
+        achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+        traffic, traffic_src = None, "no ncu --set full capture recorded for this build"
+        tp = os.path.join(ROOT, "profiles", "r02_k_record_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            except Exception:
+                pass
         line = {
             "metric": METRIC, "value": pods_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -314,17 +326,17 @@ def main():
                     # engine-side phases of one step (kai_engine_stats); the rest of e2e is marshalling in the caller
                     "phases_ms": {k: v / max(args.steps, 1) for k, v in phase_ms.items()}},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_action", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_record (one node-table sweep per launch: fit + score + per-scanner top-M, "
+                                                   "merged and cut by the last CTA)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "algorithmic_bytes_per_launch": alg_bytes // max(args.steps, 1),
-                         # the naive path sweeps every node for every pod; executed sweeps are what
-                         # `achieved` counts, this is the same workload in the reference's own terms
-                         "naive_equivalent_bytes_per_launch": int(snap.n_nodes) * int(pods_all // max(args.steps, 1)) * BYTES_PER_NODE,
-                         "kernel_ms_per_launch": act_ms / args.steps, "traffic": None,
-                         "traffic_note": "the host-sequenced kernel cannot run under ncu (the profiler serialises it with the "
-                                         "host thread that feeds it); ncu --set full of the same kernel with the device-resident "
-                                         "sequencer: dram read 440 KB + write 1.8 KB per launch on config1 "
-                                         "(profiles/r01c_k_action_device_config1_raw.csv): rows are shared-memory resident"},
+                         "algorithmic_bytes_per_launch": sweep_bytes, "rows_per_launch": sweep_rows,
+                         "kernel_us_per_launch": 1e3 * sweep_ms,
+                         "how": "200 back-to-back launches of one list sweep timed with CUDA events on the engine's stream, after the timed steps",
+                         "sweeps_per_step": decisions, "sweep_share_of_step": (decisions * sweep_ms) / (act_ms / args.steps) if act_ms > 0 else None,
+                         # the naive path sweeps every node for every pod
+                         "naive_equivalent_bytes_per_step": int(snap.n_nodes) * int(pods_all // max(args.steps, 1)) * BYTES_PER_NODE,
+                         "traffic": traffic, "traffic_source": traffic_src},
             "clocks": clocks,
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }

@@ -100,7 +100,20 @@ __global__ void k_prep_jobs(DevSnap s, int filter_non_pending, int filter_unread
         rec.req0[r] = sum[r];
       }
       s.j_req_valid[j] = 1;
-      if (prefix && act == 0 && rec.cnt[2] == 0) rec.n_tta = taken;
+      if (prefix && act == 0 && rec.cnt[2] == 0) {
+        rec.n_tta = taken;
+        // pad[0]: the selected tasks are interchangeable for the sweep (bit-identical request, nominated node, predicate
+        // class): the host sequencer may defer their per-task bookkeeping until the gang is complete
+        bool uniform = taken >= 1;
+        const int t0 = rec.tb;
+        for (int t = t0 + 1; t < t0 + taken && uniform; t++) {
+          for (int r = 0; r < s.R; r++)
+            if (__double_as_longlong(s.t_req[(size_t)t * s.R + r]) != __double_as_longlong(s.t_req[(size_t)t0 * s.R + r])) uniform = false;
+          if (s.t_nominated && s.t_nominated[t] != s.t_nominated[t0]) uniform = false;
+          if (s.t_pred_class && s.t_pred_class[t] != s.t_pred_class[t0]) uniform = false;
+        }
+        rec.pad[0] = uniform ? 1 : 0;
+      }
     }
     s.jrec[j] = rec;
   }
@@ -894,6 +907,29 @@ KAI_HD void seq_flush_deltas(Seq &q) {
 // =============================================================================================
 // scanner CTA
 // =============================================================================================
+// the arrays of a tile inside one contiguous block (shared memory of a persistent scanner, or the scanner's block of
+// g_tiles; the launch transport copies the latter into shared memory for the sweep, same offsets)
+__device__ __forceinline__ void tile_carve(Tile &tile, unsigned char *ptr) {
+  const int npc = tile.npc;
+  tile.I = (double *)ptr;
+  ptr += sizeof(double) * tile.R * npc;
+  tile.L = (double *)ptr;
+  ptr += sizeof(double) * tile.R * npc;
+  tile.Agpu = (double *)ptr;
+  ptr += sizeof(double) * npc;
+  tile.Acpu = (double *)ptr;
+  ptr += sizeof(double) * npc;
+  tile.gpu_count = (double *)ptr;
+  ptr += sizeof(double) * npc;
+  tile.rank = (int *)ptr;
+  ptr += sizeof(int) * npc;
+  tile.flags = (uint32_t *)ptr;
+  ptr += sizeof(uint32_t) * npc;
+  tile.node = (int *)ptr;
+  ptr += sizeof(int) * npc;
+  tile.dom = (int *)ptr;
+}
+
 struct ScanShared {
   unsigned long long dw[kDecWords];
   Decision dec;
@@ -902,7 +938,7 @@ struct ScanShared {
   int pref_level;                           // topology node scoring: global level index or -1 (off)
   unsigned char dom_bucket[kDomBuckets];    // bucket per preferred-level domain, 255 = no entry
   int2 delta[kMaxDelta];
-  unsigned char mine[kMaxDelta];
+  unsigned int mine_bits[kMaxDelta / 32], ext_bits[kMaxDelta / 32];  // per 32 list entries: owned by this scanner / extended
   int fit_count;
   int ext_dirty;  // launch transport: the preferred-level score table changed in this launch
   int excl[kTopM];
@@ -935,24 +971,8 @@ __device__ bool scanner_main(const ActionParams &p, const LaunchRec *lrec, unsig
       long long first = (long long)my * tile.nshard + tile.shard, step = (long long)tile.nscan * tile.nshard;
       tile.count = first < s.N ? (int)((s.N - first + step - 1) / step) : 0;
     }
-    tile.I = (double *)ptr;
-    ptr += sizeof(double) * s.R * npc;
-    tile.L = (double *)ptr;
-    ptr += sizeof(double) * s.R * npc;
-    tile.Agpu = (double *)ptr;
-    ptr += sizeof(double) * npc;
-    tile.Acpu = (double *)ptr;
-    ptr += sizeof(double) * npc;
-    tile.gpu_count = (double *)ptr;
-    ptr += sizeof(double) * npc;
-    tile.rank = (int *)ptr;
-    ptr += sizeof(int) * npc;
-    tile.flags = (uint32_t *)ptr;
-    ptr += sizeof(uint32_t) * npc;
-    tile.node = (int *)ptr;
-    ptr += sizeof(int) * npc;
-    tile.dom = (int *)ptr;
     tile.n_dom_levels = p.node_domain ? p.n_dom_levels : 0;
+    tile_carve(tile, ptr);
     sh.pref_level = -1;
     sh.ext_dirty = 0;
     if (LAUNCH && (int)(lrec->dw[0] & 0xff) != DK_LOAD) sh.pref_level = *(const int *)gstate;
@@ -1050,76 +1070,100 @@ __device__ bool scanner_main(const ActionParams &p, const LaunchRec *lrec, unsig
     __syncthreads();
     long long c2 = clock64();
     // ---- apply the node deltas that belong to this tile (loads in parallel, application in list order) ----
+    // Every scanner sees the whole list but owns ~1/scanners of it: the entries are classified in parallel (ballot bits
+    // per 32 entries: "mine", "extended") and only the set bits are walked, in list order.
     const int nd = sh.n_delta;
     if (nd > 0) {
       const unsigned long long *dl = p.delta + (size_t)(seq & 1) * kMaxDelta * 2;
-      for (int e = tid; e < nd; e += blockDim.x) {
-        unsigned long long lo, hi;
-        if (LAUNCH) {
-          lo = (unsigned long long)lrec->dkey[e] | ((unsigned long long)lrec->dtask[e] << 32);
-          hi = (unsigned long long)seq | ((unsigned long long)lrec->dcount[e] << 32);
-        } else {
-          Spin spin;
-          do {
-            ld_relaxed_b128(dl + 2 * e, lo, hi);
-          } while (((unsigned int)hi != (unsigned int)seq) && !spin.expired(p, 9, (unsigned int)seq, (int)(e)));
+      for (int e0 = 0; e0 < nd; e0 += blockDim.x) {
+        const int e = e0 + tid;
+        bool mine = false, ext = false;
+        if (e < nd) {
+          unsigned long long lo, hi;
+          if (LAUNCH) {
+            lo = (unsigned long long)lrec->dkey[e] | ((unsigned long long)lrec->dtask[e] << 32);
+            hi = (unsigned long long)seq | ((unsigned long long)lrec->dcount[e] << 32);
+          } else {
+            Spin spin;
+            do {
+              ld_relaxed_b128(dl + 2 * e, lo, hi);
+            } while (((unsigned int)hi != (unsigned int)seq) && !spin.expired(p, 9, (unsigned int)seq, (int)(e)));
+          }
+          int2 en = make_int2((int)(unsigned int)(lo & 0xffffffffu), (int)(unsigned int)(lo >> 32));
+          sh.delta[e] = en;
+          int ln = 0;
+          ext = en.x < 0;
+          mine = en.x >= 0 && tile_owns(tile, (unsigned int)(en.x & 0x0fffffff), ln) && ln < tile.count;
+          sh.dln[e] = ln | ((int)(hi >> 32) << 24);  // repeat count - 1 in the top byte
+          if (mine && ((en.x >> 28) & 7) < ND_FEAS_SET)
+            for (int r = 0; r < s.R; r++) sh.dreq[e][r] = __ldg(&s.t_req[(size_t)en.y * s.R + r]);
         }
-        int2 en = make_int2((int)(unsigned int)(lo & 0xffffffffu), (int)(unsigned int)(lo >> 32));
-        sh.delta[e] = en;
-        int ln = 0;
-        bool mine = en.x >= 0 && tile_owns(tile, (unsigned int)(en.x & 0x0fffffff), ln) && ln < tile.count;
-        sh.mine[e] = mine ? 1 : 0;
-        sh.dln[e] = ln | ((int)(hi >> 32) << 24);  // repeat count - 1 in the top byte
-        if (mine && ((en.x >> 28) & 7) < ND_FEAS_SET)
-          for (int r = 0; r < s.R; r++) sh.dreq[e][r] = __ldg(&s.t_req[(size_t)en.y * s.R + r]);
+        const unsigned int mb = __ballot_sync(0xffffffffu, mine), xb = __ballot_sync(0xffffffffu, ext);
+        if (lane == 0) {
+          sh.mine_bits[(e0 >> 5) + warp] = mb;
+          sh.ext_bits[(e0 >> 5) + warp] = xb;
+        }
       }
       __syncthreads();
+      const int n_words = (nd + 31) >> 5;
       if (warp == 0 && lane < s.R) {
-        for (int e = 0; e < nd; e++) {
-          if (!sh.mine[e]) continue;
-          int2 en = sh.delta[e];
-          const int ln = sh.dln[e] & 0xffffff, reps = ((unsigned int)sh.dln[e] >> 24) + 1;
-          const int code = (en.x >> 28) & 7;
-          if (code >= ND_FEAS_SET) {
-            if (lane == 0) tile.flags[ln] = code == ND_FEAS_SET ? (tile.flags[ln] | kTileFeas) : (tile.flags[ln] & ~kTileFeas);
-            continue;
+        for (int w = 0; w < n_words; w++) {
+          unsigned int bits = sh.mine_bits[w];
+          while (bits) {
+            const int e = (w << 5) + __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            int2 en = sh.delta[e];
+            const int ln = sh.dln[e] & 0xffffff, reps = ((unsigned int)sh.dln[e] >> 24) + 1;
+            const int code = (en.x >> 28) & 7;
+            if (code >= ND_FEAS_SET) {
+              if (lane == 0) tile.flags[ln] = code == ND_FEAS_SET ? (tile.flags[ln] | kTileFeas) : (tile.flags[ln] & ~kTileFeas);
+              continue;
+            }
+            for (int k = 0; k < reps; k++)
+              apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], code, sh.dreq[e][lane]);
           }
-          for (int k = 0; k < reps; k++)
-            apply_delta_row(tile.I[lane * tile.npc + ln], tile.L[lane * tile.npc + ln], code, sh.dreq[e][lane]);
         }
       }
       __syncthreads();
-    }
-    if (nd > 0) {  // extended entries, in list order: topology domain selection and the per-domain score table
-      for (int e = 0; e < nd; e++) {
-        const int2 en = sh.delta[e];
-        if (en.x >= 0) continue;
-        const int kind = (en.x >> 28) & 7;
-        const unsigned int a = (unsigned int)en.x & 0x0fffffffu, b = (unsigned int)en.y;
-        if (kind == EXT_SELECT || kind == EXT_SELECT_ROOT) {
-          const int slot = kind == EXT_SELECT ? (int)((a >> 8) & 7u) : (int)((a >> 16) & 7u);
-          const uint32_t bit = kTileDom >> slot;
-          for (int ln = tid; ln < tile.count; ln += blockDim.x) {
-            bool in;
-            if (kind == EXT_SELECT) {
-              in = tile.dom[((int)(a & 0xffu) - 1) * tile.npc + ln] == (int)b;
-            } else {
-              in = true;
-              for (int l = (int)(a & 0xff); l < (int)((a >> 8) & 0xff); l++)
-                if (tile.dom[l * tile.npc + ln] < 0) in = false;
+      // extended entries, in list order: topology domain selection (each thread its own rows) and the per-domain
+      // score table (thread 0; the clearing BEGIN is the only step the others take part in)
+      bool any_ext = false;
+      for (int w = 0; w < n_words; w++) {
+        unsigned int bits = sh.ext_bits[w];
+        while (bits) {
+          const int e = (w << 5) + __ffs((int)bits) - 1;
+          bits &= bits - 1;
+          any_ext = true;
+          const int2 en = sh.delta[e];
+          const int kind = (en.x >> 28) & 7;
+          const unsigned int a = (unsigned int)en.x & 0x0fffffffu, b = (unsigned int)en.y;
+          if (kind == EXT_SELECT || kind == EXT_SELECT_ROOT) {
+            const int slot = kind == EXT_SELECT ? (int)((a >> 8) & 7u) : (int)((a >> 16) & 7u);
+            const uint32_t bit = kTileDom >> slot;
+            for (int ln = tid; ln < tile.count; ln += blockDim.x) {
+              bool in;
+              if (kind == EXT_SELECT) {
+                in = tile.dom[((int)(a & 0xffu) - 1) * tile.npc + ln] == (int)b;
+              } else {
+                in = true;
+                for (int l = (int)(a & 0xff); l < (int)((a >> 8) & 0xff); l++)
+                  if (tile.dom[l * tile.npc + ln] < 0) in = false;
+              }
+              tile.flags[ln] = in ? (tile.flags[ln] | bit) : (tile.flags[ln] & ~bit);
             }
-            tile.flags[ln] = in ? (tile.flags[ln] | bit) : (tile.flags[ln] & ~bit);
+          } else if (kind == EXT_SCORE_BEGIN) {
+            __syncthreads();  // earlier EXT_SCORE writes of thread 0 precede the clearing
+            for (int i = tid; i < kDomBuckets; i += blockDim.x) sh.dom_bucket[i] = 255;
+            if (tid == 0) sh.pref_level = (int)a, sh.ext_dirty = 1;
+            __syncthreads();
+          } else if (kind == EXT_SCORE) {
+            if (tid == 0 && a < (unsigned int)kDomBuckets) sh.dom_bucket[a] = (unsigned char)b, sh.ext_dirty = 1;
+          } else if (kind == EXT_SCORE_END) {
+            if (tid == 0) sh.pref_level = -1, sh.ext_dirty = 1;
           }
-        } else if (kind == EXT_SCORE_BEGIN) {
-          for (int i = tid; i < kDomBuckets; i += blockDim.x) sh.dom_bucket[i] = 255;
-          if (tid == 0) sh.pref_level = (int)a, sh.ext_dirty = 1;
-        } else if (kind == EXT_SCORE) {
-          if (tid == 0 && a < (unsigned int)kDomBuckets) sh.dom_bucket[a] = (unsigned char)b, sh.ext_dirty = 1;
-        } else if (kind == EXT_SCORE_END) {
-          if (tid == 0) sh.pref_level = -1, sh.ext_dirty = 1;
         }
-        __syncthreads();
       }
+      if (any_ext) __syncthreads();
     }
     if (sh.xbits & (XB_SNAP_ALL | XB_SNAP_GPUFREE)) {  // common.FeasibleNodesForJob (feasible_nodes.go:11-26)
       const bool all = (sh.xbits & XB_SNAP_ALL) != 0;
@@ -1132,8 +1176,19 @@ __device__ bool scanner_main(const ActionParams &p, const LaunchRec *lrec, unsig
     long long c3 = clock64();
     const int kind = sh.kind;
     if (kind == DK_DONE || ((volatile long long *)p.counters)[24] != 0) break;
+    if (LAUNCH && p.hot_in_smem && (kind == DK_SCAN || kind == DK_TOPK || kind == DK_MINMAX)) {
+      // the sweep reads every row several times (top-M passes, repeat analysis): stage this scanner's block of g_tiles
+      // in shared memory with one pass of independent 16-byte loads; deltas and row flags were applied to the
+      // global copy above, nothing below writes the tile
+      const uint4 *src = (const uint4 *)(p.g_tiles + (size_t)my * p.g_tile_stride);
+      uint4 *dst = (uint4 *)smem;
+      const int n16 = (int)(p.tile_bytes >> 4);
+      for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
+      if (tid == 0) tile_carve(tile, smem);
+      __syncthreads();
+    }
     unsigned long long *slot = p.xbuf + (size_t)(seq & 1) * kMaxGrid * kSlotWords + (size_t)my * kSlotWords;
-    if (LAUNCH && kind == DK_SCAN && (sh.xbits & XB_FUSED_MM)) {
+    if (LAUNCH && !p.fused_in_kernel && kind == DK_SCAN && (sh.xbits & XB_FUSED_MM)) {
       // the extremes of this row set were reduced by the MINMAX launch that precedes this one on the stream
       if (tid == 0) {
         const int k = sh.dec.res == KAI_RES_GPU ? 0 : 1;
@@ -1338,6 +1393,8 @@ __device__ bool scanner_main(const ActionParams &p, const LaunchRec *lrec, unsig
       break;
     }
   }
+  if (LAUNCH && tid == 0 && my == 0)  // launches of one action follow each other on the stream: plain accumulation
+    for (int i = 0; i < 7; i++) p.counters[32 + i] += ts[i];
   if (LAUNCH) {
     if (sh.ext_dirty) {  // preferred-level score table of this scanner: back to its global copy
       for (int i = tid; i < kDomBuckets; i += blockDim.x) gstate[16 + i] = sh.dom_bucket[i];
@@ -1833,23 +1890,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
 // fitting rows than they reported — the rule HostBackend::gather_list applies), and write the usable prefix as
 // 48-byte entries {score, meta, Ig, Lg, Ic, Lc} + one header word to host memory: the host reads one contiguous list
 // instead of scanners x (1 + M) cache lines.
-struct MergeKey {
-  double score;
-  uint32_t rank;
-  uint32_t src;  // scanner * kTopM + m
+struct MergeKey {  // 16 bytes of shared memory per candidate (two u64 planes: kh = score key, kl = rank | source)
+  unsigned long long h, l;
 };
-__device__ __forceinline__ bool key_before(const MergeKey &a, const MergeKey &b) {  // a sorts before b
-  if (a.rank == kRankNone) return false;
-  if (b.rank == kRankNone) return true;
-  return a.score > b.score || (a.score == b.score && a.rank < b.rank);
-}
-__device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_payload, MergeKey *keys, Cand *sh_warp,
+// Integer sort keys: kh = ~bits(score) (scores are sums of non-negative terms, so ascending kh is descending score),
+// kl = rank << 32 | source (scanner * kTopM + m); an empty slot is all ones in both and sorts last.
+__device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_payload, MergeKey *keymem, Cand *sh_warp,
                             int *sh_i) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int n_scan = p.grid - 1;
   const int n_c = n_scan * kTopM;
   int n_pow = 1;
   while (n_pow < n_c) n_pow <<= 1;
+  unsigned long long *kh = (unsigned long long *)keymem, *kl = kh + n_pow;
   const unsigned long long *base = p.h_list + (size_t)(seq & 1) * kListScanners * kListLines * kListLineWords;
   // ---- candidates + the cut ----
   Cand cut;
@@ -1861,19 +1914,22 @@ __device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_p
     bool more = false;
     double last_score = 0;
     uint32_t last_rank = kRankNone;
+    unsigned long long lo[kTopM], hi[kTopM];
+#pragma unroll
+    for (int m = 0; m < kTopM; m++) ld_relaxed_b128(lines + 2 * m, lo[m], hi[m]);
+#pragma unroll
     for (int m = 0; m < kTopM; m++) {
-      unsigned long long lo, hi;
-      ld_relaxed_b128(lines + 2 * m, lo, hi);
-      MergeKey k;
-      k.score = __longlong_as_double((long long)lo);
-      k.rank = (uint32_t)(hi & 0xffffffu);
-      k.src = (uint32_t)(c * kTopM + m);
-      if (((uint32_t)(hi >> 32) & 0xffu) & LF_MORE) more = true;
-      if (k.rank != kRankNone) {
-        last_score = k.score;
-        last_rank = k.rank;
+      const uint32_t rank = (uint32_t)(hi[m] & 0xffffffu);
+      if (((uint32_t)(hi[m] >> 32) & 0xffu) & LF_MORE) more = true;
+      if (rank != kRankNone) {
+        last_score = __longlong_as_double((long long)lo[m]);
+        last_rank = rank;
+        kh[c * kTopM + m] = ~lo[m];
+        kl[c * kTopM + m] = ((unsigned long long)rank << 32) | (unsigned long long)(c * kTopM + m);
+      } else {
+        kh[c * kTopM + m] = ~0ull;
+        kl[c * kTopM + m] = ~0ull;
       }
-      keys[c * kTopM + m] = k;
     }
     if (more && last_rank != kRankNone && better(last_score, last_rank, cut.score, cut.rank)) {
       cut.score = last_score;
@@ -1881,9 +1937,8 @@ __device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_p
     }
   }
   for (int i = n_c + tid; i < n_pow; i += blockDim.x) {
-    keys[i].score = -1.0;
-    keys[i].rank = kRankNone;
-    keys[i].src = 0;
+    kh[i] = ~0ull;
+    kl[i] = ~0ull;
   }
   for (int o = 16; o > 0; o >>= 1) {
     double os = __shfl_xor_sync(0xffffffffu, cut.score, o);
@@ -1899,28 +1954,37 @@ __device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_p
   for (int w = 1; w < nw; w++)
     if (better(sh_warp[w].score, sh_warp[w].rank, cut.score, cut.rank)) cut = sh_warp[w];
   const bool have_cut = cut.rank != kRankNone;
-  // ---- bitonic sort, best key first ----
+  const long long tm1 = clock64();
+  // ---- bitonic sort, best key first: one compare-exchange per thread and step on pairs (i, i | j) ----
+  const int half = n_pow >> 1;
   for (int k = 2; k <= n_pow; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n_pow; i += blockDim.x) {
-        const int l = i ^ j;
-        if (l > i) {
-          const MergeKey a = keys[i], b = keys[l];
-          const bool up = (i & k) == 0;
-          if (up ? key_before(b, a) : key_before(a, b)) {
-            keys[i] = b;
-            keys[l] = a;
-          }
+#pragma unroll 4
+      for (int t = tid; t < half; t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned long long ah = kh[i], al = kl[i], bh = kh[l], bl = kl[l];
+        const bool a_first = ah < bh || (ah == bh && al < bl);
+        const bool b_first = bh < ah || (bh == ah && bl < al);
+        const bool up = (i & k) == 0;
+        if (up ? b_first : a_first) {
+          kh[i] = bh;
+          kl[i] = bl;
+          kh[l] = ah;
+          kl[l] = al;
         }
       }
       __syncthreads();
     }
+  const long long tm2 = clock64();
   // ---- usable prefix: real entries that are not worse than the cut ----
   int first_bad = n_c;
   for (int i = tid; i < n_c; i += blockDim.x) {
-    const MergeKey k = keys[i];
-    bool ok = k.rank != kRankNone;
-    if (ok && have_cut && !(k.score > cut.score || (k.score == cut.score && k.rank <= cut.rank))) ok = false;
+    const unsigned long long h = kh[i], l = kl[i];
+    bool ok = l != ~0ull;
+    const double score = __longlong_as_double((long long)~h);
+    const uint32_t rank = (uint32_t)(l >> 32);
+    if (ok && have_cut && !(score > cut.score || (score == cut.score && rank <= cut.rank))) ok = false;
     if (!ok && i < first_bad) first_bad = i;
   }
   for (int o = 16; o > 0; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
@@ -1930,30 +1994,42 @@ __device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_p
   for (int w = 1; w < nw; w++) first_bad = min(first_bad, sh_i[w]);
   const int n_out = first_bad;
   unsigned long long *out = p.h_clist + (size_t)(seq & 1) * kCListWords;
+  // entries are assembled in shared memory (behind the keys) and leave as one linear stream of 16-byte stores:
+  // consecutive threads write consecutive addresses, so the writes cross PCIe as full-size packets
+  unsigned long long *stage = kl + n_pow;
   for (int i = tid; i < n_out; i += blockDim.x) {
-    const MergeKey k = keys[i];
-    const int c = (int)(k.src / kTopM), m = (int)(k.src % kTopM);
+    const int src = (int)(kl[i] & 0xffffffffu);
+    const int c = src / kTopM, m = src % kTopM;
     const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
     unsigned long long lo, hi, w[4] = {0, 0, 0, 0};
     ld_relaxed_b128(lines + 2 * m, lo, hi);
     if (with_payload) {
       const unsigned long long *pl = lines + (size_t)(1 + m) * kListLineWords;
+#pragma unroll
       for (int q = 0; q < 4; q++) {
-        unsigned long long plo, phi;
-        ld_relaxed_b128(pl + 2 * q, plo, phi);
-        w[q] = plo;
+        unsigned long long phi;
+        ld_relaxed_b128(pl + 2 * q, w[q], phi);
       }
     }
-    unsigned long long *e = out + 2 + (size_t)i * kCEntryWords;
-    st_relaxed_sys_b128(e, lo, hi);
-    st_relaxed_sys_b128(e + 2, w[0], w[1]);
-    st_relaxed_sys_b128(e + 4, w[2], w[3]);
+    unsigned long long *e = stage + (size_t)i * kCEntryWords;
+    e[0] = lo;
+    e[1] = hi;
+    e[2] = w[0];
+    e[3] = w[1];
+    e[4] = w[2];
+    e[5] = w[3];
   }
-  __threadfence_system();
+  __syncthreads();
+  const int n16 = (n_out * kCEntryWords) / 2;  // kCEntryWords is even: whole 16-byte words
+  for (int i = tid; i < n16; i += blockDim.x) st_relaxed_sys_b128(out + 2 + 2 * (size_t)i, stage[2 * i], stage[2 * i + 1]);
+  const long long tm3 = clock64();
   __syncthreads();
   if (tid == 0) {
-    __threadfence_system();
+    __threadfence_system();  // the entries (ordered before by the barrier) reach host memory before the header
     st_relaxed_sys_b128(out, (unsigned long long)(unsigned int)n_out | (have_cut ? (1ull << 31) : 0ull), (unsigned long long)seq);
+    p.counters[46] += tm2 - tm1;           // sort
+    p.counters[47] += clock64() - tm3;     // fence + header
+    p.counters[43] += tm3 - tm2;           // prefix + entries out
   }
 }
 
@@ -1965,7 +2041,7 @@ __global__ void __launch_bounds__(kThreads) k_record(const __grid_constant__ Act
   __shared__ double sh_d[(kThreads / 32) * 8];
   __shared__ int sh_i[(kThreads / 32) * 4];
   __shared__ int is_last;
-  const bool answers = scanner_main<true>(p, &rec, nullptr, sh_warp, sh_d, sh_i, scan_sh, tile);
+  const bool answers = scanner_main<true>(p, &rec, smem, sh_warp, sh_d, sh_i, scan_sh, tile);
   if (!answers) return;
   // ---- the last CTA to finish reduces the answers of all scanners and writes the result to host memory ----
   __threadfence();
@@ -1977,8 +2053,14 @@ __global__ void __launch_bounds__(kThreads) k_record(const __grid_constant__ Act
   if (threadIdx.x == 0) *p.ticket = 0;  // the next launch follows in stream order
   const int kind = scan_sh.kind;
   const unsigned int seq = rec.seq;
-  if (kind == DK_TOPK || (kind == DK_SCAN && p.topm && !(scan_sh.xbits & XB_SINGLE)))
+  if (kind == DK_TOPK || (kind == DK_SCAN && p.topm && !(scan_sh.xbits & XB_SINGLE))) {
+    const long long t0 = clock64();
     merge_lists(p, seq, kind == DK_SCAN, (MergeKey *)smem, sh_warp, sh_i);
+    if (threadIdx.x == 0) {
+      p.counters[44] += clock64() - t0;  // cycles the last CTA spent merging (profile)
+      p.counters[45] += 1;
+    }
+  }
   else if (threadIdx.x < 32)
     relay_reduce(p, kind, seq);
 }

@@ -108,6 +108,9 @@ struct DevSnap {
 // Cached comparator inputs of one queue node (plugins/proportion/queue_order/queue_order.go:19-73)
 struct QKey {
   double drf_job, drf;
+  // the first four criteria of queue_order.go:19-73 packed so that an ascending integer compare orders them as the
+  // comparator does: over fair share (bit 44) | not starved (43) | inverted priority (42..10) | limit violation (9)
+  unsigned long long w0;
   int priority;
   unsigned char over, starved, viol, valid;
 };
@@ -173,6 +176,7 @@ struct ActionParams {
   unsigned int *ticket;        // CTAs that finished the current launch (the last one reduces the answers)
   double *mm_result;           // [4] gpu mn, gpu mx, cpu mn, cpu mx of the last MINMAX launch (read by XB_FUSED_MM sweeps)
   unsigned long long *h_clist; // this GPU's merged candidate list [2][kCListWords] in (shared) host memory
+  int fused_in_kernel;         // XB_FUSED_MM sweeps exchange their extremes inside the launch (cooperative launch: all CTAs resident)
 };
 
 constexpr int kMergeCap = 2048;                      // candidates the last CTA of a launch can merge (scanners x kTopM)

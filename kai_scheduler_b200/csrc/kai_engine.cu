@@ -125,7 +125,7 @@ struct kai_engine {
   // launch transport (default): one k_record launch per decision record, node tiles resident in global memory
   DeviceArena dlaunch;
   int lgrid = 0, lnpc = 0;  // scanners (= CTAs of k_record) and rows per scanner
-  size_t ltile_stride = 0;
+  size_t ltile_stride = 0, ltile_bytes = 0, lsmem_bytes = 0;
   unsigned char *g_tiles = nullptr, *g_scan_state = nullptr;
   unsigned long long *d_list = nullptr;
   unsigned int *ticket = nullptr;
@@ -700,7 +700,13 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     lnpc = (lnpc + 1) & ~1;
     e->lgrid = lg;
     e->lnpc = lnpc;
-    e->ltile_stride = align_up((size_t)lnpc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4 + (size_t)4 * n_dom_levels), 256);
+    e->ltile_bytes = align_up((size_t)lnpc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4 + (size_t)4 * n_dom_levels), 16);
+    e->ltile_stride = align_up(e->ltile_bytes, 256);
+    // dynamic shared memory of k_record: the staged tile during the sweep, the merge keys of the last CTA afterwards
+    size_t n_pow = 1;
+    while ((int)n_pow < lg * kTopM) n_pow <<= 1;
+    const size_t merge_bytes = sizeof(MergeKey) * n_pow + (size_t)lg * kTopM * kCEntryWords * 8;  // sort keys + staged entries
+    e->lsmem_bytes = std::max(merge_bytes, std::min(e->ltile_bytes, (size_t)e->max_smem_optin - 40 * 1024));
     const size_t list_words = (size_t)2 * kListScanners * kListLines * kListLineWords;
     CK(e->dlaunch.reserve((size_t)lg * e->ltile_stride + (size_t)lg * align_up(kScanStateBytes, 256) + list_words * 8 + 4096));
     e->g_tiles = e->dlaunch.take<unsigned char>((size_t)lg * e->ltile_stride);
@@ -867,8 +873,14 @@ static bool engine_launch_record(void *ctx, const LaunchRec &rec) {
   kai_engine *e = (kai_engine *)ctx;
   const int kind = (int)(rec.dw[0] & 0xff);
   const unsigned int xbits = (unsigned int)((rec.dw[0] >> 48) & 0xffff);
-  const size_t dyn = sizeof(MergeKey) * (size_t)kMergeCap;
-  if (kind == DK_SCAN && (xbits & XB_FUSED_MM)) {
+  const size_t dyn = e->lsmem_bytes;
+  if (kind == DK_SCAN && (xbits & XB_FUSED_MM) && e->lp.fused_in_kernel) {
+    // every CTA is resident (checked at load): the scanners exchange their binpack extremes among themselves
+    // through tagged device slots inside this one launch
+    void *args[] = {(void *)&e->lp, (void *)&rec};
+    cudaLaunchCooperativeKernel((const void *)k_record, dim3(e->lgrid), dim3(kThreads), args, dyn, e->stream);
+    e->record_launches++;
+  } else if (kind == DK_SCAN && (xbits & XB_FUSED_MM)) {
     // pack.go:66-86 over the row set of this sweep: a MINMAX launch (applies the deltas and the feasible-set snapshot,
     // leaves the reduced extremes in device memory) followed by the sweep itself, back to back on the stream
     LaunchRec a = rec;
@@ -963,6 +975,14 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       p.mm_result = e->mm_result;
       p.h_clist = e->cfg.shard_count > 1 ? e->shm_dev + shm_clist_offset_words() + (size_t)e->cfg.shard_rank * 2 * kCListWords : e->h_clist;
       p.spin_log2 = 22;
+      p.tile_bytes = e->ltile_bytes;
+      p.hot_in_smem = e->ltile_bytes <= e->lsmem_bytes ? 1 : 0;  // the scanners stage their tile in shared memory for a sweep
+      {
+        int per_sm = 0;
+        CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lsmem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_record, kThreads, e->lsmem_bytes));
+        p.fused_in_kernel = (per_sm * e->num_sms >= e->lgrid && !getenv("KAI_NO_FUSED_LAUNCH")) ? 1 : 0;
+      }
     }
   }
   void *args[] = {(void *)&p};
@@ -988,11 +1008,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     }
     cudaEventRecord(e->ev_mirror, e->stream);
     if (launch_mode) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MergeKey) * kMergeCap)));
-        attr_set = true;
-      }
+      CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lsmem_bytes));
       e->lp = p;
       e->record_launches = 0;
       LaunchRec load;
@@ -1038,6 +1054,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.list_invalidate();
     hb.batching = p.batching;
     hb.failed = false;
+    hb.gang_fast = getenv("KAI_NO_GANG_FAST") == nullptr;
+    hb.gang_bulk = hb.gang_replayed = hb.gang_failed = 0;
     hb.rank_to_node = e->rank_to_node_h.data();
     CK(cudaEventSynchronize(e->ev_mirror));
     if (refresh_mirror && !e->h_tmp.empty()) {  // re-read tables -> node-major mirror
@@ -1214,7 +1232,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       long long cd[48];
       CK(cudaMemcpy(cd, e->counters, sizeof(cd), cudaMemcpyDeviceToHost));
       for (int i = 20; i < 28; i++) c[i] = cd[i];
-      for (int i = 32; i < 44; i++) c[i] = cd[i];
+      for (int i = 32; i < 48; i++) c[i] = cd[i];
     }
     c[0] = seq.n_visits;
     c[1] = seq.sweeps;
@@ -1268,12 +1286,16 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
               launch_mode ? "launch" : "persistent", launch_mode ? e->record_launches : 0LL, e->hb.t_total * 1e3, e->hb.t_exchange * 1e3,
               c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
     if (host_mode) fprintf(stderr, "[kai] sweeps answered with a single row (XB_SINGLE): %lld; FLUSH records %lld\n", e->hb.single_sweeps, e->hb.n_flush);
+    if (host_mode) fprintf(stderr, "[kai] fresh gangs: %lld committed in bulk, %lld replayed per task, %lld discarded\n", e->hb.gang_bulk, e->hb.gang_replayed, e->hb.gang_failed);
     if (host_mode && e->hb.n_topo_jobs)
       fprintf(stderr, "[kai] topology: %lld constrained jobs with candidates, %lld domains tried; subSetNodesFn %.1f ms, score table %.1f ms, placing %.1f ms\n",
               e->hb.n_topo_jobs, e->hb.n_topo_domains, e->hb.t_topo[0] * 1e3, e->hb.t_topo[1] * 1e3, e->hb.t_topo[2] * 1e3);
     if (host_mode)
       fprintf(stderr, "[kai] host sequencer rdtsc Mcycles: pop %.2f admit %.2f place(+sweeps) %.2f finish %.2f loop %.2f\n",
               e->hb.t_sec[0] / 1e6, e->hb.t_sec[1] / 1e6, e->hb.t_sec[2] / 1e6, e->hb.t_sec[3] / 1e6, e->hb.t_sec[4] / 1e6);
+    if (host_mode && c[45] > 0)
+      fprintf(stderr, "[kai] last-CTA list merge: %lld cycles per list (%lld lists): sort %lld, prefix + entries out %lld, fences + header %lld\n",
+              c[44] / c[45], c[45], c[46] / c[45], c[43] / c[45], c[47] / c[45]);
     if (host_mode && c[22] > 0)
       fprintf(stderr, "[kai] relay CTA per record: forward %lld cycles, scanners+reduce %lld cycles (%lld records)\n",
               c[20] / c[22], c[21] / c[22], c[22]);
@@ -1305,6 +1327,79 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   if (c[6] == 2) return e->fail(KAI_ERR_UNSUPPORTED, "topology: more preferred-level domains than the score table holds (kDomBuckets)");
   if (c[6] != 0) return e->fail(KAI_ERR_CUDA, "device sequencer overflow (statement log)");
   return download(e, out, c[0], c[3], c[4]);
+}
+
+int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, int64_t *rows_per_launch) {
+  if (!e || !elapsed_ms || !rows_per_launch || n_launches < 1) return KAI_ERR_INVALID;
+  if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
+  CK(cudaSetDevice(e->device));
+  ActionParams p;
+  memset(&p, 0, sizeof(p));
+  p.s = e->ds;
+  p.cfg = e->cfg;
+  p.action = KAI_ACTION_ALLOCATE;
+  p.grid = e->lgrid + 1;
+  p.nodes_per_cta = e->lnpc;
+  p.xbuf = e->xbuf;
+  p.mmbuf = e->mmbuf;
+  p.counters = e->counters;
+  p.node_domain = e->d_node_domain;
+  p.n_dom_levels = e->n_dom_levels;
+  p.mode = 2;
+  p.spin_log2 = 22;
+  p.topm = 1;
+  p.batching = 1;
+  p.h_list = e->d_list;
+  p.g_tiles = e->g_tiles;
+  p.g_tile_stride = e->ltile_stride;
+  p.g_scan_state = e->g_scan_state;
+  p.ticket = e->ticket;
+  p.mm_result = e->mm_result;
+  p.h_slot = e->h_slots;
+  p.h_mmslot = e->h_mm;
+  p.h_clist = e->h_clist;
+  CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lsmem_bytes));
+  p.tile_bytes = e->ltile_bytes;
+  p.hot_in_smem = e->ltile_bytes <= e->lsmem_bytes ? 1 : 0;
+  e->lp = p;
+  LaunchRec rec;
+  memset(&rec, 0, sizeof(rec));
+  rec.dw[0] = (unsigned long long)DK_LOAD;
+  rec.seq = e->seq;
+  if (!engine_launch_record(e, rec)) return e->cuda_fail(cudaGetLastError(), "k_record (tile load)");
+  // one list sweep: the benchmark pod (jobs_fake/jobs.go:261-291), binpack on the GPU column with the extremes of an
+  // empty-to-full cluster; no deltas, so every launch reads the same rows
+  Ctl c;
+  memset(&c, 0, sizeof(c));
+  c.dec.req[KAI_RES_CPU] = 1000.0;
+  c.dec.req[KAI_RES_MEM] = 1e9;
+  c.dec.req[KAI_RES_GPU] = 1.0;
+  if (e->R > 3) c.dec.req[3] = 1.0;
+  c.dec.gpu_task = 1;
+  c.dec.res = KAI_RES_GPU;
+  c.dec.strategy = e->cfg.gpu_placement;
+  c.dec.nominated = c.dec.pred_class = -1;
+  c.trk[0].mn = 0.0;
+  c.trk[0].mx = 8.0;
+  c.trk[0].cnt_mn = c.trk[0].cnt_mx = 1;
+  c.trk[1].dirty = 1;
+  build_decision_words(c, DK_SCAN, 1);
+  for (int i = 0; i < kDecWords; i++) rec.dw[i] = c.dw[i];
+  rec.n_delta = 0;
+  cudaEventRecord(e->ev[0], e->stream);
+  for (int i = 0; i < n_launches; i++) {
+    rec.seq = e->seq + 1 + (unsigned int)i;
+    if (!engine_launch_record(e, rec)) return e->cuda_fail(cudaGetLastError(), "k_record");
+  }
+  cudaEventRecord(e->ev[1], e->stream);
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+  *elapsed_ms = ms;
+  const int n_shard_rows = e->N > e->cfg.shard_rank ? (e->N - e->cfg.shard_rank + e->cfg.shard_count - 1) / e->cfg.shard_count : 0;
+  *rows_per_launch = n_shard_rows;
+  e->seq += (unsigned int)n_launches + 4;
+  return KAI_OK;
 }
 
 int kai_engine_stats(kai_engine *e, kai_stats *out) {

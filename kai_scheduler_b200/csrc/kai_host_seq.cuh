@@ -319,6 +319,121 @@ struct HostBackend {
     list.clear();
     ctl.batch.valid = 0;
   }
+  // ---- fresh gangs: deferred bookkeeping ----
+  // A gang whose tasks are untouched and interchangeable (JobRec::pad[0]) is placed task by task like any other job —
+  // same sweeps, lists, capacity checks, node deltas and queue shares, in the same order — but the per-task writes of
+  // Statement.Allocate / Pipeline that nothing reads before the gang is complete (task status / node / statement log,
+  // PodSet counters) are made once at the end: in bulk when every task went to Idle resources (the job is committed
+  // as it stands: statement.go:536-571), otherwise replayed in placement order so that the usual finish
+  // (ShouldPipelineJob, ConvertAllAllocatedToPipelined, Commit) sees exactly the state the per-task path leaves.
+  bool gang_mode = false, gang_fast = true;
+  int gang_n = 0;
+  std::vector<int> gang_node;
+  std::vector<unsigned char> gang_idle;
+  long long gang_bulk = 0, gang_replayed = 0, gang_failed = 0;
+  void place(int t, int node, bool to_idle) {
+    if (gang_mode) {
+      gang_node[gang_n] = node;
+      gang_idle[gang_n] = to_idle ? 1 : 0;
+      gang_n++;
+      emit_delta(seq, node, to_idle ? ND_ADD : ND_ADD_PIPELINED, t);  // node_info.go:457-493
+      queue_allocate(seq, t, true, ctl.ctx_job);                      // proportion.go:443-466
+      return;
+    }
+    if (to_idle)
+      stmt_allocate(seq, t, node, ctl.ctx_fresh != 0);
+    else
+      stmt_pipeline(seq, t, node, ctl.ctx_fresh != 0);
+  }
+  bool place_fresh_gang(int job, int n, int base) {
+    if ((int)gang_node.size() < n) {
+      gang_node.resize(n);
+      gang_idle.resize(n);
+    }
+    gang_n = 0;
+    gang_mode = true;
+    const bool ok = place_tasks(job, n);
+    gang_mode = false;
+    const DevSnap &s = *seq.s;
+    if (!ok) {  // Discard (statement.go:522-534): undo in reverse order; the tasks' own fields were never written
+      for (int k = gang_n - 1; k >= 0; k--) {
+        emit_delta(seq, gang_node[k], gang_idle[k] ? ND_REM : ND_REM_PIPELINED, base + k);
+        queue_allocate(seq, base + k, false, job);
+      }
+      if (gang_n > 0) {
+        node_state_disturbed(seq);
+        seq.rp.touched[job >> 5] |= 1u << (job & 31);
+        seq.rp.j_req_valid[job] = 0;
+        invalidate_chain(seq, ctl.ctx_queue);
+      }
+      gang_failed++;
+      return false;
+    }
+    bool all_idle = gang_n == n;
+    for (int k = 0; k < gang_n; k++) all_idle = all_idle && gang_idle[k];
+    if (all_idle) {  // Allocate x n then Commit: Binding on the chosen nodes
+      for (int k = 0; k < n; k++) {
+        const int t = base + k;
+        seq.rp.t_status[t] = KAI_POD_BINDING;
+        seq.rp.t_node[t] = gang_node[k];
+        seq.rp.t_node_status[t] = KAI_POD_BINDING;
+        seq.rp.t_virtual[t] = 1;
+      }
+      ctl.ctx_cnt[0] += n;  // active allocated
+      ctl.ctx_cnt[1] -= n;  // pending
+      seq.rp.touched[job >> 5] |= 1u << (job & 31);
+      seq.rp.j_req_valid[job] = 0;
+      invalidate_chain(seq, ctl.ctx_queue);
+      seq.pods_placed += n;
+      gang_bulk++;
+      return true;
+    }
+    for (int k = 0; k < gang_n; k++) {  // replay what stmt_place writes besides the node delta and the queue shares
+      const int t = base + k;
+      Op op;
+      op.kind = gang_idle[k] ? OP_ALLOCATE : OP_PIPELINE;
+      op.task = t;
+      op.prev_status = KAI_POD_PENDING;
+      op.prev_node = -1;
+      op.prev_virtual = 0;
+      op.next_node = gang_node[k];
+      op.undo_index = -1;
+      op.pad = 0;
+      const int st = gang_idle[k] ? KAI_POD_ALLOCATED : KAI_POD_PIPELINED;
+      set_status(seq, t, st, job, KAI_POD_PENDING);
+      seq.rp.t_node[t] = gang_node[k];
+      seq.rp.t_node_status[t] = st;
+      push_op(seq, op);
+      seq.rp.t_virtual[t] = 1;
+    }
+    (void)s;
+    gang_replayed++;
+    return true;
+  }
+  // seq_apply_winner / seq_apply_batched (kai_seq.cuh) with the placement routed through place()
+  void apply_winner_host(int t) {
+    seq.sweeps++;
+    seq.nodes_scanned += seq.s->N;
+    if (ctl.win.node < 0) {
+      ctl.item_ok = 0;
+      return;
+    }
+    place(t, ctl.win.node, (ctl.win.flags & SLOT_TO_IDLE) != 0);
+    ctl.item_ok = 1;
+  }
+  void apply_batched_host(int t) {
+    Batch &b = ctl.batch;
+    uint32_t f6 = (uint32_t)((b.fl >> (6 * b.idx)) & 0x3fu);
+    for (int k = 0; k < 2; k++) {
+      uint32_t f = (f6 >> (3 * k)) & 7u;
+      if (f) track_decrease(ctl.trk[k], f, 0.0);
+    }
+    b.idx++;
+    b.left--;
+    place(t, b.node, b.to_idle != 0);
+    seq.batched++;
+    ctl.item_ok = 1;
+  }
   // Place task t on the current list candidate (pack.go / node_info.go arithmetic restated on the reported row
   // values), update the min/max trackers exactly and decide whether the list stays usable.
   bool apply_listed(int t) {
@@ -357,10 +472,7 @@ struct HostBackend {
       if (scored && d.strategy == KAI_PLACEMENT_BINPACK && (tr.dirty || tr.mn != before.mn || tr.mx != before.mx))
         scored_moved = true;
     }
-    if (to_idle)
-      stmt_allocate(seq, t, lc.node, ctl.ctx_fresh != 0);
-    else
-      stmt_pipeline(seq, t, lc.node, ctl.ctx_fresh != 0);
+    place(t, lc.node, to_idle);
     lc.used++;
     listed++;
     list_served++;
@@ -475,7 +587,7 @@ struct HostBackend {
             break;
           }
         } else {
-          seq_apply_batched(seq, t);
+          apply_batched_host(t);
           continue;
         }
       }
@@ -516,7 +628,7 @@ struct HostBackend {
         ctl.item_ok = 0;
         if (list_available()) apply_listed(t);
       } else {
-        seq_apply_winner(seq, t);
+        apply_winner_host(t);
       }
       if (!ctl.item_ok) {
         job_success = false;
@@ -643,7 +755,10 @@ struct HostBackend {
         job_success = allocate_constrained(*topo, job, tta);
       } else if (job_success) {
         if (topo) topo->scores_off(seq);  // no NodeOrderFn term from the previous job's topology scores
-        job_success = place_tasks(job, n);
+        if (gang_fast && ctl.ctx_fresh && rec.pad[0] && n == rec.n_tta)
+          job_success = place_fresh_gang(job, n, rec.tb);
+        else
+          job_success = place_tasks(job, n);
       }
       lap(2);
       if (job_success) {

@@ -735,6 +735,8 @@ KAI_HD const QKey &queue_key(Seq &q, int qi) {
   k.drf_job = dj;
   k.drf = dr;
   k.priority = kldg(&s.q_priority[qi]);
+  k.w0 = ((unsigned long long)(over ? 1 : 0) << 44) | ((unsigned long long)(starved ? 0 : 1) << 43) |
+         (((unsigned long long)(0x80000000LL - (long long)k.priority) & 0x1ffffffffull) << 10) | ((unsigned long long)(viol ? 1 : 0) << 9);
   k.valid = 1;
   q.t_key += kclock() - tkk;
   return k;
@@ -742,20 +744,16 @@ KAI_HD const QKey &queue_key(Seq &q, int qi) {
 KAI_HD bool node_less(Seq &q, int l, int r) {  // :256-278 buildNodeOrderFn (pending order)
   if (qn_len(q, l) == 0) return true;
   if (qn_len(q, r) == 0) return false;
-  const QKey kl = queue_key(q, l);
-  const QKey kr = queue_key(q, r);
-  if (!kl.over && kr.over) return true;
-  if (kl.over && !kr.over) return false;
-  if (kl.starved && !kr.starved) return true;
-  if (kr.starved && !kl.starved) return false;
-  if (kl.priority > kr.priority) return true;
-  if (kl.priority < kr.priority) return false;
-  if (kl.viol && !kr.viol) return false;
-  if (!kl.viol && kr.viol) return true;
-  if (kl.drf_job < kr.drf_job) return true;
-  if (kl.drf_job > kr.drf_job) return false;
-  if (kl.drf < kr.drf) return true;
-  if (kl.drf > kr.drf) return false;
+  // over fair share last, starved first, higher priority first, limit violations last (packed: QKey::w0), then the
+  // dominant shares with and without the best pending job
+  const unsigned long long wl = queue_key(q, l).w0;
+  const double jl = q.rp.qkey[l].drf_job, dl = q.rp.qkey[l].drf;
+  const QKey &kr = queue_key(q, r);  // (a recomputation writes only the entry of r)
+  if (wl != kr.w0) return wl < kr.w0;
+  if (jl < kr.drf_job) return true;
+  if (jl > kr.drf_job) return false;
+  if (dl < kr.drf) return true;
+  if (dl > kr.drf) return false;
   const DevSnap &s = *q.s;
   bool l_le_r = true, r_le_l = true;  // :221-233
   for (int i = 0; i < QR; i++) {

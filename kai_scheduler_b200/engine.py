@@ -103,6 +103,15 @@ class Engine:
         self._check(self._lib.kai_engine_stats(self._h, C.byref(s)))
         return s
 
+    def time_sweeps(self, n_launches: int = 200):
+        """(milliseconds per launch, node rows per launch) of the sweep kernel, back-to-back launches, CUDA events."""
+        ms, rows = C.c_double(), C.c_int64()
+        fn = self._lib.kai_engine_time_sweeps
+        fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        fn.restype = C.c_int
+        self._check(fn(self._h, n_launches, C.byref(ms), C.byref(rows)))
+        return ms.value / n_launches, rows.value
+
     def export_peer_handle(self) -> bytes:
         buf = (C.c_uint8 * abi.PEER_HANDLE_BYTES)()
         self._check(self._lib.kai_engine_export_peer_handle(self._h, buf))
