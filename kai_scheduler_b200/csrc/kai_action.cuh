@@ -1890,146 +1890,153 @@ __global__ void __launch_bounds__(kThreads, 1) k_action(const __grid_constant__ 
 // fitting rows than they reported — the rule HostBackend::gather_list applies), and write the usable prefix as
 // 48-byte entries {score, meta, Ig, Lg, Ic, Lc} + one header word to host memory: the host reads one contiguous list
 // instead of scanners x (1 + M) cache lines.
-struct MergeKey {  // 16 bytes of shared memory per candidate (two u64 planes: kh = score key, kl = rank | source)
-  unsigned long long h, l;
-};
-// Integer sort keys: kh = ~bits(score) (scores are sums of non-negative terms, so ascending kh is descending score),
-// kl = rank << 32 | source (scanner * kTopM + m); an empty slot is all ones in both and sorts last.
-__device__ void merge_lists(const ActionParams &p, unsigned int seq, bool with_payload, MergeKey *keymem, Cand *sh_warp,
-                            int *sh_i) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+// Integer sort keys of a candidate: h = ~bits(score) (scores are sums of non-negative terms, so ascending h is descending
+// score), l = rank << 32 | source (scanner * kTopM + m); an empty slot is all ones in both and sorts last.
+constexpr int kMergeThreads = 1024;  // one candidate per thread: scanners x kTopM <= 1024
+constexpr size_t kMergeSmemBytes = (size_t)kMergeThreads * 8 * (2 + kCEntryWords);
+__device__ __forceinline__ bool mk_before(unsigned long long ah, unsigned long long al, unsigned long long bh, unsigned long long bl) {
+  return ah < bh || (ah == bh && al < bl);
+}
+// Merge kernel of the launch transport (one CTA, launched right after a list sweep on the same stream): sorts the
+// scanners' top-M candidates by (score desc, name rank asc) — bitonic network, partner exchange by warp shuffle below
+// 32 lanes and through shared memory above —, cuts the list where an unseen row could be better (the best "last
+// reported key" among scanners that have more fitting rows than they reported: the rule HostBackend::gather_list
+// applies) and streams the usable prefix as 48-byte entries {score, meta, Ig, Lg, Ic, Lc} + one header word to host
+// memory: the host reads one contiguous list instead of scanners x (1 + M) cache lines.
+__global__ void __launch_bounds__(kMergeThreads, 1) k_merge(const __grid_constant__ ActionParams p, unsigned int seq, int with_payload) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];  // kMergeSmemBytes: exchange planes + staged entries
+  unsigned long long *xh = (unsigned long long *)dyn_smem, *xl = xh + kMergeThreads, *stage = xl + kMergeThreads;
+  __shared__ unsigned long long cut_h[kMergeThreads / 32];
+  __shared__ unsigned int cut_r[kMergeThreads / 32];
+  __shared__ int n_ok[kMergeThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_scan = p.grid - 1;
   const int n_c = n_scan * kTopM;
-  int n_pow = 1;
-  while (n_pow < n_c) n_pow <<= 1;
-  unsigned long long *kh = (unsigned long long *)keymem, *kl = kh + n_pow;
   const unsigned long long *base = p.h_list + (size_t)(seq & 1) * kListScanners * kListLines * kListLineWords;
-  // ---- candidates + the cut ----
-  Cand cut;
-  cut.score = -1.0;
-  cut.rank = kRankNone;
-  cut.ln = 0;
-  for (int c = tid; c < n_scan; c += blockDim.x) {
+  const long long t0 = clock64();
+  // ---- my candidate; the cut key of my scanner (lanes 4c .. 4c+3 hold scanner c) ----
+  unsigned long long h = ~0ull, l = ~0ull;
+  bool more = false;
+  if (tid < n_c) {
+    const int c = tid / kTopM, m = tid % kTopM;
     const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
-    bool more = false;
-    double last_score = 0;
-    uint32_t last_rank = kRankNone;
-    unsigned long long lo[kTopM], hi[kTopM];
-#pragma unroll
-    for (int m = 0; m < kTopM; m++) ld_relaxed_b128(lines + 2 * m, lo[m], hi[m]);
-#pragma unroll
-    for (int m = 0; m < kTopM; m++) {
-      const uint32_t rank = (uint32_t)(hi[m] & 0xffffffu);
-      if (((uint32_t)(hi[m] >> 32) & 0xffu) & LF_MORE) more = true;
-      if (rank != kRankNone) {
-        last_score = __longlong_as_double((long long)lo[m]);
-        last_rank = rank;
-        kh[c * kTopM + m] = ~lo[m];
-        kl[c * kTopM + m] = ((unsigned long long)rank << 32) | (unsigned long long)(c * kTopM + m);
-      } else {
-        kh[c * kTopM + m] = ~0ull;
-        kl[c * kTopM + m] = ~0ull;
-      }
-    }
-    if (more && last_rank != kRankNone && better(last_score, last_rank, cut.score, cut.rank)) {
-      cut.score = last_score;
-      cut.rank = last_rank;
+    const uint4 v = __ldcg((const uint4 *)(lines + 2 * m));  // written by the previous launch: plain (overlappable) loads
+    const unsigned long long lo = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+    const unsigned long long hi = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+    const uint32_t rank = (uint32_t)(hi & 0xffffffu);
+    more = (((uint32_t)(hi >> 32) & 0xffu) & LF_MORE) != 0;
+    if (rank != kRankNone) {
+      h = ~lo;
+      l = ((unsigned long long)rank << 32) | (unsigned long long)tid;
     }
   }
-  for (int i = n_c + tid; i < n_pow; i += blockDim.x) {
-    kh[i] = ~0ull;
-    kl[i] = ~0ull;
+  // cut candidate of a scanner: its last reported key when it has more rows; the best of those over all scanners
+  static_assert(kTopM == 4, "the group reductions below assume 4 candidates per scanner");
+  const unsigned int grp = 0xfu << (lane & ~3);
+  const bool any_more = (__ballot_sync(0xffffffffu, more) & grp) != 0;
+  const unsigned int real = __ballot_sync(0xffffffffu, l != ~0ull) & grp;
+  unsigned long long ch = ~0ull;  // candidate cut key held by the lane of the group's last real entry
+  unsigned int cr = kRankNone;
+  if (any_more && real && lane == 31 - __clz((int)real)) {
+    ch = h;
+    cr = (unsigned int)(l >> 32);
   }
   for (int o = 16; o > 0; o >>= 1) {
-    double os = __shfl_xor_sync(0xffffffffu, cut.score, o);
-    uint32_t orank = __shfl_xor_sync(0xffffffffu, cut.rank, o);
-    if (better(os, orank, cut.score, cut.rank)) {
-      cut.score = os;
-      cut.rank = orank;
+    const unsigned long long oh = __shfl_xor_sync(0xffffffffu, ch, o);
+    const unsigned int orr = __shfl_xor_sync(0xffffffffu, cr, o);
+    if (orr != kRankNone && (cr == kRankNone || oh < ch || (oh == ch && orr < cr))) {
+      ch = oh;
+      cr = orr;
     }
   }
-  if (lane == 0) sh_warp[warp] = cut;
-  __syncthreads();
-  cut = sh_warp[0];
-  for (int w = 1; w < nw; w++)
-    if (better(sh_warp[w].score, sh_warp[w].rank, cut.score, cut.rank)) cut = sh_warp[w];
-  const bool have_cut = cut.rank != kRankNone;
-  const long long tm1 = clock64();
-  // ---- bitonic sort, best key first: one compare-exchange per thread and step on pairs (i, i | j) ----
-  const int half = n_pow >> 1;
-  for (int k = 2; k <= n_pow; k <<= 1)
+  if (lane == 0) {
+    cut_h[warp] = ch;
+    cut_r[warp] = cr;
+  }
+  const long long t1 = clock64();
+  // ---- bitonic sort, one element per thread ----
+  for (int k = 2; k <= kMergeThreads; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 4
-      for (int t = tid; t < half; t += blockDim.x) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int l = i | j;
-        const unsigned long long ah = kh[i], al = kl[i], bh = kh[l], bl = kl[l];
-        const bool a_first = ah < bh || (ah == bh && al < bl);
-        const bool b_first = bh < ah || (bh == ah && bl < al);
-        const bool up = (i & k) == 0;
-        if (up ? b_first : a_first) {
-          kh[i] = bh;
-          kl[i] = bl;
-          kh[l] = ah;
-          kl[l] = al;
-        }
+      unsigned long long oh, ol;
+      if (j < 32) {
+        oh = __shfl_xor_sync(0xffffffffu, h, j);
+        ol = __shfl_xor_sync(0xffffffffu, l, j);
+      } else {
+        xh[tid] = h;
+        xl[tid] = l;
+        __syncthreads();
+        oh = xh[tid ^ j];
+        ol = xl[tid ^ j];
+        __syncthreads();
       }
-      __syncthreads();
+      const bool lower = (tid & j) == 0;        // I keep the earlier key of the pair when the run ascends
+      const bool up = (tid & k) == 0;
+      const bool other_first = mk_before(oh, ol, h, l);
+      const bool take = (lower == up) ? other_first : mk_before(h, l, oh, ol);
+      if (take) {
+        h = oh;
+        l = ol;
+      }
     }
-  const long long tm2 = clock64();
-  // ---- usable prefix: real entries that are not worse than the cut ----
-  int first_bad = n_c;
-  for (int i = tid; i < n_c; i += blockDim.x) {
-    const unsigned long long h = kh[i], l = kl[i];
-    bool ok = l != ~0ull;
-    const double score = __longlong_as_double((long long)~h);
-    const uint32_t rank = (uint32_t)(l >> 32);
-    if (ok && have_cut && !(score > cut.score || (score == cut.score && rank <= cut.rank))) ok = false;
-    if (!ok && i < first_bad) first_bad = i;
-  }
-  for (int o = 16; o > 0; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
-  if (lane == 0) sh_i[warp] = first_bad;
   __syncthreads();
-  first_bad = sh_i[0];
-  for (int w = 1; w < nw; w++) first_bad = min(first_bad, sh_i[w]);
-  const int n_out = first_bad;
+  const long long t2 = clock64();
+  unsigned long long gh = ~0ull;
+  unsigned int gr = kRankNone;
+  for (int w = 0; w < kMergeThreads / 32; w++) {
+    const unsigned long long oh = cut_h[w];
+    const unsigned int orr = cut_r[w];
+    if (orr != kRankNone && (gr == kRankNone || oh < gh || (oh == gh && orr < gr))) {
+      gh = oh;
+      gr = orr;
+    }
+  }
+  const bool have_cut = gr != kRankNone;
+  // ---- usable prefix: real entries that are not worse than the cut (sorted: they form a prefix) ----
+  const unsigned int my_rank = (unsigned int)(l >> 32);
+  const bool ok = l != ~0ull && (!have_cut || h < gh || (h == gh && my_rank <= gr));
+  const unsigned int okb = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) n_ok[warp] = __popc(okb);
+  __syncthreads();
+  int n_out = 0;
+  for (int w = 0; w < kMergeThreads / 32; w++) n_out += n_ok[w];
   unsigned long long *out = p.h_clist + (size_t)(seq & 1) * kCListWords;
-  // entries are assembled in shared memory (behind the keys) and leave as one linear stream of 16-byte stores:
-  // consecutive threads write consecutive addresses, so the writes cross PCIe as full-size packets
-  unsigned long long *stage = kl + n_pow;
-  for (int i = tid; i < n_out; i += blockDim.x) {
-    const int src = (int)(kl[i] & 0xffffffffu);
+  if (tid < n_out) {
+    const int src = (int)(l & 0xffffffffu);
     const int c = src / kTopM, m = src % kTopM;
     const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
-    unsigned long long lo, hi, w[4] = {0, 0, 0, 0};
-    ld_relaxed_b128(lines + 2 * m, lo, hi);
+    const uint4 v = __ldcg((const uint4 *)(lines + 2 * m));
+    uint4 pw[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) pw[q] = make_uint4(0, 0, 0, 0);
     if (with_payload) {
       const unsigned long long *pl = lines + (size_t)(1 + m) * kListLineWords;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        unsigned long long phi;
-        ld_relaxed_b128(pl + 2 * q, w[q], phi);
-      }
+      for (int q = 0; q < 4; q++) pw[q] = __ldcg((const uint4 *)(pl + 2 * q));
     }
-    unsigned long long *e = stage + (size_t)i * kCEntryWords;
-    e[0] = lo;
-    e[1] = hi;
-    e[2] = w[0];
-    e[3] = w[1];
-    e[4] = w[2];
-    e[5] = w[3];
+    unsigned long long *e = stage + (size_t)tid * kCEntryWords;
+    e[0] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+    e[1] = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+#pragma unroll
+    for (int q = 0; q < 4; q++) e[2 + q] = (unsigned long long)pw[q].x | ((unsigned long long)pw[q].y << 32);
   }
   __syncthreads();
-  const int n16 = (n_out * kCEntryWords) / 2;  // kCEntryWords is even: whole 16-byte words
-  for (int i = tid; i < n16; i += blockDim.x) st_relaxed_sys_b128(out + 2 + 2 * (size_t)i, stage[2 * i], stage[2 * i + 1]);
-  const long long tm3 = clock64();
+  const long long t3 = clock64();
+  // one linear stream of 16-byte stores: consecutive threads write consecutive addresses (full-size PCIe packets)
+  const int n16 = (n_out * kCEntryWords) / 2;
+  for (int i = tid; i < n16; i += kMergeThreads) st_relaxed_sys_b128(out + 2 + 2 * (size_t)i, stage[2 * i], stage[2 * i + 1]);
   __syncthreads();
+  const long long t4 = clock64();
   if (tid == 0) {
     __threadfence_system();  // the entries (ordered before by the barrier) reach host memory before the header
     st_relaxed_sys_b128(out, (unsigned long long)(unsigned int)n_out | (have_cut ? (1ull << 31) : 0ull), (unsigned long long)seq);
-    p.counters[46] += tm2 - tm1;           // sort
-    p.counters[47] += clock64() - tm3;     // fence + header
-    p.counters[43] += tm3 - tm2;           // prefix + entries out
+    const long long t5 = clock64();
+    p.counters[44] += t5 - t0;
+    p.counters[45] += 1;
+    p.counters[46] += t2 - t1;  // sort
+    p.counters[47] += t4 - t3;  // stream to the host
+    p.counters[43] += t5 - t4;  // fence + header
+    p.counters[39] += t1 - t0;  // candidate loads + cut
+    p.counters[31] += t3 - t2;  // prefix + payload loads
   }
 }
 
@@ -2043,6 +2050,8 @@ __global__ void __launch_bounds__(kThreads) k_record(const __grid_constant__ Act
   __shared__ int is_last;
   const bool answers = scanner_main<true>(p, &rec, smem, sh_warp, sh_d, sh_i, scan_sh, tile);
   if (!answers) return;
+  // list answers (top-M lines in device memory) are merged by k_merge, the next launch on the stream
+  if (scan_sh.kind == DK_TOPK || (scan_sh.kind == DK_SCAN && p.topm && !(scan_sh.xbits & XB_SINGLE))) return;
   // ---- the last CTA to finish reduces the answers of all scanners and writes the result to host memory ----
   __threadfence();
   __syncthreads();
@@ -2052,17 +2061,7 @@ __global__ void __launch_bounds__(kThreads) k_record(const __grid_constant__ Act
   __threadfence();
   if (threadIdx.x == 0) *p.ticket = 0;  // the next launch follows in stream order
   const int kind = scan_sh.kind;
-  const unsigned int seq = rec.seq;
-  if (kind == DK_TOPK || (kind == DK_SCAN && p.topm && !(scan_sh.xbits & XB_SINGLE))) {
-    const long long t0 = clock64();
-    merge_lists(p, seq, kind == DK_SCAN, (MergeKey *)smem, sh_warp, sh_i);
-    if (threadIdx.x == 0) {
-      p.counters[44] += clock64() - t0;  // cycles the last CTA spent merging (profile)
-      p.counters[45] += 1;
-    }
-  }
-  else if (threadIdx.x < 32)
-    relay_reduce(p, kind, seq);
+  if (threadIdx.x < 32) relay_reduce(p, kind, rec.seq);
 }
 
 }  // namespace kai

@@ -179,7 +179,7 @@ struct ActionParams {
   int fused_in_kernel;         // XB_FUSED_MM sweeps exchange their extremes inside the launch (cooperative launch: all CTAs resident)
 };
 
-constexpr int kMergeCap = 2048;                      // candidates the last CTA of a launch can merge (scanners x kTopM)
+constexpr int kMergeCap = 1024;                      // candidates k_merge sorts, one per thread (scanners x kTopM)
 constexpr int kCEntryWords = 6;                      // score, meta, Ig, Lg, Ic, Lc
 constexpr int kCListWords = 2 + kMergeCap * kCEntryWords;  // header {count | more << 31, tag} + entries
 constexpr int kScanStateBytes = 16 + kDomBuckets;

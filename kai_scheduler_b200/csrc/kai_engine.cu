@@ -686,15 +686,15 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->visits_cap = std::max(16, 2 * J + T + 16);
   {  // launch transport: scanners = CTAs of k_record; the last CTA merges scanners x kTopM candidates (<= kMergeCap)
     int lg = 1;
-    while (lg * 2 <= std::min(2 * e->num_sms, kMergeCap / kTopM)) lg *= 2;  // 256 on B200: a power of two keeps the merge sort full
+    while (lg * 2 <= std::min(2 * e->num_sms, kMergeThreads / kTopM)) lg *= 2;  // 256 on B200: a power of two keeps the merge sort full
     if (const char *g = getenv("KAI_LAUNCH_GRID")) {
       int v = atoi(g);
-      if (v >= 1) lg = std::min(v, kMergeCap / kTopM);
+      if (v >= 1) lg = std::min(v, kMergeThreads / kTopM);
     }
     if (N > 0) lg = std::min(lg, std::max(1, n_shard_rows));
     if (const char *g = getenv("KAI_GRID_EXACT")) {  // tests: the same forced geometries as the persistent kernel (grid - 1 scanners)
       int v = atoi(g);
-      if (v >= 2) lg = std::min(v - 1, kMergeCap / kTopM);
+      if (v >= 2) lg = std::min(v - 1, kMergeThreads / kTopM);
     }
     int lnpc = std::max(1, (n_shard_rows + lg - 1) / lg);
     lnpc = (lnpc + 1) & ~1;
@@ -702,11 +702,8 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     e->lnpc = lnpc;
     e->ltile_bytes = align_up((size_t)lnpc * ((size_t)2 * R * 8 + 3 * 8 + 4 + 4 + 4 + (size_t)4 * n_dom_levels), 16);
     e->ltile_stride = align_up(e->ltile_bytes, 256);
-    // dynamic shared memory of k_record: the staged tile during the sweep, the merge keys of the last CTA afterwards
-    size_t n_pow = 1;
-    while ((int)n_pow < lg * kTopM) n_pow <<= 1;
-    const size_t merge_bytes = sizeof(MergeKey) * n_pow + (size_t)lg * kTopM * kCEntryWords * 8;  // sort keys + staged entries
-    e->lsmem_bytes = std::max(merge_bytes, std::min(e->ltile_bytes, (size_t)e->max_smem_optin - 40 * 1024));
+    // dynamic shared memory of k_record: the staged tile during a sweep (scanned from global memory when it does not fit)
+    e->lsmem_bytes = e->ltile_bytes <= (size_t)e->max_smem_optin - 40 * 1024 ? e->ltile_bytes : 16;
     const size_t list_words = (size_t)2 * kListScanners * kListLines * kListLineWords;
     CK(e->dlaunch.reserve((size_t)lg * e->ltile_stride + (size_t)lg * align_up(kScanStateBytes, 256) + list_words * 8 + 4096));
     e->g_tiles = e->dlaunch.take<unsigned char>((size_t)lg * e->ltile_stride);
@@ -894,6 +891,10 @@ static bool engine_launch_record(void *ctx, const LaunchRec &rec) {
   } else {
     k_record<<<e->lgrid, kThreads, dyn, e->stream>>>(e->lp, rec);
     e->record_launches++;
+    if (kind == DK_TOPK || (kind == DK_SCAN && e->lp.topm && !(xbits & XB_SINGLE))) {  // list answer: sort, cut, stream to the host
+      k_merge<<<1, kMergeThreads, kMergeSmemBytes, e->stream>>>(e->lp, rec.seq, kind == DK_SCAN ? 1 : 0);
+      e->record_launches++;
+    }
   }
   return cudaPeekAtLastError() == cudaSuccess;
 }
@@ -980,6 +981,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       {
         int per_sm = 0;
         CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lsmem_bytes));
+        CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeSmemBytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_record, kThreads, e->lsmem_bytes));
         p.fused_in_kernel = (per_sm * e->num_sms >= e->lgrid && !getenv("KAI_NO_FUSED_LAUNCH")) ? 1 : 0;
       }
@@ -1231,7 +1233,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     {
       long long cd[48];
       CK(cudaMemcpy(cd, e->counters, sizeof(cd), cudaMemcpyDeviceToHost));
-      for (int i = 20; i < 28; i++) c[i] = cd[i];
+      for (int i = 20; i < 32; i++) c[i] = cd[i];
       for (int i = 32; i < 48; i++) c[i] = cd[i];
     }
     c[0] = seq.n_visits;
@@ -1294,8 +1296,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       fprintf(stderr, "[kai] host sequencer rdtsc Mcycles: pop %.2f admit %.2f place(+sweeps) %.2f finish %.2f loop %.2f\n",
               e->hb.t_sec[0] / 1e6, e->hb.t_sec[1] / 1e6, e->hb.t_sec[2] / 1e6, e->hb.t_sec[3] / 1e6, e->hb.t_sec[4] / 1e6);
     if (host_mode && c[45] > 0)
-      fprintf(stderr, "[kai] last-CTA list merge: %lld cycles per list (%lld lists): sort %lld, prefix + entries out %lld, fences + header %lld\n",
-              c[44] / c[45], c[45], c[46] / c[45], c[43] / c[45], c[47] / c[45]);
+      fprintf(stderr, "[kai] k_merge: %lld cycles per list (%lld lists): load %lld, sort %lld, prefix + payload %lld, stream out %lld, fence + header %lld\n",
+              c[44] / c[45], c[45], c[39] / c[45], c[46] / c[45], c[31] / c[45], c[47] / c[45], c[43] / c[45]);
     if (host_mode && c[22] > 0)
       fprintf(stderr, "[kai] relay CTA per record: forward %lld cycles, scanners+reduce %lld cycles (%lld records)\n",
               c[20] / c[22], c[21] / c[22], c[22]);
@@ -1359,6 +1361,7 @@ int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, in
   p.h_mmslot = e->h_mm;
   p.h_clist = e->h_clist;
   CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lsmem_bytes));
+  CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeSmemBytes));
   p.tile_bytes = e->ltile_bytes;
   p.hot_in_smem = e->ltile_bytes <= e->lsmem_bytes ? 1 : 0;
   e->lp = p;

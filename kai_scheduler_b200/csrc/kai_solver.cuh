@@ -490,6 +490,7 @@ struct Solver {
     ops_truncate(0);
   }
   void stmt_commit() {  // :536-571: pipelines keep Pipelined, evictions keep Releasing and stop being virtual
+    commit_epoch++;
     for (int i = 0; i < (int)ops.size(); i++) {
       if (!op_valid(i)) continue;
       if (ops[i].kind == OPK_PIPELINE)
@@ -725,6 +726,7 @@ struct Solver {
     int queue = -1, parent = -1;
     bool is_leaf = false, needs_reorder = false;
     HeapGo<int> children;
+    int lazy_queue = -1;  // victims queue: only the best job of this leaf is loaded so far (Solver::victim_leaf_list has the rest)
   };
   struct JobsOrder {
     Solver *o = nullptr;
@@ -785,9 +787,28 @@ struct Solver {
     }
     void victims_allocated(int ni, double *out) {  // :338-346
       int leaf = leaf_of_best(ni);
-      std::vector<int> v = popped_by_queue[nodes[leaf].queue];
-      if (!nodes[leaf].children.empty()) v.push_back(nodes[leaf].children.peek());
-      for (int vi : v) o->v_allocated(vi, out);
+      for (int vi : popped_by_queue[nodes[leaf].queue]) o->v_allocated(vi, out);
+      if (!nodes[leaf].children.empty()) o->v_allocated(nodes[leaf].children.peek(), out);
+    }
+    // the comparators capture `this`: a copy must bind its own
+    void rebind() {
+      root.less = [this](const int &a, const int &b) { return node_less(a, b); };
+      for (auto &n : nodes) {
+        if (n.is_leaf)
+          n.children.less = [this](const int &a, const int &b) { return victim_queue ? !job_less(a, b) : job_less(a, b); };
+        else
+          n.children.less = [this](const int &a, const int &b) { return node_less(a, b); };
+      }
+    }
+    void copy_from(const JobsOrder &src) {
+      o = src.o;
+      victim_queue = src.victim_queue;
+      nodes = src.nodes;
+      queue_node = src.queue_node;
+      linked = src.linked;
+      root = src.root;
+      popped_by_queue = src.popped_by_queue;
+      rebind();
     }
     void init(Solver *solver, bool victims) {
       o = solver;
@@ -838,10 +859,18 @@ struct Solver {
       }
       if (is_new) ensure_chain(pn);
     }
+    // a lazily loaded leaf holds its best job only; anything that reads or changes more loads the whole run first
+    void materialize(int leaf) {
+      if (nodes[leaf].lazy_queue < 0) return;
+      const int q = nodes[leaf].lazy_queue;
+      nodes[leaf].lazy_queue = -1;
+      nodes[leaf].children.a = o->victim_leaf_list(*this, q);  // same best job on top: the ancestors' heaps are unaffected
+    }
     void push_job(int v) {  // :90-119
       int q = o->s.j_queue[o->vjob(v)];
       if (q < 0 || o->s.q_nchildren[q] != 0) return;
       int leaf = queue_node[q];
+      if (leaf >= 0) materialize(leaf);
       bool needs_linking = leaf < 0;
       if (needs_linking) {
         leaf = make_node(q, true);
@@ -891,6 +920,7 @@ struct Solver {
         }
         pq = &nodes[ni].children;
       }
+      materialize(leaf);
       int job = nodes[leaf].children.pop();
       if (victim_queue) popped_by_queue[nodes[leaf].queue].push_back(job);
       handle_pop(leaf);
@@ -1407,8 +1437,31 @@ struct Solver {
   // leaf is linked into its ancestors' heaps with its best job on top either way, so the tree below is the one
   // push_job would have produced, queue by queue in ascending order.
   std::vector<std::vector<int>> vq_leaf;
-  std::vector<long long> vq_leaf_epoch, leaf_epoch;
+  std::vector<long long> vq_leaf_epoch, leaf_epoch, vq_top_epoch;
+  std::vector<int> vq_top;  // best victim of the leaf (-1: none), valid while vq_top_epoch matches
   long long vq_rebuilt = 0, vq_reused = 0;
+  unsigned long long victim_key(JobsOrder &jo, int j) {
+    bool below, above, exactly;
+    jo.min_available_state(j, below, above, exactly);
+    return make_job_key(s.j_priority[j], below ? 0 : (exactly ? 1 : 2), s.j_order_rank[j]);
+  }
+  int victim_leaf_top(JobsOrder &jo, int q) {
+    if (vq_top_epoch[q] == leaf_epoch[q]) return vq_top[q];
+    int best = -1;
+    unsigned long long best_key = 0;
+    for (int i = s.q_job_begin[q]; i < s.q_job_begin[q + 1]; i++) {
+      const int j = s.q_jobs_sorted[i];
+      if (!preemptible(j) || count_job(j, kActiveAllocated) == 0) continue;
+      const unsigned long long k = victim_key(jo, j);
+      if (best < 0 || k > best_key) {
+        best = j;
+        best_key = k;
+      }
+    }
+    vq_top[q] = best;
+    vq_top_epoch[q] = leaf_epoch[q];
+    return best;
+  }
   const std::vector<int> &victim_leaf_list(JobsOrder &jo, int q) {
     if (vq_leaf_epoch[q] == leaf_epoch[q]) {
       vq_reused++;
@@ -1419,9 +1472,7 @@ struct Solver {
     for (int i = s.q_job_begin[q]; i < s.q_job_begin[q + 1]; i++) {
       const int j = s.q_jobs_sorted[i];
       if (!preemptible(j) || count_job(j, kActiveAllocated) == 0) continue;
-      bool below, above, exactly;
-      jo.min_available_state(j, below, above, exactly);
-      keyed.push_back({make_job_key(s.j_priority[j], below ? 0 : (exactly ? 1 : 2), s.j_order_rank[j]), j});
+      keyed.push_back({victim_key(jo, j), j});
     }
     std::sort(keyed.begin(), keyed.end(), [](const std::pair<unsigned long long, int> &a, const std::pair<unsigned long long, int> &b) { return a.first > b.first; });
     vq_leaf[q].clear();
@@ -1437,27 +1488,48 @@ struct Solver {
     for (int q = 0; q < Q; q++) {
       if (s.q_nchildren[q] != 0 || s.q_job_begin[q + 1] == s.q_job_begin[q]) continue;
       if (solver_kind == 0 && q == pq) continue;  // reclaim.go:126: other queues only
-      const std::vector<int> &lst = victim_leaf_list(jo, q);
-      if (lst.empty()) continue;
+      if (solver_kind == 1 && q == pq) {  // consolidation.go:127: every job of the queue but the pending one
+        std::vector<int> a = victim_leaf_list(jo, q);
+        a.erase(std::remove(a.begin(), a.end(), pending_job), a.end());
+        if (a.empty()) continue;
+        const int leaf = jo.make_node(q, true);
+        jo.queue_node[q] = leaf;
+        jo.nodes[leaf].children.a = a;
+        jo.ensure_chain(leaf);
+        jo.mark_ancestors(leaf);
+        continue;
+      }
+      // only the leaf's best job is needed until the leaf itself is popped: the rest of its run is loaded then
+      const int top = victim_leaf_top(jo, q);
+      if (top < 0) continue;
       const int leaf = jo.make_node(q, true);
       jo.queue_node[q] = leaf;
-      jo.nodes[leaf].children.a = lst;
-      if (solver_kind == 1 && q == pq) {  // consolidation.go:127: every job but the pending one
-        auto &a = jo.nodes[leaf].children.a;
-        a.erase(std::remove(a.begin(), a.end(), pending_job), a.end());
-        if (a.empty()) {
-          jo.queue_node[q] = -1;
-          continue;
-        }
-      }
+      jo.nodes[leaf].children.a.assign(1, top);
+      jo.nodes[leaf].lazy_queue = q;
       jo.ensure_chain(leaf);
       jo.mark_ancestors(leaf);
     }
     return true;
   }
+  // the partial jobs of one pending job (job_solver.go:60-88) start from the same committed state: the queue built for
+  // the first one is copied for the others (commit_epoch counts the statements committed in this action)
+  JobsOrder vq_proto;
+  int vq_proto_job = -1, vq_proto_kind = -1;
+  long long vq_proto_commit = -1, commit_epoch = 0;
   void build_victims_queue(JobsOrder &jo, int pending_job) {
+    if (vq_proto_job == pending_job && vq_proto_kind == solver_kind && vq_proto_commit == commit_epoch && ops.empty() &&
+        !getenv("KAI_NO_VICTIM_CACHE")) {
+      jo.copy_from(vq_proto);
+      return;
+    }
     jo.init(this, true);
-    if (build_victims_queue_cached(jo, pending_job)) return;
+    if (build_victims_queue_cached(jo, pending_job)) {
+      vq_proto.copy_from(jo);
+      vq_proto_job = pending_job;
+      vq_proto_kind = solver_kind;
+      vq_proto_commit = commit_epoch;
+      return;
+    }
     std::vector<int> vs;
     OrderOpts op;
     if (solver_kind == 0) {  // reclaim.go:121-143
@@ -1675,6 +1747,8 @@ struct Solver {
     job_cache.assign(J, Cache());
     vq_leaf.assign(Q, {});
     vq_leaf_epoch.assign(Q, -1);
+    vq_top.assign(Q, -1);
+    vq_top_epoch.assign(Q, -1);
     leaf_epoch.assign(Q, 0);
     pending_cnt.assign(J, 0);
     pending_jobs.clear();
