@@ -302,7 +302,7 @@ def main():
         pods_all = pods
     # dominant kernel: k_record, one launch per node-table sweep.  Its duration is measured live: back-to-back launches of
     # one list sweep over this rank's node rows, CUDA events on the engine's stream (kai_engine_time_sweeps)
-    sweep_ms, sweep_rows = eng.time_sweeps(200) if args.steps > 0 else (0.0, 0)
+    sweep_ms, merge_ms, sweep_rows = eng.time_sweeps(200) if args.steps > 0 else (0.0, 0.0, 0)
     if rank == 0:
         peak, which = measured_peak_gbs()
         sweep_bytes = sweep_rows * BYTES_PER_NODE
@@ -326,13 +326,14 @@ def main():
                     # engine-side phases of one step (kai_engine_stats); the rest of e2e is marshalling in the caller
                     "phases_ms": {k: v / max(args.steps, 1) for k, v in phase_ms.items()}},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_record (one node-table sweep per launch: fit + score + per-scanner top-M, "
-                                                   "merged and cut by the last CTA)",
+            "roofline": {"bound": "hbm", "kernel": "k_record (one node-table sweep per launch: node deltas, fit + score of every row, "
+                                                   "per-scanner top-M; 74 % of the GPU time of a step, profiles/r02_launches_bench.csv)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": sweep_bytes, "rows_per_launch": sweep_rows,
                          "kernel_us_per_launch": 1e3 * sweep_ms,
                          "how": "200 back-to-back launches of one list sweep timed with CUDA events on the engine's stream, after the timed steps",
+                         "merge_kernel_us_per_launch": 1e3 * merge_ms,
                          "sweeps_per_step": decisions, "sweep_share_of_step": (decisions * sweep_ms) / (act_ms / args.steps) if act_ms > 0 else None,
                          # the naive path sweeps every node for every pod
                          "naive_equivalent_bytes_per_step": int(snap.n_nodes) * int(pods_all // max(args.steps, 1)) * BYTES_PER_NODE,

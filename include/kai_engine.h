@@ -303,9 +303,10 @@ int kai_engine_stats(kai_engine *e, kai_stats *out);
 
 /* Measurement aid (no reference counterpart): times `n_launches` back-to-back launches of the sweep kernel (k_record,
    one list sweep of a 1-GPU / 1000 mCPU / 1e9 B pod over every node row of the loaded snapshot: the a4-a8 inner loop
-   of framework/session.go:201-264) with CUDA events on the engine's stream.  The session state is not changed.
-   Writes the elapsed milliseconds and the node rows one launch sweeps (x 76 B = its algorithmic bytes). */
-int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, int64_t *rows_per_launch);
+   of framework/session.go:201-264) and then as many of the merge kernel (k_merge: sort, cut and stream one answer
+   list to host memory) with CUDA events on the engine's stream.  The session state is not changed.  Writes the elapsed
+   milliseconds of both and the node rows one launch sweeps (x 76 B = its algorithmic bytes). */
+int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, double *merge_ms, int64_t *rows_per_launch);
 
 /* Multi-GPU wiring (one engine per process per GPU).  Shard s of
    shard_count owns the nodes of name rank s, s + S, s + 2S, ... (kai_shard_range

@@ -1331,7 +1331,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
   return download(e, out, c[0], c[3], c[4]);
 }
 
-int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, int64_t *rows_per_launch) {
+int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, double *merge_ms, int64_t *rows_per_launch) {
   if (!e || !elapsed_ms || !rows_per_launch || n_launches < 1) return KAI_ERR_INVALID;
   if (!e->loaded) return e->fail(KAI_ERR_STATE, "no snapshot loaded");
   CK(cudaSetDevice(e->device));
@@ -1389,16 +1389,22 @@ int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, in
   build_decision_words(c, DK_SCAN, 1);
   for (int i = 0; i < kDecWords; i++) rec.dw[i] = c.dw[i];
   rec.n_delta = 0;
+  // the sweep kernel alone (its top-M lines stay in device memory), then the merge kernel alone on the last answer
   cudaEventRecord(e->ev[0], e->stream);
   for (int i = 0; i < n_launches; i++) {
     rec.seq = e->seq + 1 + (unsigned int)i;
-    if (!engine_launch_record(e, rec)) return e->cuda_fail(cudaGetLastError(), "k_record");
+    k_record<<<e->lgrid, kThreads, e->lsmem_bytes, e->stream>>>(e->lp, rec);
   }
   cudaEventRecord(e->ev[1], e->stream);
+  for (int i = 0; i < n_launches; i++) k_merge<<<1, kMergeThreads, kMergeSmemBytes, e->stream>>>(e->lp, rec.seq, 1);
+  cudaEventRecord(e->ev[2], e->stream);
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
   *elapsed_ms = ms;
+  cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]);
+  if (merge_ms) *merge_ms = ms;
   const int n_shard_rows = e->N > e->cfg.shard_rank ? (e->N - e->cfg.shard_rank + e->cfg.shard_count - 1) / e->cfg.shard_count : 0;
   *rows_per_launch = n_shard_rows;
   e->seq += (unsigned int)n_launches + 4;

@@ -42,7 +42,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "kai_engine_create", "kai_engine_load_snapshot", "kai_engine_run", "kai_engine_fair_share",
     "kai_engine_stats", "kai_engine_export_peer_handle", "kai_engine_wire_peers", "kai_engine_destroy",
-    "kai_last_error", "kai_abi_version", "kai_shard_range",
+    "kai_last_error", "kai_abi_version", "kai_shard_range", "kai_engine_time_sweeps",
 ]
 
 
@@ -104,13 +104,13 @@ class Engine:
         return s
 
     def time_sweeps(self, n_launches: int = 200):
-        """(milliseconds per launch, node rows per launch) of the sweep kernel, back-to-back launches, CUDA events."""
-        ms, rows = C.c_double(), C.c_int64()
+        """(ms per sweep launch, ms per merge launch, node rows per launch): back-to-back launches, CUDA events."""
+        ms, mms, rows = C.c_double(), C.c_double(), C.c_int64()
         fn = self._lib.kai_engine_time_sweeps
-        fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         fn.restype = C.c_int
-        self._check(fn(self._h, n_launches, C.byref(ms), C.byref(rows)))
-        return ms.value / n_launches, rows.value
+        self._check(fn(self._h, n_launches, C.byref(ms), C.byref(mms), C.byref(rows)))
+        return ms.value / n_launches, mms.value / n_launches, rows.value
 
     def export_peer_handle(self) -> bytes:
         buf = (C.c_uint8 * abi.PEER_HANDLE_BYTES)()
