@@ -161,6 +161,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="config3-cycle", choices=sorted(synthetic.CONFIG_ACTIONS))
+    ap.add_argument("--resident", default="on", choices=["on", "off"],
+                    help="on: steps after the first refresh the per-cycle columns of a resident snapshot (structure_epoch); "
+                         "off: every step is a full kai_engine_load_snapshot")
     ap.add_argument("--parity", default="auto", choices=["auto", "off"],
                     help="compare the last step's outcome with the CPU oracle (threaded) and exit 1 on a mismatch")
     ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "off"])
@@ -227,8 +230,15 @@ def main():
         handles = [eng.export_peer_handle() if rank == 0 else b""]
         dist.broadcast_object_list(handles, src=0)
         eng.wire_peers(handles * world)
+    # steady-state cycle: the cluster's structure (queues, pod groups, requests, node identities) is unchanged between
+    # cycles, the per-cycle columns (node idle / releasing / flags, task status / node) are refreshed from host buffers
+    # every step (kai_snapshot.structure_epoch, ABI v7).  --resident off reloads the whole snapshot every step.
+    snap.structure_epoch = 1 if args.resident == "on" else 0
     c_snap = snap.to_c()
-    h2d = snap.host_bytes()
+    full_bytes = snap.host_bytes()
+    dyn_bytes = int(snap.node_idle.nbytes + snap.node_releasing.nbytes + snap.node_flags.nbytes + snap.task_status.nbytes +
+                    snap.task_node.nbytes)
+    h2d = dyn_bytes if args.resident == "on" else full_bytes
 
     def barrier():
         if world > 1:
@@ -323,6 +333,8 @@ def main():
             "config": workload,
             "e2e": {"value": pods_all / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "snapshot": ("resident: per-cycle columns re-read from host buffers each step (structure_epoch); a full load is "
+                                 f"{full_bytes} B" if args.resident == "on" else "full load every step"),
                     # engine-side phases of one step (kai_engine_stats); the rest of e2e is marshalling in the caller
                     "phases_ms": {k: v / max(args.steps, 1) for k, v in phase_ms.items()}},
             "gpu_launches": launches,

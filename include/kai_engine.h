@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KAI_ABI_VERSION 6
+#define KAI_ABI_VERSION 7
 #define KAI_MAX_RES 8 /* resource dims per node/task row (>= 4) */
 #define KAI_QRES 3    /* queue-level resources: CPU, Memory, GPU */
 #define KAI_MAX_QUEUE_DEPTH 8 /* max levels in the queue hierarchy */
@@ -237,6 +237,15 @@ typedef struct kai_snapshot {
          from the PodGroup's `kai.scheduler/stale-podgroup-timestamp` annotation (job_info.go:174-182), on the clock of
          now_s; <= 0 = nil (the action stamps time.Now(), i.e. zero time in stale state).  NULL = nil for all jobs. ---- */
   const double *job_stale_since_s;           /* [J] */
+  /* ---- resident snapshot (ABI v7).  The reference rebuilds ClusterInfo from the informer caches every cycle
+         (cache/cluster_info/cluster_info.go:118-228) although most of it — queues, pod groups, PodSets, requests, order
+         ranks, node identities and labels — only changes when an object is added, removed or edited.  A caller that
+         tracks that (the informers' resourceVersions) passes the same non-zero structure_epoch as long as only the
+         per-cycle columns changed: node_idle, node_releasing, node_flags, task_status, task_node, queue_usage, now_s,
+         job_last_start_s, job_stale_since_s.  kai_engine_load_snapshot then keeps everything it derived from the rest
+         (index structures, task renumbering, device copies) and uploads those columns only.  0 = always a full load.
+         The other fields must still describe the same cluster (they are not re-read). ---- */
+  uint64_t structure_epoch;
 } kai_snapshot;
 
 /* One entry per job popped by an action, in visiting order. */

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-KAI_ABI_VERSION = 6
+KAI_ABI_VERSION = 7
 KAI_MAX_RES = 8
 KAI_QRES = 3
 RES_CPU, RES_MEM, RES_GPU, RES_PODS = 0, 1, 2, 3
@@ -90,6 +90,7 @@ class KaiSnapshot(C.Structure):
         ("podset_required_level", _ip), ("podset_preferred_level", _ip),
         ("now_s", C.c_double), ("queue_preempt_min_runtime_s", _dp), ("queue_reclaim_min_runtime_s", _dp),
         ("job_last_start_s", _dp), ("job_stale_since_s", _dp),
+        ("structure_epoch", C.c_uint64),
     ]
 
 
@@ -187,6 +188,7 @@ class Snapshot:
     queue_reclaim_min_runtime_s: np.ndarray | None = None
     job_last_start_s: np.ndarray | None = None             # [J] f64 seconds, <= 0 = never started
     job_stale_since_s: np.ndarray | None = None            # [J] f64 seconds, <= 0 = no staleness timestamp (stalegangeviction)
+    structure_epoch: int = 0                               # != 0 and unchanged: only the per-cycle columns are reloaded (ABI v7)
     names: dict = field(default_factory=dict)  # optional: node/job/task/queue names for reporting
     _keep: list = field(default_factory=list, repr=False)
 
@@ -283,6 +285,7 @@ class Snapshot:
         s.now_s = float(self.now_s)
         for name in ("queue_preempt_min_runtime_s", "queue_reclaim_min_runtime_s", "job_last_start_s", "job_stale_since_s"):
             setattr(s, name, p(getattr(self, name), np.float64, _dp))
+        s.structure_epoch = int(self.structure_epoch)
         self._keep = keep
         return s
 

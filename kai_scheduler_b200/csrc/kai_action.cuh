@@ -964,6 +964,7 @@ __device__ bool scanner_main(const ActionParams &p, const LaunchRec *lrec, unsig
     tile.npc = npc;
     tile.R = s.R;
     tile.nscan = p.grid - 1;
+    tile.nscan_log2 = (tile.nscan > 0 && (tile.nscan & (tile.nscan - 1)) == 0) ? 31 - __clz(tile.nscan) : -1;
     tile.my = my;
     tile.nshard = p.cfg.shard_count;
     tile.shard = p.cfg.shard_rank;

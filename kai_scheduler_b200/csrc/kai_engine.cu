@@ -157,6 +157,10 @@ struct kai_engine {
   std::vector<double> j_stale_since;                               // stalegangeviction input (host only)
   double now_s = 0;
   size_t dev_only_begin = 0, dev_only_bytes = 0;
+  // resident snapshot (kai_snapshot::structure_epoch): where the per-cycle columns live in the arena
+  unsigned long long structure_epoch = 0;
+  int shape[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // R, N, Q, J, S, T, pred classes, optional-array presence bits
+  size_t off_idle = 0, off_rel = 0, off_nflags = 0, off_usage = 0, off_tst = 0, off_tnode = 0, off_tnst = 0;
   std::vector<int> task_perm;
   std::vector<int32_t> r_tmp_node, r_tmp_status;
   long long *counters = nullptr;
@@ -187,6 +191,80 @@ struct kai_engine {
     cudaError_t _e = (call);                       \
     if (_e != cudaSuccess) return e->cuda_fail(_e, #call); \
   } while (0)
+
+static int load_tail(kai_engine *e, const kai_snapshot *s, int n_dom_levels, bool resident) {
+  const int N = e->N, T = e->T, Q = e->Q;
+  const DevSnap &ds = e->ds;
+  const size_t RN = (size_t)e->R * N, QN = (size_t)QR * Q;
+  (void)RN;
+  // ---------------- open session: totals, queue usage, fair share ----------------
+  if (N > 0) {
+    int blocks = std::min(e->num_sms * 4, (N + 255) / 256);
+    k_node_totals<<<blocks, 256, 0, e->stream>>>(ds);
+  }
+  if (T > 0) {
+    int blocks = std::min(e->num_sms * 8, (T + 255) / 256);
+    k_queue_usage<<<blocks, 256, 0, e->stream>>>(ds);
+  }
+  if (Q > 0) k_fair_share<<<1, 1024, 0, e->stream>>>(ds, e->cfg.k_value, e->fs_w, e->fs_rr);
+  cudaEventRecord(e->ev[2], e->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+  e->stats.upload_ms = ms;
+  cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]);
+  e->stats.open_session_ms = ms;
+  e->stats.kernel_launches = (N > 0) + (T > 0) + (Q > 0);
+  e->stats.action_ms = 0;
+  e->stats.download_ms = 0;
+  e->stats.decisions = e->stats.nodes_scanned = e->stats.algorithmic_bytes = 0;
+
+  // result buffers
+  e->r_task_node.assign(T, -1);
+  e->r_task_status.assign(T, 0);
+  e->r_fair.assign(QN, 0);
+  e->r_alloc.assign(QN, 0);
+  e->r_alloc_np.assign(QN, 0);
+  e->r_request.assign(QN, 0);
+  e->r_idle.assign(RN, 0);
+  e->r_rel.assign(RN, 0);
+  e->r_visits.clear();
+  e->on_other_node.clear();
+  e->on_other_status.clear();
+  e->on_extra.clear();
+  e->job_signature.clear();
+  e->h_mirror.resize((size_t)2 * s->n_res * s->n_nodes);
+  for (int n = 0; n < s->n_nodes; n++)
+    for (int r = 0; r < s->n_res; r++) {
+      e->h_mirror[(size_t)n * 2 * s->n_res + r] = s->node_idle[(size_t)r * s->n_nodes + n];
+      e->h_mirror[(size_t)n * 2 * s->n_res + s->n_res + r] = s->node_releasing[(size_t)r * s->n_nodes + n];
+    }
+  if (e->d_node_domain && !resident) {
+    cudaFree(e->d_node_domain);
+    e->d_node_domain = nullptr;
+  }
+  e->n_dom_levels = n_dom_levels;
+  e->topo.build(s);
+  if (n_dom_levels > 0 && s->n_nodes > 0 && !resident) {
+    CK(cudaMalloc(&e->d_node_domain, sizeof(int) * (size_t)n_dom_levels * s->n_nodes));
+    CK(cudaMemcpy(e->d_node_domain, s->node_domain, sizeof(int) * (size_t)n_dom_levels * s->n_nodes, cudaMemcpyHostToDevice));
+  }
+  e->mirror_valid = true;
+  if (s->job_signature) e->job_signature.assign(s->job_signature, s->job_signature + s->n_jobs);
+  e->q_preempt_mrt.clear();
+  e->q_reclaim_mrt.clear();
+  e->j_last_start.clear();
+  e->j_stale_since.clear();
+  e->now_s = s->now_s;
+  if (s->queue_preempt_min_runtime_s) e->q_preempt_mrt.assign(s->queue_preempt_min_runtime_s, s->queue_preempt_min_runtime_s + s->n_queues);
+  if (s->queue_reclaim_min_runtime_s) e->q_reclaim_mrt.assign(s->queue_reclaim_min_runtime_s, s->queue_reclaim_min_runtime_s + s->n_queues);
+  if (s->job_last_start_s) e->j_last_start.assign(s->job_last_start_s, s->job_last_start_s + s->n_jobs);
+  if (s->job_stale_since_s) e->j_stale_since.assign(s->job_stale_since_s, s->job_stale_since_s + s->n_jobs);
+  e->loaded = true;
+  return KAI_OK;
+}
+
 
 extern "C" {
 
@@ -282,6 +360,48 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   if (!s->node_allocatable || !s->node_idle || !s->node_releasing || !s->node_name_rank || !s->node_flags)
     if (s->n_nodes > 0) return e->fail(KAI_ERR_INVALID, "null node table");
   CK(cudaSetDevice(e->device));
+  {  // resident snapshot: same structure as the previous load -> only the per-cycle columns are refreshed
+    const int opt = (s->queue_usage ? 1 : 0) | (s->node_foreign ? 2 : 0) | (s->task_nominated ? 4 : 0) | (s->task_pred_class ? 8 : 0) |
+                    (s->pred_mask ? 16 : 0) | (s->node_gpu_count ? 32 : 0) | ((s->n_topologies > 0) ? 64 : 0);
+    const int shape[8] = {s->n_res, s->n_nodes, s->n_queues, s->n_jobs, s->n_podsets, s->n_tasks, s->n_pred_classes, opt};
+    const bool resident = e->loaded && s->structure_epoch != 0 && s->structure_epoch == e->structure_epoch &&
+                          memcmp(shape, e->shape, sizeof(shape)) == 0 && !getenv("KAI_NO_RESIDENT");
+    memcpy(e->shape, shape, sizeof(shape));
+    e->structure_epoch = s->structure_epoch;
+    if (resident) {
+      const int R = s->n_res, N = s->n_nodes, Q = s->n_queues, T = s->n_tasks;
+      const size_t RN = (size_t)R * N, QN = (size_t)QR * Q;
+      e->loaded = false;
+      for (int t = 0; t < T; t++) {
+        int n = s->task_node[t];
+        if (n >= N) return e->fail(KAI_ERR_INVALID, "bad task_node");
+        if ((s->task_status[t] & kActiveUsed) && n < 0) return e->fail(KAI_ERR_INVALID, "active task without node");
+      }
+      cudaEventRecord(e->ev[0], e->stream);
+      unsigned char *h = e->stage.host, *d = e->dsnap.base;
+      memcpy(h + e->off_idle, s->node_idle, RN * 8);
+      memcpy(h + e->off_rel, s->node_releasing, RN * 8);
+      memcpy(h + e->off_nflags, s->node_flags, (size_t)N * 4);
+      if (s->queue_usage) memcpy(h + e->off_usage, s->queue_usage, QN * 8);
+      {
+        const std::vector<int> &perm = e->task_perm;
+        int *x = (int *)(h + e->off_tst), *y = (int *)(h + e->off_tnst), *tn = (int *)(h + e->off_tnode);
+        for (int t = 0; t < T; t++) {
+          const int st = s->task_status[perm[t]];
+          x[t] = y[t] = st;
+          tn[t] = (st & kActiveUsed) ? s->task_node[perm[t]] : -1;
+        }
+      }
+      // idle | releasing and status | node | node status are adjacent regions of the arena: one copy each
+      CK(cudaMemcpyAsync(d + e->off_idle, h + e->off_idle, (e->off_rel - e->off_idle) + RN * 8, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(d + e->off_nflags, h + e->off_nflags, (size_t)N * 4, cudaMemcpyHostToDevice, e->stream));
+      if (s->queue_usage) CK(cudaMemcpyAsync(d + e->off_usage, h + e->off_usage, QN * 8, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(d + e->off_tst, h + e->off_tst, (e->off_tnst - e->off_tst) + (size_t)std::max(T, 1) * 4, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemsetAsync(d + e->dev_only_begin, 0, e->dev_only_bytes, e->stream));
+      cudaEventRecord(e->ev[1], e->stream);
+      return load_tail(e, s, e->n_dom_levels, true);
+    }
+  }
   e->loaded = false;
   const int R = s->n_res, N = s->n_nodes, Q = s->n_queues, J = s->n_jobs, S = s->n_podsets, T = s->n_tasks;
   e->R = R;
@@ -456,6 +576,13 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   size_t o_tnst = reserve_up((size_t)std::max(T, 1) * 4);
   size_t o_mask = (s->pred_mask && NPC > 0) ? reserve_up((size_t)NPC * mask_words * 4) : 0;
   const size_t upload_bytes = up;
+  e->off_idle = o_idle;
+  e->off_rel = o_rel;
+  e->off_nflags = o_nflags;
+  e->off_usage = o_quse;
+  e->off_tst = o_tst;
+  e->off_tnode = o_tnode;
+  e->off_tnst = o_tnst;
   // device-only region
   size_t o_tvirt = reserve_up((size_t)std::max(T, 1));
   size_t o_qfair = reserve_up(QN * 8), o_qreq = reserve_up(QN * 8), o_qal = reserve_up(QN * 8), o_qalnp = reserve_up(QN * 8);
@@ -741,72 +868,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
     }
   }
 
-  // ---------------- open session: totals, queue usage, fair share ----------------
-  if (N > 0) {
-    int blocks = std::min(e->num_sms * 4, (N + 255) / 256);
-    k_node_totals<<<blocks, 256, 0, e->stream>>>(ds);
-  }
-  if (T > 0) {
-    int blocks = std::min(e->num_sms * 8, (T + 255) / 256);
-    k_queue_usage<<<blocks, 256, 0, e->stream>>>(ds);
-  }
-  if (Q > 0) k_fair_share<<<1, 1024, 0, e->stream>>>(ds, e->cfg.k_value, e->fs_w, e->fs_rr);
-  cudaEventRecord(e->ev[2], e->stream);
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(e->stream));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
-  e->stats.upload_ms = ms;
-  cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]);
-  e->stats.open_session_ms = ms;
-  e->stats.kernel_launches = (N > 0) + (T > 0) + (Q > 0);
-  e->stats.action_ms = 0;
-  e->stats.download_ms = 0;
-  e->stats.decisions = e->stats.nodes_scanned = e->stats.algorithmic_bytes = 0;
-
-  // result buffers
-  e->r_task_node.assign(T, -1);
-  e->r_task_status.assign(T, 0);
-  e->r_fair.assign(QN, 0);
-  e->r_alloc.assign(QN, 0);
-  e->r_alloc_np.assign(QN, 0);
-  e->r_request.assign(QN, 0);
-  e->r_idle.assign(RN, 0);
-  e->r_rel.assign(RN, 0);
-  e->r_visits.clear();
-  e->on_other_node.clear();
-  e->on_other_status.clear();
-  e->on_extra.clear();
-  e->job_signature.clear();
-  e->h_mirror.resize((size_t)2 * s->n_res * s->n_nodes);
-  for (int n = 0; n < s->n_nodes; n++)
-    for (int r = 0; r < s->n_res; r++) {
-      e->h_mirror[(size_t)n * 2 * s->n_res + r] = s->node_idle[(size_t)r * s->n_nodes + n];
-      e->h_mirror[(size_t)n * 2 * s->n_res + s->n_res + r] = s->node_releasing[(size_t)r * s->n_nodes + n];
-    }
-  if (e->d_node_domain) {
-    cudaFree(e->d_node_domain);
-    e->d_node_domain = nullptr;
-  }
-  e->n_dom_levels = n_dom_levels;
-  e->topo.build(s);
-  if (n_dom_levels > 0 && s->n_nodes > 0) {
-    CK(cudaMalloc(&e->d_node_domain, sizeof(int) * (size_t)n_dom_levels * s->n_nodes));
-    CK(cudaMemcpy(e->d_node_domain, s->node_domain, sizeof(int) * (size_t)n_dom_levels * s->n_nodes, cudaMemcpyHostToDevice));
-  }
-  e->mirror_valid = true;
-  if (s->job_signature) e->job_signature.assign(s->job_signature, s->job_signature + s->n_jobs);
-  e->q_preempt_mrt.clear();
-  e->q_reclaim_mrt.clear();
-  e->j_last_start.clear();
-  e->j_stale_since.clear();
-  e->now_s = s->now_s;
-  if (s->queue_preempt_min_runtime_s) e->q_preempt_mrt.assign(s->queue_preempt_min_runtime_s, s->queue_preempt_min_runtime_s + s->n_queues);
-  if (s->queue_reclaim_min_runtime_s) e->q_reclaim_mrt.assign(s->queue_reclaim_min_runtime_s, s->queue_reclaim_min_runtime_s + s->n_queues);
-  if (s->job_last_start_s) e->j_last_start.assign(s->job_last_start_s, s->job_last_start_s + s->n_jobs);
-  if (s->job_stale_since_s) e->j_stale_since.assign(s->job_stale_since_s, s->job_stale_since_s + s->n_jobs);
-  e->loaded = true;
-  return KAI_OK;
+  return load_tail(e, s, n_dom_levels, false);
 }
 
 static int download(kai_engine *e, kai_result *out, long long n_visits, long long placed, long long evicted) {
@@ -1043,6 +1105,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
     hb.launch_fn = &engine_launch_record;
     hb.launch_ctx = e;
     hb.launches = 0;
+    hb.t_launch = 0;
     hb.n_ranks = e->cfg.shard_count;
     hb.h_clist = e->cfg.shard_count > 1 ? e->shm_base + shm_clist_offset_words() : e->h_clist;
     hb.listed = 0;
@@ -1287,6 +1350,7 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       fprintf(stderr, "[kai] host sequencer (%s transport, %lld record launches): total %.3f ms, of which waiting for sweeps %.3f ms (%.2f us per sweep)\n",
               launch_mode ? "launch" : "persistent", launch_mode ? e->record_launches : 0LL, e->hb.t_total * 1e3, e->hb.t_exchange * 1e3,
               c[1] ? e->hb.t_exchange * 1e6 / c[1] : 0.0);
+    if (host_mode && launch_mode) fprintf(stderr, "[kai] launch calls: %.3f ms on the host thread (%.2f us per record)\n", e->hb.t_launch * 1e3, e->hb.launches ? e->hb.t_launch * 1e6 / e->hb.launches : 0.0);
     if (host_mode) fprintf(stderr, "[kai] sweeps answered with a single row (XB_SINGLE): %lld; FLUSH records %lld\n", e->hb.single_sweeps, e->hb.n_flush);
     if (host_mode) fprintf(stderr, "[kai] fresh gangs: %lld committed in bulk, %lld replayed per task, %lld discarded\n", e->hb.gang_bulk, e->hb.gang_replayed, e->hb.gang_failed);
     if (host_mode && e->hb.n_topo_jobs)

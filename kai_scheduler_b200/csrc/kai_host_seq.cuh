@@ -93,6 +93,7 @@ struct HostBackend {
   int n_ranks = 1;
   LaunchRec lrec;
   long long launches = 0;
+  double t_launch = 0;  // seconds inside the launch calls (KAI_PROFILE)
   void publish(int kind) {
     trace_kind[trace_n & 63] = kind;
     trace_seq[trace_n & 63] = ctl.seq;
@@ -111,7 +112,9 @@ struct HostBackend {
         lrec.dcount[e] = (unsigned char)((dl[2 * e + 1] >> 32) & 0xffu);
       }
       launches++;
+      const double tl = prof ? now() : 0.0;
       if (!launch_fn(launch_ctx, lrec)) failed = true;
+      if (prof) t_launch += now() - tl;
       return;
     }
     unsigned long long *rec = h_rec + (size_t)(ctl.seq & 1) * kDecWords * 2;

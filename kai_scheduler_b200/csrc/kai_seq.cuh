@@ -197,13 +197,23 @@ struct Tile {  // shared-memory node tile of this CTA
   // of shard `shard` is the node of name rank (j * nscan + my) * nshard + shard.  Consecutive ranks land on
   // different scanners, so the global top-K rows of a sweep come from ~K different scanners.
   int nscan, my, nshard, shard;
+  int nscan_log2;  // log2(nscan) when nscan is a power of two, else -1
 };
 KAI_HD inline int tile_row_rank(const Tile &tl, int ln) { return (ln * tl.nscan + tl.my) * tl.nshard + tl.shard; }
 KAI_HD inline bool tile_owns(const Tile &tl, unsigned int rank, int &ln) {
-  unsigned int q = rank / (unsigned int)tl.nshard;
-  if (rank - q * (unsigned int)tl.nshard != (unsigned int)tl.shard) return false;
-  unsigned int j = q / (unsigned int)tl.nscan;
-  if (q - j * (unsigned int)tl.nscan != (unsigned int)tl.my) return false;
+  unsigned int q = rank;
+  if (tl.nshard != 1) {  // one GPU: every rank is this shard's
+    q = rank / (unsigned int)tl.nshard;
+    if (rank - q * (unsigned int)tl.nshard != (unsigned int)tl.shard) return false;
+  }
+  unsigned int j;
+  if (tl.nscan_log2 >= 0) {  // scanner count is a power of two (256 by default): no integer division on the device
+    j = q >> tl.nscan_log2;
+    if ((q & ((1u << tl.nscan_log2) - 1u)) != (unsigned int)tl.my) return false;
+  } else {
+    j = q / (unsigned int)tl.nscan;
+    if (q - j * (unsigned int)tl.nscan != (unsigned int)tl.my) return false;
+  }
   ln = (int)j;
   return true;
 }

@@ -27,7 +27,7 @@ def test_header_symbols_exported():
 def test_struct_sizes_match_header():
     # field order/size sanity: the C side rejects a mismatching abi_version, sizes are checked here
     assert C.sizeof(abi.KaiConfig) == 4 * 4 + 8 * 2 + 4 * 7 + 4 + 8 * 2  # 4 bytes of padding before the doubles
-    assert C.sizeof(abi.KaiSnapshot) == 8 * 4 + 30 * 8 + 2 * 4 + 5 * 8 + 2 * 4 + 10 * 8 + 5 * 8
+    assert C.sizeof(abi.KaiSnapshot) == 8 * 4 + 30 * 8 + 2 * 4 + 5 * 8 + 2 * 4 + 10 * 8 + 5 * 8 + 8
     assert C.sizeof(abi.KaiJobVisit) == 8
 
 

@@ -365,3 +365,40 @@ def test_tables_persistent_transport(grid, monkeypatch):
     assert_same(*run_both(snap))
     snap = synthetic.config_snapshot("config4-small")
     assert_same(*run_both(snap))
+
+
+def test_resident_snapshot_reload_equals_full_load():
+    """kai_snapshot.structure_epoch (ABI v7): a second load with the same epoch refreshes the per-cycle columns only (node
+    idle / releasing / flags, task status / node, queue usage) and must behave exactly like a full load of the same data."""
+    rng = np.random.default_rng(77)
+    base = synthetic.reclaim_snapshot(n_nodes=96, running_per_node=6, victim_queues=3, reclaimer_jobs=24, reclaimer_tasks=2,
+                                      reclaimer_gpus=3.0)
+    e = Engine()
+    base.structure_epoch = 41
+    e.load(base)
+    for act in ("allocate", "reclaim"):
+        e.run(act)
+    # next cycle: some running pods finished (their resources are free again), two nodes went NotReady
+    nxt = synthetic.reclaim_snapshot(n_nodes=96, running_per_node=6, victim_queues=3, reclaimer_jobs=24, reclaimer_tasks=2,
+                                     reclaimer_gpus=3.0)
+    done = rng.choice(np.flatnonzero(nxt.task_status == abi.POD_RUNNING), size=60, replace=False)
+    for t in done:
+        nxt.node_idle[:, nxt.task_node[t]] += nxt.task_req[t]
+    nxt.task_status[done] = abi.POD_STATUS_NAMES["Succeeded"]
+    nxt.task_node[done] = -1
+    nxt.node_flags[[5, 17]] &= ~np.uint32(abi.NODE_READY)
+    nxt.structure_epoch = 41
+    e.load(nxt)          # resident path
+    full = Engine()
+    nxt.structure_epoch = 0
+    full.load(nxt)       # full path
+    o = Oracle()
+    o.load(nxt)
+    for act in ("allocate", "consolidation", "reclaim", "preempt"):
+        r1, r2, ro = e.run(act), full.run(act), o.run(act)
+        assert_same(r1, ro)
+        assert_same(r2, ro)
+        assert r1.pods_evicted == ro.pods_evicted
+    e.close()
+    full.close()
+    o.close()
