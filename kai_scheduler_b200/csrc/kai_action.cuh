@@ -26,6 +26,8 @@
 #include <cfloat>
 #include <cstdint>
 
+#include <cooperative_groups.h>
+
 #include "kai_device.cuh"
 #include "kai_kernels.cuh"
 #include "kai_seq.cuh"
@@ -2038,6 +2040,181 @@ __global__ void __launch_bounds__(kMergeThreads, 1) k_merge(const __grid_constan
     p.counters[43] += t5 - t4;  // fence + header
     p.counters[39] += t1 - t0;  // candidate loads + cut
     p.counters[31] += t3 - t2;  // prefix + payload loads
+  }
+}
+
+// The same merge on a thread-block cluster (Blackwell: 4 CTAs x 256 threads on 4 SMs, one candidate per thread): the
+// 55-step network is bound by instruction issue, so four SMs run it ~3x faster than one.  Partner exchange: warp shuffle
+// below 32 lanes, the CTA's shared memory below 256, the partner CTA's shared memory (distributed shared memory,
+// cluster.map_shared_rank) for the three steps with j >= 256; every CTA streams its own quarter of the sorted prefix to
+// host memory, CTA 0 writes the header after the cluster barrier.
+constexpr int kMergeCtas = 4, kMergeCtaThreads = kMergeThreads / kMergeCtas;
+constexpr size_t kMergeCtaSmemBytes = (size_t)kMergeCtaThreads * 8 * (2 + kCEntryWords);
+__global__ void __cluster_dims__(kMergeCtas, 1, 1) __launch_bounds__(kMergeCtaThreads, 1)
+    k_merge_cluster(const __grid_constant__ ActionParams p, unsigned int seq, int with_payload) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  unsigned long long *xh = (unsigned long long *)dyn_smem, *xl = xh + kMergeCtaThreads, *stage = xl + kMergeCtaThreads;
+  __shared__ unsigned long long cut_h[kMergeCtaThreads / 32];
+  __shared__ unsigned int cut_r[kMergeCtaThreads / 32];
+  __shared__ int n_ok[kMergeCtaThreads / 32];
+  __shared__ unsigned long long cta_cut_h;  // read by the other CTAs of the cluster
+  __shared__ unsigned int cta_cut_r;
+  __shared__ int cta_n_ok;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned int crank = cluster.block_rank();
+  const int g = (int)crank * kMergeCtaThreads + tid;  // my position in the network
+  const int n_scan = p.grid - 1;
+  const int n_c = n_scan * kTopM;
+  const unsigned long long *base = p.h_list + (size_t)(seq & 1) * kListScanners * kListLines * kListLineWords;
+  const long long t0 = clock64();
+  unsigned long long h = ~0ull, l = ~0ull;
+  bool more = false;
+  if (g < n_c) {
+    const int c = g / kTopM, m = g % kTopM;
+    const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
+    const uint4 v = __ldcg((const uint4 *)(lines + 2 * m));
+    const unsigned long long lo = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+    const unsigned long long hi = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+    const uint32_t rank = (uint32_t)(hi & 0xffffffu);
+    more = (((uint32_t)(hi >> 32) & 0xffu) & LF_MORE) != 0;
+    if (rank != kRankNone) {
+      h = ~lo;
+      l = ((unsigned long long)rank << 32) | (unsigned long long)g;
+    }
+  }
+  static_assert(kTopM == 4, "the group reductions below assume 4 candidates per scanner");
+  const unsigned int grp = 0xfu << (lane & ~3);
+  const bool any_more = (__ballot_sync(0xffffffffu, more) & grp) != 0;
+  const unsigned int real = __ballot_sync(0xffffffffu, l != ~0ull) & grp;
+  unsigned long long ch = ~0ull;
+  unsigned int cr = kRankNone;
+  if (any_more && real && lane == 31 - __clz((int)real)) {
+    ch = h;
+    cr = (unsigned int)(l >> 32);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long oh = __shfl_xor_sync(0xffffffffu, ch, o);
+    const unsigned int orr = __shfl_xor_sync(0xffffffffu, cr, o);
+    if (orr != kRankNone && (cr == kRankNone || oh < ch || (oh == ch && orr < cr))) {
+      ch = oh;
+      cr = orr;
+    }
+  }
+  if (lane == 0) {
+    cut_h[warp] = ch;
+    cut_r[warp] = cr;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long bh = ~0ull;
+    unsigned int br = kRankNone;
+    for (int w = 0; w < kMergeCtaThreads / 32; w++)
+      if (cut_r[w] != kRankNone && (br == kRankNone || cut_h[w] < bh || (cut_h[w] == bh && cut_r[w] < br))) {
+        bh = cut_h[w];
+        br = cut_r[w];
+      }
+    cta_cut_h = bh;
+    cta_cut_r = br;
+  }
+  const long long t1 = clock64();
+  // ---- bitonic sort over the cluster, one element per thread ----
+  for (int k = 2; k <= kMergeThreads; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long oh, ol;
+      if (j < 32) {
+        oh = __shfl_xor_sync(0xffffffffu, h, j);
+        ol = __shfl_xor_sync(0xffffffffu, l, j);
+      } else if (j < kMergeCtaThreads) {
+        xh[tid] = h;
+        xl[tid] = l;
+        __syncthreads();
+        oh = xh[tid ^ j];
+        ol = xl[tid ^ j];
+        __syncthreads();
+      } else {  // the partner sits at the same thread index of CTA crank ^ (j / 256)
+        xh[tid] = h;
+        xl[tid] = l;
+        cluster.sync();
+        const unsigned int peer = crank ^ (unsigned int)(j / kMergeCtaThreads);
+        const unsigned long long *rh = cluster.map_shared_rank(xh, peer), *rl = cluster.map_shared_rank(xl, peer);
+        oh = rh[tid];
+        ol = rl[tid];
+        cluster.sync();
+      }
+      const bool lower = (g & j) == 0;
+      const bool up = (g & k) == 0;
+      const bool take = (lower == up) ? mk_before(oh, ol, h, l) : mk_before(h, l, oh, ol);
+      if (take) {
+        h = oh;
+        l = ol;
+      }
+    }
+  cluster.sync();  // every CTA's cut candidate is written; the exchange planes are free
+  const long long t2 = clock64();
+  unsigned long long gh = ~0ull;
+  unsigned int gr = kRankNone;
+  for (unsigned int c = 0; c < (unsigned int)kMergeCtas; c++) {
+    const unsigned long long oh = *cluster.map_shared_rank(&cta_cut_h, c);
+    const unsigned int orr = *cluster.map_shared_rank(&cta_cut_r, c);
+    if (orr != kRankNone && (gr == kRankNone || oh < gh || (oh == gh && orr < gr))) {
+      gh = oh;
+      gr = orr;
+    }
+  }
+  const bool have_cut = gr != kRankNone;
+  const unsigned int my_rank = (unsigned int)(l >> 32);
+  const bool ok = l != ~0ull && (!have_cut || h < gh || (h == gh && my_rank <= gr));
+  const unsigned int okb = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) n_ok[warp] = __popc(okb);
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < kMergeCtaThreads / 32; w++) t += n_ok[w];
+    cta_n_ok = t;
+  }
+  cluster.sync();
+  int n_out = 0;
+  for (unsigned int c = 0; c < (unsigned int)kMergeCtas; c++) n_out += *cluster.map_shared_rank(&cta_n_ok, c);
+  unsigned long long *out = p.h_clist + (size_t)(seq & 1) * kCListWords;
+  // this CTA's quarter of the sorted list: positions [crank * 256, crank * 256 + 256) below n_out
+  if (g < n_out) {
+    const int src = (int)(l & 0xffffffffu);
+    const int c = src / kTopM, m = src % kTopM;
+    const unsigned long long *lines = base + (size_t)(p.scanner_base + c) * kListLines * kListLineWords;
+    const uint4 v = __ldcg((const uint4 *)(lines + 2 * m));
+    uint4 pw[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) pw[q] = make_uint4(0, 0, 0, 0);
+    if (with_payload) {
+      const unsigned long long *pl = lines + (size_t)(1 + m) * kListLineWords;
+#pragma unroll
+      for (int q = 0; q < 4; q++) pw[q] = __ldcg((const uint4 *)(pl + 2 * q));
+    }
+    unsigned long long *e = stage + (size_t)tid * kCEntryWords;
+    e[0] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+    e[1] = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+#pragma unroll
+    for (int q = 0; q < 4; q++) e[2 + q] = (unsigned long long)pw[q].x | ((unsigned long long)pw[q].y << 32);
+  }
+  __syncthreads();
+  const int first = (int)crank * kMergeCtaThreads;
+  const int mine = max(0, min(n_out - first, kMergeCtaThreads));
+  const int n16 = (mine * kCEntryWords) / 2;
+  unsigned long long *out_mine = out + 2 + (size_t)first * kCEntryWords;
+  for (int i = tid; i < n16; i += kMergeCtaThreads) st_relaxed_sys_b128(out_mine + 2 * (size_t)i, stage[2 * i], stage[2 * i + 1]);
+  __threadfence_system();  // my entries are out before the cluster barrier lets CTA 0 write the header
+  cluster.sync();
+  if (crank == 0 && tid == 0) {
+    __threadfence_system();
+    st_relaxed_sys_b128(out, (unsigned long long)(unsigned int)n_out | (have_cut ? (1ull << 31) : 0ull), (unsigned long long)seq);
+    const long long t3 = clock64();
+    p.counters[44] += t3 - t0;
+    p.counters[45] += 1;
+    p.counters[46] += t2 - t1;  // sort
+    p.counters[39] += t1 - t0;  // candidate loads + cut
+    p.counters[31] += t3 - t2;  // prefix, payload, stream out, header
   }
 }
 

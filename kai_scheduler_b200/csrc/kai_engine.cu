@@ -133,6 +133,7 @@ struct kai_engine {
   unsigned long long *h_clist = nullptr;  // pinned mapped: [2][kCListWords]
   ActionParams lp;                        // parameters of the running action (launch transport)
   long long record_launches = 0;
+  bool merge_cluster = true;  // k_merge_cluster (4-CTA cluster) instead of the one-CTA k_merge (KAI_MERGE=single)
   // multi-GPU (one engine per process per GPU): the reduced answer lines of all GPUs live in one POSIX shm
   // segment that every process maps and registers with CUDA; each host sequencer reads all lines.
   unsigned long long *shm_base = nullptr;  // [slots | mm], each [2][kMaxGrid][kSlotWords]
@@ -954,7 +955,10 @@ static bool engine_launch_record(void *ctx, const LaunchRec &rec) {
     k_record<<<e->lgrid, kThreads, dyn, e->stream>>>(e->lp, rec);
     e->record_launches++;
     if (kind == DK_TOPK || (kind == DK_SCAN && e->lp.topm && !(xbits & XB_SINGLE))) {  // list answer: sort, cut, stream to the host
-      k_merge<<<1, kMergeThreads, kMergeSmemBytes, e->stream>>>(e->lp, rec.seq, kind == DK_SCAN ? 1 : 0);
+      if (e->merge_cluster)
+        k_merge_cluster<<<kMergeCtas, kMergeCtaThreads, kMergeCtaSmemBytes, e->stream>>>(e->lp, rec.seq, kind == DK_SCAN ? 1 : 0);
+      else
+        k_merge<<<1, kMergeThreads, kMergeSmemBytes, e->stream>>>(e->lp, rec.seq, kind == DK_SCAN ? 1 : 0);
       e->record_launches++;
     }
   }
@@ -1044,6 +1048,10 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
         int per_sm = 0;
         CK(cudaFuncSetAttribute(k_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lsmem_bytes));
         CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeSmemBytes));
+        {
+          const char *mk = getenv("KAI_MERGE");
+          e->merge_cluster = !(mk && strcmp(mk, "single") == 0);
+        }
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_record, kThreads, e->lsmem_bytes));
         p.fused_in_kernel = (per_sm * e->num_sms >= e->lgrid && !getenv("KAI_NO_FUSED_LAUNCH")) ? 1 : 0;
       }
@@ -1360,8 +1368,8 @@ int kai_engine_run(kai_engine *e, kai_action action, kai_result *out) {
       fprintf(stderr, "[kai] host sequencer rdtsc Mcycles: pop %.2f admit %.2f place(+sweeps) %.2f finish %.2f loop %.2f\n",
               e->hb.t_sec[0] / 1e6, e->hb.t_sec[1] / 1e6, e->hb.t_sec[2] / 1e6, e->hb.t_sec[3] / 1e6, e->hb.t_sec[4] / 1e6);
     if (host_mode && c[45] > 0)
-      fprintf(stderr, "[kai] k_merge: %lld cycles per list (%lld lists): load %lld, sort %lld, prefix + payload %lld, stream out %lld, fence + header %lld\n",
-              c[44] / c[45], c[45], c[39] / c[45], c[46] / c[45], c[31] / c[45], c[47] / c[45], c[43] / c[45]);
+      fprintf(stderr, "[kai] %s: %lld cycles per list (%lld lists): load %lld, sort %lld, prefix + payload %lld, stream out %lld, fence + header %lld\n",
+              e->merge_cluster ? "k_merge_cluster" : "k_merge", c[44] / c[45], c[45], c[39] / c[45], c[46] / c[45], c[31] / c[45], c[47] / c[45], c[43] / c[45]);
     if (host_mode && c[22] > 0)
       fprintf(stderr, "[kai] relay CTA per record: forward %lld cycles, scanners+reduce %lld cycles (%lld records)\n",
               c[20] / c[22], c[21] / c[22], c[22]);
@@ -1460,7 +1468,16 @@ int kai_engine_time_sweeps(kai_engine *e, int n_launches, double *elapsed_ms, do
     k_record<<<e->lgrid, kThreads, e->lsmem_bytes, e->stream>>>(e->lp, rec);
   }
   cudaEventRecord(e->ev[1], e->stream);
-  for (int i = 0; i < n_launches; i++) k_merge<<<1, kMergeThreads, kMergeSmemBytes, e->stream>>>(e->lp, rec.seq, 1);
+  {
+    const char *mk = getenv("KAI_MERGE");
+    e->merge_cluster = !(mk && strcmp(mk, "single") == 0);
+  }
+  for (int i = 0; i < n_launches; i++) {
+    if (e->merge_cluster)
+      k_merge_cluster<<<kMergeCtas, kMergeCtaThreads, kMergeCtaSmemBytes, e->stream>>>(e->lp, rec.seq, 1);
+    else
+      k_merge<<<1, kMergeThreads, kMergeSmemBytes, e->stream>>>(e->lp, rec.seq, 1);
+  }
   cudaEventRecord(e->ev[2], e->stream);
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaGetLastError());

@@ -308,6 +308,11 @@ RECLAIM_CONFIGS = {
     **{f"reclaim-large-{n}": dict(n_nodes=n) for n in (10, 50, 100, 200, 500, 1000)},
     "cycle5-small": dict(n_nodes=200, running_per_node=8, victim_queues=4, reclaimer_jobs=100, reclaimer_tasks=2,
                          reclaimer_gpus=4.0),
+    # BASELINE config 5 ladder (reclaim + consolidate cycle: every node full of running over-quota pods, pending reclaimers)
+    "cycle5-1000": dict(n_nodes=1000, running_per_node=8, victim_queues=4, reclaimer_jobs=250, reclaimer_tasks=2,
+                        reclaimer_gpus=4.0),
+    "cycle5-5000": dict(n_nodes=5000, running_per_node=8, victim_queues=4, reclaimer_jobs=500, reclaimer_tasks=2,
+                        reclaimer_gpus=4.0),
 }
 # BASELINE.json's metric: one allocate + reclaim cycle over 50k nodes / 200k pending pods / 1k queues (+250 departments)
 CYCLE_CONFIGS = {
@@ -316,7 +321,7 @@ CYCLE_CONFIGS = {
 }
 CONFIG_ACTIONS = {**{k: ["allocate", "reclaim"] for k in CYCLE_CONFIGS}, **{k: ["allocate"] for k in CONFIGS}, **{k: ["allocate"] for k in TOPOLOGY_CONFIGS},
                   **{k: ["reclaim"] for k in RECLAIM_CONFIGS},
-                  "cycle5-small": ["allocate", "consolidation", "reclaim"]}
+                  **{k: ["allocate", "consolidation", "reclaim"] for k in ("cycle5-small", "cycle5-1000", "cycle5-5000")}}
 # ms/op the reference publishes for BenchmarkReclaimLargeJobs (other hardware, includes BuildSession)
 REFERENCE_PUBLISHED_MS = {"reclaim-large-10": 104.4, "reclaim-large-50": 130.2, "reclaim-large-100": 241.2,
                           "reclaim-large-200": 816.0, "reclaim-large-500": 8970.0}
