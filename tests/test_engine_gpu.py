@@ -402,3 +402,21 @@ def test_resident_snapshot_reload_equals_full_load():
     e.close()
     full.close()
     o.close()
+
+
+def test_metric_cycle_small():
+    """The allocate + reclaim cycle of bench.py's default configuration (synthetic.cycle_snapshot) at a size the oracle
+    finishes in milliseconds; bench.py asserts the same at 50 000 nodes on every run."""
+    snap = synthetic.config_snapshot("config3-cycle-small")
+    e, o = Engine(), Oracle()
+    e.load(snap)
+    o.load(snap)
+    evicted = 0
+    for act in synthetic.CONFIG_ACTIONS["config3-cycle-small"]:
+        re_, ro = e.run(act), o.run(act)
+        assert_same(re_, ro)
+        assert re_.pods_evicted == ro.pods_evicted
+        evicted += re_.pods_evicted
+    assert evicted == 16 and int((re_.task_status == abi.POD_PENDING).sum()) == 0
+    e.close()
+    o.close()

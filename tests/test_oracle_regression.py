@@ -31,7 +31,7 @@ def _workloads():
         dict(n_nodes=1000, n_jobs=3000, tasks_per_job=2, n_queues=40, mixed=True),
     ]):
         out[f"allocate-{i}"] = (synthetic.benchmark_snapshot(**kw), {}, ["allocate"])
-    for name in ("reclaim-large-10", "reclaim-large-100", "cycle5-small", "config4-small"):
+    for name in ("reclaim-large-10", "reclaim-large-100", "cycle5-small", "config4-small", "config3-cycle-small"):
         out[name] = (synthetic.config_snapshot(name), {}, list(synthetic.CONFIG_ACTIONS.get(name, ["allocate"])))
     snap = synthetic.reclaim_snapshot(64, victim_queues=3, reclaimer_jobs=6, reclaimer_tasks=2, reclaimer_gpus=4.0)
     out["victims-all-actions"] = (snap, {}, ["allocate", "consolidation", "reclaim", "preempt", "stalegangeviction"])
