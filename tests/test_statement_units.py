@@ -150,3 +150,26 @@ def test_statement_checkpoint_rollback(name, ops):
     assert exercise(o, ops) >= 1
     assert exercise(o, [(ROLLBACK, 0)]) >= 0
     assert state(o) == before
+
+
+def test_one_clone_per_node_is_unbounded():
+    """NodeInfo.PodInfos is a map per node (node_info.go:400-402): a pod that is evicted on A, pipelined to B, evicted
+    there and pipelined to C holds a clone on each of the three nodes (Releasing, Releasing, Pipelined); Discard walks
+    back through all of them.  (Round 2: oracle and engine used to keep two entries and disagreed on B200.)"""
+    topo = {"Nodes": {f"node{i}": {"GPUs": 2} for i in range(3)}, "Queues": [{"Name": "queue0", "DeservedGPUs": 6}],
+            "Jobs": [job("running_job0", "Running", "node0")]}
+    snap, _ = dsl.build_snapshot(topo)
+    o = Oracle()
+    o.load(snap)
+    before = state(o)
+    S = abi.POD_STATUS_NAMES
+    assert o.node_entries() == [(0, 0, S["Running"])]
+    assert exercise(o, [(EVICT, 0), (PIPELINE, 0, 1), (EVICT, 0), (PIPELINE, 0, 2)]) == 4
+    assert sorted(o.node_entries()) == [(0, 0, S["Releasing"]), (0, 1, S["Releasing"]), (0, 2, S["Pipelined"])]
+    r = o.fair_share()
+    # node0: the original pod is Releasing (its GPU still taken, counted as releasing); node1: an evicted Pipelined clone
+    # takes a GPU out of Idle and adds it to Releasing (pod_status.go:66: Pipelined is active-allocated, so it can be
+    # evicted); node2: the Pipelined clone takes the GPU out of Releasing
+    assert r.node_idle[2].tolist() == [1.0, 1.0, 2.0] and r.node_releasing[2].tolist() == [1.0, 1.0, -1.0]
+    assert exercise(o, [(DISCARD, 0)]) == 0
+    assert state(o) == before and o.node_entries() == [(0, 0, S["Running"])]
