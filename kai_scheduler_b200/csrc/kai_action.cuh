@@ -1,16 +1,19 @@
-// kai_action.cuh — the persistent action kernel (allocate) and its two prepare kernels.
+// kai_action.cuh — the action kernels and the two prepare kernels.
 //
-//   k_prep_jobs    per job: podset status counters, readiness, JobOrderFn sort key, cached
-//                  GetTasksToAllocateInitResource                                        (grid-parallel)
-//   k_prep_queues  per leaf queue: eligible jobs in JobOrderFn order                     (thread per queue)
-//   k_action       whole Action on device, one CTA per SM, cooperative launch:
-//                    CTA 0      the sequencer (warp 0): job-order tree, capacity checks, statement; its
-//                               per-queue state lives in shared memory, per-task/job state is the session
-//                               state in HBM/L2 (single copy)
-//                    CTA 1..G-1 scanners: each keeps its slice of the node tables in shared memory for the
-//                               whole action and answers every decision record with one 16-byte candidate
-//                  sequencer -> scanners: a 16-word decision record (tagged 128-bit relaxed stores) plus a
-//                  list of node deltas since the previous record; scanners -> sequencer: one slot per CTA.
+//   k_prep_jobs      per job: podset status counters, readiness, JobOrderFn sort key, cached
+//                    GetTasksToAllocateInitResource, "fresh uniform gang" flag                (grid-parallel)
+//   k_prep_queues    per leaf queue: eligible jobs in JobOrderFn order                        (CTA per queue)
+//   k_record         launch transport (default): ONE decision record per launch, 256 scanners x 128 threads.  Every
+//                    scanner owns a stripe of node rows (tile, resident in global memory / L2 between launches, staged
+//                    in shared memory for the sweep), applies the node deltas addressed to it, evaluates fit + score of
+//                    its rows and answers: top-M candidates (lists), or one slot reduced by the last CTA to finish.
+//   k_merge_cluster  (k_merge: one-CTA form) sorts the scanners' candidates, cuts the list where an unseen row could be
+//                    better and streams it to host memory — the next launch on the stream after a list sweep.
+//   k_action         the same scanner code as ONE persistent cooperative kernel (one CTA per SM, tiles in shared memory
+//                    for the whole action): CTA 0 relays the records the host writes into pinned mapped memory
+//                    (KAI_TRANSPORT=persistent) or runs the sequencer itself (KAI_SEQUENCER=device): a 16-word decision
+//                    record (tagged 128-bit relaxed stores) plus the node deltas since the previous record go out,
+//                    one slot / M list lines per scanner come back.
 //
 // Exactness notes
 //   * FittingNode + NodeOrderFn + sortNodesByScore (framework/session.go:201-264,466-485) are evaluated as

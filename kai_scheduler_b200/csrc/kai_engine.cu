@@ -2,8 +2,10 @@
 //
 // Validates the caller's SoA snapshot, derives the index structures the kernels need (queue
 // children CSR, jobs grouped by leaf queue in JobOrderFn order, tasks per podset in TaskOrderFn
-// order, name-rank inverse), stages everything through one pinned buffer into HBM, runs the
-// open-session kernels and the persistent action kernel, and copies results back.
+// order, name-rank inverse), stages everything through one pinned buffer into HBM (or, for a resident
+// snapshot, refreshes the per-cycle columns only), runs the open-session kernels, drives the sweep
+// kernels of an action from the host sequencer (one k_record launch per decision record; or the
+// persistent k_action kernel), and copies results back.
 //
 // There is NO CPU fallback: without a usable CUDA device kai_engine_create fails.
 #include <algorithm>
@@ -812,7 +814,7 @@ int kai_engine_load_snapshot(kai_engine *e, const kai_snapshot *s) {
   e->smem_bytes = std::max(tile_bytes, hot_in_smem ? hot : (size_t)0);
   e->ops_cap = ops_cap;
   e->visits_cap = std::max(16, 2 * J + T + 16);
-  {  // launch transport: scanners = CTAs of k_record; the last CTA merges scanners x kTopM candidates (<= kMergeCap)
+  {  // launch transport: scanners = CTAs of k_record; k_merge sorts scanners x kTopM candidates (<= kMergeThreads)
     int lg = 1;
     while (lg * 2 <= std::min(2 * e->num_sms, kMergeThreads / kTopM)) lg *= 2;  // 256 on B200: a power of two keeps the merge sort full
     if (const char *g = getenv("KAI_LAUNCH_GRID")) {

@@ -1,10 +1,13 @@
 // kai_host_seq.cuh — host backend of the sequencer (host-sequenced mode).
 //
-// The sequencer source (kai_seq.cuh) is compiled for the host as well.  In this mode a CPU thread of
-// libkaigpu.so runs it against a host mirror of the session state while the GPU runs k_action in
-// "scan server" form: CTA 0 relays the decision records the host writes into pinned mapped memory to the
-// scanners' device-side record buffer, the scanners keep their node tiles in shared memory and answer
-// every record with one tagged 128-bit candidate written straight into pinned host memory.
+// The sequencer source (kai_seq.cuh) is compiled for the host as well.  A CPU thread of libkaigpu.so runs it against a
+// host mirror of the session state and sends the GPU one decision record per node-table sweep:
+//   * launch transport (default): publish() = one k_record launch carrying the record in its kernel parameters; list
+//     answers come back as ONE merged, cut and sorted list per GPU (k_merge_cluster), single-row / min-max answers as one
+//     line reduced by the last CTA; the host waits on a sequence tag in pinned host memory;
+//   * persistent transport: the GPU runs k_action as a "scan server": CTA 0 relays the records the host writes into pinned
+//     mapped memory to the scanners' device-side record buffer, the scanners keep their node tiles in shared memory and
+//     answer every record with tagged 128-bit words written straight into pinned host memory.
 //
 // Why: measured on B200 (profiles/microbench, profiles/r01_sequencer_modes.md) one GPU lane needs ~20k
 // cycles (10 us) of dependent L1/L2/shared-memory latencies per job for the pointer-chasing part of the
